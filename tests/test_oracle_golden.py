@@ -1,0 +1,128 @@
+"""Pins oracle/xggm_oracle.py to the reference: every fixture under tests/golden was
+produced by oracle/make_golden.py executing the unmodified reference modules."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2, rel_max
+from oracle import xggm_oracle as O
+
+TOL = 2e-5  # fp32 oracle vs fp32 reference, different association order only
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def _check_param_grads(gold, params, tol):
+    seen = 0
+    for name, v in params.items():
+        g = v.grad if v.grad is not None else torch.zeros_like(v)
+        if "g/" + name in gold:
+            ref = gold["g/" + name]
+            if np.abs(ref).max() == 0:
+                assert float(g.abs().max()) == 0.0, name
+            else:
+                assert rel_l2(g, ref) < tol, name
+            seen += 1
+        elif "gn/" + name in gold:
+            nrm, sm = gold["gn/" + name]
+            if nrm == 0:
+                assert float(g.abs().max()) == 0.0, name
+            else:
+                assert abs(float(g.double().norm()) - nrm) / nrm < tol, name
+                assert rel_l2(g.reshape(-1)[:16], gold["gh/" + name]) < 50 * tol, name
+            seen += 1
+    assert seen == sum(1 for k in gold if k.startswith(("g/", "gn/")))
+
+
+GEN_CASES = [("gcn_h64_train", "GCN"), ("gcn_h64_eval", "GCN"), ("gcn_h768_train", "GCN"),
+             ("gin_h64_train", "GIN"), ("gin_h768_train", "GIN"),
+             ("gat_h64_train", "GAT"), ("gat_h768_eval", "GAT")]
+
+
+@pytest.mark.parametrize("name,gnn", GEN_CASES)
+def test_generator_matches_reference(name, gnn):
+    gold = load_golden(name)
+    seed, hidden, B, n_layers, training = [int(v) for v in gold["meta"]]
+    p = O.make_params(seed, gnn, hidden, n_layers, 36, heads=False)
+    for v in p.values():
+        v.requires_grad_(True)
+    visn, _, _ = O.make_inputs(seed + 1, B, 36, hidden)
+    nh = {"GCN": 3, "GIN": 2, "GAT": 1}[gnn]
+    keeps = O.make_keeps(seed + 3, n_layers, nh, (B, 36, hidden)) if training else None
+    if gnn == "GAT" and keeps is not None:
+        keeps = [k[0] for k in keeps]
+    x = visn.clone().requires_grad_(True)
+    adj = _t(gold["adj_in"]).clone().requires_grad_(True)
+    xo, ao = O.GENERATORS[gnn](x, adj, p, n_layers, keeps, pre="generator.")
+    assert rel_l2(xo, gold["x_out"]) < TOL
+    assert rel_l2(ao, gold["adj_out"]) < TOL
+    # bit-exact structure: zero diagonal
+    assert float(torch.diagonal(ao, dim1=1, dim2=2).abs().max()) == 0.0
+    ((xo * _t(gold["cx"])).sum() + (ao * _t(gold["ca"])).sum()).backward()
+    assert rel_l2(x.grad, gold["gx"]) < 5 * TOL
+    ga = adj.grad if adj.grad is not None else torch.zeros_like(adj)
+    if np.abs(gold["gadj"]).max() == 0:
+        assert float(ga.abs().max()) == 0.0
+    else:
+        assert rel_l2(ga, gold["gadj"]) < 5 * TOL
+    _check_param_grads(gold, p, 10 * TOL)
+
+
+BRANCH_CASES = [("branch_relation_gcn_h64", "relation", "GCN"),
+                ("branch_node_gcn_h64", "node", "GCN"),
+                ("branch_node_gcn_h768", "node", "GCN"),
+                ("branch_relation_gin_h64", "relation", "GIN")]
+
+
+@pytest.mark.parametrize("name,which,gnn", BRANCH_CASES)
+def test_branch_matches_reference(name, which, gnn):
+    gold = load_golden(name)
+    seed, hidden, B, n_layers, _ = [int(v) for v in gold["meta"]]
+    sigma, A = float(gold["sigma"]), int(gold["num_answers"])
+    p = O.make_params(seed, gnn, hidden, n_layers, 36, heads=True)
+    for v in p.values():
+        v.requires_grad_(True)
+    visn, xp, adj_true = O.make_inputs(seed + 1, B, 36, hidden)
+    nh = {"GCN": 3, "GIN": 2}[gnn]
+    keeps = O.make_keeps(seed + 3, n_layers, nh, (B, 36, hidden))
+    xp = xp.clone().requires_grad_(True)
+    visn = visn.clone().requires_grad_(True)
+    fn = O.relation_branch if which == "relation" else O.node_branch
+    x_gen, loss_sm, nodes, adj_g = fn(xp, visn, adj_true, p, sigma, _t(gold["randn"]), keeps, A,
+                                      gnn=gnn, n_layers=n_layers)
+    assert rel_l2(x_gen, gold["x_gen"]) < TOL
+    assert rel_l2(nodes, gold["nodes"]) < TOL
+    assert rel_l2(adj_g, gold["adj_gen"]) < TOL
+    assert abs(float(loss_sm) - float(gold["loss_sm"])) / abs(float(gold["loss_sm"])) < TOL
+    ((x_gen * _t(gold["c"])).sum() + loss_sm).backward()
+    assert rel_l2(xp.grad, gold["gxp"]) < 10 * TOL
+    gv = visn.grad if visn.grad is not None else torch.zeros_like(visn)
+    assert rel_l2(gv, gold["gvisn"]) < 10 * TOL
+    _check_param_grads(gold, p, 20 * TOL)
+
+
+def test_glue_matches_reference():
+    g = load_golden("glue")
+    a, b, f, h = (_t(g[k]) for k in "abfh")
+    an, at = O.edge_noise(a, 0.7, _t(g["rn_a"]))
+    fn, ft = O.feat_noise(f, 0.7, _t(g["rn_f"]))
+    # noise arithmetic is elementwise in the same order: bit-exact
+    assert torch.equal(an, _t(g["edge_noisy"])) and torch.equal(at, _t(g["edge_target"]))
+    assert torch.equal(fn, _t(g["feat_noisy"])) and torch.equal(ft, _t(g["feat_target"]))
+    assert torch.equal(O.strip_diag(a), _t(g["strip"]))
+    assert torch.equal(O.triu_scatter(_t(g["v"]), 36), _t(g["scatter"]))
+    assert abs(float(O.score_matching_loss(a, b, 0.7)) - float(g["sm_adj"])) < 1e-6 * abs(float(g["sm_adj"]))
+    assert abs(float(O.score_matching_loss(f, h, 0.7)) - float(g["sm_feat"])) < 1e-6 * abs(float(g["sm_feat"]))
+    assert abs(float(O.sym_kl_loss(a, b)) - float(g["kl_adj"])) < 1e-5 * abs(float(g["kl_adj"]))
+    assert abs(float(O.sym_kl_loss(f, h)) - float(g["kl_feat"])) < 1e-5 * abs(float(g["kl_feat"]))
+
+
+def test_triu_index_closed_form():
+    n = 36
+    idx = O.triu_index_map(n)
+    for i in range(n):
+        for j in range(i + 1, n):
+            assert int(idx[i, j]) == i * (2 * n - i - 1) // 2 + (j - i - 1)
+    assert int(idx.max()) == n * (n - 1) // 2 - 1
