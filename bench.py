@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""Benchmark of the X-GGM graph-generative block (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one pass of the hot path over one batch: the GGM node-generation branch the
+shipped VQA-CP v2 recipe always takes (--delta 0, script/vqacpv2.sh:22 of the reference):
+strip_diag(adj_true) -> node_fc(x) (+36-fold broadcast) -> Gaussian feature noise ->
+GCNGenerator(L=2) -> symmetric-KL + score-matching losses -> fusion_fc read-out, forward AND
+backward down to every parameter gradient and the gradients of the LXMERT outputs that feed
+the block.  The LXMERT encoder / answer head that surround the block are outside the hot path
+(SURVEY.md section 8); their place is taken by resident inputs and a fixed cotangent on x_gen.
+
+Per-GPU batch B=256 (BASELINE configs[1]), N=36, H=768, fp32.  N>1 ranks = data parallel
+(weak scaling): each rank runs its own B=256 shard and the block's gradients are summed with
+one NCCL all-reduce per step.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port of the
+reference path on the host cores instead (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_GPU, N_NODES, HID, N_LAYERS, SIGMA, NUM_ANS, GNN = 256, 36, 768, 2, 1.0, 2274, "GCN"
+CPU_SAMPLE_B = 32
+METRIC = "xggm_graph_block_train_samples_per_sec"
+
+
+def algorithmic_flops_per_sample(N=N_NODES, H=HID, L=N_LAYERS):
+    """F_fwd = L(5*2NH^2 + 3*2N^2H); fwd+bwd = 3x."""
+    return 3 * L * (5 * 2 * N * H * H + 3 * 2 * N * N * H)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------- CPU baseline
+def cpu_reference_steps(steps, warmup, threads, B=CPU_SAMPLE_B):
+    """The reference's PyTorch CPU path for the same step, restated in oracle/ (the reference tree
+    does not exist on the GPU box).  Returns seconds per step (median)."""
+    from oracle import xggm_oracle as O
+    torch.set_num_threads(threads)
+    p = O.make_params(9595, GNN, HID, N_LAYERS, N_NODES, heads=True)
+    for v in p.values():
+        v.requires_grad_(True)
+    visn, xp, adj_true = O.make_inputs(9596, B, N_NODES, HID)
+    g = torch.Generator().manual_seed(1)
+    c = torch.randn(B, HID, generator=g)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        x = xp.clone().requires_grad_(True)
+        feat = visn.clone().requires_grad_(True)
+        keeps = [[(torch.rand(B, N_NODES, HID) >= 0.5) for _ in range(3)] for _ in range(N_LAYERS)]  # F.dropout's bernoulli
+        randn = torch.randn(B, N_NODES, HID)
+        x_gen, loss_sm, _, _ = O.node_branch(x, feat, adj_true, p, SIGMA, randn, keeps, NUM_ANS, GNN, N_LAYERS)
+        ((x_gen * c).sum() + 1.1 * loss_sm).backward()
+        for v in p.values():
+            v.grad = None
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    times.sort()
+    return times[len(times) // 2]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sec = cpu_reference_steps(args.steps, args.warmup, threads)
+    val = CPU_SAMPLE_B / sec
+    sample = f"B={CPU_SAMPLE_B} graphs per step (bounded sample of the B={B_PER_GPU} workload), {args.steps} steps"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": f"cfg2 graph block: VQA-CP v2 GGM node branch (delta=0), GCNGenerator L={N_LAYERS}, fwd+bwd, "
+                        f"B={B_PER_GPU}/GPU, N={N_NODES}, H={HID}, sigma={SIGMA}, A={NUM_ANS}, fp32",
+            "global_batch": B_PER_GPU * n_gpus, "per_gpu_batch": B_PER_GPU, "parallelism": f"dp{n_gpus}",
+            "l2": "flushed between timed steps (256 MiB write, outside the per-step CUDA-event pairs)"}
+
+
+# ---------------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch.distributed as dist
+    import xggm_b200 as X
+    from xggm_b200 import _lib
+    from oracle import xggm_oracle as O  # input factory + cpu_baseline leg only
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(9595)  # reference default seed, src/param.py:49 (same on every rank: same branch, same init)
+
+    B = B_PER_GPU
+    model = X.XGGMHeads(HID, GNN, N_LAYERS, N_NODES).to(dev).train()
+    params = [p for p in model.parameters()]
+    flat_grad = torch.zeros(sum(p.numel() for p in params), device=dev)
+    off = 0
+    for p in params:  # .grad are views of one flat buffer -> one all-reduce, no staging copy
+        p.grad = flat_grad[off:off + p.numel()].view_as(p)
+        off += p.numel()
+
+    visn_h, xp_h, adj_h = (t.pin_memory() for t in O.make_inputs(9596 + rank, B, N_NODES, HID))
+    cot_h = torch.randn(B, HID, generator=torch.Generator().manual_seed(2 + rank)).pin_memory()
+    visn_d, xp_d, adj_d, cot_d = (t.to(dev) for t in (visn_h, xp_h, adj_h, cot_h))
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step(visn, xp, adj):
+        flat_grad.zero_()
+        x = xp.requires_grad_(True)
+        feat = visn.requires_grad_(True)
+        x_gen, loss_sm, _, _ = model.node_step(x, feat, adj, SIGMA, NUM_ANS)
+        loss = (x_gen * cot_d).sum() + 1.1 * loss_sm
+        loss.backward()
+        if world > 1:
+            dist.all_reduce(flat_grad)
+        x.grad = feat.grad = None
+        return loss_sm
+
+    def resident_step():
+        return step(visn_d.detach(), xp_d.detach(), adj_d)
+
+    def e2e_step():
+        v = visn_h.to(dev, non_blocking=True)
+        x = xp_h.to(dev, non_blocking=True)
+        a = adj_h.to(dev, non_blocking=True)
+        l = step(v, x, a)
+        loss_host.copy_(l.detach().reshape(1), non_blocking=True)
+
+    def timed(fn, k):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        for s, e in evs:
+            flush.fill_(1.0)  # L2 flush, outside the event pair
+            s.record()
+            fn()
+            e.record()
+        torch.cuda.synchronize()
+        ms = sum(s.elapsed_time(e) for s, e in evs)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+            dist.barrier()
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        resident_step()
+        e2e_step()
+    torch.cuda.synchronize()
+
+    with ClockSampler(local) as clk:
+        l0 = _lib.kernel_launches()
+        ms_res = timed(resident_step, args.steps)
+        launches = _lib.kernel_launches() - l0
+        ms_e2e = timed(e2e_step, args.steps)
+    clocks = clk.summary()
+
+    # per-launch timing of the dominant kernel (projection GEMM), CUDA events on its own stream
+    _lib.gemm_profile(True)
+    prof_steps = min(args.steps, 3)
+    for _ in range(prof_steps):
+        flush.fill_(1.0)
+        resident_step()
+    torch.cuda.synchronize()
+    g_ms, g_n, g_flops = _lib.gemm_profile()
+    _lib.gemm_profile(False)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    ms_step = ms_res / args.steps
+    value = B * world / (ms_step * 1e-3)
+    e2e_val = B * world / (ms_e2e / args.steps * 1e-3)
+    flops_step = algorithmic_flops_per_sample() * B
+    gemm_tflops = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    peak = peaks["bf16_tflops"]
+    h2d = sum(t.numel() * 4 for t in (visn_h, xp_h, adj_h))
+    threads = os.cpu_count() or 1
+    cpu_sec = cpu_reference_steps(5, 2, threads)
+    line = {
+        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+        "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "gemm_simt_kernel (768x768 node projections, fp32 SIMT engine)",
+                     "achieved": gemm_tflops, "peak": peak, "unit": "TFLOP/s", "frac": gemm_tflops / peak,
+                     "traffic": None, "peak_source": f"{peaks['source']} bf16 burst (MEASURED_PEAKS.json)",
+                     "launches_timed": g_n, "avg_launch_us": (g_ms / g_n * 1e3) if g_n else None,
+                     "gemm_share_of_step": (g_ms / prof_steps) / ms_step if ms_step > 0 else None},
+        "block_roofline": {"algorithmic_gflop_per_step": flops_step / 1e9,
+                           "achieved_tflops": flops_step / (ms_step * 1e-3) / 1e12,
+                           "frac_of_bf16_peak": flops_step / (ms_step * 1e-3) / 1e12 / peak,
+                           "t_roof_us": flops_step / (peak * 1e12) * 1e6},
+        "cpu_baseline": {"value": CPU_SAMPLE_B / cpu_sec, "unit": "samples/s", "cores": threads, "kind": "port",
+                         "sample": f"B={CPU_SAMPLE_B} graphs/step, 5 timed steps after 2 warm-up, median"},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="xggm_b200", choices=["xggm_b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,217 @@
+/* xggm_b200 -- C ABI of the B200-native X-GGM graph block (sm_100a).
+ *
+ * The reference (jingjing12110/X-GGM) is pure PyTorch and has no FFI; this header
+ * is the new native surface its nn.Module boundary binds to (INTEGRATION.md shows
+ * the ctypes stub).  Every entry point cites the reference lines it replaces
+ * (paths relative to the reference root; "ggm.py" =
+ * src/module/graph_generative_modeling.py).
+ *
+ * Conventions
+ *  - All tensors are dense, row-major, contiguous fp32 DEVICE buffers owned by the
+ *    caller (PyTorch allocates them); the library never allocates, frees or keeps
+ *    a pointer after the call returns.  "?" marks a pointer that may be NULL.
+ *  - B graphs, N nodes per graph (36 for obj36), H feature width (768), M = B*N rows.
+ *  - Every call enqueues on the caller's stream and returns without synchronising.
+ *  - Return value: XGGM_OK or a negative XGGM_ERR_* code.  Nothing throws.
+ *  - Stateless and re-entrant; one CUDA context per process (one process per GPU).
+ *  - No CPU fallback: xggm_device_check() fails on anything but compute
+ *    capability 10.x and the kernels exist only as sm_100a SASS.
+ */
+#ifndef XGGM_B200_H
+#define XGGM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XGGM_ABI_VERSION 1
+
+#define XGGM_OK 0
+#define XGGM_ERR_ARG (-1)         /* bad shape / NULL pointer / unsupported size */
+#define XGGM_ERR_CUDA (-2)        /* CUDA runtime error; see xggm_last_cuda_error() */
+#define XGGM_ERR_ARCH (-3)        /* device is not compute capability 10.x */
+#define XGGM_ERR_UNSUPPORTED (-4) /* valid request this build does not implement */
+
+typedef void* xggm_stream_t; /* a cudaStream_t */
+
+int xggm_abi_version(void);
+const char* xggm_strerror(int code);
+const char* xggm_last_cuda_error(void);
+/* Number of CUDA kernels this library has launched in this process (bench accounting). */
+unsigned long long xggm_launch_count(void);
+/* Bench instrumentation: while enabled, every projection-GEMM launch is bracketed by a
+ * CUDA-event pair on its stream; xggm_prof_read sums their durations (ms), counts them and
+ * sums their algorithmic FLOPs (2*M*N*K).  Enabling (or disabling) clears the records. */
+int xggm_prof_enable(int on);
+int xggm_prof_read(double* total_ms, long long* launches, double* flops);
+/* The library links its own (static) CUDA runtime: make `device` current for the calling
+ * thread before enqueueing work on one of its streams (cheap; call it per entry). */
+int xggm_set_device(int device);
+/* XGGM_OK iff `device` is a compute-capability-10.x GPU (B200). */
+int xggm_device_check(int device);
+
+/* ------------------------------------------------------------------------- *
+ * Dense node projections  (nn.Linear: src/module/gcn.py:13,44; gin.py:14)
+ * ------------------------------------------------------------------------- */
+/* out[M,N] = a[M,K] w[N,K]^T + bias[N]? + resid[M,N]? */
+int xggm_linear_fwd(const float* a, const float* w, const float* bias, const float* resid,
+                    float* out, int M, int N, int K, xggm_stream_t s);
+/* ga[M,K] (+)= g[M,N] w[N,K]   (accumulate != 0 adds into ga) */
+int xggm_linear_bwd_input(const float* g, const float* w, float* ga, int M, int N, int K,
+                          int accumulate, xggm_stream_t s);
+/* gw[N,K] = g[M,N]^T a[M,K];  gbias[N]? = column sums of g.  Overwrites. */
+int xggm_linear_bwd_weight(const float* g, const float* a, float* gw, float* gbias,
+                           int M, int N, int K, xggm_stream_t s);
+
+/* ------------------------------------------------------------------------- *
+ * Adjacency-weighted message passing
+ *   GCNConv  torch.bmm(adj, x)                    src/module/gcn.py:28
+ *   GINConv  X + (1 + eps) * A @ X                src/module/gin.py:32
+ * out[b] = self_w * x[b] + alpha * adj[b] @ x[b],  alpha = alpha0 + (*alpha_dev if non-NULL)
+ * ------------------------------------------------------------------------- */
+int xggm_adj_apply_fwd(const float* adj, const float* x, float* out, int B, int N, int H,
+                       float alpha0, const float* alpha_dev, float self_w, xggm_stream_t s);
+/* gx (+)= self_w*gout + alpha * adj^T @ gout ; gadj_raw? = gout @ x^T (NOT scaled by alpha;
+ * the caller scales, and d alpha = <gadj_raw, adj>). */
+int xggm_adj_apply_bwd(const float* adj, const float* x, const float* gout, float* gx,
+                       float* gadj_raw, int B, int N, int H, float alpha0,
+                       const float* alpha_dev, float self_w, int accumulate_gx, xggm_stream_t s);
+
+/* ------------------------------------------------------------------------- *
+ * Row normalisation / activations
+ * ------------------------------------------------------------------------- */
+/* nn.LayerNorm(H) of src/module/gcn.py:14,29: h = xhat*gamma+beta; saves xhat and rstd. */
+int xggm_layernorm_fwd(const float* u, const float* gamma, const float* beta, float* h,
+                       float* xhat, float* rstd, int M, int H, float eps, xggm_stream_t s);
+/* gu = LN backward; ggamma/gbeta are ACCUMULATED into (caller zeroes them). */
+int xggm_layernorm_bwd(const float* gh, const float* xhat, const float* rstd, const float* gamma,
+                       float* gu, float* ggamma, float* gbeta, int M, int H, xggm_stream_t s);
+/* Jump-knowledge head tail  F.dropout(LN(GeLU(z)), p)  src/module/gcn.py:44-47,72-76
+ * (GeLU = exact erf, src/lxrt/modeling.py:116-124).
+ * out (=|+=) keep*scale*LN(gelu(z)); keep? is a uint8 mask (1 = keep), scale = 1/(1-p).
+ * Saves per-row mean and rstd of gelu(z). */
+int xggm_gelu_ln_drop_fwd(const float* z, const float* gamma, const float* beta,
+                          const uint8_t* keep, float scale, float* out, float* mean, float* rstd,
+                          int M, int H, float eps, int accumulate, xggm_stream_t s);
+/* gz = backward of the above w.r.t. z; ggamma/gbeta ACCUMULATED. */
+int xggm_gelu_ln_drop_bwd(const float* gout, const float* z, const float* mean, const float* rstd,
+                          const float* gamma, const uint8_t* keep, float scale, float* gz,
+                          float* ggamma, float* gbeta, int M, int H, xggm_stream_t s);
+
+/* ------------------------------------------------------------------------- *
+ * Adjacency regeneration   ggm.py:225-228 (GCN), :188-191 (GIN), :261-264 (GAT),
+ * :124-126 (EdgeGenerator, squash = 0)
+ *   S = x x^T ; m_i = max_k S[k,i] ; adj[i,j] = sigmoid(S[i,j]/m_i) (i != j), 0 on the diagonal
+ * Saves S[B,N,N] and the arg-max row index amax[B,N] (first index on ties, as torch.max).
+ * ------------------------------------------------------------------------- */
+int xggm_adj_regen_fwd(const float* x, float* adj_out, float* S, int32_t* amax, int B, int N,
+                       int H, int squash, xggm_stream_t s);
+/* gx (+)= (dS + dS^T) x.  `work` is a [B,N,N] scratch buffer. */
+int xggm_adj_regen_bwd(const float* gadj, const float* x, const float* S, const int32_t* amax,
+                       float* gx, float* work, int B, int N, int H, int squash,
+                       int accumulate_gx, xggm_stream_t s);
+
+/* ------------------------------------------------------------------------- *
+ * Whole GCN / GIN layers (conv chain + jump-knowledge read-out)
+ *   GCN.forward  src/module/gcn.py:64-77   (GCNConv :22-29)
+ *   GIN.forward  src/module/gin.py:68-87   (GINConv :21-34)
+ * Parameter tables are HOST arrays of DEVICE pointers:
+ *   GCN conv k : conv_params[3k+0..2] = ctx_layer.weight[H,H], layer_norm.weight[H], layer_norm.bias[H]
+ *   GIN conv k : conv_params[5k+0..4] = eps[1], linear.0.weight[H,H], linear.0.bias[H],
+ *                                        linear.2.weight[H], linear.2.bias[H]
+ *   head j     : head_params[4j+0..3] = 0.weight[H,H], 0.bias[H], 2.weight[H], 2.bias[H]
+ *   keeps[j]?  : uint8 [M,H] keep-mask of head j (NULL table => eval mode, no dropout)
+ * `saved` (xggm_gnn_saved_floats floats) carries activations to the backward call;
+ * `work` (xggm_gnn_work_floats floats) is scratch.  kind: 0 = GCN, 1 = GIN.
+ * ------------------------------------------------------------------------- */
+#define XGGM_KIND_GCN 0
+#define XGGM_KIND_GIN 1
+long long xggm_gnn_saved_floats(int kind, int B, int N, int H, int n_convs);
+long long xggm_gnn_work_floats(int kind, int B, int N, int H, int n_convs);
+int xggm_gnn_fwd(int kind, const float* x, const float* adj, const float* const* conv_params,
+                 const float* const* head_params, const uint8_t* const* keeps, float drop_p,
+                 float* out, float* saved, float* work, int B, int N, int H, int n_convs,
+                 xggm_stream_t s);
+/* Gradient tables mirror the parameter tables (same order); every gradient buffer is
+ * OVERWRITTEN.  gadj[B,N,N] and gx[B,N,H] are overwritten. */
+int xggm_gnn_bwd(int kind, const float* gout, const float* x, const float* adj,
+                 const float* const* conv_params, const float* const* head_params,
+                 const uint8_t* const* keeps, float drop_p, const float* saved, float* work,
+                 float* gx, float* gadj, float* const* conv_grads, float* const* head_grads,
+                 int B, int N, int H, int n_convs, xggm_stream_t s);
+
+/* ------------------------------------------------------------------------- *
+ * GAT attention  src/module/gat.py:25-49 (after h = linear_layer(x), which is
+ * xggm_linear_fwd).  e_ij = LeakyReLU_alpha(a1.h_i + a2.h_j); masked_fill(adj==0,-9e15);
+ * row softmax; out = elu(att @ h) (apply_elu = concat flag, gat.py:46-49).
+ * a = attn_layer.weight[2H].  Saves att[B,N,N] and pre-activation pre[B,N,H] = att @ h.
+ * ------------------------------------------------------------------------- */
+int xggm_gat_attn_fwd(const float* h, const float* a, const float* adj, float* out, float* att,
+                      float* pre, int B, int N, int H, float alpha, int apply_elu, xggm_stream_t s);
+/* gh overwritten; ga[2H] ACCUMULATED (caller zeroes); work = B*N*H + B*N*N floats scratch. */
+int xggm_gat_attn_bwd(const float* gout, const float* h, const float* a, const float* adj,
+                      const float* att, const float* pre, float* gh, float* ga, float* work, int B,
+                      int N, int H, float alpha, int apply_elu, xggm_stream_t s);
+
+/* ------------------------------------------------------------------------- *
+ * Trainer glue  (src/vqa/vqacpv2.py, src/gqa/gqa_ood.py, src/module/graph_utils.py)
+ * ------------------------------------------------------------------------- */
+/* a.triu(1)+a.tril(-1)                                   src/vqa/vqacpv2.py:188 */
+int xggm_strip_diag(const float* a, float* out, int B, int N, xggm_stream_t s);
+/* v[B,N(N-1)/2] -> symmetric adj[B,N,N], zero diagonal    src/vqa/vqacpv2.py:195-199 */
+int xggm_triu_scatter_fwd(const float* v, float* adj, int B, int N, xggm_stream_t s);
+/* gv[b,k] = gadj[b,i,j] + gadj[b,j,i] */
+int xggm_triu_scatter_bwd(const float* gadj, float* gv, int B, int N, xggm_stream_t s);
+/* add_edge_noise_v2                                       src/module/graph_utils.py:162-168
+ * randn = torch.randn_like(adj) drawn by the caller (keeps torch's RNG stream).
+ * target = -n / (float)(sigma*sigma), the reference's `-noise / (sigma ** 2)`. */
+int xggm_edge_noise(const float* adj, const float* randn, double sigma, float* noisy,
+                    float* target, int B, int N, xggm_stream_t s);
+/* add_feature_noise_v2                                    src/module/graph_utils.py:144-149
+ * f is [B,N,H], or [B,H] broadcast over the N nodes when f_is_broadcast != 0
+ * (node_fc on 36 identical rows, src/vqa/vqacpv2.py:228-229). */
+int xggm_feat_noise(const float* f, const float* randn, double sigma, float* noisy, float* target,
+                    int B, int N, int H, int f_is_broadcast, xggm_stream_t s);
+/* out[B,H] = sum_n g[B,n,H]  (backward of the broadcast above) */
+int xggm_sum_nodes(const float* g, float* out, int B, int N, int H, xggm_stream_t s);
+/* loss_func                                               src/vqa/vqacpv2.py:48-51
+ * loss[0] = 0.5 sigma^2 / n_elem * sum (score-target)^2 ; n_elem = B*R*C of the [B,R,C] inputs
+ * (sum over the last two dims, mean over B, divided by R*C). */
+int xggm_score_mse_fwd(const float* score, const float* target, double sigma, float* loss,
+                       long long n_elem, xggm_stream_t s);
+/* gscore = gloss[0] * sigma^2/n_elem * (score-target) */
+int xggm_score_mse_bwd(const float* score, const float* target, const float* gloss, double sigma,
+                       float* gscore, long long n_elem, xggm_stream_t s);
+/* compute_kl_loss                                         src/vqa/vqacpv2.py:54-61
+ * x,y are [R,C], softmax over C; loss[0] = mean over R*C. */
+int xggm_sym_kl_fwd(const float* x, const float* y, float* loss, int R, int C, xggm_stream_t s);
+/* gx?, gy? overwritten with d loss/dx * gloss[0], d loss/dy * gloss[0]. */
+int xggm_sym_kl_bwd(const float* x, const float* y, const float* gloss, float* gx, float* gy,
+                    int R, int C, xggm_stream_t s);
+/* cat[x, tanh(mean_n nodes)]                              src/vqa/vqacpv2.py:216-218
+ * out[B,2H] = [xp[B,H] | tanh(mean_n nodes[B,N,H])] */
+int xggm_fuse_readout_fwd(const float* xp, const float* nodes, float* out, int B, int N, int H,
+                          xggm_stream_t s);
+/* gxp[B,H] = gout[:, :H];  gnodes[B,N,H] (+)= gout[:, H:] * (1-t^2)/N with t = out[:, H:] */
+int xggm_fuse_readout_bwd(const float* gout, const float* out, float* gxp, float* gnodes, int B,
+                          int N, int H, int accumulate_gnodes, xggm_stream_t s);
+/* elementwise sigmoid (encoder_adj tail, src/vqa/vqacpv2_model.py:91-94) */
+int xggm_sigmoid_fwd(const float* x, float* y, long long n, xggm_stream_t s);
+int xggm_sigmoid_bwd(const float* gy, const float* y, float* gx, long long n, xggm_stream_t s);
+/* GeLU (exact erf), src/lxrt/modeling.py:116-140 */
+int xggm_gelu_fwd(const float* x, float* y, long long n, xggm_stream_t s);
+int xggm_gelu_bwd(const float* gy, const float* x, float* gx, long long n, xggm_stream_t s);
+/* inverted dropout with an explicit mask, y = keep ? x*scale : 0 (GAT input dropout,
+ * src/module/gat.py:73); the same call is its backward. */
+int xggm_mask_scale(const float* x, const uint8_t* keep, float scale, float* y, long long n,
+                    xggm_stream_t s);
+/* Philox keep-mask (1 = keep with probability 1-p), counter = element index. */
+int xggm_keep_mask(uint8_t* keep, long long n, float p, uint64_t seed, uint64_t stream_id,
+                   xggm_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XGGM_B200_H */

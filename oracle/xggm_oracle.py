@@ -36,16 +36,13 @@ def gelu_erf(t):
 
 
 def row_norm(t, gamma, beta, eps=LN_EPS):
-    """LayerNorm over the last axis (biased variance).  nn.LayerNorm semantics."""
-    mu = t.mean(dim=-1, keepdim=True)
-    var = ((t - mu) ** 2).mean(dim=-1, keepdim=True)
-    return (t - mu) / torch.sqrt(var + eps) * gamma + beta
+    """LayerNorm over the last axis (biased variance): nn.LayerNorm, as the reference uses."""
+    return torch.nn.functional.layer_norm(t, (t.shape[-1],), gamma, beta, eps)
 
 
 def affine(t, weight, bias=None):
     """y = t W^T (+ b): nn.Linear."""
-    y = t @ weight.transpose(-1, -2)
-    return y if bias is None else y + bias
+    return torch.nn.functional.linear(t, weight, bias)
 
 
 def keep_scale(t, keep, p):

@@ -1,0 +1,385 @@
+"""GPU parity: the CUDA path (through the C ABI / nn.Module boundary) against the CPU oracle
+and the committed golden fixtures.  fp32 tolerance 1e-4 relative (BASELINE.json north_star);
+masks, index maps, arg-max indices and noise arithmetic are bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2, rel_max
+from oracle import xggm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def _close(a, b, tol=TOL, name=""):
+    b = torch.as_tensor(b)
+    if float(b.abs().max()) == 0.0:
+        assert float(a.detach().abs().max().cpu()) == 0.0, name
+        return
+    e2, em = rel_l2(a.detach().cpu(), b), rel_max(a.detach().cpu(), b)
+    assert e2 < tol and em < 5 * tol, f"{name}: rel_l2={e2:.3e} rel_max={em:.3e}"
+
+
+def _load_params(module, params, prefix=""):
+    sd = {k[len(prefix):]: v for k, v in params.items() if k.startswith(prefix)}
+    module.load_state_dict(sd, strict=True)
+    return module
+
+
+# --------------------------------------------------------------------------- primitives
+@pytest.mark.parametrize("M,N,K", [(72, 768, 768), (3, 630, 768), (130, 64, 96), (1, 768, 1536), (257, 10, 7)])
+def test_linear_fwd_bwd(M, N, K):
+    import xggm_b200.functional as XF
+    g = torch.Generator().manual_seed(M * 7 + N)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    r = torch.randn(M, N, generator=g)
+    c = torch.randn(M, N, generator=g)
+    ad, wd, bd, rd = (t.clone().to(dev()).requires_grad_(True) for t in (a, w, b, r))
+    out = XF.linear(ad, wd, bd, rd)
+    (out * c.to(dev())).sum().backward()
+    a64, w64, b64, r64 = (t.double().requires_grad_(True) for t in (a, w, b, r))
+    ref = a64 @ w64.T + b64 + r64
+    (ref * c.double()).sum().backward()
+    _close(out, ref, name="out")
+    _close(ad.grad, a64.grad, name="ga")
+    _close(wd.grad, w64.grad, name="gw")
+    _close(bd.grad, b64.grad, name="gb")
+    _close(rd.grad, r64.grad, name="gr")
+
+
+@pytest.mark.parametrize("B,N,H", [(3, 36, 768), (2, 5, 64), (1, 64, 96), (2, 100, 40)])
+def test_adj_apply_and_regen(B, N, H):
+    import xggm_b200.functional as XF
+    g = torch.Generator().manual_seed(B * 100 + N)
+    x = torch.randn(B, N, H, generator=g)
+    adj = torch.randn(B, N, N, generator=g)
+    eps = torch.tensor([0.25])
+    cx = torch.randn(B, N, H, generator=g)
+    ca = torch.randn(B, N, N, generator=g)
+    xd, ad, ed = (t.clone().to(dev()).requires_grad_(True) for t in (x, adj, eps))
+    out = XF.adj_apply(ad, xd, 1.0, ed, 1.0)
+    (out * cx.to(dev())).sum().backward()
+    x64, a64, e64 = (t.double().requires_grad_(True) for t in (x, adj, eps))
+    ref = x64 + torch.bmm((1 + e64) * a64, x64)
+    (ref * cx.double()).sum().backward()
+    _close(out, ref, name="adj_apply")
+    _close(xd.grad, x64.grad, name="gx")
+    _close(ad.grad, a64.grad, name="gadj")
+    _close(ed.grad, e64.grad, name="geps")
+    # regeneration, both variants
+    for squash in (True, False):
+        xd2 = x.clone().to(dev()).requires_grad_(True)
+        adj_g, amax = XF.adj_regen(xd2, squash, return_argmax=True)
+        (adj_g * ca.to(dev())).sum().backward()
+        x2 = x.double().requires_grad_(True)
+        ref_g = O.adj_regen(x2, squash)
+        (ref_g * ca.double()).sum().backward()
+        _close(adj_g, ref_g, name="regen")
+        _close(xd2.grad, x2.grad, name="regen gx")
+        assert float(torch.diagonal(adj_g, dim1=1, dim2=2).abs().max()) == 0.0  # bit-exact mask
+        # bit-exact arg-max row per column against fp32 torch on the kernel's own S ordering
+        s32 = torch.bmm(x, x.transpose(1, 2))
+        ref_arg = s32.max(dim=1)[1]
+        s_top2 = s32.topk(2, dim=1)[0]
+        decisive = (s_top2[:, 0] - s_top2[:, 1]) > 1e-4 * s_top2[:, 0].abs()
+        assert torch.equal(amax.cpu().long()[decisive], ref_arg[decisive])
+
+
+def test_regen_symmetry_and_ties():
+    """S is bitwise symmetric (same k-order for (i,j) and (j,i)); ties pick the first row."""
+    import xggm_b200.functional as XF
+    x = torch.randn(4, 36, 768, generator=torch.Generator().manual_seed(5))
+    x[0, 7] = x[0, 3]  # duplicate node: S[3,c] == S[7,c] for every c -> tie between rows 3 and 7
+    x[0, 3] *= 4.0
+    x[0, 7] *= 4.0
+    adj, amax = XF.adj_regen(x.to(dev()), False, return_argmax=True)
+    # squash=False: adj[i,j] = S[i,j]/m_i off-diagonal. Row-scale back and compare transposes.
+    assert torch.equal(amax[0, 3].cpu(), torch.tensor(3, dtype=torch.int32))
+    assert int(amax[0, 7]) == 3  # first index on the exact tie, as torch.max
+    a = adj.cpu()
+    s = torch.bmm(x, x.transpose(1, 2))
+    m = s.max(dim=1)[0]
+    i, j = 2, 9
+    assert abs(float(a[1, i, j] * m[1, i]) - float(a[1, j, i] * m[1, j])) < 1e-3 * abs(float(s[1, i, j])) + 1e-5
+
+
+@pytest.mark.parametrize("M,H", [(72, 768), (5, 64), (33, 1536), (1, 32)])
+def test_rowops(M, H):
+    import xggm_b200.functional as XF
+    g = torch.Generator().manual_seed(M + H)
+    z = torch.randn(M, H, generator=g) * 2
+    gam = 1 + 0.2 * torch.randn(H, generator=g)
+    bet = 0.2 * torch.randn(H, generator=g)
+    keep = (torch.rand(M, H, generator=g) > 0.5).to(torch.uint8)
+    c = torch.randn(M, H, generator=g)
+    # LayerNorm
+    zd, gd, bd = (t.clone().to(dev()).requires_grad_(True) for t in (z, gam, bet))
+    out = XF.layer_norm(zd, gd, bd)
+    (out * c.to(dev())).sum().backward()
+    z64, g64, b64 = (t.double().requires_grad_(True) for t in (z, gam, bet))
+    ref = O.row_norm(z64, g64, b64)
+    (ref * c.double()).sum().backward()
+    for a, b, n in ((out, ref, "ln"), (zd.grad, z64.grad, "gz"), (gd.grad, g64.grad, "ggamma"), (bd.grad, b64.grad, "gbeta")):
+        _close(a, b, name=n)
+    # dropout(LN(GeLU(z)))
+    zd, gd, bd = (t.clone().to(dev()).requires_grad_(True) for t in (z, gam, bet))
+    out = XF.gelu_ln_drop(zd, gd, bd, keep.to(dev()), 0.5)
+    (out * c.to(dev())).sum().backward()
+    z64, g64, b64 = (t.double().requires_grad_(True) for t in (z, gam, bet))
+    ref = O.keep_scale(O.row_norm(O.gelu_erf(z64), g64, b64), keep, 0.5)
+    (ref * c.double()).sum().backward()
+    for a, b, n in ((out, ref, "head"), (zd.grad, z64.grad, "gz"), (gd.grad, g64.grad, "ggamma"), (bd.grad, b64.grad, "gbeta")):
+        _close(a, b, name=n)
+    assert torch.equal((out == 0).cpu() | (keep == 1), torch.ones(M, H, dtype=torch.bool))  # dropped entries are exactly 0
+    # GeLU alone
+    zd = z.clone().to(dev()).requires_grad_(True)
+    y = XF.gelu(zd)
+    (y * c.to(dev())).sum().backward()
+    z64 = z.double().requires_grad_(True)
+    r = O.gelu_erf(z64)
+    (r * c.double()).sum().backward()
+    _close(y, r, name="gelu")
+    _close(zd.grad, z64.grad, name="gelu grad")
+
+
+def test_glue_bit_exact_against_reference_fixture():
+    import xggm_b200 as X
+    g = load_golden("glue")
+    d = dev()
+    a, f = _t(g["a"]).to(d), _t(g["f"]).to(d)
+    an, at = X.add_edge_noise(a, sigma=0.7, randn=_t(g["rn_a"]).to(d))
+    fn, ft = X.add_feature_noise(f, sigma=0.7, randn=_t(g["rn_f"]).to(d))
+    assert torch.equal(an.cpu(), _t(g["edge_noisy"])) and torch.equal(at.cpu(), _t(g["edge_target"]))
+    assert torch.equal(fn.cpu(), _t(g["feat_noisy"])) and torch.equal(ft.cpu(), _t(g["feat_target"]))
+    assert torch.equal(X.glue.strip_diag(a).cpu(), _t(g["strip"]))
+    assert torch.equal(X.glue.triu_scatter(_t(g["v"]).to(d), 36).cpu(), _t(g["scatter"]))
+    b, h = _t(g["b"]).to(d), _t(g["h"]).to(d)
+    for got, key in ((X.loss_func(a, b, sigma=0.7), "sm_adj"), (X.loss_func(f, h, sigma=0.7), "sm_feat"),
+                     (X.compute_kl_loss(a, b), "kl_adj"), (X.compute_kl_loss(f, h), "kl_feat")):
+        assert abs(float(got) - float(g[key])) < 1e-5 * abs(float(g[key])), key
+
+
+def test_glue_gradients():
+    import xggm_b200 as X
+    g = torch.Generator().manual_seed(11)
+    d = dev()
+    for shape in ((3, 36, 36), (2, 36, 768), (4, 7, 50)):
+        x, y = torch.randn(shape, generator=g), torch.randn(shape, generator=g)
+        xd, yd = x.clone().to(d).requires_grad_(True), y.clone().to(d).requires_grad_(True)
+        (3.0 * X.compute_kl_loss(xd, yd) + 2.0 * X.loss_func(xd, yd, sigma=0.5)).backward()
+        x64, y64 = x.double().requires_grad_(True), y.double().requires_grad_(True)
+        (3.0 * O.sym_kl_loss(x64, y64) + 2.0 * O.score_matching_loss(x64, y64, 0.5)).backward()
+        _close(xd.grad, x64.grad, name="gx")
+        _close(yd.grad, y64.grad, name="gy")
+    # scatter / readout / broadcast-noise backward
+    v = torch.rand(3, 630, generator=g)
+    c = torch.randn(3, 36, 36, generator=g)
+    vd = v.clone().to(d).requires_grad_(True)
+    (X.glue.triu_scatter(vd, 36) * c.to(d)).sum().backward()
+    v64 = v.double().requires_grad_(True)
+    (O.triu_scatter(v64, 36) * c.double()).sum().backward()
+    assert torch.equal(vd.grad.cpu(), v64.grad.float())  # a two-term sum: exact in fp32
+    xp, nodes = torch.randn(3, 64, generator=g), torch.randn(3, 36, 64, generator=g)
+    c2 = torch.randn(3, 128, generator=g)
+    xpd, nd = xp.clone().to(d).requires_grad_(True), nodes.clone().to(d).requires_grad_(True)
+    (X.glue.fuse_readout(xpd, nd) * c2.to(d)).sum().backward()
+    xp64, n64 = xp.double().requires_grad_(True), nodes.double().requires_grad_(True)
+    (torch.cat([xp64, torch.tanh(n64.mean(1))], -1) * c2.double()).sum().backward()
+    _close(xpd.grad, xp64.grad, name="gxp")
+    _close(nd.grad, n64.grad, name="gnodes")
+    f = torch.randn(3, 64, generator=g)
+    rn = torch.randn(3, 36, 64, generator=g)
+    fd = f.clone().to(d).requires_grad_(True)
+    noisy, tgt = X.add_feature_noise(fd, sigma=1.0, randn=rn.to(d))
+    (noisy * nodes.to(d)).sum().backward()
+    _close(fd.grad, nodes.sum(1), name="broadcast grad")
+    assert torch.equal(noisy.cpu(), f.unsqueeze(1) + rn)
+
+
+# --------------------------------------------------------------------------- generators
+GEN_CASES = [("gcn_h64_train", "GCN"), ("gcn_h64_eval", "GCN"), ("gcn_h768_train", "GCN"),
+             ("gin_h64_train", "GIN"), ("gin_h768_train", "GIN"),
+             ("gat_h64_train", "GAT"), ("gat_h768_eval", "GAT")]
+
+
+def _param_grad_check(gold, named, tol):
+    for name, v in named:
+        g = v.grad if v.grad is not None else torch.zeros_like(v)
+        if "g/" + name in gold:
+            _close(g, gold["g/" + name], tol, name)
+        elif "gn/" + name in gold:
+            nrm = float(gold["gn/" + name][0])
+            if nrm == 0:
+                assert float(g.abs().max()) == 0.0, name
+            else:
+                assert abs(float(g.double().norm()) - nrm) / nrm < tol, name
+                _close(g.reshape(-1)[:16], gold["gh/" + name], 20 * tol, name)
+        else:
+            raise AssertionError("fixture has no gradient for " + name)
+
+
+@pytest.mark.parametrize("name,gnn", GEN_CASES)
+def test_generator_matches_reference_fixture(name, gnn):
+    import xggm_b200 as X
+    from xggm_b200.functional import inject_keep_masks
+    gold = load_golden(name)
+    seed, hidden, B, n_layers, training = [int(v) for v in gold["meta"]]
+    p = O.make_params(seed, gnn, hidden, n_layers, 36, heads=False)
+    cls = {"GCN": X.GCNGenerator, "GIN": X.GINGenerator, "GAT": X.GATGenerator}[gnn]
+    mod = _load_params(cls(hidden, n_layers), p, "generator.").to(dev()).train(bool(training))
+    visn, _, _ = O.make_inputs(seed + 1, B, 36, hidden)
+    nh = {"GCN": 3, "GIN": 2, "GAT": 1}[gnn]
+    masks = []
+    if training:
+        masks = [m for layer in O.make_keeps(seed + 3, n_layers, nh, (B, 36, hidden)) for m in layer]
+    x = visn.clone().to(dev()).requires_grad_(True)
+    adj = _t(gold["adj_in"]).to(dev()).requires_grad_(True)
+    with inject_keep_masks(masks):
+        xo, ao = mod(x, adj)
+    _close(xo, gold["x_out"], name="x_out")
+    _close(ao, gold["adj_out"], name="adj_out")
+    assert float(torch.diagonal(ao, dim1=1, dim2=2).abs().max()) == 0.0
+    ((xo * _t(gold["cx"]).to(dev())).sum() + (ao * _t(gold["ca"]).to(dev())).sum()).backward()
+    _close(x.grad, gold["gx"], 2 * TOL, "gx")
+    ga = adj.grad if adj.grad is not None else torch.zeros_like(adj)
+    _close(ga, gold["gadj"], 2 * TOL, "gadj")
+    _param_grad_check(gold, [("generator." + k, v) for k, v in mod.named_parameters()], 3 * TOL)
+
+
+BRANCH_CASES = [("branch_relation_gcn_h64", "relation", "GCN"), ("branch_node_gcn_h64", "node", "GCN"),
+                ("branch_node_gcn_h768", "node", "GCN"), ("branch_relation_gin_h64", "relation", "GIN")]
+
+
+@pytest.mark.parametrize("name,which,gnn", BRANCH_CASES)
+def test_ggm_branch_matches_reference_fixture(name, which, gnn):
+    import xggm_b200 as X
+    from xggm_b200.functional import inject_keep_masks
+    gold = load_golden(name)
+    seed, hidden, B, n_layers, _ = [int(v) for v in gold["meta"]]
+    sigma, A = float(gold["sigma"]), int(gold["num_answers"])
+    p = O.make_params(seed, gnn, hidden, n_layers, 36, heads=True)
+    mod = _load_params(X.XGGMHeads(hidden, gnn, n_layers), p).to(dev()).train()
+    visn, xp, adj_true = O.make_inputs(seed + 1, B, 36, hidden)
+    nh = {"GCN": 3, "GIN": 2}[gnn]
+    masks = [m for layer in O.make_keeps(seed + 3, n_layers, nh, (B, 36, hidden)) for m in layer]
+    x = xp.clone().to(dev()).requires_grad_(True)
+    feat = visn.clone().to(dev()).requires_grad_(True)
+    randn = _t(gold["randn"]).to(dev())
+    with inject_keep_masks(masks):
+        if which == "relation":
+            x_gen, loss_sm, nodes, adj_g = mod.relation_step(x, feat, adj_true.to(dev()), sigma, A, 8.0, randn)
+        else:
+            x_gen, loss_sm, nodes, adj_g = mod.node_step(x, feat, adj_true.to(dev()), sigma, A, randn)
+    _close(x_gen, gold["x_gen"], name="x_gen")
+    _close(nodes, gold["nodes"], name="nodes")
+    _close(adj_g, gold["adj_gen"], name="adj_gen")
+    assert abs(float(loss_sm) - float(gold["loss_sm"])) < TOL * abs(float(gold["loss_sm"]))
+    ((x_gen * _t(gold["c"]).to(dev())).sum() + loss_sm).backward()
+    _close(x.grad, gold["gxp"], 3 * TOL, "gxp")
+    gv = feat.grad if feat.grad is not None else torch.zeros_like(feat)
+    _close(gv, gold["gvisn"], 3 * TOL, "gvisn")
+    _param_grad_check(gold, list(mod.named_parameters()), 5 * TOL)
+
+
+@pytest.mark.parametrize("gnn,B,N,H", [("GCN", 5, 36, 768), ("GCN", 2, 64, 128), ("GIN", 3, 100, 64), ("GCN", 1, 36, 768)])
+def test_generator_vs_oracle_seeded(gnn, B, N, H):
+    """Sizes the fixtures do not cover (other N, ragged B) against the fp64 oracle."""
+    import xggm_b200 as X
+    from xggm_b200.functional import inject_keep_masks
+    p = O.make_params(77, gnn, H, 2, N, heads=False)
+    cls = {"GCN": X.GCNGenerator, "GIN": X.GINGenerator}[gnn]
+    mod = _load_params(cls(H, 2), p, "generator.").to(dev()).train()
+    visn, _, adj_true = O.make_inputs(78, B, N, H)
+    adj = O.strip_diag(adj_true)
+    nh = {"GCN": 3, "GIN": 2}[gnn]
+    keeps = O.make_keeps(79, 2, nh, (B, N, H))
+    x = visn.clone().to(dev()).requires_grad_(True)
+    a = adj.clone().to(dev()).requires_grad_(True)
+    with inject_keep_masks([m for layer in keeps for m in layer]):
+        xo, ao = mod(x, a)
+    (xo.sum() + (ao * ao).sum()).backward()
+    p64 = {k: v.double() for k, v in p.items()}
+    x64 = visn.double().requires_grad_(True)
+    a64 = adj.double().requires_grad_(True)
+    xr, ar = O.GENERATORS[gnn](x64, a64, p64, 2, keeps, pre="generator.")
+    (xr.sum() + (ar * ar).sum()).backward()
+    _close(xo, xr, name="x")
+    _close(ao, ar, name="adj")
+    _close(x.grad, x64.grad, 2 * TOL, "gx")
+    _close(a.grad, a64.grad, 2 * TOL, "gadj")
+
+
+def test_empty_batch_and_errors():
+    import xggm_b200 as X
+    mod = X.GCNGenerator(64, 1).to(dev())
+    x = torch.zeros(0, 36, 64, device=dev())
+    adj = torch.zeros(0, 36, 36, device=dev())
+    xo, ao = mod(x, adj)
+    assert xo.shape == (0, 36, 64) and ao.shape == (0, 36, 36)
+    with pytest.raises(RuntimeError):
+        mod(torch.zeros(2, 36, 64), torch.zeros(2, 36, 36))            # CPU tensors: no fallback
+    with pytest.raises(RuntimeError):
+        mod(torch.zeros(2, 36, 64, device=dev()).double(), torch.zeros(2, 36, 36, device=dev()).double())
+    with pytest.raises(RuntimeError):
+        mod(torch.zeros(2, 36, 64, device=dev()), torch.zeros(2, 35, 35, device=dev()))
+    with pytest.raises(Exception):
+        X.GATGenerator(64, 2).to(dev())(torch.randn(2, 36, 64, device=dev()), torch.ones(2, 36, 36, device=dev()))
+
+
+def test_full_size_properties():
+    """BASELINE cfg-2 size (B=256, N=36, H=768): size-independent properties of the block."""
+    import xggm_b200 as X
+    torch.manual_seed(9595)
+    B, N, H = 256, 36, 768
+    mod = X.XGGMHeads(H, "GCN", 2).to(dev()).train()
+    visn, xp, adj_true = (t.to(dev()) for t in O.make_inputs(1, B, N, H))
+    x = xp.clone().requires_grad_(True)
+    feat = visn.clone().requires_grad_(True)
+    x_gen, loss_sm, nodes, adj_g = mod.node_step(x, feat, adj_true, 1.0, 2274)
+    (x_gen.sum() + loss_sm).backward()
+    assert torch.isfinite(loss_sm) and torch.isfinite(nodes).all() and torch.isfinite(adj_g).all()
+    assert float(torch.diagonal(adj_g, dim1=1, dim2=2).abs().max()) == 0.0
+    off = adj_g[:, ~torch.eye(N, dtype=torch.bool, device=dev())]
+    assert float(off.min()) > 0.0 and float(off.max()) <= 0.7311  # sigmoid(S/colmax) <= sigmoid(1)
+    # per-sample independence: graph b's output does not depend on the other graphs
+    mod.eval()
+    with torch.no_grad():
+        full, _ = mod.generator(visn, X.glue.strip_diag(adj_true))
+        part, _ = mod.generator(visn[100:103], X.glue.strip_diag(adj_true)[100:103])
+    assert torch.equal(full[100:103], part)
+    # linearity of the backward pass in the cotangent (eval mode: deterministic)
+    xa = visn[:8].clone().requires_grad_(True)
+    out, _ = mod.generator(xa, X.glue.strip_diag(adj_true)[:8])
+    c1, c2 = torch.randn_like(out), torch.randn_like(out)
+    g1, = torch.autograd.grad(out, xa, c1, retain_graph=True)
+    g2, = torch.autograd.grad(out, xa, c2, retain_graph=True)
+    g12, = torch.autograd.grad(out, xa, c1 + 2 * c2)
+    _close(g12, (g1 + 2 * g2).cpu(), 1e-5, "linearity")
+    for p_ in mod.parameters():
+        if p_.grad is not None:
+            assert torch.isfinite(p_.grad).all()
+
+
+def test_keep_mask_statistics_and_determinism():
+    import xggm_b200.functional as XF
+    torch.manual_seed(123)
+    m1 = XF.keep_mask((64, 36, 768), 0.5, dev())
+    m2 = XF.keep_mask((64, 36, 768), 0.5, dev())
+    frac = float(m1.float().mean())
+    assert abs(frac - 0.5) < 2e-3
+    assert not torch.equal(m1, m2)
+    m3 = XF.keep_mask((1000, 1000), 0.1, dev())
+    assert abs(float(m3.float().mean()) - 0.9) < 2e-3
+    assert set(m1.unique().tolist()) <= {0, 1}

@@ -1,0 +1,442 @@
+// extern "C" surface of libxggm_b200.so (see include/xggm_b200.h) and the composite
+// GCN / GIN layer drivers that sequence the kernels on the caller's stream.
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace xggm {
+
+// ---- declarations of the per-file launchers --------------------------------
+int gemm_simt(int op, const float* A, const float* Bm, const float* bias, const float* resid,
+              float* C, int M, int N, int K, int accumulate, cudaStream_t st);
+int colsum(const float* g, float* out, int R, int C, cudaStream_t st);
+int gemm_prof_enable(int on);
+int gemm_prof_read(double* total_ms, long long* launches, double* flops);
+int layernorm_fwd(const float*, const float*, const float*, float*, float*, float*, int, int, float, cudaStream_t);
+int layernorm_bwd(const float*, const float*, const float*, const float*, float*, float*, float*, int, int, cudaStream_t);
+int gelu_ln_drop_fwd(const float*, const float*, const float*, const uint8_t*, float, float*, float*, float*, int, int, float, int, cudaStream_t);
+int gelu_ln_drop_bwd(const float*, const float*, const float*, const float*, const float*, const uint8_t*, float, float*, float*, float*, int, int, cudaStream_t);
+int adj_apply(const float*, const float*, float*, int, int, int, float, const float*, float, bool, int, cudaStream_t);
+int bmm_nt(const float*, const float*, float*, int, int, int, float, const float*, int, const float*, float*, cudaStream_t);
+int adj_regen_fwd(const float*, float*, float*, int32_t*, int, int, int, int, cudaStream_t);
+int adj_regen_bwd(const float*, const float*, const float*, const int32_t*, float*, float*, int, int, int, int, int, cudaStream_t);
+int gat_attn_fwd(const float*, const float*, const float*, float*, float*, float*, int, int, int, float, int, cudaStream_t);
+int gat_attn_bwd(const float*, const float*, const float*, const float*, const float*, const float*, float*, float*, float*, int, int, int, float, int, cudaStream_t);
+int gelu_fwd(const float*, float*, long long, cudaStream_t);
+int gelu_bwd(const float*, const float*, float*, long long, cudaStream_t);
+int mask_scale(const float*, const uint8_t*, float, float*, long long, cudaStream_t);
+int strip_diag(const float*, float*, int, int, cudaStream_t);
+int triu_scatter_fwd(const float*, float*, int, int, cudaStream_t);
+int triu_scatter_bwd(const float*, float*, int, int, cudaStream_t);
+int edge_noise(const float*, const float*, float, float, float*, float*, int, int, cudaStream_t);
+int feat_noise(const float*, const float*, float, float, float*, float*, int, int, int, int, cudaStream_t);
+int sum_nodes(const float*, float*, int, int, int, cudaStream_t);
+int score_mse_fwd(const float*, const float*, float, float*, long long, cudaStream_t);
+int score_mse_bwd(const float*, const float*, const float*, float, float*, long long, cudaStream_t);
+int sym_kl_fwd(const float*, const float*, float*, int, int, cudaStream_t);
+int sym_kl_bwd(const float*, const float*, const float*, float*, float*, int, int, cudaStream_t);
+int fuse_readout_fwd(const float*, const float*, float*, int, int, int, cudaStream_t);
+int fuse_readout_bwd(const float*, const float*, float*, float*, int, int, int, int, cudaStream_t);
+int sigmoid_fwd(const float*, float*, long long, cudaStream_t);
+int sigmoid_bwd(const float*, const float*, float*, long long, cudaStream_t);
+int keep_mask(uint8_t*, long long, float, uint64_t, uint64_t, cudaStream_t);
+
+// ---- error state -------------------------------------------------------------
+static thread_local char g_cuda_err[256] = "";
+unsigned long long g_kernel_launches = 0;
+void set_cuda_error(cudaError_t e, const char* where) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", cudaGetErrorName(e), cudaGetErrorString(e), where);
+}
+
+constexpr float LN_EPS = 1e-5f;  // nn.LayerNorm default (src/module/gcn.py:14,47)
+
+static inline long long al4(long long n) { return (n + 3) & ~3LL; }
+
+// ---- saved-activation layout of one GCN / GIN layer ---------------------------
+struct GnnLayout {
+    long long MH, Mr;       // padded sizes of an [M,H] and an [M] chunk
+    int n_convs, n_heads, kind;
+    long long conv_stride, head_stride, head_base, total;
+    // GCN conv k: agg | xhat | h_next | rstd        GIN conv k: pre | z | h_next | mean | rstd
+    GnnLayout(int kind_, long long M, int H, int nc) : kind(kind_) {
+        MH = al4(M * H);
+        Mr = al4(M);
+        n_convs = nc;
+        n_heads = nc + 1;
+        conv_stride = (kind == XGGM_KIND_GCN) ? 3 * MH + Mr : 3 * MH + 2 * Mr;
+        head_stride = MH + 2 * Mr;  // z | mean | rstd
+        head_base = conv_stride * nc;
+        total = head_base + head_stride * n_heads;
+    }
+    long long conv(int k, int slot) const {  // slot indexes MH-sized chunks first, then M-sized
+        const long long base = conv_stride * k;
+        return slot < 3 ? base + slot * MH : base + 3 * MH + (slot - 3) * Mr;
+    }
+    long long head(int j, int slot) const {
+        const long long base = head_base + head_stride * j;
+        return slot == 0 ? base : base + MH + (slot - 1) * Mr;
+    }
+};
+
+static int gnn_fwd(int kind, const float* x, const float* adj, const float* const* cp,
+                   const float* const* hp, const uint8_t* const* keeps, float drop_p, float* out,
+                   float* saved, float* work, int B, int N, int H, int nc, cudaStream_t st) {
+    XGGM_REQUIRE(kind == XGGM_KIND_GCN || kind == XGGM_KIND_GIN);
+    XGGM_REQUIRE(B >= 0 && N > 0 && H > 0 && nc >= 0 && drop_p >= 0.f && drop_p < 1.f);
+    const int M = B * N;
+    if (M == 0) return XGGM_OK;
+    XGGM_REQUIRE(x && adj && cp && hp && out && saved && work);
+    const GnnLayout L(kind, M, H, nc);
+    const float scale = 1.f / (1.f - drop_p);
+    const float* h = x;
+    for (int k = 0; k < nc; ++k) {
+        float* h_next = saved + L.conv(k, 2);
+        if (kind == XGGM_KIND_GCN) {
+            const float* W = cp[3 * k], *g = cp[3 * k + 1], *b = cp[3 * k + 2];
+            float* agg = saved + L.conv(k, 0);
+            float* xhat = saved + L.conv(k, 1);
+            float* rstd = saved + L.conv(k, 3);
+            float* u = work;
+            XGGM_TRY(adj_apply(adj, h, agg, B, N, H, 1.f, nullptr, 0.f, false, 0, st));
+            XGGM_TRY(gemm_simt(0, agg, W, nullptr, h, u, M, H, H, 0, st));
+            XGGM_TRY(layernorm_fwd(u, g, b, h_next, xhat, rstd, M, H, LN_EPS, st));
+        } else {
+            const float* eps = cp[5 * k], *W = cp[5 * k + 1], *bias = cp[5 * k + 2];
+            const float* g = cp[5 * k + 3], *b = cp[5 * k + 4];
+            float* pre = saved + L.conv(k, 0);
+            float* z = saved + L.conv(k, 1);
+            float* mean = saved + L.conv(k, 3);
+            float* rstd = saved + L.conv(k, 4);
+            XGGM_TRY(adj_apply(adj, h, pre, B, N, H, 1.f, eps, 1.f, false, 0, st));
+            XGGM_TRY(gemm_simt(0, pre, W, bias, nullptr, z, M, H, H, 0, st));
+            XGGM_TRY(gelu_ln_drop_fwd(z, g, b, nullptr, 1.f, h_next, mean, rstd, M, H, LN_EPS, 0, st));
+        }
+        h = h_next;
+    }
+    for (int j = 0; j <= nc; ++j) {
+        const float* hj = (j == 0) ? x : saved + L.conv(j - 1, 2);
+        const float* W = hp[4 * j], *bias = hp[4 * j + 1], *g = hp[4 * j + 2], *b = hp[4 * j + 3];
+        float* z = saved + L.head(j, 0);
+        XGGM_TRY(gemm_simt(0, hj, W, bias, nullptr, z, M, H, H, 0, st));
+        XGGM_TRY(gelu_ln_drop_fwd(z, g, b, keeps ? keeps[j] : nullptr, scale, out,
+                                  saved + L.head(j, 1), saved + L.head(j, 2), M, H, LN_EPS, j > 0, st));
+    }
+    return XGGM_OK;
+}
+
+static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj,
+                   const float* const* cp, const float* const* hp, const uint8_t* const* keeps,
+                   float drop_p, const float* saved, float* work, float* gx, float* gadj,
+                   float* const* cg, float* const* hg, int B, int N, int H, int nc,
+                   cudaStream_t st) {
+    XGGM_REQUIRE(kind == XGGM_KIND_GCN || kind == XGGM_KIND_GIN);
+    XGGM_REQUIRE(B >= 0 && N > 0 && H > 0 && nc >= 0 && cp && hp && cg && hg);
+    const int M = B * N;
+    if (M == 0) {  // empty batch: parameter gradients are zero
+        const int per = (kind == XGGM_KIND_GCN) ? 3 : 5;
+        for (int k = 0; k < nc; ++k)
+            for (int q = 0; q < per; ++q) {
+                const size_t n = (kind == XGGM_KIND_GCN) ? (q == 0 ? (size_t)H * H : H)
+                                                         : (q == 0 ? 1 : (q == 1 ? (size_t)H * H : H));
+                XGGM_CUDA_TRY(cudaMemsetAsync(cg[per * k + q], 0, sizeof(float) * n, st));
+            }
+        for (int j = 0; j <= nc; ++j)
+            for (int q = 0; q < 4; ++q)
+                XGGM_CUDA_TRY(cudaMemsetAsync(hg[4 * j + q], 0, sizeof(float) * (q == 0 ? (size_t)H * H : H), st));
+        return XGGM_OK;
+    }
+    XGGM_REQUIRE(gout && x && adj && saved && work && gx && gadj);
+    const GnnLayout L(kind, M, H, nc);
+    const float scale = 1.f / (1.f - drop_p);
+    const long long MH = L.MH;
+    float* buf[2] = {work, work + MH};
+    float* gt = work + 2 * MH;  // gz / gu
+    float* gq = work + 3 * MH;
+    XGGM_CUDA_TRY(cudaMemsetAsync(gadj, 0, sizeof(float) * (size_t)B * N * N, st));
+
+    // head j contributes gz_j -> (gW_j, gb_j, ggamma_j, gbeta_j) and gz_j W_j into grad of h_j
+    auto head_bwd = [&](int j, float* gh, int accumulate) -> int {
+        const float* hj = (j == 0) ? x : saved + L.conv(j - 1, 2);
+        XGGM_CUDA_TRY(cudaMemsetAsync(hg[4 * j + 2], 0, sizeof(float) * H, st));
+        XGGM_CUDA_TRY(cudaMemsetAsync(hg[4 * j + 3], 0, sizeof(float) * H, st));
+        XGGM_TRY(gelu_ln_drop_bwd(gout, saved + L.head(j, 0), saved + L.head(j, 1), saved + L.head(j, 2),
+                                  hp[4 * j + 2], keeps ? keeps[j] : nullptr, scale, gt,
+                                  hg[4 * j + 2], hg[4 * j + 3], M, H, st));
+        XGGM_TRY(gemm_simt(2, gt, hj, nullptr, nullptr, hg[4 * j], H, H, M, 0, st));
+        XGGM_TRY(colsum(gt, hg[4 * j + 1], M, H, st));
+        XGGM_TRY(gemm_simt(1, gt, hp[4 * j], nullptr, nullptr, gh, M, H, H, accumulate, st));
+        return XGGM_OK;
+    };
+
+    int cur = 0;
+    float* gh = (nc == 0) ? gx : buf[cur];
+    XGGM_TRY(head_bwd(nc, gh, 0));
+    for (int k = nc - 1; k >= 0; --k) {
+        const float* hk = (k == 0) ? x : saved + L.conv(k - 1, 2);
+        float* gnext = (k == 0) ? gx : buf[cur ^ 1];
+        if (kind == XGGM_KIND_GCN) {
+            const float* W = cp[3 * k], *g = cp[3 * k + 1];
+            XGGM_CUDA_TRY(cudaMemsetAsync(cg[3 * k + 1], 0, sizeof(float) * H, st));
+            XGGM_CUDA_TRY(cudaMemsetAsync(cg[3 * k + 2], 0, sizeof(float) * H, st));
+            // gu = LN backward, written straight into the next-level gradient (residual path)
+            XGGM_TRY(layernorm_bwd(gh, saved + L.conv(k, 1), saved + L.conv(k, 3), g, gnext,
+                                   cg[3 * k + 1], cg[3 * k + 2], M, H, st));
+            XGGM_TRY(gemm_simt(2, gnext, saved + L.conv(k, 0), nullptr, nullptr, cg[3 * k], H, H, M, 0, st));
+            XGGM_TRY(gemm_simt(1, gnext, W, nullptr, nullptr, gq, M, H, H, 0, st));  // gq = gu Wc
+            XGGM_TRY(bmm_nt(gq, hk, gadj, B, N, H, 1.f, nullptr, 1, nullptr, nullptr, st));
+            XGGM_TRY(adj_apply(adj, gq, gnext, B, N, H, 1.f, nullptr, 0.f, true, 1, st));
+        } else {
+            const float* eps = cp[5 * k], *W = cp[5 * k + 1], *g = cp[5 * k + 3];
+            XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k], 0, sizeof(float), st));
+            XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k + 3], 0, sizeof(float) * H, st));
+            XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k + 4], 0, sizeof(float) * H, st));
+            XGGM_TRY(gelu_ln_drop_bwd(gh, saved + L.conv(k, 1), saved + L.conv(k, 3), saved + L.conv(k, 4),
+                                      g, nullptr, 1.f, gt, cg[5 * k + 3], cg[5 * k + 4], M, H, st));
+            XGGM_TRY(gemm_simt(2, gt, saved + L.conv(k, 0), nullptr, nullptr, cg[5 * k + 1], H, H, M, 0, st));
+            XGGM_TRY(colsum(gt, cg[5 * k + 2], M, H, st));
+            XGGM_TRY(gemm_simt(1, gt, W, nullptr, nullptr, gq, M, H, H, 0, st));      // gpre
+            // gadj += (1+eps) gpre h^T ; geps += <gpre h^T, adj>
+            XGGM_TRY(bmm_nt(gq, hk, gadj, B, N, H, 1.f, eps, 1, adj, cg[5 * k], st));
+            // grad h_k = gpre + (1+eps) adj^T gpre
+            XGGM_TRY(adj_apply(adj, gq, gnext, B, N, H, 1.f, eps, 1.f, true, 0, st));
+        }
+        XGGM_TRY(head_bwd(k, gnext, 1));
+        gh = gnext;
+        cur ^= 1;
+    }
+    return XGGM_OK;
+}
+
+}  // namespace xggm
+
+using namespace xggm;
+
+extern "C" {
+
+int xggm_abi_version(void) { return XGGM_ABI_VERSION; }
+
+const char* xggm_strerror(int code) {
+    switch (code) {
+        case XGGM_OK: return "ok";
+        case XGGM_ERR_ARG: return "invalid argument (shape, NULL pointer or unsupported size)";
+        case XGGM_ERR_CUDA: return "CUDA runtime error (see xggm_last_cuda_error)";
+        case XGGM_ERR_ARCH: return "device is not compute capability 10.x (B200 / sm_100a required)";
+        case XGGM_ERR_UNSUPPORTED: return "not implemented in this build";
+        default: return "unknown error";
+    }
+}
+
+const char* xggm_last_cuda_error(void) { return g_cuda_err; }
+int xggm_prof_enable(int on) { return gemm_prof_enable(on); }
+int xggm_prof_read(double* total_ms, long long* launches, double* flops) {
+    XGGM_REQUIRE(total_ms && launches && flops);
+    return gemm_prof_read(total_ms, launches, flops);
+}
+unsigned long long xggm_launch_count(void) { return g_kernel_launches; }
+
+int xggm_set_device(int device) {
+    XGGM_CUDA_TRY(cudaSetDevice(device));
+    return XGGM_OK;
+}
+
+int xggm_device_check(int device) {
+    cudaDeviceProp prop;
+    XGGM_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    return prop.major == 10 ? XGGM_OK : XGGM_ERR_ARCH;
+}
+
+int xggm_linear_fwd(const float* a, const float* w, const float* bias, const float* resid,
+                    float* out, int M, int N, int K, xggm_stream_t s) {
+    XGGM_REQUIRE(a && w && out && M >= 0 && N > 0 && K > 0);
+    return gemm_simt(0, a, w, bias, resid, out, M, N, K, 0, as_stream(s));
+}
+int xggm_linear_bwd_input(const float* g, const float* w, float* ga, int M, int N, int K,
+                          int accumulate, xggm_stream_t s) {
+    XGGM_REQUIRE(g && w && ga && M >= 0 && N > 0 && K > 0);
+    return gemm_simt(1, g, w, nullptr, nullptr, ga, M, K, N, accumulate, as_stream(s));
+}
+int xggm_linear_bwd_weight(const float* g, const float* a, float* gw, float* gbias, int M, int N,
+                           int K, xggm_stream_t s) {
+    XGGM_REQUIRE(g && a && gw && M >= 0 && N > 0 && K > 0);
+    if (M == 0) {
+        XGGM_CUDA_TRY(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)N * K, as_stream(s)));
+        if (gbias) XGGM_CUDA_TRY(cudaMemsetAsync(gbias, 0, sizeof(float) * N, as_stream(s)));
+        return XGGM_OK;
+    }
+    XGGM_TRY(gemm_simt(2, g, a, nullptr, nullptr, gw, N, K, M, 0, as_stream(s)));
+    if (gbias) XGGM_TRY(colsum(g, gbias, M, N, as_stream(s)));
+    return XGGM_OK;
+}
+
+int xggm_adj_apply_fwd(const float* adj, const float* x, float* out, int B, int N, int H,
+                       float alpha0, const float* alpha_dev, float self_w, xggm_stream_t s) {
+    XGGM_REQUIRE(adj && x && out && B >= 0);
+    return adj_apply(adj, x, out, B, N, H, alpha0, alpha_dev, self_w, false, 0, as_stream(s));
+}
+int xggm_adj_apply_bwd(const float* adj, const float* x, const float* gout, float* gx,
+                       float* gadj_raw, int B, int N, int H, float alpha0, const float* alpha_dev,
+                       float self_w, int accumulate_gx, xggm_stream_t s) {
+    XGGM_REQUIRE(adj && x && gout && gx && B >= 0);
+    XGGM_TRY(adj_apply(adj, gout, gx, B, N, H, alpha0, alpha_dev, self_w, true, accumulate_gx, as_stream(s)));
+    if (gadj_raw) XGGM_TRY(bmm_nt(gout, x, gadj_raw, B, N, H, 1.f, nullptr, 0, nullptr, nullptr, as_stream(s)));
+    return XGGM_OK;
+}
+
+int xggm_layernorm_fwd(const float* u, const float* gamma, const float* beta, float* h,
+                       float* xhat, float* rstd, int M, int H, float eps, xggm_stream_t s) {
+    XGGM_REQUIRE(u && gamma && beta && h && M >= 0 && H > 0);
+    return layernorm_fwd(u, gamma, beta, h, xhat, rstd, M, H, eps, as_stream(s));
+}
+int xggm_layernorm_bwd(const float* gh, const float* xhat, const float* rstd, const float* gamma,
+                       float* gu, float* ggamma, float* gbeta, int M, int H, xggm_stream_t s) {
+    XGGM_REQUIRE(gh && xhat && rstd && gamma && gu && ggamma && gbeta && M >= 0 && H > 0);
+    return layernorm_bwd(gh, xhat, rstd, gamma, gu, ggamma, gbeta, M, H, as_stream(s));
+}
+int xggm_gelu_ln_drop_fwd(const float* z, const float* gamma, const float* beta,
+                          const uint8_t* keep, float scale, float* out, float* mean, float* rstd,
+                          int M, int H, float eps, int accumulate, xggm_stream_t s) {
+    XGGM_REQUIRE(z && gamma && beta && out && M >= 0 && H > 0);
+    return gelu_ln_drop_fwd(z, gamma, beta, keep, scale, out, mean, rstd, M, H, eps, accumulate, as_stream(s));
+}
+int xggm_gelu_ln_drop_bwd(const float* gout, const float* z, const float* mean, const float* rstd,
+                          const float* gamma, const uint8_t* keep, float scale, float* gz,
+                          float* ggamma, float* gbeta, int M, int H, xggm_stream_t s) {
+    XGGM_REQUIRE(gout && z && mean && rstd && gamma && gz && ggamma && gbeta && M >= 0 && H > 0);
+    return gelu_ln_drop_bwd(gout, z, mean, rstd, gamma, keep, scale, gz, ggamma, gbeta, M, H, as_stream(s));
+}
+
+int xggm_adj_regen_fwd(const float* x, float* adj_out, float* S, int32_t* amax, int B, int N,
+                       int H, int squash, xggm_stream_t s) {
+    XGGM_REQUIRE(B >= 0 && H > 0);
+    if (B == 0) return XGGM_OK;
+    XGGM_REQUIRE(x && adj_out);
+    return adj_regen_fwd(x, adj_out, S, amax, B, N, H, squash, as_stream(s));
+}
+int xggm_adj_regen_bwd(const float* gadj, const float* x, const float* S, const int32_t* amax,
+                       float* gx, float* work, int B, int N, int H, int squash,
+                       int accumulate_gx, xggm_stream_t s) {
+    XGGM_REQUIRE(B >= 0 && H > 0);
+    if (B == 0) return XGGM_OK;
+    XGGM_REQUIRE(gadj && x && S && amax && gx && work);
+    return adj_regen_bwd(gadj, x, S, amax, gx, work, B, N, H, squash, accumulate_gx, as_stream(s));
+}
+
+long long xggm_gnn_saved_floats(int kind, int B, int N, int H, int n_convs) {
+    if ((kind != XGGM_KIND_GCN && kind != XGGM_KIND_GIN) || B < 0 || N <= 0 || H <= 0 || n_convs < 0) return -1;
+    return GnnLayout(kind, (long long)B * N, H, n_convs).total;
+}
+long long xggm_gnn_work_floats(int kind, int B, int N, int H, int n_convs) {
+    if ((kind != XGGM_KIND_GCN && kind != XGGM_KIND_GIN) || B < 0 || N <= 0 || H <= 0 || n_convs < 0) return -1;
+    return 4 * GnnLayout(kind, (long long)B * N, H, n_convs).MH;
+}
+int xggm_gnn_fwd(int kind, const float* x, const float* adj, const float* const* conv_params,
+                 const float* const* head_params, const uint8_t* const* keeps, float drop_p,
+                 float* out, float* saved, float* work, int B, int N, int H, int n_convs,
+                 xggm_stream_t s) {
+    return gnn_fwd(kind, x, adj, conv_params, head_params, keeps, drop_p, out, saved, work, B, N, H, n_convs, as_stream(s));
+}
+int xggm_gnn_bwd(int kind, const float* gout, const float* x, const float* adj,
+                 const float* const* conv_params, const float* const* head_params,
+                 const uint8_t* const* keeps, float drop_p, const float* saved, float* work,
+                 float* gx, float* gadj, float* const* conv_grads, float* const* head_grads,
+                 int B, int N, int H, int n_convs, xggm_stream_t s) {
+    return gnn_bwd(kind, gout, x, adj, conv_params, head_params, keeps, drop_p, saved, work, gx, gadj,
+                   conv_grads, head_grads, B, N, H, n_convs, as_stream(s));
+}
+
+int xggm_gat_attn_fwd(const float* h, const float* a, const float* adj, float* out, float* att,
+                      float* pre, int B, int N, int H, float alpha, int apply_elu, xggm_stream_t s) {
+    XGGM_REQUIRE(h && a && adj && out && att && pre && B >= 0 && H > 0);
+    return gat_attn_fwd(h, a, adj, out, att, pre, B, N, H, alpha, apply_elu, as_stream(s));
+}
+int xggm_gat_attn_bwd(const float* gout, const float* h, const float* a, const float* adj,
+                      const float* att, const float* pre, float* gh, float* ga, float* work, int B,
+                      int N, int H, float alpha, int apply_elu, xggm_stream_t s) {
+    XGGM_REQUIRE(gout && h && a && adj && att && pre && gh && ga && work && B >= 0 && H > 0);
+    return gat_attn_bwd(gout, h, a, adj, att, pre, gh, ga, work, B, N, H, alpha, apply_elu, as_stream(s));
+}
+int xggm_gelu_fwd(const float* x, float* y, long long n, xggm_stream_t s) {
+    XGGM_REQUIRE(x && y && n >= 0);
+    return gelu_fwd(x, y, n, as_stream(s));
+}
+int xggm_gelu_bwd(const float* gy, const float* x, float* gx, long long n, xggm_stream_t s) {
+    XGGM_REQUIRE(gy && x && gx && n >= 0);
+    return gelu_bwd(gy, x, gx, n, as_stream(s));
+}
+int xggm_mask_scale(const float* x, const uint8_t* keep, float scale, float* y, long long n,
+                    xggm_stream_t s) {
+    XGGM_REQUIRE(x && keep && y && n >= 0);
+    return mask_scale(x, keep, scale, y, n, as_stream(s));
+}
+
+int xggm_strip_diag(const float* a, float* out, int B, int N, xggm_stream_t s) {
+    XGGM_REQUIRE(a && out && B >= 0 && N > 0);
+    return strip_diag(a, out, B, N, as_stream(s));
+}
+int xggm_triu_scatter_fwd(const float* v, float* adj, int B, int N, xggm_stream_t s) {
+    XGGM_REQUIRE(v && adj && B >= 0 && N > 0);
+    return triu_scatter_fwd(v, adj, B, N, as_stream(s));
+}
+int xggm_triu_scatter_bwd(const float* gadj, float* gv, int B, int N, xggm_stream_t s) {
+    XGGM_REQUIRE(gadj && gv && B >= 0 && N > 0);
+    return triu_scatter_bwd(gadj, gv, B, N, as_stream(s));
+}
+int xggm_edge_noise(const float* adj, const float* randn, double sigma, float* noisy,
+                    float* target, int B, int N, xggm_stream_t s) {
+    XGGM_REQUIRE(adj && randn && noisy && target && B >= 0 && N > 0 && sigma != 0.0);
+    return edge_noise(adj, randn, (float)sigma, (float)(sigma * sigma), noisy, target, B, N, as_stream(s));
+}
+int xggm_feat_noise(const float* f, const float* randn, double sigma, float* noisy, float* target,
+                    int B, int N, int H, int f_is_broadcast, xggm_stream_t s) {
+    XGGM_REQUIRE(f && randn && noisy && target && B >= 0 && N > 0 && H > 0 && sigma != 0.0);
+    return feat_noise(f, randn, (float)sigma, (float)(sigma * sigma), noisy, target, B, N, H, f_is_broadcast, as_stream(s));
+}
+int xggm_sum_nodes(const float* g, float* out, int B, int N, int H, xggm_stream_t s) {
+    XGGM_REQUIRE(g && out && B >= 0 && N > 0 && H > 0);
+    return sum_nodes(g, out, B, N, H, as_stream(s));
+}
+int xggm_score_mse_fwd(const float* score, const float* target, double sigma, float* loss,
+                       long long n_elem, xggm_stream_t s) {
+    XGGM_REQUIRE(score && target && loss && n_elem >= 0);
+    return score_mse_fwd(score, target, (float)sigma, loss, n_elem, as_stream(s));
+}
+int xggm_score_mse_bwd(const float* score, const float* target, const float* gloss, double sigma,
+                       float* gscore, long long n_elem, xggm_stream_t s) {
+    XGGM_REQUIRE(score && target && gloss && gscore && n_elem >= 0);
+    return score_mse_bwd(score, target, gloss, (float)sigma, gscore, n_elem, as_stream(s));
+}
+int xggm_sym_kl_fwd(const float* x, const float* y, float* loss, int R, int C, xggm_stream_t s) {
+    XGGM_REQUIRE(x && y && loss && R >= 0 && C > 0);
+    return sym_kl_fwd(x, y, loss, R, C, as_stream(s));
+}
+int xggm_sym_kl_bwd(const float* x, const float* y, const float* gloss, float* gx, float* gy,
+                    int R, int C, xggm_stream_t s) {
+    XGGM_REQUIRE(x && y && gloss && R >= 0 && C > 0);
+    return sym_kl_bwd(x, y, gloss, gx, gy, R, C, as_stream(s));
+}
+int xggm_fuse_readout_fwd(const float* xp, const float* nodes, float* out, int B, int N, int H,
+                          xggm_stream_t s) {
+    XGGM_REQUIRE(xp && nodes && out && B >= 0 && N > 0 && H > 0);
+    return fuse_readout_fwd(xp, nodes, out, B, N, H, as_stream(s));
+}
+int xggm_fuse_readout_bwd(const float* gout, const float* out, float* gxp, float* gnodes, int B,
+                          int N, int H, int accumulate_gnodes, xggm_stream_t s) {
+    XGGM_REQUIRE(gout && out && gnodes && B >= 0 && N > 0 && H > 0);
+    return fuse_readout_bwd(gout, out, gxp, gnodes, B, N, H, accumulate_gnodes, as_stream(s));
+}
+int xggm_sigmoid_fwd(const float* x, float* y, long long n, xggm_stream_t s) {
+    XGGM_REQUIRE(x && y && n >= 0);
+    return sigmoid_fwd(x, y, n, as_stream(s));
+}
+int xggm_sigmoid_bwd(const float* gy, const float* y, float* gx, long long n, xggm_stream_t s) {
+    XGGM_REQUIRE(gy && y && gx && n >= 0);
+    return sigmoid_bwd(gy, y, gx, n, as_stream(s));
+}
+int xggm_keep_mask(uint8_t* keep, long long n, float p, uint64_t seed, uint64_t stream_id,
+                   xggm_stream_t s) {
+    XGGM_REQUIRE(keep && n >= 0);
+    return keep_mask(keep, n, p, seed, stream_id, as_stream(s));
+}
+
+}  // extern "C"

@@ -1,0 +1,93 @@
+// Shared device helpers for the X-GGM graph-block kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/xggm_b200.h"
+
+namespace xggm {
+
+constexpr int WARP = 32;
+
+// ---- error plumbing (never throw across the C ABI) -------------------------
+void set_cuda_error(cudaError_t e, const char* where);
+#define XGGM_CUDA_TRY(expr)                                   \
+    do {                                                      \
+        cudaError_t _e = (expr);                              \
+        if (_e != cudaSuccess) {                              \
+            ::xggm::set_cuda_error(_e, #expr);                \
+            return XGGM_ERR_CUDA;                             \
+        }                                                     \
+    } while (0)
+// one XGGM_LAUNCH_CHECK per kernel launch: also feeds xggm_launch_count()
+extern unsigned long long g_kernel_launches;
+#define XGGM_LAUNCH_CHECK()                  \
+    do {                                     \
+        ++::xggm::g_kernel_launches;         \
+        XGGM_CUDA_TRY(cudaGetLastError());   \
+    } while (0)
+#define XGGM_TRY(expr)                 \
+    do {                               \
+        int _r = (expr);               \
+        if (_r != XGGM_OK) return _r;  \
+    } while (0)
+#define XGGM_REQUIRE(cond)                 \
+    do {                                   \
+        if (!(cond)) return XGGM_ERR_ARG;  \
+    } while (0)
+
+static inline cudaStream_t as_stream(xggm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- warp / block reductions -----------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- math ------------------------------------------------------------------
+// Exact-erf GeLU (src/lxrt/modeling.py:116-124 of the reference): x*0.5*(1+erf(x/sqrt2)).
+__device__ __forceinline__ float gelu_erf(float x) {
+    return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+}
+// d/dx gelu_erf = Phi(x) + x*phi(x)
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ---- Philox4x32-10 counter RNG (dropout / noise without mask tensors) --------
+struct Philox {
+    uint32_t key0, key1;
+    __device__ __forceinline__ Philox(uint64_t seed) : key0((uint32_t)seed), key1((uint32_t)(seed >> 32)) {}
+    __device__ __forceinline__ uint4 operator()(uint64_t counter, uint64_t stream_id) const {
+        uint32_t c0 = (uint32_t)counter, c1 = (uint32_t)(counter >> 32);
+        uint32_t c2 = (uint32_t)stream_id, c3 = (uint32_t)(stream_id >> 32);
+        uint32_t k0 = key0, k1 = key1;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+            k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+        }
+        return make_uint4(c0, c1, c2, c3);
+    }
+};
+
+}  // namespace xggm

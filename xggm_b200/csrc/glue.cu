@@ -1,0 +1,389 @@
+// Trainer-glue kernels of the GGM step: diagonal strip, upper-triangle scatter,
+// Gaussian perturbation + score target, score-matching MSE, symmetric row-softmax KL,
+// fusion read-out, sigmoid, Philox keep-masks.  All are one-pass, coalesced,
+// HBM-bound element/row kernels.
+#include "common.cuh"
+
+namespace xggm {
+
+static inline int grid1d(long long n, int block = 256) { return ceil_div(n, block); }
+
+// ----------------------------------------------------------------- strip_diag
+__global__ void strip_diag_kernel(const float* __restrict__ a, float* __restrict__ out,
+                                  long long total, int N) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int r = (int)(e % ((long long)N * N));
+    out[e] = (r / N == r % N) ? 0.f : a[e];
+}
+int strip_diag(const float* a, float* out, int B, int N, cudaStream_t st) {
+    const long long total = (long long)B * N * N;
+    if (total <= 0) return XGGM_OK;
+    strip_diag_kernel<<<grid1d(total), 256, 0, st>>>(a, out, total, N);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+
+// --------------------------------------------------------------- triu scatter
+// k(i<j) = i(2N-i-1)/2 + (j-i-1): row-major order of the boolean-mask assignment.
+__device__ __forceinline__ int triu_index(int i, int j, int N) { return i * (2 * N - i - 1) / 2 + (j - i - 1); }
+
+__global__ void triu_scatter_fwd_kernel(const float* __restrict__ v, float* __restrict__ adj,
+                                        long long total, int N) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int NN = N * N, E = N * (N - 1) / 2;
+    const long long b = e / NN;
+    const int r = (int)(e - b * NN), i = r / N, j = r - i * N;
+    adj[e] = (i == j) ? 0.f : v[b * E + triu_index(min(i, j), max(i, j), N)];
+}
+__global__ void triu_scatter_bwd_kernel(const float* __restrict__ gadj, float* __restrict__ gv,
+                                        long long total, int N) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int NN = N * N, E = N * (N - 1) / 2;
+    const long long b = e / NN;
+    const int r = (int)(e - b * NN), i = r / N, j = r - i * N;
+    if (i < j) gv[b * E + triu_index(i, j, N)] = gadj[e] + gadj[b * NN + j * N + i];
+}
+int triu_scatter_fwd(const float* v, float* adj, int B, int N, cudaStream_t st) {
+    const long long total = (long long)B * N * N;
+    if (total <= 0) return XGGM_OK;
+    triu_scatter_fwd_kernel<<<grid1d(total), 256, 0, st>>>(v, adj, total, N);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+int triu_scatter_bwd(const float* gadj, float* gv, int B, int N, cudaStream_t st) {
+    const long long total = (long long)B * N * N;
+    if (total <= 0) return XGGM_OK;
+    triu_scatter_bwd_kernel<<<grid1d(total), 256, 0, st>>>(gadj, gv, total, N);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+
+// --------------------------------------------------------------------- noise
+// n = randn.triu(1)*sigma ; n += n^T ; target = -n/sigma^2 ; noisy = adj + n
+__global__ void edge_noise_kernel(const float* __restrict__ adj, const float* __restrict__ randn,
+                                  float sigma, float sigma2, float* __restrict__ noisy,
+                                  float* __restrict__ target, long long total, int N) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int NN = N * N;
+    const long long b = e / NN;
+    const int r = (int)(e - b * NN), i = r / N, j = r - i * N;
+    // (triu(1)*sigma) + transpose: exactly one of the two addends is non-zero off the diagonal
+    const float up = (i < j) ? randn[e] * sigma : 0.f;
+    const float lo = (j < i) ? randn[b * NN + j * N + i] * sigma : 0.f;
+    const float n = up + lo;
+    target[e] = -n / sigma2;
+    noisy[e] = adj[e] + n;
+}
+// sigma2 = (float)(sigma*sigma) evaluated in double by the caller, as Python's `sigma ** 2`
+int edge_noise(const float* adj, const float* randn, float sigma, float sigma2, float* noisy,
+               float* target, int B, int N, cudaStream_t st) {
+    const long long total = (long long)B * N * N;
+    if (total <= 0) return XGGM_OK;
+    edge_noise_kernel<<<grid1d(total), 256, 0, st>>>(adj, randn, sigma, sigma2, noisy, target, total, N);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+
+__global__ void feat_noise_kernel(const float* __restrict__ f, const float* __restrict__ randn,
+                                  float sigma, float sigma2, float* __restrict__ noisy,
+                                  float* __restrict__ target, long long total, int N, int H,
+                                  int bcast) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const float n = randn[e] * sigma;
+    float fv;
+    if (bcast) {
+        const long long b = e / ((long long)N * H);
+        fv = f[b * H + (e % H)];
+    } else {
+        fv = f[e];
+    }
+    noisy[e] = fv + n;
+    target[e] = -n / sigma2;
+}
+int feat_noise(const float* f, const float* randn, float sigma, float sigma2, float* noisy,
+               float* target, int B, int N, int H, int bcast, cudaStream_t st) {
+    const long long total = (long long)B * N * H;
+    if (total <= 0) return XGGM_OK;
+    feat_noise_kernel<<<grid1d(total), 256, 0, st>>>(f, randn, sigma, sigma2, noisy, target, total, N, H, bcast);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+
+__global__ void sum_nodes_kernel(const float* __restrict__ g, float* __restrict__ out, int B,
+                                 int N, int H) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)B * H) return;
+    const long long b = e / H;
+    const int c = (int)(e - b * H);
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += g[(b * N + n) * H + c];
+    out[e] = s;
+}
+int sum_nodes(const float* g, float* out, int B, int N, int H, cudaStream_t st) {
+    const long long total = (long long)B * H;
+    if (total <= 0) return XGGM_OK;
+    sum_nodes_kernel<<<grid1d(total), 256, 0, st>>>(g, out, B, N, H);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+
+// ------------------------------------------------------------ score-matching
+__global__ void __launch_bounds__(256)
+score_mse_fwd_kernel(const float* __restrict__ s, const float* __restrict__ t, float coef,
+                     float* __restrict__ loss, long long n) {
+    __shared__ float part[8];
+    float acc = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float d = s[i] - t[i];
+        acc = fmaf(d, d, acc);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < 8 ? part[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) atomicAdd(loss, v * coef);
+    }
+}
+__global__ void score_mse_bwd_kernel(const float* __restrict__ s, const float* __restrict__ t,
+                                     const float* __restrict__ gloss, float coef,
+                                     float* __restrict__ gs, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) gs[i] = gloss[0] * coef * (s[i] - t[i]);
+}
+int score_mse_fwd(const float* s, const float* t, float sigma, float* loss, long long n,
+                  cudaStream_t st) {
+    XGGM_CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float), st));
+    if (n <= 0) return XGGM_OK;
+    const float coef = 0.5f * sigma * sigma / (float)n;
+    const int grid = (int)min((long long)148 * 8, (n + 255) / 256);
+    score_mse_fwd_kernel<<<grid, 256, 0, st>>>(s, t, coef, loss, n);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+int score_mse_bwd(const float* s, const float* t, const float* gloss, float sigma, float* gs,
+                  long long n, cudaStream_t st) {
+    if (n <= 0) return XGGM_OK;
+    const float coef = sigma * sigma / (float)n;
+    score_mse_bwd_kernel<<<grid1d(n), 256, 0, st>>>(s, t, gloss, coef, gs, n);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+
+// ---------------------------------------------------------------- symmetric KL
+// One warp per row.  L_row = sum_c (py-px)(log py - log px).
+struct RowSoftmax {
+    float mx, lse;  // log p_c = v_c - mx - lse
+};
+__device__ __forceinline__ RowSoftmax row_softmax_stats(const float* __restrict__ v, int C, int lane) {
+    float mx = -INFINITY;
+    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, v[c]);
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += expf(v[c] - mx);
+    s = warp_sum(s);
+    return {mx, logf(s)};
+}
+
+__global__ void __launch_bounds__(256)
+sym_kl_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                  float* __restrict__ loss, int R, int C, float inv_count) {
+    __shared__ float part[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float acc = 0.f;
+    for (int r = blockIdx.x * 8 + warp; r < R; r += gridDim.x * 8) {
+        const float* xr = x + (size_t)r * C;
+        const float* yr = y + (size_t)r * C;
+        const RowSoftmax sx = row_softmax_stats(xr, C, lane), sy = row_softmax_stats(yr, C, lane);
+        for (int c = lane; c < C; c += 32) {
+            const float lpx = xr[c] - sx.mx - sx.lse, lpy = yr[c] - sy.mx - sy.lse;
+            const float px = expf(lpx), py = expf(lpy);
+            // F.kl_div(log_px, py) + F.kl_div(log_py, px), reduction='none'
+            acc += py * (lpy - lpx) + px * (lpx - lpy);
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) part[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < 8 ? part[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) atomicAdd(loss, v * inv_count);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sym_kl_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                  const float* __restrict__ gloss, float* __restrict__ gx,
+                  float* __restrict__ gy, int R, int C, float inv_count) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float g = gloss[0] * inv_count;
+    for (int r = blockIdx.x * 8 + warp; r < R; r += gridDim.x * 8) {
+        const float* xr = x + (size_t)r * C;
+        const float* yr = y + (size_t)r * C;
+        const RowSoftmax sx = row_softmax_stats(xr, C, lane), sy = row_softmax_stats(yr, C, lane);
+        float ax = 0.f, ay = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float lpx = xr[c] - sx.mx - sx.lse, lpy = yr[c] - sy.mx - sy.lse;
+            const float e = lpy - lpx;
+            ax = fmaf(expf(lpx), e, ax);
+            ay = fmaf(expf(lpy), e, ay);
+        }
+        ax = warp_sum(ax);
+        ay = warp_sum(ay);
+        for (int c = lane; c < C; c += 32) {
+            const float lpx = xr[c] - sx.mx - sx.lse, lpy = yr[c] - sy.mx - sy.lse;
+            const float px = expf(lpx), py = expf(lpy);
+            const float e = lpy - lpx, d = py - px;
+            if (gx) gx[(size_t)r * C + c] = g * (px * (ax - e) - d);
+            if (gy) gy[(size_t)r * C + c] = g * (py * (e - ay) + d);
+        }
+    }
+}
+int sym_kl_fwd(const float* x, const float* y, float* loss, int R, int C, cudaStream_t st) {
+    XGGM_CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float), st));
+    if (R <= 0 || C <= 0) return XGGM_OK;
+    const int grid = min(148 * 8, ceil_div(R, 8));
+    sym_kl_fwd_kernel<<<grid, 256, 0, st>>>(x, y, loss, R, C, 1.0f / ((float)R * (float)C));
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+int sym_kl_bwd(const float* x, const float* y, const float* gloss, float* gx, float* gy, int R,
+               int C, cudaStream_t st) {
+    if (R <= 0 || C <= 0) return XGGM_OK;
+    const int grid = min(148 * 8, ceil_div(R, 8));
+    sym_kl_bwd_kernel<<<grid, 256, 0, st>>>(x, y, gloss, gx, gy, R, C, 1.0f / ((float)R * (float)C));
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+
+// --------------------------------------------------------------- fusion readout
+__global__ void fuse_readout_fwd_kernel(const float* __restrict__ xp, const float* __restrict__ nodes,
+                                        float* __restrict__ out, int B, int N, int H) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)B * H) return;
+    const long long b = e / H;
+    const int c = (int)(e - b * H);
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += nodes[(b * N + n) * H + c];
+    out[b * 2 * H + c] = xp[e];
+    out[b * 2 * H + H + c] = tanhf(s / (float)N);
+}
+__global__ void fuse_readout_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ out,
+                                        float* __restrict__ gxp, float* __restrict__ gnodes, int B,
+                                        int N, int H, int accumulate) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)B * H) return;
+    const long long b = e / H;
+    const int c = (int)(e - b * H);
+    if (gxp) gxp[e] = gout[b * 2 * H + c];
+    const float t = out[b * 2 * H + H + c];
+    const float g = gout[b * 2 * H + H + c] * (1.f - t * t) / (float)N;
+    for (int n = 0; n < N; ++n) {
+        float* p = gnodes + (b * N + n) * H + c;
+        *p = accumulate ? *p + g : g;
+    }
+}
+int fuse_readout_fwd(const float* xp, const float* nodes, float* out, int B, int N, int H, cudaStream_t st) {
+    const long long total = (long long)B * H;
+    if (total <= 0) return XGGM_OK;
+    fuse_readout_fwd_kernel<<<grid1d(total), 256, 0, st>>>(xp, nodes, out, B, N, H);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+int fuse_readout_bwd(const float* gout, const float* out, float* gxp, float* gnodes, int B, int N,
+                     int H, int accumulate, cudaStream_t st) {
+    const long long total = (long long)B * H;
+    if (total <= 0) return XGGM_OK;
+    fuse_readout_bwd_kernel<<<grid1d(total), 256, 0, st>>>(gout, out, gxp, gnodes, B, N, H, accumulate);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+
+// ------------------------------------------------------------------- sigmoid
+__global__ void sigmoid_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = sigmoidf_(x[i]);
+}
+__global__ void sigmoid_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ y,
+                                   float* __restrict__ gx, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const float v = y[i]; gx[i] = gy[i] * v * (1.f - v); }
+}
+int sigmoid_fwd(const float* x, float* y, long long n, cudaStream_t st) {
+    if (n <= 0) return XGGM_OK;
+    sigmoid_fwd_kernel<<<grid1d(n), 256, 0, st>>>(x, y, n);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+int sigmoid_bwd(const float* gy, const float* y, float* gx, long long n, cudaStream_t st) {
+    if (n <= 0) return XGGM_OK;
+    sigmoid_bwd_kernel<<<grid1d(n), 256, 0, st>>>(gy, y, gx, n);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+
+// ------------------------------------------------------- GeLU / masked scaling
+__global__ void gelu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = gelu_erf(x[i]);
+}
+__global__ void gelu_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x,
+                                float* __restrict__ gx, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) gx[i] = gy[i] * gelu_erf_grad(x[i]);
+}
+int gelu_fwd(const float* x, float* y, long long n, cudaStream_t st) {
+    if (n <= 0) return XGGM_OK;
+    gelu_fwd_kernel<<<grid1d(n), 256, 0, st>>>(x, y, n);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+int gelu_bwd(const float* gy, const float* x, float* gx, long long n, cudaStream_t st) {
+    if (n <= 0) return XGGM_OK;
+    gelu_bwd_kernel<<<grid1d(n), 256, 0, st>>>(gy, x, gx, n);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+// inverted dropout with an explicit mask: y = keep ? x*scale : 0 (its own backward)
+__global__ void mask_scale_kernel(const float* __restrict__ x, const uint8_t* __restrict__ keep,
+                                  float scale, float* __restrict__ y, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = keep[i] ? x[i] * scale : 0.f;
+}
+int mask_scale(const float* x, const uint8_t* keep, float scale, float* y, long long n, cudaStream_t st) {
+    if (n <= 0) return XGGM_OK;
+    mask_scale_kernel<<<grid1d(n), 256, 0, st>>>(x, keep, scale, y, n);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+
+// ----------------------------------------------------------------- keep mask
+__global__ void keep_mask_kernel(uint8_t* __restrict__ keep, long long n, uint32_t thresh,
+                                 uint64_t seed, uint64_t stream_id) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // 4 elements per thread
+    if (q * 4 >= n) return;
+    const uint4 r = Philox(seed)((uint64_t)q, stream_id);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (q * 4 + i < n) keep[q * 4 + i] = w[i] >= thresh ? 1 : 0;
+}
+int keep_mask(uint8_t* keep, long long n, float p, uint64_t seed, uint64_t stream_id, cudaStream_t st) {
+    if (n <= 0) return XGGM_OK;
+    XGGM_REQUIRE(p >= 0.f && p < 1.f);
+    const double t = (double)p * 4294967296.0;
+    const uint32_t thresh = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+    keep_mask_kernel<<<grid1d((n + 3) / 4), 256, 0, st>>>(keep, n, thresh, seed, stream_id);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+
+}  // namespace xggm

@@ -1,0 +1,477 @@
+// Per-graph operators: each N x N adjacency is staged whole in shared memory.
+//   adj_apply : out = self_w*x + alpha * (adj | adj^T) @ x        (message passing)
+//   bmm_nt    : out[b] = p[b] q[b]^T  ([N,H] x [H,N])             (gadj, pair scores)
+//   adj_regen : sigmoid(S / colmax) with zero diagonal, fwd + bwd  (ggm.py:225-228)
+//   gat_attn  : dense masked attention of GATConv                  (gat.py:25-49)
+#include "common.cuh"
+
+namespace xggm {
+
+constexpr int MAX_NODES = 104;  // smem sizing of the N x N stages (cfg-4 sweep goes to N=100)
+
+// ----------------------------------------------------------------- adj_apply
+// grid (ceil(H/256), B); thread = one feature column; adjacency in smem (broadcast reads);
+// node rows are walked in register tiles of RT.
+template <int RT, bool TRANS>
+__global__ void __launch_bounds__(256)
+adj_apply_kernel(const float* __restrict__ adj, const float* __restrict__ x,
+                 float* __restrict__ out, int N, int H, float alpha0,
+                 const float* __restrict__ alpha_dev, float self_w, int accumulate) {
+    extern __shared__ float s_adj[];  // [N][N], s_adj[i*N+j] = coefficient of x_j in out_i
+    const int b = blockIdx.y;
+    const float* ab = adj + (size_t)b * N * N;
+    for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+        const int i = e / N, j = e - i * N;
+        s_adj[e] = TRANS ? ab[j * N + i] : ab[e];
+    }
+    __syncthreads();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= H) return;
+    const float alpha = alpha0 + (alpha_dev ? alpha_dev[0] : 0.f);
+    const float* xb = x + (size_t)b * N * H + c;
+    float* ob = out + (size_t)b * N * H + c;
+    for (int i0 = 0; i0 < N; i0 += RT) {
+        float acc[RT];
+#pragma unroll
+        for (int i = 0; i < RT; ++i) acc[i] = 0.f;
+        for (int j = 0; j < N; ++j) {
+            const float xv = xb[(size_t)j * H];
+#pragma unroll
+            for (int i = 0; i < RT; ++i)
+                if (i0 + i < N) acc[i] = fmaf(s_adj[(i0 + i) * N + j], xv, acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+            if (i0 + i >= N) break;
+            float v = alpha * acc[i];
+            if (self_w != 0.f) v = fmaf(self_w, xb[(size_t)(i0 + i) * H], v);
+            float* o = ob + (size_t)(i0 + i) * H;
+            *o = accumulate ? *o + v : v;
+        }
+    }
+}
+
+int adj_apply(const float* adj, const float* x, float* out, int B, int N, int H, float alpha0,
+              const float* alpha_dev, float self_w, bool trans, int accumulate, cudaStream_t st) {
+    if (B <= 0) return XGGM_OK;
+    XGGM_REQUIRE(N >= 1 && N <= MAX_NODES && H >= 1);
+    dim3 grid(ceil_div(H, 256), B);
+    const size_t smem = sizeof(float) * N * N;
+    if (trans)
+        adj_apply_kernel<12, true><<<grid, 256, smem, st>>>(adj, x, out, N, H, alpha0, alpha_dev, self_w, accumulate);
+    else
+        adj_apply_kernel<12, false><<<grid, 256, smem, st>>>(adj, x, out, N, H, alpha0, alpha_dev, self_w, accumulate);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+
+// -------------------------------------------------------------------- bmm_nt
+// One CTA per graph.  Feature columns are streamed through smem in chunks of CK;
+// each thread owns up to MAXB 3x3 blocks of the N x N result.  The k-order of every
+// dot product is identical for (i,j) and (j,i), so p == q gives a bitwise-symmetric S.
+constexpr int CK = 64;
+constexpr int MAXB = 5;
+
+struct PairTile {
+    float acc[MAXB][9];
+};
+
+__device__ __forceinline__ void pair_scores(const float* __restrict__ pb, const float* __restrict__ qb,
+                                            int N, int H, float* ps, float* qs, PairTile& tile) {
+    const int nb = (N + 2) / 3, nblk = nb * nb;
+    const bool same = (pb == qb);
+#pragma unroll
+    for (int u = 0; u < MAXB; ++u)
+#pragma unroll
+        for (int e = 0; e < 9; ++e) tile.acc[u][e] = 0.f;
+    for (int c0 = 0; c0 < H; c0 += CK) {
+        const int cw = min(CK, H - c0);
+        for (int e = threadIdx.x; e < N * CK; e += blockDim.x) {
+            const int i = e / CK, c = e - i * CK;
+            const float pv = c < cw ? pb[(size_t)i * H + c0 + c] : 0.f;
+            ps[i * (CK + 1) + c] = pv;
+            if (!same) qs[i * (CK + 1) + c] = c < cw ? qb[(size_t)i * H + c0 + c] : 0.f;
+        }
+        __syncthreads();
+        const float* qsrc = same ? ps : qs;
+#pragma unroll
+        for (int u = 0; u < MAXB; ++u) {
+            const int blk = threadIdx.x + u * blockDim.x;
+            if (blk < nblk) {
+                const int ib = blk / nb, jb = blk - ib * nb;
+                const int i0 = min(ib * 3, N - 1), i1 = min(ib * 3 + 1, N - 1), i2 = min(ib * 3 + 2, N - 1);
+                const int j0 = min(jb * 3, N - 1), j1 = min(jb * 3 + 1, N - 1), j2 = min(jb * 3 + 2, N - 1);
+                const float* p0 = ps + i0 * (CK + 1); const float* p1 = ps + i1 * (CK + 1); const float* p2 = ps + i2 * (CK + 1);
+                const float* q0 = qsrc + j0 * (CK + 1); const float* q1 = qsrc + j1 * (CK + 1); const float* q2 = qsrc + j2 * (CK + 1);
+                float* a = tile.acc[u];
+#pragma unroll 8
+                for (int c = 0; c < CK; ++c) {
+                    const float x0 = p0[c], x1 = p1[c], x2 = p2[c];
+                    const float y0 = q0[c], y1 = q1[c], y2 = q2[c];
+                    a[0] = fmaf(x0, y0, a[0]); a[1] = fmaf(x0, y1, a[1]); a[2] = fmaf(x0, y2, a[2]);
+                    a[3] = fmaf(x1, y0, a[3]); a[4] = fmaf(x1, y1, a[4]); a[5] = fmaf(x1, y2, a[5]);
+                    a[6] = fmaf(x2, y0, a[6]); a[7] = fmaf(x2, y1, a[7]); a[8] = fmaf(x2, y2, a[8]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// scatter the register tiles into an [N][N] array (smem or global)
+__device__ __forceinline__ void pair_store(const PairTile& tile, float* dst, int N) {
+    const int nb = (N + 2) / 3, nblk = nb * nb;
+#pragma unroll
+    for (int u = 0; u < MAXB; ++u) {
+        const int blk = threadIdx.x + u * blockDim.x;
+        if (blk < nblk) {
+            const int ib = blk / nb, jb = blk - ib * nb;
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int i = ib * 3 + r, j = jb * 3 + c;
+                    if (i < N && j < N) dst[i * N + j] = tile.acc[u][r * 3 + c];
+                }
+        }
+    }
+}
+
+// out[b] (=|+=) alpha * p[b] q[b]^T ;  dot_out? += sum_b <p[b] q[b]^T, dot_ref[b]>
+__global__ void __launch_bounds__(256)
+bmm_nt_kernel(const float* __restrict__ p, const float* __restrict__ q, float* __restrict__ out,
+              int N, int H, float alpha0, const float* __restrict__ alpha_dev, int accumulate,
+              const float* __restrict__ dot_ref, float* __restrict__ dot_out) {
+    extern __shared__ float sm[];
+    __shared__ float part[8];
+    float* ps = sm;
+    float* qs = sm + N * (CK + 1);
+    const int b = blockIdx.x;
+    PairTile tile;
+    pair_scores(p + (size_t)b * N * H, q + (size_t)b * N * H, N, H, ps, qs, tile);
+    const float alpha = alpha0 + (alpha_dev ? alpha_dev[0] : 0.f);
+    float* ob = out + (size_t)b * N * N;
+    const float* rb = dot_ref ? dot_ref + (size_t)b * N * N : nullptr;
+    const int nb = (N + 2) / 3, nblk = nb * nb;
+    float dot = 0.f;
+#pragma unroll
+    for (int u = 0; u < MAXB; ++u) {
+        const int blk = threadIdx.x + u * blockDim.x;
+        if (blk < nblk) {
+            const int ib = blk / nb, jb = blk - ib * nb;
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int i = ib * 3 + r, j = jb * 3 + c;
+                    if (i < N && j < N) {
+                        const float v = tile.acc[u][r * 3 + c];
+                        if (rb) dot = fmaf(v, rb[i * N + j], dot);
+                        const float o = alpha * v;
+                        ob[i * N + j] = accumulate ? ob[i * N + j] + o : o;
+                    }
+                }
+        }
+    }
+    if (dot_out) {
+        dot = warp_sum(dot);
+        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = dot;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float v = threadIdx.x < 8 ? part[threadIdx.x] : 0.f;
+            v = warp_sum(v);
+            if (threadIdx.x == 0) atomicAdd(dot_out, v);
+        }
+    }
+}
+
+int bmm_nt(const float* p, const float* q, float* out, int B, int N, int H, float alpha0,
+           const float* alpha_dev, int accumulate, const float* dot_ref, float* dot_out,
+           cudaStream_t st) {
+    if (B <= 0) return XGGM_OK;
+    XGGM_REQUIRE(N >= 1 && N <= MAX_NODES);
+    const size_t smem = sizeof(float) * 2 * N * (CK + 1);
+    if (smem > 48 * 1024)
+        XGGM_CUDA_TRY(cudaFuncSetAttribute(bmm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bmm_nt_kernel<<<B, 256, smem, st>>>(p, q, out, N, H, alpha0, alpha_dev, accumulate, dot_ref, dot_out);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+
+// ----------------------------------------------------------------- adj_regen
+__global__ void __launch_bounds__(256)
+adj_regen_fwd_kernel(const float* __restrict__ x, float* __restrict__ adj_out,
+                     float* __restrict__ S_out, int32_t* __restrict__ amax_out, int N, int H,
+                     int squash) {
+    extern __shared__ float sm[];
+    float* ps = sm;                       // [N][CK+1]
+    float* S = sm + N * (CK + 1);         // [N][N]
+    float* m = S + N * N;                 // [N]
+    const int b = blockIdx.x;
+    PairTile tile;
+    pair_scores(x + (size_t)b * N * H, x + (size_t)b * N * H, N, H, ps, ps, tile);
+    pair_store(tile, S, N);
+    __syncthreads();
+    // column max, first index on ties (torch.max(dim=1) semantics), ggm.py:226
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        float best = S[i];
+        int arg = 0;
+        for (int k = 1; k < N; ++k) {
+            const float v = S[k * N + i];
+            if (v > best) { best = v; arg = k; }
+        }
+        m[i] = best;
+        if (amax_out) amax_out[(size_t)b * N + i] = arg;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+        const int i = e / N, j = e - i * N;
+        const float s = S[e];
+        if (S_out) S_out[(size_t)b * N * N + e] = s;
+        float v = s / m[i];
+        if (squash) v = sigmoidf_(v);
+        adj_out[(size_t)b * N * N + e] = (i == j) ? 0.f : v;
+    }
+}
+
+int adj_regen_fwd(const float* x, float* adj_out, float* S, int32_t* amax, int B, int N, int H,
+                  int squash, cudaStream_t st) {
+    if (B <= 0) return XGGM_OK;
+    XGGM_REQUIRE(N >= 1 && N <= MAX_NODES);
+    const size_t smem = sizeof(float) * ((size_t)N * (CK + 1) + (size_t)N * N + N);
+    if (smem > 48 * 1024)
+        XGGM_CUDA_TRY(cudaFuncSetAttribute(adj_regen_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    adj_regen_fwd_kernel<<<B, 256, smem, st>>>(x, adj_out, S, amax, N, H, squash);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+
+// d(adj_out)/dS folded into a symmetric coefficient matrix D = dS + dS^T so that
+// gx += D x.  One CTA per graph.
+__global__ void __launch_bounds__(256)
+adj_regen_bwd_kernel(const float* __restrict__ gadj, const float* __restrict__ S_in,
+                     const int32_t* __restrict__ amax, float* __restrict__ D_out, int N,
+                     int squash) {
+    extern __shared__ float sm[];
+    float* S = sm;             // [N][N]
+    float* dS = S + N * N;     // [N][N]
+    float* m = dS + N * N;     // [N]
+    float* dm = m + N;         // [N]
+    const int b = blockIdx.x;
+    const float* Sb = S_in + (size_t)b * N * N;
+    const float* gb = gadj + (size_t)b * N * N;
+    const int32_t* ab = amax + (size_t)b * N;
+    for (int e = threadIdx.x; e < N * N; e += blockDim.x) S[e] = Sb[e];
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) m[i] = S[ab[i] * N + i];
+    __syncthreads();
+    // dt and dS (without the max path)
+    for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+        const int i = e / N, j = e - i * N;
+        float dt = 0.f;
+        if (i != j) {
+            dt = gb[e];
+            if (squash) {
+                const float y = sigmoidf_(S[e] / m[i]);
+                dt *= y * (1.f - y);
+            }
+        }
+        dS[e] = dt / m[i];
+    }
+    __syncthreads();
+    // dm_i = - sum_j dt_ij S_ij / m_i^2 = - sum_j dS_ij * S_ij / m_i   (one warp per row)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int i = warp; i < N; i += nwarp) {
+        float s = 0.f;
+        for (int j = lane; j < N; j += 32) s = fmaf(dS[i * N + j], S[i * N + j], s);
+        s = warp_sum(s);
+        if (lane == 0) dm[i] = -s / m[i];
+    }
+    __syncthreads();
+    // route dm_i to the arg-max entry of column i (distinct columns -> no write conflicts)
+    for (int i = threadIdx.x; i < N; i += blockDim.x) dS[ab[i] * N + i] += dm[i];
+    __syncthreads();
+    for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+        const int i = e / N, j = e - i * N;
+        D_out[(size_t)b * N * N + e] = dS[e] + dS[j * N + i];
+    }
+}
+
+int adj_regen_bwd(const float* gadj, const float* x, const float* S, const int32_t* amax,
+                  float* gx, float* work, int B, int N, int H, int squash, int accumulate_gx,
+                  cudaStream_t st) {
+    if (B <= 0) return XGGM_OK;
+    XGGM_REQUIRE(N >= 1 && N <= MAX_NODES);
+    const size_t smem = sizeof(float) * (2 * (size_t)N * N + 2 * N);
+    if (smem > 48 * 1024)
+        XGGM_CUDA_TRY(cudaFuncSetAttribute(adj_regen_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    adj_regen_bwd_kernel<<<B, 256, smem, st>>>(gadj, S, amax, work, N, squash);
+    XGGM_LAUNCH_CHECK();
+    return adj_apply(work, x, gx, B, N, H, 1.f, nullptr, 0.f, false, accumulate_gx, st);
+}
+
+// ------------------------------------------------------------------ GAT attn
+// scores + mask + row softmax: one CTA per graph
+__global__ void __launch_bounds__(256)
+gat_scores_kernel(const float* __restrict__ h, const float* __restrict__ a,
+                  const float* __restrict__ adj, float* __restrict__ att, int N, int H,
+                  float slope) {
+    extern __shared__ float sm[];
+    float* s1 = sm;        // [N]  a[:H] . h_i
+    float* s2 = sm + N;    // [N]  a[H:] . h_j
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const float* hb = h + (size_t)b * N * H;
+    for (int i = warp; i < N; i += nwarp) {
+        float u = 0.f, v = 0.f;
+        for (int c = lane; c < H; c += 32) {
+            const float hv = hb[(size_t)i * H + c];
+            u = fmaf(hv, a[c], u);
+            v = fmaf(hv, a[H + c], v);
+        }
+        u = warp_sum(u); v = warp_sum(v);
+        if (lane == 0) { s1[i] = u; s2[i] = v; }
+    }
+    __syncthreads();
+    const float* ab = adj + (size_t)b * N * N;
+    float* ob = att + (size_t)b * N * N;
+    for (int i = warp; i < N; i += nwarp) {
+        float mx = -INFINITY;
+        for (int j = lane; j < N; j += 32) {
+            float e = s1[i] + s2[j];
+            e = e > 0.f ? e : slope * e;
+            if (ab[i * N + j] == 0.f) e = -9e15f;
+            mx = fmaxf(mx, e);
+        }
+        mx = warp_max(mx);
+        float den = 0.f;
+        for (int j = lane; j < N; j += 32) {
+            float e = s1[i] + s2[j];
+            e = e > 0.f ? e : slope * e;
+            if (ab[i * N + j] == 0.f) e = -9e15f;
+            den += expf(e - mx);
+        }
+        den = warp_sum(den);
+        for (int j = lane; j < N; j += 32) {
+            float e = s1[i] + s2[j];
+            e = e > 0.f ? e : slope * e;
+            if (ab[i * N + j] == 0.f) e = -9e15f;
+            ob[i * N + j] = expf(e - mx) / den;
+        }
+    }
+}
+
+__global__ void elu_fwd_kernel(const float* __restrict__ pre, float* __restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const float v = pre[i]; out[i] = v > 0.f ? v : expm1f(v); }
+}
+__global__ void elu_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ pre,
+                               float* __restrict__ gpre, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const float v = pre[i]; gpre[i] = gout[i] * (v > 0.f ? 1.f : expf(v)); }
+}
+
+int gat_attn_fwd(const float* h, const float* a, const float* adj, float* out, float* att,
+                 float* pre, int B, int N, int H, float slope, int apply_elu, cudaStream_t st) {
+    if (B <= 0) return XGGM_OK;
+    XGGM_REQUIRE(N >= 1 && N <= MAX_NODES);
+    gat_scores_kernel<<<B, 256, sizeof(float) * 2 * N, st>>>(h, a, adj, att, N, H, slope);
+    XGGM_LAUNCH_CHECK();
+    if (!apply_elu) return adj_apply(att, h, out, B, N, H, 1.f, nullptr, 0.f, false, 0, st);
+    XGGM_TRY(adj_apply(att, h, pre, B, N, H, 1.f, nullptr, 0.f, false, 0, st));
+    const long long n = (long long)B * N * H;
+    elu_fwd_kernel<<<ceil_div(n, 256), 256, 0, st>>>(pre, out, n);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+
+// softmax / LeakyReLU / mask backward + the rank-1 score terms.  One CTA per graph.
+// In: gatt[N][N] = gpre @ h^T.  Out: gh_i += gs1_i a1 + gs2_i a2 ; ga += [sum gs1_i h_i | sum gs2_j h_j]
+__global__ void __launch_bounds__(256)
+gat_scores_bwd_kernel(const float* __restrict__ h, const float* __restrict__ a,
+                      const float* __restrict__ adj, const float* __restrict__ att,
+                      const float* __restrict__ gatt, float* __restrict__ gh,
+                      float* __restrict__ ga, int N, int H, float slope) {
+    extern __shared__ float sm[];
+    float* s1 = sm;            // [N]
+    float* s2 = s1 + N;        // [N]
+    float* g1 = s2 + N;        // [N]  gs1
+    float* g2 = g1 + N;        // [N]  gs2
+    float* ge = g2 + N;        // [N][N] gradient w.r.t. the pre-LeakyReLU score
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const float* hb = h + (size_t)b * N * H;
+    for (int i = warp; i < N; i += nwarp) {
+        float u = 0.f, v = 0.f;
+        for (int c = lane; c < H; c += 32) {
+            const float hv = hb[(size_t)i * H + c];
+            u = fmaf(hv, a[c], u);
+            v = fmaf(hv, a[H + c], v);
+        }
+        u = warp_sum(u); v = warp_sum(v);
+        if (lane == 0) { s1[i] = u; s2[i] = v; }
+    }
+    __syncthreads();
+    const float* ab = adj + (size_t)b * N * N;
+    const float* pb = att + (size_t)b * N * N;
+    const float* gb = gatt + (size_t)b * N * N;
+    for (int i = warp; i < N; i += nwarp) {
+        float dot = 0.f;
+        for (int j = lane; j < N; j += 32) dot = fmaf(pb[i * N + j], gb[i * N + j], dot);
+        dot = warp_sum(dot);
+        float rs = 0.f;
+        for (int j = lane; j < N; j += 32) {
+            float g = pb[i * N + j] * (gb[i * N + j] - dot);
+            if (ab[i * N + j] == 0.f) g = 0.f;           // masked_fill blocks the gradient
+            else g *= (s1[i] + s2[j]) > 0.f ? 1.f : slope;
+            ge[i * N + j] = g;
+            rs += g;
+        }
+        rs = warp_sum(rs);
+        if (lane == 0) g1[i] = rs;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        float cs = 0.f;
+        for (int i = 0; i < N; ++i) cs += ge[i * N + j];
+        g2[j] = cs;
+    }
+    __syncthreads();
+    float* ghb = gh + (size_t)b * N * H;
+    for (int c = threadIdx.x; c < H; c += blockDim.x) {
+        const float a1 = a[c], a2 = a[H + c];
+        float d1 = 0.f, d2 = 0.f;
+        for (int i = 0; i < N; ++i) {
+            const float hv = hb[(size_t)i * H + c];
+            ghb[(size_t)i * H + c] += g1[i] * a1 + g2[i] * a2;
+            d1 = fmaf(g1[i], hv, d1);
+            d2 = fmaf(g2[i], hv, d2);
+        }
+        atomicAdd(&ga[c], d1);
+        atomicAdd(&ga[H + c], d2);
+    }
+}
+
+// work: [B,N,H] (gpre) + [B,N,N] (gatt)
+int gat_attn_bwd(const float* gout, const float* h, const float* a, const float* adj,
+                 const float* att, const float* pre, float* gh, float* ga, float* work, int B,
+                 int N, int H, float slope, int apply_elu, cudaStream_t st) {
+    if (B <= 0) return XGGM_OK;
+    XGGM_REQUIRE(N >= 1 && N <= MAX_NODES);
+    const long long n = (long long)B * N * H;
+    const float* gpre = gout;
+    float* gatt = work + n;
+    if (apply_elu) {
+        elu_bwd_kernel<<<ceil_div(n, 256), 256, 0, st>>>(gout, pre, work, n);
+        XGGM_LAUNCH_CHECK();
+        gpre = work;
+    }
+    XGGM_TRY(adj_apply(att, gpre, gh, B, N, H, 1.f, nullptr, 0.f, true, 0, st));   // gh = att^T gpre
+    XGGM_TRY(bmm_nt(gpre, h, gatt, B, N, H, 1.f, nullptr, 0, nullptr, nullptr, st));                                   // gatt = gpre h^T
+    const size_t smem = sizeof(float) * (4 * (size_t)N + (size_t)N * N);
+    gat_scores_bwd_kernel<<<B, 256, smem, st>>>(h, a, adj, att, gatt, gh, ga, N, H, slope);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+
+}  // namespace xggm

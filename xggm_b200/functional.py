@@ -1,0 +1,583 @@
+"""torch.autograd.Function wrappers over the C ABI (include/xggm_b200.h).
+
+Each Function allocates its outputs / saved buffers with torch (so the caching
+allocator and stream semantics stay torch's) and enqueues the kernels on
+``torch.cuda.current_stream()`` through ``_lib.call``.  There is no eager
+PyTorch fallback anywhere in this file.
+"""
+import torch
+
+from . import _lib
+from ._lib import call, f32, ptr, ptr_table
+
+LN_EPS = 1e-5
+KIND = {"GCN": 0, "GIN": 1}
+
+
+def _u8(t):
+    if t is None:
+        return None
+    if t.dtype != torch.uint8:
+        t = t.to(torch.uint8)
+    _lib.check_device(t)
+    return t.contiguous()
+
+
+# ---------------------------------------------------------------------------
+# dense projection (nn.Linear)
+# ---------------------------------------------------------------------------
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, w, bias, resid):
+        a2 = f32(a, "input").reshape(-1, a.shape[-1])
+        w = f32(w, "weight")
+        M, K = a2.shape
+        N = w.shape[0]
+        if w.shape[1] != K:
+            raise RuntimeError(f"xggm_b200.linear: weight {tuple(w.shape)} does not match input width {K}")
+        bias = None if bias is None else f32(bias, "bias")
+        r2 = None if resid is None else f32(resid, "resid").reshape(-1, N)
+        out = torch.empty((M, N), device=a.device, dtype=torch.float32)
+        call("xggm_linear_fwd", ptr(a2), ptr(w), ptr(bias), ptr(r2), ptr(out), M, N, K)
+        ctx.save_for_backward(a2, w)
+        ctx.has_bias, ctx.has_resid, ctx.in_shape = bias is not None, resid is not None, a.shape
+        return out.reshape(*a.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, g):
+        a2, w = ctx.saved_tensors
+        M, K = a2.shape
+        N = w.shape[0]
+        g2 = f32(g).reshape(M, N)
+        ga = gw = gb = gr = None
+        if ctx.needs_input_grad[0]:
+            ga = torch.empty_like(a2)
+            call("xggm_linear_bwd_input", ptr(g2), ptr(w), ptr(ga), M, N, K, 0)
+            ga = ga.reshape(ctx.in_shape)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            gw = torch.empty_like(w)
+            gb = torch.empty(N, device=w.device, dtype=torch.float32) if ctx.has_bias else None
+            call("xggm_linear_bwd_weight", ptr(g2), ptr(a2), ptr(gw), ptr(gb), M, N, K)
+        if ctx.has_resid and ctx.needs_input_grad[3]:
+            gr = g
+        return ga, gw, gb, gr
+
+
+def linear(a, w, bias=None, resid=None):
+    """a w^T + bias + resid through the library's GEMM engine."""
+    return _Linear.apply(a, w, bias, resid)
+
+
+# ---------------------------------------------------------------------------
+# message passing
+# ---------------------------------------------------------------------------
+class _AdjApply(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, adj, x, alpha0, alpha_dev, self_w):
+        adj, x = f32(adj, "adj"), f32(x, "x")
+        B, N, H = x.shape
+        if adj.shape != (B, N, N):
+            raise RuntimeError(f"xggm_b200.adj_apply: adj {tuple(adj.shape)} vs x {tuple(x.shape)}")
+        al = None if alpha_dev is None else f32(alpha_dev, "alpha")
+        out = torch.empty_like(x)
+        call("xggm_adj_apply_fwd", ptr(adj), ptr(x), ptr(out), B, N, H, float(alpha0), ptr(al), float(self_w))
+        ctx.save_for_backward(adj, x, al)
+        ctx.cfg = (float(alpha0), float(self_w))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        adj, x, al = ctx.saved_tensors
+        alpha0, self_w = ctx.cfg
+        B, N, H = x.shape
+        g = f32(g)
+        gx = torch.empty_like(x)
+        graw = torch.empty_like(adj)
+        call("xggm_adj_apply_bwd", ptr(adj), ptr(x), ptr(g), ptr(gx), ptr(graw), B, N, H, alpha0, ptr(al),
+             self_w, 0)
+        alpha = alpha0 if al is None else alpha0 + al
+        gadj = graw * alpha
+        gal = None
+        if al is not None and ctx.needs_input_grad[3]:
+            gal = (graw * adj).sum().reshape(al.shape)
+        return gadj, gx, None, gal, None
+
+
+def adj_apply(adj, x, alpha0=1.0, alpha_dev=None, self_w=0.0):
+    """self_w*x + (alpha0 + alpha_dev) * adj @ x."""
+    return _AdjApply.apply(adj, x, alpha0, alpha_dev, self_w)
+
+
+# ---------------------------------------------------------------------------
+# row ops
+# ---------------------------------------------------------------------------
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u, gamma, beta, eps):
+        u2 = f32(u, "input").reshape(-1, u.shape[-1])
+        gamma, beta = f32(gamma, "weight"), f32(beta, "bias")
+        M, H = u2.shape
+        h = torch.empty_like(u2)
+        xhat = torch.empty_like(u2)
+        rstd = torch.empty(M, device=u.device, dtype=torch.float32)
+        call("xggm_layernorm_fwd", ptr(u2), ptr(gamma), ptr(beta), ptr(h), ptr(xhat), ptr(rstd), M, H, float(eps))
+        ctx.save_for_backward(xhat, rstd, gamma)
+        return h.reshape(u.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        xhat, rstd, gamma = ctx.saved_tensors
+        M, H = xhat.shape
+        g2 = f32(g).reshape(M, H)
+        gu = torch.empty_like(xhat)
+        gg = torch.zeros(H, device=g.device, dtype=torch.float32)
+        gb = torch.zeros(H, device=g.device, dtype=torch.float32)
+        call("xggm_layernorm_bwd", ptr(g2), ptr(xhat), ptr(rstd), ptr(gamma), ptr(gu), ptr(gg), ptr(gb), M, H)
+        return gu.reshape(g.shape), gg, gb, None
+
+
+def layer_norm(u, gamma, beta, eps=LN_EPS):
+    return _LayerNorm.apply(u, gamma, beta, eps)
+
+
+class _GeluLnDrop(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, gamma, beta, keep, scale, eps):
+        z2 = f32(z, "input").reshape(-1, z.shape[-1])
+        gamma, beta = f32(gamma, "weight"), f32(beta, "bias")
+        keep = _u8(keep)
+        M, H = z2.shape
+        out = torch.empty_like(z2)
+        mean = torch.empty(M, device=z.device, dtype=torch.float32)
+        rstd = torch.empty(M, device=z.device, dtype=torch.float32)
+        call("xggm_gelu_ln_drop_fwd", ptr(z2), ptr(gamma), ptr(beta), ptr(keep), float(scale), ptr(out),
+             ptr(mean), ptr(rstd), M, H, float(eps), 0)
+        ctx.save_for_backward(z2, mean, rstd, gamma, keep)
+        ctx.scale = float(scale)
+        return out.reshape(z.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        z2, mean, rstd, gamma, keep = ctx.saved_tensors
+        M, H = z2.shape
+        g2 = f32(g).reshape(M, H)
+        gz = torch.empty_like(z2)
+        gg = torch.zeros(H, device=g.device, dtype=torch.float32)
+        gb = torch.zeros(H, device=g.device, dtype=torch.float32)
+        call("xggm_gelu_ln_drop_bwd", ptr(g2), ptr(z2), ptr(mean), ptr(rstd), ptr(gamma), ptr(keep), ctx.scale,
+             ptr(gz), ptr(gg), ptr(gb), M, H)
+        return gz.reshape(g.shape), gg, gb, None, None, None
+
+
+def gelu_ln_drop(z, gamma, beta, keep=None, drop_p=0.0, eps=LN_EPS):
+    """dropout(LayerNorm(GeLU_erf(z))) with an explicit keep-mask (None = no dropout)."""
+    scale = 1.0 / (1.0 - drop_p) if keep is not None else 1.0
+    return _GeluLnDrop.apply(z, gamma, beta, keep, scale, eps)
+
+
+# ---------------------------------------------------------------------------
+# adjacency regeneration
+# ---------------------------------------------------------------------------
+class _AdjRegen(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, squash):
+        x = f32(x, "x")
+        B, N, H = x.shape
+        adj = torch.empty((B, N, N), device=x.device, dtype=torch.float32)
+        S = torch.empty_like(adj)
+        amax = torch.empty((B, N), device=x.device, dtype=torch.int32)
+        call("xggm_adj_regen_fwd", ptr(x), ptr(adj), ptr(S), ptr(amax), B, N, H, int(squash))
+        ctx.save_for_backward(x, S, amax)
+        ctx.squash = int(squash)
+        ctx.mark_non_differentiable(amax)
+        return adj, amax
+
+    @staticmethod
+    def backward(ctx, g, _g_amax):
+        x, S, amax = ctx.saved_tensors
+        B, N, H = x.shape
+        g = f32(g)
+        gx = torch.empty_like(x)
+        work = torch.empty_like(S)
+        call("xggm_adj_regen_bwd", ptr(g), ptr(x), ptr(S), ptr(amax), ptr(gx), ptr(work), B, N, H, ctx.squash, 0)
+        return gx, None
+
+
+def adj_regen(x, squash=True, return_argmax=False):
+    """sigmoid(x x^T / colmax) with zero diagonal (ggm.py:225-228)."""
+    adj, amax = _AdjRegen.apply(x, squash)
+    return (adj, amax) if return_argmax else adj
+
+
+# ---------------------------------------------------------------------------
+# whole GCN / GIN layer
+# ---------------------------------------------------------------------------
+class _GnnLayer(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, kind, n_convs, drop_p, keeps, x, adj, *params):
+        x, adj = f32(x, "x"), f32(adj, "adj")
+        B, N, H = x.shape
+        if adj.shape != (B, N, N):
+            raise RuntimeError(f"xggm_b200: adj {tuple(adj.shape)} does not match x {tuple(x.shape)}")
+        per_conv = 3 if kind == 0 else 5
+        n_cp = per_conv * n_convs
+        params = [f32(p, "parameter") for p in params]
+        if len(params) != n_cp + 4 * (n_convs + 1):
+            raise RuntimeError("xggm_b200: wrong number of layer parameters")
+        cp, hp = params[:n_cp], params[n_cp:]
+        keeps = None if keeps is None else [_u8(k) for k in keeps]
+        if keeps is not None and (len(keeps) != n_convs + 1 or any(k.numel() != B * N * H for k in keeps)):
+            raise RuntimeError("xggm_b200: need one [B,N,H] keep-mask per read-out head")
+        lib = _lib.load()
+        n_saved = lib.xggm_gnn_saved_floats(kind, B, N, H, n_convs)
+        n_work = lib.xggm_gnn_work_floats(kind, B, N, H, n_convs)
+        saved = torch.empty(max(n_saved, 1), device=x.device, dtype=torch.float32)
+        work = torch.empty(max(n_work, 1), device=x.device, dtype=torch.float32)
+        out = torch.empty_like(x)
+        cpt, hpt = ptr_table(cp), ptr_table(hp)
+        kt = None if keeps is None else ptr_table(keeps)
+        call("xggm_gnn_fwd", kind, ptr(x), ptr(adj), cpt, hpt, kt, float(drop_p), ptr(out), ptr(saved),
+             ptr(work), B, N, H, n_convs)
+        ctx.save_for_backward(x, adj, saved, *params)
+        ctx.keeps = keeps
+        ctx.cfg = (kind, n_convs, float(drop_p), n_cp)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, adj, saved, *params = ctx.saved_tensors
+        kind, n_convs, drop_p, n_cp = ctx.cfg
+        B, N, H = x.shape
+        cp, hp = params[:n_cp], params[n_cp:]
+        g = f32(g)
+        lib = _lib.load()
+        work = torch.empty(max(lib.xggm_gnn_work_floats(kind, B, N, H, n_convs), 1), device=x.device,
+                           dtype=torch.float32)
+        gx = torch.empty_like(x)
+        gadj = torch.empty_like(adj)
+        grads = [torch.empty_like(p) for p in params]
+        kt = None if ctx.keeps is None else ptr_table(ctx.keeps)
+        call("xggm_gnn_bwd", kind, ptr(g), ptr(x), ptr(adj), ptr_table(cp), ptr_table(hp), kt, drop_p,
+             ptr(saved), ptr(work), ptr(gx), ptr(gadj), ptr_table(grads[:n_cp]), ptr_table(grads[n_cp:]),
+             B, N, H, n_convs)
+        return (None, None, None, None, gx, gadj, *grads)
+
+
+def gnn_layer(kind, x, adj, conv_params, head_params, keeps=None, drop_p=0.5):
+    """One GCN (kind='GCN') or GIN (kind='GIN') layer: conv chain + jump-knowledge heads.
+    conv_params / head_params are flat lists in the order documented in xggm_b200.h."""
+    k = KIND[kind]
+    per_conv = 3 if k == 0 else 5
+    n_convs = len(conv_params) // per_conv
+    return _GnnLayer.apply(k, n_convs, drop_p, keeps, x, adj, *conv_params, *head_params)
+
+
+# ---------------------------------------------------------------------------
+# GAT attention
+# ---------------------------------------------------------------------------
+class _GatAttn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, a, adj, slope, apply_elu):
+        h, adj = f32(h, "h"), f32(adj, "adj")
+        ctx.a_shape = a.shape
+        a = f32(a, "attn weight").reshape(-1)
+        B, N, H = h.shape
+        if a.numel() != 2 * H:
+            raise RuntimeError("xggm_b200.gat_attn: attention vector must have 2*H entries")
+        out = torch.empty_like(h)
+        pre = torch.empty_like(h)
+        att = torch.empty((B, N, N), device=h.device, dtype=torch.float32)
+        call("xggm_gat_attn_fwd", ptr(h), ptr(a), ptr(adj), ptr(out), ptr(att), ptr(pre), B, N, H, float(slope),
+             int(apply_elu))
+        ctx.save_for_backward(h, a, adj, att, pre)
+        ctx.slope, ctx.apply_elu = float(slope), int(apply_elu)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        h, a, adj, att, pre = ctx.saved_tensors
+        B, N, H = h.shape
+        g = f32(g)
+        gh = torch.empty_like(h)
+        ga = torch.zeros_like(a)
+        work = torch.empty(B * N * H + B * N * N, device=h.device, dtype=torch.float32)
+        call("xggm_gat_attn_bwd", ptr(g), ptr(h), ptr(a), ptr(adj), ptr(att), ptr(pre), ptr(gh), ptr(ga),
+             ptr(work), B, N, H, ctx.slope, ctx.apply_elu)
+        return gh, ga.reshape(ctx.a_shape), None, None, None
+
+
+def gat_attn(h, a, adj, slope=0.2, apply_elu=True):
+    """Masked dense attention of GATConv on already-projected features h (gat.py:31-49)."""
+    return _GatAttn.apply(h, a, adj, slope, apply_elu)
+
+
+class _Gelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = f32(x, "x")
+        y = torch.empty_like(x)
+        call("xggm_gelu_fwd", ptr(x), ptr(y), x.numel())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        g = f32(g)
+        gx = torch.empty_like(x)
+        call("xggm_gelu_bwd", ptr(g), ptr(x), ptr(gx), x.numel())
+        return gx
+
+
+def gelu(x):
+    """Exact-erf GeLU (src/lxrt/modeling.py:116-124)."""
+    return _Gelu.apply(x)
+
+
+class _MaskScale(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, keep, scale):
+        x, keep = f32(x, "x"), _u8(keep)
+        y = torch.empty_like(x)
+        call("xggm_mask_scale", ptr(x), ptr(keep), float(scale), ptr(y), x.numel())
+        ctx.save_for_backward(keep)
+        ctx.scale = float(scale)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (keep,) = ctx.saved_tensors
+        g = f32(g)
+        gx = torch.empty_like(g)
+        call("xggm_mask_scale", ptr(g), ptr(keep), ctx.scale, ptr(gx), g.numel())
+        return gx, None, None
+
+
+def dropout(x, p, training):
+    """F.dropout with a library-generated (or injected) keep-mask."""
+    if not training or p == 0.0:
+        return x
+    keep = keep_mask(x.shape, p, x.device)
+    return _MaskScale.apply(x, keep, 1.0 / (1.0 - p))
+
+
+# ---------------------------------------------------------------------------
+# trainer glue
+# ---------------------------------------------------------------------------
+class _StripDiag(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a):
+        a = f32(a, "adj")
+        B, N, _ = a.shape
+        out = torch.empty_like(a)
+        call("xggm_strip_diag", ptr(a), ptr(out), B, N)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = f32(g)
+        out = torch.empty_like(g)
+        call("xggm_strip_diag", ptr(g), ptr(out), g.shape[0], g.shape[1])
+        return out
+
+
+def strip_diag(a):
+    return _StripDiag.apply(a)
+
+
+class _TriuScatter(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v, n):
+        v = f32(v, "v")
+        B = v.shape[0]
+        if v.shape[1] != n * (n - 1) // 2:
+            raise RuntimeError(f"xggm_b200.triu_scatter: need {n * (n - 1) // 2} values per graph, got {v.shape[1]}")
+        adj = torch.empty((B, n, n), device=v.device, dtype=torch.float32)
+        call("xggm_triu_scatter_fwd", ptr(v), ptr(adj), B, n)
+        ctx.n = n
+        return adj
+
+    @staticmethod
+    def backward(ctx, g):
+        g = f32(g)
+        B, n = g.shape[0], ctx.n
+        gv = torch.empty((B, n * (n - 1) // 2), device=g.device, dtype=torch.float32)
+        call("xggm_triu_scatter_bwd", ptr(g), ptr(gv), B, n)
+        return gv, None
+
+
+def triu_scatter(v, n):
+    return _TriuScatter.apply(v, n)
+
+
+class _EdgeNoise(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, adj, randn, sigma):
+        adj, randn = f32(adj, "adj"), f32(randn, "randn")
+        B, N, _ = adj.shape
+        noisy, target = torch.empty_like(adj), torch.empty_like(adj)
+        call("xggm_edge_noise", ptr(adj), ptr(randn), float(sigma), ptr(noisy), ptr(target), B, N)
+        ctx.mark_non_differentiable(target)
+        return noisy, target
+
+    @staticmethod
+    def backward(ctx, g, _gt):
+        return g, None, None
+
+
+class _FeatNoise(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f, randn, sigma):
+        f, randn = f32(f, "feats"), f32(randn, "randn")
+        B, N, H = randn.shape
+        bcast = f.dim() == 2
+        noisy, target = torch.empty_like(randn), torch.empty_like(randn)
+        call("xggm_feat_noise", ptr(f), ptr(randn), float(sigma), ptr(noisy), ptr(target), B, N, H, int(bcast))
+        ctx.bcast = bcast
+        ctx.mark_non_differentiable(target)
+        return noisy, target
+
+    @staticmethod
+    def backward(ctx, g, _gt):
+        if not ctx.bcast:
+            return g, None, None
+        g = f32(g)
+        B, N, H = g.shape
+        out = torch.empty((B, H), device=g.device, dtype=torch.float32)
+        call("xggm_sum_nodes", ptr(g), ptr(out), B, N, H)
+        return out, None, None
+
+
+class _ScoreMse(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, score, target, sigma):
+        score, target = f32(score, "score"), f32(target, "target")
+        loss = torch.empty(1, device=score.device, dtype=torch.float32)
+        call("xggm_score_mse_fwd", ptr(score), ptr(target), float(sigma), ptr(loss), score.numel())
+        ctx.save_for_backward(score, target)
+        ctx.sigma = float(sigma)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        score, target = ctx.saved_tensors
+        g = f32(g).reshape(1)
+        gs = torch.empty_like(score)
+        call("xggm_score_mse_bwd", ptr(score), ptr(target), ptr(g), ctx.sigma, ptr(gs), score.numel())
+        return gs, None, None
+
+
+class _SymKl(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        x, y = f32(x, "x"), f32(y, "y")
+        if x.shape != y.shape:
+            raise RuntimeError("xggm_b200.sym_kl: shape mismatch")
+        C = x.shape[-1]
+        R = x.numel() // C
+        loss = torch.empty(1, device=x.device, dtype=torch.float32)
+        call("xggm_sym_kl_fwd", ptr(x), ptr(y), ptr(loss), R, C)
+        ctx.save_for_backward(x, y)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        C = x.shape[-1]
+        R = x.numel() // C
+        g = f32(g).reshape(1)
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gy = torch.empty_like(y) if ctx.needs_input_grad[1] else None
+        call("xggm_sym_kl_bwd", ptr(x), ptr(y), ptr(g), ptr(gx), ptr(gy), R, C)
+        return gx, gy
+
+
+class _FuseReadout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xp, nodes):
+        xp, nodes = f32(xp, "x"), f32(nodes, "nodes")
+        B, N, H = nodes.shape
+        out = torch.empty((B, 2 * H), device=xp.device, dtype=torch.float32)
+        call("xggm_fuse_readout_fwd", ptr(xp), ptr(nodes), ptr(out), B, N, H)
+        ctx.save_for_backward(out)
+        ctx.shape = (B, N, H)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (out,) = ctx.saved_tensors
+        B, N, H = ctx.shape
+        g = f32(g)
+        gxp = torch.empty((B, H), device=g.device, dtype=torch.float32)
+        gn = torch.empty((B, N, H), device=g.device, dtype=torch.float32)
+        call("xggm_fuse_readout_bwd", ptr(g), ptr(out), ptr(gxp), ptr(gn), B, N, H, 0)
+        return gxp, gn
+
+
+def fuse_readout(xp, nodes):
+    """cat[x, tanh(mean_n nodes)] (src/vqa/vqacpv2.py:216-218)."""
+    return _FuseReadout.apply(xp, nodes)
+
+
+class _Sigmoid(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = f32(x, "x")
+        y = torch.empty_like(x)
+        call("xggm_sigmoid_fwd", ptr(x), ptr(y), x.numel())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        g = f32(g)
+        gx = torch.empty_like(y)
+        call("xggm_sigmoid_bwd", ptr(g), ptr(y), ptr(gx), y.numel())
+        return gx
+
+
+def sigmoid(x):
+    return _Sigmoid.apply(x)
+
+
+# ---------------------------------------------------------------------------
+# dropout keep-masks (Philox, generated on the device by the library)
+# ---------------------------------------------------------------------------
+_mask_calls = 0
+_mask_feed = []
+
+
+def keep_mask(shape, p, device):
+    """uint8 keep-mask: injected (parity runs, see inject_keep_masks) or Philox-generated
+    keyed by (torch.initial_seed(), call counter) -- deterministic under torch.manual_seed."""
+    global _mask_calls
+    if _mask_feed:
+        m = _mask_feed.pop(0)
+        if tuple(m.shape) != tuple(shape):
+            raise RuntimeError(f"xggm_b200: injected keep-mask has shape {tuple(m.shape)}, need {tuple(shape)}")
+        return _u8(m.to(device))
+    m = torch.empty(shape, device=device, dtype=torch.uint8)
+    _lib.check_device(m)
+    _mask_calls += 1
+    call("xggm_keep_mask", ptr(m), m.numel(), float(p), torch.initial_seed() & (2 ** 64 - 1), _mask_calls)
+    return m
+
+
+class inject_keep_masks:
+    """Context manager: the next dropout sites consume these masks in call order
+    (what oracle/make_golden.py does to the reference's F.dropout)."""
+
+    def __init__(self, masks):
+        self.masks = list(masks)
+
+    def __enter__(self):
+        _mask_feed.extend(self.masks)
+        return self
+
+    def __exit__(self, *exc):
+        left = len(_mask_feed)
+        _mask_feed.clear()
+        if exc[0] is None and left:
+            raise RuntimeError(f"xggm_b200: {left} injected keep-masks were not consumed")
+        return False

@@ -1,0 +1,53 @@
+"""Trainer-side glue of the GGM step, under the reference's own function names.
+
+  add_edge_noise / add_feature_noise  = add_*_noise_v2, src/module/graph_utils.py:144-168
+                                        (the aliases the trainers import, src/vqa/vqacpv2.py:18-19)
+  loss_func / compute_kl_loss         = src/vqa/vqacpv2.py:48-61 (= src/gqa/gqa_ood.py:48-61)
+  strip_diag / triu_scatter           = src/vqa/vqacpv2.py:188 / :195-199
+
+The Gaussian draw itself stays ``torch.randn_like`` (same generator stream as the
+reference on the same device); everything after it is one fused kernel.
+"""
+import torch
+
+from . import functional as XF
+
+strip_diag = XF.strip_diag
+triu_scatter = XF.triu_scatter
+fuse_readout = XF.fuse_readout
+
+
+def add_edge_noise_v2(adjs, sigma=0.2, randn=None):
+    assert isinstance(adjs, torch.Tensor)
+    if randn is None:
+        randn = torch.randn_like(adjs)
+    return XF._EdgeNoise.apply(adjs, randn, sigma)
+
+
+def add_feature_noise_v2(feats, sigma=0.2, randn=None, n_nodes=None):
+    """feats [B,N,H]; or [B,H] with ``n_nodes`` to perturb N broadcast copies of each row
+    (node_fc on 36 identical rows, src/vqa/vqacpv2.py:228-231) without materialising them."""
+    assert isinstance(feats, torch.Tensor)
+    if feats.dim() == 2:
+        if n_nodes is None and randn is None:
+            raise RuntimeError("xggm_b200: n_nodes is required for broadcast [B,H] features")
+        shape = (feats.shape[0], n_nodes if randn is None else randn.shape[1], feats.shape[1])
+    else:
+        shape = feats.shape
+    if randn is None:
+        randn = torch.randn(shape, device=feats.device, dtype=feats.dtype)
+    return XF._FeatNoise.apply(feats, randn, sigma)
+
+
+add_edge_noise = add_edge_noise_v2
+add_feature_noise = add_feature_noise_v2
+
+
+def loss_func(score, grad_log_q_noise, sigma=0.2):
+    """Score-matching loss: 0.5 sigma^2 mean_b sum_{last two dims}(score-target)^2 / (R*C)."""
+    return XF._ScoreMse.apply(score, grad_log_q_noise, sigma)
+
+
+def compute_kl_loss(x, y):
+    """Symmetric KL between the last-dim softmaxes of x and y, mean over all elements."""
+    return XF._SymKl.apply(x, y)

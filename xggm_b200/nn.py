@@ -1,0 +1,294 @@
+"""nn.Module boundary of the X-GGM graph block.
+
+Class names, constructor signatures, sub-module attribute names and therefore
+``state_dict`` keys/shapes are those of the reference
+(src/module/{gcn,gin,gat}.py, src/module/graph_generative_modeling.py), so the
+LXMERT-based VQA-CP v2 / GQA-OOD containers can swap these in and reference
+checkpoints load unchanged.  ``nn.Linear`` / ``nn.LayerNorm`` instances are used
+as *parameter holders only* (same names, same default initialisation); every
+forward pass below runs the library's CUDA kernels via ``xggm_b200.functional``.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import functional as XF
+
+
+class GeLU(nn.Module):
+    """Exact-erf GeLU (reference: src/lxrt/modeling.py:127-140)."""
+
+    def forward(self, x):
+        return XF.gelu(x)
+
+
+def _head(in_dim, out_dim):
+    # Linear -> GeLU -> LayerNorm, indices 0/1/2 as in src/module/gcn.py:44-47
+    return nn.Sequential(nn.Linear(in_dim, out_dim), GeLU(), nn.LayerNorm(out_dim))
+
+
+def _head_params(seq):
+    return [seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias]
+
+
+def _check_uniform(input_dim, hidden_dims, n_layers, who):
+    dims = [input_dim] + list(hidden_dims[:max(n_layers, 1)]) + [hidden_dims[-2], hidden_dims[-1]]
+    if any(d != input_dim for d in dims):
+        raise NotImplementedError(
+            f"xggm_b200.{who}: only equal feature widths are supported (the reference generators "
+            f"build hidden_dims=[H, H]; the residual in GCNConv requires it anyway), got {dims}")
+
+
+def _head_forward(seq, h, keep=None, drop_p=0.0):
+    z = XF.linear(h, seq[0].weight, seq[0].bias)
+    return XF.gelu_ln_drop(z, seq[2].weight, seq[2].bias, keep, drop_p, seq[2].eps)
+
+
+# ---------------------------------------------------------------------------
+# GCN  (reference: src/module/gcn.py)
+# ---------------------------------------------------------------------------
+class GCNConv(nn.Module):
+    """LN(x + dropout(W_ctx (adj @ x))) -- src/module/gcn.py:10-29."""
+
+    def __init__(self, dim_hidden, dropout=0.0):
+        super().__init__()
+        self.ctx_layer = nn.Linear(dim_hidden, dim_hidden, bias=False)
+        self.layer_norm = nn.LayerNorm(dim_hidden)
+        self.dropout = nn.Dropout(p=dropout)
+
+    def forward(self, x, adj):
+        agg = XF.adj_apply(adj, x)
+        if self.dropout.p > 0.0 and self.training:
+            u = x + XF.dropout(XF.linear(agg, self.ctx_layer.weight), self.dropout.p, True)
+        else:
+            u = XF.linear(agg, self.ctx_layer.weight, None, x)
+        return XF.layer_norm(u, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps)
+
+
+class GCN(nn.Module):
+    """Conv chain + jump-knowledge read-out -- src/module/gcn.py:32-77."""
+
+    def __init__(self, input_dim, hidden_dims, n_layers, dropout=0.5):
+        super().__init__()
+        _check_uniform(input_dim, hidden_dims, n_layers, "GCN")
+        self.dropout_p = dropout
+        self.gnn_layers = nn.ModuleList(GCNConv(input_dim) for _ in range(n_layers))
+        self.linear_prediction = nn.ModuleList(_head(input_dim, input_dim) for _ in range(n_layers + 1))
+
+    def _flat_params(self):
+        cp, hp = [], []
+        for conv in self.gnn_layers:
+            cp += [conv.ctx_layer.weight, conv.layer_norm.weight, conv.layer_norm.bias]
+        for seq in self.linear_prediction:
+            hp += _head_params(seq)
+        return cp, hp
+
+    def forward(self, x, adj):
+        cp, hp = self._flat_params()
+        keeps = None
+        if self.training and self.dropout_p > 0.0:
+            keeps = [XF.keep_mask(x.shape, self.dropout_p, x.device) for _ in self.linear_prediction]
+        return XF.gnn_layer("GCN", x, adj, cp, hp, keeps, self.dropout_p)
+
+
+# ---------------------------------------------------------------------------
+# GIN  (reference: src/module/gin.py)
+# ---------------------------------------------------------------------------
+class GINConv(nn.Module):
+    """LN(GeLU(Linear(X + ((1+eps) A) @ X))) -- src/module/gin.py:10-34."""
+
+    def __init__(self, input_dim, hidden_dim):
+        super().__init__()
+        self.eps = nn.Parameter(torch.zeros(1))
+        self.linear = _head(input_dim, hidden_dim)
+
+    def forward(self, X, A):
+        pre = XF.adj_apply(A, X, 1.0, self.eps, 1.0)
+        return _head_forward(self.linear, pre)
+
+
+class GIN(nn.Module):
+    """src/module/gin.py:37-87."""
+
+    def __init__(self, input_dim, hidden_dims, n_layers, dropout=0.5):
+        super().__init__()
+        _check_uniform(input_dim, hidden_dims, n_layers, "GIN")
+        self.dropout_p = dropout
+        self.gnn_convs = nn.ModuleList(GINConv(input_dim, input_dim) for _ in range(n_layers))
+        self.linear_prediction = nn.ModuleList(_head(input_dim, input_dim) for _ in range(n_layers + 1))
+
+    def _flat_params(self):
+        cp, hp = [], []
+        for conv in self.gnn_convs:
+            cp += [conv.eps] + _head_params(conv.linear)
+        for seq in self.linear_prediction:
+            hp += _head_params(seq)
+        return cp, hp
+
+    def forward(self, X, A):
+        cp, hp = self._flat_params()
+        keeps = None
+        if self.training and self.dropout_p > 0.0:
+            keeps = [XF.keep_mask(X.shape, self.dropout_p, X.device) for _ in self.linear_prediction]
+        return XF.gnn_layer("GIN", X, A, cp, hp, keeps, self.dropout_p)
+
+
+# ---------------------------------------------------------------------------
+# GAT  (reference: src/module/gat.py)
+# ---------------------------------------------------------------------------
+class GATConv(nn.Module):
+    """Dense masked attention -- src/module/gat.py:6-49.  The [B,N,N,2H] concat tensor of the
+    reference is never built: a.[h_i || h_j] = a1.h_i + a2.h_j is evaluated per graph in smem."""
+
+    def __init__(self, dim_input, dim_hidden, dropout=0.5, alpha=0.2, concat=True):
+        super().__init__()
+        self.dropout = dropout
+        self.concat = concat
+        self.dim_hidden = dim_hidden
+        self.alpha = alpha
+        self.linear_layer = nn.Linear(dim_input, dim_hidden, bias=False)
+        self.attn_layer = nn.Linear(2 * dim_hidden, 1, bias=False)
+        self.reset_parameters()
+        self.leaky_relu = nn.LeakyReLU(alpha)
+
+    def reset_parameters(self):
+        gain = math.sqrt(2.0)  # nn.init.calculate_gain('relu'), src/module/gat.py:20-23
+        nn.init.xavier_normal_(self.linear_layer.weight, gain=gain)
+        nn.init.xavier_normal_(self.attn_layer.weight, gain=gain)
+
+    def forward(self, x, adj):
+        h = XF.linear(x, self.linear_layer.weight)
+        return XF.gat_attn(h, self.attn_layer.weight, adj, self.alpha, self.concat)
+
+
+class GAT(nn.Module):
+    """Input dropout + n_head GATConv, concatenated -- src/module/gat.py:52-79."""
+
+    def __init__(self, input_dim, hidden_dim, n_head, dropout=0.5, alpha=0.2, merge='cat'):
+        super().__init__()
+        self.dropout = dropout
+        self.merge = merge
+        self.gat_layers = nn.ModuleList(
+            GATConv(input_dim, hidden_dim, dropout=dropout, alpha=alpha, concat=True) for _ in range(n_head))
+
+    def forward(self, x, adj):
+        x = XF.dropout(x, self.dropout, self.training)
+        outs = [att(x, adj) for att in self.gat_layers]
+        if self.merge == 'cat':
+            return torch.cat(outs, dim=2)
+        return torch.mean(torch.stack(outs))  # as the reference (src/module/gat.py:77): a global mean
+
+
+# ---------------------------------------------------------------------------
+# generators  (reference: src/module/graph_generative_modeling.py)
+# ---------------------------------------------------------------------------
+class _Generator(nn.Module):
+    """x <- GNN_l(x, adj); adj <- sigmoid(x x^T / colmax) minus diagonal, per layer."""
+    squash = True
+
+    def __init__(self, n_layers, dropout):
+        super().__init__()
+        self.dropout_p = dropout
+        self.n_layers = n_layers
+
+    def forward(self, x, adj):
+        for layer in range(self.n_layers):
+            x = self.gnn_layers[layer](x, adj)
+            adj = XF.adj_regen(x, self.squash)
+        return x, adj
+
+
+class GCNGenerator(_Generator):
+    """ggm.py:199-233: n_layers x GCN(H, [H,H], n_layers=2)."""
+
+    def __init__(self, hidden_dim, n_layers, dropout=0.5):
+        super().__init__(n_layers, dropout)
+        self.act = nn.Sigmoid()
+        self.gnn_layers = nn.ModuleList(
+            GCN(hidden_dim, [hidden_dim, hidden_dim], 2, dropout=dropout) for _ in range(n_layers))
+
+
+class GINGenerator(_Generator):
+    """ggm.py:162-196: n_layers x GIN(H, [H,H], n_layers=1)."""
+
+    def __init__(self, hidden_dim, n_layers, dropout=0.5):
+        super().__init__(n_layers, dropout)
+        self.act = nn.Sigmoid()
+        self.gnn_layers = nn.ModuleList(
+            GIN(hidden_dim, [hidden_dim, hidden_dim], 1, dropout=dropout) for _ in range(n_layers))
+
+
+class GATGenerator(_Generator):
+    """ggm.py:236-269: n_layers x GAT(H, H, n_head=2).  As in the reference the 2-head concat
+    widens H -> 2H, so only n_layers=1 is shape-valid (layer 2 raises, here as there)."""
+
+    def __init__(self, hidden_dim, n_layers, dropout=0.5):
+        super().__init__(n_layers, dropout)
+        self.act = nn.Sigmoid()
+        self.gnn_layers = nn.ModuleList(GAT(hidden_dim, hidden_dim, n_head=2) for _ in range(n_layers))
+
+
+class EdgeGenerator(_Generator):
+    """ggm.py:100-130: GIN layers, adjacency regenerated WITHOUT the sigmoid; returns adj only."""
+    squash = False
+
+    def __init__(self, hidden_dim, n_layers, dropout=0.5):
+        super().__init__(n_layers, dropout)
+        self.gnn_layers = nn.ModuleList(
+            GIN(hidden_dim, [hidden_dim, hidden_dim], 1, dropout=dropout) for _ in range(n_layers))
+
+    def forward(self, x, adj):
+        return super().forward(x, adj)[1]
+
+
+class _PlainStack(nn.Module):
+    def __init__(self, n_layers, dropout):
+        super().__init__()
+        self.dropout_p = dropout
+        self.n_layers = n_layers
+
+    def forward(self, x, adj):
+        for layer in range(self.n_layers):
+            x = self.gnn_layers[layer](x, adj)
+        return x
+
+
+class NodeGenerator(_PlainStack):
+    """ggm.py:133-159."""
+
+    def __init__(self, hidden_dim, n_layers, dropout=0.5):
+        super().__init__(n_layers, dropout)
+        self.gnn_layers = nn.ModuleList(
+            GIN(hidden_dim, [hidden_dim, hidden_dim], 1, dropout=dropout) for _ in range(n_layers))
+
+
+class GinPlainEncoder(_PlainStack):
+    """ggm.py:15-40."""
+
+    def __init__(self, hidden_dim, n_layers=2, dropout=0.5):
+        super().__init__(n_layers, dropout)
+        self.gnn_layers = nn.ModuleList(
+            GIN(hidden_dim, [hidden_dim, hidden_dim], 1) for _ in range(n_layers))
+
+
+class GCNPlainEncoder(_PlainStack):
+    """ggm.py:43-68."""
+
+    def __init__(self, hidden_dim, n_layers=2, dropout=0.5):
+        super().__init__(n_layers, dropout)
+        self.gnn_layers = nn.ModuleList(
+            GCN(hidden_dim, [hidden_dim, hidden_dim], 1) for _ in range(n_layers))
+
+
+class Discriminator(nn.Module):
+    """ggm.py:71-82: Linear -> GeLU -> LayerNorm -> Linear on the flattened graph."""
+
+    def __init__(self, hidden_dim):
+        super().__init__()
+        self.model = nn.Sequential(nn.Linear(hidden_dim, 512), GeLU(), nn.LayerNorm(512), nn.Linear(512, 1))
+
+    def forward(self, x):
+        m = self.model
+        h = _head_forward(m, x.reshape(x.shape[0], -1))
+        return XF.linear(h, m[3].weight, m[3].bias)
