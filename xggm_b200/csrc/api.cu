@@ -248,22 +248,25 @@ int xggm_device_check(int device) {
 
 int xggm_linear_fwd(const float* a, const float* w, const float* bias, const float* resid,
                     float* out, int M, int N, int K, xggm_stream_t s) {
+    if (M == 0) return XGGM_OK;
     XGGM_REQUIRE(a && w && out && M >= 0 && N > 0 && K > 0);
     return gemm_simt(0, a, w, bias, resid, out, M, N, K, 0, as_stream(s));
 }
 int xggm_linear_bwd_input(const float* g, const float* w, float* ga, int M, int N, int K,
                           int accumulate, xggm_stream_t s) {
+    if (M == 0) return XGGM_OK;
     XGGM_REQUIRE(g && w && ga && M >= 0 && N > 0 && K > 0);
     return gemm_simt(1, g, w, nullptr, nullptr, ga, M, K, N, accumulate, as_stream(s));
 }
 int xggm_linear_bwd_weight(const float* g, const float* a, float* gw, float* gbias, int M, int N,
                            int K, xggm_stream_t s) {
-    XGGM_REQUIRE(g && a && gw && M >= 0 && N > 0 && K > 0);
+    XGGM_REQUIRE(gw && M >= 0 && N > 0 && K > 0);
     if (M == 0) {
         XGGM_CUDA_TRY(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)N * K, as_stream(s)));
         if (gbias) XGGM_CUDA_TRY(cudaMemsetAsync(gbias, 0, sizeof(float) * N, as_stream(s)));
         return XGGM_OK;
     }
+    XGGM_REQUIRE(g && a);
     XGGM_TRY(gemm_simt(2, g, a, nullptr, nullptr, gw, N, K, M, 0, as_stream(s)));
     if (gbias) XGGM_TRY(colsum(g, gbias, M, N, as_stream(s)));
     return XGGM_OK;
@@ -271,12 +274,14 @@ int xggm_linear_bwd_weight(const float* g, const float* a, float* gw, float* gbi
 
 int xggm_adj_apply_fwd(const float* adj, const float* x, float* out, int B, int N, int H,
                        float alpha0, const float* alpha_dev, float self_w, xggm_stream_t s) {
+    if (B == 0) return XGGM_OK;
     XGGM_REQUIRE(adj && x && out && B >= 0);
     return adj_apply(adj, x, out, B, N, H, alpha0, alpha_dev, self_w, false, 0, as_stream(s));
 }
 int xggm_adj_apply_bwd(const float* adj, const float* x, const float* gout, float* gx,
                        float* gadj_raw, int B, int N, int H, float alpha0, const float* alpha_dev,
                        float self_w, int accumulate_gx, xggm_stream_t s) {
+    if (B == 0) return XGGM_OK;
     XGGM_REQUIRE(adj && x && gout && gx && B >= 0);
     XGGM_TRY(adj_apply(adj, gout, gx, B, N, H, alpha0, alpha_dev, self_w, true, accumulate_gx, as_stream(s)));
     if (gadj_raw) XGGM_TRY(bmm_nt(gout, x, gadj_raw, B, N, H, 1.f, nullptr, 0, nullptr, nullptr, as_stream(s)));
@@ -285,23 +290,27 @@ int xggm_adj_apply_bwd(const float* adj, const float* x, const float* gout, floa
 
 int xggm_layernorm_fwd(const float* u, const float* gamma, const float* beta, float* h,
                        float* xhat, float* rstd, int M, int H, float eps, xggm_stream_t s) {
+    if (M == 0) return XGGM_OK;
     XGGM_REQUIRE(u && gamma && beta && h && M >= 0 && H > 0);
     return layernorm_fwd(u, gamma, beta, h, xhat, rstd, M, H, eps, as_stream(s));
 }
 int xggm_layernorm_bwd(const float* gh, const float* xhat, const float* rstd, const float* gamma,
                        float* gu, float* ggamma, float* gbeta, int M, int H, xggm_stream_t s) {
+    if (M == 0) return XGGM_OK;
     XGGM_REQUIRE(gh && xhat && rstd && gamma && gu && ggamma && gbeta && M >= 0 && H > 0);
     return layernorm_bwd(gh, xhat, rstd, gamma, gu, ggamma, gbeta, M, H, as_stream(s));
 }
 int xggm_gelu_ln_drop_fwd(const float* z, const float* gamma, const float* beta,
                           const uint8_t* keep, float scale, float* out, float* mean, float* rstd,
                           int M, int H, float eps, int accumulate, xggm_stream_t s) {
+    if (M == 0) return XGGM_OK;
     XGGM_REQUIRE(z && gamma && beta && out && M >= 0 && H > 0);
     return gelu_ln_drop_fwd(z, gamma, beta, keep, scale, out, mean, rstd, M, H, eps, accumulate, as_stream(s));
 }
 int xggm_gelu_ln_drop_bwd(const float* gout, const float* z, const float* mean, const float* rstd,
                           const float* gamma, const uint8_t* keep, float scale, float* gz,
                           float* ggamma, float* gbeta, int M, int H, xggm_stream_t s) {
+    if (M == 0) return XGGM_OK;
     XGGM_REQUIRE(gout && z && mean && rstd && gamma && gz && ggamma && gbeta && M >= 0 && H > 0);
     return gelu_ln_drop_bwd(gout, z, mean, rstd, gamma, keep, scale, gz, ggamma, gbeta, M, H, as_stream(s));
 }
@@ -347,52 +356,63 @@ int xggm_gnn_bwd(int kind, const float* gout, const float* x, const float* adj,
 
 int xggm_gat_attn_fwd(const float* h, const float* a, const float* adj, float* out, float* att,
                       float* pre, int B, int N, int H, float alpha, int apply_elu, xggm_stream_t s) {
+    if (B == 0) return XGGM_OK;
     XGGM_REQUIRE(h && a && adj && out && att && pre && B >= 0 && H > 0);
     return gat_attn_fwd(h, a, adj, out, att, pre, B, N, H, alpha, apply_elu, as_stream(s));
 }
 int xggm_gat_attn_bwd(const float* gout, const float* h, const float* a, const float* adj,
                       const float* att, const float* pre, float* gh, float* ga, float* work, int B,
                       int N, int H, float alpha, int apply_elu, xggm_stream_t s) {
+    if (B == 0) return XGGM_OK;
     XGGM_REQUIRE(gout && h && a && adj && att && pre && gh && ga && work && B >= 0 && H > 0);
     return gat_attn_bwd(gout, h, a, adj, att, pre, gh, ga, work, B, N, H, alpha, apply_elu, as_stream(s));
 }
 int xggm_gelu_fwd(const float* x, float* y, long long n, xggm_stream_t s) {
+    if (n == 0) return XGGM_OK;
     XGGM_REQUIRE(x && y && n >= 0);
     return gelu_fwd(x, y, n, as_stream(s));
 }
 int xggm_gelu_bwd(const float* gy, const float* x, float* gx, long long n, xggm_stream_t s) {
+    if (n == 0) return XGGM_OK;
     XGGM_REQUIRE(gy && x && gx && n >= 0);
     return gelu_bwd(gy, x, gx, n, as_stream(s));
 }
 int xggm_mask_scale(const float* x, const uint8_t* keep, float scale, float* y, long long n,
                     xggm_stream_t s) {
+    if (n == 0) return XGGM_OK;
     XGGM_REQUIRE(x && keep && y && n >= 0);
     return mask_scale(x, keep, scale, y, n, as_stream(s));
 }
 
 int xggm_strip_diag(const float* a, float* out, int B, int N, xggm_stream_t s) {
+    if (B == 0) return XGGM_OK;
     XGGM_REQUIRE(a && out && B >= 0 && N > 0);
     return strip_diag(a, out, B, N, as_stream(s));
 }
 int xggm_triu_scatter_fwd(const float* v, float* adj, int B, int N, xggm_stream_t s) {
+    if (B == 0) return XGGM_OK;
     XGGM_REQUIRE(v && adj && B >= 0 && N > 0);
     return triu_scatter_fwd(v, adj, B, N, as_stream(s));
 }
 int xggm_triu_scatter_bwd(const float* gadj, float* gv, int B, int N, xggm_stream_t s) {
+    if (B == 0) return XGGM_OK;
     XGGM_REQUIRE(gadj && gv && B >= 0 && N > 0);
     return triu_scatter_bwd(gadj, gv, B, N, as_stream(s));
 }
 int xggm_edge_noise(const float* adj, const float* randn, double sigma, float* noisy,
                     float* target, int B, int N, xggm_stream_t s) {
+    if (B == 0) return XGGM_OK;
     XGGM_REQUIRE(adj && randn && noisy && target && B >= 0 && N > 0 && sigma != 0.0);
     return edge_noise(adj, randn, (float)sigma, (float)(sigma * sigma), noisy, target, B, N, as_stream(s));
 }
 int xggm_feat_noise(const float* f, const float* randn, double sigma, float* noisy, float* target,
                     int B, int N, int H, int f_is_broadcast, xggm_stream_t s) {
+    if (B == 0) return XGGM_OK;
     XGGM_REQUIRE(f && randn && noisy && target && B >= 0 && N > 0 && H > 0 && sigma != 0.0);
     return feat_noise(f, randn, (float)sigma, (float)(sigma * sigma), noisy, target, B, N, H, f_is_broadcast, as_stream(s));
 }
 int xggm_sum_nodes(const float* g, float* out, int B, int N, int H, xggm_stream_t s) {
+    if (B == 0) return XGGM_OK;
     XGGM_REQUIRE(g && out && B >= 0 && N > 0 && H > 0);
     return sum_nodes(g, out, B, N, H, as_stream(s));
 }
@@ -403,6 +423,7 @@ int xggm_score_mse_fwd(const float* score, const float* target, double sigma, fl
 }
 int xggm_score_mse_bwd(const float* score, const float* target, const float* gloss, double sigma,
                        float* gscore, long long n_elem, xggm_stream_t s) {
+    if (n_elem == 0) return XGGM_OK;
     XGGM_REQUIRE(score && target && gloss && gscore && n_elem >= 0);
     return score_mse_bwd(score, target, gloss, (float)sigma, gscore, n_elem, as_stream(s));
 }
@@ -412,29 +433,35 @@ int xggm_sym_kl_fwd(const float* x, const float* y, float* loss, int R, int C, x
 }
 int xggm_sym_kl_bwd(const float* x, const float* y, const float* gloss, float* gx, float* gy,
                     int R, int C, xggm_stream_t s) {
+    if (R == 0) return XGGM_OK;
     XGGM_REQUIRE(x && y && gloss && R >= 0 && C > 0);
     return sym_kl_bwd(x, y, gloss, gx, gy, R, C, as_stream(s));
 }
 int xggm_fuse_readout_fwd(const float* xp, const float* nodes, float* out, int B, int N, int H,
                           xggm_stream_t s) {
+    if (B == 0) return XGGM_OK;
     XGGM_REQUIRE(xp && nodes && out && B >= 0 && N > 0 && H > 0);
     return fuse_readout_fwd(xp, nodes, out, B, N, H, as_stream(s));
 }
 int xggm_fuse_readout_bwd(const float* gout, const float* out, float* gxp, float* gnodes, int B,
                           int N, int H, int accumulate_gnodes, xggm_stream_t s) {
+    if (B == 0) return XGGM_OK;
     XGGM_REQUIRE(gout && out && gnodes && B >= 0 && N > 0 && H > 0);
     return fuse_readout_bwd(gout, out, gxp, gnodes, B, N, H, accumulate_gnodes, as_stream(s));
 }
 int xggm_sigmoid_fwd(const float* x, float* y, long long n, xggm_stream_t s) {
+    if (n == 0) return XGGM_OK;
     XGGM_REQUIRE(x && y && n >= 0);
     return sigmoid_fwd(x, y, n, as_stream(s));
 }
 int xggm_sigmoid_bwd(const float* gy, const float* y, float* gx, long long n, xggm_stream_t s) {
+    if (n == 0) return XGGM_OK;
     XGGM_REQUIRE(gy && y && gx && n >= 0);
     return sigmoid_bwd(gy, y, gx, n, as_stream(s));
 }
 int xggm_keep_mask(uint8_t* keep, long long n, float p, uint64_t seed, uint64_t stream_id,
                    xggm_stream_t s) {
+    if (n == 0) return XGGM_OK;
     XGGM_REQUIRE(keep && n >= 0);
     return keep_mask(keep, n, p, seed, stream_id, as_stream(s));
 }

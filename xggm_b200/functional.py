@@ -464,7 +464,7 @@ class _ScoreMse(torch.autograd.Function):
         g = f32(g).reshape(1)
         gs = torch.empty_like(score)
         call("xggm_score_mse_bwd", ptr(score), ptr(target), ptr(g), ctx.sigma, ptr(gs), score.numel())
-        return gs, None, None
+        return gs, (-gs if ctx.needs_input_grad[1] else None), None
 
 
 class _SymKl(torch.autograd.Function):
