@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define XGGM_ABI_VERSION 1
+#define XGGM_ABI_VERSION 2
 
 #define XGGM_OK 0
 #define XGGM_ERR_ARG (-1)         /* bad shape / NULL pointer / unsupported size */
@@ -53,17 +53,35 @@ int xggm_set_device(int device);
 int xggm_device_check(int device);
 
 /* ------------------------------------------------------------------------- *
- * Dense node projections  (nn.Linear: src/module/gcn.py:13,44; gin.py:14)
+ * Projection engine (process-wide setting; default XGGM_PREC_FP32)
+ *   XGGM_PREC_FP32      tcgen05 tensor cores, every fp32 operand split into bf16 hi+lo planes and
+ *                       multiplied in three passes (lo*hi + hi*lo + hi*hi, fp32 accumulation in
+ *                       TMEM): ~1e-5 relative error, inside the 1e-4 fp32 parity budget.
+ *   XGGM_PREC_BF16      tcgen05, operands rounded to bf16 once (single pass): the 2e-2 bf16 budget.
+ *   XGGM_PREC_FP32_SIMT exact fp32 FMA kernel (no tensor cores); also taken for shapes whose
+ *                       row pitch TMA cannot address (N or K not a multiple of 8).
  * ------------------------------------------------------------------------- */
+#define XGGM_PREC_FP32 0
+#define XGGM_PREC_BF16 1
+#define XGGM_PREC_FP32_SIMT 2
+int xggm_set_precision(int mode);
+int xggm_get_precision(void);
+
+/* ------------------------------------------------------------------------- *
+ * Dense node projections  (nn.Linear: src/module/gcn.py:13,44; gin.py:14)
+ * `work` is caller-owned scratch of xggm_linear_work_bytes(M,N,K) bytes (16-byte aligned) that
+ * receives the bf16 operand planes of the tcgen05 engine; NULL selects the exact SIMT kernel.
+ * ------------------------------------------------------------------------- */
+long long xggm_linear_work_bytes(int M, int N, int K);
 /* out[M,N] = a[M,K] w[N,K]^T + bias[N]? + resid[M,N]? */
 int xggm_linear_fwd(const float* a, const float* w, const float* bias, const float* resid,
-                    float* out, int M, int N, int K, xggm_stream_t s);
+                    float* out, int M, int N, int K, void* work, xggm_stream_t s);
 /* ga[M,K] (+)= g[M,N] w[N,K]   (accumulate != 0 adds into ga) */
 int xggm_linear_bwd_input(const float* g, const float* w, float* ga, int M, int N, int K,
-                          int accumulate, xggm_stream_t s);
+                          int accumulate, void* work, xggm_stream_t s);
 /* gw[N,K] = g[M,N]^T a[M,K];  gbias[N]? = column sums of g.  Overwrites. */
 int xggm_linear_bwd_weight(const float* g, const float* a, float* gw, float* gbias,
-                           int M, int N, int K, xggm_stream_t s);
+                           int M, int N, int K, void* work, xggm_stream_t s);
 
 /* ------------------------------------------------------------------------- *
  * Adjacency-weighted message passing

@@ -23,9 +23,12 @@ SIGNATURES = {
     "xggm_prof_read": [_vp, _vp, _vp],
     "xggm_set_device": [_i],
     "xggm_device_check": [_i],
-    "xggm_linear_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
-    "xggm_linear_bwd_input": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
-    "xggm_linear_bwd_weight": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "xggm_set_precision": [_i],
+    "xggm_get_precision": [],
+    "xggm_linear_work_bytes": [_i, _i, _i],
+    "xggm_linear_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp],
+    "xggm_linear_bwd_input": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "xggm_linear_bwd_weight": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp],
     "xggm_adj_apply_fwd": [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _f, _vp],
     "xggm_adj_apply_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _f, _i, _vp],
     "xggm_layernorm_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp],
@@ -61,7 +64,7 @@ SIGNATURES = {
     "xggm_keep_mask": [_vp, _ll, _f, _u64, _u64, _vp],
 }
 _RESTYPES = {"xggm_launch_count": C.c_ulonglong, "xggm_strerror": C.c_char_p, "xggm_last_cuda_error": C.c_char_p,
-             "xggm_gnn_saved_floats": _ll, "xggm_gnn_work_floats": _ll}
+             "xggm_gnn_saved_floats": _ll, "xggm_gnn_work_floats": _ll, "xggm_linear_work_bytes": _ll}
 
 _lib = None
 _checked_devices = set()
@@ -100,10 +103,26 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
-    if lib.xggm_abi_version() != 1:
+    if lib.xggm_abi_version() != 2:
         raise RuntimeError("libxggm_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib
+
+
+PRECISIONS = {"fp32": 0, "bf16": 1, "fp32_simt": 2}
+
+
+def set_precision(mode):
+    """Projection engine: 'fp32' (tcgen05, split-bf16 x3, default), 'bf16' (tcgen05, single pass),
+    'fp32_simt' (exact fp32 FMA kernel).  Process-wide."""
+    rc = load().xggm_set_precision(PRECISIONS[mode])
+    if rc != 0:
+        _raise(rc)
+
+
+def get_precision():
+    code = load().xggm_get_precision()
+    return {v: k for k, v in PRECISIONS.items()}[code]
 
 
 def _raise(code):

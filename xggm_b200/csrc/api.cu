@@ -3,6 +3,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace xggm {
@@ -11,6 +13,12 @@ namespace xggm {
 int gemm_simt(int op, const float* A, const float* Bm, const float* bias, const float* resid,
               float* C, int M, int N, int K, int accumulate, cudaStream_t st);
 int colsum(const float* g, float* out, int R, int C, cudaStream_t st);
+bool gemm_tc_supported(int M, int N, int K);
+int gemm_tc(bool a_mn, bool b_mn, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const __nv_bfloat16* b_hi,
+            const __nv_bfloat16* b_lo, const float* bias, const float* resid, float* C, int M, int N, int K,
+            int accumulate, int allow_split_k, int npass, cudaStream_t st);
+int split_planes(const float* const* src, __nv_bfloat16* const* hi, __nv_bfloat16* const* lo, const long long* n,
+                 int count, cudaStream_t st);
 int gemm_prof_enable(int on);
 int gemm_prof_read(double* total_ms, long long* launches, double* flops);
 int layernorm_fwd(const float*, const float*, const float*, float*, float*, float*, int, int, float, cudaStream_t);
@@ -51,74 +59,167 @@ void set_cuda_error(cudaError_t e, const char* where) {
 
 constexpr float LN_EPS = 1e-5f;  // nn.LayerNorm default (src/module/gcn.py:14,47)
 
-static inline long long al4(long long n) { return (n + 3) & ~3LL; }
+// chunk sizes are padded to 8 floats so that every bf16 plane starts 16-byte aligned (TMA)
+static inline long long al4(long long n) { return (n + 7) & ~7LL; }
+
+// ---- projection engine selection -------------------------------------------------
+// precision: XGGM_PREC_FP32 (tcgen05, split-bf16 x3), XGGM_PREC_BF16 (tcgen05, single pass),
+// XGGM_PREC_FP32_SIMT (exact fp32 FMA kernel).  Shapes TMA cannot address (row pitch not a
+// multiple of 16 bytes) always take the SIMT kernel.
+int g_precision = XGGM_PREC_FP32;
+
+typedef __nv_bfloat16 bf16;
+struct Operand {          // one GEMM operand: the fp32 tensor and (tcgen05 engine) its bf16 planes
+    const float* f32;
+    const bf16* hi;
+    const bf16* lo;
+};
+static inline bool use_tc(int M, int N, int K) {
+    return g_precision != XGGM_PREC_FP32_SIMT && gemm_tc_supported(M, N, K);
+}
+static inline int npass() { return g_precision == XGGM_PREC_BF16 ? 1 : 3; }
+// planes of an [n]-element fp32 array stored in a region of al4(n) floats: hi | lo
+static inline Operand planes_at(const float* f32, float* region, long long n) {
+    bf16* hi = reinterpret_cast<bf16*>(region);
+    return Operand{f32, hi, hi + al4(n) };
+}
+static int split_one(const Operand& o, long long n, cudaStream_t st) {
+    const float* src[1] = {o.f32};
+    bf16* hi[1] = {const_cast<bf16*>(o.hi)};
+    bf16* lo[1] = {const_cast<bf16*>(o.lo)};
+    return split_planes(src, hi, npass() == 3 ? lo : nullptr, &n, 1, st);
+}
+// out[M,N] = a[M,K] w[N,K]^T + bias + resid
+static int proj_fwd(bool tc, const Operand& a, const Operand& w, const float* bias, const float* resid,
+                    float* out, int M, int N, int K, cudaStream_t st) {
+    if (tc) return gemm_tc(false, false, a.hi, a.lo, w.hi, w.lo, bias, resid, out, M, N, K, 0, 0, npass(), st);
+    return gemm_simt(0, a.f32, w.f32, bias, resid, out, M, N, K, 0, st);
+}
+// ga[M,K] (+)= g[M,N] w[N,K]
+static int proj_dgrad(bool tc, const Operand& g, const Operand& w, float* ga, int M, int N, int K,
+                      int accumulate, cudaStream_t st) {
+    if (tc) return gemm_tc(false, true, g.hi, g.lo, w.hi, w.lo, nullptr, nullptr, ga, M, K, N, accumulate, 0, npass(), st);
+    return gemm_simt(1, g.f32, w.f32, nullptr, nullptr, ga, M, K, N, accumulate, st);
+}
+// gw[N,K] = g[M,N]^T a[M,K]
+static int proj_wgrad(bool tc, const Operand& g, const Operand& a, float* gw, int M, int N, int K,
+                      cudaStream_t st) {
+    if (tc) return gemm_tc(true, true, g.hi, g.lo, a.hi, a.lo, nullptr, nullptr, gw, N, K, M, 0, 1, npass(), st);
+    return gemm_simt(2, g.f32, a.f32, nullptr, nullptr, gw, N, K, M, 0, st);
+}
 
 // ---- saved-activation layout of one GCN / GIN layer ---------------------------
 struct GnnLayout {
-    long long MH, Mr;       // padded sizes of an [M,H] and an [M] chunk
+    long long MH, Mr, HH;   // padded sizes of an [M,H], an [M] and an [H,H] chunk
     int n_convs, n_heads, kind;
-    long long conv_stride, head_stride, head_base, total;
-    // GCN conv k: agg | xhat | h_next | rstd        GIN conv k: pre | z | h_next | mean | rstd
+    long long conv_stride, head_stride, head_base, xplanes, total;
+    // GCN conv k: agg | xhat | h_next | rstd | (pad) | P(agg) | P(h_next)
+    // GIN conv k: pre | z    | h_next | mean | rstd  | P(pre) | P(h_next)
     GnnLayout(int kind_, long long M, int H, int nc) : kind(kind_) {
         MH = al4(M * H);
         Mr = al4(M);
+        HH = al4((long long)H * H);
         n_convs = nc;
         n_heads = nc + 1;
-        conv_stride = (kind == XGGM_KIND_GCN) ? 3 * MH + Mr : 3 * MH + 2 * Mr;
+        conv_stride = 5 * MH + 2 * Mr;
         head_stride = MH + 2 * Mr;  // z | mean | rstd
         head_base = conv_stride * nc;
-        total = head_base + head_stride * n_heads;
+        xplanes = head_base + head_stride * n_heads;   // P(x)
+        total = xplanes + MH;
     }
-    long long conv(int k, int slot) const {  // slot indexes MH-sized chunks first, then M-sized
+    long long conv(int k, int slot) const {  // slots 0..2 fp32 [M,H]; 3,4 [M]; 5,6 plane regions
         const long long base = conv_stride * k;
-        return slot < 3 ? base + slot * MH : base + 3 * MH + (slot - 3) * Mr;
+        if (slot < 3) return base + slot * MH;
+        if (slot < 5) return base + 3 * MH + (slot - 3) * Mr;
+        return base + 3 * MH + 2 * Mr + (slot - 5) * MH;
     }
     long long head(int j, int slot) const {
         const long long base = head_base + head_stride * j;
         return slot == 0 ? base : base + MH + (slot - 1) * Mr;
     }
+    long long work_fwd() const { return MH + (2 * n_convs + 1) * HH; }
+    long long work_bwd() const { return 5 * MH + (2 * n_convs + 1) * HH; }
 };
+
+// weight planes for one layer live at the tail of the work buffer: conv k -> slot k, head j -> slot nc + j
+static int split_weights(int kind, const float* const* cp, const float* const* hp, float* wregion,
+                         const GnnLayout& L, int H, Operand* wconv, Operand* whead, bool tc, cudaStream_t st) {
+    const int nc = L.n_convs;
+    const float* src[16];
+    bf16* hi[16];
+    bf16* lo[16];
+    long long n[16];
+    int cnt = 0;
+    for (int k = 0; k < nc; ++k) {
+        const float* W = (kind == XGGM_KIND_GCN) ? cp[3 * k] : cp[5 * k + 1];
+        wconv[k] = planes_at(W, wregion + (long long)k * L.HH, (long long)H * H);
+    }
+    for (int j = 0; j <= nc; ++j)
+        whead[j] = planes_at(hp[4 * j], wregion + (long long)(nc + j) * L.HH, (long long)H * H);
+    if (!tc) return XGGM_OK;
+    for (int i = 0; i < 2 * nc + 1; ++i) {
+        const Operand& o = i < nc ? wconv[i] : whead[i - nc];
+        src[cnt] = o.f32; hi[cnt] = const_cast<bf16*>(o.hi); lo[cnt] = const_cast<bf16*>(o.lo);
+        n[cnt] = (long long)H * H;
+        if (++cnt == 16) { XGGM_TRY(split_planes(src, hi, npass() == 3 ? lo : nullptr, n, cnt, st)); cnt = 0; }
+    }
+    if (cnt) XGGM_TRY(split_planes(src, hi, npass() == 3 ? lo : nullptr, n, cnt, st));
+    return XGGM_OK;
+}
+
+constexpr int MAX_CONVS = 7;
 
 static int gnn_fwd(int kind, const float* x, const float* adj, const float* const* cp,
                    const float* const* hp, const uint8_t* const* keeps, float drop_p, float* out,
                    float* saved, float* work, int B, int N, int H, int nc, cudaStream_t st) {
     XGGM_REQUIRE(kind == XGGM_KIND_GCN || kind == XGGM_KIND_GIN);
-    XGGM_REQUIRE(B >= 0 && N > 0 && H > 0 && nc >= 0 && drop_p >= 0.f && drop_p < 1.f);
+    XGGM_REQUIRE(B >= 0 && N > 0 && H > 0 && nc >= 0 && nc <= MAX_CONVS && drop_p >= 0.f && drop_p < 1.f);
     const int M = B * N;
     if (M == 0) return XGGM_OK;
     XGGM_REQUIRE(x && adj && cp && hp && out && saved && work);
     const GnnLayout L(kind, M, H, nc);
+    const bool tc = use_tc(M, H, H);
     const float scale = 1.f / (1.f - drop_p);
+    const long long MHn = (long long)M * H;
+    Operand wconv[MAX_CONVS], whead[MAX_CONVS + 1];
+    XGGM_TRY(split_weights(kind, cp, hp, work + L.MH, L, H, wconv, whead, tc, st));
+    Operand hop = planes_at(x, saved + L.xplanes, MHn);   // current node features as a GEMM operand
+    if (tc) XGGM_TRY(split_one(hop, MHn, st));
+    Operand hops[MAX_CONVS + 1];
+    hops[0] = hop;
     const float* h = x;
     for (int k = 0; k < nc; ++k) {
         float* h_next = saved + L.conv(k, 2);
+        float* pre = saved + L.conv(k, 0);   // GCN: agg = adj @ h ; GIN: pre = h + (1+eps) adj @ h
+        Operand pre_op = planes_at(pre, saved + L.conv(k, 5), MHn);
         if (kind == XGGM_KIND_GCN) {
-            const float* W = cp[3 * k], *g = cp[3 * k + 1], *b = cp[3 * k + 2];
-            float* agg = saved + L.conv(k, 0);
+            const float* g = cp[3 * k + 1], *b = cp[3 * k + 2];
             float* xhat = saved + L.conv(k, 1);
             float* rstd = saved + L.conv(k, 3);
             float* u = work;
-            XGGM_TRY(adj_apply(adj, h, agg, B, N, H, 1.f, nullptr, 0.f, false, 0, st));
-            XGGM_TRY(gemm_simt(0, agg, W, nullptr, h, u, M, H, H, 0, st));
+            XGGM_TRY(adj_apply(adj, h, pre, B, N, H, 1.f, nullptr, 0.f, false, 0, st));
+            if (tc) XGGM_TRY(split_one(pre_op, MHn, st));
+            XGGM_TRY(proj_fwd(tc, pre_op, wconv[k], nullptr, h, u, M, H, H, st));
             XGGM_TRY(layernorm_fwd(u, g, b, h_next, xhat, rstd, M, H, LN_EPS, st));
         } else {
-            const float* eps = cp[5 * k], *W = cp[5 * k + 1], *bias = cp[5 * k + 2];
+            const float* eps = cp[5 * k], *bias = cp[5 * k + 2];
             const float* g = cp[5 * k + 3], *b = cp[5 * k + 4];
-            float* pre = saved + L.conv(k, 0);
             float* z = saved + L.conv(k, 1);
             float* mean = saved + L.conv(k, 3);
             float* rstd = saved + L.conv(k, 4);
             XGGM_TRY(adj_apply(adj, h, pre, B, N, H, 1.f, eps, 1.f, false, 0, st));
-            XGGM_TRY(gemm_simt(0, pre, W, bias, nullptr, z, M, H, H, 0, st));
+            if (tc) XGGM_TRY(split_one(pre_op, MHn, st));
+            XGGM_TRY(proj_fwd(tc, pre_op, wconv[k], bias, nullptr, z, M, H, H, st));
             XGGM_TRY(gelu_ln_drop_fwd(z, g, b, nullptr, 1.f, h_next, mean, rstd, M, H, LN_EPS, 0, st));
         }
+        hops[k + 1] = planes_at(h_next, saved + L.conv(k, 6), MHn);
+        if (tc) XGGM_TRY(split_one(hops[k + 1], MHn, st));
         h = h_next;
     }
     for (int j = 0; j <= nc; ++j) {
-        const float* hj = (j == 0) ? x : saved + L.conv(j - 1, 2);
-        const float* W = hp[4 * j], *bias = hp[4 * j + 1], *g = hp[4 * j + 2], *b = hp[4 * j + 3];
+        const float* bias = hp[4 * j + 1], *g = hp[4 * j + 2], *b = hp[4 * j + 3];
         float* z = saved + L.head(j, 0);
-        XGGM_TRY(gemm_simt(0, hj, W, bias, nullptr, z, M, H, H, 0, st));
+        XGGM_TRY(proj_fwd(tc, hops[j], whead[j], bias, nullptr, z, M, H, H, st));
         XGGM_TRY(gelu_ln_drop_fwd(z, g, b, keeps ? keeps[j] : nullptr, scale, out,
                                   saved + L.head(j, 1), saved + L.head(j, 2), M, H, LN_EPS, j > 0, st));
     }
@@ -127,11 +228,11 @@ static int gnn_fwd(int kind, const float* x, const float* adj, const float* cons
 
 static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj,
                    const float* const* cp, const float* const* hp, const uint8_t* const* keeps,
-                   float drop_p, const float* saved, float* work, float* gx, float* gadj,
+                   float drop_p, const float* saved_c, float* work, float* gx, float* gadj,
                    float* const* cg, float* const* hg, int B, int N, int H, int nc,
                    cudaStream_t st) {
     XGGM_REQUIRE(kind == XGGM_KIND_GCN || kind == XGGM_KIND_GIN);
-    XGGM_REQUIRE(B >= 0 && N > 0 && H > 0 && nc >= 0 && cp && hp && cg && hg);
+    XGGM_REQUIRE(B >= 0 && N > 0 && H > 0 && nc >= 0 && nc <= MAX_CONVS && cp && hp && cg && hg);
     const int M = B * N;
     if (M == 0) {  // empty batch: parameter gradients are zero
         const int per = (kind == XGGM_KIND_GCN) ? 3 : 5;
@@ -146,26 +247,38 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
                 XGGM_CUDA_TRY(cudaMemsetAsync(hg[4 * j + q], 0, sizeof(float) * (q == 0 ? (size_t)H * H : H), st));
         return XGGM_OK;
     }
-    XGGM_REQUIRE(gout && x && adj && saved && work && gx && gadj);
+    XGGM_REQUIRE(gout && x && adj && saved_c && work && gx && gadj);
+    float* saved = const_cast<float*>(saved_c);  // plane regions are read-only here; the cast only feeds planes_at
     const GnnLayout L(kind, M, H, nc);
+    const bool tc = use_tc(M, H, H);
     const float scale = 1.f / (1.f - drop_p);
-    const long long MH = L.MH;
+    const long long MH = L.MH, MHn = (long long)M * H;
     float* buf[2] = {work, work + MH};
     float* gt = work + 2 * MH;  // gz / gu
     float* gq = work + 3 * MH;
+    Operand wconv[MAX_CONVS], whead[MAX_CONVS + 1];
+    XGGM_TRY(split_weights(kind, cp, hp, work + 5 * MH, L, H, wconv, whead, tc, st));
     XGGM_CUDA_TRY(cudaMemsetAsync(gadj, 0, sizeof(float) * (size_t)B * N * N, st));
+
+    auto act = [&](int j) -> Operand {   // h_j as a GEMM operand (planes saved by the forward pass)
+        return j == 0 ? planes_at(x, saved + L.xplanes, MHn)
+                      : planes_at(saved + L.conv(j - 1, 2), saved + L.conv(j - 1, 6), MHn);
+    };
+    // gradient tensor `g32` as an operand: its planes go to the scratch region work[4 MH ..)
+    auto grad_op = [&](const float* g32) -> Operand { return planes_at(g32, work + 4 * MH, MHn); };
 
     // head j contributes gz_j -> (gW_j, gb_j, ggamma_j, gbeta_j) and gz_j W_j into grad of h_j
     auto head_bwd = [&](int j, float* gh, int accumulate) -> int {
-        const float* hj = (j == 0) ? x : saved + L.conv(j - 1, 2);
         XGGM_CUDA_TRY(cudaMemsetAsync(hg[4 * j + 2], 0, sizeof(float) * H, st));
         XGGM_CUDA_TRY(cudaMemsetAsync(hg[4 * j + 3], 0, sizeof(float) * H, st));
         XGGM_TRY(gelu_ln_drop_bwd(gout, saved + L.head(j, 0), saved + L.head(j, 1), saved + L.head(j, 2),
                                   hp[4 * j + 2], keeps ? keeps[j] : nullptr, scale, gt,
                                   hg[4 * j + 2], hg[4 * j + 3], M, H, st));
-        XGGM_TRY(gemm_simt(2, gt, hj, nullptr, nullptr, hg[4 * j], H, H, M, 0, st));
+        const Operand g = grad_op(gt);
+        if (tc) XGGM_TRY(split_one(g, MHn, st));
+        XGGM_TRY(proj_wgrad(tc, g, act(j), hg[4 * j], M, H, H, st));
         XGGM_TRY(colsum(gt, hg[4 * j + 1], M, H, st));
-        XGGM_TRY(gemm_simt(1, gt, hp[4 * j], nullptr, nullptr, gh, M, H, H, accumulate, st));
+        XGGM_TRY(proj_dgrad(tc, g, whead[j], gh, M, H, H, accumulate, st));
         return XGGM_OK;
     };
 
@@ -175,27 +288,32 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
     for (int k = nc - 1; k >= 0; --k) {
         const float* hk = (k == 0) ? x : saved + L.conv(k - 1, 2);
         float* gnext = (k == 0) ? gx : buf[cur ^ 1];
+        const Operand pre_op = planes_at(saved + L.conv(k, 0), saved + L.conv(k, 5), MHn);
         if (kind == XGGM_KIND_GCN) {
-            const float* W = cp[3 * k], *g = cp[3 * k + 1];
+            const float* g = cp[3 * k + 1];
             XGGM_CUDA_TRY(cudaMemsetAsync(cg[3 * k + 1], 0, sizeof(float) * H, st));
             XGGM_CUDA_TRY(cudaMemsetAsync(cg[3 * k + 2], 0, sizeof(float) * H, st));
             // gu = LN backward, written straight into the next-level gradient (residual path)
             XGGM_TRY(layernorm_bwd(gh, saved + L.conv(k, 1), saved + L.conv(k, 3), g, gnext,
                                    cg[3 * k + 1], cg[3 * k + 2], M, H, st));
-            XGGM_TRY(gemm_simt(2, gnext, saved + L.conv(k, 0), nullptr, nullptr, cg[3 * k], H, H, M, 0, st));
-            XGGM_TRY(gemm_simt(1, gnext, W, nullptr, nullptr, gq, M, H, H, 0, st));  // gq = gu Wc
+            const Operand gu = grad_op(gnext);
+            if (tc) XGGM_TRY(split_one(gu, MHn, st));
+            XGGM_TRY(proj_wgrad(tc, gu, pre_op, cg[3 * k], M, H, H, st));
+            XGGM_TRY(proj_dgrad(tc, gu, wconv[k], gq, M, H, H, 0, st));  // gq = gu Wc
             XGGM_TRY(bmm_nt(gq, hk, gadj, B, N, H, 1.f, nullptr, 1, nullptr, nullptr, st));
             XGGM_TRY(adj_apply(adj, gq, gnext, B, N, H, 1.f, nullptr, 0.f, true, 1, st));
         } else {
-            const float* eps = cp[5 * k], *W = cp[5 * k + 1], *g = cp[5 * k + 3];
+            const float* eps = cp[5 * k], *g = cp[5 * k + 3];
             XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k], 0, sizeof(float), st));
             XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k + 3], 0, sizeof(float) * H, st));
             XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k + 4], 0, sizeof(float) * H, st));
             XGGM_TRY(gelu_ln_drop_bwd(gh, saved + L.conv(k, 1), saved + L.conv(k, 3), saved + L.conv(k, 4),
                                       g, nullptr, 1.f, gt, cg[5 * k + 3], cg[5 * k + 4], M, H, st));
-            XGGM_TRY(gemm_simt(2, gt, saved + L.conv(k, 0), nullptr, nullptr, cg[5 * k + 1], H, H, M, 0, st));
+            const Operand gz = grad_op(gt);
+            if (tc) XGGM_TRY(split_one(gz, MHn, st));
+            XGGM_TRY(proj_wgrad(tc, gz, pre_op, cg[5 * k + 1], M, H, H, st));
             XGGM_TRY(colsum(gt, cg[5 * k + 2], M, H, st));
-            XGGM_TRY(gemm_simt(1, gt, W, nullptr, nullptr, gq, M, H, H, 0, st));      // gpre
+            XGGM_TRY(proj_dgrad(tc, gz, wconv[k], gq, M, H, H, 0, st));      // gpre
             // gadj += (1+eps) gpre h^T ; geps += <gpre h^T, adj>
             XGGM_TRY(bmm_nt(gq, hk, gadj, B, N, H, 1.f, eps, 1, adj, cg[5 * k], st));
             // grad h_k = gpre + (1+eps) adj^T gpre
@@ -246,20 +364,60 @@ int xggm_device_check(int device) {
     return prop.major == 10 ? XGGM_OK : XGGM_ERR_ARCH;
 }
 
+int xggm_set_precision(int mode) {
+    XGGM_REQUIRE(mode == XGGM_PREC_FP32 || mode == XGGM_PREC_BF16 || mode == XGGM_PREC_FP32_SIMT);
+    g_precision = mode;
+    return XGGM_OK;
+}
+int xggm_get_precision(void) { return g_precision; }
+
+// work layout of the Linear entry points: P(a)[M,K] | P(w)[N,K] | P(g)[M,N]
+long long xggm_linear_work_bytes(int M, int N, int K) {
+    if (M < 0 || N <= 0 || K <= 0) return -1;
+    return 4 * (al4((long long)M * K) + al4((long long)N * K) + al4((long long)M * N));
+}
+static inline bool linear_tc(const void* work, int M, int N, int K) {
+    return work != nullptr && M > 0 && use_tc(M, N, K);
+}
+
 int xggm_linear_fwd(const float* a, const float* w, const float* bias, const float* resid,
-                    float* out, int M, int N, int K, xggm_stream_t s) {
+                    float* out, int M, int N, int K, void* work, xggm_stream_t s) {
     if (M == 0) return XGGM_OK;
     XGGM_REQUIRE(a && w && out && M >= 0 && N > 0 && K > 0);
-    return gemm_simt(0, a, w, bias, resid, out, M, N, K, 0, as_stream(s));
+    const bool tc = linear_tc(work, M, N, K);
+    float* wk = static_cast<float*>(work);
+    Operand ao{a, nullptr, nullptr}, wo{w, nullptr, nullptr};
+    if (tc) {
+        ao = planes_at(a, wk, (long long)M * K);
+        wo = planes_at(w, wk + al4((long long)M * K), (long long)N * K);
+        const float* src[2] = {a, w};
+        bf16* hi[2] = {const_cast<bf16*>(ao.hi), const_cast<bf16*>(wo.hi)};
+        bf16* lo[2] = {const_cast<bf16*>(ao.lo), const_cast<bf16*>(wo.lo)};
+        const long long n[2] = {(long long)M * K, (long long)N * K};
+        XGGM_TRY(split_planes(src, hi, npass() == 3 ? lo : nullptr, n, 2, as_stream(s)));
+    }
+    return proj_fwd(tc, ao, wo, bias, resid, out, M, N, K, as_stream(s));
 }
 int xggm_linear_bwd_input(const float* g, const float* w, float* ga, int M, int N, int K,
-                          int accumulate, xggm_stream_t s) {
+                          int accumulate, void* work, xggm_stream_t s) {
     if (M == 0) return XGGM_OK;
     XGGM_REQUIRE(g && w && ga && M >= 0 && N > 0 && K > 0);
-    return gemm_simt(1, g, w, nullptr, nullptr, ga, M, K, N, accumulate, as_stream(s));
+    const bool tc = linear_tc(work, M, N, K);
+    float* wk = static_cast<float*>(work);
+    Operand go{g, nullptr, nullptr}, wo{w, nullptr, nullptr};
+    if (tc) {
+        wo = planes_at(w, wk + al4((long long)M * K), (long long)N * K);
+        go = planes_at(g, wk + al4((long long)M * K) + al4((long long)N * K), (long long)M * N);
+        const float* src[2] = {g, w};
+        bf16* hi[2] = {const_cast<bf16*>(go.hi), const_cast<bf16*>(wo.hi)};
+        bf16* lo[2] = {const_cast<bf16*>(go.lo), const_cast<bf16*>(wo.lo)};
+        const long long n[2] = {(long long)M * N, (long long)N * K};
+        XGGM_TRY(split_planes(src, hi, npass() == 3 ? lo : nullptr, n, 2, as_stream(s)));
+    }
+    return proj_dgrad(tc, go, wo, ga, M, N, K, accumulate, as_stream(s));
 }
 int xggm_linear_bwd_weight(const float* g, const float* a, float* gw, float* gbias, int M, int N,
-                           int K, xggm_stream_t s) {
+                           int K, void* work, xggm_stream_t s) {
     XGGM_REQUIRE(gw && M >= 0 && N > 0 && K > 0);
     if (M == 0) {
         XGGM_CUDA_TRY(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)N * K, as_stream(s)));
@@ -267,7 +425,19 @@ int xggm_linear_bwd_weight(const float* g, const float* a, float* gw, float* gbi
         return XGGM_OK;
     }
     XGGM_REQUIRE(g && a);
-    XGGM_TRY(gemm_simt(2, g, a, nullptr, nullptr, gw, N, K, M, 0, as_stream(s)));
+    const bool tc = linear_tc(work, M, N, K);
+    float* wk = static_cast<float*>(work);
+    Operand go{g, nullptr, nullptr}, ao{a, nullptr, nullptr};
+    if (tc) {
+        ao = planes_at(a, wk, (long long)M * K);
+        go = planes_at(g, wk + al4((long long)M * K) + al4((long long)N * K), (long long)M * N);
+        const float* src[2] = {g, a};
+        bf16* hi[2] = {const_cast<bf16*>(go.hi), const_cast<bf16*>(ao.hi)};
+        bf16* lo[2] = {const_cast<bf16*>(go.lo), const_cast<bf16*>(ao.lo)};
+        const long long n[2] = {(long long)M * N, (long long)M * K};
+        XGGM_TRY(split_planes(src, hi, npass() == 3 ? lo : nullptr, n, 2, as_stream(s)));
+    }
+    XGGM_TRY(proj_wgrad(tc, go, ao, gw, M, N, K, as_stream(s)));
     if (gbias) XGGM_TRY(colsum(g, gbias, M, N, as_stream(s)));
     return XGGM_OK;
 }
@@ -337,7 +507,8 @@ long long xggm_gnn_saved_floats(int kind, int B, int N, int H, int n_convs) {
 }
 long long xggm_gnn_work_floats(int kind, int B, int N, int H, int n_convs) {
     if ((kind != XGGM_KIND_GCN && kind != XGGM_KIND_GIN) || B < 0 || N <= 0 || H <= 0 || n_convs < 0) return -1;
-    return 4 * GnnLayout(kind, (long long)B * N, H, n_convs).MH;
+    const GnnLayout L(kind, (long long)B * N, H, n_convs);
+    return L.work_bwd() > L.work_fwd() ? L.work_bwd() : L.work_fwd();
 }
 int xggm_gnn_fwd(int kind, const float* x, const float* adj, const float* const* conv_params,
                  const float* const* head_params, const uint8_t* const* keeps, float drop_p,

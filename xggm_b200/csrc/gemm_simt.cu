@@ -156,17 +156,21 @@ int gemm_prof_read(double* total_ms, long long* launches, double* flops) {
     }
     return XGGM_OK;
 }
+void* gemm_prof_begin(double flops, cudaStream_t st) {
+    if (!g_prof_on || g_prof_n >= 4096) return nullptr;
+    ProfRec* r = &g_prof[g_prof_n++];
+    r->flops = flops;
+    cudaEventCreate(&r->e0); cudaEventCreate(&r->e1);
+    cudaEventRecord(r->e0, st);
+    return r;
+}
+void gemm_prof_end(void* rec, cudaStream_t st) {
+    if (rec) cudaEventRecord(static_cast<ProfRec*>(rec)->e1, st);
+}
 struct ProfScope {
-    ProfRec* r = nullptr; cudaStream_t st;
-    ProfScope(double flops, cudaStream_t s) : st(s) {
-        if (g_prof_on && g_prof_n < 4096) {
-            r = &g_prof[g_prof_n++];
-            r->flops = flops;
-            cudaEventCreate(&r->e0); cudaEventCreate(&r->e1);
-            cudaEventRecord(r->e0, st);
-        }
-    }
-    ~ProfScope() { if (r) cudaEventRecord(r->e1, st); }
+    void* r; cudaStream_t st;
+    ProfScope(double flops, cudaStream_t s) : r(gemm_prof_begin(flops, s)), st(s) {}
+    ~ProfScope() { gemm_prof_end(r, st); }
 };
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

@@ -1,0 +1,572 @@
+// tcgen05 / TMEM / TMA GEMM engine for the dense node projections (sm_100a only).
+//
+//   C[M,N] (=|+=) sum_k A(m,k) * B(n,k)  (+ bias[n]) (+ resid[m,n])
+//
+// Operands are bf16 "planes".  fp32 parity mode (NPASS = 3) represents every fp32 value v as
+// hi = bf16(v), lo = bf16(v - hi) and issues three tensor-core products per k-step
+//   A_lo*B_hi + A_hi*B_lo + A_hi*B_hi      (fp32 accumulation in TMEM)
+// which carries 16 mantissa bits per operand (relative error ~1e-5, measured in the tests);
+// bf16 mode (NPASS = 1) uses the hi planes only.
+//
+// Either operand may be K-major (stored [MN, K], k contiguous) or MN-major (stored [K, MN]),
+// which covers the three products of a Linear layer without a transpose:
+//   forward  out = a w^T : A = a  [M,K]  K-major,   B = w [N,K]   K-major
+//   dgrad    ga  = g w   : A = g  [M,N'] K-major,   B = w [N',K'] MN-major
+//   wgrad    gw  = g^T a : A = g  [rows,N] MN-major, B = a [rows,K] MN-major  (+ split-K)
+//
+// Kernel shape: persistent CTAs (one per SM), 192 threads:
+//   warp 0      TMA producer   (cp.async.bulk.tensor, SWIZZLE_128B, mbarrier complete_tx)
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (128 x BN x 16 per instruction)
+//   warps 2..5  epilogue: tcgen05.ld 32x32b -> smem transpose -> coalesced fp32 stores
+// Two accumulator buffers in TMEM (2 x BN columns) let the epilogue of tile i overlap the
+// main loop of tile i+1.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace xggm {
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 64;   // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int UK = 16;   // K of one tcgen05.mma for 16-bit operands
+constexpr int NUM_THREADS = 192;
+constexpr int EPI_PITCH = 33;
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// ---- mbarrier ------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.b32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// A lost arrival must surface as a CUDA error, never as a hung GPU: trap after 2 s of waiting.
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const uint64_t t0 = global_ns();
+    while (!mbar_try_wait(bar, parity)) {
+        if (global_ns() - t0 > 2000000000ull) __trap();
+    }
+}
+
+// ---- TMA -----------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c_inner, int c_outer) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// ---- tcgen05 -------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on `bar` once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (SWIZZLE_128B, Blackwell version 1).
+//   K-major  tile [rows][64 bf16]: 8-row atoms of 1024 B  -> SBO = 1024 (LBO unused)
+//   MN-major tile [BK rows][64 bf16] per 64-wide MN atom  -> SBO = 1024 (8 k-rows), LBO = BK*128 (next MN atom)
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor: bf16 x bf16 -> fp32, M = 128, N = BN, per-operand major-ness.
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+struct Params {
+    int M, N;            // output extent
+    int num_kb;          // ceil(K / BK)
+    int tiles_m, tiles_n, splits, kb_per_split;
+    const float* bias;   // [N] or null
+    const float* resid;  // [M,N] or null
+    float* C;
+    int ldc;
+    int accumulate;      // C += (non-atomic)
+    int atomic;          // split-K partial sums: atomicAdd into a pre-zeroed / pre-initialised C
+};
+
+template <int BN, int NPASS>
+struct Cfg {
+    static constexpr int A_TILE = BM * BK * 2;
+    static constexpr int B_TILE = BN * BK * 2;
+    static constexpr int NPLANE = NPASS == 3 ? 2 : 1;
+    static constexpr int STAGE_BYTES = NPLANE * (A_TILE + B_TILE);
+    static constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;
+    static constexpr int FIXED = EPI_BYTES + 256 + 1024;  // + barriers + alignment slack
+    static constexpr int STAGES_RAW = (SMEM_LIMIT - FIXED) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + FIXED;
+    static constexpr int TMEM_COLS = 2 * BN <= 256 ? 256 : 512;
+    static_assert(STAGES >= 2, "need at least a double-buffered operand ring");
+};
+
+template <int BN, int NPASS, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+               const Params p) {
+    using C = Cfg<BN, NPASS>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* stage_base = smem;
+    float* epi = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::EPI_BYTES);
+    uint64_t* full = bars;                    // [STAGES] TMA -> MMA
+    uint64_t* empty = bars + C::STAGES;       // [STAGES] MMA -> TMA
+    uint64_t* acc_full = bars + 2 * C::STAGES;      // [2] MMA -> epilogue
+    uint64_t* acc_empty = bars + 2 * C::STAGES + 2; // [2] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = p.tiles_m * p.tiles_n * p.splits;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&map_a_hi);
+        prefetch_tmap(&map_b_hi);
+        if (NPASS == 3) {
+            prefetch_tmap(&map_a_lo);
+            prefetch_tmap(&map_b_lo);
+        }
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int sp = tile % p.splits;
+                const int mn = tile / p.splits;
+                const int m0 = (mn / p.tiles_n) * BM, n0 = (mn % p.tiles_n) * BN;
+                const int kb0 = sp * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+                    uint8_t* sa = stage_base + stage * C::STAGE_BYTES;
+                    uint8_t* sb = sa + C::NPLANE * C::A_TILE;
+                    const int k0 = kb * BK;
+#pragma unroll
+                    for (int pl = 0; pl < C::NPLANE; ++pl) {
+                        const CUtensorMap* ma = pl == 0 ? &map_a_hi : &map_a_lo;
+                        const CUtensorMap* mb = pl == 0 ? &map_b_hi : &map_b_lo;
+                        if (A_MN) {
+#pragma unroll
+                            for (int i = 0; i < BM / 64; ++i)
+                                tma_load_2d(sa + pl * C::A_TILE + i * (BK * 128), ma, &full[stage], m0 + 64 * i, k0);
+                        } else {
+                            tma_load_2d(sa + pl * C::A_TILE, ma, &full[stage], k0, m0);
+                        }
+                        if (B_MN) {
+#pragma unroll
+                            for (int i = 0; i < BN / 64; ++i)
+                                tma_load_2d(sb + pl * C::B_TILE + i * (BK * 128), mb, &full[stage], n0 + 64 * i, k0);
+                        } else {
+                            tma_load_2d(sb + pl * C::B_TILE, mb, &full[stage], k0, n0);
+                        }
+                    }
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
+            constexpr uint32_t a_lbo = A_MN ? BK * 128 : 16, b_lbo = B_MN ? BK * 128 : 16;
+            constexpr uint32_t a_kstep = A_MN ? UK * 128 : UK * 2;  // bytes per 16-wide k-step
+            constexpr uint32_t b_kstep = B_MN ? UK * 128 : UK * 2;
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int sp = tile % p.splits;
+                const int kb0 = sp * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+                mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                uint32_t first = 1;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(stage_base + stage * C::STAGE_BYTES);
+                    const uint32_t sb = sa + C::NPLANE * C::A_TILE;
+                    // pass order: small cross terms first, hi*hi last
+#pragma unroll
+                    for (int pass = 0; pass < NPASS; ++pass) {
+                        const int apl = (NPASS == 3 && pass == 0) ? 1 : 0;   // A_lo, A_hi, A_hi
+                        const int bpl = (NPASS == 3 && pass == 1) ? 1 : 0;   // B_hi, B_lo, B_hi
+                        const uint64_t adesc0 = make_sdesc(sa + apl * C::A_TILE, a_lbo, 1024);
+                        const uint64_t bdesc0 = make_sdesc(sb + bpl * C::B_TILE, b_lbo, 1024);
+#pragma unroll
+                        for (int k = 0; k < BK / UK; ++k) {
+                            umma_bf16(d_tmem, adesc0 + (uint64_t)((k * a_kstep) >> 4),
+                                      bdesc0 + (uint64_t)((k * b_kstep) >> 4), idesc, first ? 0u : 1u);
+                            first = 0;
+                        }
+                    }
+                    umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&acc_full[acc]);     // accumulator complete -> epilogue
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ================================ epilogue ====================================
+        const int q = warp & 3;  // TMEM lane quarter this warp may read: lanes 32q .. 32q+31
+        float* st = epi + (warp - 2) * 32 * EPI_PITCH;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int mn = tile / p.splits;
+            const int sp = tile % p.splits;
+            const int m0 = (mn / p.tiles_n) * BM, n0 = (mn % p.tiles_n) * BN;
+            const bool lead = (sp == 0);  // bias / residual are added by the first split only
+            mbar_wait(&acc_full[acc], acc_phase);
+            tc_fence_after();
+            const int mrow0 = m0 + q * 32;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                const int ncol0 = n0 + c * 32;
+                if (ncol0 >= p.N || mrow0 >= p.M) break;  // warp-uniform
+                uint32_t v[32];
+                tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) st[lane * EPI_PITCH + j] = __uint_as_float(v[j]);
+                __syncwarp();
+                const int n = ncol0 + lane;
+                const bool n_ok = n < p.N;
+                const float bv = (lead && p.bias && n_ok) ? p.bias[n] : 0.f;
+                const int rows = min(32, p.M - mrow0);
+                if (n_ok) {
+#pragma unroll 4
+                    for (int i = 0; i < rows; ++i) {
+                        float val = st[i * EPI_PITCH + lane] + bv;
+                        const size_t o = (size_t)(mrow0 + i) * p.ldc + n;
+                        if (lead && p.resid) val += p.resid[o];
+                        if (p.atomic) atomicAdd(&p.C[o], val);
+                        else p.C[o] = p.accumulate ? p.C[o] + val : val;
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// ---- fp32 -> bf16 hi/lo planes -----------------------------------------------------------------
+__device__ __forceinline__ void split1(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(x);
+    const float h = __bfloat162float(hi);
+    const float r = x - h;
+    lo = __float2bfloat16_rn((h - h == 0.f) ? r : 0.f);  // inf/nan: keep them in hi only
+}
+
+struct SplitJob {
+    const float* src;
+    __nv_bfloat16* hi;
+    __nv_bfloat16* lo;  // may be null (bf16 mode)
+    long long n;
+};
+constexpr int MAX_SPLIT_JOBS = 8;
+struct SplitJobs {
+    SplitJob j[MAX_SPLIT_JOBS];
+    int count;
+};
+
+__global__ void __launch_bounds__(256) split_planes_kernel(const SplitJobs jobs) {
+    const SplitJob job = jobs.j[blockIdx.y];
+    const long long n4 = job.n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = reinterpret_cast<const float4*>(job.src)[i];
+        __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+        split1(v.x, h0, l0); split1(v.y, h1, l1); split1(v.z, h2, l2); split1(v.w, h3, l3);
+        __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
+        uint2 hv = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+        reinterpret_cast<uint2*>(job.hi)[i] = hv;
+        if (job.lo) {
+            __nv_bfloat162 c = __halves2bfloat162(l0, l1), d = __halves2bfloat162(l2, l3);
+            reinterpret_cast<uint2*>(job.lo)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&c), *reinterpret_cast<uint32_t*>(&d));
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // tail (n % 4)
+        for (long long i = n4 << 2; i < job.n; ++i) {
+            __nv_bfloat16 h, l;
+            split1(job.src[i], h, l);
+            job.hi[i] = h;
+            if (job.lo) job.lo[i] = l;
+        }
+    }
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// 2-D bf16 tensor [rows][cols] (cols contiguous), box = [box_rows][64], SWIZZLE_128B, zero OOB fill.
+static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return XGGM_ERR_UNSUPPORTED;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? XGGM_OK : XGGM_ERR_ARG;
+}
+
+struct ProfScopeTc;  // (per-launch timing lives in gemm_simt.cu: gemm_prof_begin / gemm_prof_end)
+void* gemm_prof_begin(double flops, cudaStream_t st);
+void gemm_prof_end(void* rec, cudaStream_t st);
+
+static int g_num_sms = 0;
+static int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+template <int BN, int NPASS, bool A_MN, bool B_MN>
+static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
+                     const tc::Params& p, int grid, cudaStream_t st) {
+    using C = tc::Cfg<BN, NPASS>;
+    static bool attr_set = false;
+    auto kern = tc::gemm_tc_kernel<BN, NPASS, A_MN, B_MN>;
+    if (!attr_set) {
+        XGGM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        attr_set = true;
+    }
+    kern<<<grid, tc::NUM_THREADS, C::SMEM, st>>>(ah, al, bh, bl, p);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+
+template <int BN, int NPASS>
+static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
+                          const CUtensorMap& bl, const tc::Params& p, int grid, cudaStream_t st) {
+    if (!a_mn && !b_mn) return launch_tc<BN, NPASS, false, false>(ah, al, bh, bl, p, grid, st);
+    if (!a_mn && b_mn) return launch_tc<BN, NPASS, false, true>(ah, al, bh, bl, p, grid, st);
+    if (a_mn && b_mn) return launch_tc<BN, NPASS, true, true>(ah, al, bh, bl, p, grid, st);
+    return XGGM_ERR_UNSUPPORTED;  // (MN-major A with K-major B is not needed by a Linear layer)
+}
+
+bool gemm_tc_supported(int M, int N, int K) {
+    // TMA needs 16-byte row pitches in every plane a Linear's three products touch
+    return M > 0 && N > 0 && K > 0 && (N % 8 == 0) && (K % 8 == 0);
+}
+
+// A planes: a_mn ? [K,M] : [M,K];  B planes: b_mn ? [K,N] : [N,K].  lo planes may be null when npass == 1.
+int gemm_tc(bool a_mn, bool b_mn, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const __nv_bfloat16* b_hi,
+            const __nv_bfloat16* b_lo, const float* bias, const float* resid, float* C, int M, int N, int K,
+            int accumulate, int allow_split_k, int npass, cudaStream_t st) {
+    if (M <= 0 || N <= 0 || K <= 0) return XGGM_OK;
+    XGGM_REQUIRE(a_hi && b_hi && C && (npass == 1 || (npass == 3 && a_lo && b_lo)));
+    const int sms = num_sms();
+    const int tiles_m = ceil_div(M, tc::BM);
+    const int num_kb = ceil_div(K, tc::BK);
+    // tile width: fewest "waves x width"; ties go to the wider tile (less A re-read)
+    int bn = 128;
+    long long best = -1;
+    const int cand[2] = {192, 128};
+    int splits_for[2] = {1, 1};
+    for (int ci = 0; ci < 2; ++ci) {
+        const int w = cand[ci];
+        const int tn = ceil_div(N, w);
+        int splits = 1;
+        if (allow_split_k) {
+            splits = max(1, min(num_kb / 4, sms / max(1, tiles_m * tn)));
+        }
+        splits_for[ci] = splits;
+        const long long kb_per = ceil_div(num_kb, splits);
+        const long long waves = ceil_div((long long)tiles_m * tn * splits, sms);
+        const long long cost = waves * w * kb_per;
+        if (best < 0 || cost < best) { best = cost; bn = w; }
+    }
+    int splits = splits_for[bn == 192 ? 0 : 1];
+    const int tiles_n = ceil_div(N, bn);
+    int kb_per_split = ceil_div(num_kb, splits);
+    splits = ceil_div(num_kb, kb_per_split);
+
+    CUtensorMap ah, al, bh, bl;
+    const long long a_rows = a_mn ? K : M, a_cols = a_mn ? M : K;
+    const long long b_rows = b_mn ? K : N, b_cols = b_mn ? N : K;
+    const int a_box = a_mn ? tc::BK : tc::BM, b_box = b_mn ? tc::BK : bn;
+    XGGM_TRY(make_map(&ah, a_hi, a_rows, a_cols, a_box));
+    XGGM_TRY(make_map(&bh, b_hi, b_rows, b_cols, b_box));
+    if (npass == 3) {
+        XGGM_TRY(make_map(&al, a_lo, a_rows, a_cols, a_box));
+        XGGM_TRY(make_map(&bl, b_lo, b_rows, b_cols, b_box));
+    } else {
+        al = ah;
+        bl = bh;
+    }
+    tc::Params p;
+    p.M = M; p.N = N; p.num_kb = num_kb;
+    p.tiles_m = tiles_m; p.tiles_n = tiles_n; p.splits = splits; p.kb_per_split = kb_per_split;
+    p.bias = bias; p.resid = resid; p.C = C; p.ldc = N;
+    p.accumulate = accumulate; p.atomic = splits > 1 ? 1 : 0;
+    if (splits > 1 && !accumulate)
+        XGGM_CUDA_TRY(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
+    const int grid = min(sms, tiles_m * tiles_n * splits);
+
+    void* prof = gemm_prof_begin(2.0 * M * N * K, st);
+    int rc;
+    if (bn == 192) {
+        rc = npass == 3 ? dispatch_major<192, 3>(a_mn, b_mn, ah, al, bh, bl, p, grid, st)
+                        : dispatch_major<192, 1>(a_mn, b_mn, ah, al, bh, bl, p, grid, st);
+    } else {
+        rc = npass == 3 ? dispatch_major<128, 3>(a_mn, b_mn, ah, al, bh, bl, p, grid, st)
+                        : dispatch_major<128, 1>(a_mn, b_mn, ah, al, bh, bl, p, grid, st);
+    }
+    gemm_prof_end(prof, st);
+    return rc;
+}
+
+// Split up to MAX_SPLIT_JOBS fp32 arrays into bf16 hi (+ lo) planes with one launch.
+int split_planes(const float* const* src, __nv_bfloat16* const* hi, __nv_bfloat16* const* lo, const long long* n,
+                 int count, cudaStream_t st) {
+    int done = 0;
+    while (done < count) {
+        tc::SplitJobs jobs;
+        jobs.count = min(tc::MAX_SPLIT_JOBS, count - done);
+        long long nmax = 0;
+        for (int i = 0; i < jobs.count; ++i) {
+            jobs.j[i].src = src[done + i];
+            jobs.j[i].hi = hi[done + i];
+            jobs.j[i].lo = lo ? lo[done + i] : nullptr;
+            jobs.j[i].n = n[done + i];
+            nmax = n[done + i] > nmax ? n[done + i] : nmax;
+        }
+        if (nmax > 0) {
+            const int gx = (int)max(1LL, min((long long)num_sms() * 8, (nmax / 4 + 255) / 256));
+            tc::split_planes_kernel<<<dim3(gx, jobs.count), 256, 0, st>>>(jobs);
+            XGGM_LAUNCH_CHECK();
+        }
+        done += jobs.count;
+    }
+    return XGGM_OK;
+}
+
+}  // namespace xggm

@@ -26,6 +26,12 @@ def _u8(t):
 # ---------------------------------------------------------------------------
 # dense projection (nn.Linear)
 # ---------------------------------------------------------------------------
+def _linear_work(M, N, K, device):
+    """Scratch for the bf16 operand planes of the tcgen05 engine (caller-owned, see xggm_b200.h)."""
+    n = _lib.load().xggm_linear_work_bytes(M, N, K)
+    return torch.empty(max(int(n), 16), device=device, dtype=torch.uint8)
+
+
 class _Linear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, w, bias, resid):
@@ -38,7 +44,8 @@ class _Linear(torch.autograd.Function):
         bias = None if bias is None else f32(bias, "bias")
         r2 = None if resid is None else f32(resid, "resid").reshape(-1, N)
         out = torch.empty((M, N), device=a.device, dtype=torch.float32)
-        call("xggm_linear_fwd", ptr(a2), ptr(w), ptr(bias), ptr(r2), ptr(out), M, N, K)
+        work = _linear_work(M, N, K, a.device)
+        call("xggm_linear_fwd", ptr(a2), ptr(w), ptr(bias), ptr(r2), ptr(out), M, N, K, ptr(work))
         ctx.save_for_backward(a2, w)
         ctx.has_bias, ctx.has_resid, ctx.in_shape = bias is not None, resid is not None, a.shape
         return out.reshape(*a.shape[:-1], N)
@@ -50,14 +57,15 @@ class _Linear(torch.autograd.Function):
         N = w.shape[0]
         g2 = f32(g).reshape(M, N)
         ga = gw = gb = gr = None
+        work = _linear_work(M, N, K, g.device)
         if ctx.needs_input_grad[0]:
             ga = torch.empty_like(a2)
-            call("xggm_linear_bwd_input", ptr(g2), ptr(w), ptr(ga), M, N, K, 0)
+            call("xggm_linear_bwd_input", ptr(g2), ptr(w), ptr(ga), M, N, K, 0, ptr(work))
             ga = ga.reshape(ctx.in_shape)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             gw = torch.empty_like(w)
             gb = torch.empty(N, device=w.device, dtype=torch.float32) if ctx.has_bias else None
-            call("xggm_linear_bwd_weight", ptr(g2), ptr(a2), ptr(gw), ptr(gb), M, N, K)
+            call("xggm_linear_bwd_weight", ptr(g2), ptr(a2), ptr(gw), ptr(gb), M, N, K, ptr(work))
         if ctx.has_resid and ctx.needs_input_grad[3]:
             gr = g
         return ga, gw, gb, gr
