@@ -21,11 +21,11 @@ int split_planes(const float* const* src, __nv_bfloat16* const* hi, __nv_bfloat1
                  int count, cudaStream_t st);
 int gemm_prof_enable(int on);
 int gemm_prof_read(double* total_ms, long long* launches, double* flops);
-int layernorm_fwd(const float*, const float*, const float*, float*, float*, float*, int, int, float, cudaStream_t);
-int layernorm_bwd(const float*, const float*, const float*, const float*, float*, float*, float*, int, int, cudaStream_t);
-int gelu_ln_drop_fwd(const float*, const float*, const float*, const uint8_t*, float, float*, float*, float*, int, int, float, int, cudaStream_t);
-int gelu_ln_drop_bwd(const float*, const float*, const float*, const float*, const float*, const uint8_t*, float, float*, float*, float*, int, int, cudaStream_t);
-int adj_apply(const float*, const float*, float*, int, int, int, float, const float*, float, bool, int, cudaStream_t);
+int layernorm_fwd(const float*, const float*, const float*, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, float, cudaStream_t);
+int layernorm_bwd(const float*, const float*, const float*, const float*, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, cudaStream_t);
+int gelu_ln_drop_fwd(const float*, const float*, const float*, const uint8_t*, float, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, float, int, cudaStream_t);
+int gelu_ln_drop_bwd(const float*, const float*, const float*, const float*, const float*, const uint8_t*, float, float*, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, cudaStream_t);
+int adj_apply(const float*, const float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, int, float, const float*, float, bool, int, cudaStream_t);
 int bmm_nt(const float*, const float*, float*, int, int, int, float, const float*, int, const float*, float*, cudaStream_t);
 int adj_regen_fwd(const float*, float*, float*, int32_t*, int, int, int, int, cudaStream_t);
 int adj_regen_bwd(const float*, const float*, const float*, const int32_t*, float*, float*, int, int, int, int, int, cudaStream_t);
@@ -83,6 +83,8 @@ static inline Operand planes_at(const float* f32, float* region, long long n) {
     bf16* hi = reinterpret_cast<bf16*>(region);
     return Operand{f32, hi, hi + al4(n) };
 }
+static inline bf16* mut(const bf16* p) { return const_cast<bf16*>(p); }
+static inline bf16* lo_or_null(const Operand& o) { return npass() == 3 ? const_cast<bf16*>(o.lo) : nullptr; }
 static int split_one(const Operand& o, long long n, cudaStream_t st) {
     const float* src[1] = {o.f32};
     bf16* hi[1] = {const_cast<bf16*>(o.hi)};
@@ -192,28 +194,31 @@ static int gnn_fwd(int kind, const float* x, const float* adj, const float* cons
         float* h_next = saved + L.conv(k, 2);
         float* pre = saved + L.conv(k, 0);   // GCN: agg = adj @ h ; GIN: pre = h + (1+eps) adj @ h
         Operand pre_op = planes_at(pre, saved + L.conv(k, 5), MHn);
+        const Operand next_op = planes_at(h_next, saved + L.conv(k, 6), MHn);
         if (kind == XGGM_KIND_GCN) {
             const float* g = cp[3 * k + 1], *b = cp[3 * k + 2];
             float* xhat = saved + L.conv(k, 1);
             float* rstd = saved + L.conv(k, 3);
             float* u = work;
-            XGGM_TRY(adj_apply(adj, h, pre, B, N, H, 1.f, nullptr, 0.f, false, 0, st));
-            if (tc) XGGM_TRY(split_one(pre_op, MHn, st));
+            // tensor-core engine: the aggregate is only ever a GEMM operand -> bf16 planes, no fp32 copy
+            XGGM_TRY(adj_apply(adj, h, tc ? nullptr : pre, tc ? mut(pre_op.hi) : nullptr, tc ? lo_or_null(pre_op) : nullptr,
+                               B, N, H, 1.f, nullptr, 0.f, false, 0, st));
             XGGM_TRY(proj_fwd(tc, pre_op, wconv[k], nullptr, h, u, M, H, H, st));
-            XGGM_TRY(layernorm_fwd(u, g, b, h_next, xhat, rstd, M, H, LN_EPS, st));
+            XGGM_TRY(layernorm_fwd(u, g, b, h_next, xhat, rstd, tc ? mut(next_op.hi) : nullptr,
+                                   tc ? lo_or_null(next_op) : nullptr, M, H, LN_EPS, st));
         } else {
             const float* eps = cp[5 * k], *bias = cp[5 * k + 2];
             const float* g = cp[5 * k + 3], *b = cp[5 * k + 4];
             float* z = saved + L.conv(k, 1);
             float* mean = saved + L.conv(k, 3);
             float* rstd = saved + L.conv(k, 4);
-            XGGM_TRY(adj_apply(adj, h, pre, B, N, H, 1.f, eps, 1.f, false, 0, st));
-            if (tc) XGGM_TRY(split_one(pre_op, MHn, st));
+            XGGM_TRY(adj_apply(adj, h, tc ? nullptr : pre, tc ? mut(pre_op.hi) : nullptr, tc ? lo_or_null(pre_op) : nullptr,
+                               B, N, H, 1.f, eps, 1.f, false, 0, st));
             XGGM_TRY(proj_fwd(tc, pre_op, wconv[k], bias, nullptr, z, M, H, H, st));
-            XGGM_TRY(gelu_ln_drop_fwd(z, g, b, nullptr, 1.f, h_next, mean, rstd, M, H, LN_EPS, 0, st));
+            XGGM_TRY(gelu_ln_drop_fwd(z, g, b, nullptr, 1.f, h_next, mean, rstd, tc ? mut(next_op.hi) : nullptr,
+                                      tc ? lo_or_null(next_op) : nullptr, M, H, LN_EPS, 0, st));
         }
-        hops[k + 1] = planes_at(h_next, saved + L.conv(k, 6), MHn);
-        if (tc) XGGM_TRY(split_one(hops[k + 1], MHn, st));
+        hops[k + 1] = next_op;
         h = h_next;
     }
     for (int j = 0; j <= nc; ++j) {
@@ -221,7 +226,7 @@ static int gnn_fwd(int kind, const float* x, const float* adj, const float* cons
         float* z = saved + L.head(j, 0);
         XGGM_TRY(proj_fwd(tc, hops[j], whead[j], bias, nullptr, z, M, H, H, st));
         XGGM_TRY(gelu_ln_drop_fwd(z, g, b, keeps ? keeps[j] : nullptr, scale, out,
-                                  saved + L.head(j, 1), saved + L.head(j, 2), M, H, LN_EPS, j > 0, st));
+                                  saved + L.head(j, 1), saved + L.head(j, 2), nullptr, nullptr, M, H, LN_EPS, j > 0, st));
     }
     return XGGM_OK;
 }
@@ -271,13 +276,15 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
     auto head_bwd = [&](int j, float* gh, int accumulate) -> int {
         XGGM_CUDA_TRY(cudaMemsetAsync(hg[4 * j + 2], 0, sizeof(float) * H, st));
         XGGM_CUDA_TRY(cudaMemsetAsync(hg[4 * j + 3], 0, sizeof(float) * H, st));
-        XGGM_TRY(gelu_ln_drop_bwd(gout, saved + L.head(j, 0), saved + L.head(j, 1), saved + L.head(j, 2),
-                                  hp[4 * j + 2], keeps ? keeps[j] : nullptr, scale, gt,
-                                  hg[4 * j + 2], hg[4 * j + 3], M, H, st));
+        XGGM_CUDA_TRY(cudaMemsetAsync(hg[4 * j + 1], 0, sizeof(float) * H, st));
+        // gz only exists as GEMM-operand planes under the tensor-core engine; its column sums (the
+        // bias gradient) are accumulated by the same kernel
         const Operand g = grad_op(gt);
-        if (tc) XGGM_TRY(split_one(g, MHn, st));
+        XGGM_TRY(gelu_ln_drop_bwd(gout, saved + L.head(j, 0), saved + L.head(j, 1), saved + L.head(j, 2),
+                                  hp[4 * j + 2], keeps ? keeps[j] : nullptr, scale, tc ? nullptr : gt,
+                                  hg[4 * j + 2], hg[4 * j + 3], hg[4 * j + 1], tc ? mut(g.hi) : nullptr,
+                                  tc ? lo_or_null(g) : nullptr, M, H, st));
         XGGM_TRY(proj_wgrad(tc, g, act(j), hg[4 * j], M, H, H, st));
-        XGGM_TRY(colsum(gt, hg[4 * j + 1], M, H, st));
         XGGM_TRY(proj_dgrad(tc, g, whead[j], gh, M, H, H, accumulate, st));
         return XGGM_OK;
     };
@@ -294,30 +301,30 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
             XGGM_CUDA_TRY(cudaMemsetAsync(cg[3 * k + 1], 0, sizeof(float) * H, st));
             XGGM_CUDA_TRY(cudaMemsetAsync(cg[3 * k + 2], 0, sizeof(float) * H, st));
             // gu = LN backward, written straight into the next-level gradient (residual path)
-            XGGM_TRY(layernorm_bwd(gh, saved + L.conv(k, 1), saved + L.conv(k, 3), g, gnext,
-                                   cg[3 * k + 1], cg[3 * k + 2], M, H, st));
             const Operand gu = grad_op(gnext);
-            if (tc) XGGM_TRY(split_one(gu, MHn, st));
+            XGGM_TRY(layernorm_bwd(gh, saved + L.conv(k, 1), saved + L.conv(k, 3), g, gnext,
+                                   cg[3 * k + 1], cg[3 * k + 2], tc ? mut(gu.hi) : nullptr,
+                                   tc ? lo_or_null(gu) : nullptr, M, H, st));
             XGGM_TRY(proj_wgrad(tc, gu, pre_op, cg[3 * k], M, H, H, st));
             XGGM_TRY(proj_dgrad(tc, gu, wconv[k], gq, M, H, H, 0, st));  // gq = gu Wc
             XGGM_TRY(bmm_nt(gq, hk, gadj, B, N, H, 1.f, nullptr, 1, nullptr, nullptr, st));
-            XGGM_TRY(adj_apply(adj, gq, gnext, B, N, H, 1.f, nullptr, 0.f, true, 1, st));
+            XGGM_TRY(adj_apply(adj, gq, gnext, nullptr, nullptr, B, N, H, 1.f, nullptr, 0.f, true, 1, st));
         } else {
             const float* eps = cp[5 * k], *g = cp[5 * k + 3];
             XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k], 0, sizeof(float), st));
             XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k + 3], 0, sizeof(float) * H, st));
             XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k + 4], 0, sizeof(float) * H, st));
-            XGGM_TRY(gelu_ln_drop_bwd(gh, saved + L.conv(k, 1), saved + L.conv(k, 3), saved + L.conv(k, 4),
-                                      g, nullptr, 1.f, gt, cg[5 * k + 3], cg[5 * k + 4], M, H, st));
+            XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k + 2], 0, sizeof(float) * H, st));
             const Operand gz = grad_op(gt);
-            if (tc) XGGM_TRY(split_one(gz, MHn, st));
+            XGGM_TRY(gelu_ln_drop_bwd(gh, saved + L.conv(k, 1), saved + L.conv(k, 3), saved + L.conv(k, 4),
+                                      g, nullptr, 1.f, tc ? nullptr : gt, cg[5 * k + 3], cg[5 * k + 4], cg[5 * k + 2],
+                                      tc ? mut(gz.hi) : nullptr, tc ? lo_or_null(gz) : nullptr, M, H, st));
             XGGM_TRY(proj_wgrad(tc, gz, pre_op, cg[5 * k + 1], M, H, H, st));
-            XGGM_TRY(colsum(gt, cg[5 * k + 2], M, H, st));
             XGGM_TRY(proj_dgrad(tc, gz, wconv[k], gq, M, H, H, 0, st));      // gpre
             // gadj += (1+eps) gpre h^T ; geps += <gpre h^T, adj>
             XGGM_TRY(bmm_nt(gq, hk, gadj, B, N, H, 1.f, eps, 1, adj, cg[5 * k], st));
             // grad h_k = gpre + (1+eps) adj^T gpre
-            XGGM_TRY(adj_apply(adj, gq, gnext, B, N, H, 1.f, eps, 1.f, true, 0, st));
+            XGGM_TRY(adj_apply(adj, gq, gnext, nullptr, nullptr, B, N, H, 1.f, eps, 1.f, true, 0, st));
         }
         XGGM_TRY(head_bwd(k, gnext, 1));
         gh = gnext;
@@ -446,14 +453,14 @@ int xggm_adj_apply_fwd(const float* adj, const float* x, float* out, int B, int 
                        float alpha0, const float* alpha_dev, float self_w, xggm_stream_t s) {
     if (B == 0) return XGGM_OK;
     XGGM_REQUIRE(adj && x && out && B >= 0);
-    return adj_apply(adj, x, out, B, N, H, alpha0, alpha_dev, self_w, false, 0, as_stream(s));
+    return adj_apply(adj, x, out, nullptr, nullptr, B, N, H, alpha0, alpha_dev, self_w, false, 0, as_stream(s));
 }
 int xggm_adj_apply_bwd(const float* adj, const float* x, const float* gout, float* gx,
                        float* gadj_raw, int B, int N, int H, float alpha0, const float* alpha_dev,
                        float self_w, int accumulate_gx, xggm_stream_t s) {
     if (B == 0) return XGGM_OK;
     XGGM_REQUIRE(adj && x && gout && gx && B >= 0);
-    XGGM_TRY(adj_apply(adj, gout, gx, B, N, H, alpha0, alpha_dev, self_w, true, accumulate_gx, as_stream(s)));
+    XGGM_TRY(adj_apply(adj, gout, gx, nullptr, nullptr, B, N, H, alpha0, alpha_dev, self_w, true, accumulate_gx, as_stream(s)));
     if (gadj_raw) XGGM_TRY(bmm_nt(gout, x, gadj_raw, B, N, H, 1.f, nullptr, 0, nullptr, nullptr, as_stream(s)));
     return XGGM_OK;
 }
@@ -462,27 +469,27 @@ int xggm_layernorm_fwd(const float* u, const float* gamma, const float* beta, fl
                        float* xhat, float* rstd, int M, int H, float eps, xggm_stream_t s) {
     if (M == 0) return XGGM_OK;
     XGGM_REQUIRE(u && gamma && beta && h && M >= 0 && H > 0);
-    return layernorm_fwd(u, gamma, beta, h, xhat, rstd, M, H, eps, as_stream(s));
+    return layernorm_fwd(u, gamma, beta, h, xhat, rstd, nullptr, nullptr, M, H, eps, as_stream(s));
 }
 int xggm_layernorm_bwd(const float* gh, const float* xhat, const float* rstd, const float* gamma,
                        float* gu, float* ggamma, float* gbeta, int M, int H, xggm_stream_t s) {
     if (M == 0) return XGGM_OK;
     XGGM_REQUIRE(gh && xhat && rstd && gamma && gu && ggamma && gbeta && M >= 0 && H > 0);
-    return layernorm_bwd(gh, xhat, rstd, gamma, gu, ggamma, gbeta, M, H, as_stream(s));
+    return layernorm_bwd(gh, xhat, rstd, gamma, gu, ggamma, gbeta, nullptr, nullptr, M, H, as_stream(s));
 }
 int xggm_gelu_ln_drop_fwd(const float* z, const float* gamma, const float* beta,
                           const uint8_t* keep, float scale, float* out, float* mean, float* rstd,
                           int M, int H, float eps, int accumulate, xggm_stream_t s) {
     if (M == 0) return XGGM_OK;
     XGGM_REQUIRE(z && gamma && beta && out && M >= 0 && H > 0);
-    return gelu_ln_drop_fwd(z, gamma, beta, keep, scale, out, mean, rstd, M, H, eps, accumulate, as_stream(s));
+    return gelu_ln_drop_fwd(z, gamma, beta, keep, scale, out, mean, rstd, nullptr, nullptr, M, H, eps, accumulate, as_stream(s));
 }
 int xggm_gelu_ln_drop_bwd(const float* gout, const float* z, const float* mean, const float* rstd,
                           const float* gamma, const uint8_t* keep, float scale, float* gz,
                           float* ggamma, float* gbeta, int M, int H, xggm_stream_t s) {
     if (M == 0) return XGGM_OK;
     XGGM_REQUIRE(gout && z && mean && rstd && gamma && gz && ggamma && gbeta && M >= 0 && H > 0);
-    return gelu_ln_drop_bwd(gout, z, mean, rstd, gamma, keep, scale, gz, ggamma, gbeta, M, H, as_stream(s));
+    return gelu_ln_drop_bwd(gout, z, mean, rstd, gamma, keep, scale, gz, ggamma, gbeta, nullptr, nullptr, nullptr, M, H, as_stream(s));
 }
 
 int xggm_adj_regen_fwd(const float* x, float* adj_out, float* S, int32_t* amax, int B, int N,

@@ -154,6 +154,7 @@ struct Params {
     int ldc;
     int accumulate;      // C += (non-atomic)
     int atomic;          // split-K partial sums: atomicAdd into a pre-zeroed / pre-initialised C
+    int vec4;            // C / resid / bias are 16-byte aligned and N % 4 == 0: float4 epilogue
 };
 
 template <int BN, int NPASS>
@@ -312,27 +313,67 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
             const int mrow0 = m0 + q * 32;
+            const int rows = min(32, p.M - mrow0);
+            const bool vec = p.vec4 && !p.atomic;
+            // float4 domain: lane -> (row = 4*it + lane/8, 4 columns at 4*(lane%8))
+            const int rsub = lane >> 3, c4 = (lane & 7) * 4;
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 const int ncol0 = n0 + c * 32;
                 if (ncol0 >= p.N || mrow0 >= p.M) break;  // warp-uniform
+                // (1) issue this chunk's bias / residual / accumulate loads first: their latency hides
+                //     behind the TMEM load and the smem transpose below
+                float4 e[8];
+                const int nv = ncol0 + c4;
+                const bool nv_ok = vec && nv < p.N;  // N % 4 == 0 in vec mode: no straddling
+                if (nv_ok) {
+                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (lead && p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + nv));
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        e[it] = bv;
+                        const int row = 4 * it + rsub;
+                        if (lead && p.resid && row < rows) {
+                            const float4 r = __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)(mrow0 + row) * p.ldc + nv));
+                            e[it].x += r.x; e[it].y += r.y; e[it].z += r.z; e[it].w += r.w;
+                        }
+                        if (p.accumulate && row < rows) {
+                            const float4 r = *reinterpret_cast<const float4*>(p.C + (size_t)(mrow0 + row) * p.ldc + nv);
+                            e[it].x += r.x; e[it].y += r.y; e[it].z += r.z; e[it].w += r.w;
+                        }
+                    }
+                }
+                // (2) accumulator chunk: TMEM -> registers (thread = row) -> smem transpose
                 uint32_t v[32];
                 tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) st[lane * EPI_PITCH + j] = __uint_as_float(v[j]);
                 __syncwarp();
-                const int n = ncol0 + lane;
-                const bool n_ok = n < p.N;
-                const float bv = (lead && p.bias && n_ok) ? p.bias[n] : 0.f;
-                const int rows = min(32, p.M - mrow0);
-                if (n_ok) {
+                // (3) coalesced stores
+                if (vec) {
+                    if (nv_ok) {
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int row = 4 * it + rsub;
+                            if (row < rows) {
+                                const float* sp = st + row * EPI_PITCH + c4;
+                                *reinterpret_cast<float4*>(p.C + (size_t)(mrow0 + row) * p.ldc + nv) =
+                                    make_float4(sp[0] + e[it].x, sp[1] + e[it].y, sp[2] + e[it].z, sp[3] + e[it].w);
+                            }
+                        }
+                    }
+                } else {
+                    const int n = ncol0 + lane;
+                    if (n < p.N) {
+                        const float bv = (lead && p.bias) ? p.bias[n] : 0.f;
 #pragma unroll 4
-                    for (int i = 0; i < rows; ++i) {
-                        float val = st[i * EPI_PITCH + lane] + bv;
-                        const size_t o = (size_t)(mrow0 + i) * p.ldc + n;
-                        if (lead && p.resid) val += p.resid[o];
-                        if (p.atomic) atomicAdd(&p.C[o], val);
-                        else p.C[o] = p.accumulate ? p.C[o] + val : val;
+                        for (int i = 0; i < rows; ++i) {
+                            float val = st[i * EPI_PITCH + lane] + bv;
+                            const size_t o = (size_t)(mrow0 + i) * p.ldc + n;
+                            if (lead && p.resid) val += p.resid[o];
+                            if (p.atomic) atomicAdd(&p.C[o], val);
+                            else p.C[o] = p.accumulate ? p.C[o] + val : val;
+                        }
                     }
                 }
                 __syncwarp();
@@ -527,6 +568,8 @@ int gemm_tc(bool a_mn, bool b_mn, const __nv_bfloat16* a_hi, const __nv_bfloat16
     p.tiles_m = tiles_m; p.tiles_n = tiles_n; p.splits = splits; p.kb_per_split = kb_per_split;
     p.bias = bias; p.resid = resid; p.C = C; p.ldc = N;
     p.accumulate = accumulate; p.atomic = splits > 1 ? 1 : 0;
+    p.vec4 = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(resid) |
+                               reinterpret_cast<uintptr_t>(bias)) & 15) == 0;
     if (splits > 1 && !accumulate)
         XGGM_CUDA_TRY(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
     const int grid = min(sms, tiles_m * tiles_n * splits);

@@ -3,6 +3,8 @@
 //   bmm_nt    : out[b] = p[b] q[b]^T  ([N,H] x [H,N])             (gadj, pair scores)
 //   adj_regen : sigmoid(S / colmax) with zero diagonal, fwd + bwd  (ggm.py:225-228)
 //   gat_attn  : dense masked attention of GATConv                  (gat.py:25-49)
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace xggm {
@@ -10,13 +12,20 @@ namespace xggm {
 constexpr int MAX_NODES = 104;  // smem sizing of the N x N stages (cfg-4 sweep goes to N=100)
 
 // ----------------------------------------------------------------- adj_apply
-// grid (ceil(H/256), B); thread = one feature column; adjacency in smem (broadcast reads);
-// node rows are walked in register tiles of RT.
+typedef __nv_bfloat16 bf16;
+__device__ __forceinline__ void split_bf16(float v, bf16& h, bf16& l) {
+    h = __float2bfloat16_rn(v);
+    const float hf = __bfloat162float(h);
+    l = __float2bfloat16_rn((hf - hf == 0.f) ? v - hf : 0.f);
+}
+
+// Generic kernel (any N <= MAX_NODES): grid (ceil(H/256), B); thread = one feature column;
+// adjacency in smem (broadcast reads); node rows are walked in register tiles of RT.
 template <int RT, bool TRANS>
 __global__ void __launch_bounds__(256)
 adj_apply_kernel(const float* __restrict__ adj, const float* __restrict__ x,
-                 float* __restrict__ out, int N, int H, float alpha0,
-                 const float* __restrict__ alpha_dev, float self_w, int accumulate) {
+                 float* __restrict__ out, bf16* __restrict__ hi, bf16* __restrict__ lo, int N, int H,
+                 float alpha0, const float* __restrict__ alpha_dev, float self_w, int accumulate) {
     extern __shared__ float s_adj[];  // [N][N], s_adj[i*N+j] = coefficient of x_j in out_i
     const int b = blockIdx.y;
     const float* ab = adj + (size_t)b * N * N;
@@ -29,7 +38,7 @@ adj_apply_kernel(const float* __restrict__ adj, const float* __restrict__ x,
     if (c >= H) return;
     const float alpha = alpha0 + (alpha_dev ? alpha_dev[0] : 0.f);
     const float* xb = x + (size_t)b * N * H + c;
-    float* ob = out + (size_t)b * N * H + c;
+    const size_t ob = (size_t)b * N * H + c;
     for (int i0 = 0; i0 < N; i0 += RT) {
         float acc[RT];
 #pragma unroll
@@ -45,22 +54,98 @@ adj_apply_kernel(const float* __restrict__ adj, const float* __restrict__ x,
             if (i0 + i >= N) break;
             float v = alpha * acc[i];
             if (self_w != 0.f) v = fmaf(self_w, xb[(size_t)(i0 + i) * H], v);
-            float* o = ob + (size_t)(i0 + i) * H;
-            *o = accumulate ? *o + v : v;
+            const size_t o = ob + (size_t)(i0 + i) * H;
+            if (out) {
+                if (accumulate) v += out[o];
+                out[o] = v;
+            }
+            if (hi) {
+                bf16 h, l;
+                split_bf16(v, h, l);
+                hi[o] = h;
+                if (lo) lo[o] = l;
+            }
         }
     }
 }
 
-int adj_apply(const float* adj, const float* x, float* out, int B, int N, int H, float alpha0,
-              const float* alpha_dev, float self_w, bool trans, int accumulate, cudaStream_t st) {
+// obj36 fast path: N = 36 exactly.  grid (ceil(H/256), B), 128 threads, each thread owns two
+// adjacent feature columns and keeps their 36 node values in registers (one coalesced 8-byte
+// load per node row); adjacency coefficients come from smem as broadcast LDS.128, so the inner
+// loop is FMA-bound (8 FMAs per LDS).  Fully unrolled: 36 x 36 x 2 FMAs per thread.
+template <bool TRANS>
+__global__ void __launch_bounds__(128)
+adj_apply36_kernel(const float* __restrict__ adj, const float* __restrict__ x, float* __restrict__ out,
+                   bf16* __restrict__ hi, bf16* __restrict__ lo, int H, float alpha0,
+                   const float* __restrict__ alpha_dev, float self_w, int accumulate) {
+    constexpr int N = 36;
+    __shared__ __align__(16) float s_adj[N * N];
+    const int b = blockIdx.y;
+    const float* ab = adj + (size_t)b * N * N;
+    for (int e = threadIdx.x; e < N * N; e += 128) {
+        const int i = e / N, j = e - i * N;
+        s_adj[e] = TRANS ? ab[j * N + i] : ab[e];
+    }
+    __syncthreads();
+    const int c = blockIdx.x * 256 + 2 * threadIdx.x;
+    if (c >= H) return;
+    const float alpha = alpha0 + (alpha_dev ? alpha_dev[0] : 0.f);
+    const size_t base = (size_t)b * N * H + c;
+    float2 xv[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) xv[j] = *reinterpret_cast<const float2*>(x + base + (size_t)j * H);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        float ax = 0.f, ay = 0.f;
+#pragma unroll
+        for (int j4 = 0; j4 < N / 4; ++j4) {
+            const float4 a = *reinterpret_cast<const float4*>(&s_adj[i * N + 4 * j4]);
+            ax = fmaf(a.x, xv[4 * j4].x, ax);     ay = fmaf(a.x, xv[4 * j4].y, ay);
+            ax = fmaf(a.y, xv[4 * j4 + 1].x, ax); ay = fmaf(a.y, xv[4 * j4 + 1].y, ay);
+            ax = fmaf(a.z, xv[4 * j4 + 2].x, ax); ay = fmaf(a.z, xv[4 * j4 + 2].y, ay);
+            ax = fmaf(a.w, xv[4 * j4 + 3].x, ax); ay = fmaf(a.w, xv[4 * j4 + 3].y, ay);
+        }
+        float vx = alpha * ax, vy = alpha * ay;
+        if (self_w != 0.f) { vx = fmaf(self_w, xv[i].x, vx); vy = fmaf(self_w, xv[i].y, vy); }
+        const size_t o = base + (size_t)i * H;
+        if (out) {
+            if (accumulate) {
+                const float2 p = *reinterpret_cast<const float2*>(out + o);
+                vx += p.x; vy += p.y;
+            }
+            *reinterpret_cast<float2*>(out + o) = make_float2(vx, vy);
+        }
+        if (hi) {
+            bf16 hx, lx, hy, ly;
+            split_bf16(vx, hx, lx);
+            split_bf16(vy, hy, ly);
+            *reinterpret_cast<__nv_bfloat162*>(hi + o) = __halves2bfloat162(hx, hy);
+            if (lo) *reinterpret_cast<__nv_bfloat162*>(lo + o) = __halves2bfloat162(lx, ly);
+        }
+    }
+}
+
+// out (fp32, optional) and / or hi+lo (bf16 planes, optional) receive
+//   self_w * x + alpha * (adj | adj^T) @ x      (+ previous out when accumulate)
+int adj_apply(const float* adj, const float* x, float* out, bf16* hi, bf16* lo, int B, int N, int H,
+              float alpha0, const float* alpha_dev, float self_w, bool trans, int accumulate, cudaStream_t st) {
     if (B <= 0) return XGGM_OK;
-    XGGM_REQUIRE(N >= 1 && N <= MAX_NODES && H >= 1);
-    dim3 grid(ceil_div(H, 256), B);
-    const size_t smem = sizeof(float) * N * N;
-    if (trans)
-        adj_apply_kernel<12, true><<<grid, 256, smem, st>>>(adj, x, out, N, H, alpha0, alpha_dev, self_w, accumulate);
-    else
-        adj_apply_kernel<12, false><<<grid, 256, smem, st>>>(adj, x, out, N, H, alpha0, alpha_dev, self_w, accumulate);
+    XGGM_REQUIRE(N >= 1 && N <= MAX_NODES && H >= 1 && (out || hi));
+    auto al8 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; };
+    if (N == 36 && H % 2 == 0 && al8(x) && al8(out) && al8(hi) && al8(lo)) {
+        dim3 grid(ceil_div(H, 256), B);
+        if (trans)
+            adj_apply36_kernel<true><<<grid, 128, 0, st>>>(adj, x, out, hi, lo, H, alpha0, alpha_dev, self_w, accumulate);
+        else
+            adj_apply36_kernel<false><<<grid, 128, 0, st>>>(adj, x, out, hi, lo, H, alpha0, alpha_dev, self_w, accumulate);
+    } else {
+        dim3 grid(ceil_div(H, 256), B);
+        const size_t smem = sizeof(float) * N * N;
+        if (trans)
+            adj_apply_kernel<12, true><<<grid, 256, smem, st>>>(adj, x, out, hi, lo, N, H, alpha0, alpha_dev, self_w, accumulate);
+        else
+            adj_apply_kernel<12, false><<<grid, 256, smem, st>>>(adj, x, out, hi, lo, N, H, alpha0, alpha_dev, self_w, accumulate);
+    }
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
@@ -307,7 +392,7 @@ int adj_regen_bwd(const float* gadj, const float* x, const float* S, const int32
         XGGM_CUDA_TRY(cudaFuncSetAttribute(adj_regen_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     adj_regen_bwd_kernel<<<B, 256, smem, st>>>(gadj, S, amax, work, N, squash);
     XGGM_LAUNCH_CHECK();
-    return adj_apply(work, x, gx, B, N, H, 1.f, nullptr, 0.f, false, accumulate_gx, st);
+    return adj_apply(work, x, gx, nullptr, nullptr, B, N, H, 1.f, nullptr, 0.f, false, accumulate_gx, st);
 }
 
 // ------------------------------------------------------------------ GAT attn
@@ -377,8 +462,8 @@ int gat_attn_fwd(const float* h, const float* a, const float* adj, float* out, f
     XGGM_REQUIRE(N >= 1 && N <= MAX_NODES);
     gat_scores_kernel<<<B, 256, sizeof(float) * 2 * N, st>>>(h, a, adj, att, N, H, slope);
     XGGM_LAUNCH_CHECK();
-    if (!apply_elu) return adj_apply(att, h, out, B, N, H, 1.f, nullptr, 0.f, false, 0, st);
-    XGGM_TRY(adj_apply(att, h, pre, B, N, H, 1.f, nullptr, 0.f, false, 0, st));
+    if (!apply_elu) return adj_apply(att, h, out, nullptr, nullptr, B, N, H, 1.f, nullptr, 0.f, false, 0, st);
+    XGGM_TRY(adj_apply(att, h, pre, nullptr, nullptr, B, N, H, 1.f, nullptr, 0.f, false, 0, st));
     const long long n = (long long)B * N * H;
     elu_fwd_kernel<<<ceil_div(n, 256), 256, 0, st>>>(pre, out, n);
     XGGM_LAUNCH_CHECK();
@@ -466,7 +551,7 @@ int gat_attn_bwd(const float* gout, const float* h, const float* a, const float*
         XGGM_LAUNCH_CHECK();
         gpre = work;
     }
-    XGGM_TRY(adj_apply(att, gpre, gh, B, N, H, 1.f, nullptr, 0.f, true, 0, st));   // gh = att^T gpre
+    XGGM_TRY(adj_apply(att, gpre, gh, nullptr, nullptr, B, N, H, 1.f, nullptr, 0.f, true, 0, st));   // gh = att^T gpre
     XGGM_TRY(bmm_nt(gpre, h, gatt, B, N, H, 1.f, nullptr, 0, nullptr, nullptr, st));                                   // gatt = gpre h^T
     const size_t smem = sizeof(float) * (4 * (size_t)N + (size_t)N * N);
     gat_scores_bwd_kernel<<<B, 256, smem, st>>>(h, a, adj, att, gatt, gh, ga, N, H, slope);

@@ -1,30 +1,295 @@
 // Row-wise fused epilogues of the graph block: LayerNorm and the jump-knowledge head
-// tail  dropout(LN(GeLU(z))).  One warp owns one row (H = 768 -> 24 values per lane);
-// reductions are warp shuffles, statistics are fp32 two-pass (mean, then centred
-// sum of squares) like torch's LayerNorm.  Column-wise parameter gradients
-// (gamma/beta) are accumulated per warp in shared memory and flushed once per CTA.
+// tail  dropout(LN(GeLU(z))), forward and backward.
+//
+// Fast path (H % 128 == 0, H <= 1024; H = 768 in X-GGM): one warp owns one row and keeps it in
+// registers -- lane l holds the float4 at columns 128*i + 4*l -- so every tensor is read exactly
+// once with 512-byte coalesced warp accesses, GeLU/erf is evaluated once per element, statistics
+// are fp32 two-pass (mean, then centred sum of squares, as torch's LayerNorm) via warp shuffles,
+// and the column-wise parameter gradients (gamma / beta / bias) accumulate in registers across
+// the rows a warp walks, are combined across the CTA's warps in shared memory and flushed with
+// one atomicAdd per column per CTA.  Each kernel can also emit the bf16 hi/lo planes of its
+// output (the tensor-core operand format of gemm_tc.cu), which removes a separate split pass.
+// Generic path (any H): the same math with strided loops.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace xggm {
 
-constexpr int ROW_WARPS = 4;        // warps per CTA
-constexpr int ROWS_PER_WARP = 8;    // rows each warp walks through
+typedef __nv_bfloat16 bf16;
 
-__device__ __forceinline__ void row_range(int M, int& r0, int& r1) {
-    const int warp = threadIdx.x >> 5;
-    const int base = (blockIdx.x * ROW_WARPS + warp) * ROWS_PER_WARP;
-    r0 = base;
-    r1 = min(M, base + ROWS_PER_WARP);
+constexpr int ROW_WARPS = 8;  // warps per CTA (fast path)
+
+__device__ __forceinline__ void split_store4(bf16* hi, bf16* lo, size_t off, float a, float b, float c, float d) {
+    const float v[4] = {a, b, c, d};
+    bf16 h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        h[i] = __float2bfloat16_rn(v[i]);
+        const float hf = __bfloat162float(h[i]);
+        l[i] = __float2bfloat16_rn((hf - hf == 0.f) ? v[i] - hf : 0.f);
+    }
+    __nv_bfloat162 h01 = __halves2bfloat162(h[0], h[1]), h23 = __halves2bfloat162(h[2], h[3]);
+    *reinterpret_cast<uint2*>(hi + off) = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
+    if (lo) {
+        __nv_bfloat162 l01 = __halves2bfloat162(l[0], l[1]), l23 = __halves2bfloat162(l[2], l[3]);
+        *reinterpret_cast<uint2*>(lo + off) = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
+    }
 }
 
-static inline int row_grid(int M) { return ceil_div(M, ROW_WARPS * ROWS_PER_WARP); }
+template <int NV>
+__device__ __forceinline__ void load_row(const float* __restrict__ p, int lane, float (&v)[NV * 4]) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float4 t = *reinterpret_cast<const float4*>(p + 128 * i + 4 * lane);
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+}
+template <int NV>
+__device__ __forceinline__ void store_row(float* __restrict__ p, int lane, const float (&v)[NV * 4]) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+        *reinterpret_cast<float4*>(p + 128 * i + 4 * lane) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+template <int NV>
+__device__ __forceinline__ void store_planes(bf16* hi, bf16* lo, size_t row_off, int lane, const float (&v)[NV * 4]) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+        split_store4(hi, lo, row_off + 128 * i + 4 * lane, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+template <int NV>
+__device__ __forceinline__ void row_stats(const float (&v)[NV * 4], float inv_h, float eps, float& mean, float& rstd) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV * 4; ++i) s += v[i];
+    mean = warp_sum(s) * inv_h;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV * 4; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+    rstd = 1.0f / sqrtf(warp_sum(q) * inv_h + eps);
+}
+// combine per-warp register column accumulators across the CTA and add them to dst[H]
+template <int NV>
+__device__ __forceinline__ void flush_columns(const float (&acc)[NV * 4], float* __restrict__ dst, float* sm) {
+    constexpr int H = NV * 128;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+        *reinterpret_cast<float4*>(sm + warp * H + 128 * i + 4 * lane) =
+            make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < H; c += blockDim.x) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < ROW_WARPS; ++w) a += sm[w * H + c];
+        atomicAdd(&dst[c], a);
+    }
+}
 
-// ---------------------------------------------------------------- LayerNorm fwd
+// ================================================================== fast kernels
+template <int NV>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
-layernorm_fwd_kernel(const float* __restrict__ u, const float* __restrict__ gamma,
-                     const float* __restrict__ beta, float* __restrict__ h,
-                     float* __restrict__ xhat, float* __restrict__ rstd_out, int M, int H,
-                     float eps) {
+ln_fwd_fast(const float* __restrict__ u, const float* __restrict__ gamma, const float* __restrict__ beta,
+            float* __restrict__ h, float* __restrict__ xhat, float* __restrict__ rstd_out,
+            bf16* __restrict__ hi, bf16* __restrict__ lo, int M, float eps) {
+    constexpr int H = NV * 128;
+    const int lane = threadIdx.x & 31;
+    const int wid = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5), nw = gridDim.x * ROW_WARPS;
+    float g[NV * 4], b[NV * 4];
+    load_row<NV>(gamma, lane, g);
+    load_row<NV>(beta, lane, b);
+    for (int r = wid; r < M; r += nw) {
+        float v[NV * 4];
+        load_row<NV>(u + (size_t)r * H, lane, v);
+        float mean, rstd;
+        row_stats<NV>(v, 1.0f / (float)H, eps, mean, rstd);
+#pragma unroll
+        for (int i = 0; i < NV * 4; ++i) v[i] = (v[i] - mean) * rstd;
+        if (xhat) store_row<NV>(xhat + (size_t)r * H, lane, v);
+#pragma unroll
+        for (int i = 0; i < NV * 4; ++i) v[i] = fmaf(v[i], g[i], b[i]);
+        store_row<NV>(h + (size_t)r * H, lane, v);
+        if (hi) store_planes<NV>(hi, lo, (size_t)r * H, lane, v);
+        if (lane == 0 && rstd_out) rstd_out[r] = rstd;
+    }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+ln_bwd_fast(const float* __restrict__ gh, const float* __restrict__ xhat, const float* __restrict__ rstd,
+            const float* __restrict__ gamma, float* __restrict__ gu, float* __restrict__ ggamma,
+            float* __restrict__ gbeta, bf16* __restrict__ hi, bf16* __restrict__ lo, int M) {
+    constexpr int H = NV * 128;
+    extern __shared__ float sm[];
+    const int lane = threadIdx.x & 31;
+    const int wid = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5), nw = gridDim.x * ROW_WARPS;
+    float gam[NV * 4], ag[NV * 4], ab[NV * 4];
+    load_row<NV>(gamma, lane, gam);
+#pragma unroll
+    for (int i = 0; i < NV * 4; ++i) { ag[i] = 0.f; ab[i] = 0.f; }
+    for (int r = wid; r < M; r += nw) {
+        float g[NV * 4], xh[NV * 4];
+        load_row<NV>(gh + (size_t)r * H, lane, g);
+        load_row<NV>(xhat + (size_t)r * H, lane, xh);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV * 4; ++i) {
+            const float d = g[i] * gam[i];
+            s1 += d;
+            s2 = fmaf(d, xh[i], s2);
+        }
+        const float c1 = warp_sum(s1) / (float)H, c2 = warp_sum(s2) / (float)H;
+        const float rs = rstd[r];
+#pragma unroll
+        for (int i = 0; i < NV * 4; ++i) {
+            ag[i] = fmaf(g[i], xh[i], ag[i]);
+            ab[i] += g[i];
+            g[i] = rs * (g[i] * gam[i] - c1 - xh[i] * c2);
+        }
+        store_row<NV>(gu + (size_t)r * H, lane, g);
+        if (hi) store_planes<NV>(hi, lo, (size_t)r * H, lane, g);
+    }
+    flush_columns<NV>(ag, ggamma, sm);
+    flush_columns<NV>(ab, gbeta, sm);
+}
+
+__device__ __forceinline__ void load_keep4(const uint8_t* __restrict__ k, size_t off, bool (&m)[4]) {
+    const uchar4 t = *reinterpret_cast<const uchar4*>(k + off);
+    m[0] = t.x != 0; m[1] = t.y != 0; m[2] = t.z != 0; m[3] = t.w != 0;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+gld_fwd_fast(const float* __restrict__ z, const float* __restrict__ gamma, const float* __restrict__ beta,
+             const uint8_t* __restrict__ keep, float scale, float* __restrict__ out,
+             float* __restrict__ mean_out, float* __restrict__ rstd_out, bf16* __restrict__ hi,
+             bf16* __restrict__ lo, int M, float eps, int accumulate) {
+    constexpr int H = NV * 128;
+    const int lane = threadIdx.x & 31;
+    const int wid = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5), nw = gridDim.x * ROW_WARPS;
+    float g[NV * 4], b[NV * 4];
+    load_row<NV>(gamma, lane, g);
+    load_row<NV>(beta, lane, b);
+    for (int r = wid; r < M; r += nw) {
+        const size_t ro = (size_t)r * H;
+        float v[NV * 4];
+        load_row<NV>(z + ro, lane, v);
+#pragma unroll
+        for (int i = 0; i < NV * 4; ++i) v[i] = gelu_erf(v[i]);
+        float mean, rstd;
+        row_stats<NV>(v, 1.0f / (float)H, eps, mean, rstd);
+#pragma unroll
+        for (int i = 0; i < NV * 4; ++i) v[i] = fmaf((v[i] - mean) * rstd, g[i], b[i]);
+        if (keep) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                bool m[4];
+                load_keep4(keep, ro + 128 * i + 4 * lane, m);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[4 * i + j] = m[j] ? v[4 * i + j] * scale : 0.f;
+            }
+        }
+        if (accumulate) {
+            float o[NV * 4];
+            load_row<NV>(out + ro, lane, o);
+#pragma unroll
+            for (int i = 0; i < NV * 4; ++i) v[i] += o[i];
+        }
+        store_row<NV>(out + ro, lane, v);
+        if (hi) store_planes<NV>(hi, lo, ro, lane, v);
+        if (lane == 0) {
+            if (mean_out) mean_out[r] = mean;
+            if (rstd_out) rstd_out[r] = rstd;
+        }
+    }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(ROW_WARPS * 32, 1)
+gld_bwd_fast(const float* __restrict__ gout, const float* __restrict__ z, const float* __restrict__ mean,
+             const float* __restrict__ rstd, const float* __restrict__ gamma, const uint8_t* __restrict__ keep,
+             float scale, float* __restrict__ gz, float* __restrict__ ggamma, float* __restrict__ gbeta,
+             float* __restrict__ gbias, bf16* __restrict__ hi, bf16* __restrict__ lo, int M) {
+    constexpr int H = NV * 128;
+    extern __shared__ float sm[];
+    const int lane = threadIdx.x & 31;
+    const int wid = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5), nw = gridDim.x * ROW_WARPS;
+    float ag[NV * 4], ab[NV * 4], az[NV * 4];
+#pragma unroll
+    for (int i = 0; i < NV * 4; ++i) { ag[i] = 0.f; ab[i] = 0.f; az[i] = 0.f; }
+    for (int r = wid; r < M; r += nw) {
+        const size_t ro = (size_t)r * H;
+        float gy[NV * 4], zv[NV * 4], yh[NV * 4];
+        load_row<NV>(gout + ro, lane, gy);
+        load_row<NV>(z + ro, lane, zv);
+        if (keep) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                bool m[4];
+                load_keep4(keep, ro + 128 * i + 4 * lane, m);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) gy[4 * i + j] = m[j] ? gy[4 * i + j] * scale : 0.f;
+            }
+        }
+        const float mu = mean[r], rs = rstd[r];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const float4 gm = *reinterpret_cast<const float4*>(gamma + 128 * i + 4 * lane);
+            const float gmv[4] = {gm.x, gm.y, gm.z, gm.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int e = 4 * i + j;
+                // one erf per element: cdf feeds both gelu(z) and its derivative
+                const float cdf = 0.5f * (1.0f + erff(zv[e] * 0.70710678118654752440f));
+                yh[e] = (zv[e] * cdf - mu) * rs;
+                const float pdf = 0.39894228040143267794f * expf(-0.5f * zv[e] * zv[e]);
+                zv[e] = cdf + zv[e] * pdf;  // gelu'(z)
+                ag[e] = fmaf(gy[e], yh[e], ag[e]);
+                ab[e] += gy[e];
+                gy[e] *= gmv[j];            // d = gy * gamma
+                s1 += gy[e];
+                s2 = fmaf(gy[e], yh[e], s2);
+            }
+        }
+        const float c1 = warp_sum(s1) / (float)H, c2 = warp_sum(s2) / (float)H;
+#pragma unroll
+        for (int i = 0; i < NV * 4; ++i) {
+            gy[i] = rs * (gy[i] - c1 - yh[i] * c2) * zv[i];
+            az[i] += gy[i];
+        }
+        if (gz) store_row<NV>(gz + ro, lane, gy);
+        if (hi) store_planes<NV>(hi, lo, ro, lane, gy);
+    }
+    flush_columns<NV>(ag, ggamma, sm);
+    flush_columns<NV>(ab, gbeta, sm);
+    if (gbias) flush_columns<NV>(az, gbias, sm);
+}
+
+// ================================================================== generic kernels (any H)
+constexpr int GEN_WARPS = 4;
+constexpr int GEN_ROWS = 8;
+__device__ __forceinline__ void row_range(int M, int& r0, int& r1) {
+    const int base = (blockIdx.x * GEN_WARPS + (threadIdx.x >> 5)) * GEN_ROWS;
+    r0 = base;
+    r1 = min(M, base + GEN_ROWS);
+}
+static inline int gen_grid(int M) { return ceil_div(M, GEN_WARPS * GEN_ROWS); }
+
+__device__ __forceinline__ void split_store1(bf16* hi, bf16* lo, size_t o, float v) {
+    const bf16 h = __float2bfloat16_rn(v);
+    hi[o] = h;
+    if (lo) {
+        const float hf = __bfloat162float(h);
+        lo[o] = __float2bfloat16_rn((hf - hf == 0.f) ? v - hf : 0.f);
+    }
+}
+
+__global__ void __launch_bounds__(GEN_WARPS * 32)
+ln_fwd_gen(const float* __restrict__ u, const float* __restrict__ gamma, const float* __restrict__ beta,
+           float* __restrict__ h, float* __restrict__ xhat, float* __restrict__ rstd_out,
+           bf16* __restrict__ hi, bf16* __restrict__ lo, int M, int H, float eps) {
     const int lane = threadIdx.x & 31;
     int r0, r1;
     row_range(M, r0, r1);
@@ -37,24 +302,25 @@ layernorm_fwd_kernel(const float* __restrict__ u, const float* __restrict__ gamm
         for (int c = lane; c < H; c += 32) { const float d = ur[c] - mean; q = fmaf(d, d, q); }
         const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)H + eps);
         for (int c = lane; c < H; c += 32) {
+            const size_t o = (size_t)r * H + c;
             const float xh = (ur[c] - mean) * rstd;
-            if (xhat) xhat[(size_t)r * H + c] = xh;
-            h[(size_t)r * H + c] = fmaf(xh, gamma[c], beta[c]);
+            if (xhat) xhat[o] = xh;
+            const float y = fmaf(xh, gamma[c], beta[c]);
+            h[o] = y;
+            if (hi) split_store1(hi, lo, o, y);
         }
         if (lane == 0 && rstd_out) rstd_out[r] = rstd;
     }
 }
 
-// ---------------------------------------------------------------- LayerNorm bwd
-// smem: [ROW_WARPS][2][H] private column accumulators
-__global__ void __launch_bounds__(ROW_WARPS * 32)
-layernorm_bwd_kernel(const float* __restrict__ gh, const float* __restrict__ xhat,
-                     const float* __restrict__ rstd, const float* __restrict__ gamma,
-                     float* __restrict__ gu, float* __restrict__ ggamma,
-                     float* __restrict__ gbeta, int M, int H) {
+// smem: [GEN_WARPS][3][H] private column accumulators
+__global__ void __launch_bounds__(GEN_WARPS * 32)
+ln_bwd_gen(const float* __restrict__ gh, const float* __restrict__ xhat, const float* __restrict__ rstd,
+           const float* __restrict__ gamma, float* __restrict__ gu, float* __restrict__ ggamma,
+           float* __restrict__ gbeta, bf16* __restrict__ hi, bf16* __restrict__ lo, int M, int H) {
     extern __shared__ float sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* sg = sm + (size_t)warp * 2 * H;
+    float* sg = sm + (size_t)warp * 3 * H;
     float* sb = sg + H;
     for (int c = lane; c < H; c += 32) { sg[c] = 0.f; sb[c] = 0.f; }
     int r0, r1;
@@ -71,8 +337,11 @@ layernorm_bwd_kernel(const float* __restrict__ gh, const float* __restrict__ xha
         const float c1 = warp_sum(s1) / (float)H, c2 = warp_sum(s2) / (float)H;
         const float rs = rstd[r];
         for (int c = lane; c < H; c += 32) {
+            const size_t o = (size_t)r * H + c;
             const float g = gr[c], xh = xr[c];
-            gu[(size_t)r * H + c] = rs * (g * gamma[c] - c1 - xh * c2);
+            const float v = rs * (g * gamma[c] - c1 - xh * c2);
+            gu[o] = v;
+            if (hi) split_store1(hi, lo, o, v);
             sg[c] = fmaf(g, xh, sg[c]);
             sb[c] += g;
         }
@@ -81,18 +350,17 @@ layernorm_bwd_kernel(const float* __restrict__ gh, const float* __restrict__ xha
     for (int c = threadIdx.x; c < H; c += blockDim.x) {
         float a = 0.f, b = 0.f;
 #pragma unroll
-        for (int w = 0; w < ROW_WARPS; ++w) { a += sm[(size_t)w * 2 * H + c]; b += sm[(size_t)w * 2 * H + H + c]; }
+        for (int w = 0; w < GEN_WARPS; ++w) { a += sm[(size_t)w * 3 * H + c]; b += sm[(size_t)w * 3 * H + H + c]; }
         atomicAdd(&ggamma[c], a);
         atomicAdd(&gbeta[c], b);
     }
 }
 
-// ------------------------------------------------- dropout(LN(GeLU(z))) forward
-__global__ void __launch_bounds__(ROW_WARPS * 32)
-gelu_ln_drop_fwd_kernel(const float* __restrict__ z, const float* __restrict__ gamma,
-                        const float* __restrict__ beta, const uint8_t* __restrict__ keep,
-                        float scale, float* __restrict__ out, float* __restrict__ mean_out,
-                        float* __restrict__ rstd_out, int M, int H, float eps, int accumulate) {
+__global__ void __launch_bounds__(GEN_WARPS * 32)
+gld_fwd_gen(const float* __restrict__ z, const float* __restrict__ gamma, const float* __restrict__ beta,
+            const uint8_t* __restrict__ keep, float scale, float* __restrict__ out,
+            float* __restrict__ mean_out, float* __restrict__ rstd_out, bf16* __restrict__ hi,
+            bf16* __restrict__ lo, int M, int H, float eps, int accumulate) {
     const int lane = threadIdx.x & 31;
     int r0, r1;
     row_range(M, r0, r1);
@@ -108,7 +376,9 @@ gelu_ln_drop_fwd_kernel(const float* __restrict__ z, const float* __restrict__ g
             const size_t o = (size_t)r * H + c;
             float y = fmaf((gelu_erf(zr[c]) - mean) * rstd, gamma[c], beta[c]);
             if (keep) y = keep[o] ? y * scale : 0.f;
-            out[o] = accumulate ? out[o] + y : y;
+            if (accumulate) y += out[o];
+            out[o] = y;
+            if (hi) split_store1(hi, lo, o, y);
         }
         if (lane == 0) {
             if (mean_out) mean_out[r] = mean;
@@ -117,18 +387,17 @@ gelu_ln_drop_fwd_kernel(const float* __restrict__ z, const float* __restrict__ g
     }
 }
 
-// ------------------------------------------------ dropout(LN(GeLU(z))) backward
-__global__ void __launch_bounds__(ROW_WARPS * 32)
-gelu_ln_drop_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ z,
-                        const float* __restrict__ mean, const float* __restrict__ rstd,
-                        const float* __restrict__ gamma, const uint8_t* __restrict__ keep,
-                        float scale, float* __restrict__ gz, float* __restrict__ ggamma,
-                        float* __restrict__ gbeta, int M, int H) {
+__global__ void __launch_bounds__(GEN_WARPS * 32)
+gld_bwd_gen(const float* __restrict__ gout, const float* __restrict__ z, const float* __restrict__ mean,
+            const float* __restrict__ rstd, const float* __restrict__ gamma, const uint8_t* __restrict__ keep,
+            float scale, float* __restrict__ gz, float* __restrict__ ggamma, float* __restrict__ gbeta,
+            float* __restrict__ gbias, bf16* __restrict__ hi, bf16* __restrict__ lo, int M, int H) {
     extern __shared__ float sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* sg = sm + (size_t)warp * 2 * H;
+    float* sg = sm + (size_t)warp * 3 * H;
     float* sb = sg + H;
-    for (int c = lane; c < H; c += 32) { sg[c] = 0.f; sb[c] = 0.f; }
+    float* sz = sb + H;
+    for (int c = lane; c < H; c += 32) { sg[c] = 0.f; sb[c] = 0.f; sz[c] = 0.f; }
     int r0, r1;
     row_range(M, r0, r1);
     for (int r = r0; r < r1; ++r) {
@@ -147,66 +416,128 @@ gelu_ln_drop_bwd_kernel(const float* __restrict__ gout, const float* __restrict_
         }
         const float c1 = warp_sum(s1) / (float)H, c2 = warp_sum(s2) / (float)H;
         for (int c = lane; c < H; c += 32) {
+            const size_t o = (size_t)r * H + c;
             float gy = gr[c];
             if (kr) gy = kr[c] ? gy * scale : 0.f;
             const float zv = zr[c];
             const float yh = (gelu_erf(zv) - mu) * rs;
-            const float gg = rs * (gy * gamma[c] - c1 - yh * c2);
-            gz[(size_t)r * H + c] = gg * gelu_erf_grad(zv);
+            const float v = rs * (gy * gamma[c] - c1 - yh * c2) * gelu_erf_grad(zv);
+            if (gz) gz[o] = v;
+            if (hi) split_store1(hi, lo, o, v);
             sg[c] = fmaf(gy, yh, sg[c]);
             sb[c] += gy;
+            sz[c] += v;
         }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < H; c += blockDim.x) {
-        float a = 0.f, b = 0.f;
+        float a = 0.f, b = 0.f, d = 0.f;
 #pragma unroll
-        for (int w = 0; w < ROW_WARPS; ++w) { a += sm[(size_t)w * 2 * H + c]; b += sm[(size_t)w * 2 * H + H + c]; }
+        for (int w = 0; w < GEN_WARPS; ++w) {
+            a += sm[(size_t)w * 3 * H + c];
+            b += sm[(size_t)w * 3 * H + H + c];
+            d += sm[(size_t)w * 3 * H + 2 * H + c];
+        }
         atomicAdd(&ggamma[c], a);
         atomicAdd(&gbeta[c], b);
+        if (gbias) atomicAdd(&gbias[c], d);
     }
 }
 
-// ------------------------------------------------------------------ launchers
-int layernorm_fwd(const float* u, const float* gamma, const float* beta, float* h, float* xhat,
-                  float* rstd, int M, int H, float eps, cudaStream_t st) {
+// ================================================================== launchers
+static int row_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+static int fast_grid(int M, int ctas_per_sm = 2) {
+    return max(1, min(ceil_div(M, ROW_WARPS), ctas_per_sm * row_sms()));
+}
+static inline bool fast_ok(int H, const void* a, const void* b = nullptr, const void* c = nullptr) {
+    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    return H % 128 == 0 && H >= 128 && H <= 1024 && al(a) && al(b) && al(c);
+}
+#define XGGM_ROW_DISPATCH(H, CALL)          \
+    switch ((H) / 128) {                    \
+        case 1: { constexpr int NV = 1; CALL; } break; \
+        case 2: { constexpr int NV = 2; CALL; } break; \
+        case 3: { constexpr int NV = 3; CALL; } break; \
+        case 4: { constexpr int NV = 4; CALL; } break; \
+        case 5: { constexpr int NV = 5; CALL; } break; \
+        case 6: { constexpr int NV = 6; CALL; } break; \
+        case 7: { constexpr int NV = 7; CALL; } break; \
+        default: { constexpr int NV = 8; CALL; } break; \
+    }
+
+template <typename K>
+static int gen_smem(K kernel, int H, size_t& bytes) {
+    bytes = sizeof(float) * (size_t)GEN_WARPS * 3 * H;
+    if (bytes > 227 * 1024) return XGGM_ERR_ARG;
+    if (bytes > 48 * 1024)
+        XGGM_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return XGGM_OK;
+}
+
+// hi/lo: optional bf16 planes of the output h (lo may be null with hi set: bf16 engine)
+int layernorm_fwd(const float* u, const float* gamma, const float* beta, float* h, float* xhat, float* rstd,
+                  bf16* hi, bf16* lo, int M, int H, float eps, cudaStream_t st) {
     if (M <= 0) return XGGM_OK;
-    layernorm_fwd_kernel<<<row_grid(M), ROW_WARPS * 32, 0, st>>>(u, gamma, beta, h, xhat, rstd, M, H, eps);
+    if (fast_ok(H, u, h, xhat) && fast_ok(H, gamma, beta, hi) && fast_ok(H, lo)) {
+        XGGM_ROW_DISPATCH(H, (ln_fwd_fast<NV><<<fast_grid(M), ROW_WARPS * 32, 0, st>>>(u, gamma, beta, h, xhat, rstd, hi, lo, M, eps)));
+    } else {
+        ln_fwd_gen<<<gen_grid(M), GEN_WARPS * 32, 0, st>>>(u, gamma, beta, h, xhat, rstd, hi, lo, M, H, eps);
+    }
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
 
-static int col_smem(int H, size_t& bytes) {
-    bytes = sizeof(float) * (size_t)ROW_WARPS * 2 * H;
-    return bytes <= 48 * 1024 ? XGGM_OK : XGGM_ERR_ARG;
-}
-
-int layernorm_bwd(const float* gh, const float* xhat, const float* rstd, const float* gamma,
-                  float* gu, float* ggamma, float* gbeta, int M, int H, cudaStream_t st) {
+// ggamma / gbeta are ACCUMULATED into (caller zeroes them)
+int layernorm_bwd(const float* gh, const float* xhat, const float* rstd, const float* gamma, float* gu,
+                  float* ggamma, float* gbeta, bf16* hi, bf16* lo, int M, int H, cudaStream_t st) {
     if (M <= 0) return XGGM_OK;
-    size_t smem;
-    XGGM_TRY(col_smem(H, smem));
-    layernorm_bwd_kernel<<<row_grid(M), ROW_WARPS * 32, smem, st>>>(gh, xhat, rstd, gamma, gu, ggamma, gbeta, M, H);
+    if (fast_ok(H, gh, xhat, gu) && fast_ok(H, gamma, hi, lo)) {
+        const size_t smem = sizeof(float) * ROW_WARPS * H;
+        XGGM_ROW_DISPATCH(H, (ln_bwd_fast<NV><<<fast_grid(M), ROW_WARPS * 32, smem, st>>>(gh, xhat, rstd, gamma, gu, ggamma, gbeta, hi, lo, M)));
+    } else {
+        size_t smem;
+        XGGM_TRY(gen_smem(ln_bwd_gen, H, smem));
+        ln_bwd_gen<<<gen_grid(M), GEN_WARPS * 32, smem, st>>>(gh, xhat, rstd, gamma, gu, ggamma, gbeta, hi, lo, M, H);
+    }
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
 
-int gelu_ln_drop_fwd(const float* z, const float* gamma, const float* beta, const uint8_t* keep,
-                     float scale, float* out, float* mean, float* rstd, int M, int H, float eps,
+int gelu_ln_drop_fwd(const float* z, const float* gamma, const float* beta, const uint8_t* keep, float scale,
+                     float* out, float* mean, float* rstd, bf16* hi, bf16* lo, int M, int H, float eps,
                      int accumulate, cudaStream_t st) {
     if (M <= 0) return XGGM_OK;
-    gelu_ln_drop_fwd_kernel<<<row_grid(M), ROW_WARPS * 32, 0, st>>>(z, gamma, beta, keep, scale, out, mean, rstd, M, H, eps, accumulate);
+    if (fast_ok(H, z, out, hi) && fast_ok(H, gamma, beta, lo) && (reinterpret_cast<uintptr_t>(keep) & 3) == 0) {
+        XGGM_ROW_DISPATCH(H, (gld_fwd_fast<NV><<<fast_grid(M), ROW_WARPS * 32, 0, st>>>(z, gamma, beta, keep, scale, out, mean, rstd, hi, lo, M, eps, accumulate)));
+    } else {
+        gld_fwd_gen<<<gen_grid(M), GEN_WARPS * 32, 0, st>>>(z, gamma, beta, keep, scale, out, mean, rstd, hi, lo, M, H, eps, accumulate);
+    }
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
 
-int gelu_ln_drop_bwd(const float* gout, const float* z, const float* mean, const float* rstd,
-                     const float* gamma, const uint8_t* keep, float scale, float* gz,
-                     float* ggamma, float* gbeta, int M, int H, cudaStream_t st) {
+// gz may be null (only the planes are wanted); ggamma / gbeta / gbias? are ACCUMULATED into
+int gelu_ln_drop_bwd(const float* gout, const float* z, const float* mean, const float* rstd, const float* gamma,
+                     const uint8_t* keep, float scale, float* gz, float* ggamma, float* gbeta, float* gbias,
+                     bf16* hi, bf16* lo, int M, int H, cudaStream_t st) {
     if (M <= 0) return XGGM_OK;
-    size_t smem;
-    XGGM_TRY(col_smem(H, smem));
-    gelu_ln_drop_bwd_kernel<<<row_grid(M), ROW_WARPS * 32, smem, st>>>(gout, z, mean, rstd, gamma, keep, scale, gz, ggamma, gbeta, M, H);
+    if (fast_ok(H, gout, z, gz) && fast_ok(H, gamma, hi, lo) && (reinterpret_cast<uintptr_t>(keep) & 3) == 0) {
+        const size_t smem = sizeof(float) * ROW_WARPS * H;
+        XGGM_ROW_DISPATCH(H, (gld_bwd_fast<NV><<<fast_grid(M, 1), ROW_WARPS * 32, smem, st>>>(gout, z, mean, rstd, gamma, keep, scale, gz, ggamma, gbeta, gbias, hi, lo, M)));
+    } else {
+        size_t smem;
+        XGGM_TRY(gen_smem(gld_bwd_gen, H, smem));
+        gld_bwd_gen<<<gen_grid(M), GEN_WARPS * 32, smem, st>>>(gout, z, mean, rstd, gamma, keep, scale, gz, ggamma, gbeta, gbias, hi, lo, M, H);
+    }
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
