@@ -124,8 +124,11 @@ int xggm_gelu_ln_drop_bwd(const float* gout, const float* z, const float* mean, 
  *   S = x x^T ; m_i = max_k S[k,i] ; adj[i,j] = sigmoid(S[i,j]/m_i) (i != j), 0 on the diagonal
  * Saves S[B,N,N] and the arg-max row index amax[B,N] (first index on ties, as torch.max).
  * ------------------------------------------------------------------------- */
+/* `work` (xggm_adj_regen_work_bytes bytes, 16-byte aligned) lets the pair scores run on the
+ * tensor cores (bf16 planes of x + batched Gram kernel); NULL selects the per-graph SIMT kernel. */
+long long xggm_adj_regen_work_bytes(int B, int N, int H);
 int xggm_adj_regen_fwd(const float* x, float* adj_out, float* S, int32_t* amax, int B, int N,
-                       int H, int squash, xggm_stream_t s);
+                       int H, int squash, void* work, xggm_stream_t s);
 /* gx (+)= (dS + dS^T) x.  `work` is a [B,N,N] scratch buffer. */
 int xggm_adj_regen_bwd(const float* gadj, const float* x, const float* S, const int32_t* amax,
                        float* gx, float* work, int B, int N, int H, int squash,

@@ -15,8 +15,14 @@ int gemm_simt(int op, const float* A, const float* Bm, const float* bias, const 
 int colsum(const float* g, float* out, int R, int C, cudaStream_t st);
 bool gemm_tc_supported(int M, int N, int K);
 int gemm_tc(bool a_mn, bool b_mn, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const __nv_bfloat16* b_hi,
-            const __nv_bfloat16* b_lo, const float* bias, const float* resid, float* C, int M, int N, int K,
-            int accumulate, int allow_split_k, int npass, cudaStream_t st);
+            const __nv_bfloat16* b_lo, const float* bias, const float* resid, float* C, __nv_bfloat16* c_hi,
+            __nv_bfloat16* c_lo, int M, int N, int K, int accumulate, int allow_split_k, int npass, cudaStream_t st);
+bool gram_tc_supported(int N, int H);
+int gram_tc(const __nv_bfloat16* p_hi, const __nv_bfloat16* p_lo, const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo,
+            float* S, int B, int N, int H, int npass, cudaStream_t st);
+int adj_regen_from_s(const float* S, float* adj_out, int32_t* amax, int B, int N, int squash, cudaStream_t st);
+int scale_accum(const float* S, float* out, long long n, float alpha0, const float* alpha_dev, int accumulate,
+                const float* dot_ref, float* dot_out, cudaStream_t st);
 int split_planes(const float* const* src, __nv_bfloat16* const* hi, __nv_bfloat16* const* lo, const long long* n,
                  int count, cudaStream_t st);
 int gemm_prof_enable(int on);
@@ -94,19 +100,22 @@ static int split_one(const Operand& o, long long n, cudaStream_t st) {
 // out[M,N] = a[M,K] w[N,K]^T + bias + resid
 static int proj_fwd(bool tc, const Operand& a, const Operand& w, const float* bias, const float* resid,
                     float* out, int M, int N, int K, cudaStream_t st) {
-    if (tc) return gemm_tc(false, false, a.hi, a.lo, w.hi, w.lo, bias, resid, out, M, N, K, 0, 0, npass(), st);
+    if (tc) return gemm_tc(false, false, a.hi, a.lo, w.hi, w.lo, bias, resid, out, nullptr, nullptr, M, N, K, 0, 0, npass(), st);
     return gemm_simt(0, a.f32, w.f32, bias, resid, out, M, N, K, 0, st);
 }
 // ga[M,K] (+)= g[M,N] w[N,K]
+// ga_planes (optional, tensor-core engine only): also emit ga as bf16 operand planes
 static int proj_dgrad(bool tc, const Operand& g, const Operand& w, float* ga, int M, int N, int K,
-                      int accumulate, cudaStream_t st) {
-    if (tc) return gemm_tc(false, true, g.hi, g.lo, w.hi, w.lo, nullptr, nullptr, ga, M, K, N, accumulate, 0, npass(), st);
+                      int accumulate, cudaStream_t st, const Operand* ga_planes = nullptr) {
+    if (tc) return gemm_tc(false, true, g.hi, g.lo, w.hi, w.lo, nullptr, nullptr, ga,
+                           ga_planes ? const_cast<bf16*>(ga_planes->hi) : nullptr,
+                           ga_planes ? const_cast<bf16*>(ga_planes->lo) : nullptr, M, K, N, accumulate, 0, npass(), st);
     return gemm_simt(1, g.f32, w.f32, nullptr, nullptr, ga, M, K, N, accumulate, st);
 }
 // gw[N,K] = g[M,N]^T a[M,K]
 static int proj_wgrad(bool tc, const Operand& g, const Operand& a, float* gw, int M, int N, int K,
                       cudaStream_t st) {
-    if (tc) return gemm_tc(true, true, g.hi, g.lo, a.hi, a.lo, nullptr, nullptr, gw, N, K, M, 0, 1, npass(), st);
+    if (tc) return gemm_tc(true, true, g.hi, g.lo, a.hi, a.lo, nullptr, nullptr, gw, nullptr, nullptr, N, K, M, 0, 1, npass(), st);
     return gemm_simt(2, g.f32, a.f32, nullptr, nullptr, gw, N, K, M, 0, st);
 }
 
@@ -140,7 +149,8 @@ struct GnnLayout {
         return slot == 0 ? base : base + MH + (slot - 1) * Mr;
     }
     long long work_fwd() const { return MH + (2 * n_convs + 1) * HH; }
-    long long work_bwd() const { return 5 * MH + (2 * n_convs + 1) * HH; }
+    // bwd: buf0 | buf1 | gt | gq | P(grad) | P(gq) | weight planes | S scratch [B,N,N]
+    long long work_bwd(long long bnn) const { return 6 * MH + (2 * n_convs + 1) * HH + al4(bnn); }
 };
 
 // weight planes for one layer live at the tail of the work buffer: conv k -> slot k, head j -> slot nc + j
@@ -262,8 +272,13 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
     float* gt = work + 2 * MH;  // gz / gu
     float* gq = work + 3 * MH;
     Operand wconv[MAX_CONVS], whead[MAX_CONVS + 1];
-    XGGM_TRY(split_weights(kind, cp, hp, work + 5 * MH, L, H, wconv, whead, tc, st));
+    XGGM_TRY(split_weights(kind, cp, hp, work + 6 * MH, L, H, wconv, whead, tc, st));
     XGGM_CUDA_TRY(cudaMemsetAsync(gadj, 0, sizeof(float) * (size_t)B * N * N, st));
+    // per-graph products gq h^T go through the tensor-core Gram kernel when it can address them
+    const bool gram = tc && gram_tc_supported(N, H);
+    const Operand gq_op = planes_at(gq, work + 5 * MH, MHn);
+    float* s_scratch = work + 6 * MH + (2 * nc + 1) * L.HH;
+    const long long BNN = (long long)B * N * N;
 
     auto act = [&](int j) -> Operand {   // h_j as a GEMM operand (planes saved by the forward pass)
         return j == 0 ? planes_at(x, saved + L.xplanes, MHn)
@@ -306,8 +321,14 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
                                    cg[3 * k + 1], cg[3 * k + 2], tc ? mut(gu.hi) : nullptr,
                                    tc ? lo_or_null(gu) : nullptr, M, H, st));
             XGGM_TRY(proj_wgrad(tc, gu, pre_op, cg[3 * k], M, H, H, st));
-            XGGM_TRY(proj_dgrad(tc, gu, wconv[k], gq, M, H, H, 0, st));  // gq = gu Wc
-            XGGM_TRY(bmm_nt(gq, hk, gadj, B, N, H, 1.f, nullptr, 1, nullptr, nullptr, st));
+            XGGM_TRY(proj_dgrad(tc, gu, wconv[k], gq, M, H, H, 0, st, gram ? &gq_op : nullptr));  // gq = gu Wc
+            if (gram) {   // gadj += gq h_k^T
+                const Operand hk_op = act(k);
+                XGGM_TRY(gram_tc(gq_op.hi, gq_op.lo, hk_op.hi, hk_op.lo, s_scratch, B, N, H, npass(), st));
+                XGGM_TRY(scale_accum(s_scratch, gadj, BNN, 1.f, nullptr, 1, nullptr, nullptr, st));
+            } else {
+                XGGM_TRY(bmm_nt(gq, hk, gadj, B, N, H, 1.f, nullptr, 1, nullptr, nullptr, st));
+            }
             XGGM_TRY(adj_apply(adj, gq, gnext, nullptr, nullptr, B, N, H, 1.f, nullptr, 0.f, true, 1, st));
         } else {
             const float* eps = cp[5 * k], *g = cp[5 * k + 3];
@@ -320,9 +341,15 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
                                       g, nullptr, 1.f, tc ? nullptr : gt, cg[5 * k + 3], cg[5 * k + 4], cg[5 * k + 2],
                                       tc ? mut(gz.hi) : nullptr, tc ? lo_or_null(gz) : nullptr, M, H, st));
             XGGM_TRY(proj_wgrad(tc, gz, pre_op, cg[5 * k + 1], M, H, H, st));
-            XGGM_TRY(proj_dgrad(tc, gz, wconv[k], gq, M, H, H, 0, st));      // gpre
+            XGGM_TRY(proj_dgrad(tc, gz, wconv[k], gq, M, H, H, 0, st, gram ? &gq_op : nullptr));      // gpre
             // gadj += (1+eps) gpre h^T ; geps += <gpre h^T, adj>
-            XGGM_TRY(bmm_nt(gq, hk, gadj, B, N, H, 1.f, eps, 1, adj, cg[5 * k], st));
+            if (gram) {
+                const Operand hk_op = act(k);
+                XGGM_TRY(gram_tc(gq_op.hi, gq_op.lo, hk_op.hi, hk_op.lo, s_scratch, B, N, H, npass(), st));
+                XGGM_TRY(scale_accum(s_scratch, gadj, BNN, 1.f, eps, 1, adj, cg[5 * k], st));
+            } else {
+                XGGM_TRY(bmm_nt(gq, hk, gadj, B, N, H, 1.f, eps, 1, adj, cg[5 * k], st));
+            }
             // grad h_k = gpre + (1+eps) adj^T gpre
             XGGM_TRY(adj_apply(adj, gq, gnext, nullptr, nullptr, B, N, H, 1.f, eps, 1.f, true, 0, st));
         }
@@ -492,11 +519,23 @@ int xggm_gelu_ln_drop_bwd(const float* gout, const float* z, const float* mean, 
     return gelu_ln_drop_bwd(gout, z, mean, rstd, gamma, keep, scale, gz, ggamma, gbeta, nullptr, nullptr, nullptr, M, H, as_stream(s));
 }
 
+long long xggm_adj_regen_work_bytes(int B, int N, int H) {
+    if (B < 0 || N <= 0 || H <= 0) return -1;
+    return 4 * al4((long long)B * N * H);
+}
 int xggm_adj_regen_fwd(const float* x, float* adj_out, float* S, int32_t* amax, int B, int N,
-                       int H, int squash, xggm_stream_t s) {
+                       int H, int squash, void* work, xggm_stream_t s) {
     XGGM_REQUIRE(B >= 0 && H > 0);
     if (B == 0) return XGGM_OK;
     XGGM_REQUIRE(x && adj_out);
+    if (work && S && g_precision != XGGM_PREC_FP32_SIMT && gram_tc_supported(N, H)) {
+        // pair scores on the tensor cores: planes of x -> Gram kernel -> S, then the per-graph tail
+        const long long n = (long long)B * N * H;
+        const Operand xo = planes_at(x, static_cast<float*>(work), n);
+        XGGM_TRY(split_one(xo, n, as_stream(s)));
+        XGGM_TRY(gram_tc(xo.hi, xo.lo, xo.hi, xo.lo, S, B, N, H, npass(), as_stream(s)));
+        return adj_regen_from_s(S, adj_out, amax, B, N, squash, as_stream(s));
+    }
     return adj_regen_fwd(x, adj_out, S, amax, B, N, H, squash, as_stream(s));
 }
 int xggm_adj_regen_bwd(const float* gadj, const float* x, const float* S, const int32_t* amax,
@@ -515,7 +554,8 @@ long long xggm_gnn_saved_floats(int kind, int B, int N, int H, int n_convs) {
 long long xggm_gnn_work_floats(int kind, int B, int N, int H, int n_convs) {
     if ((kind != XGGM_KIND_GCN && kind != XGGM_KIND_GIN) || B < 0 || N <= 0 || H <= 0 || n_convs < 0) return -1;
     const GnnLayout L(kind, (long long)B * N, H, n_convs);
-    return L.work_bwd() > L.work_fwd() ? L.work_bwd() : L.work_fwd();
+    const long long wb = L.work_bwd((long long)B * N * N);
+    return wb > L.work_fwd() ? wb : L.work_fwd();
 }
 int xggm_gnn_fwd(int kind, const float* x, const float* adj, const float* const* conv_params,
                  const float* const* head_params, const uint8_t* const* keeps, float drop_p,

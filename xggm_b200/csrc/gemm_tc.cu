@@ -144,6 +144,18 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+__device__ __forceinline__ void split1(float x, __nv_bfloat16& hi, __nv_bfloat16& lo);
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t off, const float4& o) {
+    __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+    split1(o.x, h0, l0); split1(o.y, h1, l1); split1(o.z, h2, l2); split1(o.w, h3, l3);
+    __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
+    *reinterpret_cast<uint2*>(hi + off) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    if (lo) {
+        __nv_bfloat162 c = __halves2bfloat162(l0, l1), d = __halves2bfloat162(l2, l3);
+        *reinterpret_cast<uint2*>(lo + off) = make_uint2(*reinterpret_cast<uint32_t*>(&c), *reinterpret_cast<uint32_t*>(&d));
+    }
+}
+
 struct Params {
     int M, N;            // output extent
     int num_kb;          // ceil(K / BK)
@@ -155,6 +167,12 @@ struct Params {
     int accumulate;      // C += (non-atomic)
     int atomic;          // split-K partial sums: atomicAdd into a pre-zeroed / pre-initialised C
     int vec4;            // C / resid / bias are 16-byte aligned and N % 4 == 0: float4 epilogue
+    __nv_bfloat16* c_hi; // optional: also emit C as bf16 planes (vec4 mode only; operand of a later GEMM)
+    __nv_bfloat16* c_lo;
+    // Batched per-graph Gram mode (gram_n > 0): A and B are the SAME-row tiles of two [M,K] K-major
+    // tensors, tile t covers the gram_g complete graphs starting at row t*gram_g*gram_n, and only the
+    // gram_n x gram_n diagonal blocks  S[b] = P[b] Q[b]^T  are written to C[B][gram_n][gram_n].
+    int gram_n, gram_g, gram_b;
 };
 
 template <int BN, int NPASS>
@@ -223,7 +241,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int sp = tile % p.splits;
                 const int mn = tile / p.splits;
-                const int m0 = (mn / p.tiles_n) * BM, n0 = (mn % p.tiles_n) * BN;
+                int m0 = (mn / p.tiles_n) * BM, n0 = (mn % p.tiles_n) * BN;
+                if (p.gram_n > 0) m0 = n0 = mn * p.gram_g * p.gram_n;
                 const int kb0 = sp * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
@@ -312,6 +331,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const bool lead = (sp == 0);  // bias / residual are added by the first split only
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
+            if (p.gram_n > 0) {
+                // thread = accumulator row r of the tile; keep the columns of r's own graph only
+                const int gn = p.gram_n, span = p.gram_g * gn;
+                const int r = q * 32 + lane;
+                const int gl = r / gn;                       // graph slot of this row inside the tile
+                const long long b = (long long)mn * p.gram_g + gl;
+                const bool row_ok = r < span && b < p.gram_b;
+                const int lo_col = (q * 32) / gn * gn;                       // warp-uniform column window
+                const int hi_col = min(span, ((q * 32 + 31) / gn + 1) * gn);
+                float* orow = p.C + (b * gn + (r - gl * gn)) * gn - gl * gn;  // orow[col] = S[b][i][col - gl*gn]
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    if (c * 32 + 32 <= lo_col || c * 32 >= hi_col) continue;  // warp-uniform
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int col = c * 32 + j;
+                            if (col >= gl * gn && col < gl * gn + gn) orow[col] = __uint_as_float(v[j]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&acc_empty[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+                continue;
+            }
             const int mrow0 = m0 + q * 32;
             const int rows = min(32, p.M - mrow0);
             const bool vec = p.vec4 && !p.atomic;
@@ -357,8 +405,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                             const int row = 4 * it + rsub;
                             if (row < rows) {
                                 const float* sp = st + row * EPI_PITCH + c4;
-                                *reinterpret_cast<float4*>(p.C + (size_t)(mrow0 + row) * p.ldc + nv) =
-                                    make_float4(sp[0] + e[it].x, sp[1] + e[it].y, sp[2] + e[it].z, sp[3] + e[it].w);
+                                const float4 o = make_float4(sp[0] + e[it].x, sp[1] + e[it].y, sp[2] + e[it].z, sp[3] + e[it].w);
+                                const size_t off = (size_t)(mrow0 + row) * p.ldc + nv;
+                                *reinterpret_cast<float4*>(p.C + off) = o;
+                                if (p.c_hi) store_planes4(p.c_hi, p.c_lo, off, o);
                             }
                         }
                     }
@@ -520,8 +570,8 @@ bool gemm_tc_supported(int M, int N, int K) {
 
 // A planes: a_mn ? [K,M] : [M,K];  B planes: b_mn ? [K,N] : [N,K].  lo planes may be null when npass == 1.
 int gemm_tc(bool a_mn, bool b_mn, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const __nv_bfloat16* b_hi,
-            const __nv_bfloat16* b_lo, const float* bias, const float* resid, float* C, int M, int N, int K,
-            int accumulate, int allow_split_k, int npass, cudaStream_t st) {
+            const __nv_bfloat16* b_lo, const float* bias, const float* resid, float* C, __nv_bfloat16* c_hi,
+            __nv_bfloat16* c_lo, int M, int N, int K, int accumulate, int allow_split_k, int npass, cudaStream_t st) {
     if (M <= 0 || N <= 0 || K <= 0) return XGGM_OK;
     XGGM_REQUIRE(a_hi && b_hi && C && (npass == 1 || (npass == 3 && a_lo && b_lo)));
     const int sms = num_sms();
@@ -570,6 +620,10 @@ int gemm_tc(bool a_mn, bool b_mn, const __nv_bfloat16* a_hi, const __nv_bfloat16
     p.accumulate = accumulate; p.atomic = splits > 1 ? 1 : 0;
     p.vec4 = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(resid) |
                                reinterpret_cast<uintptr_t>(bias)) & 15) == 0;
+    p.c_hi = c_hi; p.c_lo = npass == 3 ? c_lo : nullptr;
+    p.gram_n = p.gram_g = p.gram_b = 0;
+    if (c_hi && (!p.vec4 || p.atomic || (reinterpret_cast<uintptr_t>(c_hi) & 7) || (reinterpret_cast<uintptr_t>(c_lo) & 7)))
+        return XGGM_ERR_ARG;  // plane emission needs the float4 epilogue
     if (splits > 1 && !accumulate)
         XGGM_CUDA_TRY(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
     const int grid = min(sms, tiles_m * tiles_n * splits);
@@ -583,6 +637,40 @@ int gemm_tc(bool a_mn, bool b_mn, const __nv_bfloat16* a_hi, const __nv_bfloat16
         rc = npass == 3 ? dispatch_major<128, 3>(a_mn, b_mn, ah, al, bh, bl, p, grid, st)
                         : dispatch_major<128, 1>(a_mn, b_mn, ah, al, bh, bl, p, grid, st);
     }
+    gemm_prof_end(prof, st);
+    return rc;
+}
+
+bool gram_tc_supported(int N, int H) { return N >= 1 && N <= tc::BM && H > 0 && H % 8 == 0; }
+
+// S[b] = P[b] Q[b]^T for every graph b: P, Q are [B*N, H] bf16 planes (K-major), S is [B,N,N] fp32 (overwritten).
+// One 128 x 128 tensor-core tile covers floor(128/N) whole graphs; only its diagonal blocks are stored.
+int gram_tc(const __nv_bfloat16* p_hi, const __nv_bfloat16* p_lo, const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo,
+            float* S, int B, int N, int H, int npass, cudaStream_t st) {
+    if (B <= 0) return XGGM_OK;
+    XGGM_REQUIRE(p_hi && q_hi && S && gram_tc_supported(N, H) && (npass == 1 || (npass == 3 && p_lo && q_lo)));
+    const long long M = (long long)B * N;
+    const int G = tc::BM / N;
+    CUtensorMap ah, al, bh, bl;
+    XGGM_TRY(make_map(&ah, p_hi, M, H, tc::BM));
+    XGGM_TRY(make_map(&bh, q_hi, M, H, 128));
+    if (npass == 3) {
+        XGGM_TRY(make_map(&al, p_lo, M, H, tc::BM));
+        XGGM_TRY(make_map(&bl, q_lo, M, H, 128));
+    } else {
+        al = ah;
+        bl = bh;
+    }
+    tc::Params p;
+    p.M = (int)M; p.N = (int)M; p.num_kb = ceil_div(H, tc::BK);
+    p.tiles_m = ceil_div(B, G); p.tiles_n = 1; p.splits = 1; p.kb_per_split = p.num_kb;
+    p.bias = nullptr; p.resid = nullptr; p.C = S; p.ldc = N;
+    p.accumulate = 0; p.atomic = 0; p.vec4 = 0; p.c_hi = nullptr; p.c_lo = nullptr;
+    p.gram_n = N; p.gram_g = G; p.gram_b = B;
+    const int grid = min(num_sms(), p.tiles_m);
+    void* prof = gemm_prof_begin(2.0 * B * N * N * H, st);
+    const int rc = npass == 3 ? launch_tc<128, 3, false, false>(ah, al, bh, bl, p, grid, st)
+                              : launch_tc<128, 1, false, false>(ah, al, bh, bl, p, grid, st);
     gemm_prof_end(prof, st);
     return rc;
 }

@@ -331,6 +331,83 @@ int adj_regen_fwd(const float* x, float* adj_out, float* S, int32_t* amax, int B
     return XGGM_OK;
 }
 
+// Second half of adj_regen_fwd when S = x x^T was produced by the tensor-core Gram kernel:
+// column max / arg-max (first index on ties), divide, sigmoid, zero diagonal.  One CTA per graph.
+__global__ void __launch_bounds__(128)
+regen_from_s_kernel(const float* __restrict__ S_in, float* __restrict__ adj_out,
+                    int32_t* __restrict__ amax_out, int N, int squash) {
+    extern __shared__ float sm[];
+    float* S = sm;          // [N][N]
+    float* m = sm + N * N;  // [N]
+    const int b = blockIdx.x;
+    const float* Sb = S_in + (size_t)b * N * N;
+    for (int e = threadIdx.x; e < N * N; e += blockDim.x) S[e] = Sb[e];
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        float best = S[i];
+        int arg = 0;
+        for (int k = 1; k < N; ++k) {
+            const float v = S[k * N + i];
+            if (v > best) { best = v; arg = k; }
+        }
+        m[i] = best;
+        if (amax_out) amax_out[(size_t)b * N + i] = arg;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+        const int i = e / N, j = e - i * N;
+        float v = S[e] / m[i];
+        if (squash) v = sigmoidf_(v);
+        adj_out[(size_t)b * N * N + e] = (i == j) ? 0.f : v;
+    }
+}
+
+int adj_regen_from_s(const float* S, float* adj_out, int32_t* amax, int B, int N, int squash, cudaStream_t st) {
+    if (B <= 0) return XGGM_OK;
+    XGGM_REQUIRE(N >= 1 && N <= 128);
+    const size_t smem = sizeof(float) * ((size_t)N * N + N);
+    if (smem > 48 * 1024)
+        XGGM_CUDA_TRY(cudaFuncSetAttribute(regen_from_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    regen_from_s_kernel<<<B, 128, smem, st>>>(S, adj_out, amax, N, squash);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+
+// out (=|+=) alpha * S ;  dot_out? += <S, dot_ref>   (tail of bmm_nt when S came from the Gram kernel)
+__global__ void __launch_bounds__(256)
+scale_accum_kernel(const float* __restrict__ S, float* __restrict__ out, long long n, float alpha0,
+                   const float* __restrict__ alpha_dev, int accumulate, const float* __restrict__ dot_ref,
+                   float* __restrict__ dot_out) {
+    __shared__ float part[8];
+    const float alpha = alpha0 + (alpha_dev ? alpha_dev[0] : 0.f);
+    float dot = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = S[i];
+        if (dot_ref) dot = fmaf(v, dot_ref[i], dot);
+        const float o = alpha * v;
+        out[i] = accumulate ? out[i] + o : o;
+    }
+    if (dot_out) {
+        dot = warp_sum(dot);
+        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = dot;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float v = threadIdx.x < 8 ? part[threadIdx.x] : 0.f;
+            v = warp_sum(v);
+            if (threadIdx.x == 0) atomicAdd(dot_out, v);
+        }
+    }
+}
+
+int scale_accum(const float* S, float* out, long long n, float alpha0, const float* alpha_dev, int accumulate,
+                const float* dot_ref, float* dot_out, cudaStream_t st) {
+    if (n <= 0) return XGGM_OK;
+    const int grid = (int)min((long long)296, (n + 255) / 256);
+    scale_accum_kernel<<<grid, 256, 0, st>>>(S, out, n, alpha0, alpha_dev, accumulate, dot_ref, dot_out);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+
 // d(adj_out)/dS folded into a symmetric coefficient matrix D = dS + dS^T so that
 // gx += D x.  One CTA per graph.
 __global__ void __launch_bounds__(256)

@@ -194,7 +194,9 @@ class _AdjRegen(torch.autograd.Function):
         adj = torch.empty((B, N, N), device=x.device, dtype=torch.float32)
         S = torch.empty_like(adj)
         amax = torch.empty((B, N), device=x.device, dtype=torch.int32)
-        call("xggm_adj_regen_fwd", ptr(x), ptr(adj), ptr(S), ptr(amax), B, N, H, int(squash))
+        nwork = _lib.load().xggm_adj_regen_work_bytes(B, N, H)
+        work = torch.empty(max(int(nwork), 16), device=x.device, dtype=torch.uint8)
+        call("xggm_adj_regen_fwd", ptr(x), ptr(adj), ptr(S), ptr(amax), B, N, H, int(squash), ptr(work))
         ctx.save_for_backward(x, S, amax)
         ctx.squash = int(squash)
         ctx.mark_non_differentiable(amax)
