@@ -143,24 +143,34 @@ int xggm_adj_regen_bwd(const float* gadj, const float* x, const float* S, const 
  *   GIN conv k : conv_params[5k+0..4] = eps[1], linear.0.weight[H,H], linear.0.bias[H],
  *                                        linear.2.weight[H], linear.2.bias[H]
  *   head j     : head_params[4j+0..3] = 0.weight[H,H], 0.bias[H], 2.weight[H], 2.bias[H]
- *   keeps[j]?  : uint8 [M,H] keep-mask of head j (NULL table => eval mode, no dropout)
+ *   keeps[j]?  : uint8 [M,H] keep-mask of head j (NULL table and NULL philox => no dropout)
  * `saved` (xggm_gnn_saved_floats floats) carries activations to the backward call;
  * `work` (xggm_gnn_work_floats floats) is scratch.  kind: 0 = GCN, 1 = GIN.
  * ------------------------------------------------------------------------- */
 #define XGGM_KIND_GCN 0
 #define XGGM_KIND_GIN 1
+/* In-kernel dropout of the read-out heads (used when `keeps` is NULL, `philox` is not, drop_p > 0):
+ * Philox4x32-10, key = seed, counter = element index / 4, subsequence = stream0 + head index
+ * (+ (*dev_epoch << 32) when dev_epoch, a DEVICE counter, is given -- lets a captured CUDA graph
+ * draw fresh masks on every replay).  Forward and backward must receive the same triple.
+ * xggm_keep_mask(seed, stream0 + j, dev_epoch) materialises exactly the mask head j uses. */
+typedef struct {
+    uint64_t seed;
+    uint64_t stream0;
+    const uint64_t* dev_epoch;
+} xggm_philox_t;
 long long xggm_gnn_saved_floats(int kind, int B, int N, int H, int n_convs);
 long long xggm_gnn_work_floats(int kind, int B, int N, int H, int n_convs);
 int xggm_gnn_fwd(int kind, const float* x, const float* adj, const float* const* conv_params,
-                 const float* const* head_params, const uint8_t* const* keeps, float drop_p,
-                 float* out, float* saved, float* work, int B, int N, int H, int n_convs,
+                 const float* const* head_params, const uint8_t* const* keeps, const xggm_philox_t* philox,
+                 float drop_p, float* out, float* saved, float* work, int B, int N, int H, int n_convs,
                  xggm_stream_t s);
 /* Gradient tables mirror the parameter tables (same order); every gradient buffer is
  * OVERWRITTEN.  gadj[B,N,N] and gx[B,N,H] are overwritten. */
 int xggm_gnn_bwd(int kind, const float* gout, const float* x, const float* adj,
                  const float* const* conv_params, const float* const* head_params,
-                 const uint8_t* const* keeps, float drop_p, const float* saved, float* work,
-                 float* gx, float* gadj, float* const* conv_grads, float* const* head_grads,
+                 const uint8_t* const* keeps, const xggm_philox_t* philox, float drop_p, const float* saved,
+                 float* work, float* gx, float* gadj, float* const* conv_grads, float* const* head_grads,
                  int B, int N, int H, int n_convs, xggm_stream_t s);
 
 /* ------------------------------------------------------------------------- *
@@ -228,9 +238,10 @@ int xggm_gelu_bwd(const float* gy, const float* x, float* gx, long long n, xggm_
  * src/module/gat.py:73); the same call is its backward. */
 int xggm_mask_scale(const float* x, const uint8_t* keep, float scale, float* y, long long n,
                     xggm_stream_t s);
-/* Philox keep-mask (1 = keep with probability 1-p), counter = element index. */
+/* Philox keep-mask (1 = keep with probability 1-p): counter = element index / 4,
+ * subsequence = stream_id + (*dev_epoch << 32 if dev_epoch, a device counter, is non-NULL). */
 int xggm_keep_mask(uint8_t* keep, long long n, float p, uint64_t seed, uint64_t stream_id,
-                   xggm_stream_t s);
+                   const uint64_t* dev_epoch, xggm_stream_t s);
 
 #ifdef __cplusplus
 }

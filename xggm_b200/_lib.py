@@ -40,8 +40,8 @@ SIGNATURES = {
     "xggm_adj_regen_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "xggm_gnn_saved_floats": [_i, _i, _i, _i, _i],
     "xggm_gnn_work_floats": [_i, _i, _i, _i, _i],
-    "xggm_gnn_fwd": [_i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
-    "xggm_gnn_bwd": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp,
+    "xggm_gnn_fwd": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "xggm_gnn_bwd": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp,
                      _i, _i, _i, _i, _vp],
     "xggm_gat_attn_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp],
     "xggm_gat_attn_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp],
@@ -62,7 +62,7 @@ SIGNATURES = {
     "xggm_fuse_readout_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "xggm_sigmoid_fwd": [_vp, _vp, _ll, _vp],
     "xggm_sigmoid_bwd": [_vp, _vp, _vp, _ll, _vp],
-    "xggm_keep_mask": [_vp, _ll, _f, _u64, _u64, _vp],
+    "xggm_keep_mask": [_vp, _ll, _f, _u64, _u64, _vp, _vp],
 }
 _RESTYPES = {"xggm_launch_count": C.c_ulonglong, "xggm_strerror": C.c_char_p, "xggm_last_cuda_error": C.c_char_p,
              "xggm_gnn_saved_floats": _ll, "xggm_gnn_work_floats": _ll, "xggm_linear_work_bytes": _ll, "xggm_adj_regen_work_bytes": _ll}
@@ -108,6 +108,11 @@ def load():
         raise RuntimeError("libxggm_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib
+
+
+class PhiloxSpec(C.Structure):
+    """xggm_philox_t of include/xggm_b200.h."""
+    _fields_ = [("seed", C.c_uint64), ("stream0", C.c_uint64), ("dev_epoch", C.c_void_p)]
 
 
 PRECISIONS = {"fp32": 0, "bf16": 1, "fp32_simt": 2}

@@ -29,8 +29,8 @@ int gemm_prof_enable(int on);
 int gemm_prof_read(double* total_ms, long long* launches, double* flops);
 int layernorm_fwd(const float*, const float*, const float*, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, float, cudaStream_t);
 int layernorm_bwd(const float*, const float*, const float*, const float*, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, cudaStream_t);
-int gelu_ln_drop_fwd(const float*, const float*, const float*, const uint8_t*, float, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, float, int, cudaStream_t);
-int gelu_ln_drop_bwd(const float*, const float*, const float*, const float*, const float*, const uint8_t*, float, float*, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, cudaStream_t);
+int gelu_ln_drop_fwd(const float*, const float*, const float*, const DropSpec&, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, float, int, cudaStream_t);
+int gelu_ln_drop_bwd(const float*, const float*, const float*, const float*, const float*, const DropSpec&, float*, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, cudaStream_t);
 int adj_apply(const float*, const float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, int, float, const float*, float, bool, int, cudaStream_t);
 int bmm_nt(const float*, const float*, float*, int, int, int, float, const float*, int, const float*, float*, cudaStream_t);
 int adj_regen_fwd(const float*, float*, float*, int32_t*, int, int, int, int, cudaStream_t);
@@ -54,7 +54,7 @@ int fuse_readout_fwd(const float*, const float*, float*, int, int, int, cudaStre
 int fuse_readout_bwd(const float*, const float*, float*, float*, int, int, int, int, cudaStream_t);
 int sigmoid_fwd(const float*, float*, long long, cudaStream_t);
 int sigmoid_bwd(const float*, const float*, float*, long long, cudaStream_t);
-int keep_mask(uint8_t*, long long, float, uint64_t, uint64_t, cudaStream_t);
+int keep_mask(uint8_t*, long long, float, uint64_t, uint64_t, const uint64_t*, cudaStream_t);
 
 // ---- error state -------------------------------------------------------------
 static thread_local char g_cuda_err[256] = "";
@@ -181,8 +181,17 @@ static int split_weights(int kind, const float* const* cp, const float* const* h
 
 constexpr int MAX_CONVS = 7;
 
+// dropout of read-out head j: explicit masks win, then in-kernel Philox, else none
+static inline DropSpec head_drop(const uint8_t* const* keeps, const xggm_philox_t* ph, float drop_p, int j) {
+    const float scale = 1.f / (1.f - drop_p);
+    if (keeps) return drop_mask(keeps[j], scale);
+    if (ph && drop_p > 0.f)
+        return DropSpec{nullptr, ph->dev_epoch, ph->seed, ph->stream0 + (uint64_t)j, drop_threshold(drop_p), scale, 2};
+    return drop_none();
+}
+
 static int gnn_fwd(int kind, const float* x, const float* adj, const float* const* cp,
-                   const float* const* hp, const uint8_t* const* keeps, float drop_p, float* out,
+                   const float* const* hp, const uint8_t* const* keeps, const xggm_philox_t* philox, float drop_p, float* out,
                    float* saved, float* work, int B, int N, int H, int nc, cudaStream_t st) {
     XGGM_REQUIRE(kind == XGGM_KIND_GCN || kind == XGGM_KIND_GIN);
     XGGM_REQUIRE(B >= 0 && N > 0 && H > 0 && nc >= 0 && nc <= MAX_CONVS && drop_p >= 0.f && drop_p < 1.f);
@@ -191,7 +200,6 @@ static int gnn_fwd(int kind, const float* x, const float* adj, const float* cons
     XGGM_REQUIRE(x && adj && cp && hp && out && saved && work);
     const GnnLayout L(kind, M, H, nc);
     const bool tc = use_tc(M, H, H);
-    const float scale = 1.f / (1.f - drop_p);
     const long long MHn = (long long)M * H;
     Operand wconv[MAX_CONVS], whead[MAX_CONVS + 1];
     XGGM_TRY(split_weights(kind, cp, hp, work + L.MH, L, H, wconv, whead, tc, st));
@@ -225,7 +233,7 @@ static int gnn_fwd(int kind, const float* x, const float* adj, const float* cons
             XGGM_TRY(adj_apply(adj, h, tc ? nullptr : pre, tc ? mut(pre_op.hi) : nullptr, tc ? lo_or_null(pre_op) : nullptr,
                                B, N, H, 1.f, eps, 1.f, false, 0, st));
             XGGM_TRY(proj_fwd(tc, pre_op, wconv[k], bias, nullptr, z, M, H, H, st));
-            XGGM_TRY(gelu_ln_drop_fwd(z, g, b, nullptr, 1.f, h_next, mean, rstd, tc ? mut(next_op.hi) : nullptr,
+            XGGM_TRY(gelu_ln_drop_fwd(z, g, b, drop_none(), h_next, mean, rstd, tc ? mut(next_op.hi) : nullptr,
                                       tc ? lo_or_null(next_op) : nullptr, M, H, LN_EPS, 0, st));
         }
         hops[k + 1] = next_op;
@@ -235,7 +243,7 @@ static int gnn_fwd(int kind, const float* x, const float* adj, const float* cons
         const float* bias = hp[4 * j + 1], *g = hp[4 * j + 2], *b = hp[4 * j + 3];
         float* z = saved + L.head(j, 0);
         XGGM_TRY(proj_fwd(tc, hops[j], whead[j], bias, nullptr, z, M, H, H, st));
-        XGGM_TRY(gelu_ln_drop_fwd(z, g, b, keeps ? keeps[j] : nullptr, scale, out,
+        XGGM_TRY(gelu_ln_drop_fwd(z, g, b, head_drop(keeps, philox, drop_p, j), out,
                                   saved + L.head(j, 1), saved + L.head(j, 2), nullptr, nullptr, M, H, LN_EPS, j > 0, st));
     }
     return XGGM_OK;
@@ -243,7 +251,7 @@ static int gnn_fwd(int kind, const float* x, const float* adj, const float* cons
 
 static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj,
                    const float* const* cp, const float* const* hp, const uint8_t* const* keeps,
-                   float drop_p, const float* saved_c, float* work, float* gx, float* gadj,
+                   const xggm_philox_t* philox, float drop_p, const float* saved_c, float* work, float* gx, float* gadj,
                    float* const* cg, float* const* hg, int B, int N, int H, int nc,
                    cudaStream_t st) {
     XGGM_REQUIRE(kind == XGGM_KIND_GCN || kind == XGGM_KIND_GIN);
@@ -266,7 +274,6 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
     float* saved = const_cast<float*>(saved_c);  // plane regions are read-only here; the cast only feeds planes_at
     const GnnLayout L(kind, M, H, nc);
     const bool tc = use_tc(M, H, H);
-    const float scale = 1.f / (1.f - drop_p);
     const long long MH = L.MH, MHn = (long long)M * H;
     float* buf[2] = {work, work + MH};
     float* gt = work + 2 * MH;  // gz / gu
@@ -296,7 +303,7 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
         // bias gradient) are accumulated by the same kernel
         const Operand g = grad_op(gt);
         XGGM_TRY(gelu_ln_drop_bwd(gout, saved + L.head(j, 0), saved + L.head(j, 1), saved + L.head(j, 2),
-                                  hp[4 * j + 2], keeps ? keeps[j] : nullptr, scale, tc ? nullptr : gt,
+                                  hp[4 * j + 2], head_drop(keeps, philox, drop_p, j), tc ? nullptr : gt,
                                   hg[4 * j + 2], hg[4 * j + 3], hg[4 * j + 1], tc ? mut(g.hi) : nullptr,
                                   tc ? lo_or_null(g) : nullptr, M, H, st));
         XGGM_TRY(proj_wgrad(tc, g, act(j), hg[4 * j], M, H, H, st));
@@ -338,7 +345,7 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
             XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k + 2], 0, sizeof(float) * H, st));
             const Operand gz = grad_op(gt);
             XGGM_TRY(gelu_ln_drop_bwd(gh, saved + L.conv(k, 1), saved + L.conv(k, 3), saved + L.conv(k, 4),
-                                      g, nullptr, 1.f, tc ? nullptr : gt, cg[5 * k + 3], cg[5 * k + 4], cg[5 * k + 2],
+                                      g, drop_none(), tc ? nullptr : gt, cg[5 * k + 3], cg[5 * k + 4], cg[5 * k + 2],
                                       tc ? mut(gz.hi) : nullptr, tc ? lo_or_null(gz) : nullptr, M, H, st));
             XGGM_TRY(proj_wgrad(tc, gz, pre_op, cg[5 * k + 1], M, H, H, st));
             XGGM_TRY(proj_dgrad(tc, gz, wconv[k], gq, M, H, H, 0, st, gram ? &gq_op : nullptr));      // gpre
@@ -509,14 +516,14 @@ int xggm_gelu_ln_drop_fwd(const float* z, const float* gamma, const float* beta,
                           int M, int H, float eps, int accumulate, xggm_stream_t s) {
     if (M == 0) return XGGM_OK;
     XGGM_REQUIRE(z && gamma && beta && out && M >= 0 && H > 0);
-    return gelu_ln_drop_fwd(z, gamma, beta, keep, scale, out, mean, rstd, nullptr, nullptr, M, H, eps, accumulate, as_stream(s));
+    return gelu_ln_drop_fwd(z, gamma, beta, drop_mask(keep, scale), out, mean, rstd, nullptr, nullptr, M, H, eps, accumulate, as_stream(s));
 }
 int xggm_gelu_ln_drop_bwd(const float* gout, const float* z, const float* mean, const float* rstd,
                           const float* gamma, const uint8_t* keep, float scale, float* gz,
                           float* ggamma, float* gbeta, int M, int H, xggm_stream_t s) {
     if (M == 0) return XGGM_OK;
     XGGM_REQUIRE(gout && z && mean && rstd && gamma && gz && ggamma && gbeta && M >= 0 && H > 0);
-    return gelu_ln_drop_bwd(gout, z, mean, rstd, gamma, keep, scale, gz, ggamma, gbeta, nullptr, nullptr, nullptr, M, H, as_stream(s));
+    return gelu_ln_drop_bwd(gout, z, mean, rstd, gamma, drop_mask(keep, scale), gz, ggamma, gbeta, nullptr, nullptr, nullptr, M, H, as_stream(s));
 }
 
 long long xggm_adj_regen_work_bytes(int B, int N, int H) {
@@ -558,17 +565,17 @@ long long xggm_gnn_work_floats(int kind, int B, int N, int H, int n_convs) {
     return wb > L.work_fwd() ? wb : L.work_fwd();
 }
 int xggm_gnn_fwd(int kind, const float* x, const float* adj, const float* const* conv_params,
-                 const float* const* head_params, const uint8_t* const* keeps, float drop_p,
-                 float* out, float* saved, float* work, int B, int N, int H, int n_convs,
+                 const float* const* head_params, const uint8_t* const* keeps, const xggm_philox_t* philox,
+                 float drop_p, float* out, float* saved, float* work, int B, int N, int H, int n_convs,
                  xggm_stream_t s) {
-    return gnn_fwd(kind, x, adj, conv_params, head_params, keeps, drop_p, out, saved, work, B, N, H, n_convs, as_stream(s));
+    return gnn_fwd(kind, x, adj, conv_params, head_params, keeps, philox, drop_p, out, saved, work, B, N, H, n_convs, as_stream(s));
 }
 int xggm_gnn_bwd(int kind, const float* gout, const float* x, const float* adj,
                  const float* const* conv_params, const float* const* head_params,
-                 const uint8_t* const* keeps, float drop_p, const float* saved, float* work,
-                 float* gx, float* gadj, float* const* conv_grads, float* const* head_grads,
+                 const uint8_t* const* keeps, const xggm_philox_t* philox, float drop_p, const float* saved,
+                 float* work, float* gx, float* gadj, float* const* conv_grads, float* const* head_grads,
                  int B, int N, int H, int n_convs, xggm_stream_t s) {
-    return gnn_bwd(kind, gout, x, adj, conv_params, head_params, keeps, drop_p, saved, work, gx, gadj,
+    return gnn_bwd(kind, gout, x, adj, conv_params, head_params, keeps, philox, drop_p, saved, work, gx, gadj,
                    conv_grads, head_grads, B, N, H, n_convs, as_stream(s));
 }
 
@@ -678,10 +685,10 @@ int xggm_sigmoid_bwd(const float* gy, const float* y, float* gx, long long n, xg
     return sigmoid_bwd(gy, y, gx, n, as_stream(s));
 }
 int xggm_keep_mask(uint8_t* keep, long long n, float p, uint64_t seed, uint64_t stream_id,
-                   xggm_stream_t s) {
+                   const uint64_t* dev_epoch, xggm_stream_t s) {
     if (n == 0) return XGGM_OK;
     XGGM_REQUIRE(keep && n >= 0);
-    return keep_mask(keep, n, p, seed, stream_id, as_stream(s));
+    return keep_mask(keep, n, p, seed, stream_id, dev_epoch, as_stream(s));
 }
 
 }  // extern "C"

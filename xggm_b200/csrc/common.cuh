@@ -90,4 +90,26 @@ struct Philox {
     }
 };
 
+// Dropout of the read-out heads (F.dropout, src/module/gcn.py:72-76), three ways:
+//   mode 0 none; mode 1 explicit uint8 keep-mask (parity runs inject the reference's masks);
+//   mode 2 Philox4x32-10 drawn inside the consuming kernel: key = seed, counter = element/4,
+//          subsequence = stream + (*epoch << 32).  `epoch` is an optional DEVICE counter so that a
+//          captured CUDA graph draws fresh masks on every replay.
+struct DropSpec {
+    const uint8_t* keep;
+    const uint64_t* epoch;
+    uint64_t seed, stream;
+    uint32_t thresh;   // keep iff random word >= thresh
+    float scale;       // 1 / (1 - p)
+    int mode;
+};
+static inline uint32_t drop_threshold(float p) {
+    const double t = (double)p * 4294967296.0;
+    return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+}
+static inline DropSpec drop_none() { return DropSpec{nullptr, nullptr, 0, 0, 0u, 1.f, 0}; }
+static inline DropSpec drop_mask(const uint8_t* keep, float scale) {
+    return keep ? DropSpec{keep, nullptr, 0, 0, 0u, scale, 1} : drop_none();
+}
+
 }  // namespace xggm

@@ -366,22 +366,31 @@ int mask_scale(const float* x, const uint8_t* keep, float scale, float* y, long 
 }
 
 // ----------------------------------------------------------------- keep mask
+// 4 elements per thread, one Philox call, one 4-byte store.  Same draw as DropSpec mode 2.
 __global__ void keep_mask_kernel(uint8_t* __restrict__ keep, long long n, uint32_t thresh,
-                                 uint64_t seed, uint64_t stream_id) {
-    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // 4 elements per thread
+                                 uint64_t seed, uint64_t stream_id, const uint64_t* __restrict__ epoch,
+                                 int aligned4) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (q * 4 >= n) return;
-    const uint4 r = Philox(seed)((uint64_t)q, stream_id);
+    const uint64_t stream = stream_id + (epoch ? (*epoch << 32) : 0ull);
+    const uint4 r = Philox(seed)((uint64_t)q, stream);
     const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    if (aligned4 && q * 4 + 3 < n) {
+        uchar4 o;
+        o.x = w[0] >= thresh; o.y = w[1] >= thresh; o.z = w[2] >= thresh; o.w = w[3] >= thresh;
+        reinterpret_cast<uchar4*>(keep)[q] = o;
+    } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-        if (q * 4 + i < n) keep[q * 4 + i] = w[i] >= thresh ? 1 : 0;
+        for (int i = 0; i < 4; ++i)
+            if (q * 4 + i < n) keep[q * 4 + i] = w[i] >= thresh ? 1 : 0;
+    }
 }
-int keep_mask(uint8_t* keep, long long n, float p, uint64_t seed, uint64_t stream_id, cudaStream_t st) {
+int keep_mask(uint8_t* keep, long long n, float p, uint64_t seed, uint64_t stream_id, const uint64_t* epoch,
+              cudaStream_t st) {
     if (n <= 0) return XGGM_OK;
     XGGM_REQUIRE(p >= 0.f && p < 1.f);
-    const double t = (double)p * 4294967296.0;
-    const uint32_t thresh = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
-    keep_mask_kernel<<<grid1d((n + 3) / 4), 256, 0, st>>>(keep, n, thresh, seed, stream_id);
+    const int aligned4 = (reinterpret_cast<uintptr_t>(keep) & 3) == 0;
+    keep_mask_kernel<<<grid1d((n + 3) / 4), 256, 0, st>>>(keep, n, drop_threshold(p), seed, stream_id, epoch, aligned4);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }

@@ -159,14 +159,37 @@ __device__ __forceinline__ void load_keep4(const uint8_t* __restrict__ k, size_t
     m[0] = t.x != 0; m[1] = t.y != 0; m[2] = t.z != 0; m[3] = t.w != 0;
 }
 
+// keep decision for the 4 consecutive elements starting at flat offset `off` (off % 4 == 0):
+// mode 1 reads the uint8 mask, mode 2 draws them with Philox exactly as keep_mask_kernel would
+// (counter = off / 4, subsequence = stream), so a mask tensor never has to exist.
+__device__ __forceinline__ void drop_bits4(const DropSpec& d, uint64_t stream, size_t off, bool (&m)[4]) {
+    if (d.mode == 1) {
+        load_keep4(d.keep, off, m);
+    } else {
+        const uint4 r = Philox(d.seed)((uint64_t)(off >> 2), stream);
+        m[0] = r.x >= d.thresh; m[1] = r.y >= d.thresh; m[2] = r.z >= d.thresh; m[3] = r.w >= d.thresh;
+    }
+}
+__device__ __forceinline__ bool drop_bit1(const DropSpec& d, uint64_t stream, size_t off) {
+    if (d.mode == 1) return d.keep[off] != 0;
+    const uint4 r = Philox(d.seed)((uint64_t)(off >> 2), stream);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    return w[off & 3] >= d.thresh;
+}
+__device__ __forceinline__ uint64_t drop_stream(const DropSpec& d) {
+    return d.stream + ((d.mode == 2 && d.epoch) ? (*d.epoch << 32) : 0ull);
+}
+
 template <int NV>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 gld_fwd_fast(const float* __restrict__ z, const float* __restrict__ gamma, const float* __restrict__ beta,
-             const uint8_t* __restrict__ keep, float scale, float* __restrict__ out,
+             const DropSpec drop, float* __restrict__ out,
              float* __restrict__ mean_out, float* __restrict__ rstd_out, bf16* __restrict__ hi,
              bf16* __restrict__ lo, int M, float eps, int accumulate) {
     constexpr int H = NV * 128;
     const int lane = threadIdx.x & 31;
+    const uint64_t dstream = drop_stream(drop);
+    const float scale = drop.scale;
     const int wid = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5), nw = gridDim.x * ROW_WARPS;
     float g[NV * 4], b[NV * 4];
     load_row<NV>(gamma, lane, g);
@@ -181,11 +204,11 @@ gld_fwd_fast(const float* __restrict__ z, const float* __restrict__ gamma, const
         row_stats<NV>(v, 1.0f / (float)H, eps, mean, rstd);
 #pragma unroll
         for (int i = 0; i < NV * 4; ++i) v[i] = fmaf((v[i] - mean) * rstd, g[i], b[i]);
-        if (keep) {
+        if (drop.mode) {
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 bool m[4];
-                load_keep4(keep, ro + 128 * i + 4 * lane, m);
+                drop_bits4(drop, dstream, ro + 128 * i + 4 * lane, m);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) v[4 * i + j] = m[j] ? v[4 * i + j] * scale : 0.f;
             }
@@ -208,12 +231,14 @@ gld_fwd_fast(const float* __restrict__ z, const float* __restrict__ gamma, const
 template <int NV>
 __global__ void __launch_bounds__(ROW_WARPS * 32, 1)
 gld_bwd_fast(const float* __restrict__ gout, const float* __restrict__ z, const float* __restrict__ mean,
-             const float* __restrict__ rstd, const float* __restrict__ gamma, const uint8_t* __restrict__ keep,
-             float scale, float* __restrict__ gz, float* __restrict__ ggamma, float* __restrict__ gbeta,
+             const float* __restrict__ rstd, const float* __restrict__ gamma, const DropSpec drop,
+             float* __restrict__ gz, float* __restrict__ ggamma, float* __restrict__ gbeta,
              float* __restrict__ gbias, bf16* __restrict__ hi, bf16* __restrict__ lo, int M) {
     constexpr int H = NV * 128;
     extern __shared__ float sm[];
     const int lane = threadIdx.x & 31;
+    const uint64_t dstream = drop_stream(drop);
+    const float scale = drop.scale;
     const int wid = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5), nw = gridDim.x * ROW_WARPS;
     float ag[NV * 4], ab[NV * 4], az[NV * 4];
 #pragma unroll
@@ -223,11 +248,11 @@ gld_bwd_fast(const float* __restrict__ gout, const float* __restrict__ z, const 
         float gy[NV * 4], zv[NV * 4], yh[NV * 4];
         load_row<NV>(gout + ro, lane, gy);
         load_row<NV>(z + ro, lane, zv);
-        if (keep) {
+        if (drop.mode) {
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 bool m[4];
-                load_keep4(keep, ro + 128 * i + 4 * lane, m);
+                drop_bits4(drop, dstream, ro + 128 * i + 4 * lane, m);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) gy[4 * i + j] = m[j] ? gy[4 * i + j] * scale : 0.f;
             }
@@ -358,10 +383,12 @@ ln_bwd_gen(const float* __restrict__ gh, const float* __restrict__ xhat, const f
 
 __global__ void __launch_bounds__(GEN_WARPS * 32)
 gld_fwd_gen(const float* __restrict__ z, const float* __restrict__ gamma, const float* __restrict__ beta,
-            const uint8_t* __restrict__ keep, float scale, float* __restrict__ out,
+            const DropSpec drop, float* __restrict__ out,
             float* __restrict__ mean_out, float* __restrict__ rstd_out, bf16* __restrict__ hi,
             bf16* __restrict__ lo, int M, int H, float eps, int accumulate) {
     const int lane = threadIdx.x & 31;
+    const uint64_t dstream = drop_stream(drop);
+    const float scale = drop.scale;
     int r0, r1;
     row_range(M, r0, r1);
     for (int r = r0; r < r1; ++r) {
@@ -375,7 +402,7 @@ gld_fwd_gen(const float* __restrict__ z, const float* __restrict__ gamma, const 
         for (int c = lane; c < H; c += 32) {
             const size_t o = (size_t)r * H + c;
             float y = fmaf((gelu_erf(zr[c]) - mean) * rstd, gamma[c], beta[c]);
-            if (keep) y = keep[o] ? y * scale : 0.f;
+            if (drop.mode) y = drop_bit1(drop, dstream, o) ? y * scale : 0.f;
             if (accumulate) y += out[o];
             out[o] = y;
             if (hi) split_store1(hi, lo, o, y);
@@ -389,11 +416,13 @@ gld_fwd_gen(const float* __restrict__ z, const float* __restrict__ gamma, const 
 
 __global__ void __launch_bounds__(GEN_WARPS * 32)
 gld_bwd_gen(const float* __restrict__ gout, const float* __restrict__ z, const float* __restrict__ mean,
-            const float* __restrict__ rstd, const float* __restrict__ gamma, const uint8_t* __restrict__ keep,
-            float scale, float* __restrict__ gz, float* __restrict__ ggamma, float* __restrict__ gbeta,
+            const float* __restrict__ rstd, const float* __restrict__ gamma, const DropSpec drop,
+            float* __restrict__ gz, float* __restrict__ ggamma, float* __restrict__ gbeta,
             float* __restrict__ gbias, bf16* __restrict__ hi, bf16* __restrict__ lo, int M, int H) {
     extern __shared__ float sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t dstream = drop_stream(drop);
+    const float scale = drop.scale;
     float* sg = sm + (size_t)warp * 3 * H;
     float* sb = sg + H;
     float* sz = sb + H;
@@ -403,12 +432,11 @@ gld_bwd_gen(const float* __restrict__ gout, const float* __restrict__ z, const f
     for (int r = r0; r < r1; ++r) {
         const float* gr = gout + (size_t)r * H;
         const float* zr = z + (size_t)r * H;
-        const uint8_t* kr = keep ? keep + (size_t)r * H : nullptr;
         const float mu = mean[r], rs = rstd[r];
         float s1 = 0.f, s2 = 0.f;
         for (int c = lane; c < H; c += 32) {
             float gy = gr[c];
-            if (kr) gy = kr[c] ? gy * scale : 0.f;
+            if (drop.mode) gy = drop_bit1(drop, dstream, (size_t)r * H + c) ? gy * scale : 0.f;
             const float yh = (gelu_erf(zr[c]) - mu) * rs;
             const float d = gy * gamma[c];
             s1 += d;
@@ -418,7 +446,7 @@ gld_bwd_gen(const float* __restrict__ gout, const float* __restrict__ z, const f
         for (int c = lane; c < H; c += 32) {
             const size_t o = (size_t)r * H + c;
             float gy = gr[c];
-            if (kr) gy = kr[c] ? gy * scale : 0.f;
+            if (drop.mode) gy = drop_bit1(drop, dstream, o) ? gy * scale : 0.f;
             const float zv = zr[c];
             const float yh = (gelu_erf(zv) - mu) * rs;
             const float v = rs * (gy * gamma[c] - c1 - yh * c2) * gelu_erf_grad(zv);
@@ -512,14 +540,14 @@ int layernorm_bwd(const float* gh, const float* xhat, const float* rstd, const f
     return XGGM_OK;
 }
 
-int gelu_ln_drop_fwd(const float* z, const float* gamma, const float* beta, const uint8_t* keep, float scale,
+int gelu_ln_drop_fwd(const float* z, const float* gamma, const float* beta, const DropSpec& drop,
                      float* out, float* mean, float* rstd, bf16* hi, bf16* lo, int M, int H, float eps,
                      int accumulate, cudaStream_t st) {
     if (M <= 0) return XGGM_OK;
-    if (fast_ok(H, z, out, hi) && fast_ok(H, gamma, beta, lo) && (reinterpret_cast<uintptr_t>(keep) & 3) == 0) {
-        XGGM_ROW_DISPATCH(H, (gld_fwd_fast<NV><<<fast_grid(M), ROW_WARPS * 32, 0, st>>>(z, gamma, beta, keep, scale, out, mean, rstd, hi, lo, M, eps, accumulate)));
+    if (fast_ok(H, z, out, hi) && fast_ok(H, gamma, beta, lo) && (reinterpret_cast<uintptr_t>(drop.keep) & 3) == 0) {
+        XGGM_ROW_DISPATCH(H, (gld_fwd_fast<NV><<<fast_grid(M), ROW_WARPS * 32, 0, st>>>(z, gamma, beta, drop, out, mean, rstd, hi, lo, M, eps, accumulate)));
     } else {
-        gld_fwd_gen<<<gen_grid(M), GEN_WARPS * 32, 0, st>>>(z, gamma, beta, keep, scale, out, mean, rstd, hi, lo, M, H, eps, accumulate);
+        gld_fwd_gen<<<gen_grid(M), GEN_WARPS * 32, 0, st>>>(z, gamma, beta, drop, out, mean, rstd, hi, lo, M, H, eps, accumulate);
     }
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
@@ -527,16 +555,16 @@ int gelu_ln_drop_fwd(const float* z, const float* gamma, const float* beta, cons
 
 // gz may be null (only the planes are wanted); ggamma / gbeta / gbias? are ACCUMULATED into
 int gelu_ln_drop_bwd(const float* gout, const float* z, const float* mean, const float* rstd, const float* gamma,
-                     const uint8_t* keep, float scale, float* gz, float* ggamma, float* gbeta, float* gbias,
+                     const DropSpec& drop, float* gz, float* ggamma, float* gbeta, float* gbias,
                      bf16* hi, bf16* lo, int M, int H, cudaStream_t st) {
     if (M <= 0) return XGGM_OK;
-    if (fast_ok(H, gout, z, gz) && fast_ok(H, gamma, hi, lo) && (reinterpret_cast<uintptr_t>(keep) & 3) == 0) {
+    if (fast_ok(H, gout, z, gz) && fast_ok(H, gamma, hi, lo) && (reinterpret_cast<uintptr_t>(drop.keep) & 3) == 0) {
         const size_t smem = sizeof(float) * ROW_WARPS * H;
-        XGGM_ROW_DISPATCH(H, (gld_bwd_fast<NV><<<fast_grid(M, 1), ROW_WARPS * 32, smem, st>>>(gout, z, mean, rstd, gamma, keep, scale, gz, ggamma, gbeta, gbias, hi, lo, M)));
+        XGGM_ROW_DISPATCH(H, (gld_bwd_fast<NV><<<fast_grid(M, 1), ROW_WARPS * 32, smem, st>>>(gout, z, mean, rstd, gamma, drop, gz, ggamma, gbeta, gbias, hi, lo, M)));
     } else {
         size_t smem;
         XGGM_TRY(gen_smem(gld_bwd_gen, H, smem));
-        gld_bwd_gen<<<gen_grid(M), GEN_WARPS * 32, smem, st>>>(gout, z, mean, rstd, gamma, keep, scale, gz, ggamma, gbeta, gbias, hi, lo, M, H);
+        gld_bwd_gen<<<gen_grid(M), GEN_WARPS * 32, smem, st>>>(gout, z, mean, rstd, gamma, drop, gz, ggamma, gbeta, gbias, hi, lo, M, H);
     }
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;

@@ -5,6 +5,8 @@ allocator and stream semantics stay torch's) and enqueues the kernels on
 ``torch.cuda.current_stream()`` through ``_lib.call``.  There is no eager
 PyTorch fallback anywhere in this file.
 """
+import ctypes as C
+
 import torch
 
 from . import _lib
@@ -224,7 +226,7 @@ def adj_regen(x, squash=True, return_argmax=False):
 # ---------------------------------------------------------------------------
 class _GnnLayer(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, kind, n_convs, drop_p, keeps, x, adj, *params):
+    def forward(ctx, kind, n_convs, drop_p, keeps, philox, x, adj, *params):
         x, adj = f32(x, "x"), f32(adj, "adj")
         B, N, H = x.shape
         if adj.shape != (B, N, N):
@@ -246,10 +248,11 @@ class _GnnLayer(torch.autograd.Function):
         out = torch.empty_like(x)
         cpt, hpt = ptr_table(cp), ptr_table(hp)
         kt = None if keeps is None else ptr_table(keeps)
-        call("xggm_gnn_fwd", kind, ptr(x), ptr(adj), cpt, hpt, kt, float(drop_p), ptr(out), ptr(saved),
-             ptr(work), B, N, H, n_convs)
+        call("xggm_gnn_fwd", kind, ptr(x), ptr(adj), cpt, hpt, kt, _philox_arg(philox), float(drop_p), ptr(out),
+             ptr(saved), ptr(work), B, N, H, n_convs)
         ctx.save_for_backward(x, adj, saved, *params)
         ctx.keeps = keeps
+        ctx.philox = philox
         ctx.cfg = (kind, n_convs, float(drop_p), n_cp)
         return out
 
@@ -267,19 +270,36 @@ class _GnnLayer(torch.autograd.Function):
         gadj = torch.empty_like(adj)
         grads = [torch.empty_like(p) for p in params]
         kt = None if ctx.keeps is None else ptr_table(ctx.keeps)
-        call("xggm_gnn_bwd", kind, ptr(g), ptr(x), ptr(adj), ptr_table(cp), ptr_table(hp), kt, drop_p,
-             ptr(saved), ptr(work), ptr(gx), ptr(gadj), ptr_table(grads[:n_cp]), ptr_table(grads[n_cp:]),
-             B, N, H, n_convs)
-        return (None, None, None, None, gx, gadj, *grads)
+        call("xggm_gnn_bwd", kind, ptr(g), ptr(x), ptr(adj), ptr_table(cp), ptr_table(hp), kt,
+             _philox_arg(ctx.philox), drop_p, ptr(saved), ptr(work), ptr(gx), ptr(gadj), ptr_table(grads[:n_cp]),
+             ptr_table(grads[n_cp:]), B, N, H, n_convs)
+        return (None, None, None, None, None, gx, gadj, *grads)
 
 
-def gnn_layer(kind, x, adj, conv_params, head_params, keeps=None, drop_p=0.5):
+def _philox_arg(philox):
+    """(seed, stream0, epoch_tensor|None) -> pointer to an xggm_philox_t (or NULL)."""
+    if philox is None:
+        return None
+    seed, stream0, epoch = philox
+    spec = _lib.PhiloxSpec(seed & (2 ** 64 - 1), stream0, None if epoch is None else epoch.data_ptr())
+    return C.cast(C.pointer(spec), C.c_void_p)
+
+
+def gnn_layer(kind, x, adj, conv_params, head_params, training=False, drop_p=0.5):
     """One GCN (kind='GCN') or GIN (kind='GIN') layer: conv chain + jump-knowledge heads.
-    conv_params / head_params are flat lists in the order documented in xggm_b200.h."""
+    conv_params / head_params are flat lists in the order documented in xggm_b200.h.
+    Training-mode dropout of the heads: injected keep-masks if any are queued (parity runs),
+    otherwise Philox bits drawn inside the kernels (no mask tensors)."""
     k = KIND[kind]
     per_conv = 3 if k == 0 else 5
     n_convs = len(conv_params) // per_conv
-    return _GnnLayer.apply(k, n_convs, drop_p, keeps, x, adj, *conv_params, *head_params)
+    keeps = philox = None
+    if training and drop_p > 0.0:
+        if _mask_feed:
+            keeps = [keep_mask(x.shape, drop_p, x.device) for _ in range(n_convs + 1)]
+        else:
+            philox = (torch.initial_seed(), _next_sites(n_convs + 1), _drop.epoch)
+    return _GnnLayer.apply(k, n_convs, drop_p, keeps, philox, x, adj, *conv_params, *head_params)
 
 
 # ---------------------------------------------------------------------------
@@ -554,14 +574,42 @@ def sigmoid(x):
 # ---------------------------------------------------------------------------
 # dropout keep-masks (Philox, generated on the device by the library)
 # ---------------------------------------------------------------------------
-_mask_calls = 0
+class _DropState:
+    site = 0       # next Philox subsequence id (one per dropout site)
+    epoch = None   # device int64 counter while a CUDA-graph-captured step is being built / replayed
+
+
+_drop = _DropState()
 _mask_feed = []
+
+
+def _next_sites(n):
+    s = _drop.site
+    _drop.site += n
+    return s
+
+
+class dropout_epoch:
+    """Context for CUDA-graph capture: dropout sites are numbered from ``base`` on every entry (so the
+    captured kernels and their replays agree) and every site adds ``epoch`` -- a device int64 tensor
+    the captured step increments -- to its Philox subsequence, so each replay draws new masks."""
+
+    def __init__(self, epoch, base=0):
+        self.epoch, self.base = epoch, base
+
+    def __enter__(self):
+        self.old = (_drop.site, _drop.epoch)
+        _drop.site, _drop.epoch = self.base, self.epoch
+        return self
+
+    def __exit__(self, *exc):
+        _drop.site, _drop.epoch = self.old
+        return False
 
 
 def keep_mask(shape, p, device):
     """uint8 keep-mask: injected (parity runs, see inject_keep_masks) or Philox-generated
     keyed by (torch.initial_seed(), call counter) -- deterministic under torch.manual_seed."""
-    global _mask_calls
     if _mask_feed:
         m = _mask_feed.pop(0)
         if tuple(m.shape) != tuple(shape):
@@ -569,8 +617,8 @@ def keep_mask(shape, p, device):
         return _u8(m.to(device))
     m = torch.empty(shape, device=device, dtype=torch.uint8)
     _lib.check_device(m)
-    _mask_calls += 1
-    call("xggm_keep_mask", ptr(m), m.numel(), float(p), torch.initial_seed() & (2 ** 64 - 1), _mask_calls)
+    call("xggm_keep_mask", ptr(m), m.numel(), float(p), torch.initial_seed() & (2 ** 64 - 1), _next_sites(1),
+         ptr(_drop.epoch))
     return m
 
 

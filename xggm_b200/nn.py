@@ -86,10 +86,7 @@ class GCN(nn.Module):
 
     def forward(self, x, adj):
         cp, hp = self._flat_params()
-        keeps = None
-        if self.training and self.dropout_p > 0.0:
-            keeps = [XF.keep_mask(x.shape, self.dropout_p, x.device) for _ in self.linear_prediction]
-        return XF.gnn_layer("GCN", x, adj, cp, hp, keeps, self.dropout_p)
+        return XF.gnn_layer("GCN", x, adj, cp, hp, self.training, self.dropout_p)
 
 
 # ---------------------------------------------------------------------------
@@ -128,10 +125,7 @@ class GIN(nn.Module):
 
     def forward(self, X, A):
         cp, hp = self._flat_params()
-        keeps = None
-        if self.training and self.dropout_p > 0.0:
-            keeps = [XF.keep_mask(X.shape, self.dropout_p, X.device) for _ in self.linear_prediction]
-        return XF.gnn_layer("GIN", X, A, cp, hp, keeps, self.dropout_p)
+        return XF.gnn_layer("GIN", X, A, cp, hp, self.training, self.dropout_p)
 
 
 # ---------------------------------------------------------------------------
