@@ -79,9 +79,10 @@ int xggm_linear_fwd(const float* a, const float* w, const float* bias, const flo
 /* ga[M,K] (+)= g[M,N] w[N,K]   (accumulate != 0 adds into ga) */
 int xggm_linear_bwd_input(const float* g, const float* w, float* ga, int M, int N, int K,
                           int accumulate, void* work, xggm_stream_t s);
-/* gw[N,K] = g[M,N]^T a[M,K];  gbias[N]? = column sums of g.  Overwrites. */
+/* gw[N,K] (+)= g[M,N]^T a[M,K];  gbias[N]? (+)= column sums of g.  accumulate != 0 adds into the
+ * buffers (gradient accumulation straight into a parameter's .grad), otherwise they are overwritten. */
 int xggm_linear_bwd_weight(const float* g, const float* a, float* gw, float* gbias,
-                           int M, int N, int K, void* work, xggm_stream_t s);
+                           int M, int N, int K, int accumulate, void* work, xggm_stream_t s);
 
 /* ------------------------------------------------------------------------- *
  * Adjacency-weighted message passing
@@ -165,13 +166,14 @@ int xggm_gnn_fwd(int kind, const float* x, const float* adj, const float* const*
                  const float* const* head_params, const uint8_t* const* keeps, const xggm_philox_t* philox,
                  float drop_p, float* out, float* saved, float* work, int B, int N, int H, int n_convs,
                  xggm_stream_t s);
-/* Gradient tables mirror the parameter tables (same order); every gradient buffer is
- * OVERWRITTEN.  gadj[B,N,N] and gx[B,N,H] are overwritten. */
+/* Gradient tables mirror the parameter tables (same order); every parameter-gradient buffer is
+ * overwritten, or accumulated into when accumulate_param_grads != 0 (the buffers then are the
+ * parameters' live .grad tensors).  gadj[B,N,N] and gx[B,N,H] are always overwritten. */
 int xggm_gnn_bwd(int kind, const float* gout, const float* x, const float* adj,
                  const float* const* conv_params, const float* const* head_params,
                  const uint8_t* const* keeps, const xggm_philox_t* philox, float drop_p, const float* saved,
                  float* work, float* gx, float* gadj, float* const* conv_grads, float* const* head_grads,
-                 int B, int N, int H, int n_convs, xggm_stream_t s);
+                 int accumulate_param_grads, int B, int N, int H, int n_convs, xggm_stream_t s);
 
 /* ------------------------------------------------------------------------- *
  * GAT attention  src/module/gat.py:25-49 (after h = linear_layer(x), which is

@@ -34,15 +34,19 @@ def _run(M, N, K, seed=0):
     gb = torch.full((N,), float("nan"), device=dev)
     call("xggm_linear_fwd", ptr(a_d), ptr(w_d), ptr(b_d), ptr(r_d), ptr(out), M, N, K, ptr(work))
     call("xggm_linear_bwd_input", ptr(g_d), ptr(w_d), ptr(ga), M, N, K, 0, ptr(work))
-    call("xggm_linear_bwd_weight", ptr(g_d), ptr(a_d), ptr(gw), ptr(gb), M, N, K, ptr(work))
+    call("xggm_linear_bwd_weight", ptr(g_d), ptr(a_d), ptr(gw), ptr(gb), M, N, K, 0, ptr(work))
+    # accumulate flag of wgrad (gradient accumulation straight into a .grad buffer)
+    gw2 = torch.full((N, K), 2.0, device=dev)
+    gb2 = torch.full((N,), 3.0, device=dev)
+    call("xggm_linear_bwd_weight", ptr(g_d), ptr(a_d), ptr(gw2), ptr(gb2), M, N, K, 1, ptr(work))
     # accumulate flag of dgrad
     ga2 = torch.ones((M, K), device=dev)
     call("xggm_linear_bwd_input", ptr(g_d), ptr(w_d), ptr(ga2), M, N, K, 1, ptr(work))
     torch.cuda.synchronize()
     a64, w64, g64 = a.double(), w.double(), go.double()
     ref = {"out": a64 @ w64.T + bias.double() + resid.double(), "ga": g64 @ w64, "gw": g64.T @ a64,
-           "gb": g64.sum(0), "ga_acc": g64 @ w64 + 1.0}
-    got = {"out": out, "ga": ga, "gw": gw, "gb": gb, "ga_acc": ga2}
+           "gb": g64.sum(0), "ga_acc": g64 @ w64 + 1.0, "gw_acc": g64.T @ a64 + 2.0, "gb_acc": g64.sum(0) + 3.0}
+    got = {"out": out, "ga": ga, "gw": gw, "gb": gb, "ga_acc": ga2, "gw_acc": gw2, "gb_acc": gb2}
     return {k: (rel_l2(got[k].cpu(), ref[k]), rel_max(got[k].cpu(), ref[k])) for k in ref}
 
 

@@ -464,3 +464,31 @@ def test_graphed_step_matches_eager_and_redraws_dropout():
     torch.cuda.synchronize()
     assert torch.isfinite(a).all() and torch.isfinite(b).all()
     assert not torch.equal(a, b)
+
+
+def test_fused_grad_accumulation_matches_autograd_accumulation():
+    """Kernels accumulating straight into pre-existing .grad buffers == autograd's AccumulateGrad path,
+    including accumulation over two backward passes."""
+    import xggm_b200 as X
+    import xggm_b200.functional as XF
+    from xggm_b200.ddp import FlatGrads
+    torch.manual_seed(3)
+    B, H = 4, 768
+    visn, xp, adj_true = (t.to(dev()) for t in O.make_inputs(21, B, 36, H))
+    randn = torch.randn(B, 36, H, device=dev())
+    out = {}
+    for fused in (True, False):
+        torch.manual_seed(5)
+        model = X.XGGMHeads(H, "GIN", 2).to(dev()).eval()
+        grads = FlatGrads(model.parameters())
+        XF.FUSE_GRAD_ACCUMULATION = fused
+        try:
+            for _ in range(2):   # two passes: the second must ADD to the first
+                x = xp.clone().requires_grad_(True)
+                x_gen, loss_sm, _, _ = model.relation_step(x, visn, adj_true, 1.0, 2274, 12.0, randn[:, :, :36].contiguous())
+                (x_gen.sum() + loss_sm).backward()
+        finally:
+            XF.FUSE_GRAD_ACCUMULATION = True
+        out[fused] = grads.flat.clone()
+    assert float(out[False].abs().max()) > 0
+    assert rel_l2(out[True].cpu(), out[False].cpu()) < 2e-6

@@ -28,7 +28,7 @@ SIGNATURES = {
     "xggm_linear_work_bytes": [_i, _i, _i],
     "xggm_linear_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp],
     "xggm_linear_bwd_input": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
-    "xggm_linear_bwd_weight": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp],
+    "xggm_linear_bwd_weight": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "xggm_adj_apply_fwd": [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _f, _vp],
     "xggm_adj_apply_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _f, _i, _vp],
     "xggm_layernorm_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp],
@@ -42,7 +42,7 @@ SIGNATURES = {
     "xggm_gnn_work_floats": [_i, _i, _i, _i, _i],
     "xggm_gnn_fwd": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "xggm_gnn_bwd": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp,
-                     _i, _i, _i, _i, _vp],
+                     _i, _i, _i, _i, _i, _vp],
     "xggm_gat_attn_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp],
     "xggm_gat_attn_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp],
     "xggm_gelu_fwd": [_vp, _vp, _ll, _vp],

@@ -12,7 +12,7 @@ namespace xggm {
 // ---- declarations of the per-file launchers --------------------------------
 int gemm_simt(int op, const float* A, const float* Bm, const float* bias, const float* resid,
               float* C, int M, int N, int K, int accumulate, cudaStream_t st);
-int colsum(const float* g, float* out, int R, int C, cudaStream_t st);
+int colsum(const float* g, float* out, int R, int C, int accumulate, cudaStream_t st);
 bool gemm_tc_supported(int M, int N, int K);
 int gemm_tc(bool a_mn, bool b_mn, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const __nv_bfloat16* b_hi,
             const __nv_bfloat16* b_lo, const float* bias, const float* resid, float* C, __nv_bfloat16* c_hi,
@@ -114,9 +114,9 @@ static int proj_dgrad(bool tc, const Operand& g, const Operand& w, float* ga, in
 }
 // gw[N,K] = g[M,N]^T a[M,K]
 static int proj_wgrad(bool tc, const Operand& g, const Operand& a, float* gw, int M, int N, int K,
-                      cudaStream_t st) {
-    if (tc) return gemm_tc(true, true, g.hi, g.lo, a.hi, a.lo, nullptr, nullptr, gw, nullptr, nullptr, N, K, M, 0, 1, npass(), st);
-    return gemm_simt(2, g.f32, a.f32, nullptr, nullptr, gw, N, K, M, 0, st);
+                      int accumulate, cudaStream_t st) {
+    if (tc) return gemm_tc(true, true, g.hi, g.lo, a.hi, a.lo, nullptr, nullptr, gw, nullptr, nullptr, N, K, M, accumulate, 1, npass(), st);
+    return gemm_simt(2, g.f32, a.f32, nullptr, nullptr, gw, N, K, M, accumulate, st);
 }
 
 // ---- saved-activation layout of one GCN / GIN layer ---------------------------
@@ -252,11 +252,12 @@ static int gnn_fwd(int kind, const float* x, const float* adj, const float* cons
 static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj,
                    const float* const* cp, const float* const* hp, const uint8_t* const* keeps,
                    const xggm_philox_t* philox, float drop_p, const float* saved_c, float* work, float* gx, float* gadj,
-                   float* const* cg, float* const* hg, int B, int N, int H, int nc,
+                   float* const* cg, float* const* hg, int acc, int B, int N, int H, int nc,
                    cudaStream_t st) {
     XGGM_REQUIRE(kind == XGGM_KIND_GCN || kind == XGGM_KIND_GIN);
     XGGM_REQUIRE(B >= 0 && N > 0 && H > 0 && nc >= 0 && nc <= MAX_CONVS && cp && hp && cg && hg);
     const int M = B * N;
+    if (M == 0 && acc) return XGGM_OK;
     if (M == 0) {  // empty batch: parameter gradients are zero
         const int per = (kind == XGGM_KIND_GCN) ? 3 : 5;
         for (int k = 0; k < nc; ++k)
@@ -296,9 +297,9 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
 
     // head j contributes gz_j -> (gW_j, gb_j, ggamma_j, gbeta_j) and gz_j W_j into grad of h_j
     auto head_bwd = [&](int j, float* gh, int accumulate) -> int {
-        XGGM_CUDA_TRY(cudaMemsetAsync(hg[4 * j + 2], 0, sizeof(float) * H, st));
-        XGGM_CUDA_TRY(cudaMemsetAsync(hg[4 * j + 3], 0, sizeof(float) * H, st));
-        XGGM_CUDA_TRY(cudaMemsetAsync(hg[4 * j + 1], 0, sizeof(float) * H, st));
+        if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(hg[4 * j + 2], 0, sizeof(float) * H, st));
+        if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(hg[4 * j + 3], 0, sizeof(float) * H, st));
+        if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(hg[4 * j + 1], 0, sizeof(float) * H, st));
         // gz only exists as GEMM-operand planes under the tensor-core engine; its column sums (the
         // bias gradient) are accumulated by the same kernel
         const Operand g = grad_op(gt);
@@ -306,7 +307,7 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
                                   hp[4 * j + 2], head_drop(keeps, philox, drop_p, j), tc ? nullptr : gt,
                                   hg[4 * j + 2], hg[4 * j + 3], hg[4 * j + 1], tc ? mut(g.hi) : nullptr,
                                   tc ? lo_or_null(g) : nullptr, M, H, st));
-        XGGM_TRY(proj_wgrad(tc, g, act(j), hg[4 * j], M, H, H, st));
+        XGGM_TRY(proj_wgrad(tc, g, act(j), hg[4 * j], M, H, H, acc, st));
         XGGM_TRY(proj_dgrad(tc, g, whead[j], gh, M, H, H, accumulate, st));
         return XGGM_OK;
     };
@@ -320,14 +321,14 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
         const Operand pre_op = planes_at(saved + L.conv(k, 0), saved + L.conv(k, 5), MHn);
         if (kind == XGGM_KIND_GCN) {
             const float* g = cp[3 * k + 1];
-            XGGM_CUDA_TRY(cudaMemsetAsync(cg[3 * k + 1], 0, sizeof(float) * H, st));
-            XGGM_CUDA_TRY(cudaMemsetAsync(cg[3 * k + 2], 0, sizeof(float) * H, st));
+            if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(cg[3 * k + 1], 0, sizeof(float) * H, st));
+            if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(cg[3 * k + 2], 0, sizeof(float) * H, st));
             // gu = LN backward, written straight into the next-level gradient (residual path)
             const Operand gu = grad_op(gnext);
             XGGM_TRY(layernorm_bwd(gh, saved + L.conv(k, 1), saved + L.conv(k, 3), g, gnext,
                                    cg[3 * k + 1], cg[3 * k + 2], tc ? mut(gu.hi) : nullptr,
                                    tc ? lo_or_null(gu) : nullptr, M, H, st));
-            XGGM_TRY(proj_wgrad(tc, gu, pre_op, cg[3 * k], M, H, H, st));
+            XGGM_TRY(proj_wgrad(tc, gu, pre_op, cg[3 * k], M, H, H, acc, st));
             XGGM_TRY(proj_dgrad(tc, gu, wconv[k], gq, M, H, H, 0, st, gram ? &gq_op : nullptr));  // gq = gu Wc
             if (gram) {   // gadj += gq h_k^T
                 const Operand hk_op = act(k);
@@ -339,15 +340,15 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
             XGGM_TRY(adj_apply(adj, gq, gnext, nullptr, nullptr, B, N, H, 1.f, nullptr, 0.f, true, 1, st));
         } else {
             const float* eps = cp[5 * k], *g = cp[5 * k + 3];
-            XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k], 0, sizeof(float), st));
-            XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k + 3], 0, sizeof(float) * H, st));
-            XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k + 4], 0, sizeof(float) * H, st));
-            XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k + 2], 0, sizeof(float) * H, st));
+            if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k], 0, sizeof(float), st));
+            if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k + 3], 0, sizeof(float) * H, st));
+            if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k + 4], 0, sizeof(float) * H, st));
+            if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k + 2], 0, sizeof(float) * H, st));
             const Operand gz = grad_op(gt);
             XGGM_TRY(gelu_ln_drop_bwd(gh, saved + L.conv(k, 1), saved + L.conv(k, 3), saved + L.conv(k, 4),
                                       g, drop_none(), tc ? nullptr : gt, cg[5 * k + 3], cg[5 * k + 4], cg[5 * k + 2],
                                       tc ? mut(gz.hi) : nullptr, tc ? lo_or_null(gz) : nullptr, M, H, st));
-            XGGM_TRY(proj_wgrad(tc, gz, pre_op, cg[5 * k + 1], M, H, H, st));
+            XGGM_TRY(proj_wgrad(tc, gz, pre_op, cg[5 * k + 1], M, H, H, acc, st));
             XGGM_TRY(proj_dgrad(tc, gz, wconv[k], gq, M, H, H, 0, st, gram ? &gq_op : nullptr));      // gpre
             // gadj += (1+eps) gpre h^T ; geps += <gpre h^T, adj>
             if (gram) {
@@ -458,8 +459,9 @@ int xggm_linear_bwd_input(const float* g, const float* w, float* ga, int M, int 
     return proj_dgrad(tc, go, wo, ga, M, N, K, accumulate, as_stream(s));
 }
 int xggm_linear_bwd_weight(const float* g, const float* a, float* gw, float* gbias, int M, int N,
-                           int K, void* work, xggm_stream_t s) {
+                           int K, int accumulate, void* work, xggm_stream_t s) {
     XGGM_REQUIRE(gw && M >= 0 && N > 0 && K > 0);
+    if (M == 0 && accumulate) return XGGM_OK;
     if (M == 0) {
         XGGM_CUDA_TRY(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)N * K, as_stream(s)));
         if (gbias) XGGM_CUDA_TRY(cudaMemsetAsync(gbias, 0, sizeof(float) * N, as_stream(s)));
@@ -478,8 +480,8 @@ int xggm_linear_bwd_weight(const float* g, const float* a, float* gw, float* gbi
         const long long n[2] = {(long long)M * N, (long long)M * K};
         XGGM_TRY(split_planes(src, hi, npass() == 3 ? lo : nullptr, n, 2, as_stream(s)));
     }
-    XGGM_TRY(proj_wgrad(tc, go, ao, gw, M, N, K, as_stream(s)));
-    if (gbias) XGGM_TRY(colsum(g, gbias, M, N, as_stream(s)));
+    XGGM_TRY(proj_wgrad(tc, go, ao, gw, M, N, K, accumulate, as_stream(s)));
+    if (gbias) XGGM_TRY(colsum(g, gbias, M, N, accumulate, as_stream(s)));
     return XGGM_OK;
 }
 
@@ -574,9 +576,9 @@ int xggm_gnn_bwd(int kind, const float* gout, const float* x, const float* adj,
                  const float* const* conv_params, const float* const* head_params,
                  const uint8_t* const* keeps, const xggm_philox_t* philox, float drop_p, const float* saved,
                  float* work, float* gx, float* gadj, float* const* conv_grads, float* const* head_grads,
-                 int B, int N, int H, int n_convs, xggm_stream_t s) {
+                 int accumulate_param_grads, int B, int N, int H, int n_convs, xggm_stream_t s) {
     return gnn_bwd(kind, gout, x, adj, conv_params, head_params, keeps, philox, drop_p, saved, work, gx, gadj,
-                   conv_grads, head_grads, B, N, H, n_convs, as_stream(s));
+                   conv_grads, head_grads, accumulate_param_grads, B, N, H, n_convs, as_stream(s));
 }
 
 int xggm_gat_attn_fwd(const float* h, const float* a, const float* adj, float* out, float* att,

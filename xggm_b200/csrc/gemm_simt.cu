@@ -223,8 +223,8 @@ __global__ void colsum_kernel(const float* __restrict__ g, float* __restrict__ o
     atomicAdd(&out[c], s);
 }
 
-int colsum(const float* g, float* out, int R, int C, cudaStream_t st) {
-    XGGM_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
+int colsum(const float* g, float* out, int R, int C, int accumulate, cudaStream_t st) {
+    if (!accumulate) XGGM_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
     if (R <= 0) return XGGM_OK;
     const int rpb = 64;
     dim3 grid(ceil_div(C, 128), ceil_div(R, rpb));

@@ -15,6 +15,22 @@ from ._lib import call, f32, ptr, ptr_table
 LN_EPS = 1e-5
 KIND = {"GCN": 0, "GIN": 1}
 
+# When a leaf parameter already owns a dense fp32 ``.grad`` buffer (e.g. a slice of
+# ``xggm_b200.ddp.FlatGrads``), the backward kernels accumulate into it directly and the autograd
+# Function returns None for that parameter: no temporary gradient, no extra add kernel.  Set to
+# False if something must observe parameter gradients through autograd hooks (torch DDP does).
+FUSE_GRAD_ACCUMULATION = True
+
+
+def _grad_target(p):
+    """The live .grad buffer of ``p`` if the kernels may accumulate into it, else None."""
+    if not FUSE_GRAD_ACCUMULATION or not getattr(p, "is_leaf", False) or not p.requires_grad:
+        return None
+    g = p.grad
+    if g is None or g.dtype != torch.float32 or g.device != p.device or g.shape != p.shape or not g.is_contiguous():
+        return None
+    return g
+
 
 def _u8(t):
     if t is None:
@@ -49,6 +65,7 @@ class _Linear(torch.autograd.Function):
         work = _linear_work(M, N, K, a.device)
         call("xggm_linear_fwd", ptr(a2), ptr(w), ptr(bias), ptr(r2), ptr(out), M, N, K, ptr(work))
         ctx.save_for_backward(a2, w)
+        ctx.bias_ref = bias   # only consulted for its .grad buffer in backward
         ctx.has_bias, ctx.has_resid, ctx.in_shape = bias is not None, resid is not None, a.shape
         return out.reshape(*a.shape[:-1], N)
 
@@ -65,9 +82,14 @@ class _Linear(torch.autograd.Function):
             call("xggm_linear_bwd_input", ptr(g2), ptr(w), ptr(ga), M, N, K, 0, ptr(work))
             ga = ga.reshape(ctx.in_shape)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            gw = torch.empty_like(w)
-            gb = torch.empty(N, device=w.device, dtype=torch.float32) if ctx.has_bias else None
-            call("xggm_linear_bwd_weight", ptr(g2), ptr(a2), ptr(gw), ptr(gb), M, N, K, ptr(work))
+            bias = ctx.bias_ref
+            tw, tb = _grad_target(w), (_grad_target(bias) if ctx.has_bias else None)
+            if tw is not None and (not ctx.has_bias or tb is not None):
+                call("xggm_linear_bwd_weight", ptr(g2), ptr(a2), ptr(tw), ptr(tb), M, N, K, 1, ptr(work))
+            else:
+                gw = torch.empty_like(w)
+                gb = torch.empty(N, device=w.device, dtype=torch.float32) if ctx.has_bias else None
+                call("xggm_linear_bwd_weight", ptr(g2), ptr(a2), ptr(gw), ptr(gb), M, N, K, 0, ptr(work))
         if ctx.has_resid and ctx.needs_input_grad[3]:
             gr = g
         return ga, gw, gb, gr
@@ -132,6 +154,7 @@ class _LayerNorm(torch.autograd.Function):
         rstd = torch.empty(M, device=u.device, dtype=torch.float32)
         call("xggm_layernorm_fwd", ptr(u2), ptr(gamma), ptr(beta), ptr(h), ptr(xhat), ptr(rstd), M, H, float(eps))
         ctx.save_for_backward(xhat, rstd, gamma)
+        ctx.beta_ref = beta
         return h.reshape(u.shape)
 
     @staticmethod
@@ -140,10 +163,12 @@ class _LayerNorm(torch.autograd.Function):
         M, H = xhat.shape
         g2 = f32(g).reshape(M, H)
         gu = torch.empty_like(xhat)
-        gg = torch.zeros(H, device=g.device, dtype=torch.float32)
-        gb = torch.zeros(H, device=g.device, dtype=torch.float32)
+        tg, tb = _grad_target(gamma), _grad_target(ctx.beta_ref)
+        fused = tg is not None and tb is not None
+        gg = tg if fused else torch.zeros(H, device=g.device, dtype=torch.float32)
+        gb = tb if fused else torch.zeros(H, device=g.device, dtype=torch.float32)
         call("xggm_layernorm_bwd", ptr(g2), ptr(xhat), ptr(rstd), ptr(gamma), ptr(gu), ptr(gg), ptr(gb), M, H)
-        return gu.reshape(g.shape), gg, gb, None
+        return gu.reshape(g.shape), (None if fused else gg), (None if fused else gb), None
 
 
 def layer_norm(u, gamma, beta, eps=LN_EPS):
@@ -163,6 +188,7 @@ class _GeluLnDrop(torch.autograd.Function):
         call("xggm_gelu_ln_drop_fwd", ptr(z2), ptr(gamma), ptr(beta), ptr(keep), float(scale), ptr(out),
              ptr(mean), ptr(rstd), M, H, float(eps), 0)
         ctx.save_for_backward(z2, mean, rstd, gamma, keep)
+        ctx.beta_ref = beta
         ctx.scale = float(scale)
         return out.reshape(z.shape)
 
@@ -172,11 +198,13 @@ class _GeluLnDrop(torch.autograd.Function):
         M, H = z2.shape
         g2 = f32(g).reshape(M, H)
         gz = torch.empty_like(z2)
-        gg = torch.zeros(H, device=g.device, dtype=torch.float32)
-        gb = torch.zeros(H, device=g.device, dtype=torch.float32)
+        tg, tb = _grad_target(gamma), _grad_target(ctx.beta_ref)
+        fused = tg is not None and tb is not None
+        gg = tg if fused else torch.zeros(H, device=g.device, dtype=torch.float32)
+        gb = tb if fused else torch.zeros(H, device=g.device, dtype=torch.float32)
         call("xggm_gelu_ln_drop_bwd", ptr(g2), ptr(z2), ptr(mean), ptr(rstd), ptr(gamma), ptr(keep), ctx.scale,
              ptr(gz), ptr(gg), ptr(gb), M, H)
-        return gz.reshape(g.shape), gg, gb, None, None, None
+        return gz.reshape(g.shape), (None if fused else gg), (None if fused else gb), None, None, None
 
 
 def gelu_ln_drop(z, gamma, beta, keep=None, drop_p=0.0, eps=LN_EPS):
@@ -268,11 +296,15 @@ class _GnnLayer(torch.autograd.Function):
                            dtype=torch.float32)
         gx = torch.empty_like(x)
         gadj = torch.empty_like(adj)
-        grads = [torch.empty_like(p) for p in params]
+        targets = [_grad_target(p) for p in params]
+        fused = all(t is not None for t in targets)
+        grads = targets if fused else [torch.empty_like(p) for p in params]
         kt = None if ctx.keeps is None else ptr_table(ctx.keeps)
         call("xggm_gnn_bwd", kind, ptr(g), ptr(x), ptr(adj), ptr_table(cp), ptr_table(hp), kt,
              _philox_arg(ctx.philox), drop_p, ptr(saved), ptr(work), ptr(gx), ptr(gadj), ptr_table(grads[:n_cp]),
-             ptr_table(grads[n_cp:]), B, N, H, n_convs)
+             ptr_table(grads[n_cp:]), int(fused), B, N, H, n_convs)
+        if fused:
+            grads = [None] * len(params)
         return (None, None, None, None, None, gx, gadj, *grads)
 
 
