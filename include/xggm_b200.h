@@ -46,6 +46,10 @@ unsigned long long xggm_launch_count(void);
  * sums their algorithmic FLOPs (2*M*N*K).  Enabling (or disabling) clears the records. */
 int xggm_prof_enable(int on);
 int xggm_prof_read(double* total_ms, long long* launches, double* flops);
+/* Kernel-tuning aid: while dev_buf (>= 32 uint64 of DEVICE memory) is set, CTA 0 of every tcgen05
+ * GEMM launch records %globaltimer at its pipeline milestones (tools/gemm_timeline.py decodes them).
+ * NULL switches it off. */
+int xggm_debug_timeline(unsigned long long* dev_buf);
 /* The library links its own (static) CUDA runtime: make `device` current for the calling
  * thread before enqueueing work on one of its streams (cheap; call it per entry). */
 int xggm_set_device(int device);

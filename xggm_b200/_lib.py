@@ -21,6 +21,7 @@ SIGNATURES = {
     "xggm_launch_count": [],
     "xggm_prof_enable": [_i],
     "xggm_prof_read": [_vp, _vp, _vp],
+    "xggm_debug_timeline": [_vp],
     "xggm_set_device": [_i],
     "xggm_device_check": [_i],
     "xggm_set_precision": [_i],

@@ -25,6 +25,9 @@ int scale_accum(const float* S, float* out, long long n, float alpha0, const flo
                 const float* dot_ref, float* dot_out, cudaStream_t st);
 int split_planes(const float* const* src, __nv_bfloat16* const* hi, __nv_bfloat16* const* lo, const long long* n,
                  int count, cudaStream_t st);
+int split_planes_t(const float* const* src, __nv_bfloat16* const* hi, __nv_bfloat16* const* lo, int R, int C,
+                   int count, cudaStream_t st);
+void gemm_tc_set_debug(unsigned long long* dev_buf);
 int gemm_prof_enable(int on);
 int gemm_prof_read(double* total_ms, long long* launches, double* flops);
 int layernorm_fwd(const float*, const float*, const float*, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, float, cudaStream_t);
@@ -104,10 +107,11 @@ static int proj_fwd(bool tc, const Operand& a, const Operand& w, const float* bi
     return gemm_simt(0, a.f32, w.f32, bias, resid, out, M, N, K, 0, st);
 }
 // ga[M,K] (+)= g[M,N] w[N,K]
-// ga_planes (optional, tensor-core engine only): also emit ga as bf16 operand planes
+// Tensor-core engine: `w` carries the planes of W^T ([K,N], contraction N contiguous) so that dgrad is
+// the same K-major x K-major product as the forward pass.  ga_planes (optional): also emit ga as planes.
 static int proj_dgrad(bool tc, const Operand& g, const Operand& w, float* ga, int M, int N, int K,
                       int accumulate, cudaStream_t st, const Operand* ga_planes = nullptr) {
-    if (tc) return gemm_tc(false, true, g.hi, g.lo, w.hi, w.lo, nullptr, nullptr, ga,
+    if (tc) return gemm_tc(false, false, g.hi, g.lo, w.hi, w.lo, nullptr, nullptr, ga,
                            ga_planes ? const_cast<bf16*>(ga_planes->hi) : nullptr,
                            ga_planes ? const_cast<bf16*>(ga_planes->lo) : nullptr, M, K, N, accumulate, 0, npass(), st);
     return gemm_simt(1, g.f32, w.f32, nullptr, nullptr, ga, M, K, N, accumulate, st);
@@ -154,8 +158,10 @@ struct GnnLayout {
 };
 
 // weight planes for one layer live at the tail of the work buffer: conv k -> slot k, head j -> slot nc + j
+// transposed = true (backward pass): the planes hold W^T, the layout proj_dgrad wants.
 static int split_weights(int kind, const float* const* cp, const float* const* hp, float* wregion,
-                         const GnnLayout& L, int H, Operand* wconv, Operand* whead, bool tc, cudaStream_t st) {
+                         const GnnLayout& L, int H, Operand* wconv, Operand* whead, bool tc, bool transposed,
+                         cudaStream_t st) {
     const int nc = L.n_convs;
     const float* src[16];
     bf16* hi[16];
@@ -169,6 +175,13 @@ static int split_weights(int kind, const float* const* cp, const float* const* h
     for (int j = 0; j <= nc; ++j)
         whead[j] = planes_at(hp[4 * j], wregion + (long long)(nc + j) * L.HH, (long long)H * H);
     if (!tc) return XGGM_OK;
+    if (transposed) {
+        for (int i = 0; i < 2 * nc + 1; ++i) {
+            const Operand& o = i < nc ? wconv[i] : whead[i - nc];
+            src[i] = o.f32; hi[i] = const_cast<bf16*>(o.hi); lo[i] = const_cast<bf16*>(o.lo);
+        }
+        return split_planes_t(src, hi, npass() == 3 ? lo : nullptr, H, H, 2 * nc + 1, st);
+    }
     for (int i = 0; i < 2 * nc + 1; ++i) {
         const Operand& o = i < nc ? wconv[i] : whead[i - nc];
         src[cnt] = o.f32; hi[cnt] = const_cast<bf16*>(o.hi); lo[cnt] = const_cast<bf16*>(o.lo);
@@ -202,7 +215,7 @@ static int gnn_fwd(int kind, const float* x, const float* adj, const float* cons
     const bool tc = use_tc(M, H, H);
     const long long MHn = (long long)M * H;
     Operand wconv[MAX_CONVS], whead[MAX_CONVS + 1];
-    XGGM_TRY(split_weights(kind, cp, hp, work + L.MH, L, H, wconv, whead, tc, st));
+    XGGM_TRY(split_weights(kind, cp, hp, work + L.MH, L, H, wconv, whead, tc, false, st));
     Operand hop = planes_at(x, saved + L.xplanes, MHn);   // current node features as a GEMM operand
     if (tc) XGGM_TRY(split_one(hop, MHn, st));
     Operand hops[MAX_CONVS + 1];
@@ -280,7 +293,7 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
     float* gt = work + 2 * MH;  // gz / gu
     float* gq = work + 3 * MH;
     Operand wconv[MAX_CONVS], whead[MAX_CONVS + 1];
-    XGGM_TRY(split_weights(kind, cp, hp, work + 6 * MH, L, H, wconv, whead, tc, st));
+    XGGM_TRY(split_weights(kind, cp, hp, work + 6 * MH, L, H, wconv, whead, tc, true, st));
     XGGM_CUDA_TRY(cudaMemsetAsync(gadj, 0, sizeof(float) * (size_t)B * N * N, st));
     // per-graph products gq h^T go through the tensor-core Gram kernel when it can address them
     const bool gram = tc && gram_tc_supported(N, H);
@@ -389,6 +402,10 @@ const char* xggm_strerror(int code) {
 
 const char* xggm_last_cuda_error(void) { return g_cuda_err; }
 int xggm_prof_enable(int on) { return gemm_prof_enable(on); }
+int xggm_debug_timeline(unsigned long long* dev_buf) {
+    gemm_tc_set_debug(dev_buf);
+    return XGGM_OK;
+}
 int xggm_prof_read(double* total_ms, long long* launches, double* flops) {
     XGGM_REQUIRE(total_ms && launches && flops);
     return gemm_prof_read(total_ms, launches, flops);
@@ -450,11 +467,11 @@ int xggm_linear_bwd_input(const float* g, const float* w, float* ga, int M, int 
     if (tc) {
         wo = planes_at(w, wk + al4((long long)M * K), (long long)N * K);
         go = planes_at(g, wk + al4((long long)M * K) + al4((long long)N * K), (long long)M * N);
-        const float* src[2] = {g, w};
-        bf16* hi[2] = {const_cast<bf16*>(go.hi), const_cast<bf16*>(wo.hi)};
-        bf16* lo[2] = {const_cast<bf16*>(go.lo), const_cast<bf16*>(wo.lo)};
-        const long long n[2] = {(long long)M * N, (long long)N * K};
-        XGGM_TRY(split_planes(src, hi, npass() == 3 ? lo : nullptr, n, 2, as_stream(s)));
+        XGGM_TRY(split_one(go, (long long)M * N, as_stream(s)));
+        const float* src[1] = {w};
+        bf16* hi[1] = {const_cast<bf16*>(wo.hi)};
+        bf16* lo[1] = {const_cast<bf16*>(wo.lo)};
+        XGGM_TRY(split_planes_t(src, hi, npass() == 3 ? lo : nullptr, N, K, 1, as_stream(s)));   // planes of w^T [K,N]
     }
     return proj_dgrad(tc, go, wo, ga, M, N, K, accumulate, as_stream(s));
 }

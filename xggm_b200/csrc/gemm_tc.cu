@@ -14,14 +14,15 @@
 //   dgrad    ga  = g w   : A = g  [M,N'] K-major,   B = w [N',K'] MN-major
 //   wgrad    gw  = g^T a : A = g  [rows,N] MN-major, B = a [rows,K] MN-major  (+ split-K)
 //
-// Kernel shape: persistent CTAs (one per SM), 192 threads:
+// Kernel shape: persistent CTAs (one per SM), 320 threads:
 //   warp 0      TMA producer   (cp.async.bulk.tensor, SWIZZLE_128B, mbarrier complete_tx)
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (128 x BN x 16 per instruction)
-//   warps 2..5  epilogue: tcgen05.ld 32x32b -> smem transpose -> coalesced fp32 stores
+//   warps 2..9  epilogue (two per TMEM lane quarter): tcgen05.ld 32x32b -> smem transpose -> coalesced fp32 stores
 // Two accumulator buffers in TMEM (2 x BN columns) let the epilogue of tile i overlap the
 // main loop of tile i+1.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -31,7 +32,8 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 64;   // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UK = 16;   // K of one tcgen05.mma for 16-bit operands
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;   // two per TMEM lane quarter: a lone warp's dependent-issue rate bounds the epilogue
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int EPI_PITCH = 33;
 constexpr int SMEM_LIMIT = 227 * 1024;
 
@@ -75,12 +77,41 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// ---- cluster helpers (CTA pairs, cta_group::2) --------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a local shared address) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
 // ---- TMA -----------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
                                             int c_inner, int c_outer) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
+        : "memory");
+}
+// CTA-pair variant: the data lands in this CTA's smem, the bytes are counted on the barrier at
+// `bar_cluster_addr` (the pair leader's full barrier)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr,
+                                                 int c_inner, int c_outer) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_cluster_addr), "r"(c_inner), "r"(c_outer)
         : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
@@ -97,6 +128,15 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -106,6 +146,23 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 256 x N x 16 across a CTA pair: issued by the leader, A rows / B columns / D rows split over both CTAs
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// pair variant of the commit: arrives on the barrier at the same smem offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"((uint16_t)3)
         : "memory");
 }
 // arrives on `bar` once every previously issued tcgen05.mma of this thread has completed
@@ -139,9 +196,9 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_byte
     return d;
 }
 // Instruction descriptor: bf16 x bf16 -> fp32, M = 128, N = BN, per-operand major-ness.
-__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn, bool b_mn) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void split1(float x, __nv_bfloat16& hi, __nv_bfloat16& lo);
@@ -173,15 +230,18 @@ struct Params {
     // tensors, tile t covers the gram_g complete graphs starting at row t*gram_g*gram_n, and only the
     // gram_n x gram_n diagonal blocks  S[b] = P[b] Q[b]^T  are written to C[B][gram_n][gram_n].
     int gram_n, gram_g, gram_b;
+    unsigned long long* dbg;   // optional device buffer: CTA 0 records a globaltimer timeline (tools/gemm_timeline.py)
 };
 
-template <int BN, int NPASS>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cta_group::2) per 256 x BN tile; each CTA
+// stages its own 128 A rows and HALF of the B tile, so a stage is smaller and the ring deeper.
+template <int BN, int NPASS, int CG = 1>
 struct Cfg {
     static constexpr int A_TILE = BM * BK * 2;
-    static constexpr int B_TILE = BN * BK * 2;
+    static constexpr int B_TILE = (BN / CG) * BK * 2;
     static constexpr int NPLANE = NPASS == 3 ? 2 : 1;
     static constexpr int STAGE_BYTES = NPLANE * (A_TILE + B_TILE);
-    static constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;
+    static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4;
     static constexpr int FIXED = EPI_BYTES + 256 + 1024;  // + barriers + alignment slack
     static constexpr int STAGES_RAW = (SMEM_LIMIT - FIXED) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
@@ -190,14 +250,16 @@ struct Cfg {
     static_assert(STAGES >= 2, "need at least a double-buffered operand ring");
 };
 
-template <int BN, int NPASS, bool A_MN, bool B_MN>
+template <int BN, int NPASS, bool A_MN, bool B_MN, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                const Params p) {
-    using C = Cfg<BN, NPASS>;
+    using C = Cfg<BN, NPASS, CG>;
+    static_assert(CG == 1 || (!A_MN && !B_MN), "the CTA-pair kernel takes K-major operands");
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment for SWIZZLE_128B, computed as an offset so the pointer keeps its shared-space provenance
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* stage_base = smem;
     float* epi = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::EPI_BYTES);
@@ -209,6 +271,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = p.tiles_m * p.tiles_n * p.splits;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;       // 0 = pair leader (issues the MMAs)
+    const int worker = blockIdx.x / CG, num_workers = gridDim.x / CG;  // a worker = a CTA or a CTA pair
+    const bool trace = p.dbg != nullptr && blockIdx.x == 0;
+#define XGGM_TRACE(slot) do { if (trace) p.dbg[slot] = global_ns(); } while (0)
+    if (threadIdx.x == 0) XGGM_TRACE(0);
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&map_a_hi);
@@ -223,29 +290,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&acc_full[a], 1);
-            mbar_init(&acc_empty[a], 128);
+            mbar_init(&acc_empty[a], EPI_WARPS * CG);   // one elected arrival per epilogue warp (of both CTAs)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    if (warp == 1) {
+        if (CG == 2) tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
+        else tmem_alloc(tmem_slot, C::TMEM_COLS);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();   // the peer's barriers must exist before anything signals them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) XGGM_TRACE(1);
 
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = worker; tile < num_tiles; tile += num_workers) {
                 const int sp = tile % p.splits;
                 const int mn = tile / p.splits;
-                int m0 = (mn / p.tiles_n) * BM, n0 = (mn % p.tiles_n) * BN;
+                int m0 = (mn / p.tiles_n) * (BM * CG) + (int)rank * BM, n0 = (mn % p.tiles_n) * BN;
                 if (p.gram_n > 0) m0 = n0 = mn * p.gram_g * p.gram_n;
                 const int kb0 = sp * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
+                    if (CG == 2) {
+                        // pair: both CTAs' bytes are counted on the leader's barrier
+                        const uint32_t lead_full = map_to_cta(&full[stage], 0);
+                        if (rank == 0) mbar_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
+                        uint8_t* sa = stage_base + stage * C::STAGE_BYTES;
+                        uint8_t* sb = sa + C::NPLANE * C::A_TILE;
+                        const int k0 = kb * BK;
+#pragma unroll
+                        for (int pl = 0; pl < C::NPLANE; ++pl) {
+                            tma_load_2d_pair(sa + pl * C::A_TILE, pl == 0 ? &map_a_hi : &map_a_lo, lead_full, k0, m0);
+                            tma_load_2d_pair(sb + pl * C::B_TILE, pl == 0 ? &map_b_hi : &map_b_lo, lead_full, k0,
+                                             n0 + (int)rank * (BN / 2));
+                        }
+                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_expect_tx(&full[stage], C::STAGE_BYTES);
                     uint8_t* sa = stage_base + stage * C::STAGE_BYTES;
                     uint8_t* sb = sa + C::NPLANE * C::A_TILE;
@@ -275,8 +363,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = make_idesc(BM * CG, BN, A_MN, B_MN);
             constexpr uint32_t a_lbo = A_MN ? BK * 128 : 16, b_lbo = B_MN ? BK * 128 : 16;
             constexpr uint32_t a_kstep = A_MN ? UK * 128 : UK * 2;  // bytes per 16-wide k-step
             constexpr uint32_t b_kstep = B_MN ? UK * 128 : UK * 2;
@@ -284,7 +372,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = worker; tile < num_tiles; tile += num_workers) {
                 const int sp = tile % p.splits;
                 const int kb0 = sp * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
                 mbar_wait(&acc_empty[acc], acc_phase ^ 1);
@@ -293,6 +381,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 uint32_t first = 1;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full[stage], phase);
+                    if (kb == kb0) XGGM_TRACE(2 + 4 * min(tile / num_workers, 3));      // first operands of the tile landed
                     tc_fence_after();
                     const uint32_t sa = smem_u32(stage_base + stage * C::STAGE_BYTES);
                     const uint32_t sb = sa + C::NPLANE * C::A_TILE;
@@ -305,15 +394,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         const uint64_t bdesc0 = make_sdesc(sb + bpl * C::B_TILE, b_lbo, 1024);
 #pragma unroll
                         for (int k = 0; k < BK / UK; ++k) {
-                            umma_bf16(d_tmem, adesc0 + (uint64_t)((k * a_kstep) >> 4),
-                                      bdesc0 + (uint64_t)((k * b_kstep) >> 4), idesc, first ? 0u : 1u);
+                            if (CG == 2)
+                                umma_bf16_pair(d_tmem, adesc0 + (uint64_t)((k * a_kstep) >> 4),
+                                               bdesc0 + (uint64_t)((k * b_kstep) >> 4), idesc, first ? 0u : 1u);
+                            else
+                                umma_bf16(d_tmem, adesc0 + (uint64_t)((k * a_kstep) >> 4),
+                                          bdesc0 + (uint64_t)((k * b_kstep) >> 4), idesc, first ? 0u : 1u);
                             first = 0;
                         }
                     }
-                    umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
+                    if (CG == 2) umma_commit_pair(&empty[stage]);   // frees the slot in both CTAs
+                    else umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&acc_full[acc]);     // accumulator complete -> epilogue
+                if (CG == 2) umma_commit_pair(&acc_full[acc]);
+                else umma_commit(&acc_full[acc]);     // accumulator complete -> epilogue
+                XGGM_TRACE(3 + 4 * min(tile / num_workers, 3));                          // all MMAs of the tile issued
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
@@ -321,15 +417,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     } else {
         // ================================ epilogue ====================================
         const int q = warp & 3;  // TMEM lane quarter this warp may read: lanes 32q .. 32q+31
+        const int csub = (warp - 2) >> 2;   // which of the quarter's EPI_WARPS/4 warps: takes column chunks c % (EPI_WARPS/4) == csub
         float* st = epi + (warp - 2) * 32 * EPI_PITCH;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = worker; tile < num_tiles; tile += num_workers) {
             const int mn = tile / p.splits;
             const int sp = tile % p.splits;
-            const int m0 = (mn / p.tiles_n) * BM, n0 = (mn % p.tiles_n) * BN;
+            const int m0 = (mn / p.tiles_n) * (BM * CG) + (int)rank * BM, n0 = (mn % p.tiles_n) * BN;
             const bool lead = (sp == 0);  // bias / residual are added by the first split only
             mbar_wait(&acc_full[acc], acc_phase);
+            if (warp == 2 && lane == 0) XGGM_TRACE(4 + 4 * min(tile / num_workers, 3)); // accumulator ready
             tc_fence_after();
             if (p.gram_n > 0) {
                 // thread = accumulator row r of the tile; keep the columns of r's own graph only
@@ -342,7 +440,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 const int hi_col = min(span, ((q * 32 + 31) / gn + 1) * gn);
                 float* orow = p.C + (b * gn + (r - gl * gn)) * gn - gl * gn;  // orow[col] = S[b][i][col - gl*gn]
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = csub; c < BN / 32; c += EPI_WARPS / 4) {
                     if (c * 32 + 32 <= lo_col || c * 32 >= hi_col) continue;  // warp-uniform
                     uint32_t v[32];
                     tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
@@ -355,7 +453,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(&acc_empty[acc]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[acc]);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
                 continue;
@@ -366,7 +465,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             // float4 domain: lane -> (row = 4*it + lane/8, 4 columns at 4*(lane%8))
             const int rsub = lane >> 3, c4 = (lane & 7) * 4;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = csub; c < BN / 32; c += EPI_WARPS / 4) {
                 const int ncol0 = n0 + c * 32;
                 if (ncol0 >= p.N || mrow0 >= p.M) break;  // warp-uniform
                 // (1) issue this chunk's bias / residual / accumulate loads first: their latency hides
@@ -429,18 +528,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 __syncwarp();
             }
             tc_fence_before();
-            mbar_arrive(&acc_empty[acc]);
+            __syncwarp();
+            if (warp == 2 && lane == 0) XGGM_TRACE(5 + 4 * min(tile / num_workers, 3)); // epilogue of the tile done
+            if (lane == 0) {   // hand the accumulator buffer back to the (pair leader's) MMA thread
+                if (CG == 2 && rank != 0) mbar_arrive_cluster(map_to_cta(&acc_empty[acc], 0));
+                else mbar_arrive(&acc_empty[acc]);
+            }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();   // neither CTA may free TMEM / exit while the pair's MMAs or signals are in flight
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, C::TMEM_COLS);
+        if (CG == 2) tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+        else tmem_dealloc(tmem_base, C::TMEM_COLS);
     }
+    if (threadIdx.x == 0) XGGM_TRACE(18);
+#undef XGGM_TRACE
 }
 
 // ---- fp32 -> bf16 hi/lo planes -----------------------------------------------------------------
@@ -489,6 +597,36 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const SplitJobs jobs)
     }
 }
 
+// transposed split: src [R,C] fp32 -> hi/lo [C,R] bf16 (weights only: dgrad reads W^T K-major)
+struct SplitTJob {
+    const float* src;
+    __nv_bfloat16* hi;
+    __nv_bfloat16* lo;
+};
+struct SplitTJobs {
+    SplitTJob j[MAX_SPLIT_JOBS];
+};
+__global__ void __launch_bounds__(256) split_planes_t_kernel(const SplitTJobs jobs, int R, int C) {
+    __shared__ float tile[32][33];
+    const SplitTJob job = jobs.j[blockIdx.z];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int i = ty; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + tx;
+        tile[i][tx] = (r < R && c < C) ? job.src[(size_t)r * C + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + tx;   // output row = source column
+        if (c < C && r < R) {
+            __nv_bfloat16 h, l;
+            split1(tile[tx][i], h, l);
+            job.hi[(size_t)c * R + r] = h;
+            if (job.lo) job.lo[(size_t)c * R + r] = l;
+        }
+    }
+}
+
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------------------
@@ -528,6 +666,8 @@ struct ProfScopeTc;  // (per-launch timing lives in gemm_simt.cu: gemm_prof_begi
 void* gemm_prof_begin(double flops, cudaStream_t st);
 void gemm_prof_end(void* rec, cudaStream_t st);
 
+static unsigned long long* g_tc_dbg = nullptr;   // see xggm_debug_timeline()
+void gemm_tc_set_debug(unsigned long long* dev_buf) { g_tc_dbg = dev_buf; }
 static int g_num_sms = 0;
 static int num_sms() {
     if (g_num_sms == 0) {
@@ -539,19 +679,45 @@ static int num_sms() {
     return g_num_sms;
 }
 
-template <int BN, int NPASS, bool A_MN, bool B_MN>
+template <int BN, int NPASS, bool A_MN, bool B_MN, int CG = 1>
 static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                      const tc::Params& p, int grid, cudaStream_t st) {
-    using C = tc::Cfg<BN, NPASS>;
+    using C = tc::Cfg<BN, NPASS, CG>;
     static bool attr_set = false;
-    auto kern = tc::gemm_tc_kernel<BN, NPASS, A_MN, B_MN>;
+    auto kern = tc::gemm_tc_kernel<BN, NPASS, A_MN, B_MN, CG>;
     if (!attr_set) {
         XGGM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
-    kern<<<grid, tc::NUM_THREADS, C::SMEM, st>>>(ah, al, bh, bl, p);
+    if (CG == 1) {
+        kern<<<grid, tc::NUM_THREADS, C::SMEM, st>>>(ah, al, bh, bl, p);
+    } else {  // CTA pairs: clusters of 2 (same TPC) so cta_group::2 MMAs can span both SMs
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(tc::NUM_THREADS);
+        cfg.dynamicSmemBytes = C::SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        XGGM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ah, al, bh, bl, p));
+    }
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
+}
+
+// CTA-pair engine on/off (XGGM_TC_PAIR=0 keeps every product on the single-CTA kernel; for A/B runs)
+static bool pair_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("XGGM_TC_PAIR");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on != 0;
 }
 
 template <int BN, int NPASS>
@@ -575,8 +741,41 @@ int gemm_tc(bool a_mn, bool b_mn, const __nv_bfloat16* a_hi, const __nv_bfloat16
     if (M <= 0 || N <= 0 || K <= 0) return XGGM_OK;
     XGGM_REQUIRE(a_hi && b_hi && C && (npass == 1 || (npass == 3 && a_lo && b_lo)));
     const int sms = num_sms();
-    const int tiles_m = ceil_div(M, tc::BM);
     const int num_kb = ceil_div(K, tc::BK);
+    if (!a_mn && !b_mn && M > tc::BM && pair_enabled() && sms % 2 == 0) {
+        // K-major x K-major (forward, and dgrad against transposed weight planes): CTA-pair kernel,
+        // 256 x 192 tiles, cta_group::2 MMAs, each CTA stages half of the B tile.
+        constexpr int PBN = 192;
+        CUtensorMap ah, al, bh, bl;
+        XGGM_TRY(make_map(&ah, a_hi, M, K, tc::BM));
+        XGGM_TRY(make_map(&bh, b_hi, N, K, PBN / 2));
+        if (npass == 3) {
+            XGGM_TRY(make_map(&al, a_lo, M, K, tc::BM));
+            XGGM_TRY(make_map(&bl, b_lo, N, K, PBN / 2));
+        } else {
+            al = ah;
+            bl = bh;
+        }
+        tc::Params p;
+        p.M = M; p.N = N; p.num_kb = num_kb;
+        p.tiles_m = ceil_div(M, 2 * tc::BM); p.tiles_n = ceil_div(N, PBN); p.splits = 1; p.kb_per_split = num_kb;
+        p.bias = bias; p.resid = resid; p.C = C; p.ldc = N;
+        p.accumulate = accumulate; p.atomic = 0;
+        p.vec4 = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(resid) |
+                                   reinterpret_cast<uintptr_t>(bias)) & 15) == 0;
+        p.c_hi = c_hi; p.c_lo = npass == 3 ? c_lo : nullptr;
+        p.gram_n = p.gram_g = p.gram_b = 0;
+        p.dbg = g_tc_dbg;
+        if (c_hi && (!p.vec4 || (reinterpret_cast<uintptr_t>(c_hi) & 7) || (reinterpret_cast<uintptr_t>(c_lo) & 7)))
+            return XGGM_ERR_ARG;
+        const int grid = 2 * min(sms / 2, p.tiles_m * p.tiles_n);
+        void* prof = gemm_prof_begin(2.0 * M * N * K, st);
+        const int rc = npass == 3 ? launch_tc<PBN, 3, false, false, 2>(ah, al, bh, bl, p, grid, st)
+                                  : launch_tc<PBN, 1, false, false, 2>(ah, al, bh, bl, p, grid, st);
+        gemm_prof_end(prof, st);
+        return rc;
+    }
+    const int tiles_m = ceil_div(M, tc::BM);
     // tile width: fewest "waves x width"; ties go to the wider tile (less A re-read)
     int bn = 128;
     long long best = -1;
@@ -622,6 +821,7 @@ int gemm_tc(bool a_mn, bool b_mn, const __nv_bfloat16* a_hi, const __nv_bfloat16
                                reinterpret_cast<uintptr_t>(bias)) & 15) == 0;
     p.c_hi = c_hi; p.c_lo = npass == 3 ? c_lo : nullptr;
     p.gram_n = p.gram_g = p.gram_b = 0;
+    p.dbg = g_tc_dbg;
     if (c_hi && (!p.vec4 || p.atomic || (reinterpret_cast<uintptr_t>(c_hi) & 7) || (reinterpret_cast<uintptr_t>(c_lo) & 7)))
         return XGGM_ERR_ARG;  // plane emission needs the float4 epilogue
     if (splits > 1 && !accumulate)
@@ -667,12 +867,34 @@ int gram_tc(const __nv_bfloat16* p_hi, const __nv_bfloat16* p_lo, const __nv_bfl
     p.bias = nullptr; p.resid = nullptr; p.C = S; p.ldc = N;
     p.accumulate = 0; p.atomic = 0; p.vec4 = 0; p.c_hi = nullptr; p.c_lo = nullptr;
     p.gram_n = N; p.gram_g = G; p.gram_b = B;
+    p.dbg = nullptr;
     const int grid = min(num_sms(), p.tiles_m);
     void* prof = gemm_prof_begin(2.0 * B * N * N * H, st);
     const int rc = npass == 3 ? launch_tc<128, 3, false, false>(ah, al, bh, bl, p, grid, st)
                               : launch_tc<128, 1, false, false>(ah, al, bh, bl, p, grid, st);
     gemm_prof_end(prof, st);
     return rc;
+}
+
+// Transposed split of `count` [R,C] fp32 matrices into [C,R] bf16 planes (one launch per 8 matrices).
+int split_planes_t(const float* const* src, __nv_bfloat16* const* hi, __nv_bfloat16* const* lo, int R, int C,
+                   int count, cudaStream_t st) {
+    int done = 0;
+    while (done < count) {
+        tc::SplitTJobs jobs;
+        const int n = min(tc::MAX_SPLIT_JOBS, count - done);
+        for (int i = 0; i < n; ++i) {
+            jobs.j[i].src = src[done + i];
+            jobs.j[i].hi = hi[done + i];
+            jobs.j[i].lo = lo ? lo[done + i] : nullptr;
+        }
+        if (R > 0 && C > 0) {
+            tc::split_planes_t_kernel<<<dim3(ceil_div(C, 32), ceil_div(R, 32), n), 256, 0, st>>>(jobs, R, C);
+            XGGM_LAUNCH_CHECK();
+        }
+        done += n;
+    }
+    return XGGM_OK;
 }
 
 // Split up to MAX_SPLIT_JOBS fp32 arrays into bf16 hi (+ lo) planes with one launch.
