@@ -492,3 +492,41 @@ def test_fused_grad_accumulation_matches_autograd_accumulation():
         out[fused] = grads.flat.clone()
     assert float(out[False].abs().max()) > 0
     assert rel_l2(out[True].cpu(), out[False].cpu()) < 2e-6
+
+
+@pytest.mark.parametrize("gnn", ["GCN", "GIN"])
+def test_bf16_engine_within_bf16_budget(gnn):
+    """Single-pass bf16 tensor-core engine (BASELINE cfg 3) vs the fp64 oracle: 2e-2 on activations
+    and gradients (north_star tolerance for bf16)."""
+    import xggm_b200 as X
+    from xggm_b200.functional import inject_keep_masks
+    B, N, H = 6, 36, 768
+    p = O.make_params(91, gnn, H, 2, N, heads=False)
+    cls = {"GCN": X.GCNGenerator, "GIN": X.GINGenerator}[gnn]
+    mod = _load_params(cls(H, 2), p, "generator.").to(dev()).train()
+    visn, _, adj_true = O.make_inputs(92, B, N, H)
+    adj = O.strip_diag(adj_true)
+    nh = {"GCN": 3, "GIN": 2}[gnn]
+    keeps = O.make_keeps(93, 2, nh, (B, N, H))
+    x = visn.clone().to(dev()).requires_grad_(True)
+    a = adj.clone().to(dev()).requires_grad_(True)
+    X.set_precision("bf16")
+    try:
+        with inject_keep_masks([m for layer in keeps for m in layer]):
+            xo, ao = mod(x, a)
+        g = torch.Generator().manual_seed(94)
+        cx, ca = torch.randn(B, N, H, generator=g), torch.randn(B, N, N, generator=g)
+        ((xo * cx.to(dev())).sum() + (ao * ca.to(dev())).sum()).backward()
+    finally:
+        X.set_precision("fp32")
+    p64 = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    x64, a64 = visn.double().requires_grad_(True), adj.double().requires_grad_(True)
+    fn = O.gcn_generator if gnn == "GCN" else O.gin_generator
+    xr, ar = fn(x64, a64, p64, 2, keeps, pre="generator.")
+    ((xr * cx.double()).sum() + (ar * ca.double()).sum()).backward()
+    BF16_TOL = 2e-2
+    assert rel_l2(xo.detach().cpu(), xr.detach()) < BF16_TOL
+    assert rel_l2(ao.detach().cpu(), ar.detach()) < BF16_TOL
+    assert float(torch.diagonal(ao, dim1=1, dim2=2).abs().max()) == 0.0   # masks stay bit-exact
+    assert rel_l2(x.grad.cpu(), x64.grad) < 2 * BF16_TOL
+    assert rel_l2(a.grad.cpu(), a64.grad) < 2 * BF16_TOL

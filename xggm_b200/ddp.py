@@ -30,11 +30,15 @@ class FlatGrads:
         if not self.params:
             raise ValueError("no trainable parameters")
         p0 = self.params[0]
-        self.flat = torch.zeros(sum(p.numel() for p in self.params), device=p0.device, dtype=p0.dtype)
-        off = 0
+        # every slice starts on a 128-byte boundary: the kernels' vector (float4) paths need 16-byte alignment
+        align = 128 // p0.element_size()
+        offs, off = [], 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+            offs.append(off)
+            off += (p.numel() + align - 1) // align * align
+        self.flat = torch.zeros(off, device=p0.device, dtype=p0.dtype)
+        for p, o in zip(self.params, offs):
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
 
     def zero_(self):
         self.flat.zero_()
