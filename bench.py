@@ -34,9 +34,12 @@ sys.path.insert(0, ROOT)
 B_PER_GPU, N_NODES, HID, N_LAYERS, SIGMA, NUM_ANS, GNN = 256, 36, 768, 2, 1.0, 2274, "GCN"
 CPU_SAMPLE_B = 32
 METRIC = "xggm_graph_block_train_samples_per_sec"
-# dram bytes (read+write) per launch of the dominant kernel from the committed `ncu --set full` capture
-# (profiles/); None until a capture of the current kernel exists
-TRAFFIC_NCU = None
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (forward projection,
+# M=9216 N=K=768, CTA-pair kernel) from the committed `ncu --set full` capture
+# profiles/r01d_ncu_gemm_tc_pair_fwd.txt: 30.72 MB read + 0.91 MB written back (the fp32 output stays in
+# the 126 MB L2 at kernel end).  Algorithmic bytes of that launch: 28.3 MB A planes + 2.4 MB W planes +
+# 28.3 MB C = 59.0 MB.
+TRAFFIC_NCU = 30716928 + 909568
 
 
 def algorithmic_flops_per_sample(N=N_NODES, H=HID, L=N_LAYERS):
@@ -202,7 +205,10 @@ def run_gpu(args):
 
     def e2e_step():
         if graphed is not None:
-            l = graphed(visn_h, xp_h, adj_h)      # H2D into the static buffers, then one replay
+            # every step: this step's inputs were put on the wire (pinned host -> device staging, side
+            # stream) while the previous step computed; move them in, replay, start the next step's H2D
+            l = graphed.run_prefetched()
+            graphed.prefetch(visn_h, xp_h, adj_h)
         else:
             l = compute(visn_h.to(dev, non_blocking=True), xp_h.to(dev, non_blocking=True),
                         adj_h.to(dev, non_blocking=True))
@@ -228,6 +234,8 @@ def run_gpu(args):
             dist.barrier()
         return ms
 
+    if graphed is not None:
+        graphed.prefetch(visn_h, xp_h, adj_h)
     for _ in range(max(args.warmup, 3)):
         resident_step()
         e2e_step()

@@ -71,56 +71,69 @@ adj_apply_kernel(const float* __restrict__ adj, const float* __restrict__ x,
 
 // obj36 fast path: N = 36 exactly.  grid (ceil(H/256), B), 128 threads, each thread owns two
 // adjacent feature columns and keeps their 36 node values in registers (one coalesced 8-byte
-// load per node row); adjacency coefficients come from smem as broadcast LDS.128, so the inner
-// loop is FMA-bound (8 FMAs per LDS).  Fully unrolled: 36 x 36 x 2 FMAs per thread.
+// load per node row).  The coefficient matrix  C = alpha * (adj | adj^T) + self_w * I  is built
+// once in shared memory, so the body is a plain C @ x: two output rows per iteration (four
+// independent FMA chains), coefficients fetched as broadcast LDS.128 (8 FMAs per LDS).  The row
+// loop is NOT unrolled: the body stays inside the instruction cache and ~100 registers allow five
+// CTAs per SM.
 template <bool TRANS>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 5)
 adj_apply36_kernel(const float* __restrict__ adj, const float* __restrict__ x, float* __restrict__ out,
                    bf16* __restrict__ hi, bf16* __restrict__ lo, int H, float alpha0,
                    const float* __restrict__ alpha_dev, float self_w, int accumulate) {
     constexpr int N = 36;
-    __shared__ __align__(16) float s_adj[N * N];
+    __shared__ __align__(16) float s_c[N * N];
     const int b = blockIdx.y;
     const float* ab = adj + (size_t)b * N * N;
+    const float alpha = alpha0 + (alpha_dev ? alpha_dev[0] : 0.f);
     for (int e = threadIdx.x; e < N * N; e += 128) {
         const int i = e / N, j = e - i * N;
-        s_adj[e] = TRANS ? ab[j * N + i] : ab[e];
+        float c = alpha * (TRANS ? ab[j * N + i] : ab[e]);
+        if (i == j) c += self_w;
+        s_c[e] = c;
     }
     __syncthreads();
     const int c = blockIdx.x * 256 + 2 * threadIdx.x;
     if (c >= H) return;
-    const float alpha = alpha0 + (alpha_dev ? alpha_dev[0] : 0.f);
     const size_t base = (size_t)b * N * H + c;
     float2 xv[N];
 #pragma unroll
     for (int j = 0; j < N; ++j) xv[j] = *reinterpret_cast<const float2*>(x + base + (size_t)j * H);
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        float ax = 0.f, ay = 0.f;
+#pragma unroll 1
+    for (int i = 0; i < N; i += 2) {
+        float v[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+        const float* r0 = s_c + i * N;
 #pragma unroll
         for (int j4 = 0; j4 < N / 4; ++j4) {
-            const float4 a = *reinterpret_cast<const float4*>(&s_adj[i * N + 4 * j4]);
-            ax = fmaf(a.x, xv[4 * j4].x, ax);     ay = fmaf(a.x, xv[4 * j4].y, ay);
-            ax = fmaf(a.y, xv[4 * j4 + 1].x, ax); ay = fmaf(a.y, xv[4 * j4 + 1].y, ay);
-            ax = fmaf(a.z, xv[4 * j4 + 2].x, ax); ay = fmaf(a.z, xv[4 * j4 + 2].y, ay);
-            ax = fmaf(a.w, xv[4 * j4 + 3].x, ax); ay = fmaf(a.w, xv[4 * j4 + 3].y, ay);
-        }
-        float vx = alpha * ax, vy = alpha * ay;
-        if (self_w != 0.f) { vx = fmaf(self_w, xv[i].x, vx); vy = fmaf(self_w, xv[i].y, vy); }
-        const size_t o = base + (size_t)i * H;
-        if (out) {
-            if (accumulate) {
-                const float2 p = *reinterpret_cast<const float2*>(out + o);
-                vx += p.x; vy += p.y;
+            const float4 a0 = *reinterpret_cast<const float4*>(r0 + 4 * j4);
+            const float4 a1 = *reinterpret_cast<const float4*>(r0 + N + 4 * j4);
+            const float c0[4] = {a0.x, a0.y, a0.z, a0.w}, c1[4] = {a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                v[0][0] = fmaf(c0[t], xv[4 * j4 + t].x, v[0][0]);
+                v[0][1] = fmaf(c0[t], xv[4 * j4 + t].y, v[0][1]);
+                v[1][0] = fmaf(c1[t], xv[4 * j4 + t].x, v[1][0]);
+                v[1][1] = fmaf(c1[t], xv[4 * j4 + t].y, v[1][1]);
             }
-            *reinterpret_cast<float2*>(out + o) = make_float2(vx, vy);
         }
-        if (hi) {
-            bf16 hx, lx, hy, ly;
-            split_bf16(vx, hx, lx);
-            split_bf16(vy, hy, ly);
-            *reinterpret_cast<__nv_bfloat162*>(hi + o) = __halves2bfloat162(hx, hy);
-            if (lo) *reinterpret_cast<__nv_bfloat162*>(lo + o) = __halves2bfloat162(lx, ly);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const size_t o = base + (size_t)(i + r) * H;
+            float vx = v[r][0], vy = v[r][1];
+            if (out) {
+                if (accumulate) {
+                    const float2 p = *reinterpret_cast<const float2*>(out + o);
+                    vx += p.x; vy += p.y;
+                }
+                *reinterpret_cast<float2*>(out + o) = make_float2(vx, vy);
+            }
+            if (hi) {
+                bf16 hx, lx, hy, ly;
+                split_bf16(vx, hx, lx);
+                split_bf16(vy, hy, ly);
+                *reinterpret_cast<__nv_bfloat162*>(hi + o) = __halves2bfloat162(hx, hy);
+                if (lo) *reinterpret_cast<__nv_bfloat162*>(lo + o) = __halves2bfloat162(lx, ly);
+            }
         }
     }
 }

@@ -46,6 +46,34 @@ class GraphedStep:
             self.epoch.add_(1)
             return self.fn(*[t.detach() for t in self.static_in])
 
+    # -- input prefetch: H2D of batch i+1 overlaps the replay of batch i ------------------------------
+    def prefetch(self, *host_inputs):
+        """Start copying the NEXT step's inputs (pinned host tensors) into device staging buffers on a
+        side stream; returns immediately.  Pair with ``run_prefetched()``."""
+        if len(host_inputs) != len(self.static_in):
+            raise RuntimeError("xggm_b200.GraphedStep: wrong number of inputs")
+        if not hasattr(self, "_stage"):
+            self._stage = [torch.empty_like(t) for t in self.static_in]
+            self._copy_stream = torch.cuda.Stream(device=self.static_in[0].device)
+            self._staged = torch.cuda.Event()
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record(torch.cuda.current_stream(self.static_in[0].device))
+        self._copy_stream.wait_event(self._stage_free)      # the previous batch has left the staging buffers
+        with torch.cuda.stream(self._copy_stream):
+            for s, t in zip(self._stage, host_inputs):
+                s.copy_(t, non_blocking=True)
+            self._staged.record(self._copy_stream)
+
+    def run_prefetched(self):
+        """Replay on the batch most recently passed to ``prefetch`` (device-to-device move into the
+        static buffers, then one graph launch)."""
+        cur = torch.cuda.current_stream(self.static_in[0].device)
+        cur.wait_event(self._staged)
+        for s, t in zip(self.static_in, self._stage):
+            s.copy_(t, non_blocking=True)
+        self._stage_free.record(cur)
+        return self.replay()
+
     def replay(self):
         """Replay on the tensors already in ``static_in`` (no input copies)."""
         self.graph.replay()
