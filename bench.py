@@ -139,10 +139,12 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus):
-    return {"workload": f"cfg2 graph block: VQA-CP v2 GGM node branch (delta=0), GCNGenerator L={N_LAYERS}, fwd+bwd, "
-                        f"B={B_PER_GPU}/GPU, N={N_NODES}, H={HID}, sigma={SIGMA}, A={NUM_ANS}, fp32",
-            "global_batch": B_PER_GPU * n_gpus, "per_gpu_batch": B_PER_GPU, "parallelism": f"dp{n_gpus}",
+def workload_config(n_gpus, B=B_PER_GPU, gnn=GNN, precision="fp32"):
+    arith = {"fp32": "fp32 (tensor cores, 3 split-bf16 passes)", "bf16": "bf16 tensor cores, fp32 storage",
+             "fp32_simt": "fp32 FMA"}[precision]
+    return {"workload": f"cfg2 graph block: VQA-CP v2 GGM node branch (delta=0), {gnn}Generator L={N_LAYERS}, fwd+bwd, "
+                        f"B={B}/GPU, N={N_NODES}, H={HID}, sigma={SIGMA}, A={NUM_ANS}, {arith}",
+            "global_batch": B * n_gpus, "per_gpu_batch": B, "parallelism": f"dp{n_gpus}",
             "l2": "flushed between timed steps (256 MiB write, outside the per-step CUDA-event pairs)",
             "launch": "one CUDA-graph replay per step (xggm_b200.GraphedStep)"}
 
@@ -163,8 +165,9 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(9595)  # reference default seed, src/param.py:49 (same on every rank: same branch, same init)
 
-    B = B_PER_GPU
-    model = X.XGGMHeads(HID, GNN, N_LAYERS, N_NODES).to(dev).train()
+    B = args.batch
+    X.set_precision(args.precision)
+    model = X.XGGMHeads(HID, args.gnn, N_LAYERS, N_NODES).to(dev).train()
     from xggm_b200.ddp import FlatGrads
     grads = FlatGrads(model.parameters())  # .grad are views of one flat buffer -> one all-reduce, no staging copy
     flat_grad = grads.flat
@@ -269,6 +272,9 @@ def run_gpu(args):
     value = B * world / (ms_step * 1e-3)
     e2e_val = B * world / (ms_e2e / args.steps * 1e-3)
     flops_step = algorithmic_flops_per_sample() * B
+    if args.gnn == "GIN":   # L(3*2NH^2 + 2*2N^2H) fwd, x3
+        flops_step = 3 * N_LAYERS * (3 * 2 * N_NODES * HID * HID + 2 * 2 * N_NODES * N_NODES * HID) * B
+    passes = 1 if args.precision == "bf16" else 3
     gemm_tflops = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     peak = peaks["bf16_tflops"]
     h2d = sum(t.numel() * 4 for t in (visn_h, xp_h, adj_h))
@@ -277,7 +283,8 @@ def run_gpu(args):
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+        "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": workload_config(world, B, args.gnn, args.precision),
         "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
@@ -286,7 +293,7 @@ def run_gpu(args):
                      "kernel": "gemm_tc_kernel (768x768 node projections fwd/dgrad/wgrad; tcgen05 kind::f16, "
                                "fp32 parity via 3 split-bf16 passes => 3x the algorithmic FLOPs are executed)",
                      "achieved": gemm_tflops, "peak": peak, "unit": "TFLOP/s", "frac": gemm_tflops / peak,
-                     "executed_tflops": 3 * gemm_tflops, "executed_frac": 3 * gemm_tflops / peak,
+                     "executed_tflops": passes * gemm_tflops, "executed_frac": passes * gemm_tflops / peak,
                      "traffic": TRAFFIC_NCU, "peak_source": f"{peaks['source']} bf16 burst (MEASURED_PEAKS.json)",
                      "launches_timed": g_n, "avg_launch_us": (g_ms / g_n * 1e3) if g_n else None,
                      "gemm_share_of_step": (g_ms / prof_steps) / ms_step if ms_step > 0 else None},
@@ -309,6 +316,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="xggm_b200", choices=["xggm_b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "fp32_simt"],
+                    help="projection engine (default fp32 = BASELINE cfg 2; bf16 = cfg 3 arithmetic)")
+    ap.add_argument("--batch", type=int, default=B_PER_GPU, help="graphs per GPU (default 256, the BASELINE config)")
+    ap.add_argument("--gnn", default=GNN, choices=["GCN", "GIN"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
