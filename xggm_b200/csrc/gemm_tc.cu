@@ -426,6 +426,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const int sp = tile % p.splits;
             const int m0 = (mn / p.tiles_n) * (BM * CG) + (int)rank * BM, n0 = (mn % p.tiles_n) * BN;
             const bool lead = (sp == 0);  // bias / residual are added by the first split only
+            const int mrow0 = m0 + q * 32;
+            const int rows = min(32, p.M - mrow0);
+            const bool vec = p.vec4 && !p.atomic && p.gram_n == 0;
+            // float4 domain: lane -> (row = 4*it + lane/8, 4 columns at 4*(lane%8))
+            const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+            constexpr int CSTEP = EPI_WARPS / 4;
+            // bias + residual + accumulate addends of column chunk `cc` for this lane's 8 float4s.  Issued one
+            // chunk AHEAD of their use (the first chunk's before the accumulator is even ready), so their
+            // L2/HBM latency hides behind the main loop / the previous chunk instead of stalling the warp.
+            // Raw loads only -- no arithmetic on the loaded values here, so the warp does not wait for them.
+            // x[] = residual rows, or (when there is no residual) the old C rows of an accumulate.
+            auto load_addends = [&](int cc, float4& bv, float4 (&x)[8]) {
+                const int nv = n0 + cc * 32 + c4;
+                const bool ok = vec && cc < BN / 32 && nv < p.N && mrow0 < p.M;   // N % 4 == 0 in vec mode
+                bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok && lead && p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + nv));
+                const float* src = (lead && p.resid) ? p.resid : (p.accumulate ? p.C : nullptr);
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int row = 4 * it + rsub;
+                    x[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok && src && row < rows)
+                        x[it] = *reinterpret_cast<const float4*>(src + (size_t)(mrow0 + row) * p.ldc + nv);
+                }
+            };
+            constexpr int NCH = (BN / 32) / CSTEP;   // column chunks per epilogue warp
+            float4 bvs[NCH + 1];
+            float4 xs[NCH + 1][8];
+            load_addends(csub, bvs[0], xs[0]);
+
             mbar_wait(&acc_full[acc], acc_phase);
             if (warp == 2 && lane == 0) XGGM_TRACE(4 + 4 * min(tile / num_workers, 3)); // accumulator ready
             tc_fence_after();
@@ -440,7 +470,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 const int hi_col = min(span, ((q * 32 + 31) / gn + 1) * gn);
                 float* orow = p.C + (b * gn + (r - gl * gn)) * gn - gl * gn;  // orow[col] = S[b][i][col - gl*gn]
 #pragma unroll 1
-                for (int c = csub; c < BN / 32; c += EPI_WARPS / 4) {
+                for (int c = csub; c < BN / 32; c += CSTEP) {
                     if (c * 32 + 32 <= lo_col || c * 32 >= hi_col) continue;  // warp-uniform
                     uint32_t v[32];
                     tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
@@ -459,37 +489,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 if (acc == 0) acc_phase ^= 1;
                 continue;
             }
-            const int mrow0 = m0 + q * 32;
-            const int rows = min(32, p.M - mrow0);
-            const bool vec = p.vec4 && !p.atomic;
-            // float4 domain: lane -> (row = 4*it + lane/8, 4 columns at 4*(lane%8))
-            const int rsub = lane >> 3, c4 = (lane & 7) * 4;
-#pragma unroll 1
-            for (int c = csub; c < BN / 32; c += EPI_WARPS / 4) {
-                const int ncol0 = n0 + c * 32;
-                if (ncol0 >= p.N || mrow0 >= p.M) break;  // warp-uniform
-                // (1) issue this chunk's bias / residual / accumulate loads first: their latency hides
-                //     behind the TMEM load and the smem transpose below
-                float4 e[8];
-                const int nv = ncol0 + c4;
-                const bool nv_ok = vec && nv < p.N;  // N % 4 == 0 in vec mode: no straddling
-                if (nv_ok) {
-                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (lead && p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + nv));
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        e[it] = bv;
-                        const int row = 4 * it + rsub;
-                        if (lead && p.resid && row < rows) {
-                            const float4 r = __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)(mrow0 + row) * p.ldc + nv));
-                            e[it].x += r.x; e[it].y += r.y; e[it].z += r.z; e[it].w += r.w;
-                        }
-                        if (p.accumulate && row < rows) {
-                            const float4 r = *reinterpret_cast<const float4*>(p.C + (size_t)(mrow0 + row) * p.ldc + nv);
-                            e[it].x += r.x; e[it].y += r.y; e[it].z += r.z; e[it].w += r.w;
-                        }
-                    }
-                }
+            for (int ci = 0; ci < NCH; ++ci) {   // fully unrolled: the addend registers ping-pong without moves
+                const int c = csub + ci * CSTEP;
+                const int ncol0 = n0 + c * 32;
+                const bool live = ncol0 < p.N && mrow0 < p.M;  // warp-uniform
+                // (1) next chunk's addends go on the wire now
+                load_addends(c + CSTEP, bvs[ci + 1], xs[ci + 1]);
+                if (!live) continue;
                 // (2) accumulator chunk: TMEM -> registers (thread = row) -> smem transpose
                 uint32_t v[32];
                 tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
@@ -498,16 +505,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 __syncwarp();
                 // (3) coalesced stores
                 if (vec) {
-                    if (nv_ok) {
+                    const int nv = ncol0 + c4;
+                    if (nv < p.N) {
+                        const bool both = lead && p.resid && p.accumulate;   // rare: second addend read late
+                        float4 o[8];
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const float* sp = st + (4 * it + rsub) * EPI_PITCH + c4;
+                            const float4 bv = bvs[ci], x = xs[ci][it];
+                            o[it] = make_float4(sp[0] + bv.x + x.x, sp[1] + bv.y + x.y, sp[2] + bv.z + x.z, sp[3] + bv.w + x.w);
+                        }
 #pragma unroll
                         for (int it = 0; it < 8; ++it) {
                             const int row = 4 * it + rsub;
                             if (row < rows) {
-                                const float* sp = st + row * EPI_PITCH + c4;
-                                const float4 o = make_float4(sp[0] + e[it].x, sp[1] + e[it].y, sp[2] + e[it].z, sp[3] + e[it].w);
                                 const size_t off = (size_t)(mrow0 + row) * p.ldc + nv;
-                                *reinterpret_cast<float4*>(p.C + off) = o;
-                                if (p.c_hi) store_planes4(p.c_hi, p.c_lo, off, o);
+                                if (both) {
+                                    const float4 a = *reinterpret_cast<const float4*>(p.C + off);
+                                    o[it].x += a.x; o[it].y += a.y; o[it].z += a.z; o[it].w += a.w;
+                                }
+                                *reinterpret_cast<float4*>(p.C + off) = o[it];
+                                if (p.c_hi) store_planes4(p.c_hi, p.c_lo, off, o[it]);
                             }
                         }
                     }
