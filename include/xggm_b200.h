@@ -93,14 +93,18 @@ int xggm_linear_bwd_weight(const float* g, const float* a, float* gw, float* gbi
  *   GCNConv  torch.bmm(adj, x)                    src/module/gcn.py:28
  *   GINConv  X + (1 + eps) * A @ X                src/module/gin.py:32
  * out[b] = self_w * x[b] + alpha * adj[b] @ x[b],  alpha = alpha0 + (*alpha_dev if non-NULL)
+ * `work` (xggm_adj_apply_work_bytes bytes, 16-byte aligned; N <= 128, H % 8 == 0) runs the product on the
+ * tensor cores (block-diagonal coefficient tiles x bf16 planes of the node features); NULL selects the
+ * SIMT kernel.
  * ------------------------------------------------------------------------- */
+long long xggm_adj_apply_work_bytes(int B, int N, int H);
 int xggm_adj_apply_fwd(const float* adj, const float* x, float* out, int B, int N, int H,
-                       float alpha0, const float* alpha_dev, float self_w, xggm_stream_t s);
+                       float alpha0, const float* alpha_dev, float self_w, void* work, xggm_stream_t s);
 /* gx (+)= self_w*gout + alpha * adj^T @ gout ; gadj_raw? = gout @ x^T (NOT scaled by alpha;
  * the caller scales, and d alpha = <gadj_raw, adj>). */
 int xggm_adj_apply_bwd(const float* adj, const float* x, const float* gout, float* gx,
                        float* gadj_raw, int B, int N, int H, float alpha0,
-                       const float* alpha_dev, float self_w, int accumulate_gx, xggm_stream_t s);
+                       const float* alpha_dev, float self_w, int accumulate_gx, void* work, xggm_stream_t s);
 
 /* ------------------------------------------------------------------------- *
  * Row normalisation / activations
@@ -134,10 +138,11 @@ int xggm_gelu_ln_drop_bwd(const float* gout, const float* z, const float* mean, 
 long long xggm_adj_regen_work_bytes(int B, int N, int H);
 int xggm_adj_regen_fwd(const float* x, float* adj_out, float* S, int32_t* amax, int B, int N,
                        int H, int squash, void* work, xggm_stream_t s);
-/* gx (+)= (dS + dS^T) x.  `work` is a [B,N,N] scratch buffer. */
+/* gx (+)= (dS + dS^T) x.  `work` is a [B,N,N] scratch buffer; `tc_work`? (xggm_adj_apply_work_bytes bytes)
+ * moves the D x product onto the tensor cores. */
 int xggm_adj_regen_bwd(const float* gadj, const float* x, const float* S, const int32_t* amax,
                        float* gx, float* work, int B, int N, int H, int squash,
-                       int accumulate_gx, xggm_stream_t s);
+                       int accumulate_gx, void* tc_work, xggm_stream_t s);
 
 /* ------------------------------------------------------------------------- *
  * Whole GCN / GIN layers (conv chain + jump-knowledge read-out)

@@ -377,7 +377,9 @@ def test_full_size_properties():
     with torch.no_grad():
         full, _ = mod.generator(visn, X.glue.strip_diag(adj_true))
         part, _ = mod.generator(visn[100:103], X.glue.strip_diag(adj_true)[100:103])
-    assert torch.equal(full[100:103], part)
+    # (to the engine's rounding level ~5e-6 per product, not bitwise: the tensor-core message-passing / Gram tiles hold 3 graphs, so a
+    # graph's position inside its tile -- hence the summation grouping of its dot products -- depends on b)
+    assert rel_l2(part.cpu(), full[100:103].cpu()) < 2e-5 and rel_max(part.cpu(), full[100:103].cpu()) < 2e-4
     # linearity of the backward pass in the cotangent (eval mode: deterministic)
     xa = visn[:8].clone().requires_grad_(True)
     out, _ = mod.generator(xa, X.glue.strip_diag(adj_true)[:8])

@@ -45,10 +45,11 @@ def timed(name, fn, mbytes):
 
 ops = args.ops.split(",")
 if "adj" in ops:
-    timed("adj_apply fwd (fp32 out)", lambda: call("xggm_adj_apply_fwd", ptr(adj), ptr(x), ptr(out), B, N, H, 1.0, None, 0.0), 2 * T)
     gx, graw = torch.empty_like(x), torch.empty_like(adj)
-    timed("adj_apply bwd (adj^T g, no gadj)", lambda: call("xggm_adj_apply_bwd", ptr(adj), ptr(x), ptr(g), ptr(gx), None, B, N, H, 1.0, None, 0.0, 0), 2 * T)
-    timed("adj_apply bwd accumulate", lambda: call("xggm_adj_apply_bwd", ptr(adj), ptr(x), ptr(g), ptr(gx), None, B, N, H, 1.0, None, 0.0, 1), 3 * T)
+    for tag, wk in (("SIMT", None), ("tensor cores", XF._adj_work(B, N, H, dev))):
+        timed(f"adj_apply fwd [{tag}]", lambda: call("xggm_adj_apply_fwd", ptr(adj), ptr(x), ptr(out), B, N, H, 1.0, None, 0.0, ptr(wk)), 2 * T)
+        timed(f"adj_apply bwd adj^T g [{tag}]", lambda: call("xggm_adj_apply_bwd", ptr(adj), ptr(x), ptr(g), ptr(gx), None, B, N, H, 1.0, None, 0.0, 0, ptr(wk)), 2 * T)
+        timed(f"adj_apply bwd accumulate [{tag}]", lambda: call("xggm_adj_apply_bwd", ptr(adj), ptr(x), ptr(g), ptr(gx), None, B, N, H, 1.0, None, 0.0, 1, ptr(wk)), 3 * T)
 if "ln" in ops:
     h, xhat, rstd = torch.empty_like(x), torch.empty_like(x), torch.empty(M, device=dev)
     timed("layernorm fwd (h, xhat)", lambda: call("xggm_layernorm_fwd", ptr(x), ptr(gamma), ptr(beta), ptr(h), ptr(xhat), ptr(rstd), M, H, 1e-5), 3 * T)

@@ -30,15 +30,16 @@ SIGNATURES = {
     "xggm_linear_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp],
     "xggm_linear_bwd_input": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "xggm_linear_bwd_weight": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
-    "xggm_adj_apply_fwd": [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _f, _vp],
-    "xggm_adj_apply_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _f, _i, _vp],
+    "xggm_adj_apply_work_bytes": [_i, _i, _i],
+    "xggm_adj_apply_fwd": [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _f, _vp, _vp],
+    "xggm_adj_apply_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _f, _i, _vp, _vp],
     "xggm_layernorm_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp],
     "xggm_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "xggm_gelu_ln_drop_fwd": [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _f, _i, _vp],
     "xggm_gelu_ln_drop_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _vp],
     "xggm_adj_regen_work_bytes": [_i, _i, _i],
     "xggm_adj_regen_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
-    "xggm_adj_regen_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "xggm_adj_regen_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "xggm_gnn_saved_floats": [_i, _i, _i, _i, _i],
     "xggm_gnn_work_floats": [_i, _i, _i, _i, _i],
     "xggm_gnn_fwd": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
@@ -66,7 +67,7 @@ SIGNATURES = {
     "xggm_keep_mask": [_vp, _ll, _f, _u64, _u64, _vp, _vp],
 }
 _RESTYPES = {"xggm_launch_count": C.c_ulonglong, "xggm_strerror": C.c_char_p, "xggm_last_cuda_error": C.c_char_p,
-             "xggm_gnn_saved_floats": _ll, "xggm_gnn_work_floats": _ll, "xggm_linear_work_bytes": _ll, "xggm_adj_regen_work_bytes": _ll}
+             "xggm_gnn_saved_floats": _ll, "xggm_gnn_work_floats": _ll, "xggm_linear_work_bytes": _ll, "xggm_adj_regen_work_bytes": _ll, "xggm_adj_apply_work_bytes": _ll}
 
 _lib = None
 _checked_devices = set()

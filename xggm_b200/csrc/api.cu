@@ -17,6 +17,13 @@ bool gemm_tc_supported(int M, int N, int K);
 int gemm_tc(bool a_mn, bool b_mn, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const __nv_bfloat16* b_hi,
             const __nv_bfloat16* b_lo, const float* bias, const float* resid, float* C, __nv_bfloat16* c_hi,
             __nv_bfloat16* c_lo, int M, int N, int K, int accumulate, int allow_split_k, int npass, cudaStream_t st);
+bool adj_tc_supported(int N, int H);
+long long adj_tc_coef_elems(int B, int N);
+int build_blockdiag(const float* adj, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int N, float alpha0,
+                    const float* alpha_dev, float self_w, int trans, cudaStream_t st);
+int adj_apply_tc(const __nv_bfloat16* c_hi, const __nv_bfloat16* c_lo, const __nv_bfloat16* x_hi,
+                 const __nv_bfloat16* x_lo, float* out, __nv_bfloat16* o_hi, __nv_bfloat16* o_lo, int B, int N, int H,
+                 int accumulate, int npass, cudaStream_t st);
 bool gram_tc_supported(int N, int H);
 int gram_tc(const __nv_bfloat16* p_hi, const __nv_bfloat16* p_lo, const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo,
             float* S, int B, int N, int H, int npass, cudaStream_t st);
@@ -38,6 +45,7 @@ int adj_apply(const float*, const float*, float*, __nv_bfloat16*, __nv_bfloat16*
 int bmm_nt(const float*, const float*, float*, int, int, int, float, const float*, int, const float*, float*, cudaStream_t);
 int adj_regen_fwd(const float*, float*, float*, int32_t*, int, int, int, int, cudaStream_t);
 int adj_regen_bwd(const float*, const float*, const float*, const int32_t*, float*, float*, int, int, int, int, int, cudaStream_t);
+int adj_regen_bwd_coeffs(const float* gadj, const float* S, const int32_t* amax, float* D, int B, int N, int squash, cudaStream_t st);
 int gat_attn_fwd(const float*, const float*, const float*, float*, float*, float*, int, int, int, float, int, cudaStream_t);
 int gat_attn_bwd(const float*, const float*, const float*, const float*, const float*, const float*, float*, float*, float*, int, int, int, float, int, cudaStream_t);
 int gelu_fwd(const float*, float*, long long, cudaStream_t);
@@ -152,9 +160,10 @@ struct GnnLayout {
         const long long base = head_base + head_stride * j;
         return slot == 0 ? base : base + MH + (slot - 1) * Mr;
     }
-    long long work_fwd() const { return MH + (2 * n_convs + 1) * HH; }
-    // bwd: buf0 | buf1 | gt | gq | P(grad) | P(gq) | weight planes | S scratch [B,N,N]
-    long long work_bwd(long long bnn) const { return 6 * MH + (2 * n_convs + 1) * HH + al4(bnn); }
+    // fwd: u | weight planes | block-diagonal coefficient planes
+    long long work_fwd(long long coef) const { return MH + (2 * n_convs + 1) * HH + al4(coef); }
+    // bwd: buf0 | buf1 | gt | gq | P(grad) | P(gq) | weight planes | S scratch [B,N,N] | coefficient planes
+    long long work_bwd(long long bnn, long long coef) const { return 6 * MH + (2 * n_convs + 1) * HH + al4(bnn) + al4(coef); }
 };
 
 // weight planes for one layer live at the tail of the work buffer: conv k -> slot k, head j -> slot nc + j
@@ -221,6 +230,13 @@ static int gnn_fwd(int kind, const float* x, const float* adj, const float* cons
     Operand hops[MAX_CONVS + 1];
     hops[0] = hop;
     const float* h = x;
+    // message passing on the tensor cores: block-diagonal coefficient tiles (built once per call for GCN,
+    // per conv for GIN whose (1+eps) differs) x the node planes
+    const bool adjtc = tc && adj_tc_supported(N, H);
+    bf16* coef_hi = reinterpret_cast<bf16*>(work + L.MH + (2 * nc + 1) * L.HH);
+    bf16* coef_lo = coef_hi + al4(adjtc ? adj_tc_coef_elems(B, N) : 0);
+    if (adjtc && kind == XGGM_KIND_GCN && nc > 0)
+        XGGM_TRY(build_blockdiag(adj, coef_hi, npass() == 3 ? coef_lo : nullptr, B, N, 1.f, nullptr, 0.f, 0, st));
     for (int k = 0; k < nc; ++k) {
         float* h_next = saved + L.conv(k, 2);
         float* pre = saved + L.conv(k, 0);   // GCN: agg = adj @ h ; GIN: pre = h + (1+eps) adj @ h
@@ -232,8 +248,12 @@ static int gnn_fwd(int kind, const float* x, const float* adj, const float* cons
             float* rstd = saved + L.conv(k, 3);
             float* u = work;
             // tensor-core engine: the aggregate is only ever a GEMM operand -> bf16 planes, no fp32 copy
-            XGGM_TRY(adj_apply(adj, h, tc ? nullptr : pre, tc ? mut(pre_op.hi) : nullptr, tc ? lo_or_null(pre_op) : nullptr,
-                               B, N, H, 1.f, nullptr, 0.f, false, 0, st));
+            if (adjtc)
+                XGGM_TRY(adj_apply_tc(coef_hi, coef_lo, hops[k].hi, hops[k].lo, nullptr, mut(pre_op.hi), lo_or_null(pre_op),
+                                      B, N, H, 0, npass(), st));
+            else
+                XGGM_TRY(adj_apply(adj, h, tc ? nullptr : pre, tc ? mut(pre_op.hi) : nullptr, tc ? lo_or_null(pre_op) : nullptr,
+                                   B, N, H, 1.f, nullptr, 0.f, false, 0, st));
             XGGM_TRY(proj_fwd(tc, pre_op, wconv[k], nullptr, h, u, M, H, H, st));
             XGGM_TRY(layernorm_fwd(u, g, b, h_next, xhat, rstd, tc ? mut(next_op.hi) : nullptr,
                                    tc ? lo_or_null(next_op) : nullptr, M, H, LN_EPS, st));
@@ -243,8 +263,14 @@ static int gnn_fwd(int kind, const float* x, const float* adj, const float* cons
             float* z = saved + L.conv(k, 1);
             float* mean = saved + L.conv(k, 3);
             float* rstd = saved + L.conv(k, 4);
-            XGGM_TRY(adj_apply(adj, h, tc ? nullptr : pre, tc ? mut(pre_op.hi) : nullptr, tc ? lo_or_null(pre_op) : nullptr,
-                               B, N, H, 1.f, eps, 1.f, false, 0, st));
+            if (adjtc) {
+                XGGM_TRY(build_blockdiag(adj, coef_hi, npass() == 3 ? coef_lo : nullptr, B, N, 1.f, eps, 1.f, 0, st));
+                XGGM_TRY(adj_apply_tc(coef_hi, coef_lo, hops[k].hi, hops[k].lo, nullptr, mut(pre_op.hi), lo_or_null(pre_op),
+                                      B, N, H, 0, npass(), st));
+            } else {
+                XGGM_TRY(adj_apply(adj, h, tc ? nullptr : pre, tc ? mut(pre_op.hi) : nullptr, tc ? lo_or_null(pre_op) : nullptr,
+                                   B, N, H, 1.f, eps, 1.f, false, 0, st));
+            }
             XGGM_TRY(proj_fwd(tc, pre_op, wconv[k], bias, nullptr, z, M, H, H, st));
             XGGM_TRY(gelu_ln_drop_fwd(z, g, b, drop_none(), h_next, mean, rstd, tc ? mut(next_op.hi) : nullptr,
                                       tc ? lo_or_null(next_op) : nullptr, M, H, LN_EPS, 0, st));
@@ -300,6 +326,11 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
     const Operand gq_op = planes_at(gq, work + 5 * MH, MHn);
     float* s_scratch = work + 6 * MH + (2 * nc + 1) * L.HH;
     const long long BNN = (long long)B * N * N;
+    const bool adjtc = gram && adj_tc_supported(N, H);   // needs the planes of gq the Gram path already emits
+    bf16* coef_hi = reinterpret_cast<bf16*>(s_scratch + al4(BNN));
+    bf16* coef_lo = coef_hi + al4(adjtc ? adj_tc_coef_elems(B, N) : 0);
+    if (adjtc && kind == XGGM_KIND_GCN && nc > 0)   // adj^T coefficients, shared by every conv of the layer
+        XGGM_TRY(build_blockdiag(adj, coef_hi, npass() == 3 ? coef_lo : nullptr, B, N, 1.f, nullptr, 0.f, 1, st));
 
     auto act = [&](int j) -> Operand {   // h_j as a GEMM operand (planes saved by the forward pass)
         return j == 0 ? planes_at(x, saved + L.xplanes, MHn)
@@ -350,7 +381,10 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
             } else {
                 XGGM_TRY(bmm_nt(gq, hk, gadj, B, N, H, 1.f, nullptr, 1, nullptr, nullptr, st));
             }
-            XGGM_TRY(adj_apply(adj, gq, gnext, nullptr, nullptr, B, N, H, 1.f, nullptr, 0.f, true, 1, st));
+            if (adjtc)   // gnext += adj^T gq
+                XGGM_TRY(adj_apply_tc(coef_hi, coef_lo, gq_op.hi, gq_op.lo, gnext, nullptr, nullptr, B, N, H, 1, npass(), st));
+            else
+                XGGM_TRY(adj_apply(adj, gq, gnext, nullptr, nullptr, B, N, H, 1.f, nullptr, 0.f, true, 1, st));
         } else {
             const float* eps = cp[5 * k], *g = cp[5 * k + 3];
             if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k], 0, sizeof(float), st));
@@ -372,7 +406,12 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
                 XGGM_TRY(bmm_nt(gq, hk, gadj, B, N, H, 1.f, eps, 1, adj, cg[5 * k], st));
             }
             // grad h_k = gpre + (1+eps) adj^T gpre
-            XGGM_TRY(adj_apply(adj, gq, gnext, nullptr, nullptr, B, N, H, 1.f, eps, 1.f, true, 0, st));
+            if (adjtc) {
+                XGGM_TRY(build_blockdiag(adj, coef_hi, npass() == 3 ? coef_lo : nullptr, B, N, 1.f, eps, 1.f, 1, st));
+                XGGM_TRY(adj_apply_tc(coef_hi, coef_lo, gq_op.hi, gq_op.lo, gnext, nullptr, nullptr, B, N, H, 0, npass(), st));
+            } else {
+                XGGM_TRY(adj_apply(adj, gq, gnext, nullptr, nullptr, B, N, H, 1.f, eps, 1.f, true, 0, st));
+            }
         }
         XGGM_TRY(head_bwd(k, gnext, 1));
         gh = gnext;
@@ -502,18 +541,44 @@ int xggm_linear_bwd_weight(const float* g, const float* a, float* gw, float* gbi
     return XGGM_OK;
 }
 
+// work layout of the message-passing entry points: P(x or gout)[B,N,H] | coefficient planes
+long long xggm_adj_apply_work_bytes(int B, int N, int H) {
+    if (B < 0 || N <= 0 || H <= 0) return -1;
+    return 4 * (al4((long long)B * N * H) + (N <= 128 ? al4(adj_tc_coef_elems(B, N)) : 0));
+}
+static inline bool adj_tc_ok(const void* work, int N, int H) {
+    return work != nullptr && g_precision != XGGM_PREC_FP32_SIMT && adj_tc_supported(N, H);
+}
+// out (=|+=) self_w * v + alpha * (adj | adj^T) @ v through the tensor cores
+static int adj_apply_tc_f32(const float* adj, const float* v, float* out, int B, int N, int H, float alpha0,
+                            const float* alpha_dev, float self_w, int trans, int accumulate, float* work,
+                            cudaStream_t st) {
+    const long long n = (long long)B * N * H;
+    const Operand vo = planes_at(v, work, n);
+    bf16* chi = reinterpret_cast<bf16*>(work + al4(n));
+    bf16* clo = chi + al4(adj_tc_coef_elems(B, N));
+    XGGM_TRY(split_one(vo, n, st));
+    XGGM_TRY(build_blockdiag(adj, chi, npass() == 3 ? clo : nullptr, B, N, alpha0, alpha_dev, self_w, trans, st));
+    return adj_apply_tc(chi, clo, vo.hi, vo.lo, out, nullptr, nullptr, B, N, H, accumulate, npass(), st);
+}
+
 int xggm_adj_apply_fwd(const float* adj, const float* x, float* out, int B, int N, int H,
-                       float alpha0, const float* alpha_dev, float self_w, xggm_stream_t s) {
+                       float alpha0, const float* alpha_dev, float self_w, void* work, xggm_stream_t s) {
     if (B == 0) return XGGM_OK;
     XGGM_REQUIRE(adj && x && out && B >= 0);
+    if (adj_tc_ok(work, N, H) && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+        return adj_apply_tc_f32(adj, x, out, B, N, H, alpha0, alpha_dev, self_w, 0, 0, static_cast<float*>(work), as_stream(s));
     return adj_apply(adj, x, out, nullptr, nullptr, B, N, H, alpha0, alpha_dev, self_w, false, 0, as_stream(s));
 }
 int xggm_adj_apply_bwd(const float* adj, const float* x, const float* gout, float* gx,
                        float* gadj_raw, int B, int N, int H, float alpha0, const float* alpha_dev,
-                       float self_w, int accumulate_gx, xggm_stream_t s) {
+                       float self_w, int accumulate_gx, void* work, xggm_stream_t s) {
     if (B == 0) return XGGM_OK;
     XGGM_REQUIRE(adj && x && gout && gx && B >= 0);
-    XGGM_TRY(adj_apply(adj, gout, gx, nullptr, nullptr, B, N, H, alpha0, alpha_dev, self_w, true, accumulate_gx, as_stream(s)));
+    if (adj_tc_ok(work, N, H) && (reinterpret_cast<uintptr_t>(gx) & 15) == 0)
+        XGGM_TRY(adj_apply_tc_f32(adj, gout, gx, B, N, H, alpha0, alpha_dev, self_w, 1, accumulate_gx, static_cast<float*>(work), as_stream(s)));
+    else
+        XGGM_TRY(adj_apply(adj, gout, gx, nullptr, nullptr, B, N, H, alpha0, alpha_dev, self_w, true, accumulate_gx, as_stream(s)));
     if (gadj_raw) XGGM_TRY(bmm_nt(gout, x, gadj_raw, B, N, H, 1.f, nullptr, 0, nullptr, nullptr, as_stream(s)));
     return XGGM_OK;
 }
@@ -566,10 +631,15 @@ int xggm_adj_regen_fwd(const float* x, float* adj_out, float* S, int32_t* amax, 
 }
 int xggm_adj_regen_bwd(const float* gadj, const float* x, const float* S, const int32_t* amax,
                        float* gx, float* work, int B, int N, int H, int squash,
-                       int accumulate_gx, xggm_stream_t s) {
+                       int accumulate_gx, void* tc_work, xggm_stream_t s) {
     XGGM_REQUIRE(B >= 0 && H > 0);
     if (B == 0) return XGGM_OK;
     XGGM_REQUIRE(gadj && x && S && amax && gx && work);
+    if (adj_tc_ok(tc_work, N, H) && (reinterpret_cast<uintptr_t>(gx) & 15) == 0) {
+        // D = dS + dS^T per graph (small kernel), then gx (+)= D x on the tensor cores
+        XGGM_TRY(adj_regen_bwd_coeffs(gadj, S, amax, work, B, N, squash, as_stream(s)));
+        return adj_apply_tc_f32(work, x, gx, B, N, H, 1.f, nullptr, 0.f, 0, accumulate_gx, static_cast<float*>(tc_work), as_stream(s));
+    }
     return adj_regen_bwd(gadj, x, S, amax, gx, work, B, N, H, squash, accumulate_gx, as_stream(s));
 }
 
@@ -580,8 +650,9 @@ long long xggm_gnn_saved_floats(int kind, int B, int N, int H, int n_convs) {
 long long xggm_gnn_work_floats(int kind, int B, int N, int H, int n_convs) {
     if ((kind != XGGM_KIND_GCN && kind != XGGM_KIND_GIN) || B < 0 || N <= 0 || H <= 0 || n_convs < 0) return -1;
     const GnnLayout L(kind, (long long)B * N, H, n_convs);
-    const long long wb = L.work_bwd((long long)B * N * N);
-    return wb > L.work_fwd() ? wb : L.work_fwd();
+    const long long coef = N <= 128 ? adj_tc_coef_elems(B, N) : 0;
+    const long long wb = L.work_bwd((long long)B * N * N, coef), wf = L.work_fwd(coef);
+    return wb > wf ? wb : wf;
 }
 int xggm_gnn_fwd(int kind, const float* x, const float* adj, const float* const* conv_params,
                  const float* const* head_params, const uint8_t* const* keeps, const xggm_philox_t* philox,

@@ -230,6 +230,11 @@ struct Params {
     // tensors, tile t covers the gram_g complete graphs starting at row t*gram_g*gram_n, and only the
     // gram_n x gram_n diagonal blocks  S[b] = P[b] Q[b]^T  are written to C[B][gram_n][gram_n].
     int gram_n, gram_g, gram_b;
+    // Block-diagonal mode (bd_stride > 0; message passing  out[b] = C[b] @ x[b]  on the tensor cores):
+    // A is a stack of dense 128 x 128 K-major tiles (tile t = the coefficient blocks of the bd_stride/N
+    // graphs starting at row t*bd_stride, zero elsewhere), B is x itself read MN-major with its k rows
+    // starting at t*bd_stride, and only the first bd_stride rows of each output tile exist.
+    int bd_stride;
     unsigned long long* dbg;   // optional device buffer: CTA 0 records a globaltimer timeline (tools/gemm_timeline.py)
 };
 
@@ -315,6 +320,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 const int mn = tile / p.splits;
                 int m0 = (mn / p.tiles_n) * (BM * CG) + (int)rank * BM, n0 = (mn % p.tiles_n) * BN;
                 if (p.gram_n > 0) m0 = n0 = mn * p.gram_g * p.gram_n;
+                const int b_krow0 = p.bd_stride > 0 ? (mn / p.tiles_n) * p.bd_stride : 0;   // block-diagonal mode
                 const int kb0 = sp * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
@@ -352,7 +358,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         if (B_MN) {
 #pragma unroll
                             for (int i = 0; i < BN / 64; ++i)
-                                tma_load_2d(sb + pl * C::B_TILE + i * (BK * 128), mb, &full[stage], n0 + 64 * i, k0);
+                                tma_load_2d(sb + pl * C::B_TILE + i * (BK * 128), mb, &full[stage], n0 + 64 * i, b_krow0 + k0);
                         } else {
                             tma_load_2d(sb + pl * C::B_TILE, mb, &full[stage], k0, n0);
                         }
@@ -424,10 +430,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         for (int tile = worker; tile < num_tiles; tile += num_workers) {
             const int mn = tile / p.splits;
             const int sp = tile % p.splits;
-            const int m0 = (mn / p.tiles_n) * (BM * CG) + (int)rank * BM, n0 = (mn % p.tiles_n) * BN;
+            const int n0 = (mn % p.tiles_n) * BN;
+            const int m0 = p.bd_stride > 0 ? (mn / p.tiles_n) * p.bd_stride
+                                           : (mn / p.tiles_n) * (BM * CG) + (int)rank * BM;
             const bool lead = (sp == 0);  // bias / residual are added by the first split only
             const int mrow0 = m0 + q * 32;
-            const int rows = min(32, p.M - mrow0);
+            const int rows = p.bd_stride > 0 ? min(32, min(p.M - mrow0, p.bd_stride - q * 32)) : min(32, p.M - mrow0);
             const bool vec = p.vec4 && !p.atomic && p.gram_n == 0;
             // float4 domain: lane -> (row = 4*it + lane/8, 4 columns at 4*(lane%8))
             const int rsub = lane >> 3, c4 = (lane & 7) * 4;
@@ -439,7 +447,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             // x[] = residual rows, or (when there is no residual) the old C rows of an accumulate.
             auto load_addends = [&](int cc, float4& bv, float4 (&x)[8]) {
                 const int nv = n0 + cc * 32 + c4;
-                const bool ok = vec && cc < BN / 32 && nv < p.N && mrow0 < p.M;   // N % 4 == 0 in vec mode
+                const bool ok = vec && cc < BN / 32 && nv < p.N && rows > 0;   // N % 4 == 0 in vec mode
                 bv = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (ok && lead && p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + nv));
                 const float* src = (lead && p.resid) ? p.resid : (p.accumulate ? p.C : nullptr);
@@ -493,7 +501,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             for (int ci = 0; ci < NCH; ++ci) {   // fully unrolled: the addend registers ping-pong without moves
                 const int c = csub + ci * CSTEP;
                 const int ncol0 = n0 + c * 32;
-                const bool live = ncol0 < p.N && mrow0 < p.M;  // warp-uniform
+                const bool live = ncol0 < p.N && rows > 0;  // warp-uniform
                 // (1) next chunk's addends go on the wire now
                 load_addends(c + CSTEP, bvs[ci + 1], xs[ci + 1]);
                 if (!live) continue;
@@ -524,7 +532,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                                     const float4 a = *reinterpret_cast<const float4*>(p.C + off);
                                     o[it].x += a.x; o[it].y += a.y; o[it].z += a.z; o[it].w += a.w;
                                 }
-                                *reinterpret_cast<float4*>(p.C + off) = o[it];
+                                if (p.C) *reinterpret_cast<float4*>(p.C + off) = o[it];
                                 if (p.c_hi) store_planes4(p.c_hi, p.c_lo, off, o[it]);
                             }
                         }
@@ -642,6 +650,39 @@ __global__ void __launch_bounds__(256) split_planes_t_kernel(const SplitTJobs jo
             job.hi[(size_t)c * R + r] = h;
             if (job.lo) job.lo[(size_t)c * R + r] = l;
         }
+    }
+}
+
+// Block-diagonal coefficient tiles for message passing on the tensor cores.  Tile t (one CTA) is a
+// dense [128][128] K-major bf16 matrix: for each of the G = 128/N graphs b = t*G + g it holds
+//   C_b = alpha * (adj_b | adj_b^T) + self_w * I     at rows/cols [g*N, g*N + N), zero elsewhere.
+// grid (tiles, 4): each CTA writes 32 rows of a tile; a thread produces 8 consecutive columns (one 16-byte store per plane).
+__global__ void __launch_bounds__(128)
+build_blockdiag_kernel(const float* __restrict__ adj, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                       int B, int N, int G, float alpha0, const float* __restrict__ alpha_dev, float self_w, int trans) {
+    const int t = blockIdx.x;
+    const float alpha = alpha0 + (alpha_dev ? alpha_dev[0] : 0.f);
+    __nv_bfloat16* th = hi + (size_t)t * BM * BM;
+    __nv_bfloat16* tl = lo ? lo + (size_t)t * BM * BM : nullptr;
+    for (int v = threadIdx.x; v < 32 * (BM / 8); v += blockDim.x) {
+        const int r = blockIdx.y * 32 + v / (BM / 8), c0 = (v % (BM / 8)) * 8;
+        const int g = r / N, i = r - g * N;
+        const long long b = (long long)t * G + g;
+        const bool row_live = g < G && b < B;
+        const float* ab = adj + (size_t)(row_live ? b : 0) * N * N;
+        __align__(16) __nv_bfloat16 hv[8], lv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = c0 + u - g * N;
+            float val = 0.f;
+            if (row_live && j >= 0 && j < N) {
+                val = alpha * ab[trans ? j * N + i : i * N + j];
+                if (i == j) val += self_w;
+            }
+            split1(val, hv[u], lv[u]);
+        }
+        *reinterpret_cast<uint4*>(th + (size_t)r * BM + c0) = *reinterpret_cast<const uint4*>(hv);
+        if (tl) *reinterpret_cast<uint4*>(tl + (size_t)r * BM + c0) = *reinterpret_cast<const uint4*>(lv);
     }
 }
 
@@ -783,6 +824,7 @@ int gemm_tc(bool a_mn, bool b_mn, const __nv_bfloat16* a_hi, const __nv_bfloat16
                                    reinterpret_cast<uintptr_t>(bias)) & 15) == 0;
         p.c_hi = c_hi; p.c_lo = npass == 3 ? c_lo : nullptr;
         p.gram_n = p.gram_g = p.gram_b = 0;
+        p.bd_stride = 0;
         p.dbg = g_tc_dbg;
         if (c_hi && (!p.vec4 || (reinterpret_cast<uintptr_t>(c_hi) & 7) || (reinterpret_cast<uintptr_t>(c_lo) & 7)))
             return XGGM_ERR_ARG;
@@ -839,6 +881,7 @@ int gemm_tc(bool a_mn, bool b_mn, const __nv_bfloat16* a_hi, const __nv_bfloat16
                                reinterpret_cast<uintptr_t>(bias)) & 15) == 0;
     p.c_hi = c_hi; p.c_lo = npass == 3 ? c_lo : nullptr;
     p.gram_n = p.gram_g = p.gram_b = 0;
+    p.bd_stride = 0;
     p.dbg = g_tc_dbg;
     if (c_hi && (!p.vec4 || p.atomic || (reinterpret_cast<uintptr_t>(c_hi) & 7) || (reinterpret_cast<uintptr_t>(c_lo) & 7)))
         return XGGM_ERR_ARG;  // plane emission needs the float4 epilogue
@@ -885,6 +928,7 @@ int gram_tc(const __nv_bfloat16* p_hi, const __nv_bfloat16* p_lo, const __nv_bfl
     p.bias = nullptr; p.resid = nullptr; p.C = S; p.ldc = N;
     p.accumulate = 0; p.atomic = 0; p.vec4 = 0; p.c_hi = nullptr; p.c_lo = nullptr;
     p.gram_n = N; p.gram_g = G; p.gram_b = B;
+    p.bd_stride = 0;
     p.dbg = nullptr;
     const int grid = min(num_sms(), p.tiles_m);
     void* prof = gemm_prof_begin(2.0 * B * N * N * H, st);
@@ -892,6 +936,59 @@ int gram_tc(const __nv_bfloat16* p_hi, const __nv_bfloat16* p_lo, const __nv_bfl
                               : launch_tc<128, 1, false, false>(ah, al, bh, bl, p, grid, st);
     gemm_prof_end(prof, st);
     return rc;
+}
+
+bool adj_tc_supported(int N, int H) { return N >= 1 && N <= tc::BM && H > 0 && H % 8 == 0; }
+long long adj_tc_coef_elems(int B, int N) { return (long long)ceil_div(B, tc::BM / N) * tc::BM * tc::BM; }
+
+// coefficient planes (adj_tc_coef_elems bf16 each) for adj_apply_tc
+int build_blockdiag(const float* adj, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int N, float alpha0,
+                    const float* alpha_dev, float self_w, int trans, cudaStream_t st) {
+    if (B <= 0) return XGGM_OK;
+    XGGM_REQUIRE(adj && hi && N >= 1 && N <= tc::BM);
+    const int G = tc::BM / N;
+    tc::build_blockdiag_kernel<<<dim3(ceil_div(B, G), 4), 128, 0, st>>>(adj, hi, lo, B, N, G, alpha0, alpha_dev, self_w, trans);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+
+// out[b] (=|+=) C[b] @ x[b] for every graph: coefficient planes from build_blockdiag, x as [B*N, H] bf16 planes.
+// out (fp32) and / or out planes; accumulate adds to the previous fp32 out.
+int adj_apply_tc(const __nv_bfloat16* c_hi_in, const __nv_bfloat16* c_lo_in, const __nv_bfloat16* x_hi,
+                 const __nv_bfloat16* x_lo, float* out, __nv_bfloat16* o_hi, __nv_bfloat16* o_lo, int B, int N, int H,
+                 int accumulate, int npass, cudaStream_t st) {
+    if (B <= 0) return XGGM_OK;
+    XGGM_REQUIRE(c_hi_in && x_hi && (out || o_hi) && adj_tc_supported(N, H) && (npass == 1 || (c_lo_in && x_lo)));
+    XGGM_REQUIRE(!accumulate || out);
+    const int G = tc::BM / N, T = ceil_div(B, G);
+    const long long M = (long long)B * N;
+    constexpr int ABN = 192;
+    CUtensorMap ah, al, bh, bl;
+    XGGM_TRY(make_map(&ah, c_hi_in, (long long)T * tc::BM, tc::BM, tc::BM));
+    XGGM_TRY(make_map(&bh, x_hi, M, H, tc::BK));
+    if (npass == 3) {
+        XGGM_TRY(make_map(&al, c_lo_in, (long long)T * tc::BM, tc::BM, tc::BM));
+        XGGM_TRY(make_map(&bl, x_lo, M, H, tc::BK));
+    } else {
+        al = ah;
+        bl = bh;
+    }
+    tc::Params p;
+    p.M = (int)M; p.N = H; p.num_kb = tc::BM / tc::BK;
+    p.tiles_m = T; p.tiles_n = ceil_div(H, ABN); p.splits = 1; p.kb_per_split = p.num_kb;
+    p.bias = nullptr; p.resid = nullptr; p.C = out; p.ldc = H;
+    p.accumulate = accumulate; p.atomic = 0;
+    p.vec4 = (H % 4 == 0) && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    p.c_hi = o_hi; p.c_lo = npass == 3 ? o_lo : nullptr;
+    p.gram_n = p.gram_g = p.gram_b = 0;
+    p.bd_stride = G * N;
+    p.dbg = g_tc_dbg;
+    XGGM_REQUIRE(p.vec4 && (reinterpret_cast<uintptr_t>(o_hi) & 7) == 0 && (reinterpret_cast<uintptr_t>(o_lo) & 7) == 0);
+    const int grid = min(num_sms(), p.tiles_m * p.tiles_n);
+    void* prof = nullptr;  // (not a projection: kept out of the GEMM roofline accounting)
+    (void)prof;
+    return npass == 3 ? launch_tc<ABN, 3, false, true>(ah, al, bh, bl, p, grid, st)
+                      : launch_tc<ABN, 1, false, true>(ah, al, bh, bl, p, grid, st);
 }
 
 // Transposed split of `count` [R,C] fp32 matrices into [C,R] bf16 planes (one launch per 8 matrices).

@@ -472,16 +472,24 @@ adj_regen_bwd_kernel(const float* __restrict__ gadj, const float* __restrict__ S
     }
 }
 
-int adj_regen_bwd(const float* gadj, const float* x, const float* S, const int32_t* amax,
-                  float* gx, float* work, int B, int N, int H, int squash, int accumulate_gx,
-                  cudaStream_t st) {
+// D[b] = dS + dS^T (the symmetric coefficient matrix of gx (+)= D x)
+int adj_regen_bwd_coeffs(const float* gadj, const float* S, const int32_t* amax, float* D, int B, int N, int squash,
+                         cudaStream_t st) {
     if (B <= 0) return XGGM_OK;
     XGGM_REQUIRE(N >= 1 && N <= MAX_NODES);
     const size_t smem = sizeof(float) * (2 * (size_t)N * N + 2 * N);
     if (smem > 48 * 1024)
         XGGM_CUDA_TRY(cudaFuncSetAttribute(adj_regen_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    adj_regen_bwd_kernel<<<B, 256, smem, st>>>(gadj, S, amax, work, N, squash);
+    adj_regen_bwd_kernel<<<B, 256, smem, st>>>(gadj, S, amax, D, N, squash);
     XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+
+int adj_regen_bwd(const float* gadj, const float* x, const float* S, const int32_t* amax,
+                  float* gx, float* work, int B, int N, int H, int squash, int accumulate_gx,
+                  cudaStream_t st) {
+    if (B <= 0) return XGGM_OK;
+    XGGM_TRY(adj_regen_bwd_coeffs(gadj, S, amax, work, B, N, squash, st));
     return adj_apply(work, x, gx, nullptr, nullptr, B, N, H, 1.f, nullptr, 0.f, false, accumulate_gx, st);
 }
 

@@ -103,6 +103,12 @@ def linear(a, w, bias=None, resid=None):
 # ---------------------------------------------------------------------------
 # message passing
 # ---------------------------------------------------------------------------
+def _adj_work(B, N, H, device):
+    """Scratch for the tensor-core message-passing path (node planes + block-diagonal coefficient tiles)."""
+    n = _lib.load().xggm_adj_apply_work_bytes(B, N, H)
+    return torch.empty(max(int(n), 16), device=device, dtype=torch.uint8)
+
+
 class _AdjApply(torch.autograd.Function):
     @staticmethod
     def forward(ctx, adj, x, alpha0, alpha_dev, self_w):
@@ -112,7 +118,8 @@ class _AdjApply(torch.autograd.Function):
             raise RuntimeError(f"xggm_b200.adj_apply: adj {tuple(adj.shape)} vs x {tuple(x.shape)}")
         al = None if alpha_dev is None else f32(alpha_dev, "alpha")
         out = torch.empty_like(x)
-        call("xggm_adj_apply_fwd", ptr(adj), ptr(x), ptr(out), B, N, H, float(alpha0), ptr(al), float(self_w))
+        call("xggm_adj_apply_fwd", ptr(adj), ptr(x), ptr(out), B, N, H, float(alpha0), ptr(al), float(self_w),
+             ptr(_adj_work(B, N, H, x.device)))
         ctx.save_for_backward(adj, x, al)
         ctx.cfg = (float(alpha0), float(self_w))
         return out
@@ -126,7 +133,7 @@ class _AdjApply(torch.autograd.Function):
         gx = torch.empty_like(x)
         graw = torch.empty_like(adj)
         call("xggm_adj_apply_bwd", ptr(adj), ptr(x), ptr(g), ptr(gx), ptr(graw), B, N, H, alpha0, ptr(al),
-             self_w, 0)
+             self_w, 0, ptr(_adj_work(B, N, H, x.device)))
         alpha = alpha0 if al is None else alpha0 + al
         gadj = graw * alpha
         gal = None
@@ -239,7 +246,8 @@ class _AdjRegen(torch.autograd.Function):
         g = f32(g)
         gx = torch.empty_like(x)
         work = torch.empty_like(S)
-        call("xggm_adj_regen_bwd", ptr(g), ptr(x), ptr(S), ptr(amax), ptr(gx), ptr(work), B, N, H, ctx.squash, 0)
+        call("xggm_adj_regen_bwd", ptr(g), ptr(x), ptr(S), ptr(amax), ptr(gx), ptr(work), B, N, H, ctx.squash, 0,
+             ptr(_adj_work(B, N, H, x.device)))
         return gx, None
 
 
