@@ -532,3 +532,39 @@ def test_bf16_engine_within_bf16_budget(gnn):
     assert float(torch.diagonal(ao, dim1=1, dim2=2).abs().max()) == 0.0   # masks stay bit-exact
     assert rel_l2(x.grad.cpu(), x64.grad) < 2 * BF16_TOL
     assert rel_l2(a.grad.cpu(), a64.grad) < 2 * BF16_TOL
+
+
+def test_api_surface_compositions_discriminator_v2_and_mix_generator():
+    """ggm.py:85-97 and :272-323 (never built by the trainers): thin compositions over the library kernels,
+    checked against the same composition written with stock torch ops in fp64."""
+    import torch.nn.functional as F
+    import xggm_b200 as X
+    torch.manual_seed(17)
+    H, B = 128, 5
+    d2 = X.DiscriminatorV2(36 * H).to(dev())
+    g = torch.randn(B, 36, H, device=dev())
+    got = d2(g)
+    m = d2.model.double()
+    ref = m(g.double().view(B, -1))
+    d2.float()
+    _close(got, ref.detach().cpu(), name="DiscriminatorV2")
+
+    mix = X.MixGenerator(H, 2).to(dev()).eval()
+    x = torch.randn(B, H, device=dev())
+    adj = torch.rand(B, 36, 36, device=dev())
+    obj = torch.rand(B, 36, H, device=dev())
+    eps = torch.randn(B, H, device=dev())
+    nodes, loss = mix(x, adj, obj, eps)
+    # stock-torch fp64 restatement of ggm.py:296-323 + gin.py:21-34,68-87 with the same weights
+    p = {k: v.detach().double().cpu() for k, v in mix.state_dict().items()}
+    xd, ad, od, ed = x.double().cpu(), adj.double().cpu(), obj.double().cpu(), eps.double().cpu()
+    mu = F.linear(xd, p["fc1.weight"], p["fc1.bias"]); lv = F.linear(xd, p["fc2.weight"], p["fc2.bias"])
+    z = mu + lv.mul(0.5).exp() * ed
+    h = F.linear(z, p["decoder.0.weight"], p["decoder.0.bias"])
+    h = torch.relu(F.layer_norm(h, (6 * H,), p["decoder.1.weight"], p["decoder.1.bias"]))
+    nf = F.linear(h, p["decoder.3.weight"], p["decoder.3.bias"]).view(-1, 36, H)
+    ref_loss = F.binary_cross_entropy_with_logits(nf, od) * 768 - 0.5 * torch.sum(1 + lv - mu.pow(2) - lv.exp())
+    for l in range(2):
+        nf = O.gin(nf, ad, p, f"gnn_layers.{l}.", 1, None)
+    _close(nodes, nf, 2 * TOL, "MixGenerator nodes")
+    assert abs(float(loss) - float(ref_loss)) < 1e-4 * abs(float(ref_loss))

@@ -10,8 +10,8 @@ from .glue import (add_edge_noise, add_edge_noise_v2, add_feature_noise,  # noqa
 from ._lib import get_precision, set_precision  # noqa: F401
 from .graphs import GraphedStep  # noqa: F401
 from .model import XGGMHeads  # noqa: F401
-from .nn import (GAT, GCN, GIN, Discriminator, EdgeGenerator, GATConv, GATGenerator,  # noqa: F401
-                 GCNConv, GCNGenerator, GCNPlainEncoder, GeLU, GINConv, GINGenerator,
-                 GinPlainEncoder, NodeGenerator)
+from .nn import (GAT, GCN, GIN, Discriminator, DiscriminatorV2, EdgeGenerator, GATConv,  # noqa: F401
+                 GATGenerator, GCNConv, GCNGenerator, GCNPlainEncoder, GeLU, GINConv, GINGenerator,
+                 GinPlainEncoder, MixGenerator, NodeGenerator)
 
 __version__ = "0.1.0"

@@ -286,3 +286,63 @@ class Discriminator(nn.Module):
         m = self.model
         h = _head_forward(m, x.reshape(x.shape[0], -1))
         return XF.linear(h, m[3].weight, m[3].bias)
+
+
+class DiscriminatorV2(nn.Module):
+    """ggm.py:85-97: Linear -> LeakyReLU(0.2) -> Linear -> LeakyReLU(0.2) -> Linear on the flattened graph.
+    (Never built by the shipped trainers; the projections run on the library's GEMM engine, the two
+    LeakyReLUs are plain elementwise torch ops.)"""
+
+    def __init__(self, hidden_dim):
+        super().__init__()
+        self.model = nn.Sequential(nn.Linear(hidden_dim, 512), nn.LeakyReLU(0.2), nn.Linear(512, 256),
+                                   nn.LeakyReLU(0.2), nn.Linear(256, 1))
+
+    def forward(self, x):
+        m = self.model
+        h = m[1](XF.linear(x.reshape(x.shape[0], -1), m[0].weight, m[0].bias))
+        h = m[3](XF.linear(h, m[2].weight, m[2].bias))
+        return XF.linear(h, m[4].weight, m[4].bias)
+
+
+class MixGenerator(nn.Module):
+    """ggm.py:272-323: VAE-style node sampler (fc1/fc2 -> reparameterise -> decoder to 36 nodes) followed by
+    GIN layers; returns (node_feats, rec_loss + kl_div_loss).  Never built by the shipped trainers.  Linear
+    layers, LayerNorm and the GIN layers run on the library's kernels; the reparameterisation and the two
+    scalar losses are a handful of elementwise torch ops."""
+
+    def __init__(self, hidden_dim, n_layers, dropout=0.5):
+        super().__init__()
+        self.hidden_dim = hidden_dim
+        self.n_layers = n_layers
+        self.fc1 = nn.Linear(hidden_dim, hidden_dim)
+        self.fc2 = nn.Linear(hidden_dim, hidden_dim)
+        self.decoder = nn.Sequential(nn.Linear(hidden_dim, 6 * hidden_dim), nn.LayerNorm(6 * hidden_dim),
+                                     nn.ReLU(inplace=True), nn.Linear(6 * hidden_dim, 36 * hidden_dim))
+        self.gnn_layers = nn.ModuleList(
+            GIN(hidden_dim, [hidden_dim, hidden_dim], 1, dropout=dropout) for _ in range(n_layers))
+
+    def forward(self, x, adj, obj_feats, eps=None):
+        node_feats, kl_div_loss = self.generate_node(x, eps)
+        rec_loss = torch.nn.functional.binary_cross_entropy_with_logits(node_feats, obj_feats) * 768
+        for layer in range(self.n_layers):
+            node_feats = self.gnn_layers[layer](node_feats, adj)
+        return node_feats, rec_loss + kl_div_loss
+
+    def generate_node(self, x, eps=None):
+        mu = XF.linear(x, self.fc1.weight, self.fc1.bias)
+        log_var = XF.linear(x, self.fc2.weight, self.fc2.bias)
+        z = self.re_parameterize(mu, log_var, eps)
+        d = self.decoder
+        h = XF.linear(z, d[0].weight, d[0].bias)
+        h = torch.relu(XF.layer_norm(h, d[1].weight, d[1].bias, d[1].eps))
+        z = XF.linear(h, d[3].weight, d[3].bias).view(-1, 36, self.hidden_dim)
+        kl_div_loss = -0.5 * torch.sum(1 + log_var - mu.pow(2) - log_var.exp())
+        return z, kl_div_loss
+
+    @staticmethod
+    def re_parameterize(mu, log_var, eps=None):
+        std = log_var.mul(0.5).exp()
+        if eps is None:
+            eps = torch.randn_like(std)
+        return mu + std * eps
