@@ -88,27 +88,86 @@ __device__ __forceinline__ void flush_columns(const float (&acc)[NV * 4], float*
 }
 
 // ================================================================== fast kernels
+// Per-warp two-stage row prefetch: lane 0 launches 1-D bulk async copies (cp.async.bulk + mbarrier
+// complete_tx) of the NEXT row of up to NT input tensors into this warp's shared-memory stage while
+// the warp computes on the current one, so a warp never sits on a DRAM round trip between rows.
+template <int NV, int NT>
+struct RowPrefetch {
+    static constexpr int H = NV * 128;
+    static constexpr int STAGE = NT * H;                          // floats per stage
+    static constexpr int WARP_FLOATS = 2 * STAGE;
+    static constexpr size_t SMEM = sizeof(float) * ROW_WARPS * WARP_FLOATS + sizeof(uint64_t) * ROW_WARPS * 2;
+    float* buf;
+    uint64_t* bar;
+    __device__ __forceinline__ void init(float* sm, int warp, int lane) {
+        buf = sm + (size_t)warp * WARP_FLOATS;
+        bar = reinterpret_cast<uint64_t*>(sm + (size_t)ROW_WARPS * WARP_FLOATS) + warp * 2;
+        if (lane == 0) {
+            ptx::mbar_init(&bar[0], 1);
+            ptx::mbar_init(&bar[1], 1);
+            ptx::fence_barrier_init();
+        }
+        __syncwarp();
+    }
+    // src[t] = row pointer of tensor t (null -> skipped)
+    __device__ __forceinline__ void issue(int stage, const float* const (&src)[NT], int lane) {
+        if (lane == 0) {
+            uint32_t bytes = 0;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) bytes += src[t] ? H * 4 : 0;
+            ptx::fence_proxy_async();   // the stage was last read through the generic proxy
+            ptx::mbar_expect_tx(&bar[stage], bytes);
+#pragma unroll
+            for (int t = 0; t < NT; ++t)
+                if (src[t]) ptx::bulk_g2s(buf + stage * STAGE + t * H, src[t], H * 4, &bar[stage]);
+        }
+    }
+    __device__ __forceinline__ void wait(int stage, uint32_t phase) { ptx::mbar_wait(&bar[stage], phase); }
+    __device__ __forceinline__ void read(int stage, int t, int lane, float (&v)[NV * 4]) {
+        load_row<NV>(buf + stage * STAGE + t * H, lane, v);
+    }
+};
+
 template <int NV>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 ln_fwd_fast(const float* __restrict__ u, const float* __restrict__ gamma, const float* __restrict__ beta,
             float* __restrict__ h, float* __restrict__ xhat, float* __restrict__ rstd_out,
             bf16* __restrict__ hi, bf16* __restrict__ lo, int M, float eps) {
     constexpr int H = NV * 128;
-    const int lane = threadIdx.x & 31;
-    const int wid = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5), nw = gridDim.x * ROW_WARPS;
-    float g[NV * 4], b[NV * 4];
-    load_row<NV>(gamma, lane, g);
-    load_row<NV>(beta, lane, b);
-    for (int r = wid; r < M; r += nw) {
+    extern __shared__ __align__(16) float sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wid = blockIdx.x * ROW_WARPS + warp, nw = gridDim.x * ROW_WARPS;
+    RowPrefetch<NV, 1> pf;
+    pf.init(sm, warp, lane);
+    if (wid < M) {
+        const float* src[1] = {u + (size_t)wid * H};
+        pf.issue(0, src, lane);
+    }
+    int it = 0;
+    for (int r = wid; r < M; r += nw, ++it) {
+        const int stage = it & 1;
+        if (r + nw < M) {
+            const float* src[1] = {u + (size_t)(r + nw) * H};
+            pf.issue(stage ^ 1, src, lane);
+        }
+        pf.wait(stage, (it >> 1) & 1);
         float v[NV * 4];
-        load_row<NV>(u + (size_t)r * H, lane, v);
+        pf.read(stage, 0, lane, v);
+        __syncwarp();
         float mean, rstd;
         row_stats<NV>(v, 1.0f / (float)H, eps, mean, rstd);
 #pragma unroll
         for (int i = 0; i < NV * 4; ++i) v[i] = (v[i] - mean) * rstd;
         if (xhat) store_row<NV>(xhat + (size_t)r * H, lane, v);
 #pragma unroll
-        for (int i = 0; i < NV * 4; ++i) v[i] = fmaf(v[i], g[i], b[i]);
+        for (int i = 0; i < NV; ++i) {
+            const float4 g = *reinterpret_cast<const float4*>(gamma + 128 * i + 4 * lane);
+            const float4 b = *reinterpret_cast<const float4*>(beta + 128 * i + 4 * lane);
+            v[4 * i] = fmaf(v[4 * i], g.x, b.x);
+            v[4 * i + 1] = fmaf(v[4 * i + 1], g.y, b.y);
+            v[4 * i + 2] = fmaf(v[4 * i + 2], g.z, b.z);
+            v[4 * i + 3] = fmaf(v[4 * i + 3], g.w, b.w);
+        }
         store_row<NV>(h + (size_t)r * H, lane, v);
         if (hi) store_planes<NV>(hi, lo, (size_t)r * H, lane, v);
         if (lane == 0 && rstd_out) rstd_out[r] = rstd;
@@ -121,17 +180,32 @@ ln_bwd_fast(const float* __restrict__ gh, const float* __restrict__ xhat, const 
             const float* __restrict__ gamma, float* __restrict__ gu, float* __restrict__ ggamma,
             float* __restrict__ gbeta, bf16* __restrict__ hi, bf16* __restrict__ lo, int M) {
     constexpr int H = NV * 128;
-    extern __shared__ float sm[];
-    const int lane = threadIdx.x & 31;
-    const int wid = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5), nw = gridDim.x * ROW_WARPS;
+    extern __shared__ __align__(16) float sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wid = blockIdx.x * ROW_WARPS + warp, nw = gridDim.x * ROW_WARPS;
+    RowPrefetch<NV, 2> pf;
+    pf.init(sm, warp, lane);
+    if (wid < M) {
+        const float* src[2] = {gh + (size_t)wid * H, xhat + (size_t)wid * H};
+        pf.issue(0, src, lane);
+    }
     float gam[NV * 4], ag[NV * 4], ab[NV * 4];
     load_row<NV>(gamma, lane, gam);
 #pragma unroll
     for (int i = 0; i < NV * 4; ++i) { ag[i] = 0.f; ab[i] = 0.f; }
-    for (int r = wid; r < M; r += nw) {
+    int it = 0;
+    for (int r = wid; r < M; r += nw, ++it) {
+        const int stage = it & 1;
+        if (r + nw < M) {
+            const float* src[2] = {gh + (size_t)(r + nw) * H, xhat + (size_t)(r + nw) * H};
+            pf.issue(stage ^ 1, src, lane);
+        }
+        const float rs = rstd[r];
+        pf.wait(stage, (it >> 1) & 1);
         float g[NV * 4], xh[NV * 4];
-        load_row<NV>(gh + (size_t)r * H, lane, g);
-        load_row<NV>(xhat + (size_t)r * H, lane, xh);
+        pf.read(stage, 0, lane, g);
+        pf.read(stage, 1, lane, xh);
+        __syncwarp();
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < NV * 4; ++i) {
@@ -140,7 +214,6 @@ ln_bwd_fast(const float* __restrict__ gh, const float* __restrict__ xhat, const 
             s2 = fmaf(d, xh[i], s2);
         }
         const float c1 = warp_sum(s1) / (float)H, c2 = warp_sum(s2) / (float)H;
-        const float rs = rstd[r];
 #pragma unroll
         for (int i = 0; i < NV * 4; ++i) {
             ag[i] = fmaf(g[i], xh[i], ag[i]);
@@ -187,23 +260,43 @@ gld_fwd_fast(const float* __restrict__ z, const float* __restrict__ gamma, const
              float* __restrict__ mean_out, float* __restrict__ rstd_out, bf16* __restrict__ hi,
              bf16* __restrict__ lo, int M, float eps, int accumulate) {
     constexpr int H = NV * 128;
-    const int lane = threadIdx.x & 31;
+    extern __shared__ __align__(16) float sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t dstream = drop_stream(drop);
     const float scale = drop.scale;
-    const int wid = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5), nw = gridDim.x * ROW_WARPS;
-    float g[NV * 4], b[NV * 4];
-    load_row<NV>(gamma, lane, g);
-    load_row<NV>(beta, lane, b);
-    for (int r = wid; r < M; r += nw) {
+    const int wid = blockIdx.x * ROW_WARPS + warp, nw = gridDim.x * ROW_WARPS;
+    RowPrefetch<NV, 2> pf;
+    pf.init(sm, warp, lane);
+    if (wid < M) {
+        const float* src[2] = {z + (size_t)wid * H, accumulate ? out + (size_t)wid * H : nullptr};
+        pf.issue(0, src, lane);
+    }
+    int it = 0;
+    for (int r = wid; r < M; r += nw, ++it) {
+        const int stage = it & 1;
         const size_t ro = (size_t)r * H;
-        float v[NV * 4];
-        load_row<NV>(z + ro, lane, v);
+        if (r + nw < M) {
+            const float* src[2] = {z + (size_t)(r + nw) * H, accumulate ? out + (size_t)(r + nw) * H : nullptr};
+            pf.issue(stage ^ 1, src, lane);
+        }
+        pf.wait(stage, (it >> 1) & 1);
+        float v[NV * 4], o[NV * 4];
+        pf.read(stage, 0, lane, v);
+        if (accumulate) pf.read(stage, 1, lane, o);
+        __syncwarp();   // every lane has drained the stage before lane 0 refills it next iteration
 #pragma unroll
         for (int i = 0; i < NV * 4; ++i) v[i] = gelu_erf(v[i]);
         float mean, rstd;
         row_stats<NV>(v, 1.0f / (float)H, eps, mean, rstd);
 #pragma unroll
-        for (int i = 0; i < NV * 4; ++i) v[i] = fmaf((v[i] - mean) * rstd, g[i], b[i]);
+        for (int i = 0; i < NV; ++i) {
+            const float4 g = *reinterpret_cast<const float4*>(gamma + 128 * i + 4 * lane);
+            const float4 b = *reinterpret_cast<const float4*>(beta + 128 * i + 4 * lane);
+            v[4 * i] = fmaf((v[4 * i] - mean) * rstd, g.x, b.x);
+            v[4 * i + 1] = fmaf((v[4 * i + 1] - mean) * rstd, g.y, b.y);
+            v[4 * i + 2] = fmaf((v[4 * i + 2] - mean) * rstd, g.z, b.z);
+            v[4 * i + 3] = fmaf((v[4 * i + 3] - mean) * rstd, g.w, b.w);
+        }
         if (drop.mode) {
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
@@ -214,8 +307,6 @@ gld_fwd_fast(const float* __restrict__ z, const float* __restrict__ gamma, const
             }
         }
         if (accumulate) {
-            float o[NV * 4];
-            load_row<NV>(out + ro, lane, o);
 #pragma unroll
             for (int i = 0; i < NV * 4; ++i) v[i] += o[i];
         }
@@ -235,19 +326,34 @@ gld_bwd_fast(const float* __restrict__ gout, const float* __restrict__ z, const 
              float* __restrict__ gz, float* __restrict__ ggamma, float* __restrict__ gbeta,
              float* __restrict__ gbias, bf16* __restrict__ hi, bf16* __restrict__ lo, int M) {
     constexpr int H = NV * 128;
-    extern __shared__ float sm[];
-    const int lane = threadIdx.x & 31;
+    extern __shared__ __align__(16) float sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t dstream = drop_stream(drop);
     const float scale = drop.scale;
-    const int wid = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5), nw = gridDim.x * ROW_WARPS;
+    const int wid = blockIdx.x * ROW_WARPS + warp, nw = gridDim.x * ROW_WARPS;
+    RowPrefetch<NV, 2> pf;
+    pf.init(sm, warp, lane);
+    if (wid < M) {
+        const float* src[2] = {gout + (size_t)wid * H, z + (size_t)wid * H};
+        pf.issue(0, src, lane);
+    }
     float ag[NV * 4], ab[NV * 4], az[NV * 4];
 #pragma unroll
     for (int i = 0; i < NV * 4; ++i) { ag[i] = 0.f; ab[i] = 0.f; az[i] = 0.f; }
-    for (int r = wid; r < M; r += nw) {
+    int it = 0;
+    for (int r = wid; r < M; r += nw, ++it) {
+        const int stage = it & 1;
         const size_t ro = (size_t)r * H;
+        if (r + nw < M) {
+            const float* src[2] = {gout + (size_t)(r + nw) * H, z + (size_t)(r + nw) * H};
+            pf.issue(stage ^ 1, src, lane);
+        }
+        const float mu = mean[r], rs = rstd[r];
+        pf.wait(stage, (it >> 1) & 1);
         float gy[NV * 4], zv[NV * 4], yh[NV * 4];
-        load_row<NV>(gout + ro, lane, gy);
-        load_row<NV>(z + ro, lane, zv);
+        pf.read(stage, 0, lane, gy);
+        pf.read(stage, 1, lane, zv);
+        __syncwarp();
         if (drop.mode) {
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
@@ -257,7 +363,6 @@ gld_bwd_fast(const float* __restrict__ gout, const float* __restrict__ z, const 
                 for (int j = 0; j < 4; ++j) gy[4 * i + j] = m[j] ? gy[4 * i + j] * scale : 0.f;
             }
         }
-        const float mu = mean[r], rs = rstd[r];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
@@ -287,6 +392,7 @@ gld_bwd_fast(const float* __restrict__ gout, const float* __restrict__ z, const 
         if (gz) store_row<NV>(gz + ro, lane, gy);
         if (hi) store_planes<NV>(hi, lo, ro, lane, gy);
     }
+    // the prefetch stages are idle now: reuse their shared memory for the column reduction
     flush_columns<NV>(ag, ggamma, sm);
     flush_columns<NV>(ab, gbeta, sm);
     if (gbias) flush_columns<NV>(az, gbias, sm);
@@ -490,16 +596,16 @@ static inline bool fast_ok(int H, const void* a, const void* b = nullptr, const 
     auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     return H % 128 == 0 && H >= 128 && H <= 1024 && al(a) && al(b) && al(c);
 }
-#define XGGM_ROW_DISPATCH(H, CALL)          \
+#define XGGM_ROW_DISPATCH(H, ...)           \
     switch ((H) / 128) {                    \
-        case 1: { constexpr int NV = 1; CALL; } break; \
-        case 2: { constexpr int NV = 2; CALL; } break; \
-        case 3: { constexpr int NV = 3; CALL; } break; \
-        case 4: { constexpr int NV = 4; CALL; } break; \
-        case 5: { constexpr int NV = 5; CALL; } break; \
-        case 6: { constexpr int NV = 6; CALL; } break; \
-        case 7: { constexpr int NV = 7; CALL; } break; \
-        default: { constexpr int NV = 8; CALL; } break; \
+        case 1: { constexpr int NV = 1; __VA_ARGS__; } break; \
+        case 2: { constexpr int NV = 2; __VA_ARGS__; } break; \
+        case 3: { constexpr int NV = 3; __VA_ARGS__; } break; \
+        case 4: { constexpr int NV = 4; __VA_ARGS__; } break; \
+        case 5: { constexpr int NV = 5; __VA_ARGS__; } break; \
+        case 6: { constexpr int NV = 6; __VA_ARGS__; } break; \
+        case 7: { constexpr int NV = 7; __VA_ARGS__; } break; \
+        default: { constexpr int NV = 8; __VA_ARGS__; } break; \
     }
 
 template <typename K>
@@ -516,7 +622,12 @@ int layernorm_fwd(const float* u, const float* gamma, const float* beta, float* 
                   bf16* hi, bf16* lo, int M, int H, float eps, cudaStream_t st) {
     if (M <= 0) return XGGM_OK;
     if (fast_ok(H, u, h, xhat) && fast_ok(H, gamma, beta, hi) && fast_ok(H, lo)) {
-        XGGM_ROW_DISPATCH(H, (ln_fwd_fast<NV><<<fast_grid(M), ROW_WARPS * 32, 0, st>>>(u, gamma, beta, h, xhat, rstd, hi, lo, M, eps)));
+        XGGM_ROW_DISPATCH(H, {
+            constexpr size_t smem = RowPrefetch<NV, 1>::SMEM;
+            static bool attr = false;
+            if (!attr) { XGGM_CUDA_TRY(cudaFuncSetAttribute(ln_fwd_fast<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+            ln_fwd_fast<NV><<<fast_grid(M, 3), ROW_WARPS * 32, smem, st>>>(u, gamma, beta, h, xhat, rstd, hi, lo, M, eps);
+        });
     } else {
         ln_fwd_gen<<<gen_grid(M), GEN_WARPS * 32, 0, st>>>(u, gamma, beta, h, xhat, rstd, hi, lo, M, H, eps);
     }
@@ -529,8 +640,12 @@ int layernorm_bwd(const float* gh, const float* xhat, const float* rstd, const f
                   float* ggamma, float* gbeta, bf16* hi, bf16* lo, int M, int H, cudaStream_t st) {
     if (M <= 0) return XGGM_OK;
     if (fast_ok(H, gh, xhat, gu) && fast_ok(H, gamma, hi, lo)) {
-        const size_t smem = sizeof(float) * ROW_WARPS * H;
-        XGGM_ROW_DISPATCH(H, (ln_bwd_fast<NV><<<fast_grid(M), ROW_WARPS * 32, smem, st>>>(gh, xhat, rstd, gamma, gu, ggamma, gbeta, hi, lo, M)));
+        XGGM_ROW_DISPATCH(H, {
+            constexpr size_t smem = RowPrefetch<NV, 2>::SMEM;   // (>= the ROW_WARPS*H floats flush_columns needs)
+            static bool attr = false;
+            if (!attr) { XGGM_CUDA_TRY(cudaFuncSetAttribute(ln_bwd_fast<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+            ln_bwd_fast<NV><<<fast_grid(M, 1), ROW_WARPS * 32, smem, st>>>(gh, xhat, rstd, gamma, gu, ggamma, gbeta, hi, lo, M);
+        });
     } else {
         size_t smem;
         XGGM_TRY(gen_smem(ln_bwd_gen, H, smem));
@@ -545,7 +660,12 @@ int gelu_ln_drop_fwd(const float* z, const float* gamma, const float* beta, cons
                      int accumulate, cudaStream_t st) {
     if (M <= 0) return XGGM_OK;
     if (fast_ok(H, z, out, hi) && fast_ok(H, gamma, beta, lo) && (reinterpret_cast<uintptr_t>(drop.keep) & 3) == 0) {
-        XGGM_ROW_DISPATCH(H, (gld_fwd_fast<NV><<<fast_grid(M), ROW_WARPS * 32, 0, st>>>(z, gamma, beta, drop, out, mean, rstd, hi, lo, M, eps, accumulate)));
+        XGGM_ROW_DISPATCH(H, {
+            constexpr size_t smem = RowPrefetch<NV, 2>::SMEM;
+            static bool attr = false;
+            if (!attr) { XGGM_CUDA_TRY(cudaFuncSetAttribute(gld_fwd_fast<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+            gld_fwd_fast<NV><<<fast_grid(M), ROW_WARPS * 32, smem, st>>>(z, gamma, beta, drop, out, mean, rstd, hi, lo, M, eps, accumulate);
+        });
     } else {
         gld_fwd_gen<<<gen_grid(M), GEN_WARPS * 32, 0, st>>>(z, gamma, beta, drop, out, mean, rstd, hi, lo, M, H, eps, accumulate);
     }
@@ -559,8 +679,12 @@ int gelu_ln_drop_bwd(const float* gout, const float* z, const float* mean, const
                      bf16* hi, bf16* lo, int M, int H, cudaStream_t st) {
     if (M <= 0) return XGGM_OK;
     if (fast_ok(H, gout, z, gz) && fast_ok(H, gamma, hi, lo) && (reinterpret_cast<uintptr_t>(drop.keep) & 3) == 0) {
-        const size_t smem = sizeof(float) * ROW_WARPS * H;
-        XGGM_ROW_DISPATCH(H, (gld_bwd_fast<NV><<<fast_grid(M, 1), ROW_WARPS * 32, smem, st>>>(gout, z, mean, rstd, gamma, drop, gz, ggamma, gbeta, gbias, hi, lo, M)));
+        XGGM_ROW_DISPATCH(H, {
+            constexpr size_t smem = RowPrefetch<NV, 2>::SMEM;   // (>= the ROW_WARPS*H floats flush_columns needs)
+            static bool attr = false;
+            if (!attr) { XGGM_CUDA_TRY(cudaFuncSetAttribute(gld_bwd_fast<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+            gld_bwd_fast<NV><<<fast_grid(M, 1), ROW_WARPS * 32, smem, st>>>(gout, z, mean, rstd, gamma, drop, gz, ggamma, gbeta, gbias, hi, lo, M);
+        });
     } else {
         size_t smem;
         XGGM_TRY(gen_smem(gld_bwd_gen, H, smem));
