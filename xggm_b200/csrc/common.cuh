@@ -108,6 +108,27 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
     const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
     return cdf + x * pdf;
 }
+// Normal CDF and PDF for the GeLU of the hot row kernels: Phi(x) = 0.5 erfc(-x/sqrt2) through the
+// Abramowitz-Stegun 7.1.26 rational form (|error| <= 1.5e-7 in erf, i.e. the same 1e-7 class as
+// erff's own 2-ulp error), sharing one exp(-x^2/2) with the PDF: ~14 instructions instead of ~33
+// for erff + expf.  The tail is formed without cancellation (0.5*poly*e on the small side).
+__device__ __forceinline__ void normal_cdf_pdf(float x, float& cdf, float& pdf) {
+    const float u = fabsf(x) * 0.70710678118654752440f;
+    const float e = __expf(-u * u);
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, u, 1.0f));
+    float p = fmaf(t, 1.061405429f, -1.453152027f);
+    p = fmaf(t, p, 1.421413741f);
+    p = fmaf(t, p, -0.284496736f);
+    p = fmaf(t, p, 0.254829592f);
+    const float half_tail = 0.5f * (p * t) * e;          // 0.5 * erfc(|x|/sqrt2)
+    cdf = x >= 0.f ? 1.0f - half_tail : half_tail;
+    pdf = 0.39894228040143267794f * e;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+    float c, p;
+    normal_cdf_pdf(x, c, p);
+    return x * c;
+}
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // ---- Philox4x32-10 counter RNG (dropout / noise without mask tensors) --------

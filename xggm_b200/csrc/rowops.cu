@@ -285,7 +285,7 @@ gld_fwd_fast(const float* __restrict__ z, const float* __restrict__ gamma, const
         if (accumulate) pf.read(stage, 1, lane, o);
         __syncwarp();   // every lane has drained the stage before lane 0 refills it next iteration
 #pragma unroll
-        for (int i = 0; i < NV * 4; ++i) v[i] = gelu_erf(v[i]);
+        for (int i = 0; i < NV * 4; ++i) v[i] = gelu_fast(v[i]);
         float mean, rstd;
         row_stats<NV>(v, 1.0f / (float)H, eps, mean, rstd);
 #pragma unroll
@@ -372,9 +372,9 @@ gld_bwd_fast(const float* __restrict__ gout, const float* __restrict__ z, const 
             for (int j = 0; j < 4; ++j) {
                 const int e = 4 * i + j;
                 // one erf per element: cdf feeds both gelu(z) and its derivative
-                const float cdf = 0.5f * (1.0f + erff(zv[e] * 0.70710678118654752440f));
+                float cdf, pdf;
+                normal_cdf_pdf(zv[e], cdf, pdf);
                 yh[e] = (zv[e] * cdf - mu) * rs;
-                const float pdf = 0.39894228040143267794f * expf(-0.5f * zv[e] * zv[e]);
                 zv[e] = cdf + zv[e] * pdf;  // gelu'(z)
                 ag[e] = fmaf(gy[e], yh[e], ag[e]);
                 ab[e] += gy[e];
