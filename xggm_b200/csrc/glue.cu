@@ -105,10 +105,32 @@ __global__ void feat_noise_kernel(const float* __restrict__ f, const float* __re
     noisy[e] = fv + n;
     target[e] = -n / sigma2;
 }
+// float4 path: grid (chunks of one graph, B); no 64-bit division per element
+__global__ void __launch_bounds__(256)
+feat_noise_vec_kernel(const float* __restrict__ f, const float* __restrict__ randn, float sigma, float sigma2,
+                      float* __restrict__ noisy, float* __restrict__ target, int NH4, int H, int bcast) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // float4 index inside graph b
+    if (i >= NH4) return;
+    const int b = blockIdx.y;
+    const size_t o = (size_t)b * NH4 + i;
+    const float4 r = reinterpret_cast<const float4*>(randn)[o];
+    const float4 fv = bcast ? *reinterpret_cast<const float4*>(f + (size_t)b * H + (4 * i) % H)
+                            : reinterpret_cast<const float4*>(f)[o];
+    const float4 n = make_float4(r.x * sigma, r.y * sigma, r.z * sigma, r.w * sigma);
+    reinterpret_cast<float4*>(noisy)[o] = make_float4(fv.x + n.x, fv.y + n.y, fv.z + n.z, fv.w + n.w);
+    reinterpret_cast<float4*>(target)[o] = make_float4(-n.x / sigma2, -n.y / sigma2, -n.z / sigma2, -n.w / sigma2);
+}
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 int feat_noise(const float* f, const float* randn, float sigma, float sigma2, float* noisy,
                float* target, int B, int N, int H, int bcast, cudaStream_t st) {
     const long long total = (long long)B * N * H;
     if (total <= 0) return XGGM_OK;
+    if (H % 4 == 0 && al16(f) && al16(randn) && al16(noisy) && al16(target) && (long long)N * H / 4 < (1LL << 30)) {
+        const int NH4 = N * H / 4;
+        feat_noise_vec_kernel<<<dim3(ceil_div(NH4, 256), B), 256, 0, st>>>(f, randn, sigma, sigma2, noisy, target, NH4, H, bcast);
+        XGGM_LAUNCH_CHECK();
+        return XGGM_OK;
+    }
     feat_noise_kernel<<<grid1d(total), 256, 0, st>>>(f, randn, sigma, sigma2, noisy, target, total, N, H, bcast);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
@@ -168,10 +190,27 @@ int score_mse_fwd(const float* s, const float* t, float sigma, float* loss, long
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
+__global__ void __launch_bounds__(256)
+score_mse_bwd_vec_kernel(const float4* __restrict__ s, const float4* __restrict__ t, const float* __restrict__ gloss,
+                         float coef, float4* __restrict__ gs, long long n4) {
+    const float c = gloss[0] * coef;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 a = s[i], b = t[i];
+        gs[i] = make_float4(c * (a.x - b.x), c * (a.y - b.y), c * (a.z - b.z), c * (a.w - b.w));
+    }
+}
 int score_mse_bwd(const float* s, const float* t, const float* gloss, float sigma, float* gs,
                   long long n, cudaStream_t st) {
     if (n <= 0) return XGGM_OK;
     const float coef = sigma * sigma / (float)n;
+    if (n % 4 == 0 && al16(s) && al16(t) && al16(gs)) {
+        const long long n4 = n / 4;
+        const int grid = (int)min((long long)148 * 16, (n4 + 255) / 256);
+        score_mse_bwd_vec_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(s), reinterpret_cast<const float4*>(t), gloss, coef,
+                                                       reinterpret_cast<float4*>(gs), n4);
+        XGGM_LAUNCH_CHECK();
+        return XGGM_OK;
+    }
     score_mse_bwd_kernel<<<grid1d(n), 256, 0, st>>>(s, t, gloss, coef, gs, n);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
@@ -247,9 +286,116 @@ sym_kl_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
         }
     }
 }
+// Fast path (C % 128 == 0, C <= 1024): both rows live in registers (lane l holds the float4s at columns
+// 128 i + 4 l), every exponential is evaluated once, p = e / sum and log p = (v - max) - log(sum).
+template <int NV>
+__device__ __forceinline__ void kl_row_load(const float* __restrict__ p, int lane, float (&d)[NV * 4], float (&e)[NV * 4],
+                                            float& inv_s, float& lse) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float4 t = *reinterpret_cast<const float4*>(p + 128 * i + 4 * lane);
+        d[4 * i] = t.x; d[4 * i + 1] = t.y; d[4 * i + 2] = t.z; d[4 * i + 3] = t.w;
+    }
+    float mx = d[0];
+#pragma unroll
+    for (int i = 1; i < NV * 4; ++i) mx = fmaxf(mx, d[i]);
+    mx = warp_max(mx);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV * 4; ++i) {
+        d[i] -= mx;
+        e[i] = expf(d[i]);
+        s += e[i];
+    }
+    s = warp_sum(s);
+    inv_s = 1.0f / s;
+    lse = logf(s);
+}
+
+template <int NV, bool BWD>
+__global__ void __launch_bounds__(256)
+sym_kl_fast_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ loss,
+                   const float* __restrict__ gloss, float* __restrict__ gx, float* __restrict__ gy, int R,
+                   float inv_count) {
+    constexpr int C = NV * 128;
+    __shared__ float part[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float g = BWD ? gloss[0] * inv_count : 0.f;
+    float acc = 0.f;
+    for (int r = blockIdx.x * 8 + warp; r < R; r += gridDim.x * 8) {
+        float dx[NV * 4], ex[NV * 4], dy[NV * 4], ey[NV * 4];
+        float isx, lsx, isy, lsy;
+        kl_row_load<NV>(x + (size_t)r * C, lane, dx, ex, isx, lsx);
+        kl_row_load<NV>(y + (size_t)r * C, lane, dy, ey, isy, lsy);
+        if (!BWD) {
+#pragma unroll
+            for (int i = 0; i < NV * 4; ++i) {
+                const float lpx = dx[i] - lsx, lpy = dy[i] - lsy;
+                acc += (ey[i] * isy - ex[i] * isx) * (lpy - lpx);   // py (lpy-lpx) + px (lpx-lpy)
+            }
+        } else {
+            float ax = 0.f, ay = 0.f;
+#pragma unroll
+            for (int i = 0; i < NV * 4; ++i) {
+                ex[i] *= isx;   // px
+                ey[i] *= isy;   // py
+                dx[i] = (dy[i] - lsy) - (dx[i] - lsx);   // e = lpy - lpx
+                ax = fmaf(ex[i], dx[i], ax);
+                ay = fmaf(ey[i], dx[i], ay);
+            }
+            ax = warp_sum(ax);
+            ay = warp_sum(ay);
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                float ox[4], oy[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = 4 * i + j;
+                    const float d = ey[k] - ex[k];
+                    ox[j] = g * (ex[k] * (ax - dx[k]) - d);
+                    oy[j] = g * (ey[k] * (dx[k] - ay) + d);
+                }
+                const size_t o = (size_t)r * C + 128 * i + 4 * lane;
+                if (gx) *reinterpret_cast<float4*>(gx + o) = make_float4(ox[0], ox[1], ox[2], ox[3]);
+                if (gy) *reinterpret_cast<float4*>(gy + o) = make_float4(oy[0], oy[1], oy[2], oy[3]);
+            }
+        }
+    }
+    if (!BWD) {
+        acc = warp_sum(acc);
+        if (lane == 0) part[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float v = threadIdx.x < 8 ? part[threadIdx.x] : 0.f;
+            v = warp_sum(v);
+            if (threadIdx.x == 0) atomicAdd(loss, v * inv_count);
+        }
+    }
+}
+#define XGGM_KL_DISPATCH(C, ...)            \
+    switch ((C) / 128) {                    \
+        case 1: { constexpr int NV = 1; __VA_ARGS__; } break; \
+        case 2: { constexpr int NV = 2; __VA_ARGS__; } break; \
+        case 3: { constexpr int NV = 3; __VA_ARGS__; } break; \
+        case 4: { constexpr int NV = 4; __VA_ARGS__; } break; \
+        case 5: { constexpr int NV = 5; __VA_ARGS__; } break; \
+        case 6: { constexpr int NV = 6; __VA_ARGS__; } break; \
+        case 7: { constexpr int NV = 7; __VA_ARGS__; } break; \
+        default: { constexpr int NV = 8; __VA_ARGS__; } break; \
+    }
+static inline bool kl_fast_ok(int C, const void* a, const void* b, const void* c = nullptr, const void* d = nullptr) {
+    return C % 128 == 0 && C >= 128 && C <= 1024 && al16(a) && al16(b) && al16(c) && al16(d);
+}
+
 int sym_kl_fwd(const float* x, const float* y, float* loss, int R, int C, cudaStream_t st) {
     XGGM_CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float), st));
     if (R <= 0 || C <= 0) return XGGM_OK;
+    if (kl_fast_ok(C, x, y)) {
+        const int grid = min(148 * 4, ceil_div(R, 8));
+        XGGM_KL_DISPATCH(C, (sym_kl_fast_kernel<NV, false><<<grid, 256, 0, st>>>(x, y, loss, nullptr, nullptr, nullptr, R, 1.0f / ((float)R * (float)C))));
+        XGGM_LAUNCH_CHECK();
+        return XGGM_OK;
+    }
     const int grid = min(148 * 8, ceil_div(R, 8));
     sym_kl_fwd_kernel<<<grid, 256, 0, st>>>(x, y, loss, R, C, 1.0f / ((float)R * (float)C));
     XGGM_LAUNCH_CHECK();
@@ -258,6 +404,12 @@ int sym_kl_fwd(const float* x, const float* y, float* loss, int R, int C, cudaSt
 int sym_kl_bwd(const float* x, const float* y, const float* gloss, float* gx, float* gy, int R,
                int C, cudaStream_t st) {
     if (R <= 0 || C <= 0) return XGGM_OK;
+    if (kl_fast_ok(C, x, y, gx, gy)) {
+        const int grid = min(148 * 4, ceil_div(R, 8));
+        XGGM_KL_DISPATCH(C, (sym_kl_fast_kernel<NV, true><<<grid, 256, 0, st>>>(x, y, nullptr, gloss, gx, gy, R, 1.0f / ((float)R * (float)C))));
+        XGGM_LAUNCH_CHECK();
+        return XGGM_OK;
+    }
     const int grid = min(148 * 8, ceil_div(R, 8));
     sym_kl_bwd_kernel<<<grid, 256, 0, st>>>(x, y, gloss, gx, gy, R, C, 1.0f / ((float)R * (float)C));
     XGGM_LAUNCH_CHECK();
