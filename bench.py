@@ -296,7 +296,9 @@ def run_gpu(args):
                      "executed_tflops": passes * gemm_tflops, "executed_frac": passes * gemm_tflops / peak,
                      "traffic": TRAFFIC_NCU, "peak_source": f"{peaks['source']} bf16 burst (MEASURED_PEAKS.json)",
                      "launches_timed": g_n, "avg_launch_us": (g_ms / g_n * 1e3) if g_n else None,
-                     "gemm_share_of_step": (g_ms / prof_steps) / ms_step if ms_step > 0 else None},
+                     "gemm_share_of_step": (g_ms / prof_steps) / ms_step if ms_step > 0 else None,
+                     "note": "launches of the dominant shape [B*N,768]x[768,768] (fwd, dgrad, wgrad), timed eagerly "
+                             "with CUDA events on the launching stream inside the library"},
         "block_roofline": {"algorithmic_gflop_per_step": flops_step / 1e9,
                            "achieved_tflops": flops_step / (ms_step * 1e-3) / 1e12,
                            "frac_of_bf16_peak": flops_step / (ms_step * 1e-3) / 1e12 / peak,

@@ -42,8 +42,9 @@ const char* xggm_last_cuda_error(void);
 /* Number of CUDA kernels this library has launched in this process (bench accounting). */
 unsigned long long xggm_launch_count(void);
 /* Bench instrumentation: while enabled, every projection-GEMM launch is bracketed by a
- * CUDA-event pair on its stream; xggm_prof_read sums their durations (ms), counts them and
- * sums their algorithmic FLOPs (2*M*N*K).  Enabling (or disabling) clears the records. */
+ * CUDA-event pair on its stream; xggm_prof_read sums the durations (ms), count and algorithmic
+ * FLOPs (2*M*N*K) of the launches of the dominant product shape (FLOPs >= half of the largest
+ * recorded launch).  Enabling (or disabling) clears the records. */
 int xggm_prof_enable(int on);
 int xggm_prof_read(double* total_ms, long long* launches, double* flops);
 /* Kernel-tuning aid: while dev_buf (>= 32 uint64 of DEVICE memory) is set, CTA 0 of every tcgen05

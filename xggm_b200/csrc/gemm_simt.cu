@@ -146,10 +146,15 @@ int gemm_prof_enable(int on) {
     g_prof_on = on != 0;
     return XGGM_OK;
 }
+// Sums the records of the DOMINANT product shape only (FLOPs >= half of the largest record): the
+// roofline leg is about the [B*N,768] x [768,768] projections, not the few tiny head GEMMs / Gram tiles.
 int gemm_prof_read(double* total_ms, long long* launches, double* flops) {
     *total_ms = 0; *launches = 0; *flops = 0;
+    double fmax = 0;
+    for (int i = 0; i < g_prof_n; ++i) fmax = g_prof[i].flops > fmax ? g_prof[i].flops : fmax;
     for (int i = 0; i < g_prof_n; ++i) {
         XGGM_CUDA_TRY(cudaEventSynchronize(g_prof[i].e1));
+        if (g_prof[i].flops < 0.5 * fmax) continue;
         float ms = 0.f;
         XGGM_CUDA_TRY(cudaEventElapsedTime(&ms, g_prof[i].e0, g_prof[i].e1));
         *total_ms += ms; *flops += g_prof[i].flops; *launches += 1;
