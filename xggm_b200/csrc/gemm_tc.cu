@@ -213,6 +213,12 @@ __device__ __forceinline__ void store_planes4(__nv_bfloat16* hi, __nv_bfloat16* 
     }
 }
 
+// 16-byte vector reduction into global memory (no return value): split-K partial tiles
+__device__ __forceinline__ void red_add_v4(float* addr, const float4& v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
 struct Params {
     int M, N;            // output extent
     int num_kb;          // ceil(K / BK)
@@ -436,7 +442,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const bool lead = (sp == 0);  // bias / residual are added by the first split only
             const int mrow0 = m0 + q * 32;
             const int rows = p.bd_stride > 0 ? min(32, min(p.M - mrow0, p.bd_stride - q * 32)) : min(32, p.M - mrow0);
-            const bool vec = p.vec4 && !p.atomic && p.gram_n == 0;
+            const bool vec = p.vec4 && p.gram_n == 0;   // (split-K partial sums use vector reductions)
             // float4 domain: lane -> (row = 4*it + lane/8, 4 columns at 4*(lane%8))
             const int rsub = lane >> 3, c4 = (lane & 7) * 4;
             constexpr int CSTEP = EPI_WARPS / 4;
@@ -450,7 +456,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 const bool ok = vec && cc < BN / 32 && nv < p.N && rows > 0;   // N % 4 == 0 in vec mode
                 bv = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (ok && lead && p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + nv));
-                const float* src = (lead && p.resid) ? p.resid : (p.accumulate ? p.C : nullptr);
+                const float* src = (lead && p.resid) ? p.resid : ((p.accumulate && !p.atomic) ? p.C : nullptr);
 #pragma unroll
                 for (int it = 0; it < 8; ++it) {
                     const int row = 4 * it + rsub;
@@ -515,7 +521,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 if (vec) {
                     const int nv = ncol0 + c4;
                     if (nv < p.N) {
-                        const bool both = lead && p.resid && p.accumulate;   // rare: second addend read late
+                        const bool both = lead && p.resid && p.accumulate && !p.atomic;   // rare: second addend read late
                         float4 o[8];
 #pragma unroll
                         for (int it = 0; it < 8; ++it) {
@@ -532,7 +538,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                                     const float4 a = *reinterpret_cast<const float4*>(p.C + off);
                                     o[it].x += a.x; o[it].y += a.y; o[it].z += a.z; o[it].w += a.w;
                                 }
-                                if (p.C) *reinterpret_cast<float4*>(p.C + off) = o[it];
+                                if (p.atomic) red_add_v4(p.C + off, o[it]);   // split-K partial sum
+                                else if (p.C) *reinterpret_cast<float4*>(p.C + off) = o[it];
                                 if (p.c_hi) store_planes4(p.c_hi, p.c_lo, off, o[it]);
                             }
                         }
