@@ -69,3 +69,35 @@ def test_unaligned_shapes_take_simt_kernel():
     assert all(v[0] < 3e-6 for v in errs.values()), errs
     errs = _run(3, 630, 768)
     assert all(v[0] < 3e-6 for v in errs.values()), errs
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 200, 136), (130, 64, 96), (9252, 768, 768), (257, 776, 72)])
+def test_outputs_stay_inside_their_buffers(M, N, K):
+    """compute-sanitizer is closed on this GPU pool, so bounds are checked by hand: every output of the
+    three Linear products (ragged M / N / K tails through TMA zero fill and the clipped epilogues) sits in
+    the middle of a larger buffer whose guard bands must keep their sentinel."""
+    from xggm_b200 import _lib
+    from xggm_b200._lib import call, ptr
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn(M, K, generator=g).to(dev)
+    w = (torch.randn(N, K, generator=g) * 0.05).to(dev)
+    go = torch.randn(M, N, generator=g).to(dev)
+    work = torch.empty(_lib.load().xggm_linear_work_bytes(M, N, K), device=dev, dtype=torch.uint8)
+    GUARD, SENT = 4096, 12345.0
+
+    def guarded(n):
+        buf = torch.full((n + 2 * GUARD,), SENT, device=dev)
+        return buf, buf[GUARD:GUARD + n]
+
+    ob, out = guarded(M * N)
+    gab, ga = guarded(M * K)
+    gwb, gw = guarded(N * K)
+    call("xggm_linear_fwd", ptr(a), ptr(w), None, None, ptr(out), M, N, K, ptr(work))
+    call("xggm_linear_bwd_input", ptr(go), ptr(w), ptr(ga), M, N, K, 0, ptr(work))
+    call("xggm_linear_bwd_weight", ptr(go), ptr(a), ptr(gw), None, M, N, K, 0, ptr(work))
+    torch.cuda.synchronize()
+    for name, buf, n in (("out", ob, M * N), ("ga", gab, M * K), ("gw", gwb, N * K)):
+        assert bool((buf[:GUARD] == SENT).all()) and bool((buf[GUARD + n:] == SENT).all()), f"{name}: guard band overwritten"
+        assert not bool((buf[GUARD:GUARD + n] == SENT).any()), f"{name}: unwritten elements"
+    assert rel_l2(out.reshape(M, N).cpu(), a.double().cpu() @ w.double().cpu().T) < 3e-5

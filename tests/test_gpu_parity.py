@@ -568,3 +568,38 @@ def test_api_surface_compositions_discriminator_v2_and_mix_generator():
         nf = O.gin(nf, ad, p, f"gnn_layers.{l}.", 1, None)
     _close(nodes, nf, 2 * TOL, "MixGenerator nodes")
     assert abs(float(loss) - float(ref_loss)) < 1e-4 * abs(float(ref_loss))
+
+
+@pytest.mark.parametrize("B,N,H", [(7, 36, 768), (5, 64, 128), (3, 100, 64), (4, 36, 776)])
+def test_tensor_core_graph_ops_match_simt_and_stay_in_bounds(B, N, H):
+    """Tensor-core message passing (block-diagonal tiles) and Gram regeneration vs the SIMT kernels on
+    ragged graph counts (B not a multiple of the graphs-per-tile) with guard bands around the outputs."""
+    import xggm_b200.functional as XF
+    from xggm_b200._lib import call, ptr
+    d = dev()
+    g = torch.Generator().manual_seed(B * 1000 + N)
+    x = torch.randn(B, N, H, generator=g).to(d)
+    adj = torch.rand(B, N, N, generator=g).to(d)
+    GUARD, SENT = 2048, 777.0
+    n = B * N * H
+    res = {}
+    for tag, wk in (("simt", None), ("tc", XF._adj_work(B, N, H, d))):
+        buf = torch.full((n + 2 * GUARD,), SENT, device=d)
+        out = buf[GUARD:GUARD + n]
+        call("xggm_adj_apply_fwd", ptr(adj), ptr(x), ptr(out), B, N, H, 0.5, None, 1.0, ptr(wk))
+        gx = torch.ones(n, device=d)
+        call("xggm_adj_apply_bwd", ptr(adj), ptr(x), ptr(x), ptr(gx), None, B, N, H, 1.0, None, 0.0, 1, ptr(wk))
+        torch.cuda.synchronize()
+        assert bool((buf[:GUARD] == SENT).all()) and bool((buf[GUARD + n:] == SENT).all()), tag
+        res[tag] = (out.clone(), gx.clone())
+    ref_f = x.double() + 0.5 * torch.bmm(adj.double(), x.double())
+    ref_b = 1.0 + torch.bmm(adj.double().transpose(1, 2), x.double())
+    for tag in ("simt", "tc"):
+        assert rel_l2(res[tag][0].cpu(), ref_f.reshape(-1).cpu()) < 3e-5, tag
+        assert rel_l2(res[tag][1].cpu(), ref_b.reshape(-1).cpu()) < 3e-5, tag
+    a1, am1 = XF.adj_regen(x, True, return_argmax=True)
+    s = torch.bmm(x.double(), x.double().transpose(1, 2))
+    ref = torch.sigmoid(s / s.max(dim=1)[0].unsqueeze(-1))
+    ref = ref - torch.diag_embed(torch.diagonal(ref, dim1=1, dim2=2))
+    assert rel_l2(a1.cpu(), ref.cpu()) < 1e-4
+    assert float(torch.diagonal(a1, dim1=1, dim2=2).abs().max()) == 0.0
