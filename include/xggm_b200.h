@@ -247,9 +247,14 @@ int xggm_sigmoid_bwd(const float* gy, const float* y, float* gx, long long n, xg
 int xggm_gelu_fwd(const float* x, float* y, long long n, xggm_stream_t s);
 int xggm_gelu_bwd(const float* gy, const float* x, float* gx, long long n, xggm_stream_t s);
 /* inverted dropout with an explicit mask, y = keep ? x*scale : 0 (GAT input dropout,
- * src/module/gat.py:73); the same call is its backward. */
+ * src/module/gat.py:73); the same call is its backward.  keep == NULL: y = x*scale. */
 int xggm_mask_scale(const float* x, const uint8_t* keep, float scale, float* y, long long n,
                     xggm_stream_t s);
+/* Tail of VisualFeatEncoder (src/lxrt/modeling.py:553-555): out = dropout((x + y) / 2),
+ * keep? a uint8 mask (NULL = eval mode), scale = 1/(1-p).  Its backward w.r.t. x and y is
+ * xggm_mask_scale(gout, keep, scale/2). */
+int xggm_avg2_drop(const float* x, const float* y, const uint8_t* keep, float scale, float* out, long long n,
+                   xggm_stream_t s);
 /* Philox keep-mask (1 = keep with probability 1-p): counter = element index / 4,
  * subsequence = stream_id + (*dev_epoch << 32 if dev_epoch, a device counter, is non-NULL). */
 int xggm_keep_mask(uint8_t* keep, long long n, float p, uint64_t seed, uint64_t stream_id,

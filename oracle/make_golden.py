@@ -237,6 +237,32 @@ def glue_case(gu, loss_func, compute_kl_loss, seed=7):
                 strip=_np(a.triu(1) + a.tril(-1)), v=_np(v), scatter=_np(sc))
 
 
+def visual_feat_case(seed=301, B=3, hidden=768, training=True):
+    """lxrt.modeling.VisualFeatEncoder (src/lxrt/modeling.py:530-556), imported unmodified."""
+    from lxrt.modeling import BertConfig, VisualFeatEncoder
+    cfg = BertConfig(vocab_size_or_config_json_file=30522, hidden_size=hidden)
+    mod = VisualFeatEncoder(cfg)
+    p = O.make_visual_params(seed, hidden)
+    mod.load_state_dict({k: v.clone() for k, v in p.items()}, strict=True)
+    mod.train(training)
+    feats, boxes = O.make_visual_inputs(seed + 1, B)
+    g = torch.Generator().manual_seed(seed + 2)
+    keep = (torch.rand(B, 36, hidden, generator=g) >= cfg.hidden_dropout_prob)
+    f = feats.clone().requires_grad_(True)
+    b = boxes.clone().requires_grad_(True)
+    out = _run_with_masks(lambda: mod((f, b)), [keep] if training else [], p=cfg.hidden_dropout_prob)
+    c = torch.randn(out.shape, generator=g)
+    (out * c).sum().backward()
+    res = dict(meta=np.array([seed, hidden, B, int(training)]), drop_p=np.array(cfg.hidden_dropout_prob),
+               keep=_np(keep.to(torch.uint8)), c=_np(c), out=_np(out),
+               gfeats_norm=np.array([float(f.grad.double().norm())]), gfeats_head=_np(f.grad.reshape(-1)[:64]),
+               gboxes=_np(b.grad))
+    res.update(_grad_summary(list(mod.named_parameters()), full=False))
+    for k in ("box_fc.weight", "box_fc.bias", "visn_layer_norm.weight", "box_layer_norm.bias"):
+        res["g/" + k] = _np(dict(mod.named_parameters())[k].grad)
+    return res
+
+
 def main():
     torch.set_num_threads(1)  # fixed summation order for the fixtures
     ggm, gu, loss_func, compute_kl_loss = _import_reference()
@@ -255,8 +281,13 @@ def main():
         "branch_node_gcn_h768": lambda: _branch(ggm, gu, loss_func, compute_kl_loss, "node", "GCN", 768, 2, 203),
         "branch_relation_gin_h64": lambda: _branch(ggm, gu, loss_func, compute_kl_loss, "relation", "GIN", 64, 3, 204),
         "glue": lambda: glue_case(gu, loss_func, compute_kl_loss),
+        "visual_feat_train": lambda: visual_feat_case(301, 3, 768, True),
+        "visual_feat_eval": lambda: visual_feat_case(302, 2, 768, False),
     }
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]   # regenerate just the named cases
     for name, fn in cases.items():
+        if only and name not in only:
+            continue
         data = fn()
         path = os.path.join(out_dir, name + ".npz")
         np.savez_compressed(path, **data)

@@ -61,6 +61,49 @@ def strip_diag(a):
 
 
 # --------------------------------------------------------------------------
+# VisualFeatEncoder  (src/lxrt/modeling.py:530-556) -- SURVEY 8(f-1), the producer of the block's input
+# --------------------------------------------------------------------------
+BERT_LN_EPS = 1e-12  # BertLayerNorm(config.hidden_size, eps=1e-12), modeling.py:538,542
+
+
+def visual_feat_encoder(feats, boxes, p, pre="", keep=None, drop_p=0.1):
+    """(LN(visn_fc(feats)) + LN(box_fc(boxes))) / 2, then dropout.  modeling.py:546-556."""
+    x = row_norm(affine(feats, p[pre + "visn_fc.weight"], p[pre + "visn_fc.bias"]),
+                 p[pre + "visn_layer_norm.weight"], p[pre + "visn_layer_norm.bias"], BERT_LN_EPS)
+    y = row_norm(affine(boxes, p[pre + "box_fc.weight"], p[pre + "box_fc.bias"]),
+                 p[pre + "box_layer_norm.weight"], p[pre + "box_layer_norm.bias"], BERT_LN_EPS)
+    return keep_scale((x + y) / 2, keep, drop_p)
+
+
+def make_visual_params(seed, hidden=768, feat_dim=2048, pos_dim=4, dtype=torch.float32):
+    """Seeded parameters of VisualFeatEncoder (nn.Linear-style uniform init; LN affine perturbed so that
+    gamma/beta gradients are exercised)."""
+    g = torch.Generator().manual_seed(seed)
+
+    def uni(shape, fan_in):
+        b = 1.0 / math.sqrt(fan_in)
+        return ((torch.rand(shape, generator=g) * 2 - 1) * b).to(dtype)
+
+    return {
+        "visn_fc.weight": uni((hidden, feat_dim), feat_dim), "visn_fc.bias": uni((hidden,), feat_dim),
+        "visn_layer_norm.weight": (1 + 0.1 * torch.randn(hidden, generator=g)).to(dtype),
+        "visn_layer_norm.bias": (0.1 * torch.randn(hidden, generator=g)).to(dtype),
+        "box_fc.weight": uni((hidden, pos_dim), pos_dim), "box_fc.bias": uni((hidden,), pos_dim),
+        "box_layer_norm.weight": (1 + 0.1 * torch.randn(hidden, generator=g)).to(dtype),
+        "box_layer_norm.bias": (0.1 * torch.randn(hidden, generator=g)).to(dtype),
+    }
+
+
+def make_visual_inputs(seed, B, n_obj=36, feat_dim=2048, dtype=torch.float32):
+    """feats = relu(N(0,1)) (post-ReLU pool5 look-alike), boxes = sorted U(0,1) corners."""
+    g = torch.Generator().manual_seed(seed)
+    feats = torch.relu(torch.randn(B, n_obj, feat_dim, generator=g)).to(dtype)
+    xy = torch.rand(B, n_obj, 2, 2, generator=g).sort(dim=-1)[0]          # [..., axis, (lo, hi)]
+    boxes = torch.stack([xy[..., 0, 0], xy[..., 1, 0], xy[..., 0, 1], xy[..., 1, 1]], dim=-1).to(dtype)  # x1,y1,x2,y2
+    return feats, boxes
+
+
+# --------------------------------------------------------------------------
 # GCN  (src/module/gcn.py)
 # --------------------------------------------------------------------------
 def gcn_conv(x, adj, p, pre):

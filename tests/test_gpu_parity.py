@@ -603,3 +603,34 @@ def test_tensor_core_graph_ops_match_simt_and_stay_in_bounds(B, N, H):
     ref = ref - torch.diag_embed(torch.diagonal(ref, dim1=1, dim2=2))
     assert rel_l2(a1.cpu(), ref.cpu()) < 1e-4
     assert float(torch.diagonal(a1, dim1=1, dim2=2).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("name", ["visual_feat_train", "visual_feat_eval"])
+def test_visual_feat_encoder_matches_reference_fixture(name, engine):
+    """xggm_b200.VisualFeatEncoder vs the fixture written by lxrt.modeling.VisualFeatEncoder
+    (src/lxrt/modeling.py:530-556); state_dict keys are the reference's."""
+    import xggm_b200 as X
+    from xggm_b200.functional import inject_keep_masks
+    gold = load_golden(name)
+    seed, hidden, B, training = [int(v) for v in gold["meta"]]
+    mod = X.VisualFeatEncoder(hidden_size=hidden, hidden_dropout_prob=float(gold["drop_p"]))
+    mod.load_state_dict(O.make_visual_params(seed, hidden), strict=True)
+    mod = mod.to(dev()).train(bool(training))
+    feats, boxes = O.make_visual_inputs(seed + 1, B)
+    f = feats.clone().to(dev()).requires_grad_(True)
+    b = boxes.clone().to(dev()).requires_grad_(True)
+    masks = [_t(gold["keep"])] if training else []
+    with inject_keep_masks(masks):
+        out = mod((f, b))
+    _close(out, gold["out"], name="out")
+    if training:   # dropped positions are exactly zero
+        assert float(out[_t(gold["keep"]).to(dev()) == 0].abs().max()) == 0.0
+    (out * _t(gold["c"]).to(dev())).sum().backward()
+    nrm = float(gold["gfeats_norm"][0])
+    assert abs(float(f.grad.double().norm()) - nrm) < 3 * TOL * nrm
+    _close(f.grad.reshape(-1)[:64], gold["gfeats_head"], 20 * TOL, "gfeats")
+    _close(b.grad, gold["gboxes"], 3 * TOL, "gboxes")
+    named = dict(mod.named_parameters())
+    for k in ("box_fc.weight", "box_fc.bias", "visn_layer_norm.weight", "box_layer_norm.bias"):
+        _close(named[k].grad, gold["g/" + k], 3 * TOL, k)
+    _param_grad_check(gold, list(mod.named_parameters()), 3 * TOL)

@@ -126,3 +126,23 @@ def test_triu_index_closed_form():
         for j in range(i + 1, n):
             assert int(idx[i, j]) == i * (2 * n - i - 1) // 2 + (j - i - 1)
     assert int(idx.max()) == n * (n - 1) // 2 - 1
+
+
+@pytest.mark.parametrize("name", ["visual_feat_train", "visual_feat_eval"])
+def test_visual_feat_encoder_matches_reference(name):
+    """oracle restatement of lxrt.modeling.VisualFeatEncoder vs the fixture written by the
+    unmodified reference class."""
+    g = load_golden(name)
+    seed, hidden, B, training = [int(v) for v in g["meta"]]
+    p = {k: v.requires_grad_(True) for k, v in O.make_visual_params(seed, hidden).items()}
+    feats, boxes = O.make_visual_inputs(seed + 1, B)
+    f, b = feats.clone().requires_grad_(True), boxes.clone().requires_grad_(True)
+    keep = _t(g["keep"]).bool() if training else None
+    out = O.visual_feat_encoder(f, b, p, keep=keep, drop_p=float(g["drop_p"]))
+    assert rel_l2(out, g["out"]) < TOL
+    (out * _t(g["c"])).sum().backward()
+    assert abs(float(f.grad.double().norm()) - float(g["gfeats_norm"][0])) < 10 * TOL * float(g["gfeats_norm"][0])
+    assert rel_l2(f.grad.reshape(-1)[:64], g["gfeats_head"]) < 20 * TOL
+    assert rel_l2(b.grad, g["gboxes"]) < 20 * TOL
+    for k in ("box_fc.weight", "box_fc.bias", "visn_layer_norm.weight", "box_layer_norm.bias"):
+        assert rel_l2(p[k].grad, g["g/" + k]) < 20 * TOL, k

@@ -13,7 +13,7 @@ import xggm_b200.functional as XF  # noqa: E402
 from xggm_b200._lib import call, ptr  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--ops", default="adj,ln,gld,regen")
+ap.add_argument("--ops", default="adj,ln,gld,regen,visual")
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("-B", type=int, default=256)
 args = ap.parse_args()
@@ -61,5 +61,16 @@ if "gld" in ops:
     timed("gelu_ln_drop fwd (mask, accumulate)", lambda: call("xggm_gelu_ln_drop_fwd", ptr(x), ptr(gamma), ptr(beta), ptr(keep), 2.0, ptr(out), ptr(mean), ptr(rstd2), M, H, 1e-5, 1), 3.25 * T)
     gz, gg, gb = torch.empty_like(x), torch.zeros(H, device=dev), torch.zeros(H, device=dev)
     timed("gelu_ln_drop bwd (mask)", lambda: call("xggm_gelu_ln_drop_bwd", ptr(g), ptr(x), ptr(mean), ptr(rstd2), ptr(gamma), ptr(keep), 2.0, ptr(gz), ptr(gg), ptr(gb), M, H), 3.25 * T)
+if "visual" in ops:
+    enc = X.VisualFeatEncoder().to(dev).train()
+    feats = torch.relu(torch.randn(B, N, 2048, device=dev))
+    boxes = torch.rand(B, N, 4, device=dev)
+
+    def vfe():
+        f = feats.requires_grad_(True)
+        o = enc((f, boxes))
+        o.backward(g)
+        f.grad = None
+    timed("VisualFeatEncoder fwd+bwd (eager)", vfe, 2 * M * 2048 * 4 / 1e6 + 6 * T)
 if "regen" in ops:
     timed("adj_regen fwd (tensor-core Gram)", lambda: XF.adj_regen(x), T)

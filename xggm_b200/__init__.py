@@ -12,6 +12,6 @@ from .graphs import GraphedStep  # noqa: F401
 from .model import XGGMHeads  # noqa: F401
 from .nn import (GAT, GCN, GIN, Discriminator, DiscriminatorV2, EdgeGenerator, GATConv,  # noqa: F401
                  GATGenerator, GCNConv, GCNGenerator, GCNPlainEncoder, GeLU, GINConv, GINGenerator,
-                 GinPlainEncoder, MixGenerator, NodeGenerator)
+                 GinPlainEncoder, MixGenerator, NodeGenerator, VisualFeatEncoder)
 
 __version__ = "0.1.0"

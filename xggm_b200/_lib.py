@@ -50,6 +50,7 @@ SIGNATURES = {
     "xggm_gelu_fwd": [_vp, _vp, _ll, _vp],
     "xggm_gelu_bwd": [_vp, _vp, _vp, _ll, _vp],
     "xggm_mask_scale": [_vp, _vp, _f, _vp, _ll, _vp],
+    "xggm_avg2_drop": [_vp, _vp, _vp, _f, _vp, _ll, _vp],
     "xggm_strip_diag": [_vp, _vp, _i, _i, _vp],
     "xggm_triu_scatter_fwd": [_vp, _vp, _i, _i, _vp],
     "xggm_triu_scatter_bwd": [_vp, _vp, _i, _i, _vp],

@@ -52,6 +52,7 @@ int gat_attn_bwd(const float*, const float*, const float*, const float*, const f
 int gelu_fwd(const float*, float*, long long, cudaStream_t);
 int gelu_bwd(const float*, const float*, float*, long long, cudaStream_t);
 int mask_scale(const float*, const uint8_t*, float, float*, long long, cudaStream_t);
+int avg2_drop(const float*, const float*, const uint8_t*, float, float*, long long, cudaStream_t);
 int strip_diag(const float*, float*, int, int, cudaStream_t);
 int triu_scatter_fwd(const float*, float*, int, int, cudaStream_t);
 int triu_scatter_bwd(const float*, float*, int, int, cudaStream_t);
@@ -772,8 +773,14 @@ int xggm_gelu_bwd(const float* gy, const float* x, float* gx, long long n, xggm_
 int xggm_mask_scale(const float* x, const uint8_t* keep, float scale, float* y, long long n,
                     xggm_stream_t s) {
     if (n == 0) return XGGM_OK;
-    XGGM_REQUIRE(x && keep && y && n >= 0);
+    XGGM_REQUIRE(x && y && n >= 0);
     return mask_scale(x, keep, scale, y, n, as_stream(s));
+}
+int xggm_avg2_drop(const float* x, const float* y, const uint8_t* keep, float scale, float* out, long long n,
+                   xggm_stream_t s) {
+    if (n == 0) return XGGM_OK;
+    XGGM_REQUIRE(x && y && out && n >= 0);
+    return avg2_drop(x, y, keep, scale, out, n, as_stream(s));
 }
 
 int xggm_strip_diag(const float* a, float* out, int B, int N, xggm_stream_t s) {

@@ -504,15 +504,50 @@ int gelu_bwd(const float* gy, const float* x, float* gx, long long n, cudaStream
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
-// inverted dropout with an explicit mask: y = keep ? x*scale : 0 (its own backward)
+// inverted dropout with an explicit mask: y = keep ? x*scale : 0 (its own backward); keep == NULL: y = x*scale
 __global__ void mask_scale_kernel(const float* __restrict__ x, const uint8_t* __restrict__ keep,
                                   float scale, float* __restrict__ y, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) y[i] = keep[i] ? x[i] * scale : 0.f;
+    if (i < n) y[i] = (!keep || keep[i]) ? x[i] * scale : 0.f;
 }
 int mask_scale(const float* x, const uint8_t* keep, float scale, float* y, long long n, cudaStream_t st) {
     if (n <= 0) return XGGM_OK;
     mask_scale_kernel<<<grid1d(n), 256, 0, st>>>(x, keep, scale, y, n);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+
+// out = dropout((x + y) / 2): the tail of VisualFeatEncoder (src/lxrt/modeling.py:553-555).
+// keep == NULL -> no dropout.  4 elements per thread when everything is 16-byte aligned.
+__global__ void __launch_bounds__(256)
+avg2_drop_kernel(const float* __restrict__ x, const float* __restrict__ y, const uint8_t* __restrict__ keep,
+                 float scale, float* __restrict__ out, long long n, int vec) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    if (vec) {
+        const long long n4 = n >> 2;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+            const float4 a = reinterpret_cast<const float4*>(x)[i], b = reinterpret_cast<const float4*>(y)[i];
+            float4 o = make_float4((a.x + b.x) / 2, (a.y + b.y) / 2, (a.z + b.z) / 2, (a.w + b.w) / 2);
+            if (keep) {
+                const uchar4 k = reinterpret_cast<const uchar4*>(keep)[i];
+                o.x = k.x ? o.x * scale : 0.f; o.y = k.y ? o.y * scale : 0.f;
+                o.z = k.z ? o.z * scale : 0.f; o.w = k.w ? o.w * scale : 0.f;
+            }
+            reinterpret_cast<float4*>(out)[i] = o;
+        }
+    } else {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+            const float o = (x[i] + y[i]) / 2;
+            out[i] = keep ? (keep[i] ? o * scale : 0.f) : o;
+        }
+    }
+}
+int avg2_drop(const float* x, const float* y, const uint8_t* keep, float scale, float* out, long long n,
+              cudaStream_t st) {
+    if (n <= 0) return XGGM_OK;
+    const int vec = n % 4 == 0 && al16(x) && al16(y) && al16(out) && (reinterpret_cast<uintptr_t>(keep) & 3) == 0;
+    const int grid = (int)min((long long)148 * 16, ((vec ? n / 4 : n) + 255) / 256);
+    avg2_drop_kernel<<<grid, 256, 0, st>>>(x, y, keep, scale, out, n, vec);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }

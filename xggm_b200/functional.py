@@ -423,6 +423,35 @@ class _MaskScale(torch.autograd.Function):
         return gx, None, None
 
 
+class _Avg2Drop(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y, keep, scale):
+        x, y = f32(x, "x"), f32(y, "y")
+        if x.shape != y.shape:
+            raise RuntimeError("xggm_b200.avg2_dropout: shape mismatch")
+        keep = _u8(keep)
+        out = torch.empty_like(x)
+        call("xggm_avg2_drop", ptr(x), ptr(y), ptr(keep), float(scale), ptr(out), x.numel())
+        ctx.save_for_backward(keep)
+        ctx.scale = float(scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (keep,) = ctx.saved_tensors
+        g = f32(g)
+        gx = torch.empty_like(g)
+        call("xggm_mask_scale", ptr(g), ptr(keep), 0.5 * ctx.scale, ptr(gx), g.numel())
+        return gx, gx, None, None
+
+
+def avg2_dropout(x, y, p, training):
+    """dropout((x + y) / 2) -- the tail of VisualFeatEncoder (src/lxrt/modeling.py:553-555)."""
+    if training and p > 0.0:
+        return _Avg2Drop.apply(x, y, keep_mask(x.shape, p, x.device), 1.0 / (1.0 - p))
+    return _Avg2Drop.apply(x, y, None, 1.0)
+
+
 def dropout(x, p, training):
     """F.dropout with a library-generated (or injected) keep-mask."""
     if not training or p == 0.0:

@@ -346,3 +346,34 @@ class MixGenerator(nn.Module):
         if eps is None:
             eps = torch.randn_like(std)
         return mu + std * eps
+
+
+# ---------------------------------------------------------------------------
+# VisualFeatEncoder  (reference: src/lxrt/modeling.py:530-556) -- SURVEY 8(f-1): the 2048-d region
+# feature projection that produces the graph block's node features
+# ---------------------------------------------------------------------------
+class VisualFeatEncoder(nn.Module):
+    """(LN_1e-12(visn_fc(feats)) + LN_1e-12(box_fc(boxes))) / 2, then dropout.
+
+    ``config`` is the reference's BertConfig (only ``hidden_size`` and ``hidden_dropout_prob`` are read);
+    feat_dim / pos_dim are VISUAL_CONFIG.visual_feat_dim / visual_pos_dim (2048 / 4).  Parameter names match
+    the reference, so the ``bert.encoder.visn_fc.*`` slice of an LXMERT checkpoint loads unchanged.  The
+    2048 -> 768 projection runs on the tcgen05 engine, the 4 -> 768 box projection on the exact kernel."""
+
+    def __init__(self, config=None, hidden_size=768, hidden_dropout_prob=0.1, feat_dim=2048, pos_dim=4):
+        super().__init__()
+        if config is not None:
+            hidden_size, hidden_dropout_prob = config.hidden_size, config.hidden_dropout_prob
+        self.visn_fc = nn.Linear(feat_dim, hidden_size)
+        self.visn_layer_norm = nn.LayerNorm(hidden_size, eps=1e-12)
+        self.box_fc = nn.Linear(pos_dim, hidden_size)
+        self.box_layer_norm = nn.LayerNorm(hidden_size, eps=1e-12)
+        self.dropout = nn.Dropout(hidden_dropout_prob)
+
+    def forward(self, visn_input):
+        feats, boxes = visn_input
+        x = XF.layer_norm(XF.linear(feats, self.visn_fc.weight, self.visn_fc.bias),
+                          self.visn_layer_norm.weight, self.visn_layer_norm.bias, self.visn_layer_norm.eps)
+        y = XF.layer_norm(XF.linear(boxes, self.box_fc.weight, self.box_fc.bias),
+                          self.box_layer_norm.weight, self.box_layer_norm.bias, self.box_layer_norm.eps)
+        return XF.avg2_dropout(x, y, self.dropout.p, self.training)
