@@ -178,7 +178,9 @@ int xggm_gnn_fwd(int kind, const float* x, const float* adj, const float* const*
                  xggm_stream_t s);
 /* Gradient tables mirror the parameter tables (same order); every parameter-gradient buffer is
  * overwritten, or accumulated into when accumulate_param_grads != 0 (the buffers then are the
- * parameters' live .grad tensors).  gadj[B,N,N] and gx[B,N,H] are always overwritten. */
+ * parameters' live .grad tensors).  gx[B,N,H] is always overwritten; gadj[B,N,N] is overwritten, or may be
+ * NULL for a GCN layer whose adjacency needs no gradient (the gq h^T products are then skipped; a GIN layer
+ * still needs them for d eps and must pass a buffer). */
 int xggm_gnn_bwd(int kind, const float* gout, const float* x, const float* adj,
                  const float* const* conv_params, const float* const* head_params,
                  const uint8_t* const* keeps, const xggm_philox_t* philox, float drop_p, const float* saved,

@@ -368,7 +368,8 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
                 XGGM_CUDA_TRY(cudaMemsetAsync(hg[4 * j + q], 0, sizeof(float) * (q == 0 ? (size_t)H * H : H), st));
         return XGGM_OK;
     }
-    XGGM_REQUIRE(gout && x && adj && saved_c && work && gx && gadj);
+    XGGM_REQUIRE(gout && x && adj && saved_c && work && gx);   // gadj == NULL: the adjacency needs no gradient
+    XGGM_REQUIRE(gadj || kind == XGGM_KIND_GCN);               // (GIN still needs gq h^T for d eps)
     float* saved = const_cast<float*>(saved_c);  // plane regions are read-only here; the cast only feeds planes_at
     const GnnLayout L(kind, M, H, nc);
     const bool tc = use_tc(M, H, H);
@@ -378,7 +379,7 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
     float* gq = work + 3 * MH;
     Operand wconv[MAX_CONVS], whead[MAX_CONVS + 1];
     XGGM_TRY(split_weights(kind, cp, hp, work + 6 * MH, L, H, wconv, whead, tc, true, st));
-    XGGM_CUDA_TRY(cudaMemsetAsync(gadj, 0, sizeof(float) * (size_t)B * N * N, st));
+    if (gadj) XGGM_CUDA_TRY(cudaMemsetAsync(gadj, 0, sizeof(float) * (size_t)B * N * N, st));
     // per-graph products gq h^T go through the tensor-core Gram kernel when it can address them
     const bool gram = tc && gram_tc_supported(N, H);
     const Operand gq_op = planes_at(gq, work + 5 * MH, MHn);
@@ -451,7 +452,9 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
                                    tc ? lo_or_null(gu) : nullptr, M, H, st));
             XGGM_TRY(wgrad(gu, pre_op, cg[3 * k]));
             XGGM_TRY(proj_dgrad(tc, gu, wconv[k], gq, M, H, H, 0, st, gram ? &gq_op : nullptr));  // gq = gu Wc
-            if (gram) {   // gadj += gq h_k^T
+            if (!gadj) {
+                // adjacency is a constant input (e.g. the ground-truth graph of the node branch): no gq h^T
+            } else if (gram) {   // gadj += gq h_k^T
                 const Operand hk_op = act(k);
                 XGGM_TRY(gram_tc(gq_op.hi, gq_op.lo, hk_op.hi, hk_op.lo, s_scratch, B, N, H, npass(), st));
                 XGGM_TRY(scale_accum(s_scratch, gadj, BNN, 1.f, nullptr, 1, nullptr, nullptr, st));

@@ -303,7 +303,9 @@ class _GnnLayer(torch.autograd.Function):
         work = torch.empty(max(lib.xggm_gnn_work_floats(kind, B, N, H, n_convs), 1), device=x.device,
                            dtype=torch.float32)
         gx = torch.empty_like(x)
-        gadj = torch.empty_like(adj)
+        # ctx.needs_input_grad: (kind, n_convs, drop_p, keeps, philox, x, adj, *params); GIN needs gq h^T for d eps
+        need_gadj = ctx.needs_input_grad[6] or kind != 0
+        gadj = torch.empty_like(adj) if need_gadj else None
         targets = [_grad_target(p) for p in params]
         fused = all(t is not None for t in targets)
         grads = targets if fused else [torch.empty_like(p) for p in params]
@@ -313,7 +315,7 @@ class _GnnLayer(torch.autograd.Function):
              ptr_table(grads[n_cp:]), int(fused), B, N, H, n_convs)
         if fused:
             grads = [None] * len(params)
-        return (None, None, None, None, None, gx, gadj, *grads)
+        return (None, None, None, None, None, gx, (gadj if ctx.needs_input_grad[6] else None), *grads)
 
 
 def _philox_arg(philox):
