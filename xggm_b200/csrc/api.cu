@@ -7,67 +7,9 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "kernels.cuh"
 
 namespace xggm {
-
-// ---- declarations of the per-file launchers --------------------------------
-int gemm_simt(int op, const float* A, const float* Bm, const float* bias, const float* resid,
-              float* C, int M, int N, int K, int accumulate, cudaStream_t st);
-int colsum(const float* g, float* out, int R, int C, int accumulate, cudaStream_t st);
-bool gemm_tc_supported(int M, int N, int K);
-int gemm_tc(bool a_mn, bool b_mn, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const __nv_bfloat16* b_hi,
-            const __nv_bfloat16* b_lo, const float* bias, const float* resid, float* C, __nv_bfloat16* c_hi,
-            __nv_bfloat16* c_lo, int M, int N, int K, int accumulate, int allow_split_k, int npass, cudaStream_t st);
-bool adj_tc_supported(int N, int H);
-long long adj_tc_coef_elems(int B, int N);
-int build_blockdiag(const float* adj, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int N, float alpha0,
-                    const float* alpha_dev, float self_w, int trans, cudaStream_t st);
-int adj_apply_tc(const __nv_bfloat16* c_hi, const __nv_bfloat16* c_lo, const __nv_bfloat16* x_hi,
-                 const __nv_bfloat16* x_lo, float* out, __nv_bfloat16* o_hi, __nv_bfloat16* o_lo, int B, int N, int H,
-                 int accumulate, int npass, cudaStream_t st);
-bool gram_tc_supported(int N, int H);
-int gram_tc(const __nv_bfloat16* p_hi, const __nv_bfloat16* p_lo, const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo,
-            float* S, int B, int N, int H, int npass, cudaStream_t st);
-int adj_regen_from_s(const float* S, float* adj_out, int32_t* amax, int B, int N, int squash, cudaStream_t st);
-int scale_accum(const float* S, float* out, long long n, float alpha0, const float* alpha_dev, int accumulate,
-                const float* dot_ref, float* dot_out, cudaStream_t st);
-int split_planes(const float* const* src, __nv_bfloat16* const* hi, __nv_bfloat16* const* lo, const long long* n,
-                 int count, cudaStream_t st);
-int split_planes_t(const float* const* src, __nv_bfloat16* const* hi, __nv_bfloat16* const* lo, int R, int C,
-                   int count, cudaStream_t st);
-void gemm_tc_set_debug(unsigned long long* dev_buf);
-int gemm_prof_enable(int on);
-int gemm_prof_read(double* total_ms, long long* launches, double* flops);
-int layernorm_fwd(const float*, const float*, const float*, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, float, cudaStream_t);
-int layernorm_bwd(const float*, const float*, const float*, const float*, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, cudaStream_t);
-int gelu_ln_drop_fwd(const float*, const float*, const float*, const DropSpec&, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, float, int, cudaStream_t);
-int gelu_ln_drop_bwd(const float*, const float*, const float*, const float*, const float*, const DropSpec&, float*, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, cudaStream_t);
-int adj_apply(const float*, const float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, int, float, const float*, float, bool, int, cudaStream_t);
-int bmm_nt(const float*, const float*, float*, int, int, int, float, const float*, int, const float*, float*, cudaStream_t);
-int adj_regen_fwd(const float*, float*, float*, int32_t*, int, int, int, int, cudaStream_t);
-int adj_regen_bwd(const float*, const float*, const float*, const int32_t*, float*, float*, int, int, int, int, int, cudaStream_t);
-int adj_regen_bwd_coeffs(const float* gadj, const float* S, const int32_t* amax, float* D, int B, int N, int squash, cudaStream_t st);
-int gat_attn_fwd(const float*, const float*, const float*, float*, float*, float*, int, int, int, float, int, cudaStream_t);
-int gat_attn_bwd(const float*, const float*, const float*, const float*, const float*, const float*, float*, float*, float*, int, int, int, float, int, cudaStream_t);
-int gelu_fwd(const float*, float*, long long, cudaStream_t);
-int gelu_bwd(const float*, const float*, float*, long long, cudaStream_t);
-int mask_scale(const float*, const uint8_t*, float, float*, long long, cudaStream_t);
-int avg2_drop(const float*, const float*, const uint8_t*, float, float*, long long, cudaStream_t);
-int strip_diag(const float*, float*, int, int, cudaStream_t);
-int triu_scatter_fwd(const float*, float*, int, int, cudaStream_t);
-int triu_scatter_bwd(const float*, float*, int, int, cudaStream_t);
-int edge_noise(const float*, const float*, float, float, float*, float*, int, int, cudaStream_t);
-int feat_noise(const float*, const float*, float, float, float*, float*, int, int, int, int, cudaStream_t);
-int sum_nodes(const float*, float*, int, int, int, cudaStream_t);
-int score_mse_fwd(const float*, const float*, float, float*, long long, cudaStream_t);
-int score_mse_bwd(const float*, const float*, const float*, float, float*, long long, cudaStream_t);
-int sym_kl_fwd(const float*, const float*, float*, int, int, cudaStream_t);
-int sym_kl_bwd(const float*, const float*, const float*, float*, float*, int, int, cudaStream_t);
-int fuse_readout_fwd(const float*, const float*, float*, int, int, int, cudaStream_t);
-int fuse_readout_bwd(const float*, const float*, float*, float*, int, int, int, int, cudaStream_t);
-int sigmoid_fwd(const float*, float*, long long, cudaStream_t);
-int sigmoid_bwd(const float*, const float*, float*, long long, cudaStream_t);
-int keep_mask(uint8_t*, long long, float, uint64_t, uint64_t, const uint64_t*, cudaStream_t);
 
 // ---- error state -------------------------------------------------------------
 static thread_local char g_cuda_err[256] = "";
@@ -79,7 +21,7 @@ void set_cuda_error(cudaError_t e, const char* where) {
 constexpr float LN_EPS = 1e-5f;  // nn.LayerNorm default (src/module/gcn.py:14,47)
 
 // chunk sizes are padded to 8 floats so that every bf16 plane starts 16-byte aligned (TMA)
-static inline long long al4(long long n) { return (n + 7) & ~7LL; }
+static inline long long pad8(long long n) { return (n + 7) & ~7LL; }
 
 // ---- projection engine selection -------------------------------------------------
 // precision: XGGM_PREC_FP32 (tcgen05, split-bf16 x3), XGGM_PREC_BF16 (tcgen05, single pass),
@@ -97,10 +39,10 @@ static inline bool use_tc(int M, int N, int K) {
     return g_precision != XGGM_PREC_FP32_SIMT && gemm_tc_supported(M, N, K);
 }
 static inline int npass() { return g_precision == XGGM_PREC_BF16 ? 1 : 3; }
-// planes of an [n]-element fp32 array stored in a region of al4(n) floats: hi | lo
+// planes of an [n]-element fp32 array stored in a region of pad8(n) floats: hi | lo
 static inline Operand planes_at(const float* f32, float* region, long long n) {
     bf16* hi = reinterpret_cast<bf16*>(region);
-    return Operand{f32, hi, hi + al4(n) };
+    return Operand{f32, hi, hi + pad8(n) };
 }
 static inline bf16* mut(const bf16* p) { return const_cast<bf16*>(p); }
 static inline bf16* lo_or_null(const Operand& o) { return npass() == 3 ? const_cast<bf16*>(o.lo) : nullptr; }
@@ -141,9 +83,9 @@ struct GnnLayout {
     // GCN conv k: agg | xhat | h_next | rstd | (pad) | P(agg) | P(h_next)
     // GIN conv k: pre | z    | h_next | mean | rstd  | P(pre) | P(h_next)
     GnnLayout(int kind_, long long M, int H, int nc) : kind(kind_) {
-        MH = al4(M * H);
-        Mr = al4(M);
-        HH = al4((long long)H * H);
+        MH = pad8(M * H);
+        Mr = pad8(M);
+        HH = pad8((long long)H * H);
         n_convs = nc;
         n_heads = nc + 1;
         conv_stride = 5 * MH + 2 * Mr;
@@ -163,9 +105,9 @@ struct GnnLayout {
         return slot == 0 ? base : base + MH + (slot - 1) * Mr;
     }
     // fwd: u | weight planes | block-diagonal coefficient planes
-    long long work_fwd(long long coef) const { return MH + (2 * n_convs + 1) * HH + al4(coef); }
+    long long work_fwd(long long coef) const { return MH + (2 * n_convs + 1) * HH + pad8(coef); }
     // bwd: buf0 | buf1 | gt | gq | P(grad) | P(gq) | weight planes | S scratch [B,N,N] | coefficient planes | P(grad)'
-    long long work_bwd(long long bnn, long long coef) const { return 7 * MH + (2 * n_convs + 1) * HH + al4(bnn) + al4(coef); }
+    long long work_bwd(long long bnn, long long coef) const { return 7 * MH + (2 * n_convs + 1) * HH + pad8(bnn) + pad8(coef); }
 };
 
 // weight planes for one layer live at the tail of the work buffer: conv k -> slot k, head j -> slot nc + j
@@ -279,7 +221,7 @@ static int gnn_fwd(int kind, const float* x, const float* adj, const float* cons
     // per conv for GIN whose (1+eps) differs) x the node planes
     const bool adjtc = tc && adj_tc_supported(N, H);
     bf16* coef_hi = reinterpret_cast<bf16*>(work + L.MH + (2 * nc + 1) * L.HH);
-    bf16* coef_lo = coef_hi + al4(adjtc ? adj_tc_coef_elems(B, N) : 0);
+    bf16* coef_lo = coef_hi + pad8(adjtc ? adj_tc_coef_elems(B, N) : 0);
     if (adjtc && kind == XGGM_KIND_GCN && nc > 0)
         XGGM_TRY(build_blockdiag(adj, coef_hi, npass() == 3 ? coef_lo : nullptr, B, N, 1.f, nullptr, 0.f, 0, st));
     // read-out head j only needs h_j: it runs on the side stream while the conv chain continues
@@ -386,8 +328,8 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
     float* s_scratch = work + 6 * MH + (2 * nc + 1) * L.HH;
     const long long BNN = (long long)B * N * N;
     const bool adjtc = gram && adj_tc_supported(N, H);   // needs the planes of gq the Gram path already emits
-    bf16* coef_hi = reinterpret_cast<bf16*>(s_scratch + al4(BNN));
-    bf16* coef_lo = coef_hi + al4(adjtc ? adj_tc_coef_elems(B, N) : 0);
+    bf16* coef_hi = reinterpret_cast<bf16*>(s_scratch + pad8(BNN));
+    bf16* coef_lo = coef_hi + pad8(adjtc ? adj_tc_coef_elems(B, N) : 0);
     if (adjtc && kind == XGGM_KIND_GCN && nc > 0)   // adj^T coefficients, shared by every conv of the layer
         XGGM_TRY(build_blockdiag(adj, coef_hi, npass() == 3 ? coef_lo : nullptr, B, N, 1.f, nullptr, 0.f, 1, st));
 
@@ -399,8 +341,8 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
     // weight-gradient GEMM that reads them runs on the side stream while the main stream already
     // produces the next gradient.  Before region i is overwritten, main waits for the wgrad that read it.
     Fork* fk = tc ? get_fork() : nullptr;
-    const long long coef_floats = N <= 128 ? al4(adj_tc_coef_elems(B, N)) : 0;   // as in xggm_gnn_work_floats
-    float* grad_region[2] = {work + 4 * MH, s_scratch + al4(BNN) + coef_floats};
+    const long long coef_floats = N <= 128 ? pad8(adj_tc_coef_elems(B, N)) : 0;   // as in xggm_gnn_work_floats
+    float* grad_region[2] = {work + 4 * MH, s_scratch + pad8(BNN) + coef_floats};
     int n_grad = 0;
     auto grad_op = [&](const float* g32) -> Operand {
         const int slot = fk ? (n_grad & 1) : 0;
@@ -553,7 +495,7 @@ int xggm_get_precision(void) { return g_precision; }
 // work layout of the Linear entry points: P(a)[M,K] | P(w)[N,K] | P(g)[M,N]
 long long xggm_linear_work_bytes(int M, int N, int K) {
     if (M < 0 || N <= 0 || K <= 0) return -1;
-    return 4 * (al4((long long)M * K) + al4((long long)N * K) + al4((long long)M * N));
+    return 4 * (pad8((long long)M * K) + pad8((long long)N * K) + pad8((long long)M * N));
 }
 static inline bool linear_tc(const void* work, int M, int N, int K) {
     return work != nullptr && M > 0 && use_tc(M, N, K);
@@ -568,7 +510,7 @@ int xggm_linear_fwd(const float* a, const float* w, const float* bias, const flo
     Operand ao{a, nullptr, nullptr}, wo{w, nullptr, nullptr};
     if (tc) {
         ao = planes_at(a, wk, (long long)M * K);
-        wo = planes_at(w, wk + al4((long long)M * K), (long long)N * K);
+        wo = planes_at(w, wk + pad8((long long)M * K), (long long)N * K);
         const float* src[2] = {a, w};
         bf16* hi[2] = {const_cast<bf16*>(ao.hi), const_cast<bf16*>(wo.hi)};
         bf16* lo[2] = {const_cast<bf16*>(ao.lo), const_cast<bf16*>(wo.lo)};
@@ -585,8 +527,8 @@ int xggm_linear_bwd_input(const float* g, const float* w, float* ga, int M, int 
     float* wk = static_cast<float*>(work);
     Operand go{g, nullptr, nullptr}, wo{w, nullptr, nullptr};
     if (tc) {
-        wo = planes_at(w, wk + al4((long long)M * K), (long long)N * K);
-        go = planes_at(g, wk + al4((long long)M * K) + al4((long long)N * K), (long long)M * N);
+        wo = planes_at(w, wk + pad8((long long)M * K), (long long)N * K);
+        go = planes_at(g, wk + pad8((long long)M * K) + pad8((long long)N * K), (long long)M * N);
         XGGM_TRY(split_one(go, (long long)M * N, as_stream(s)));
         const float* src[1] = {w};
         bf16* hi[1] = {const_cast<bf16*>(wo.hi)};
@@ -610,7 +552,7 @@ int xggm_linear_bwd_weight(const float* g, const float* a, float* gw, float* gbi
     Operand go{g, nullptr, nullptr}, ao{a, nullptr, nullptr};
     if (tc) {
         ao = planes_at(a, wk, (long long)M * K);
-        go = planes_at(g, wk + al4((long long)M * K) + al4((long long)N * K), (long long)M * N);
+        go = planes_at(g, wk + pad8((long long)M * K) + pad8((long long)N * K), (long long)M * N);
         const float* src[2] = {g, a};
         bf16* hi[2] = {const_cast<bf16*>(go.hi), const_cast<bf16*>(ao.hi)};
         bf16* lo[2] = {const_cast<bf16*>(go.lo), const_cast<bf16*>(ao.lo)};
@@ -625,7 +567,7 @@ int xggm_linear_bwd_weight(const float* g, const float* a, float* gw, float* gbi
 // work layout of the message-passing entry points: P(x or gout)[B,N,H] | coefficient planes
 long long xggm_adj_apply_work_bytes(int B, int N, int H) {
     if (B < 0 || N <= 0 || H <= 0) return -1;
-    return 4 * (al4((long long)B * N * H) + (N <= 128 ? al4(adj_tc_coef_elems(B, N)) : 0));
+    return 4 * (pad8((long long)B * N * H) + (N <= 128 ? pad8(adj_tc_coef_elems(B, N)) : 0));
 }
 static inline bool adj_tc_ok(const void* work, int N, int H) {
     return work != nullptr && g_precision != XGGM_PREC_FP32_SIMT && adj_tc_supported(N, H);
@@ -636,8 +578,8 @@ static int adj_apply_tc_f32(const float* adj, const float* v, float* out, int B,
                             cudaStream_t st) {
     const long long n = (long long)B * N * H;
     const Operand vo = planes_at(v, work, n);
-    bf16* chi = reinterpret_cast<bf16*>(work + al4(n));
-    bf16* clo = chi + al4(adj_tc_coef_elems(B, N));
+    bf16* chi = reinterpret_cast<bf16*>(work + pad8(n));
+    bf16* clo = chi + pad8(adj_tc_coef_elems(B, N));
     XGGM_TRY(split_one(vo, n, st));
     XGGM_TRY(build_blockdiag(adj, chi, npass() == 3 ? clo : nullptr, B, N, alpha0, alpha_dev, self_w, trans, st));
     return adj_apply_tc(chi, clo, vo.hi, vo.lo, out, nullptr, nullptr, B, N, H, accumulate, npass(), st);
@@ -693,7 +635,7 @@ int xggm_gelu_ln_drop_bwd(const float* gout, const float* z, const float* mean, 
 
 long long xggm_adj_regen_work_bytes(int B, int N, int H) {
     if (B < 0 || N <= 0 || H <= 0) return -1;
-    return 4 * al4((long long)B * N * H);
+    return 4 * pad8((long long)B * N * H);
 }
 int xggm_adj_regen_fwd(const float* x, float* adj_out, float* S, int32_t* amax, int B, int N,
                        int H, int squash, void* work, xggm_stream_t s) {

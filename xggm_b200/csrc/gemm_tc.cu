@@ -728,7 +728,7 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
     return r == CUDA_SUCCESS ? XGGM_OK : XGGM_ERR_ARG;
 }
 
-struct ProfScopeTc;  // (per-launch timing lives in gemm_simt.cu: gemm_prof_begin / gemm_prof_end)
+// per-launch timing lives in gemm_simt.cu
 void* gemm_prof_begin(double flops, cudaStream_t st);
 void gemm_prof_end(void* rec, cudaStream_t st);
 

@@ -1,0 +1,74 @@
+// Internal launcher prototypes shared by the translation units of libxggm_b200.so.
+// Every function enqueues on `st`, returns XGGM_OK or a negative XGGM_ERR_* code and never synchronises.
+//   gemm_simt.cu  exact-fp32 FMA GEMM, column sums, per-launch GEMM timing
+//   gemm_tc.cu    tcgen05 GEMM / Gram / block-diagonal message passing, bf16 plane builders
+//   rowops.cu     LayerNorm and GeLU+LayerNorm+dropout row kernels
+//   graph_ops.cu  per-graph SIMT kernels (message passing, pair scores, adjacency regeneration, GAT attention)
+//   glue.cu       trainer glue (noise, scatter, losses, read-out, masks)
+#pragma once
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace xggm {
+
+int gemm_simt(int op, const float* A, const float* Bm, const float* bias, const float* resid,
+              float* C, int M, int N, int K, int accumulate, cudaStream_t st);
+int colsum(const float* g, float* out, int R, int C, int accumulate, cudaStream_t st);
+bool gemm_tc_supported(int M, int N, int K);
+int gemm_tc(bool a_mn, bool b_mn, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const __nv_bfloat16* b_hi,
+            const __nv_bfloat16* b_lo, const float* bias, const float* resid, float* C, __nv_bfloat16* c_hi,
+            __nv_bfloat16* c_lo, int M, int N, int K, int accumulate, int allow_split_k, int npass, cudaStream_t st);
+bool adj_tc_supported(int N, int H);
+long long adj_tc_coef_elems(int B, int N);
+int build_blockdiag(const float* adj, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int N, float alpha0,
+                    const float* alpha_dev, float self_w, int trans, cudaStream_t st);
+int adj_apply_tc(const __nv_bfloat16* c_hi, const __nv_bfloat16* c_lo, const __nv_bfloat16* x_hi,
+                 const __nv_bfloat16* x_lo, float* out, __nv_bfloat16* o_hi, __nv_bfloat16* o_lo, int B, int N, int H,
+                 int accumulate, int npass, cudaStream_t st);
+bool gram_tc_supported(int N, int H);
+int gram_tc(const __nv_bfloat16* p_hi, const __nv_bfloat16* p_lo, const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo,
+            float* S, int B, int N, int H, int npass, cudaStream_t st);
+int adj_regen_from_s(const float* S, float* adj_out, int32_t* amax, int B, int N, int squash, cudaStream_t st);
+int scale_accum(const float* S, float* out, long long n, float alpha0, const float* alpha_dev, int accumulate,
+                const float* dot_ref, float* dot_out, cudaStream_t st);
+int split_planes(const float* const* src, __nv_bfloat16* const* hi, __nv_bfloat16* const* lo, const long long* n,
+                 int count, cudaStream_t st);
+int split_planes_t(const float* const* src, __nv_bfloat16* const* hi, __nv_bfloat16* const* lo, int R, int C,
+                   int count, cudaStream_t st);
+void gemm_tc_set_debug(unsigned long long* dev_buf);
+int gemm_prof_enable(int on);
+int gemm_prof_read(double* total_ms, long long* launches, double* flops);
+int layernorm_fwd(const float*, const float*, const float*, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, float, cudaStream_t);
+int layernorm_bwd(const float*, const float*, const float*, const float*, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, cudaStream_t);
+int gelu_ln_drop_fwd(const float*, const float*, const float*, const DropSpec&, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, float, int, cudaStream_t);
+int gelu_ln_drop_bwd(const float*, const float*, const float*, const float*, const float*, const DropSpec&, float*, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, cudaStream_t);
+int adj_apply(const float*, const float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, int, float, const float*, float, bool, int, cudaStream_t);
+int bmm_nt(const float*, const float*, float*, int, int, int, float, const float*, int, const float*, float*, cudaStream_t);
+int adj_regen_fwd(const float*, float*, float*, int32_t*, int, int, int, int, cudaStream_t);
+int adj_regen_bwd(const float*, const float*, const float*, const int32_t*, float*, float*, int, int, int, int, int, cudaStream_t);
+int adj_regen_bwd_coeffs(const float* gadj, const float* S, const int32_t* amax, float* D, int B, int N, int squash, cudaStream_t st);
+int gat_attn_fwd(const float*, const float*, const float*, float*, float*, float*, int, int, int, float, int, cudaStream_t);
+int gat_attn_bwd(const float*, const float*, const float*, const float*, const float*, const float*, float*, float*, float*, int, int, int, float, int, cudaStream_t);
+int gelu_fwd(const float*, float*, long long, cudaStream_t);
+int gelu_bwd(const float*, const float*, float*, long long, cudaStream_t);
+int mask_scale(const float*, const uint8_t*, float, float*, long long, cudaStream_t);
+int avg2_drop(const float*, const float*, const uint8_t*, float, float*, long long, cudaStream_t);
+int strip_diag(const float*, float*, int, int, cudaStream_t);
+int triu_scatter_fwd(const float*, float*, int, int, cudaStream_t);
+int triu_scatter_bwd(const float*, float*, int, int, cudaStream_t);
+int edge_noise(const float*, const float*, float, float, float*, float*, int, int, cudaStream_t);
+int feat_noise(const float*, const float*, float, float, float*, float*, int, int, int, int, cudaStream_t);
+int sum_nodes(const float*, float*, int, int, int, cudaStream_t);
+int score_mse_fwd(const float*, const float*, float, float*, long long, cudaStream_t);
+int score_mse_bwd(const float*, const float*, const float*, float, float*, long long, cudaStream_t);
+int sym_kl_fwd(const float*, const float*, float*, int, int, cudaStream_t);
+int sym_kl_bwd(const float*, const float*, const float*, float*, float*, int, int, cudaStream_t);
+int fuse_readout_fwd(const float*, const float*, float*, int, int, int, cudaStream_t);
+int fuse_readout_bwd(const float*, const float*, float*, float*, int, int, int, int, cudaStream_t);
+int sigmoid_fwd(const float*, float*, long long, cudaStream_t);
+int sigmoid_bwd(const float*, const float*, float*, long long, cudaStream_t);
+int keep_mask(uint8_t*, long long, float, uint64_t, uint64_t, const uint64_t*, cudaStream_t);
+
+
+}  // namespace xggm
