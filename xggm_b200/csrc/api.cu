@@ -106,8 +106,8 @@ struct GnnLayout {
     }
     // fwd: u | weight planes | block-diagonal coefficient planes
     long long work_fwd(long long coef) const { return MH + (2 * n_convs + 1) * HH + pad8(coef); }
-    // bwd: buf0 | buf1 | gt | gq | P(grad) | P(gq) | weight planes | S scratch [B,N,N] | coefficient planes | P(grad)'
-    long long work_bwd(long long bnn, long long coef) const { return 7 * MH + (2 * n_convs + 1) * HH + pad8(bnn) + pad8(coef); }
+    // bwd: buf0 | buf1 | gt | gq | R0 | P(gq) | weight planes | S scratch [B,N,N] | coefficient planes | R1 | R2  (R* = gradient regions)
+    long long work_bwd(long long bnn, long long coef) const { return 8 * MH + (2 * n_convs + 1) * HH + pad8(bnn) + pad8(coef); }
 };
 
 // weight planes for one layer live at the tail of the work buffer: conv k -> slot k, head j -> slot nc + j
@@ -147,49 +147,6 @@ static int split_weights(int kind, const float* const* cp, const float* const* h
 
 constexpr int MAX_CONVS = 7;
 
-// ---- independent branches on a side stream ------------------------------------------------------
-// The layer drivers fork work that nothing downstream waits for (read-out heads in the forward pass,
-// weight gradients in the backward pass) onto a per-device side stream and join before returning, so
-// the tail of one kernel overlaps the start of an independent one.  Inside a CUDA-graph capture the
-// fork/join becomes parallel graph branches.  Measured on B200 at B=256 it LOSES 2.5 % (2.378 vs 2.319
-// ms/step): every GEMM is a persistent one-CTA-per-SM kernel, so two of them only contend.  It is
-// therefore off unless XGGM_OVERLAP=1 (kept for larger batches / future non-persistent kernels).
-struct Fork {
-    cudaStream_t side = nullptr;
-    cudaEvent_t from_main = nullptr, join = nullptr, done[2] = {nullptr, nullptr};
-};
-static Fork* get_fork() {
-    static Fork forks[16];
-    static int enabled = -1;
-    if (enabled < 0) {
-        const char* e = getenv("XGGM_OVERLAP");
-        enabled = (e && e[0] == '1') ? 1 : 0;
-    }
-    if (!enabled) return nullptr;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
-    Fork& f = forks[dev];
-    if (!f.side) {
-        if (cudaStreamCreateWithFlags(&f.side, cudaStreamNonBlocking) != cudaSuccess) { f.side = nullptr; return nullptr; }
-        cudaEventCreateWithFlags(&f.from_main, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&f.join, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&f.done[0], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&f.done[1], cudaEventDisableTiming);
-    }
-    return &f;
-}
-// side stream waits for everything enqueued on `st` so far
-static int fork_after(Fork* f, cudaStream_t st) {
-    XGGM_CUDA_TRY(cudaEventRecord(f->from_main, st));
-    XGGM_CUDA_TRY(cudaStreamWaitEvent(f->side, f->from_main, 0));
-    return XGGM_OK;
-}
-static int join_into(Fork* f, cudaStream_t st) {
-    XGGM_CUDA_TRY(cudaEventRecord(f->join, f->side));
-    XGGM_CUDA_TRY(cudaStreamWaitEvent(st, f->join, 0));
-    return XGGM_OK;
-}
-
 // dropout of read-out head j: explicit masks win, then in-kernel Philox, else none
 static inline DropSpec head_drop(const uint8_t* const* keeps, const xggm_philox_t* ph, float drop_p, int j) {
     const float scale = 1.f / (1.f - drop_p);
@@ -197,6 +154,58 @@ static inline DropSpec head_drop(const uint8_t* const* keeps, const xggm_philox_
     if (ph && drop_p > 0.f)
         return DropSpec{nullptr, ph->dev_epoch, ph->seed, ph->stream0 + (uint64_t)j, drop_threshold(drop_p), scale, 2};
     return drop_none();
+}
+
+// ---- grouped projections -------------------------------------------------------------------------
+// Independent products of the same shape share ONE tensor-core launch (gemm_tc_group): the context
+// projection of conv k with read-out head k (both only need h_k), and in the backward pass their two
+// weight gradients and their two input gradients.  A lone 768x768 projection at B=256 is two tiles per
+// CTA pair, so its per-launch fixed cost (prologue, exposed last epilogue, teardown) is ~1/4 of its
+// time; a group pays it once.  The exact-fp32 engine runs the members back to back.
+struct Lin {
+    Operand a, w;              // forward: activations, weight; dgrad: gradient, W^T planes; wgrad: gradient, activations
+    const float* bias;
+    const float* resid;
+    float* out;
+    const Operand* out_planes; // also emit the result as bf16 planes (tensor-core engine only)
+    int accumulate;
+};
+static inline GemmProb as_prob(const Lin& l) {
+    return GemmProb{l.a.hi, l.a.lo, l.w.hi, l.w.lo, l.bias, l.resid, l.out,
+                    l.out_planes ? const_cast<bf16*>(l.out_planes->hi) : nullptr,
+                    l.out_planes ? const_cast<bf16*>(l.out_planes->lo) : nullptr, l.accumulate};
+}
+static int fwd_group(bool tc, const Lin* l, int n, int M, int N, int K, cudaStream_t st) {
+    if (!tc) {
+        for (int i = 0; i < n; ++i)
+            XGGM_TRY(gemm_simt(0, l[i].a.f32, l[i].w.f32, l[i].bias, l[i].resid, l[i].out, M, N, K, 0, st));
+        return XGGM_OK;
+    }
+    GemmProb q[3];
+    for (int i = 0; i < n; ++i) q[i] = as_prob(l[i]);
+    return gemm_tc_group(false, false, q, n, M, N, K, 0, npass(), st);
+}
+// ga[M,K] (+)= g[M,N] w[N,K]   (tensor-core engine: `w` carries the planes of W^T)
+static int dgrad_group(bool tc, const Lin* l, int n, int M, int N, int K, cudaStream_t st) {
+    if (!tc) {
+        for (int i = 0; i < n; ++i)
+            XGGM_TRY(gemm_simt(1, l[i].a.f32, l[i].w.f32, nullptr, nullptr, l[i].out, M, K, N, l[i].accumulate, st));
+        return XGGM_OK;
+    }
+    GemmProb q[3];
+    for (int i = 0; i < n; ++i) q[i] = as_prob(l[i]);
+    return gemm_tc_group(false, false, q, n, M, K, N, 0, npass(), st);
+}
+// gw[N,K] (+)= g[M,N]^T a[M,K]
+static int wgrad_group(bool tc, const Lin* l, int n, int M, int N, int K, cudaStream_t st) {
+    if (!tc) {
+        for (int i = 0; i < n; ++i)
+            XGGM_TRY(gemm_simt(2, l[i].a.f32, l[i].w.f32, nullptr, nullptr, l[i].out, N, K, M, l[i].accumulate, st));
+        return XGGM_OK;
+    }
+    GemmProb q[3];
+    for (int i = 0; i < n; ++i) q[i] = as_prob(l[i]);
+    return gemm_tc_group(true, true, q, n, N, K, M, 1, npass(), st);
 }
 
 static int gnn_fwd(int kind, const float* x, const float* adj, const float* const* cp,
@@ -224,68 +233,50 @@ static int gnn_fwd(int kind, const float* x, const float* adj, const float* cons
     bf16* coef_lo = coef_hi + pad8(adjtc ? adj_tc_coef_elems(B, N) : 0);
     if (adjtc && kind == XGGM_KIND_GCN && nc > 0)
         XGGM_TRY(build_blockdiag(adj, coef_hi, npass() == 3 ? coef_lo : nullptr, B, N, 1.f, nullptr, 0.f, 0, st));
-    // read-out head j only needs h_j: it runs on the side stream while the conv chain continues
-    Fork* fk = (nc > 0) ? get_fork() : nullptr;
-    auto run_head = [&](int j, cudaStream_t hs) -> int {
-        const float* bias = hp[4 * j + 1], *g = hp[4 * j + 2], *b = hp[4 * j + 3];
-        float* z = saved + L.head(j, 0);
-        XGGM_TRY(proj_fwd(tc, hops[j], whead[j], bias, nullptr, z, M, H, H, hs));
-        XGGM_TRY(gelu_ln_drop_fwd(z, g, b, head_drop(keeps, philox, drop_p, j), out,
-                                  saved + L.head(j, 1), saved + L.head(j, 2), nullptr, nullptr, M, H, LN_EPS, j > 0, hs));
-        return XGGM_OK;
+    auto head_lin = [&](int j) -> Lin {   // z_j = h_j W_j^T + b_j
+        return Lin{hops[j], whead[j], hp[4 * j + 1], nullptr, saved + L.head(j, 0), nullptr, 0};
     };
-    if (fk) {
-        XGGM_TRY(fork_after(fk, st));
-        XGGM_TRY(run_head(0, fk->side));
-    }
+    auto head_post = [&](int j) -> int {  // out (+)= dropout(LN(GeLU(z_j)))
+        return gelu_ln_drop_fwd(saved + L.head(j, 0), hp[4 * j + 2], hp[4 * j + 3], head_drop(keeps, philox, drop_p, j), out,
+                                saved + L.head(j, 1), saved + L.head(j, 2), nullptr, nullptr, M, H, LN_EPS, j > 0, st);
+    };
     for (int k = 0; k < nc; ++k) {
         float* h_next = saved + L.conv(k, 2);
         float* pre = saved + L.conv(k, 0);   // GCN: agg = adj @ h ; GIN: pre = h + (1+eps) adj @ h
         Operand pre_op = planes_at(pre, saved + L.conv(k, 5), MHn);
         const Operand next_op = planes_at(h_next, saved + L.conv(k, 6), MHn);
-        if (kind == XGGM_KIND_GCN) {
-            const float* g = cp[3 * k + 1], *b = cp[3 * k + 2];
-            float* xhat = saved + L.conv(k, 1);
-            float* rstd = saved + L.conv(k, 3);
-            float* u = work;
-            // tensor-core engine: the aggregate is only ever a GEMM operand -> bf16 planes, no fp32 copy
-            if (adjtc)
-                XGGM_TRY(adj_apply_tc(coef_hi, coef_lo, hops[k].hi, hops[k].lo, nullptr, mut(pre_op.hi), lo_or_null(pre_op),
-                                      B, N, H, 0, npass(), st));
-            else
-                XGGM_TRY(adj_apply(adj, h, tc ? nullptr : pre, tc ? mut(pre_op.hi) : nullptr, tc ? lo_or_null(pre_op) : nullptr,
-                                   B, N, H, 1.f, nullptr, 0.f, false, 0, st));
-            XGGM_TRY(proj_fwd(tc, pre_op, wconv[k], nullptr, h, u, M, H, H, st));
-            XGGM_TRY(layernorm_fwd(u, g, b, h_next, xhat, rstd, tc ? mut(next_op.hi) : nullptr,
-                                   tc ? lo_or_null(next_op) : nullptr, M, H, LN_EPS, st));
+        const bool gcn = kind == XGGM_KIND_GCN;
+        const float* eps = gcn ? nullptr : cp[5 * k];
+        // tensor-core engine: the aggregate is only ever a GEMM operand -> bf16 planes, no fp32 copy
+        if (adjtc) {
+            if (!gcn) XGGM_TRY(build_blockdiag(adj, coef_hi, npass() == 3 ? coef_lo : nullptr, B, N, 1.f, eps, 1.f, 0, st));
+            XGGM_TRY(adj_apply_tc(coef_hi, coef_lo, hops[k].hi, hops[k].lo, nullptr, mut(pre_op.hi), lo_or_null(pre_op),
+                                  B, N, H, 0, npass(), st));
         } else {
-            const float* eps = cp[5 * k], *bias = cp[5 * k + 2];
-            const float* g = cp[5 * k + 3], *b = cp[5 * k + 4];
-            float* z = saved + L.conv(k, 1);
-            float* mean = saved + L.conv(k, 3);
-            float* rstd = saved + L.conv(k, 4);
-            if (adjtc) {
-                XGGM_TRY(build_blockdiag(adj, coef_hi, npass() == 3 ? coef_lo : nullptr, B, N, 1.f, eps, 1.f, 0, st));
-                XGGM_TRY(adj_apply_tc(coef_hi, coef_lo, hops[k].hi, hops[k].lo, nullptr, mut(pre_op.hi), lo_or_null(pre_op),
-                                      B, N, H, 0, npass(), st));
-            } else {
-                XGGM_TRY(adj_apply(adj, h, tc ? nullptr : pre, tc ? mut(pre_op.hi) : nullptr, tc ? lo_or_null(pre_op) : nullptr,
-                                   B, N, H, 1.f, eps, 1.f, false, 0, st));
-            }
-            XGGM_TRY(proj_fwd(tc, pre_op, wconv[k], bias, nullptr, z, M, H, H, st));
-            XGGM_TRY(gelu_ln_drop_fwd(z, g, b, drop_none(), h_next, mean, rstd, tc ? mut(next_op.hi) : nullptr,
+            XGGM_TRY(adj_apply(adj, h, tc ? nullptr : pre, tc ? mut(pre_op.hi) : nullptr, tc ? lo_or_null(pre_op) : nullptr,
+                               B, N, H, 1.f, eps, gcn ? 0.f : 1.f, false, 0, st));
+        }
+        // conv projection + read-out head k in one launch
+        Lin g[2];
+        if (gcn) g[0] = Lin{pre_op, wconv[k], nullptr, h, work /* u */, nullptr, 0};
+        else g[0] = Lin{pre_op, wconv[k], cp[5 * k + 2], nullptr, saved + L.conv(k, 1) /* z */, nullptr, 0};
+        g[1] = head_lin(k);
+        XGGM_TRY(fwd_group(tc, g, 2, M, H, H, st));
+        if (gcn) {
+            XGGM_TRY(layernorm_fwd(work, cp[3 * k + 1], cp[3 * k + 2], h_next, saved + L.conv(k, 1), saved + L.conv(k, 3),
+                                   tc ? mut(next_op.hi) : nullptr, tc ? lo_or_null(next_op) : nullptr, M, H, LN_EPS, st));
+        } else {
+            XGGM_TRY(gelu_ln_drop_fwd(saved + L.conv(k, 1), cp[5 * k + 3], cp[5 * k + 4], drop_none(), h_next,
+                                      saved + L.conv(k, 3), saved + L.conv(k, 4), tc ? mut(next_op.hi) : nullptr,
                                       tc ? lo_or_null(next_op) : nullptr, M, H, LN_EPS, 0, st));
         }
+        XGGM_TRY(head_post(k));
         hops[k + 1] = next_op;
         h = h_next;
-        if (fk) {   // h_{k+1} (and its planes) exist: head k+1 can go
-            XGGM_TRY(fork_after(fk, st));
-            XGGM_TRY(run_head(k + 1, fk->side));
-        }
     }
-    if (fk) return join_into(fk, st);
-    for (int j = 0; j <= nc; ++j) XGGM_TRY(run_head(j, st));
-    return XGGM_OK;
+    const Lin last = head_lin(nc);
+    XGGM_TRY(fwd_group(tc, &last, 1, M, H, H, st));
+    return head_post(nc);
 }
 
 static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj,
@@ -315,9 +306,10 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
     float* saved = const_cast<float*>(saved_c);  // plane regions are read-only here; the cast only feeds planes_at
     const GnnLayout L(kind, M, H, nc);
     const bool tc = use_tc(M, H, H);
+    const bool gcn = kind == XGGM_KIND_GCN;
     const long long MH = L.MH, MHn = (long long)M * H;
     float* buf[2] = {work, work + MH};
-    float* gt = work + 2 * MH;  // gz / gu
+    float* gt = work + 2 * MH;  // GIN: gz of the conv (exact engine only; planes otherwise)
     float* gq = work + 3 * MH;
     Operand wconv[MAX_CONVS], whead[MAX_CONVS + 1];
     XGGM_TRY(split_weights(kind, cp, hp, work + 6 * MH, L, H, wconv, whead, tc, true, st));
@@ -330,70 +322,85 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
     const bool adjtc = gram && adj_tc_supported(N, H);   // needs the planes of gq the Gram path already emits
     bf16* coef_hi = reinterpret_cast<bf16*>(s_scratch + pad8(BNN));
     bf16* coef_lo = coef_hi + pad8(adjtc ? adj_tc_coef_elems(B, N) : 0);
-    if (adjtc && kind == XGGM_KIND_GCN && nc > 0)   // adj^T coefficients, shared by every conv of the layer
+    if (adjtc && gcn && nc > 0)   // adj^T coefficients, shared by every conv of the layer
         XGGM_TRY(build_blockdiag(adj, coef_hi, npass() == 3 ? coef_lo : nullptr, B, N, 1.f, nullptr, 0.f, 1, st));
 
     auto act = [&](int j) -> Operand {   // h_j as a GEMM operand (planes saved by the forward pass)
         return j == 0 ? planes_at(x, saved + L.xplanes, MHn)
                       : planes_at(saved + L.conv(j - 1, 2), saved + L.conv(j - 1, 6), MHn);
     };
-    // Gradient tensor `g32` as an operand: its planes ping-pong between two scratch regions, because the
-    // weight-gradient GEMM that reads them runs on the side stream while the main stream already
-    // produces the next gradient.  Before region i is overwritten, main waits for the wgrad that read it.
-    Fork* fk = tc ? get_fork() : nullptr;
+    // Three gradient regions of [M,H] floats each: bf16 planes under the tensor-core engine (the fp32
+    // tensor never exists), the fp32 tensor itself under the exact engine.
+    //   R0 conv-level gradient (gu / gz of conv k), R1 gz of head k, R2 gz of the last head
     const long long coef_floats = N <= 128 ? pad8(adj_tc_coef_elems(B, N)) : 0;   // as in xggm_gnn_work_floats
-    float* grad_region[2] = {work + 4 * MH, s_scratch + pad8(BNN) + coef_floats};
-    int n_grad = 0;
-    auto grad_op = [&](const float* g32) -> Operand {
-        const int slot = fk ? (n_grad & 1) : 0;
-        if (fk && n_grad >= 2) cudaStreamWaitEvent(st, fk->done[slot], 0);
-        return planes_at(g32, grad_region[slot], MHn);
-    };
-    // weight gradient: a leaf of the backward graph
-    auto wgrad = [&](const Operand& g, const Operand& a, float* gw) -> int {
-        if (!fk) return proj_wgrad(tc, g, a, gw, M, H, H, acc, st);
-        XGGM_TRY(fork_after(fk, st));
-        XGGM_TRY(proj_wgrad(tc, g, a, gw, M, H, H, acc, fk->side));
-        XGGM_CUDA_TRY(cudaEventRecord(fk->done[n_grad & 1], fk->side));
-        ++n_grad;
-        return XGGM_OK;
-    };
-
-    // head j contributes gz_j -> (gW_j, gb_j, ggamma_j, gbeta_j) and gz_j W_j into grad of h_j
-    auto head_bwd = [&](int j, float* gh, int accumulate) -> int {
+    float* R[3] = {work + 4 * MH, s_scratch + pad8(BNN) + coef_floats, s_scratch + pad8(BNN) + coef_floats + MH};
+    // head j: gz_j (as planes or fp32 in `region`) and the bias / gamma / beta gradients
+    auto head_gz = [&](int j, float* region) -> int {
         if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(hg[4 * j + 2], 0, sizeof(float) * H, st));
         if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(hg[4 * j + 3], 0, sizeof(float) * H, st));
         if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(hg[4 * j + 1], 0, sizeof(float) * H, st));
-        // gz only exists as GEMM-operand planes under the tensor-core engine; its column sums (the
-        // bias gradient) are accumulated by the same kernel
-        const Operand g = grad_op(gt);
-        XGGM_TRY(gelu_ln_drop_bwd(gout, saved + L.head(j, 0), saved + L.head(j, 1), saved + L.head(j, 2),
-                                  hp[4 * j + 2], head_drop(keeps, philox, drop_p, j), tc ? nullptr : gt,
-                                  hg[4 * j + 2], hg[4 * j + 3], hg[4 * j + 1], tc ? mut(g.hi) : nullptr,
-                                  tc ? lo_or_null(g) : nullptr, M, H, st));
-        XGGM_TRY(wgrad(g, act(j), hg[4 * j]));
-        XGGM_TRY(proj_dgrad(tc, g, whead[j], gh, M, H, H, accumulate, st));
-        return XGGM_OK;
+        const Operand g = planes_at(region, region, MHn);
+        return gelu_ln_drop_bwd(gout, saved + L.head(j, 0), saved + L.head(j, 1), saved + L.head(j, 2),
+                                hp[4 * j + 2], head_drop(keeps, philox, drop_p, j), tc ? nullptr : region,
+                                hg[4 * j + 2], hg[4 * j + 3], hg[4 * j + 1], tc ? mut(g.hi) : nullptr,
+                                tc ? lo_or_null(g) : nullptr, M, H, st);
     };
 
     int cur = 0;
     float* gh = (nc == 0) ? gx : buf[cur];
-    XGGM_TRY(head_bwd(nc, gh, 0));
+    // last head: its input gradient starts the chain; its weight gradient rides with the first conv level's
+    XGGM_TRY(head_gz(nc, R[2]));
+    const Operand gzN = planes_at(R[2], R[2], MHn);
+    Lin pending_w = Lin{gzN, act(nc), nullptr, nullptr, hg[4 * nc], nullptr, acc};
+    {
+        const Lin d = Lin{gzN, whead[nc], nullptr, nullptr, gh, nullptr, 0};
+        XGGM_TRY(dgrad_group(tc, &d, 1, M, H, H, st));
+    }
+    bool have_pending = true;
     for (int k = nc - 1; k >= 0; --k) {
         const float* hk = (k == 0) ? x : saved + L.conv(k - 1, 2);
         float* gnext = (k == 0) ? gx : buf[cur ^ 1];
         const Operand pre_op = planes_at(saved + L.conv(k, 0), saved + L.conv(k, 5), MHn);
-        if (kind == XGGM_KIND_GCN) {
-            const float* g = cp[3 * k + 1];
+        // conv-level gradient g0: GCN gu = LN backward (also the residual path: written into gnext);
+        // GIN gz of the conv's GeLU+LN
+        const float* g0_f32 = gcn ? gnext : gt;
+        const Operand g0 = planes_at(g0_f32, R[0], MHn);
+        const float* eps = gcn ? nullptr : cp[5 * k];
+        if (gcn) {
             if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(cg[3 * k + 1], 0, sizeof(float) * H, st));
             if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(cg[3 * k + 2], 0, sizeof(float) * H, st));
-            // gu = LN backward, written straight into the next-level gradient (residual path)
-            const Operand gu = grad_op(gnext);
-            XGGM_TRY(layernorm_bwd(gh, saved + L.conv(k, 1), saved + L.conv(k, 3), g, gnext,
-                                   cg[3 * k + 1], cg[3 * k + 2], tc ? mut(gu.hi) : nullptr,
-                                   tc ? lo_or_null(gu) : nullptr, M, H, st));
-            XGGM_TRY(wgrad(gu, pre_op, cg[3 * k]));
-            XGGM_TRY(proj_dgrad(tc, gu, wconv[k], gq, M, H, H, 0, st, gram ? &gq_op : nullptr));  // gq = gu Wc
+            XGGM_TRY(layernorm_bwd(gh, saved + L.conv(k, 1), saved + L.conv(k, 3), cp[3 * k + 1], gnext,
+                                   cg[3 * k + 1], cg[3 * k + 2], tc ? mut(g0.hi) : nullptr,
+                                   tc ? lo_or_null(g0) : nullptr, M, H, st));
+        } else {
+            if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k], 0, sizeof(float), st));
+            if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k + 3], 0, sizeof(float) * H, st));
+            if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k + 4], 0, sizeof(float) * H, st));
+            if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k + 2], 0, sizeof(float) * H, st));
+            XGGM_TRY(gelu_ln_drop_bwd(gh, saved + L.conv(k, 1), saved + L.conv(k, 3), saved + L.conv(k, 4),
+                                      cp[5 * k + 3], drop_none(), tc ? nullptr : gt, cg[5 * k + 3], cg[5 * k + 4], cg[5 * k + 2],
+                                      tc ? mut(g0.hi) : nullptr, tc ? lo_or_null(g0) : nullptr, M, H, st));
+        }
+        XGGM_TRY(head_gz(k, R[1]));
+        const Operand g1 = planes_at(R[1], R[1], MHn);
+        // weight gradients of the conv projection and of head k (+ the pending last head) in one launch
+        {
+            Lin w[3];
+            int n = 0;
+            w[n++] = Lin{g0, pre_op, nullptr, nullptr, gcn ? cg[3 * k] : cg[5 * k + 1], nullptr, acc};
+            w[n++] = Lin{g1, act(k), nullptr, nullptr, hg[4 * k], nullptr, acc};
+            if (have_pending) { w[n++] = pending_w; have_pending = false; }
+            XGGM_TRY(wgrad_group(tc, w, n, M, H, H, st));
+        }
+        // input gradients: gq = g0 Wc (with planes for the Gram / message-passing kernels) and
+        // gnext (+)= gz_k W_k.  GCN: gnext already holds gu; GIN: gnext is first written here.
+        {
+            Lin d[2];
+            d[0] = Lin{g0, wconv[k], nullptr, nullptr, gq, gram ? &gq_op : nullptr, 0};
+            d[1] = Lin{g1, whead[k], nullptr, nullptr, gnext, nullptr, gcn ? 1 : 0};
+            XGGM_TRY(dgrad_group(tc, d, 2, M, H, H, st));
+        }
+        if (gcn) {
             if (!gadj) {
                 // adjacency is a constant input (e.g. the ground-truth graph of the node branch): no gq h^T
             } else if (gram) {   // gadj += gq h_k^T
@@ -408,17 +415,6 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
             else
                 XGGM_TRY(adj_apply(adj, gq, gnext, nullptr, nullptr, B, N, H, 1.f, nullptr, 0.f, true, 1, st));
         } else {
-            const float* eps = cp[5 * k], *g = cp[5 * k + 3];
-            if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k], 0, sizeof(float), st));
-            if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k + 3], 0, sizeof(float) * H, st));
-            if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k + 4], 0, sizeof(float) * H, st));
-            if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k + 2], 0, sizeof(float) * H, st));
-            const Operand gz = grad_op(gt);
-            XGGM_TRY(gelu_ln_drop_bwd(gh, saved + L.conv(k, 1), saved + L.conv(k, 3), saved + L.conv(k, 4),
-                                      g, drop_none(), tc ? nullptr : gt, cg[5 * k + 3], cg[5 * k + 4], cg[5 * k + 2],
-                                      tc ? mut(gz.hi) : nullptr, tc ? lo_or_null(gz) : nullptr, M, H, st));
-            XGGM_TRY(wgrad(gz, pre_op, cg[5 * k + 1]));
-            XGGM_TRY(proj_dgrad(tc, gz, wconv[k], gq, M, H, H, 0, st, gram ? &gq_op : nullptr));      // gpre
             // gadj += (1+eps) gpre h^T ; geps += <gpre h^T, adj>
             if (gram) {
                 const Operand hk_op = act(k);
@@ -427,19 +423,18 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
             } else {
                 XGGM_TRY(bmm_nt(gq, hk, gadj, B, N, H, 1.f, eps, 1, adj, cg[5 * k], st));
             }
-            // grad h_k = gpre + (1+eps) adj^T gpre
+            // grad h_k += gpre + (1+eps) adj^T gpre
             if (adjtc) {
                 XGGM_TRY(build_blockdiag(adj, coef_hi, npass() == 3 ? coef_lo : nullptr, B, N, 1.f, eps, 1.f, 1, st));
-                XGGM_TRY(adj_apply_tc(coef_hi, coef_lo, gq_op.hi, gq_op.lo, gnext, nullptr, nullptr, B, N, H, 0, npass(), st));
+                XGGM_TRY(adj_apply_tc(coef_hi, coef_lo, gq_op.hi, gq_op.lo, gnext, nullptr, nullptr, B, N, H, 1, npass(), st));
             } else {
-                XGGM_TRY(adj_apply(adj, gq, gnext, nullptr, nullptr, B, N, H, 1.f, eps, 1.f, true, 0, st));
+                XGGM_TRY(adj_apply(adj, gq, gnext, nullptr, nullptr, B, N, H, 1.f, eps, 1.f, true, 1, st));
             }
         }
-        XGGM_TRY(head_bwd(k, gnext, 1));
         gh = gnext;
         cur ^= 1;
     }
-    if (fk) XGGM_TRY(join_into(fk, st));
+    if (have_pending) XGGM_TRY(wgrad_group(tc, &pending_w, 1, M, H, H, st));
     return XGGM_OK;
 }
 

@@ -25,6 +25,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "kernels.cuh"
 
 namespace xggm {
 namespace tc {
@@ -219,19 +220,36 @@ __device__ __forceinline__ void red_add_v4(float* addr, const float4& v) {
                  : "memory");
 }
 
+// One launch can carry up to MAX_GROUP independent products of the SAME shape and operand layout
+// (e.g. the context projection and the read-out head of one conv level, or their two weight
+// gradients): the tile list is the concatenation of the problems' tiles, so the per-launch fixed
+// cost (prologue, exposed last epilogue, teardown) is paid once per group instead of once per product.
+constexpr int MAX_GROUP = 3;
+struct ProbOut {
+    const float* bias;   // [N] or null
+    const float* resid;  // [M,N] or null
+    float* C;
+    __nv_bfloat16* c_hi; // optional: also emit C as bf16 planes (vec4 mode only; operand of a later GEMM)
+    __nv_bfloat16* c_lo;
+    int accumulate;      // C += (non-atomic)
+    int pad_;
+};
+struct MapSet {
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+};
+struct GroupMaps {
+    MapSet m[MAX_GROUP];
+};
 struct Params {
     int M, N;            // output extent
     int num_kb;          // ceil(K / BK)
     int tiles_m, tiles_n, splits, kb_per_split;
-    const float* bias;   // [N] or null
-    const float* resid;  // [M,N] or null
-    float* C;
+    int group;           // number of problems in this launch (1..MAX_GROUP)
+    int tiles_per_prob;  // tiles_m * tiles_n * splits
+    ProbOut pr[MAX_GROUP];
     int ldc;
-    int accumulate;      // C += (non-atomic)
     int atomic;          // split-K partial sums: atomicAdd into a pre-zeroed / pre-initialised C
     int vec4;            // C / resid / bias are 16-byte aligned and N % 4 == 0: float4 epilogue
-    __nv_bfloat16* c_hi; // optional: also emit C as bf16 planes (vec4 mode only; operand of a later GEMM)
-    __nv_bfloat16* c_lo;
     // Batched per-graph Gram mode (gram_n > 0): A and B are the SAME-row tiles of two [M,K] K-major
     // tensors, tile t covers the gram_g complete graphs starting at row t*gram_g*gram_n, and only the
     // gram_n x gram_n diagonal blocks  S[b] = P[b] Q[b]^T  are written to C[B][gram_n][gram_n].
@@ -263,9 +281,7 @@ struct Cfg {
 
 template <int BN, int NPASS, bool A_MN, bool B_MN, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-               const Params p) {
+gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const Params p) {
     using C = Cfg<BN, NPASS, CG>;
     static_assert(CG == 1 || (!A_MN && !B_MN), "the CTA-pair kernel takes K-major operands");
     extern __shared__ uint8_t smem_raw[];
@@ -281,7 +297,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_tiles = p.tiles_m * p.tiles_n * p.splits;
+    const int num_tiles = p.tiles_per_prob * p.group;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;       // 0 = pair leader (issues the MMAs)
     const int worker = blockIdx.x / CG, num_workers = gridDim.x / CG;  // a worker = a CTA or a CTA pair
     const bool trace = p.dbg != nullptr && blockIdx.x == 0;
@@ -289,11 +305,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (threadIdx.x == 0) XGGM_TRACE(0);
 
     if (threadIdx.x == 0) {
-        prefetch_tmap(&map_a_hi);
-        prefetch_tmap(&map_b_hi);
-        if (NPASS == 3) {
-            prefetch_tmap(&map_a_lo);
-            prefetch_tmap(&map_b_lo);
+        for (int g = 0; g < p.group; ++g) {
+            prefetch_tmap(&maps.m[g].a_hi);
+            prefetch_tmap(&maps.m[g].b_hi);
+            if (NPASS == 3) {
+                prefetch_tmap(&maps.m[g].a_lo);
+                prefetch_tmap(&maps.m[g].b_lo);
+            }
         }
         for (int s = 0; s < C::STAGES; ++s) {
             mbar_init(&full[s], 1);
@@ -322,8 +340,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = worker; tile < num_tiles; tile += num_workers) {
-                const int sp = tile % p.splits;
-                const int mn = tile / p.splits;
+                const int prob = tile / p.tiles_per_prob, t = tile - prob * p.tiles_per_prob;
+                const MapSet& ms = maps.m[prob];
+                const int sp = t % p.splits;
+                const int mn = t / p.splits;
                 int m0 = (mn / p.tiles_n) * (BM * CG) + (int)rank * BM, n0 = (mn % p.tiles_n) * BN;
                 if (p.gram_n > 0) m0 = n0 = mn * p.gram_g * p.gram_n;
                 const int b_krow0 = p.bd_stride > 0 ? (mn / p.tiles_n) * p.bd_stride : 0;   // block-diagonal mode
@@ -339,8 +359,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         const int k0 = kb * BK;
 #pragma unroll
                         for (int pl = 0; pl < C::NPLANE; ++pl) {
-                            tma_load_2d_pair(sa + pl * C::A_TILE, pl == 0 ? &map_a_hi : &map_a_lo, lead_full, k0, m0);
-                            tma_load_2d_pair(sb + pl * C::B_TILE, pl == 0 ? &map_b_hi : &map_b_lo, lead_full, k0,
+                            tma_load_2d_pair(sa + pl * C::A_TILE, pl == 0 ? &ms.a_hi : &ms.a_lo, lead_full, k0, m0);
+                            tma_load_2d_pair(sb + pl * C::B_TILE, pl == 0 ? &ms.b_hi : &ms.b_lo, lead_full, k0,
                                              n0 + (int)rank * (BN / 2));
                         }
                         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -352,8 +372,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     const int k0 = kb * BK;
 #pragma unroll
                     for (int pl = 0; pl < C::NPLANE; ++pl) {
-                        const CUtensorMap* ma = pl == 0 ? &map_a_hi : &map_a_lo;
-                        const CUtensorMap* mb = pl == 0 ? &map_b_hi : &map_b_lo;
+                        const CUtensorMap* ma = pl == 0 ? &ms.a_hi : &ms.a_lo;
+                        const CUtensorMap* mb = pl == 0 ? &ms.b_hi : &ms.b_lo;
                         if (A_MN) {
 #pragma unroll
                             for (int i = 0; i < BM / 64; ++i)
@@ -434,8 +454,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = worker; tile < num_tiles; tile += num_workers) {
-            const int mn = tile / p.splits;
-            const int sp = tile % p.splits;
+            const int prob = tile / p.tiles_per_prob, t = tile - prob * p.tiles_per_prob;
+            const ProbOut po = p.pr[prob];
+            const int mn = t / p.splits;
+            const int sp = t % p.splits;
             const int n0 = (mn % p.tiles_n) * BN;
             const int m0 = p.bd_stride > 0 ? (mn / p.tiles_n) * p.bd_stride
                                            : (mn / p.tiles_n) * (BM * CG) + (int)rank * BM;
@@ -455,8 +477,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 const int nv = n0 + cc * 32 + c4;
                 const bool ok = vec && cc < BN / 32 && nv < p.N && rows > 0;   // N % 4 == 0 in vec mode
                 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ok && lead && p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + nv));
-                const float* src = (lead && p.resid) ? p.resid : ((p.accumulate && !p.atomic) ? p.C : nullptr);
+                if (ok && lead && po.bias) bv = __ldg(reinterpret_cast<const float4*>(po.bias + nv));
+                const float* src = (lead && po.resid) ? po.resid : ((po.accumulate && !p.atomic) ? po.C : nullptr);
 #pragma unroll
                 for (int it = 0; it < 8; ++it) {
                     const int row = 4 * it + rsub;
@@ -482,7 +504,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 const bool row_ok = r < span && b < p.gram_b;
                 const int lo_col = (q * 32) / gn * gn;                       // warp-uniform column window
                 const int hi_col = min(span, ((q * 32 + 31) / gn + 1) * gn);
-                float* orow = p.C + (b * gn + (r - gl * gn)) * gn - gl * gn;  // orow[col] = S[b][i][col - gl*gn]
+                float* orow = po.C + (b * gn + (r - gl * gn)) * gn - gl * gn;  // orow[col] = S[b][i][col - gl*gn]
 #pragma unroll 1
                 for (int c = csub; c < BN / 32; c += CSTEP) {
                     if (c * 32 + 32 <= lo_col || c * 32 >= hi_col) continue;  // warp-uniform
@@ -521,7 +543,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 if (vec) {
                     const int nv = ncol0 + c4;
                     if (nv < p.N) {
-                        const bool both = lead && p.resid && p.accumulate && !p.atomic;   // rare: second addend read late
+                        const bool both = lead && po.resid && po.accumulate && !p.atomic;   // rare: second addend read late
                         float4 o[8];
 #pragma unroll
                         for (int it = 0; it < 8; ++it) {
@@ -535,26 +557,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                             if (row < rows) {
                                 const size_t off = (size_t)(mrow0 + row) * p.ldc + nv;
                                 if (both) {
-                                    const float4 a = *reinterpret_cast<const float4*>(p.C + off);
+                                    const float4 a = *reinterpret_cast<const float4*>(po.C + off);
                                     o[it].x += a.x; o[it].y += a.y; o[it].z += a.z; o[it].w += a.w;
                                 }
-                                if (p.atomic) red_add_v4(p.C + off, o[it]);   // split-K partial sum
-                                else if (p.C) *reinterpret_cast<float4*>(p.C + off) = o[it];
-                                if (p.c_hi) store_planes4(p.c_hi, p.c_lo, off, o[it]);
+                                if (p.atomic) red_add_v4(po.C + off, o[it]);   // split-K partial sum
+                                else if (po.C) *reinterpret_cast<float4*>(po.C + off) = o[it];
+                                if (po.c_hi) store_planes4(po.c_hi, po.c_lo, off, o[it]);
                             }
                         }
                     }
                 } else {
                     const int n = ncol0 + lane;
                     if (n < p.N) {
-                        const float bv = (lead && p.bias) ? p.bias[n] : 0.f;
+                        const float bv = (lead && po.bias) ? po.bias[n] : 0.f;
 #pragma unroll 4
                         for (int i = 0; i < rows; ++i) {
                             float val = st[i * EPI_PITCH + lane] + bv;
                             const size_t o = (size_t)(mrow0 + i) * p.ldc + n;
-                            if (lead && p.resid) val += p.resid[o];
-                            if (p.atomic) atomicAdd(&p.C[o], val);
-                            else p.C[o] = p.accumulate ? p.C[o] + val : val;
+                            if (lead && po.resid) val += po.resid[o];
+                            if (p.atomic) atomicAdd(&po.C[o], val);
+                            else po.C[o] = po.accumulate ? po.C[o] + val : val;
                         }
                     }
                 }
@@ -746,8 +768,7 @@ static int num_sms() {
 }
 
 template <int BN, int NPASS, bool A_MN, bool B_MN, int CG = 1>
-static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
-                     const tc::Params& p, int grid, cudaStream_t st) {
+static int launch_tc(const tc::GroupMaps& maps, const tc::Params& p, int grid, cudaStream_t st) {
     using C = tc::Cfg<BN, NPASS, CG>;
     static bool attr_set = false;
     auto kern = tc::gemm_tc_kernel<BN, NPASS, A_MN, B_MN, CG>;
@@ -756,7 +777,7 @@ static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtenso
         attr_set = true;
     }
     if (CG == 1) {
-        kern<<<grid, tc::NUM_THREADS, C::SMEM, st>>>(ah, al, bh, bl, p);
+        kern<<<grid, tc::NUM_THREADS, C::SMEM, st>>>(maps, p);
     } else {  // CTA pairs: clusters of 2 (same TPC) so cta_group::2 MMAs can span both SMs
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid);
@@ -770,7 +791,7 @@ static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtenso
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        XGGM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ah, al, bh, bl, p));
+        XGGM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, maps, p));
     }
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
@@ -787,11 +808,11 @@ static bool pair_enabled() {
 }
 
 template <int BN, int NPASS>
-static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
-                          const CUtensorMap& bl, const tc::Params& p, int grid, cudaStream_t st) {
-    if (!a_mn && !b_mn) return launch_tc<BN, NPASS, false, false>(ah, al, bh, bl, p, grid, st);
-    if (!a_mn && b_mn) return launch_tc<BN, NPASS, false, true>(ah, al, bh, bl, p, grid, st);
-    if (a_mn && b_mn) return launch_tc<BN, NPASS, true, true>(ah, al, bh, bl, p, grid, st);
+static int dispatch_major(bool a_mn, bool b_mn, const tc::GroupMaps& maps, const tc::Params& p, int grid,
+                          cudaStream_t st) {
+    if (!a_mn && !b_mn) return launch_tc<BN, NPASS, false, false>(maps, p, grid, st);
+    if (!a_mn && b_mn) return launch_tc<BN, NPASS, false, true>(maps, p, grid, st);
+    if (a_mn && b_mn) return launch_tc<BN, NPASS, true, true>(maps, p, grid, st);
     return XGGM_ERR_UNSUPPORTED;  // (MN-major A with K-major B is not needed by a Linear layer)
 }
 
@@ -800,113 +821,117 @@ bool gemm_tc_supported(int M, int N, int K) {
     return M > 0 && N > 0 && K > 0 && (N % 8 == 0) && (K % 8 == 0);
 }
 
+static void single_problem(tc::Params& p, const float* bias, const float* resid, float* C, __nv_bfloat16* c_hi,
+                           __nv_bfloat16* c_lo, int accumulate) {
+    p.group = 1;
+    p.tiles_per_prob = p.tiles_m * p.tiles_n * p.splits;
+    for (int g = 0; g < tc::MAX_GROUP; ++g) p.pr[g] = tc::ProbOut{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
+    p.pr[0] = tc::ProbOut{bias, resid, C, c_hi, c_lo, accumulate, 0};
+}
+
+// `count` (1..3) products of the same shape in ONE launch.
 // A planes: a_mn ? [K,M] : [M,K];  B planes: b_mn ? [K,N] : [N,K].  lo planes may be null when npass == 1.
-int gemm_tc(bool a_mn, bool b_mn, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const __nv_bfloat16* b_hi,
-            const __nv_bfloat16* b_lo, const float* bias, const float* resid, float* C, __nv_bfloat16* c_hi,
-            __nv_bfloat16* c_lo, int M, int N, int K, int accumulate, int allow_split_k, int npass, cudaStream_t st) {
-    if (M <= 0 || N <= 0 || K <= 0) return XGGM_OK;
-    XGGM_REQUIRE(a_hi && b_hi && C && (npass == 1 || (npass == 3 && a_lo && b_lo)));
+int gemm_tc_group(bool a_mn, bool b_mn, const GemmProb* pr, int count, int M, int N, int K, int allow_split_k,
+                  int npass, cudaStream_t st) {
+    if (M <= 0 || N <= 0 || K <= 0 || count <= 0) return XGGM_OK;
+    XGGM_REQUIRE(pr && count <= tc::MAX_GROUP && (npass == 1 || npass == 3));
+    for (int g = 0; g < count; ++g)
+        XGGM_REQUIRE(pr[g].a_hi && pr[g].b_hi && pr[g].C && (npass == 1 || (pr[g].a_lo && pr[g].b_lo)));
     const int sms = num_sms();
     const int num_kb = ceil_div(K, tc::BK);
-    if (!a_mn && !b_mn && M > tc::BM && pair_enabled() && sms % 2 == 0) {
-        // K-major x K-major (forward, and dgrad against transposed weight planes): CTA-pair kernel,
-        // 256 x 192 tiles, cta_group::2 MMAs, each CTA stages half of the B tile.
-        constexpr int PBN = 192;
-        CUtensorMap ah, al, bh, bl;
-        XGGM_TRY(make_map(&ah, a_hi, M, K, tc::BM));
-        XGGM_TRY(make_map(&bh, b_hi, N, K, PBN / 2));
-        if (npass == 3) {
-            XGGM_TRY(make_map(&al, a_lo, M, K, tc::BM));
-            XGGM_TRY(make_map(&bl, b_lo, N, K, PBN / 2));
-        } else {
-            al = ah;
-            bl = bh;
+    const bool pair = !a_mn && !b_mn && M > tc::BM && pair_enabled() && sms % 2 == 0;
+    // K-major x K-major (forward, and dgrad against transposed weight planes): CTA-pair kernel,
+    // 256 x 192 tiles, cta_group::2 MMAs, each CTA stages half of the B tile.
+    constexpr int PBN = 192;
+    int bn = PBN, splits = 1, tiles_m = ceil_div(M, 2 * tc::BM);
+    if (!pair) {
+        tiles_m = ceil_div(M, tc::BM);
+        // tile width: fewest "waves x width"; ties go to the wider tile (less A re-read)
+        long long best = -1;
+        const int cand[2] = {192, 128};
+        int splits_for[2] = {1, 1};
+        for (int ci = 0; ci < 2; ++ci) {
+            const int w = cand[ci];
+            const int tn = ceil_div(N, w);
+            int sp = 1;
+            if (allow_split_k) sp = max(1, min(num_kb / 4, sms / max(1, tiles_m * tn * count)));
+            splits_for[ci] = sp;
+            const long long kb_per = ceil_div(num_kb, sp);
+            const long long waves = ceil_div((long long)tiles_m * tn * sp * count, sms);
+            const long long cost = waves * w * kb_per;
+            if (best < 0 || cost < best) { best = cost; bn = w; }
         }
-        tc::Params p;
-        p.M = M; p.N = N; p.num_kb = num_kb;
-        p.tiles_m = ceil_div(M, 2 * tc::BM); p.tiles_n = ceil_div(N, PBN); p.splits = 1; p.kb_per_split = num_kb;
-        p.bias = bias; p.resid = resid; p.C = C; p.ldc = N;
-        p.accumulate = accumulate; p.atomic = 0;
-        p.vec4 = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(resid) |
-                                   reinterpret_cast<uintptr_t>(bias)) & 15) == 0;
-        p.c_hi = c_hi; p.c_lo = npass == 3 ? c_lo : nullptr;
-        p.gram_n = p.gram_g = p.gram_b = 0;
-        p.bd_stride = 0;
-        p.dbg = g_tc_dbg;
-        if (c_hi && (!p.vec4 || (reinterpret_cast<uintptr_t>(c_hi) & 7) || (reinterpret_cast<uintptr_t>(c_lo) & 7)))
-            return XGGM_ERR_ARG;
-        const int grid = 2 * min(sms / 2, p.tiles_m * p.tiles_n);
-        void* prof = gemm_prof_begin(2.0 * M * N * K, st);
-        const int rc = npass == 3 ? launch_tc<PBN, 3, false, false, 2>(ah, al, bh, bl, p, grid, st)
-                                  : launch_tc<PBN, 1, false, false, 2>(ah, al, bh, bl, p, grid, st);
-        gemm_prof_end(prof, st);
-        return rc;
+        splits = splits_for[bn == 192 ? 0 : 1];
     }
-    const int tiles_m = ceil_div(M, tc::BM);
-    // tile width: fewest "waves x width"; ties go to the wider tile (less A re-read)
-    int bn = 128;
-    long long best = -1;
-    const int cand[2] = {192, 128};
-    int splits_for[2] = {1, 1};
-    for (int ci = 0; ci < 2; ++ci) {
-        const int w = cand[ci];
-        const int tn = ceil_div(N, w);
-        int splits = 1;
-        if (allow_split_k) {
-            splits = max(1, min(num_kb / 4, sms / max(1, tiles_m * tn)));
-        }
-        splits_for[ci] = splits;
-        const long long kb_per = ceil_div(num_kb, splits);
-        const long long waves = ceil_div((long long)tiles_m * tn * splits, sms);
-        const long long cost = waves * w * kb_per;
-        if (best < 0 || cost < best) { best = cost; bn = w; }
-    }
-    int splits = splits_for[bn == 192 ? 0 : 1];
     const int tiles_n = ceil_div(N, bn);
-    int kb_per_split = ceil_div(num_kb, splits);
+    const int kb_per_split = ceil_div(num_kb, splits);
     splits = ceil_div(num_kb, kb_per_split);
 
-    CUtensorMap ah, al, bh, bl;
     const long long a_rows = a_mn ? K : M, a_cols = a_mn ? M : K;
     const long long b_rows = b_mn ? K : N, b_cols = b_mn ? N : K;
-    const int a_box = a_mn ? tc::BK : tc::BM, b_box = b_mn ? tc::BK : bn;
-    XGGM_TRY(make_map(&ah, a_hi, a_rows, a_cols, a_box));
-    XGGM_TRY(make_map(&bh, b_hi, b_rows, b_cols, b_box));
-    if (npass == 3) {
-        XGGM_TRY(make_map(&al, a_lo, a_rows, a_cols, a_box));
-        XGGM_TRY(make_map(&bl, b_lo, b_rows, b_cols, b_box));
-    } else {
-        al = ah;
-        bl = bh;
-    }
+    const int a_box = a_mn ? tc::BK : tc::BM, b_box = b_mn ? tc::BK : (pair ? PBN / 2 : bn);
+    tc::GroupMaps maps;
     tc::Params p;
     p.M = M; p.N = N; p.num_kb = num_kb;
     p.tiles_m = tiles_m; p.tiles_n = tiles_n; p.splits = splits; p.kb_per_split = kb_per_split;
-    p.bias = bias; p.resid = resid; p.C = C; p.ldc = N;
-    p.accumulate = accumulate; p.atomic = splits > 1 ? 1 : 0;
-    p.vec4 = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(resid) |
-                               reinterpret_cast<uintptr_t>(bias)) & 15) == 0;
-    p.c_hi = c_hi; p.c_lo = npass == 3 ? c_lo : nullptr;
+    p.group = count; p.tiles_per_prob = tiles_m * tiles_n * splits;
+    p.ldc = N;
+    p.atomic = splits > 1 ? 1 : 0;
+    p.vec4 = (N % 4 == 0);
     p.gram_n = p.gram_g = p.gram_b = 0;
     p.bd_stride = 0;
     p.dbg = g_tc_dbg;
-    if (c_hi && (!p.vec4 || p.atomic || (reinterpret_cast<uintptr_t>(c_hi) & 7) || (reinterpret_cast<uintptr_t>(c_lo) & 7)))
-        return XGGM_ERR_ARG;  // plane emission needs the float4 epilogue
-    if (splits > 1 && !accumulate)
-        XGGM_CUDA_TRY(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
-    const int grid = min(sms, tiles_m * tiles_n * splits);
-
-    void* prof = gemm_prof_begin(2.0 * M * N * K, st);
+    for (int g = 0; g < tc::MAX_GROUP; ++g) {
+        const GemmProb& q = pr[g < count ? g : 0];
+        XGGM_TRY(make_map(&maps.m[g].a_hi, q.a_hi, a_rows, a_cols, a_box));
+        XGGM_TRY(make_map(&maps.m[g].b_hi, q.b_hi, b_rows, b_cols, b_box));
+        if (npass == 3) {
+            XGGM_TRY(make_map(&maps.m[g].a_lo, q.a_lo, a_rows, a_cols, a_box));
+            XGGM_TRY(make_map(&maps.m[g].b_lo, q.b_lo, b_rows, b_cols, b_box));
+        } else {
+            maps.m[g].a_lo = maps.m[g].a_hi;
+            maps.m[g].b_lo = maps.m[g].b_hi;
+        }
+        p.pr[g] = tc::ProbOut{q.bias, q.resid, q.C, q.c_hi, npass == 3 ? q.c_lo : nullptr, q.accumulate, 0};
+        if (g >= count) continue;
+        if (((reinterpret_cast<uintptr_t>(q.C) | reinterpret_cast<uintptr_t>(q.resid) |
+              reinterpret_cast<uintptr_t>(q.bias)) & 15) != 0)
+            p.vec4 = 0;
+    }
+    for (int g = 0; g < count; ++g) {
+        const GemmProb& q = pr[g];
+        if (q.c_hi && (!p.vec4 || p.atomic || (reinterpret_cast<uintptr_t>(q.c_hi) & 7) ||
+                       (reinterpret_cast<uintptr_t>(q.c_lo) & 7)))
+            return XGGM_ERR_ARG;  // plane emission needs the float4 epilogue
+        if (splits > 1 && !q.accumulate)
+            XGGM_CUDA_TRY(cudaMemsetAsync(q.C, 0, sizeof(float) * (size_t)M * N, st));
+    }
+    const int total = p.tiles_per_prob * count;
+    void* prof = gemm_prof_begin(2.0 * M * N * K * count, st);
     int rc;
-    if (bn == 192) {
-        rc = npass == 3 ? dispatch_major<192, 3>(a_mn, b_mn, ah, al, bh, bl, p, grid, st)
-                        : dispatch_major<192, 1>(a_mn, b_mn, ah, al, bh, bl, p, grid, st);
+    if (pair) {
+        const int grid = 2 * min(sms / 2, total);
+        rc = npass == 3 ? launch_tc<PBN, 3, false, false, 2>(maps, p, grid, st)
+                        : launch_tc<PBN, 1, false, false, 2>(maps, p, grid, st);
     } else {
-        rc = npass == 3 ? dispatch_major<128, 3>(a_mn, b_mn, ah, al, bh, bl, p, grid, st)
-                        : dispatch_major<128, 1>(a_mn, b_mn, ah, al, bh, bl, p, grid, st);
+        const int grid = min(sms, total);
+        if (bn == 192) {
+            rc = npass == 3 ? dispatch_major<192, 3>(a_mn, b_mn, maps, p, grid, st)
+                            : dispatch_major<192, 1>(a_mn, b_mn, maps, p, grid, st);
+        } else {
+            rc = npass == 3 ? dispatch_major<128, 3>(a_mn, b_mn, maps, p, grid, st)
+                            : dispatch_major<128, 1>(a_mn, b_mn, maps, p, grid, st);
+        }
     }
     gemm_prof_end(prof, st);
     return rc;
+}
+
+int gemm_tc(bool a_mn, bool b_mn, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const __nv_bfloat16* b_hi,
+            const __nv_bfloat16* b_lo, const float* bias, const float* resid, float* C, __nv_bfloat16* c_hi,
+            __nv_bfloat16* c_lo, int M, int N, int K, int accumulate, int allow_split_k, int npass, cudaStream_t st) {
+    const GemmProb q{a_hi, a_lo, b_hi, b_lo, bias, resid, C, c_hi, c_lo, accumulate};
+    return gemm_tc_group(a_mn, b_mn, &q, 1, M, N, K, allow_split_k, npass, st);
 }
 
 bool gram_tc_supported(int N, int H) { return N >= 1 && N <= tc::BM && H > 0 && H % 8 == 0; }
@@ -919,7 +944,8 @@ int gram_tc(const __nv_bfloat16* p_hi, const __nv_bfloat16* p_lo, const __nv_bfl
     XGGM_REQUIRE(p_hi && q_hi && S && gram_tc_supported(N, H) && (npass == 1 || (npass == 3 && p_lo && q_lo)));
     const long long M = (long long)B * N;
     const int G = tc::BM / N;
-    CUtensorMap ah, al, bh, bl;
+    tc::GroupMaps maps;
+    CUtensorMap &ah = maps.m[0].a_hi, &al = maps.m[0].a_lo, &bh = maps.m[0].b_hi, &bl = maps.m[0].b_lo;
     XGGM_TRY(make_map(&ah, p_hi, M, H, tc::BM));
     XGGM_TRY(make_map(&bh, q_hi, M, H, 128));
     if (npass == 3) {
@@ -929,18 +955,20 @@ int gram_tc(const __nv_bfloat16* p_hi, const __nv_bfloat16* p_lo, const __nv_bfl
         al = ah;
         bl = bh;
     }
+    for (int g = 1; g < tc::MAX_GROUP; ++g) maps.m[g] = maps.m[0];
     tc::Params p;
     p.M = (int)M; p.N = (int)M; p.num_kb = ceil_div(H, tc::BK);
     p.tiles_m = ceil_div(B, G); p.tiles_n = 1; p.splits = 1; p.kb_per_split = p.num_kb;
-    p.bias = nullptr; p.resid = nullptr; p.C = S; p.ldc = N;
-    p.accumulate = 0; p.atomic = 0; p.vec4 = 0; p.c_hi = nullptr; p.c_lo = nullptr;
+    p.ldc = N;
+    p.atomic = 0; p.vec4 = 0;
+    single_problem(p, nullptr, nullptr, S, nullptr, nullptr, 0);
     p.gram_n = N; p.gram_g = G; p.gram_b = B;
     p.bd_stride = 0;
     p.dbg = nullptr;
     const int grid = min(num_sms(), p.tiles_m);
     void* prof = gemm_prof_begin(2.0 * B * N * N * H, st);
-    const int rc = npass == 3 ? launch_tc<128, 3, false, false>(ah, al, bh, bl, p, grid, st)
-                              : launch_tc<128, 1, false, false>(ah, al, bh, bl, p, grid, st);
+    const int rc = npass == 3 ? launch_tc<128, 3, false, false>(maps, p, grid, st)
+                              : launch_tc<128, 1, false, false>(maps, p, grid, st);
     gemm_prof_end(prof, st);
     return rc;
 }
@@ -970,7 +998,8 @@ int adj_apply_tc(const __nv_bfloat16* c_hi_in, const __nv_bfloat16* c_lo_in, con
     const int G = tc::BM / N, T = ceil_div(B, G);
     const long long M = (long long)B * N;
     constexpr int ABN = 192;
-    CUtensorMap ah, al, bh, bl;
+    tc::GroupMaps maps;
+    CUtensorMap &ah = maps.m[0].a_hi, &al = maps.m[0].a_lo, &bh = maps.m[0].b_hi, &bl = maps.m[0].b_lo;
     XGGM_TRY(make_map(&ah, c_hi_in, (long long)T * tc::BM, tc::BM, tc::BM));
     XGGM_TRY(make_map(&bh, x_hi, M, H, tc::BK));
     if (npass == 3) {
@@ -983,18 +1012,19 @@ int adj_apply_tc(const __nv_bfloat16* c_hi_in, const __nv_bfloat16* c_lo_in, con
     tc::Params p;
     p.M = (int)M; p.N = H; p.num_kb = tc::BM / tc::BK;
     p.tiles_m = T; p.tiles_n = ceil_div(H, ABN); p.splits = 1; p.kb_per_split = p.num_kb;
-    p.bias = nullptr; p.resid = nullptr; p.C = out; p.ldc = H;
-    p.accumulate = accumulate; p.atomic = 0;
+    p.ldc = H;
+    p.atomic = 0;
     p.vec4 = (H % 4 == 0) && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-    p.c_hi = o_hi; p.c_lo = npass == 3 ? o_lo : nullptr;
+    single_problem(p, nullptr, nullptr, out, o_hi, npass == 3 ? o_lo : nullptr, accumulate);
+    for (int g = 1; g < tc::MAX_GROUP; ++g) maps.m[g] = maps.m[0];
     p.gram_n = p.gram_g = p.gram_b = 0;
     p.bd_stride = G * N;
     p.dbg = g_tc_dbg;
     XGGM_REQUIRE(p.vec4 && (reinterpret_cast<uintptr_t>(o_hi) & 7) == 0 && (reinterpret_cast<uintptr_t>(o_lo) & 7) == 0);
     const int grid = min(num_sms(), p.tiles_m * p.tiles_n);
     // (not a projection: kept out of the GEMM roofline accounting)
-    return npass == 3 ? launch_tc<ABN, 3, false, true>(ah, al, bh, bl, p, grid, st)
-                      : launch_tc<ABN, 1, false, true>(ah, al, bh, bl, p, grid, st);
+    return npass == 3 ? launch_tc<ABN, 3, false, true>(maps, p, grid, st)
+                      : launch_tc<ABN, 1, false, true>(maps, p, grid, st);
 }
 
 // Transposed split of `count` [R,C] fp32 matrices into [C,R] bf16 planes (one launch per 8 matrices).

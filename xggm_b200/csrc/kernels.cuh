@@ -19,6 +19,17 @@ bool gemm_tc_supported(int M, int N, int K);
 int gemm_tc(bool a_mn, bool b_mn, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const __nv_bfloat16* b_hi,
             const __nv_bfloat16* b_lo, const float* bias, const float* resid, float* C, __nv_bfloat16* c_hi,
             __nv_bfloat16* c_lo, int M, int N, int K, int accumulate, int allow_split_k, int npass, cudaStream_t st);
+// one product of a grouped launch (gemm_tc_group): same shape / operand layout for every member
+struct GemmProb {
+    const __nv_bfloat16 *a_hi, *a_lo, *b_hi, *b_lo;
+    const float* bias;
+    const float* resid;
+    float* C;
+    __nv_bfloat16 *c_hi, *c_lo;
+    int accumulate;
+};
+int gemm_tc_group(bool a_mn, bool b_mn, const GemmProb* pr, int count, int M, int N, int K, int allow_split_k,
+                  int npass, cudaStream_t st);
 bool adj_tc_supported(int N, int H);
 long long adj_tc_coef_elems(int B, int N);
 int build_blockdiag(const float* adj, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int N, float alpha0,
