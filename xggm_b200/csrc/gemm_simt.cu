@@ -135,7 +135,8 @@ gemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
 
 // ---- optional per-launch timing of the projection GEMMs (bench.py roofline leg) ----
 // When enabled, every GEMM launch is bracketed by a CUDA-event pair on its own stream.
-struct ProfRec { cudaEvent_t e0, e1; double flops; };
+void* gemm_prof_begin(double flops, cudaStream_t st, int members);
+struct ProfRec { cudaEvent_t e0, e1; double flops; int members; };
 static bool g_prof_on = false;
 static ProfRec g_prof[4096];
 static int g_prof_n = 0;
@@ -146,25 +147,26 @@ int gemm_prof_enable(int on) {
     g_prof_on = on != 0;
     return XGGM_OK;
 }
-// Sums the records of the DOMINANT product shape only (FLOPs >= half of the largest record): the
+// Sums the records of the DOMINANT product shape only (FLOPs per group member >= half of the largest): the
 // roofline leg is about the [B*N,768] x [768,768] projections, not the few tiny head GEMMs / Gram tiles.
 int gemm_prof_read(double* total_ms, long long* launches, double* flops) {
     *total_ms = 0; *launches = 0; *flops = 0;
     double fmax = 0;
-    for (int i = 0; i < g_prof_n; ++i) fmax = g_prof[i].flops > fmax ? g_prof[i].flops : fmax;
+    for (int i = 0; i < g_prof_n; ++i) fmax = fmax > g_prof[i].flops / g_prof[i].members ? fmax : g_prof[i].flops / g_prof[i].members;
     for (int i = 0; i < g_prof_n; ++i) {
         XGGM_CUDA_TRY(cudaEventSynchronize(g_prof[i].e1));
-        if (g_prof[i].flops < 0.5 * fmax) continue;
+        if (g_prof[i].flops / g_prof[i].members < 0.5 * fmax) continue;
         float ms = 0.f;
         XGGM_CUDA_TRY(cudaEventElapsedTime(&ms, g_prof[i].e0, g_prof[i].e1));
         *total_ms += ms; *flops += g_prof[i].flops; *launches += 1;
     }
     return XGGM_OK;
 }
-void* gemm_prof_begin(double flops, cudaStream_t st) {
+void* gemm_prof_begin(double flops, cudaStream_t st, int members) {
     if (!g_prof_on || g_prof_n >= 4096) return nullptr;
     ProfRec* r = &g_prof[g_prof_n++];
     r->flops = flops;
+    r->members = members > 0 ? members : 1;
     cudaEventCreate(&r->e0); cudaEventCreate(&r->e1);
     cudaEventRecord(r->e0, st);
     return r;
@@ -174,7 +176,7 @@ void gemm_prof_end(void* rec, cudaStream_t st) {
 }
 struct ProfScope {
     void* r; cudaStream_t st;
-    ProfScope(double flops, cudaStream_t s) : r(gemm_prof_begin(flops, s)), st(s) {}
+    ProfScope(double flops, cudaStream_t s) : r(gemm_prof_begin(flops, s, 1)), st(s) {}
     ~ProfScope() { gemm_prof_end(r, st); }
 };
 

@@ -536,8 +536,19 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const Params p) {
                 // (2) accumulator chunk: TMEM -> registers (thread = row) -> smem transpose
                 uint32_t v[32];
                 tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
+                // vec mode: 16-byte accesses into a pitch-32 tile whose float4 index is XOR-swizzled with the row
+                // (conflict-free for the row-wise writes here and the 4-row x 8-float4 reads below)
+                float4* st4 = reinterpret_cast<float4*>(st);
+                if (vec) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) st[lane * EPI_PITCH + j] = __uint_as_float(v[j]);
+                    for (int j = 0; j < 8; ++j)
+                        st4[lane * 8 + (j ^ (lane & 7))] =
+                            make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                        __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) st[lane * EPI_PITCH + j] = __uint_as_float(v[j]);
+                }
                 __syncwarp();
                 // (3) coalesced stores
                 if (vec) {
@@ -547,9 +558,10 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const Params p) {
                         float4 o[8];
 #pragma unroll
                         for (int it = 0; it < 8; ++it) {
-                            const float* sp = st + (4 * it + rsub) * EPI_PITCH + c4;
+                            const int row = 4 * it + rsub;
+                            const float4 sp = st4[row * 8 + ((lane & 7) ^ (row & 7))];
                             const float4 bv = bvs[ci], x = xs[ci][it];
-                            o[it] = make_float4(sp[0] + bv.x + x.x, sp[1] + bv.y + x.y, sp[2] + bv.z + x.z, sp[3] + bv.w + x.w);
+                            o[it] = make_float4(sp.x + bv.x + x.x, sp.y + bv.y + x.y, sp.z + bv.z + x.z, sp.w + bv.w + x.w);
                         }
 #pragma unroll
                         for (int it = 0; it < 8; ++it) {
@@ -751,7 +763,7 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
 }
 
 // per-launch timing lives in gemm_simt.cu
-void* gemm_prof_begin(double flops, cudaStream_t st);
+void* gemm_prof_begin(double flops, cudaStream_t st, int members = 1);
 void gemm_prof_end(void* rec, cudaStream_t st);
 
 static unsigned long long* g_tc_dbg = nullptr;   // see xggm_debug_timeline()
@@ -907,7 +919,7 @@ int gemm_tc_group(bool a_mn, bool b_mn, const GemmProb* pr, int count, int M, in
             XGGM_CUDA_TRY(cudaMemsetAsync(q.C, 0, sizeof(float) * (size_t)M * N, st));
     }
     const int total = p.tiles_per_prob * count;
-    void* prof = gemm_prof_begin(2.0 * M * N * K * count, st);
+    void* prof = gemm_prof_begin(2.0 * M * N * K * count, st, count);
     int rc;
     if (pair) {
         const int grid = 2 * min(sms / 2, total);
