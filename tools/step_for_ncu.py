@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""One eager forward+backward step of the bench workload between cudaProfilerStart/Stop, for
+    ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file out.csv python tools/step_for_ncu.py
+Flags mirror bench.py (--batch/--nodes/--precision/--gnn)."""
+import argparse
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import xggm_b200 as X  # noqa: E402
+from oracle import xggm_oracle as O  # noqa: E402  (input factory only)
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--nodes", type=int, default=36)
+ap.add_argument("--precision", default="fp32")
+ap.add_argument("--gnn", default="GCN")
+ap.add_argument("--steps", type=int, default=1)
+a = ap.parse_args()
+dev = torch.device("cuda", 0)
+torch.manual_seed(9595)
+X.set_precision(a.precision)
+model = X.XGGMHeads(768, a.gnn, 2, a.nodes).to(dev).train()
+from xggm_b200.ddp import FlatGrads  # noqa: E402
+grads = FlatGrads(model.parameters())
+visn, xp, adj = (t.to(dev) for t in O.make_inputs(9596, a.batch, a.nodes, 768))
+cot = torch.randn(a.batch, 768, device=dev)
+
+
+def compute():
+    grads.flat.zero_()
+    x = xp.detach().requires_grad_(True)
+    feat = visn.detach().requires_grad_(True)
+    x_gen, loss_sm, _, _ = model.node_step(x, feat, adj, 1.0, 2274)
+    ((x_gen * cot).sum() + 1.1 * loss_sm).backward()
+
+
+for _ in range(3):
+    compute()
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStart()
+for _ in range(a.steps):
+    compute()
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()

@@ -18,6 +18,17 @@ void set_cuda_error(cudaError_t e, const char* where) {
     snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", cudaGetErrorName(e), cudaGetErrorString(e), where);
 }
 
+// XGGM_PDL: 0 (default) plain stream-ordered launches; 1 PDL on every kernel; 2 GEMM kernels only; 3 all but GEMMs.
+// Measured at B=256 inside the captured step: 2.01 ms (0) vs 2.12 (1), 2.07 (2), 2.02 (3) -> off by default.
+int pdl_mode() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("XGGM_PDL");
+        on = e ? atoi(e) : 0;
+    }
+    return on;
+}
+bool pdl_enabled() { return pdl_mode() == 1 || pdl_mode() == 3; }
 constexpr float LN_EPS = 1e-5f;  // nn.LayerNorm default (src/module/gcn.py:14,47)
 
 // chunk sizes are padded to 8 floats so that every bf16 plane starts 16-byte aligned (TMA)

@@ -37,6 +37,40 @@ extern unsigned long long g_kernel_launches;
         if (!(cond)) return XGGM_ERR_ARG;  \
     } while (0)
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization and
+// starts with pdl_prologue(): `griddepcontrol.launch_dependents` lets the NEXT kernel of the stream (or
+// captured graph) be scheduled as soon as all CTAs of this one are resident, and `griddepcontrol.wait`
+// blocks until the PREVIOUS grid has completed and its memory is visible -- so launch latency, CTA
+// scheduling and (in the GEMM kernel) barrier / TMEM / tensor-map setup overlap the predecessor's tail.
+// No kernel touches global memory before its wait, hence ordering is exactly that of a plain stream.
+// Measured SLOWER than plain launches inside the captured step on B200 (api.cu: pdl_mode), so the attribute is
+// only set when XGGM_PDL asks for it; without it both instructions are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+    pdl_launch_dependents();
+    pdl_wait();
+}
+bool pdl_enabled();
+int pdl_mode();
+template <typename... KArgs, typename... Args>
+static inline void launch_kernel(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);   // errors surface in XGGM_LAUNCH_CHECK
+}
+#define XGGM_LAUNCH(kern, grid, block, smem, st, ...) ::xggm::launch_kernel(::xggm::pdl_enabled(), kern, grid, block, smem, st, __VA_ARGS__)
+
 static inline cudaStream_t as_stream(xggm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 

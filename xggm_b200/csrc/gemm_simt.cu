@@ -62,6 +62,7 @@ gemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
                  const float* __restrict__ bias, const float* __restrict__ resid,
                  float* __restrict__ C, int M, int N, int K, int lda, int ldb, int ldc,
                  int vecA, int vecB, int accumulate, int k_per_split) {
+    pdl_prologue();
     __shared__ __align__(16) float As[2][BK][BM + PAD];
     __shared__ __align__(16) float Bs[2][BK][BN + PAD];
     const int t = threadIdx.x;
@@ -201,17 +202,17 @@ int gemm_simt(int op, const float* A, const float* Bm, const float* bias, const 
     ProfScope prof(2.0 * M * N * K, st);
     if (op == 0) {
         const int lda = K, ldb = K;
-        gemm_simt_kernel<true, true><<<grid, 256, 0, st>>>(
+        XGGM_LAUNCH((gemm_simt_kernel<true, true>), grid, 256, 0, st, 
             A, Bm, bias, resid, C, M, N, K, lda, ldb, N, (lda % 4 == 0) && aligned16(A),
             (ldb % 4 == 0) && aligned16(Bm), accumulate, kps);
     } else if (op == 1) {
         const int lda = K, ldb = N;
-        gemm_simt_kernel<true, false><<<grid, 256, 0, st>>>(
+        XGGM_LAUNCH((gemm_simt_kernel<true, false>), grid, 256, 0, st, 
             A, Bm, bias, resid, C, M, N, K, lda, ldb, N, (lda % 4 == 0) && aligned16(A),
             (ldb % 4 == 0) && aligned16(Bm), accumulate, kps);
     } else {
         const int lda = M, ldb = N;
-        gemm_simt_kernel<false, false><<<grid, 256, 0, st>>>(
+        XGGM_LAUNCH((gemm_simt_kernel<false, false>), grid, 256, 0, st, 
             A, Bm, bias, resid, C, M, N, K, lda, ldb, N, (lda % 4 == 0) && aligned16(A),
             (ldb % 4 == 0) && aligned16(Bm), accumulate, kps);
     }
@@ -222,6 +223,7 @@ int gemm_simt(int op, const float* A, const float* Bm, const float* bias, const 
 // column sums: out[c] = sum_r g[r,c]  (bias gradients)
 __global__ void colsum_kernel(const float* __restrict__ g, float* __restrict__ out, int R, int C,
                               int rows_per_block) {
+    pdl_prologue();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const int r0 = blockIdx.y * rows_per_block, r1 = min(R, r0 + rows_per_block);
@@ -235,7 +237,7 @@ int colsum(const float* g, float* out, int R, int C, int accumulate, cudaStream_
     if (R <= 0) return XGGM_OK;
     const int rpb = 64;
     dim3 grid(ceil_div(C, 128), ceil_div(R, rpb));
-    colsum_kernel<<<grid, 128, 0, st>>>(g, out, R, C, rpb);
+    XGGM_LAUNCH((colsum_kernel), grid, 128, 0, st, g, out, R, C, rpb);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }

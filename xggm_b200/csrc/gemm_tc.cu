@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const Params p) {
     using C = Cfg<BN, NPASS, CG>;
     static_assert(CG == 1 || (!A_MN && !B_MN), "the CTA-pair kernel takes K-major operands");
+    pdl_launch_dependents();   // the next kernel may be scheduled once every CTA of this one is resident
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for SWIZZLE_128B, computed as an offset so the pointer keeps its shared-space provenance
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -333,6 +334,9 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const Params p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) XGGM_TRACE(1);
+    // everything above (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel's tail; from here
+    // on operands / addends written by that kernel are read
+    pdl_wait();
 
     if (warp == 0) {
         // ================================ TMA producer ================================
@@ -639,6 +643,7 @@ struct SplitJobs {
 };
 
 __global__ void __launch_bounds__(256) split_planes_kernel(const SplitJobs jobs) {
+    pdl_prologue();
     const SplitJob job = jobs.j[blockIdx.y];
     const long long n4 = job.n >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -674,6 +679,7 @@ struct SplitTJobs {
     SplitTJob j[MAX_SPLIT_JOBS];
 };
 __global__ void __launch_bounds__(256) split_planes_t_kernel(const SplitTJobs jobs, int R, int C) {
+    pdl_prologue();
     __shared__ float tile[32][33];
     const SplitTJob job = jobs.j[blockIdx.z];
     const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -701,6 +707,7 @@ __global__ void __launch_bounds__(256) split_planes_t_kernel(const SplitTJobs jo
 __global__ void __launch_bounds__(128)
 build_blockdiag_kernel(const float* __restrict__ adj, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                        int B, int N, int G, float alpha0, const float* __restrict__ alpha_dev, float self_w, int trans) {
+    pdl_prologue();
     const int t = blockIdx.x;
     const float alpha = alpha0 + (alpha_dev ? alpha_dev[0] : 0.f);
     __nv_bfloat16* th = hi + (size_t)t * BM * BM;
@@ -789,20 +796,22 @@ static int launch_tc(const tc::GroupMaps& maps, const tc::Params& p, int grid, c
         attr_set = true;
     }
     if (CG == 1) {
-        kern<<<grid, tc::NUM_THREADS, C::SMEM, st>>>(maps, p);
+        launch_kernel(pdl_mode() == 1 || pdl_mode() == 2, kern, grid, tc::NUM_THREADS, C::SMEM, st, maps, p);
     } else {  // CTA pairs: clusters of 2 (same TPC) so cta_group::2 MMAs can span both SMs
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid);
         cfg.blockDim = dim3(tc::NUM_THREADS);
         cfg.dynamicSmemBytes = C::SMEM;
         cfg.stream = st;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        cfg.numAttrs = (pdl_mode() == 1 || pdl_mode() == 2) ? 2 : 1;
         XGGM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, maps, p));
     }
     XGGM_LAUNCH_CHECK();
@@ -994,7 +1003,7 @@ int build_blockdiag(const float* adj, __nv_bfloat16* hi, __nv_bfloat16* lo, int 
     if (B <= 0) return XGGM_OK;
     XGGM_REQUIRE(adj && hi && N >= 1 && N <= tc::BM);
     const int G = tc::BM / N;
-    tc::build_blockdiag_kernel<<<dim3(ceil_div(B, G), 4), 128, 0, st>>>(adj, hi, lo, B, N, G, alpha0, alpha_dev, self_w, trans);
+    XGGM_LAUNCH((tc::build_blockdiag_kernel), dim3(ceil_div(B, G), 4), 128, 0, st, adj, hi, lo, B, N, G, alpha0, alpha_dev, self_w, trans);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
@@ -1052,7 +1061,7 @@ int split_planes_t(const float* const* src, __nv_bfloat16* const* hi, __nv_bfloa
             jobs.j[i].lo = lo ? lo[done + i] : nullptr;
         }
         if (R > 0 && C > 0) {
-            tc::split_planes_t_kernel<<<dim3(ceil_div(C, 32), ceil_div(R, 32), n), 256, 0, st>>>(jobs, R, C);
+            XGGM_LAUNCH((tc::split_planes_t_kernel), dim3(ceil_div(C, 32), ceil_div(R, 32), n), 256, 0, st, jobs, R, C);
             XGGM_LAUNCH_CHECK();
         }
         done += n;
@@ -1077,7 +1086,7 @@ int split_planes(const float* const* src, __nv_bfloat16* const* hi, __nv_bfloat1
         }
         if (nmax > 0) {
             const int gx = (int)max(1LL, min((long long)num_sms() * 8, (nmax / 4 + 255) / 256));
-            tc::split_planes_kernel<<<dim3(gx, jobs.count), 256, 0, st>>>(jobs);
+            XGGM_LAUNCH((tc::split_planes_kernel), dim3(gx, jobs.count), 256, 0, st, jobs);
             XGGM_LAUNCH_CHECK();
         }
         done += jobs.count;

@@ -11,6 +11,7 @@ static inline int grid1d(long long n, int block = 256) { return ceil_div(n, bloc
 // ----------------------------------------------------------------- strip_diag
 __global__ void strip_diag_kernel(const float* __restrict__ a, float* __restrict__ out,
                                   long long total, int N) {
+    pdl_prologue();
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
     const int r = (int)(e % ((long long)N * N));
@@ -19,7 +20,7 @@ __global__ void strip_diag_kernel(const float* __restrict__ a, float* __restrict
 int strip_diag(const float* a, float* out, int B, int N, cudaStream_t st) {
     const long long total = (long long)B * N * N;
     if (total <= 0) return XGGM_OK;
-    strip_diag_kernel<<<grid1d(total), 256, 0, st>>>(a, out, total, N);
+    XGGM_LAUNCH((strip_diag_kernel), grid1d(total), 256, 0, st, a, out, total, N);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
@@ -30,6 +31,7 @@ __device__ __forceinline__ int triu_index(int i, int j, int N) { return i * (2 *
 
 __global__ void triu_scatter_fwd_kernel(const float* __restrict__ v, float* __restrict__ adj,
                                         long long total, int N) {
+    pdl_prologue();
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
     const int NN = N * N, E = N * (N - 1) / 2;
@@ -39,6 +41,7 @@ __global__ void triu_scatter_fwd_kernel(const float* __restrict__ v, float* __re
 }
 __global__ void triu_scatter_bwd_kernel(const float* __restrict__ gadj, float* __restrict__ gv,
                                         long long total, int N) {
+    pdl_prologue();
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
     const int NN = N * N, E = N * (N - 1) / 2;
@@ -49,14 +52,14 @@ __global__ void triu_scatter_bwd_kernel(const float* __restrict__ gadj, float* _
 int triu_scatter_fwd(const float* v, float* adj, int B, int N, cudaStream_t st) {
     const long long total = (long long)B * N * N;
     if (total <= 0) return XGGM_OK;
-    triu_scatter_fwd_kernel<<<grid1d(total), 256, 0, st>>>(v, adj, total, N);
+    XGGM_LAUNCH((triu_scatter_fwd_kernel), grid1d(total), 256, 0, st, v, adj, total, N);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
 int triu_scatter_bwd(const float* gadj, float* gv, int B, int N, cudaStream_t st) {
     const long long total = (long long)B * N * N;
     if (total <= 0) return XGGM_OK;
-    triu_scatter_bwd_kernel<<<grid1d(total), 256, 0, st>>>(gadj, gv, total, N);
+    XGGM_LAUNCH((triu_scatter_bwd_kernel), grid1d(total), 256, 0, st, gadj, gv, total, N);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
@@ -66,6 +69,7 @@ int triu_scatter_bwd(const float* gadj, float* gv, int B, int N, cudaStream_t st
 __global__ void edge_noise_kernel(const float* __restrict__ adj, const float* __restrict__ randn,
                                   float sigma, float sigma2, float* __restrict__ noisy,
                                   float* __restrict__ target, long long total, int N) {
+    pdl_prologue();
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
     const int NN = N * N;
@@ -83,7 +87,7 @@ int edge_noise(const float* adj, const float* randn, float sigma, float sigma2, 
                float* target, int B, int N, cudaStream_t st) {
     const long long total = (long long)B * N * N;
     if (total <= 0) return XGGM_OK;
-    edge_noise_kernel<<<grid1d(total), 256, 0, st>>>(adj, randn, sigma, sigma2, noisy, target, total, N);
+    XGGM_LAUNCH((edge_noise_kernel), grid1d(total), 256, 0, st, adj, randn, sigma, sigma2, noisy, target, total, N);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
@@ -92,6 +96,7 @@ __global__ void feat_noise_kernel(const float* __restrict__ f, const float* __re
                                   float sigma, float sigma2, float* __restrict__ noisy,
                                   float* __restrict__ target, long long total, int N, int H,
                                   int bcast) {
+    pdl_prologue();
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
     const float n = randn[e] * sigma;
@@ -109,6 +114,7 @@ __global__ void feat_noise_kernel(const float* __restrict__ f, const float* __re
 __global__ void __launch_bounds__(256)
 feat_noise_vec_kernel(const float* __restrict__ f, const float* __restrict__ randn, float sigma, float sigma2,
                       float* __restrict__ noisy, float* __restrict__ target, int NH4, int H, int bcast) {
+    pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;   // float4 index inside graph b
     if (i >= NH4) return;
     const int b = blockIdx.y;
@@ -127,17 +133,18 @@ int feat_noise(const float* f, const float* randn, float sigma, float sigma2, fl
     if (total <= 0) return XGGM_OK;
     if (H % 4 == 0 && al16(f) && al16(randn) && al16(noisy) && al16(target) && (long long)N * H / 4 < (1LL << 30)) {
         const int NH4 = N * H / 4;
-        feat_noise_vec_kernel<<<dim3(ceil_div(NH4, 256), B), 256, 0, st>>>(f, randn, sigma, sigma2, noisy, target, NH4, H, bcast);
+        XGGM_LAUNCH((feat_noise_vec_kernel), dim3(ceil_div(NH4, 256), B), 256, 0, st, f, randn, sigma, sigma2, noisy, target, NH4, H, bcast);
         XGGM_LAUNCH_CHECK();
         return XGGM_OK;
     }
-    feat_noise_kernel<<<grid1d(total), 256, 0, st>>>(f, randn, sigma, sigma2, noisy, target, total, N, H, bcast);
+    XGGM_LAUNCH((feat_noise_kernel), grid1d(total), 256, 0, st, f, randn, sigma, sigma2, noisy, target, total, N, H, bcast);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
 
 __global__ void sum_nodes_kernel(const float* __restrict__ g, float* __restrict__ out, int B,
                                  int N, int H) {
+    pdl_prologue();
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (long long)B * H) return;
     const long long b = e / H;
@@ -149,7 +156,7 @@ __global__ void sum_nodes_kernel(const float* __restrict__ g, float* __restrict_
 int sum_nodes(const float* g, float* out, int B, int N, int H, cudaStream_t st) {
     const long long total = (long long)B * H;
     if (total <= 0) return XGGM_OK;
-    sum_nodes_kernel<<<grid1d(total), 256, 0, st>>>(g, out, B, N, H);
+    XGGM_LAUNCH((sum_nodes_kernel), grid1d(total), 256, 0, st, g, out, B, N, H);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
@@ -158,6 +165,7 @@ int sum_nodes(const float* g, float* out, int B, int N, int H, cudaStream_t st) 
 __global__ void __launch_bounds__(256)
 score_mse_fwd_kernel(const float* __restrict__ s, const float* __restrict__ t, float coef,
                      float* __restrict__ loss, long long n) {
+    pdl_prologue();
     __shared__ float part[8];
     float acc = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -177,6 +185,7 @@ score_mse_fwd_kernel(const float* __restrict__ s, const float* __restrict__ t, f
 __global__ void score_mse_bwd_kernel(const float* __restrict__ s, const float* __restrict__ t,
                                      const float* __restrict__ gloss, float coef,
                                      float* __restrict__ gs, long long n) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) gs[i] = gloss[0] * coef * (s[i] - t[i]);
 }
@@ -186,13 +195,14 @@ int score_mse_fwd(const float* s, const float* t, float sigma, float* loss, long
     if (n <= 0) return XGGM_OK;
     const float coef = 0.5f * sigma * sigma / (float)n;
     const int grid = (int)min((long long)148 * 8, (n + 255) / 256);
-    score_mse_fwd_kernel<<<grid, 256, 0, st>>>(s, t, coef, loss, n);
+    XGGM_LAUNCH((score_mse_fwd_kernel), grid, 256, 0, st, s, t, coef, loss, n);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
 __global__ void __launch_bounds__(256)
 score_mse_bwd_vec_kernel(const float4* __restrict__ s, const float4* __restrict__ t, const float* __restrict__ gloss,
                          float coef, float4* __restrict__ gs, long long n4) {
+    pdl_prologue();
     const float c = gloss[0] * coef;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const float4 a = s[i], b = t[i];
@@ -206,12 +216,12 @@ int score_mse_bwd(const float* s, const float* t, const float* gloss, float sigm
     if (n % 4 == 0 && al16(s) && al16(t) && al16(gs)) {
         const long long n4 = n / 4;
         const int grid = (int)min((long long)148 * 16, (n4 + 255) / 256);
-        score_mse_bwd_vec_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(s), reinterpret_cast<const float4*>(t), gloss, coef,
+        XGGM_LAUNCH((score_mse_bwd_vec_kernel), grid, 256, 0, st, reinterpret_cast<const float4*>(s), reinterpret_cast<const float4*>(t), gloss, coef,
                                                        reinterpret_cast<float4*>(gs), n4);
         XGGM_LAUNCH_CHECK();
         return XGGM_OK;
     }
-    score_mse_bwd_kernel<<<grid1d(n), 256, 0, st>>>(s, t, gloss, coef, gs, n);
+    XGGM_LAUNCH((score_mse_bwd_kernel), grid1d(n), 256, 0, st, s, t, gloss, coef, gs, n);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
@@ -234,6 +244,7 @@ __device__ __forceinline__ RowSoftmax row_softmax_stats(const float* __restrict_
 __global__ void __launch_bounds__(256)
 sym_kl_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
                   float* __restrict__ loss, int R, int C, float inv_count) {
+    pdl_prologue();
     __shared__ float part[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float acc = 0.f;
@@ -262,6 +273,7 @@ __global__ void __launch_bounds__(256)
 sym_kl_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
                   const float* __restrict__ gloss, float* __restrict__ gx,
                   float* __restrict__ gy, int R, int C, float inv_count) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float g = gloss[0] * inv_count;
     for (int r = blockIdx.x * 8 + warp; r < R; r += gridDim.x * 8) {
@@ -317,6 +329,7 @@ __global__ void __launch_bounds__(256)
 sym_kl_fast_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ loss,
                    const float* __restrict__ gloss, float* __restrict__ gx, float* __restrict__ gy, int R,
                    float inv_count) {
+    pdl_prologue();
     constexpr int C = NV * 128;
     __shared__ float part[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -392,12 +405,12 @@ int sym_kl_fwd(const float* x, const float* y, float* loss, int R, int C, cudaSt
     if (R <= 0 || C <= 0) return XGGM_OK;
     if (kl_fast_ok(C, x, y)) {
         const int grid = min(148 * 4, ceil_div(R, 8));
-        XGGM_KL_DISPATCH(C, (sym_kl_fast_kernel<NV, false><<<grid, 256, 0, st>>>(x, y, loss, nullptr, nullptr, nullptr, R, 1.0f / ((float)R * (float)C))));
+        XGGM_KL_DISPATCH(C, (XGGM_LAUNCH((sym_kl_fast_kernel<NV, false>), grid, 256, 0, st, x, y, loss, nullptr, nullptr, nullptr, R, 1.0f / ((float)R * (float)C))));
         XGGM_LAUNCH_CHECK();
         return XGGM_OK;
     }
     const int grid = min(148 * 8, ceil_div(R, 8));
-    sym_kl_fwd_kernel<<<grid, 256, 0, st>>>(x, y, loss, R, C, 1.0f / ((float)R * (float)C));
+    XGGM_LAUNCH((sym_kl_fwd_kernel), grid, 256, 0, st, x, y, loss, R, C, 1.0f / ((float)R * (float)C));
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
@@ -406,12 +419,12 @@ int sym_kl_bwd(const float* x, const float* y, const float* gloss, float* gx, fl
     if (R <= 0 || C <= 0) return XGGM_OK;
     if (kl_fast_ok(C, x, y, gx, gy)) {
         const int grid = min(148 * 4, ceil_div(R, 8));
-        XGGM_KL_DISPATCH(C, (sym_kl_fast_kernel<NV, true><<<grid, 256, 0, st>>>(x, y, nullptr, gloss, gx, gy, R, 1.0f / ((float)R * (float)C))));
+        XGGM_KL_DISPATCH(C, (XGGM_LAUNCH((sym_kl_fast_kernel<NV, true>), grid, 256, 0, st, x, y, nullptr, gloss, gx, gy, R, 1.0f / ((float)R * (float)C))));
         XGGM_LAUNCH_CHECK();
         return XGGM_OK;
     }
     const int grid = min(148 * 8, ceil_div(R, 8));
-    sym_kl_bwd_kernel<<<grid, 256, 0, st>>>(x, y, gloss, gx, gy, R, C, 1.0f / ((float)R * (float)C));
+    XGGM_LAUNCH((sym_kl_bwd_kernel), grid, 256, 0, st, x, y, gloss, gx, gy, R, C, 1.0f / ((float)R * (float)C));
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
@@ -419,6 +432,7 @@ int sym_kl_bwd(const float* x, const float* y, const float* gloss, float* gx, fl
 // --------------------------------------------------------------- fusion readout
 __global__ void fuse_readout_fwd_kernel(const float* __restrict__ xp, const float* __restrict__ nodes,
                                         float* __restrict__ out, int B, int N, int H) {
+    pdl_prologue();
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (long long)B * H) return;
     const long long b = e / H;
@@ -431,6 +445,7 @@ __global__ void fuse_readout_fwd_kernel(const float* __restrict__ xp, const floa
 __global__ void fuse_readout_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ out,
                                         float* __restrict__ gxp, float* __restrict__ gnodes, int B,
                                         int N, int H, int accumulate) {
+    pdl_prologue();
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (long long)B * H) return;
     const long long b = e / H;
@@ -446,7 +461,7 @@ __global__ void fuse_readout_bwd_kernel(const float* __restrict__ gout, const fl
 int fuse_readout_fwd(const float* xp, const float* nodes, float* out, int B, int N, int H, cudaStream_t st) {
     const long long total = (long long)B * H;
     if (total <= 0) return XGGM_OK;
-    fuse_readout_fwd_kernel<<<grid1d(total), 256, 0, st>>>(xp, nodes, out, B, N, H);
+    XGGM_LAUNCH((fuse_readout_fwd_kernel), grid1d(total), 256, 0, st, xp, nodes, out, B, N, H);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
@@ -454,65 +469,70 @@ int fuse_readout_bwd(const float* gout, const float* out, float* gxp, float* gno
                      int H, int accumulate, cudaStream_t st) {
     const long long total = (long long)B * H;
     if (total <= 0) return XGGM_OK;
-    fuse_readout_bwd_kernel<<<grid1d(total), 256, 0, st>>>(gout, out, gxp, gnodes, B, N, H, accumulate);
+    XGGM_LAUNCH((fuse_readout_bwd_kernel), grid1d(total), 256, 0, st, gout, out, gxp, gnodes, B, N, H, accumulate);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
 
 // ------------------------------------------------------------------- sigmoid
 __global__ void sigmoid_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = sigmoidf_(x[i]);
 }
 __global__ void sigmoid_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ y,
                                    float* __restrict__ gx, long long n) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { const float v = y[i]; gx[i] = gy[i] * v * (1.f - v); }
 }
 int sigmoid_fwd(const float* x, float* y, long long n, cudaStream_t st) {
     if (n <= 0) return XGGM_OK;
-    sigmoid_fwd_kernel<<<grid1d(n), 256, 0, st>>>(x, y, n);
+    XGGM_LAUNCH((sigmoid_fwd_kernel), grid1d(n), 256, 0, st, x, y, n);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
 int sigmoid_bwd(const float* gy, const float* y, float* gx, long long n, cudaStream_t st) {
     if (n <= 0) return XGGM_OK;
-    sigmoid_bwd_kernel<<<grid1d(n), 256, 0, st>>>(gy, y, gx, n);
+    XGGM_LAUNCH((sigmoid_bwd_kernel), grid1d(n), 256, 0, st, gy, y, gx, n);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
 
 // ------------------------------------------------------- GeLU / masked scaling
 __global__ void gelu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = gelu_erf(x[i]);
 }
 __global__ void gelu_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x,
                                 float* __restrict__ gx, long long n) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) gx[i] = gy[i] * gelu_erf_grad(x[i]);
 }
 int gelu_fwd(const float* x, float* y, long long n, cudaStream_t st) {
     if (n <= 0) return XGGM_OK;
-    gelu_fwd_kernel<<<grid1d(n), 256, 0, st>>>(x, y, n);
+    XGGM_LAUNCH((gelu_fwd_kernel), grid1d(n), 256, 0, st, x, y, n);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
 int gelu_bwd(const float* gy, const float* x, float* gx, long long n, cudaStream_t st) {
     if (n <= 0) return XGGM_OK;
-    gelu_bwd_kernel<<<grid1d(n), 256, 0, st>>>(gy, x, gx, n);
+    XGGM_LAUNCH((gelu_bwd_kernel), grid1d(n), 256, 0, st, gy, x, gx, n);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
 // inverted dropout with an explicit mask: y = keep ? x*scale : 0 (its own backward); keep == NULL: y = x*scale
 __global__ void mask_scale_kernel(const float* __restrict__ x, const uint8_t* __restrict__ keep,
                                   float scale, float* __restrict__ y, long long n) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = (!keep || keep[i]) ? x[i] * scale : 0.f;
 }
 int mask_scale(const float* x, const uint8_t* keep, float scale, float* y, long long n, cudaStream_t st) {
     if (n <= 0) return XGGM_OK;
-    mask_scale_kernel<<<grid1d(n), 256, 0, st>>>(x, keep, scale, y, n);
+    XGGM_LAUNCH((mask_scale_kernel), grid1d(n), 256, 0, st, x, keep, scale, y, n);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
@@ -522,6 +542,7 @@ int mask_scale(const float* x, const uint8_t* keep, float scale, float* y, long 
 __global__ void __launch_bounds__(256)
 avg2_drop_kernel(const float* __restrict__ x, const float* __restrict__ y, const uint8_t* __restrict__ keep,
                  float scale, float* __restrict__ out, long long n, int vec) {
+    pdl_prologue();
     const long long stride = (long long)gridDim.x * blockDim.x;
     if (vec) {
         const long long n4 = n >> 2;
@@ -547,7 +568,7 @@ int avg2_drop(const float* x, const float* y, const uint8_t* keep, float scale, 
     if (n <= 0) return XGGM_OK;
     const int vec = n % 4 == 0 && al16(x) && al16(y) && al16(out) && (reinterpret_cast<uintptr_t>(keep) & 3) == 0;
     const int grid = (int)min((long long)148 * 16, ((vec ? n / 4 : n) + 255) / 256);
-    avg2_drop_kernel<<<grid, 256, 0, st>>>(x, y, keep, scale, out, n, vec);
+    XGGM_LAUNCH((avg2_drop_kernel), grid, 256, 0, st, x, y, keep, scale, out, n, vec);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
@@ -557,6 +578,7 @@ int avg2_drop(const float* x, const float* y, const uint8_t* keep, float scale, 
 __global__ void keep_mask_kernel(uint8_t* __restrict__ keep, long long n, uint32_t thresh,
                                  uint64_t seed, uint64_t stream_id, const uint64_t* __restrict__ epoch,
                                  int aligned4) {
+    pdl_prologue();
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (q * 4 >= n) return;
     const uint64_t stream = stream_id + (epoch ? (*epoch << 32) : 0ull);
@@ -577,7 +599,7 @@ int keep_mask(uint8_t* keep, long long n, float p, uint64_t seed, uint64_t strea
     if (n <= 0) return XGGM_OK;
     XGGM_REQUIRE(p >= 0.f && p < 1.f);
     const int aligned4 = (reinterpret_cast<uintptr_t>(keep) & 3) == 0;
-    keep_mask_kernel<<<grid1d((n + 3) / 4), 256, 0, st>>>(keep, n, drop_threshold(p), seed, stream_id, epoch, aligned4);
+    XGGM_LAUNCH((keep_mask_kernel), grid1d((n + 3) / 4), 256, 0, st, keep, n, drop_threshold(p), seed, stream_id, epoch, aligned4);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }

@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(256)
 adj_apply_kernel(const float* __restrict__ adj, const float* __restrict__ x,
                  float* __restrict__ out, bf16* __restrict__ hi, bf16* __restrict__ lo, int N, int H,
                  float alpha0, const float* __restrict__ alpha_dev, float self_w, int accumulate) {
+    pdl_prologue();
     extern __shared__ float s_adj[];  // [N][N], s_adj[i*N+j] = coefficient of x_j in out_i
     const int b = blockIdx.y;
     const float* ab = adj + (size_t)b * N * N;
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(128, 5)
 adj_apply36_kernel(const float* __restrict__ adj, const float* __restrict__ x, float* __restrict__ out,
                    bf16* __restrict__ hi, bf16* __restrict__ lo, int H, float alpha0,
                    const float* __restrict__ alpha_dev, float self_w, int accumulate) {
+    pdl_prologue();
     constexpr int N = 36;
     __shared__ __align__(16) float s_c[N * N];
     const int b = blockIdx.y;
@@ -148,16 +150,16 @@ int adj_apply(const float* adj, const float* x, float* out, bf16* hi, bf16* lo, 
     if (N == 36 && H % 2 == 0 && al8(x) && al8(out) && al8(hi) && al8(lo)) {
         dim3 grid(ceil_div(H, 256), B);
         if (trans)
-            adj_apply36_kernel<true><<<grid, 128, 0, st>>>(adj, x, out, hi, lo, H, alpha0, alpha_dev, self_w, accumulate);
+            XGGM_LAUNCH((adj_apply36_kernel<true>), grid, 128, 0, st, adj, x, out, hi, lo, H, alpha0, alpha_dev, self_w, accumulate);
         else
-            adj_apply36_kernel<false><<<grid, 128, 0, st>>>(adj, x, out, hi, lo, H, alpha0, alpha_dev, self_w, accumulate);
+            XGGM_LAUNCH((adj_apply36_kernel<false>), grid, 128, 0, st, adj, x, out, hi, lo, H, alpha0, alpha_dev, self_w, accumulate);
     } else {
         dim3 grid(ceil_div(H, 256), B);
         const size_t smem = sizeof(float) * N * N;
         if (trans)
-            adj_apply_kernel<12, true><<<grid, 256, smem, st>>>(adj, x, out, hi, lo, N, H, alpha0, alpha_dev, self_w, accumulate);
+            XGGM_LAUNCH((adj_apply_kernel<12, true>), grid, 256, smem, st, adj, x, out, hi, lo, N, H, alpha0, alpha_dev, self_w, accumulate);
         else
-            adj_apply_kernel<12, false><<<grid, 256, smem, st>>>(adj, x, out, hi, lo, N, H, alpha0, alpha_dev, self_w, accumulate);
+            XGGM_LAUNCH((adj_apply_kernel<12, false>), grid, 256, smem, st, adj, x, out, hi, lo, N, H, alpha0, alpha_dev, self_w, accumulate);
     }
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
@@ -240,6 +242,7 @@ __global__ void __launch_bounds__(256)
 bmm_nt_kernel(const float* __restrict__ p, const float* __restrict__ q, float* __restrict__ out,
               int N, int H, float alpha0, const float* __restrict__ alpha_dev, int accumulate,
               const float* __restrict__ dot_ref, float* __restrict__ dot_out) {
+    pdl_prologue();
     extern __shared__ float sm[];
     __shared__ float part[8];
     float* ps = sm;
@@ -291,7 +294,7 @@ int bmm_nt(const float* p, const float* q, float* out, int B, int N, int H, floa
     const size_t smem = sizeof(float) * 2 * N * (CK + 1);
     if (smem > 48 * 1024)
         XGGM_CUDA_TRY(cudaFuncSetAttribute(bmm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bmm_nt_kernel<<<B, 256, smem, st>>>(p, q, out, N, H, alpha0, alpha_dev, accumulate, dot_ref, dot_out);
+    XGGM_LAUNCH((bmm_nt_kernel), B, 256, smem, st, p, q, out, N, H, alpha0, alpha_dev, accumulate, dot_ref, dot_out);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
@@ -301,6 +304,7 @@ __global__ void __launch_bounds__(256)
 adj_regen_fwd_kernel(const float* __restrict__ x, float* __restrict__ adj_out,
                      float* __restrict__ S_out, int32_t* __restrict__ amax_out, int N, int H,
                      int squash) {
+    pdl_prologue();
     extern __shared__ float sm[];
     float* ps = sm;                       // [N][CK+1]
     float* S = sm + N * (CK + 1);         // [N][N]
@@ -339,7 +343,7 @@ int adj_regen_fwd(const float* x, float* adj_out, float* S, int32_t* amax, int B
     const size_t smem = sizeof(float) * ((size_t)N * (CK + 1) + (size_t)N * N + N);
     if (smem > 48 * 1024)
         XGGM_CUDA_TRY(cudaFuncSetAttribute(adj_regen_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    adj_regen_fwd_kernel<<<B, 256, smem, st>>>(x, adj_out, S, amax, N, H, squash);
+    XGGM_LAUNCH((adj_regen_fwd_kernel), B, 256, smem, st, x, adj_out, S, amax, N, H, squash);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
@@ -349,6 +353,7 @@ int adj_regen_fwd(const float* x, float* adj_out, float* S, int32_t* amax, int B
 __global__ void __launch_bounds__(128)
 regen_from_s_kernel(const float* __restrict__ S_in, float* __restrict__ adj_out,
                     int32_t* __restrict__ amax_out, int N, int squash) {
+    pdl_prologue();
     extern __shared__ float sm[];
     float* S = sm;          // [N][N]
     float* m = sm + N * N;  // [N]
@@ -381,7 +386,7 @@ int adj_regen_from_s(const float* S, float* adj_out, int32_t* amax, int B, int N
     const size_t smem = sizeof(float) * ((size_t)N * N + N);
     if (smem > 48 * 1024)
         XGGM_CUDA_TRY(cudaFuncSetAttribute(regen_from_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    regen_from_s_kernel<<<B, 128, smem, st>>>(S, adj_out, amax, N, squash);
+    XGGM_LAUNCH((regen_from_s_kernel), B, 128, smem, st, S, adj_out, amax, N, squash);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
@@ -391,6 +396,7 @@ __global__ void __launch_bounds__(256)
 scale_accum_kernel(const float* __restrict__ S, float* __restrict__ out, long long n, float alpha0,
                    const float* __restrict__ alpha_dev, int accumulate, const float* __restrict__ dot_ref,
                    float* __restrict__ dot_out) {
+    pdl_prologue();
     __shared__ float part[8];
     const float alpha = alpha0 + (alpha_dev ? alpha_dev[0] : 0.f);
     float dot = 0.f;
@@ -416,7 +422,7 @@ int scale_accum(const float* S, float* out, long long n, float alpha0, const flo
                 const float* dot_ref, float* dot_out, cudaStream_t st) {
     if (n <= 0) return XGGM_OK;
     const int grid = (int)min((long long)296, (n + 255) / 256);
-    scale_accum_kernel<<<grid, 256, 0, st>>>(S, out, n, alpha0, alpha_dev, accumulate, dot_ref, dot_out);
+    XGGM_LAUNCH((scale_accum_kernel), grid, 256, 0, st, S, out, n, alpha0, alpha_dev, accumulate, dot_ref, dot_out);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
@@ -427,6 +433,7 @@ __global__ void __launch_bounds__(256)
 adj_regen_bwd_kernel(const float* __restrict__ gadj, const float* __restrict__ S_in,
                      const int32_t* __restrict__ amax, float* __restrict__ D_out, int N,
                      int squash) {
+    pdl_prologue();
     extern __shared__ float sm[];
     float* S = sm;             // [N][N]
     float* dS = S + N * N;     // [N][N]
@@ -480,7 +487,7 @@ int adj_regen_bwd_coeffs(const float* gadj, const float* S, const int32_t* amax,
     const size_t smem = sizeof(float) * (2 * (size_t)N * N + 2 * N);
     if (smem > 48 * 1024)
         XGGM_CUDA_TRY(cudaFuncSetAttribute(adj_regen_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    adj_regen_bwd_kernel<<<B, 256, smem, st>>>(gadj, S, amax, D, N, squash);
+    XGGM_LAUNCH((adj_regen_bwd_kernel), B, 256, smem, st, gadj, S, amax, D, N, squash);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
@@ -499,6 +506,7 @@ __global__ void __launch_bounds__(256)
 gat_scores_kernel(const float* __restrict__ h, const float* __restrict__ a,
                   const float* __restrict__ adj, float* __restrict__ att, int N, int H,
                   float slope) {
+    pdl_prologue();
     extern __shared__ float sm[];
     float* s1 = sm;        // [N]  a[:H] . h_i
     float* s2 = sm + N;    // [N]  a[H:] . h_j
@@ -545,11 +553,13 @@ gat_scores_kernel(const float* __restrict__ h, const float* __restrict__ a,
 }
 
 __global__ void elu_fwd_kernel(const float* __restrict__ pre, float* __restrict__ out, long long n) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { const float v = pre[i]; out[i] = v > 0.f ? v : expm1f(v); }
 }
 __global__ void elu_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ pre,
                                float* __restrict__ gpre, long long n) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { const float v = pre[i]; gpre[i] = gout[i] * (v > 0.f ? 1.f : expf(v)); }
 }
@@ -558,12 +568,12 @@ int gat_attn_fwd(const float* h, const float* a, const float* adj, float* out, f
                  float* pre, int B, int N, int H, float slope, int apply_elu, cudaStream_t st) {
     if (B <= 0) return XGGM_OK;
     XGGM_REQUIRE(N >= 1 && N <= MAX_NODES);
-    gat_scores_kernel<<<B, 256, sizeof(float) * 2 * N, st>>>(h, a, adj, att, N, H, slope);
+    XGGM_LAUNCH((gat_scores_kernel), B, 256, sizeof(float) * 2 * N, st, h, a, adj, att, N, H, slope);
     XGGM_LAUNCH_CHECK();
     if (!apply_elu) return adj_apply(att, h, out, nullptr, nullptr, B, N, H, 1.f, nullptr, 0.f, false, 0, st);
     XGGM_TRY(adj_apply(att, h, pre, nullptr, nullptr, B, N, H, 1.f, nullptr, 0.f, false, 0, st));
     const long long n = (long long)B * N * H;
-    elu_fwd_kernel<<<ceil_div(n, 256), 256, 0, st>>>(pre, out, n);
+    XGGM_LAUNCH((elu_fwd_kernel), ceil_div(n, 256), 256, 0, st, pre, out, n);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
@@ -575,6 +585,7 @@ gat_scores_bwd_kernel(const float* __restrict__ h, const float* __restrict__ a,
                       const float* __restrict__ adj, const float* __restrict__ att,
                       const float* __restrict__ gatt, float* __restrict__ gh,
                       float* __restrict__ ga, int N, int H, float slope) {
+    pdl_prologue();
     extern __shared__ float sm[];
     float* s1 = sm;            // [N]
     float* s2 = s1 + N;        // [N]
@@ -645,14 +656,14 @@ int gat_attn_bwd(const float* gout, const float* h, const float* a, const float*
     const float* gpre = gout;
     float* gatt = work + n;
     if (apply_elu) {
-        elu_bwd_kernel<<<ceil_div(n, 256), 256, 0, st>>>(gout, pre, work, n);
+        XGGM_LAUNCH((elu_bwd_kernel), ceil_div(n, 256), 256, 0, st, gout, pre, work, n);
         XGGM_LAUNCH_CHECK();
         gpre = work;
     }
     XGGM_TRY(adj_apply(att, gpre, gh, nullptr, nullptr, B, N, H, 1.f, nullptr, 0.f, true, 0, st));   // gh = att^T gpre
     XGGM_TRY(bmm_nt(gpre, h, gatt, B, N, H, 1.f, nullptr, 0, nullptr, nullptr, st));                                   // gatt = gpre h^T
     const size_t smem = sizeof(float) * (4 * (size_t)N + (size_t)N * N);
-    gat_scores_bwd_kernel<<<B, 256, smem, st>>>(h, a, adj, att, gatt, gh, ga, N, H, slope);
+    XGGM_LAUNCH((gat_scores_bwd_kernel), B, 256, smem, st, h, a, adj, att, gatt, gh, ga, N, H, slope);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }

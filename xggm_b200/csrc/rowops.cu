@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 ln_fwd_fast(const float* __restrict__ u, const float* __restrict__ gamma, const float* __restrict__ beta,
             float* __restrict__ h, float* __restrict__ xhat, float* __restrict__ rstd_out,
             bf16* __restrict__ hi, bf16* __restrict__ lo, int M, float eps) {
+    pdl_prologue();
     constexpr int H = NV * 128;
     extern __shared__ __align__(16) float sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -179,6 +180,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 ln_bwd_fast(const float* __restrict__ gh, const float* __restrict__ xhat, const float* __restrict__ rstd,
             const float* __restrict__ gamma, float* __restrict__ gu, float* __restrict__ ggamma,
             float* __restrict__ gbeta, bf16* __restrict__ hi, bf16* __restrict__ lo, int M) {
+    pdl_prologue();
     constexpr int H = NV * 128;
     extern __shared__ __align__(16) float sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -259,6 +261,7 @@ gld_fwd_fast(const float* __restrict__ z, const float* __restrict__ gamma, const
              const DropSpec drop, float* __restrict__ out,
              float* __restrict__ mean_out, float* __restrict__ rstd_out, bf16* __restrict__ hi,
              bf16* __restrict__ lo, int M, float eps, int accumulate) {
+    pdl_prologue();
     constexpr int H = NV * 128;
     extern __shared__ __align__(16) float sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -325,6 +328,7 @@ gld_bwd_fast(const float* __restrict__ gout, const float* __restrict__ z, const 
              const float* __restrict__ rstd, const float* __restrict__ gamma, const DropSpec drop,
              float* __restrict__ gz, float* __restrict__ ggamma, float* __restrict__ gbeta,
              float* __restrict__ gbias, bf16* __restrict__ hi, bf16* __restrict__ lo, int M) {
+    pdl_prologue();
     constexpr int H = NV * 128;
     extern __shared__ __align__(16) float sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -421,6 +425,7 @@ __global__ void __launch_bounds__(GEN_WARPS * 32)
 ln_fwd_gen(const float* __restrict__ u, const float* __restrict__ gamma, const float* __restrict__ beta,
            float* __restrict__ h, float* __restrict__ xhat, float* __restrict__ rstd_out,
            bf16* __restrict__ hi, bf16* __restrict__ lo, int M, int H, float eps) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     int r0, r1;
     row_range(M, r0, r1);
@@ -449,6 +454,7 @@ __global__ void __launch_bounds__(GEN_WARPS * 32)
 ln_bwd_gen(const float* __restrict__ gh, const float* __restrict__ xhat, const float* __restrict__ rstd,
            const float* __restrict__ gamma, float* __restrict__ gu, float* __restrict__ ggamma,
            float* __restrict__ gbeta, bf16* __restrict__ hi, bf16* __restrict__ lo, int M, int H) {
+    pdl_prologue();
     extern __shared__ float sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* sg = sm + (size_t)warp * 3 * H;
@@ -492,6 +498,7 @@ gld_fwd_gen(const float* __restrict__ z, const float* __restrict__ gamma, const 
             const DropSpec drop, float* __restrict__ out,
             float* __restrict__ mean_out, float* __restrict__ rstd_out, bf16* __restrict__ hi,
             bf16* __restrict__ lo, int M, int H, float eps, int accumulate) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     const uint64_t dstream = drop_stream(drop);
     const float scale = drop.scale;
@@ -525,6 +532,7 @@ gld_bwd_gen(const float* __restrict__ gout, const float* __restrict__ z, const f
             const float* __restrict__ rstd, const float* __restrict__ gamma, const DropSpec drop,
             float* __restrict__ gz, float* __restrict__ ggamma, float* __restrict__ gbeta,
             float* __restrict__ gbias, bf16* __restrict__ hi, bf16* __restrict__ lo, int M, int H) {
+    pdl_prologue();
     extern __shared__ float sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t dstream = drop_stream(drop);
@@ -626,10 +634,10 @@ int layernorm_fwd(const float* u, const float* gamma, const float* beta, float* 
             constexpr size_t smem = RowPrefetch<NV, 1>::SMEM;
             static bool attr = false;
             if (!attr) { XGGM_CUDA_TRY(cudaFuncSetAttribute(ln_fwd_fast<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-            ln_fwd_fast<NV><<<fast_grid(M, 3), ROW_WARPS * 32, smem, st>>>(u, gamma, beta, h, xhat, rstd, hi, lo, M, eps);
+            XGGM_LAUNCH((ln_fwd_fast<NV>), fast_grid(M, 3), ROW_WARPS * 32, smem, st, u, gamma, beta, h, xhat, rstd, hi, lo, M, eps);
         });
     } else {
-        ln_fwd_gen<<<gen_grid(M), GEN_WARPS * 32, 0, st>>>(u, gamma, beta, h, xhat, rstd, hi, lo, M, H, eps);
+        XGGM_LAUNCH((ln_fwd_gen), gen_grid(M), GEN_WARPS * 32, 0, st, u, gamma, beta, h, xhat, rstd, hi, lo, M, H, eps);
     }
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
@@ -644,12 +652,12 @@ int layernorm_bwd(const float* gh, const float* xhat, const float* rstd, const f
             constexpr size_t smem = RowPrefetch<NV, 2>::SMEM;   // (>= the ROW_WARPS*H floats flush_columns needs)
             static bool attr = false;
             if (!attr) { XGGM_CUDA_TRY(cudaFuncSetAttribute(ln_bwd_fast<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-            ln_bwd_fast<NV><<<fast_grid(M, 1), ROW_WARPS * 32, smem, st>>>(gh, xhat, rstd, gamma, gu, ggamma, gbeta, hi, lo, M);
+            XGGM_LAUNCH((ln_bwd_fast<NV>), fast_grid(M, 1), ROW_WARPS * 32, smem, st, gh, xhat, rstd, gamma, gu, ggamma, gbeta, hi, lo, M);
         });
     } else {
         size_t smem;
         XGGM_TRY(gen_smem(ln_bwd_gen, H, smem));
-        ln_bwd_gen<<<gen_grid(M), GEN_WARPS * 32, smem, st>>>(gh, xhat, rstd, gamma, gu, ggamma, gbeta, hi, lo, M, H);
+        XGGM_LAUNCH((ln_bwd_gen), gen_grid(M), GEN_WARPS * 32, smem, st, gh, xhat, rstd, gamma, gu, ggamma, gbeta, hi, lo, M, H);
     }
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
@@ -664,10 +672,10 @@ int gelu_ln_drop_fwd(const float* z, const float* gamma, const float* beta, cons
             constexpr size_t smem = RowPrefetch<NV, 2>::SMEM;
             static bool attr = false;
             if (!attr) { XGGM_CUDA_TRY(cudaFuncSetAttribute(gld_fwd_fast<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-            gld_fwd_fast<NV><<<fast_grid(M), ROW_WARPS * 32, smem, st>>>(z, gamma, beta, drop, out, mean, rstd, hi, lo, M, eps, accumulate);
+            XGGM_LAUNCH((gld_fwd_fast<NV>), fast_grid(M), ROW_WARPS * 32, smem, st, z, gamma, beta, drop, out, mean, rstd, hi, lo, M, eps, accumulate);
         });
     } else {
-        gld_fwd_gen<<<gen_grid(M), GEN_WARPS * 32, 0, st>>>(z, gamma, beta, drop, out, mean, rstd, hi, lo, M, H, eps, accumulate);
+        XGGM_LAUNCH((gld_fwd_gen), gen_grid(M), GEN_WARPS * 32, 0, st, z, gamma, beta, drop, out, mean, rstd, hi, lo, M, H, eps, accumulate);
     }
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
@@ -683,12 +691,12 @@ int gelu_ln_drop_bwd(const float* gout, const float* z, const float* mean, const
             constexpr size_t smem = RowPrefetch<NV, 2>::SMEM;   // (>= the ROW_WARPS*H floats flush_columns needs)
             static bool attr = false;
             if (!attr) { XGGM_CUDA_TRY(cudaFuncSetAttribute(gld_bwd_fast<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-            gld_bwd_fast<NV><<<fast_grid(M, 1), ROW_WARPS * 32, smem, st>>>(gout, z, mean, rstd, gamma, drop, gz, ggamma, gbeta, gbias, hi, lo, M);
+            XGGM_LAUNCH((gld_bwd_fast<NV>), fast_grid(M, 1), ROW_WARPS * 32, smem, st, gout, z, mean, rstd, gamma, drop, gz, ggamma, gbeta, gbias, hi, lo, M);
         });
     } else {
         size_t smem;
         XGGM_TRY(gen_smem(gld_bwd_gen, H, smem));
-        gld_bwd_gen<<<gen_grid(M), GEN_WARPS * 32, smem, st>>>(gout, z, mean, rstd, gamma, drop, gz, ggamma, gbeta, gbias, hi, lo, M, H);
+        XGGM_LAUNCH((gld_bwd_gen), gen_grid(M), GEN_WARPS * 32, smem, st, gout, z, mean, rstd, gamma, drop, gz, ggamma, gbeta, gbias, hi, lo, M, H);
     }
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
