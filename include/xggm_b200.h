@@ -242,6 +242,20 @@ int xggm_fuse_readout_fwd(const float* xp, const float* nodes, float* out, int B
 /* gxp[B,H] = gout[:, :H];  gnodes[B,N,H] (+)= gout[:, H:] * (1-t^2)/N with t = out[:, H:] */
 int xggm_fuse_readout_bwd(const float* gout, const float* out, float* gxp, float* gnodes, int B,
                           int N, int H, int accumulate_gnodes, xggm_stream_t s);
+/* Node-branch tail in one pass per direction          src/vqa/vqacpv2.py:236-246 (= gqa_ood.py:243-252)
+ *   loss[0] = kl_w * compute_kl_loss(nodes, feat) + sm_w * loss_func(nodes, target, sigma)
+ *   cat[B,2H] = [xp | tanh(mean_n nodes)]                       (the fusion_fc input)
+ * i.e. xggm_sym_kl + xggm_score_mse + xggm_fuse_readout with the generated node features read once
+ * and their gradient written once.  kl_w carries the trainer's weights (0.15 * num_answers), sm_w = 6.
+ * bwd: gnodes[B,N,H] = gloss[0] * d loss/d nodes + read-out gradient of gcat; gfeat (nullable) =
+ * gloss[0] * d loss/d feat; gxp[B,H] = gcat[:, :H]; grow[B,H] is caller scratch. */
+int xggm_node_tail_fwd(const float* nodes, const float* feat, const float* target, const float* xp,
+                       double sigma, double kl_w, double sm_w, float* loss, float* cat, int B, int N,
+                       int H, xggm_stream_t s);
+int xggm_node_tail_bwd(const float* nodes, const float* feat, const float* target, const float* cat,
+                       const float* gloss, const float* gcat, double sigma, double kl_w, double sm_w,
+                       float* gnodes, float* gfeat, float* gxp, float* grow, int B, int N, int H,
+                       xggm_stream_t s);
 /* elementwise sigmoid (encoder_adj tail, src/vqa/vqacpv2_model.py:91-94) */
 int xggm_sigmoid_fwd(const float* x, float* y, long long n, xggm_stream_t s);
 int xggm_sigmoid_bwd(const float* gy, const float* y, float* gx, long long n, xggm_stream_t s);

@@ -63,6 +63,8 @@ SIGNATURES = {
     "xggm_sym_kl_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "xggm_fuse_readout_fwd": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "xggm_fuse_readout_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "xggm_node_tail_fwd": [_vp, _vp, _vp, _vp, _d, _d, _d, _vp, _vp, _i, _i, _i, _vp],
+    "xggm_node_tail_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "xggm_sigmoid_fwd": [_vp, _vp, _ll, _vp],
     "xggm_sigmoid_bwd": [_vp, _vp, _vp, _ll, _vp],
     "xggm_keep_mask": [_vp, _ll, _f, _u64, _u64, _vp, _vp],

@@ -799,6 +799,26 @@ int xggm_fuse_readout_bwd(const float* gout, const float* out, float* gxp, float
     XGGM_REQUIRE(gout && out && gnodes && B >= 0 && N > 0 && H > 0);
     return fuse_readout_bwd(gout, out, gxp, gnodes, B, N, H, accumulate_gnodes, as_stream(s));
 }
+int xggm_node_tail_fwd(const float* nodes, const float* feat, const float* target, const float* xp,
+                       double sigma, double kl_w, double sm_w, float* loss, float* cat, int B, int N,
+                       int H, xggm_stream_t s) {
+    XGGM_REQUIRE(loss && B >= 0 && N > 0 && H > 0);
+    if (B == 0) {
+        XGGM_CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float), as_stream(s)));
+        return XGGM_OK;
+    }
+    XGGM_REQUIRE(nodes && feat && target && xp && cat);
+    return node_tail_fwd(nodes, feat, target, xp, (float)sigma, (float)kl_w, (float)sm_w, loss, cat, B, N, H, as_stream(s));
+}
+int xggm_node_tail_bwd(const float* nodes, const float* feat, const float* target, const float* cat,
+                       const float* gloss, const float* gcat, double sigma, double kl_w, double sm_w,
+                       float* gnodes, float* gfeat, float* gxp, float* grow, int B, int N, int H,
+                       xggm_stream_t s) {
+    if (B == 0) return XGGM_OK;
+    XGGM_REQUIRE(nodes && feat && target && cat && gloss && gcat && gnodes && gxp && grow && B >= 0 && N > 0 && H > 0);
+    return node_tail_bwd(nodes, feat, target, cat, gloss, gcat, (float)sigma, (float)kl_w, (float)sm_w, gnodes, gfeat,
+                         gxp, grow, B, N, H, as_stream(s));
+}
 int xggm_sigmoid_fwd(const float* x, float* y, long long n, xggm_stream_t s) {
     if (n == 0) return XGGM_OK;
     XGGM_REQUIRE(x && y && n >= 0);

@@ -220,23 +220,33 @@ int gemm_simt(int op, const float* A, const float* Bm, const float* bias, const 
     return XGGM_OK;
 }
 
-// column sums: out[c] = sum_r g[r,c]  (bias gradients)
-__global__ void colsum_kernel(const float* __restrict__ g, float* __restrict__ out, int R, int C,
-                              int rows_per_block) {
+// column sums: out[c] = sum_r g[r,c]  (bias gradients).  A thread owns one column of a row slab and keeps
+// eight independent loads in flight; slabs are sized so that ~4 CTAs per SM exist even for a few hundred rows.
+__global__ void __launch_bounds__(128)
+colsum_kernel(const float* __restrict__ g, float* __restrict__ out, int R, int C, int rows_per_block) {
     pdl_prologue();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const int r0 = blockIdx.y * rows_per_block, r1 = min(R, r0 + rows_per_block);
     float s = 0.f;
-    for (int r = r0; r < r1; ++r) s += g[(size_t)r * C + c];
+    int r = r0;
+    for (; r + 8 <= r1; r += 8) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = g[(size_t)(r + i) * C + c];
+        s += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    }
+    for (; r < r1; ++r) s += g[(size_t)r * C + c];
     atomicAdd(&out[c], s);
 }
 
 int colsum(const float* g, float* out, int R, int C, int accumulate, cudaStream_t st) {
     if (!accumulate) XGGM_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
     if (R <= 0) return XGGM_OK;
-    const int rpb = 64;
-    dim3 grid(ceil_div(C, 128), ceil_div(R, rpb));
+    const int gx = ceil_div(C, 128);
+    int rpb = ceil_div(R, max(1, 592 / gx));   // ~592 CTAs
+    rpb = max(8, (rpb + 7) & ~7);
+    dim3 grid(gx, ceil_div(R, rpb));
     XGGM_LAUNCH((colsum_kernel), grid, 128, 0, st, g, out, R, C, rpb);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;

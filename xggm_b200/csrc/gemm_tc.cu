@@ -860,7 +860,11 @@ int gemm_tc_group(bool a_mn, bool b_mn, const GemmProb* pr, int count, int M, in
         XGGM_REQUIRE(pr[g].a_hi && pr[g].b_hi && pr[g].C && (npass == 1 || (pr[g].a_lo && pr[g].b_lo)));
     const int sms = num_sms();
     const int num_kb = ceil_div(K, tc::BK);
-    const bool pair = !a_mn && !b_mn && M > tc::BM && pair_enabled() && sms % 2 == 0;
+    // Few output tiles (a head on [B,768] rows: M = 256 -> 4 pair tiles) cannot fill the machine: those products
+    // take the single-CTA kernel with narrow 128 x 64 tiles (3x the CTAs, whole K per tile -> still deterministic).
+    const long long pair_tiles = (long long)ceil_div(M, 2 * tc::BM) * ceil_div(N, 192) * count;
+    const bool starved = !a_mn && !b_mn && !allow_split_k && pair_tiles * 8 <= sms;
+    const bool pair = !a_mn && !b_mn && M > tc::BM && pair_enabled() && sms % 2 == 0 && !starved;
     // K-major x K-major (forward, and dgrad against transposed weight planes): CTA-pair kernel,
     // 256 x 192 tiles, cta_group::2 MMAs, each CTA stages half of the B tile.
     constexpr int PBN = 192;
@@ -883,6 +887,7 @@ int gemm_tc_group(bool a_mn, bool b_mn, const GemmProb* pr, int count, int M, in
             if (best < 0 || cost < best) { best = cost; bn = w; }
         }
         splits = splits_for[bn == 192 ? 0 : 1];
+        if (starved) { bn = 64; splits = 1; }
     }
     const int tiles_n = ceil_div(N, bn);
     const int kb_per_split = ceil_div(num_kb, splits);
@@ -936,7 +941,10 @@ int gemm_tc_group(bool a_mn, bool b_mn, const GemmProb* pr, int count, int M, in
                         : launch_tc<PBN, 1, false, false, 2>(maps, p, grid, st);
     } else {
         const int grid = min(sms, total);
-        if (bn == 192) {
+        if (bn == 64) {
+            rc = npass == 3 ? launch_tc<64, 3, false, false>(maps, p, grid, st)
+                            : launch_tc<64, 1, false, false>(maps, p, grid, st);
+        } else if (bn == 192) {
             rc = npass == 3 ? dispatch_major<192, 3>(a_mn, b_mn, maps, p, grid, st)
                             : dispatch_major<192, 1>(a_mn, b_mn, maps, p, grid, st);
         } else {

@@ -228,6 +228,20 @@ int score_mse_bwd(const float* s, const float* t, const float* gloss, float sigm
 
 // ---------------------------------------------------------------- symmetric KL
 // One warp per row.  L_row = sum_c (py-px)(log py - log px).
+//
+// Node-branch tail (src/vqa/vqacpv2.py:236-246): the same pass can also carry the score-matching term of
+// loss_sm = kl_w * KL(x, y) + sm_w * loss_func(x, target) and, in the backward direction, the read-out
+// gradient that is identical for all `rows_per_group` nodes of a graph -- so the generated node features
+// are read once per direction and their gradient is written once (TailExtras; all-zero = plain KL).
+struct TailExtras {
+    const float* sm_target;   // [R,C] score-matching target, or null
+    const float* row_add;     // [R / rows_per_group, C] added to every gx row of its group, or null
+    float kl_w;               // weight of the KL term (1 for the plain entry points)
+    float sm_fwd;             // sm_w * 0.5 sigma^2 / (R*C)
+    float sm_bwd;             // sm_w * sigma^2 / (R*C)
+    int rows_per_group;
+};
+static inline TailExtras tail_none() { return TailExtras{nullptr, nullptr, 1.f, 0.f, 0.f, 1}; }
 struct RowSoftmax {
     float mx, lse;  // log p_c = v_c - mx - lse
 };
@@ -243,11 +257,11 @@ __device__ __forceinline__ RowSoftmax row_softmax_stats(const float* __restrict_
 
 __global__ void __launch_bounds__(256)
 sym_kl_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
-                  float* __restrict__ loss, int R, int C, float inv_count) {
+                  float* __restrict__ loss, int R, int C, float inv_count, const TailExtras ex) {
     pdl_prologue();
     __shared__ float part[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float acc = 0.f;
+    float acc = 0.f, acc_sm = 0.f;
     for (int r = blockIdx.x * 8 + warp; r < R; r += gridDim.x * 8) {
         const float* xr = x + (size_t)r * C;
         const float* yr = y + (size_t)r * C;
@@ -258,24 +272,32 @@ sym_kl_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
             // F.kl_div(log_px, py) + F.kl_div(log_py, px), reduction='none'
             acc += py * (lpy - lpx) + px * (lpx - lpy);
         }
+        if (ex.sm_target) {
+            const float* tr = ex.sm_target + (size_t)r * C;
+            for (int c = lane; c < C; c += 32) {
+                const float d = xr[c] - tr[c];
+                acc_sm = fmaf(d, d, acc_sm);
+            }
+        }
     }
+    acc = acc * (inv_count * ex.kl_w) + acc_sm * ex.sm_fwd;
     acc = warp_sum(acc);
     if (lane == 0) part[warp] = acc;
     __syncthreads();
     if (threadIdx.x < 32) {
         float v = threadIdx.x < 8 ? part[threadIdx.x] : 0.f;
         v = warp_sum(v);
-        if (threadIdx.x == 0) atomicAdd(loss, v * inv_count);
+        if (threadIdx.x == 0) atomicAdd(loss, v);
     }
 }
 
 __global__ void __launch_bounds__(256)
 sym_kl_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
                   const float* __restrict__ gloss, float* __restrict__ gx,
-                  float* __restrict__ gy, int R, int C, float inv_count) {
+                  float* __restrict__ gy, int R, int C, float inv_count, const TailExtras ex) {
     pdl_prologue();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float g = gloss[0] * inv_count;
+    const float g = gloss[0] * inv_count * ex.kl_w, gsm = gloss[0] * ex.sm_bwd;
     for (int r = blockIdx.x * 8 + warp; r < R; r += gridDim.x * 8) {
         const float* xr = x + (size_t)r * C;
         const float* yr = y + (size_t)r * C;
@@ -293,7 +315,10 @@ sym_kl_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
             const float lpx = xr[c] - sx.mx - sx.lse, lpy = yr[c] - sy.mx - sy.lse;
             const float px = expf(lpx), py = expf(lpy);
             const float e = lpy - lpx, d = py - px;
-            if (gx) gx[(size_t)r * C + c] = g * (px * (ax - e) - d);
+            float ox = g * (px * (ax - e) - d);
+            if (ex.sm_target) ox = fmaf(gsm, xr[c] - ex.sm_target[(size_t)r * C + c], ox);
+            if (ex.row_add) ox += ex.row_add[(size_t)(r / ex.rows_per_group) * C + c];
+            if (gx) gx[(size_t)r * C + c] = ox;
             if (gy) gy[(size_t)r * C + c] = g * (py * (e - ay) + d);
         }
     }
@@ -328,13 +353,14 @@ template <int NV, bool BWD>
 __global__ void __launch_bounds__(256)
 sym_kl_fast_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ loss,
                    const float* __restrict__ gloss, float* __restrict__ gx, float* __restrict__ gy, int R,
-                   float inv_count) {
+                   float inv_count, const TailExtras tx) {
     pdl_prologue();
     constexpr int C = NV * 128;
     __shared__ float part[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float g = BWD ? gloss[0] * inv_count : 0.f;
-    float acc = 0.f;
+    const float g = BWD ? gloss[0] * inv_count * tx.kl_w : 0.f;
+    const float gsm = BWD ? gloss[0] * tx.sm_bwd : 0.f;
+    float acc = 0.f, acc_sm = 0.f;
     for (int r = blockIdx.x * 8 + warp; r < R; r += gridDim.x * 8) {
         float dx[NV * 4], ex[NV * 4], dy[NV * 4], ey[NV * 4];
         float isx, lsx, isy, lsy;
@@ -345,6 +371,16 @@ sym_kl_fast_kernel(const float* __restrict__ x, const float* __restrict__ y, flo
             for (int i = 0; i < NV * 4; ++i) {
                 const float lpx = dx[i] - lsx, lpy = dy[i] - lsy;
                 acc += (ey[i] * isy - ex[i] * isx) * (lpy - lpx);   // py (lpy-lpx) + px (lpx-lpy)
+            }
+            if (tx.sm_target) {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    const size_t o = (size_t)r * C + 128 * i + 4 * lane;
+                    const float4 xv = *reinterpret_cast<const float4*>(x + o);
+                    const float4 tv = *reinterpret_cast<const float4*>(tx.sm_target + o);
+                    const float d0 = xv.x - tv.x, d1 = xv.y - tv.y, d2 = xv.z - tv.z, d3 = xv.w - tv.w;
+                    acc_sm += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+                }
             }
         } else {
             float ax = 0.f, ay = 0.f;
@@ -369,19 +405,31 @@ sym_kl_fast_kernel(const float* __restrict__ x, const float* __restrict__ y, flo
                     oy[j] = g * (ey[k] * (dx[k] - ay) + d);
                 }
                 const size_t o = (size_t)r * C + 128 * i + 4 * lane;
+                if (tx.sm_target) {
+                    const float4 xv = *reinterpret_cast<const float4*>(x + o);
+                    const float4 tv = *reinterpret_cast<const float4*>(tx.sm_target + o);
+                    ox[0] = fmaf(gsm, xv.x - tv.x, ox[0]); ox[1] = fmaf(gsm, xv.y - tv.y, ox[1]);
+                    ox[2] = fmaf(gsm, xv.z - tv.z, ox[2]); ox[3] = fmaf(gsm, xv.w - tv.w, ox[3]);
+                }
+                if (tx.row_add) {
+                    const float4 av = *reinterpret_cast<const float4*>(
+                        tx.row_add + (size_t)(r / tx.rows_per_group) * C + 128 * i + 4 * lane);
+                    ox[0] += av.x; ox[1] += av.y; ox[2] += av.z; ox[3] += av.w;
+                }
                 if (gx) *reinterpret_cast<float4*>(gx + o) = make_float4(ox[0], ox[1], ox[2], ox[3]);
                 if (gy) *reinterpret_cast<float4*>(gy + o) = make_float4(oy[0], oy[1], oy[2], oy[3]);
             }
         }
     }
     if (!BWD) {
+        acc = acc * (inv_count * tx.kl_w) + acc_sm * tx.sm_fwd;
         acc = warp_sum(acc);
         if (lane == 0) part[warp] = acc;
         __syncthreads();
         if (threadIdx.x < 32) {
             float v = threadIdx.x < 8 ? part[threadIdx.x] : 0.f;
             v = warp_sum(v);
-            if (threadIdx.x == 0) atomicAdd(loss, v * inv_count);
+            if (threadIdx.x == 0) atomicAdd(loss, v);
         }
     }
 }
@@ -396,37 +444,47 @@ sym_kl_fast_kernel(const float* __restrict__ x, const float* __restrict__ y, flo
         case 7: { constexpr int NV = 7; __VA_ARGS__; } break; \
         default: { constexpr int NV = 8; __VA_ARGS__; } break; \
     }
-static inline bool kl_fast_ok(int C, const void* a, const void* b, const void* c = nullptr, const void* d = nullptr) {
-    return C % 128 == 0 && C >= 128 && C <= 1024 && al16(a) && al16(b) && al16(c) && al16(d);
-}
 
-int sym_kl_fwd(const float* x, const float* y, float* loss, int R, int C, cudaStream_t st) {
+static inline bool kl_fast_ok(int C, const void* a, const void* b, const void* c = nullptr, const void* d = nullptr,
+                              const void* e = nullptr, const void* f = nullptr) {
+    return C % 128 == 0 && C >= 128 && C <= 1024 && al16(a) && al16(b) && al16(c) && al16(d) && al16(e) && al16(f);
+}
+static int kl_fwd_launch(const float* x, const float* y, float* loss, int R, int C, const TailExtras& ex, cudaStream_t st) {
     XGGM_CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float), st));
     if (R <= 0 || C <= 0) return XGGM_OK;
-    if (kl_fast_ok(C, x, y)) {
+    const float inv = 1.0f / ((float)R * (float)C);
+    if (kl_fast_ok(C, x, y, ex.sm_target)) {
         const int grid = min(148 * 4, ceil_div(R, 8));
-        XGGM_KL_DISPATCH(C, (XGGM_LAUNCH((sym_kl_fast_kernel<NV, false>), grid, 256, 0, st, x, y, loss, nullptr, nullptr, nullptr, R, 1.0f / ((float)R * (float)C))));
+        XGGM_KL_DISPATCH(C, (XGGM_LAUNCH((sym_kl_fast_kernel<NV, false>), grid, 256, 0, st, x, y, loss, nullptr, nullptr, nullptr, R, inv, ex)));
         XGGM_LAUNCH_CHECK();
         return XGGM_OK;
     }
     const int grid = min(148 * 8, ceil_div(R, 8));
-    XGGM_LAUNCH((sym_kl_fwd_kernel), grid, 256, 0, st, x, y, loss, R, C, 1.0f / ((float)R * (float)C));
+    XGGM_LAUNCH((sym_kl_fwd_kernel), grid, 256, 0, st, x, y, loss, R, C, inv, ex);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
+}
+static int kl_bwd_launch(const float* x, const float* y, const float* gloss, float* gx, float* gy, int R, int C,
+                         const TailExtras& ex, cudaStream_t st) {
+    if (R <= 0 || C <= 0) return XGGM_OK;
+    const float inv = 1.0f / ((float)R * (float)C);
+    if (kl_fast_ok(C, x, y, gx, gy, ex.sm_target, ex.row_add)) {
+        const int grid = min(148 * 4, ceil_div(R, 8));
+        XGGM_KL_DISPATCH(C, (XGGM_LAUNCH((sym_kl_fast_kernel<NV, true>), grid, 256, 0, st, x, y, nullptr, gloss, gx, gy, R, inv, ex)));
+        XGGM_LAUNCH_CHECK();
+        return XGGM_OK;
+    }
+    const int grid = min(148 * 8, ceil_div(R, 8));
+    XGGM_LAUNCH((sym_kl_bwd_kernel), grid, 256, 0, st, x, y, gloss, gx, gy, R, C, inv, ex);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+int sym_kl_fwd(const float* x, const float* y, float* loss, int R, int C, cudaStream_t st) {
+    return kl_fwd_launch(x, y, loss, R, C, tail_none(), st);
 }
 int sym_kl_bwd(const float* x, const float* y, const float* gloss, float* gx, float* gy, int R,
                int C, cudaStream_t st) {
-    if (R <= 0 || C <= 0) return XGGM_OK;
-    if (kl_fast_ok(C, x, y, gx, gy)) {
-        const int grid = min(148 * 4, ceil_div(R, 8));
-        XGGM_KL_DISPATCH(C, (XGGM_LAUNCH((sym_kl_fast_kernel<NV, true>), grid, 256, 0, st, x, y, nullptr, gloss, gx, gy, R, 1.0f / ((float)R * (float)C))));
-        XGGM_LAUNCH_CHECK();
-        return XGGM_OK;
-    }
-    const int grid = min(148 * 8, ceil_div(R, 8));
-    XGGM_LAUNCH((sym_kl_bwd_kernel), grid, 256, 0, st, x, y, gloss, gx, gy, R, C, 1.0f / ((float)R * (float)C));
-    XGGM_LAUNCH_CHECK();
-    return XGGM_OK;
+    return kl_bwd_launch(x, y, gloss, gx, gy, R, C, tail_none(), st);
 }
 
 // --------------------------------------------------------------- fusion readout
@@ -443,8 +501,8 @@ __global__ void fuse_readout_fwd_kernel(const float* __restrict__ xp, const floa
     out[b * 2 * H + H + c] = tanhf(s / (float)N);
 }
 __global__ void fuse_readout_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ out,
-                                        float* __restrict__ gxp, float* __restrict__ gnodes, int B,
-                                        int N, int H, int accumulate) {
+                                        float* __restrict__ gxp, float* __restrict__ gnodes, float* __restrict__ grow,
+                                        int B, int N, int H, int accumulate) {
     pdl_prologue();
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (long long)B * H) return;
@@ -453,6 +511,8 @@ __global__ void fuse_readout_bwd_kernel(const float* __restrict__ gout, const fl
     if (gxp) gxp[e] = gout[b * 2 * H + c];
     const float t = out[b * 2 * H + H + c];
     const float g = gout[b * 2 * H + H + c] * (1.f - t * t) / (float)N;
+    if (grow) grow[e] = g;   // the per-graph row every node shares (consumed by the fused node-tail backward)
+    if (!gnodes) return;
     for (int n = 0; n < N; ++n) {
         float* p = gnodes + (b * N + n) * H + c;
         *p = accumulate ? *p + g : g;
@@ -469,9 +529,34 @@ int fuse_readout_bwd(const float* gout, const float* out, float* gxp, float* gno
                      int H, int accumulate, cudaStream_t st) {
     const long long total = (long long)B * H;
     if (total <= 0) return XGGM_OK;
-    XGGM_LAUNCH((fuse_readout_bwd_kernel), grid1d(total), 256, 0, st, gout, out, gxp, gnodes, B, N, H, accumulate);
+    XGGM_LAUNCH((fuse_readout_bwd_kernel), grid1d(total), 256, 0, st, gout, out, gxp, gnodes, nullptr, B, N, H, accumulate);
     XGGM_LAUNCH_CHECK();
     return XGGM_OK;
+}
+
+// ------------------------------------------------------------------- node-branch tail
+// loss = kl_w * sym_kl(nodes, feat) + sm_w * loss_func(nodes, target, sigma);  cat = [xp | tanh(mean_n nodes)]
+int node_tail_fwd(const float* nodes, const float* feat, const float* target, const float* xp, float sigma, float kl_w,
+                  float sm_w, float* loss, float* cat, int B, int N, int H, cudaStream_t st) {
+    const int R = B * N;
+    const float n = (float)R * (float)H;
+    const TailExtras ex{target, nullptr, kl_w, R > 0 ? sm_w * 0.5f * sigma * sigma / n : 0.f, 0.f, N};
+    XGGM_TRY(kl_fwd_launch(nodes, feat, loss, R, H, ex, st));
+    return fuse_readout_fwd(xp, nodes, cat, B, N, H, st);
+}
+// gnodes = d loss / d nodes * gloss + (read-out gradient of gcat, the same row for every node of a graph);
+// gfeat (nullable) = d loss / d feat * gloss; gxp = gcat[:, :H]; grow [B,H] is scratch.
+int node_tail_bwd(const float* nodes, const float* feat, const float* target, const float* cat, const float* gloss,
+                  const float* gcat, float sigma, float kl_w, float sm_w, float* gnodes, float* gfeat, float* gxp,
+                  float* grow, int B, int N, int H, cudaStream_t st) {
+    const int R = B * N;
+    const long long total = (long long)B * H;
+    if (total <= 0) return XGGM_OK;
+    XGGM_LAUNCH((fuse_readout_bwd_kernel), grid1d(total), 256, 0, st, gcat, cat, gxp, nullptr, grow, B, N, H, 0);
+    XGGM_LAUNCH_CHECK();
+    const float n = (float)R * (float)H;
+    const TailExtras ex{target, grow, kl_w, 0.f, sm_w * sigma * sigma / n, N};
+    return kl_bwd_launch(nodes, feat, gloss, gnodes, gfeat, R, H, ex, st);
 }
 
 // ------------------------------------------------------------------- sigmoid

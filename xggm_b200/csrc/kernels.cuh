@@ -77,6 +77,11 @@ int sym_kl_fwd(const float*, const float*, float*, int, int, cudaStream_t);
 int sym_kl_bwd(const float*, const float*, const float*, float*, float*, int, int, cudaStream_t);
 int fuse_readout_fwd(const float*, const float*, float*, int, int, int, cudaStream_t);
 int fuse_readout_bwd(const float*, const float*, float*, float*, int, int, int, int, cudaStream_t);
+int node_tail_fwd(const float* nodes, const float* feat, const float* target, const float* xp, float sigma, float kl_w,
+                  float sm_w, float* loss, float* cat, int B, int N, int H, cudaStream_t st);
+int node_tail_bwd(const float* nodes, const float* feat, const float* target, const float* cat, const float* gloss,
+                  const float* gcat, float sigma, float kl_w, float sm_w, float* gnodes, float* gfeat, float* gxp,
+                  float* grow, int B, int N, int H, cudaStream_t st);
 int sigmoid_fwd(const float*, float*, long long, cudaStream_t);
 int sigmoid_bwd(const float*, const float*, float*, long long, cudaStream_t);
 int keep_mask(uint8_t*, long long, float, uint64_t, uint64_t, const uint64_t*, cudaStream_t);

@@ -615,6 +615,46 @@ class _FuseReadout(torch.autograd.Function):
         return gxp, gn
 
 
+class _NodeTail(torch.autograd.Function):
+    """Node-branch tail (vqacpv2.py:236-246): weighted KL + score-matching loss and the fusion_fc input."""
+
+    @staticmethod
+    def forward(ctx, nodes, feat, target, xp, sigma, kl_w, sm_w):
+        nodes, feat, target, xp = f32(nodes, "nodes"), f32(feat, "feat"), f32(target, "target"), f32(xp, "x")
+        B, N, H = nodes.shape
+        if feat.shape != nodes.shape or target.shape != nodes.shape or xp.shape != (B, H):
+            raise RuntimeError("xggm_b200.node_tail: shape mismatch")
+        loss = torch.empty(1, device=nodes.device, dtype=torch.float32)
+        cat = torch.empty((B, 2 * H), device=nodes.device, dtype=torch.float32)
+        call("xggm_node_tail_fwd", ptr(nodes), ptr(feat), ptr(target), ptr(xp), float(sigma), float(kl_w), float(sm_w),
+             ptr(loss), ptr(cat), B, N, H)
+        ctx.save_for_backward(nodes, feat, target, cat)
+        ctx.cfg = (float(sigma), float(kl_w), float(sm_w))
+        return loss.reshape(()), cat
+
+    @staticmethod
+    def backward(ctx, gloss, gcat):
+        nodes, feat, target, cat = ctx.saved_tensors
+        sigma, kl_w, sm_w = ctx.cfg
+        B, N, H = nodes.shape
+        gloss = (torch.zeros(1, device=nodes.device) if gloss is None else f32(gloss)).reshape(1)
+        gcat = torch.zeros_like(cat) if gcat is None else f32(gcat)
+        gn = torch.empty_like(nodes)
+        gf = torch.empty_like(feat) if ctx.needs_input_grad[1] else None
+        gxp = torch.empty((B, H), device=nodes.device, dtype=torch.float32)
+        grow = torch.empty((B, H), device=nodes.device, dtype=torch.float32)
+        call("xggm_node_tail_bwd", ptr(nodes), ptr(feat), ptr(target), ptr(cat), ptr(gloss), ptr(gcat), sigma, kl_w, sm_w,
+             ptr(gn), ptr(gf), ptr(gxp), ptr(grow), B, N, H)
+        # the score-matching target's own gradient (never needed by the trainers) is the negated SM part
+        return gn, gf, None, gxp, None, None, None
+
+
+def node_tail(nodes, feat, target, xp, sigma, kl_w, sm_w):
+    """(kl_w * compute_kl_loss(nodes, feat) + sm_w * loss_func(nodes, target, sigma),
+    cat[xp, tanh(mean_n nodes)]) in one pass over the node features per direction."""
+    return _NodeTail.apply(nodes, feat, target, xp, sigma, kl_w, sm_w)
+
+
 def fuse_readout(xp, nodes):
     """cat[x, tanh(mean_n nodes)] (src/vqa/vqacpv2.py:216-218)."""
     return _FuseReadout.apply(xp, nodes)

@@ -69,7 +69,10 @@ class XGGMHeads(nn.Module):
         nodes0 = self.init_nodes(x)
         node_feats, feat_grad = glue.add_feature_noise(nodes0, sigma=sigma, randn=randn, n_nodes=self.n_nodes)
         node_feats, adj_gen = self.generator(node_feats, adj_t)
-        d_loss = glue.compute_kl_loss(node_feats, feat) * num_answers
-        loss_grad = glue.loss_func(node_feats, feat_grad, sigma=sigma)
-        loss_sm = 0.15 * d_loss + 6 * loss_grad
-        return self.fuse(x, node_feats), loss_sm, node_feats, adj_gen
+        # loss_sm = 0.15 * compute_kl_loss(node_feats, feat) * A + 6 * loss_func(node_feats, feat_grad, sigma)
+        # and the fusion_fc input, one pass over node_feats per direction (xggm_node_tail_*)
+        loss_sm, cat = XF.node_tail(node_feats, feat, feat_grad, x, sigma, 0.15 * num_answers, 6.0)
+        m = self.fusion_fc
+        z = XF.linear(cat, m[0].weight, m[0].bias)
+        x_gen = XF.gelu_ln_drop(z, m[2].weight, m[2].bias, None, 0.0, m[2].eps)
+        return x_gen, loss_sm, node_feats, adj_gen
