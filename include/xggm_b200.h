@@ -129,6 +129,18 @@ int xggm_gelu_ln_drop_bwd(const float* gout, const float* z, const float* mean, 
                           float* ggamma, float* gbeta, int M, int H, xggm_stream_t s);
 
 /* ------------------------------------------------------------------------- *
+ * Operand-plane hand-over (tensor-core engines).  The tcgen05 kernels read every fp32 tensor as
+ * two bf16 "planes" (hi = bf16(v), lo = bf16(v - hi)).  A kernel that PRODUCES a tensor can emit
+ * its planes in the same pass, and the `_ex` entry points below let the caller hand those planes
+ * to the CONSUMERS of that tensor (`*_planes` arguments; NULL = build them internally, which is
+ * what the plain entry points do), so the [B,N,H] node features are not re-read and re-split once
+ * per consumer (next GNN layer, adjacency regeneration forward and backward).  A plane buffer is
+ * xggm_planes_bytes(n_elems) bytes, 16-byte aligned, layout hi[pad8(n)] | lo[pad8(n)] bf16; it is
+ * only meaningful for the precision it was written under and is ignored by the exact-fp32 engine.
+ * ------------------------------------------------------------------------- */
+long long xggm_planes_bytes(long long n_elems);
+
+/* ------------------------------------------------------------------------- *
  * Adjacency regeneration   ggm.py:225-228 (GCN), :188-191 (GIN), :261-264 (GAT),
  * :124-126 (EdgeGenerator, squash = 0)
  *   S = x x^T ; m_i = max_k S[k,i] ; adj[i,j] = sigmoid(S[i,j]/m_i) (i != j), 0 on the diagonal
@@ -139,11 +151,16 @@ int xggm_gelu_ln_drop_bwd(const float* gout, const float* z, const float* mean, 
 long long xggm_adj_regen_work_bytes(int B, int N, int H);
 int xggm_adj_regen_fwd(const float* x, float* adj_out, float* S, int32_t* amax, int B, int N,
                        int H, int squash, void* work, xggm_stream_t s);
+int xggm_adj_regen_fwd_ex(const float* x, float* adj_out, float* S, int32_t* amax, int B, int N,
+                          int H, int squash, void* work, const void* x_planes, xggm_stream_t s);
 /* gx (+)= (dS + dS^T) x.  `work` is a [B,N,N] scratch buffer; `tc_work`? (xggm_adj_apply_work_bytes bytes)
  * moves the D x product onto the tensor cores. */
 int xggm_adj_regen_bwd(const float* gadj, const float* x, const float* S, const int32_t* amax,
                        float* gx, float* work, int B, int N, int H, int squash,
                        int accumulate_gx, void* tc_work, xggm_stream_t s);
+int xggm_adj_regen_bwd_ex(const float* gadj, const float* x, const float* S, const int32_t* amax,
+                          float* gx, float* work, int B, int N, int H, int squash,
+                          int accumulate_gx, void* tc_work, const void* x_planes, xggm_stream_t s);
 
 /* ------------------------------------------------------------------------- *
  * Whole GCN / GIN layers (conv chain + jump-knowledge read-out)
@@ -176,6 +193,12 @@ int xggm_gnn_fwd(int kind, const float* x, const float* adj, const float* const*
                  const float* const* head_params, const uint8_t* const* keeps, const xggm_philox_t* philox,
                  float drop_p, float* out, float* saved, float* work, int B, int N, int H, int n_convs,
                  xggm_stream_t s);
+/* x_planes? : planes of x from its producer; out_planes? : receives the planes of `out` (emitted by the
+ * last read-out accumulation).  The backward call must get the same x_planes. */
+int xggm_gnn_fwd_ex(int kind, const float* x, const float* adj, const float* const* conv_params,
+                    const float* const* head_params, const uint8_t* const* keeps, const xggm_philox_t* philox,
+                    float drop_p, float* out, float* saved, float* work, const void* x_planes, void* out_planes,
+                    int B, int N, int H, int n_convs, xggm_stream_t s);
 /* Gradient tables mirror the parameter tables (same order); every parameter-gradient buffer is
  * overwritten, or accumulated into when accumulate_param_grads != 0 (the buffers then are the
  * parameters' live .grad tensors).  gx[B,N,H] is always overwritten; gadj[B,N,N] is overwritten, or may be
@@ -186,6 +209,12 @@ int xggm_gnn_bwd(int kind, const float* gout, const float* x, const float* adj,
                  const uint8_t* const* keeps, const xggm_philox_t* philox, float drop_p, const float* saved,
                  float* work, float* gx, float* gadj, float* const* conv_grads, float* const* head_grads,
                  int accumulate_param_grads, int B, int N, int H, int n_convs, xggm_stream_t s);
+int xggm_gnn_bwd_ex(int kind, const float* gout, const float* x, const float* adj,
+                    const float* const* conv_params, const float* const* head_params,
+                    const uint8_t* const* keeps, const xggm_philox_t* philox, float drop_p, const float* saved,
+                    float* work, float* gx, float* gadj, float* const* conv_grads, float* const* head_grads,
+                    int accumulate_param_grads, const void* x_planes, int B, int N, int H, int n_convs,
+                    xggm_stream_t s);
 
 /* ------------------------------------------------------------------------- *
  * GAT attention  src/module/gat.py:25-49 (after h = linear_layer(x), which is
@@ -219,6 +248,9 @@ int xggm_edge_noise(const float* adj, const float* randn, double sigma, float* n
  * (node_fc on 36 identical rows, src/vqa/vqacpv2.py:228-229). */
 int xggm_feat_noise(const float* f, const float* randn, double sigma, float* noisy, float* target,
                     int B, int N, int H, int f_is_broadcast, xggm_stream_t s);
+/* same, also emitting the planes of `noisy` (noisy_planes?) for the first GNN layer */
+int xggm_feat_noise_ex(const float* f, const float* randn, double sigma, float* noisy, float* target,
+                       void* noisy_planes, int B, int N, int H, int f_is_broadcast, xggm_stream_t s);
 /* out[B,H] = sum_n g[B,n,H]  (backward of the broadcast above) */
 int xggm_sum_nodes(const float* g, float* out, int B, int N, int H, xggm_stream_t s);
 /* loss_func                                               src/vqa/vqacpv2.py:48-51

@@ -451,6 +451,34 @@ def test_philox_heads_match_materialised_masks():
     assert abs(frac - 0.5) < 5e-3
 
 
+def test_operand_plane_handover_is_exact_and_drops_stale_planes():
+    """Planes emitted by the producer of a tensor (feature noise, previous GNN layer) and handed to its
+    consumers give bit-identical results to consumers that split the tensor themselves; an in-place
+    update of the tensor invalidates the hand-over."""
+    import xggm_b200 as X
+    import xggm_b200.functional as XF
+    torch.manual_seed(5)
+    mod = X.GCNGenerator(768, 2).to(dev()).eval()
+    f = torch.randn(3, 768, device=dev())
+    rn = torch.randn(3, 36, 768, device=dev())
+    adj = torch.rand(3, 36, 36, device=dev())
+    noisy, _ = X.add_feature_noise(f, sigma=1.0, randn=rn)
+    assert XF._planes_of(noisy) is not None
+    x1, a1 = mod(noisy, adj)
+    assert XF._planes_of(x1) is not None          # emitted by the last read-out accumulation
+    plain = noisy.clone()                          # a fresh tensor carries no planes
+    assert XF._planes_of(plain) is None
+    x2, a2 = mod(plain, adj)
+    assert torch.equal(x1, x2) and torch.equal(a1, a2)
+    a_direct = XF.adj_regen(x1.clone())
+    assert torch.equal(a_direct, a1)
+    noisy.mul_(2.0)                                # stale planes must not be used
+    assert XF._planes_of(noisy) is None
+    x3, _ = mod(noisy, adj)
+    x4, _ = mod(plain * 2.0, adj)
+    assert torch.equal(x3, x4)
+
+
 def test_graphed_step_matches_eager_and_redraws_dropout():
     import xggm_b200 as X
     from xggm_b200.ddp import FlatGrads

@@ -221,7 +221,8 @@ static int wgrad_group(bool tc, const Lin* l, int n, int M, int N, int K, cudaSt
 
 static int gnn_fwd(int kind, const float* x, const float* adj, const float* const* cp,
                    const float* const* hp, const uint8_t* const* keeps, const xggm_philox_t* philox, float drop_p, float* out,
-                   float* saved, float* work, int B, int N, int H, int nc, cudaStream_t st) {
+                   float* saved, float* work, const void* x_planes, void* out_planes, int B, int N, int H, int nc,
+                   cudaStream_t st) {
     XGGM_REQUIRE(kind == XGGM_KIND_GCN || kind == XGGM_KIND_GIN);
     XGGM_REQUIRE(B >= 0 && N > 0 && H > 0 && nc >= 0 && nc <= MAX_CONVS && drop_p >= 0.f && drop_p < 1.f);
     const int M = B * N;
@@ -232,8 +233,10 @@ static int gnn_fwd(int kind, const float* x, const float* adj, const float* cons
     const long long MHn = (long long)M * H;
     Operand wconv[MAX_CONVS], whead[MAX_CONVS + 1];
     XGGM_TRY(split_weights(kind, cp, hp, work + L.MH, L, H, wconv, whead, tc, false, st));
-    Operand hop = planes_at(x, saved + L.xplanes, MHn);   // current node features as a GEMM operand
-    if (tc) XGGM_TRY(split_one(hop, MHn, st));
+    // current node features as a GEMM operand: planes handed over by the producer of x, else built here
+    Operand hop = x_planes ? planes_at(x, static_cast<float*>(const_cast<void*>(x_planes)), MHn)
+                           : planes_at(x, saved + L.xplanes, MHn);
+    if (tc && !x_planes) XGGM_TRY(split_one(hop, MHn, st));
     Operand hops[MAX_CONVS + 1];
     hops[0] = hop;
     const float* h = x;
@@ -247,9 +250,13 @@ static int gnn_fwd(int kind, const float* x, const float* adj, const float* cons
     auto head_lin = [&](int j) -> Lin {   // z_j = h_j W_j^T + b_j
         return Lin{hops[j], whead[j], hp[4 * j + 1], nullptr, saved + L.head(j, 0), nullptr, 0};
     };
-    auto head_post = [&](int j) -> int {  // out (+)= dropout(LN(GeLU(z_j)))
+    // out (+)= dropout(LN(GeLU(z_j))); the last accumulation can also emit `out` as operand planes for its consumers
+    const Operand out_op = planes_at(out, static_cast<float*>(out_planes), MHn);
+    auto head_post = [&](int j) -> int {
+        const bool emit = tc && out_planes && j == nc;
         return gelu_ln_drop_fwd(saved + L.head(j, 0), hp[4 * j + 2], hp[4 * j + 3], head_drop(keeps, philox, drop_p, j), out,
-                                saved + L.head(j, 1), saved + L.head(j, 2), nullptr, nullptr, M, H, LN_EPS, j > 0, st);
+                                saved + L.head(j, 1), saved + L.head(j, 2), emit ? mut(out_op.hi) : nullptr,
+                                emit ? lo_or_null(out_op) : nullptr, M, H, LN_EPS, j > 0, st);
     };
     for (int k = 0; k < nc; ++k) {
         float* h_next = saved + L.conv(k, 2);
@@ -293,7 +300,7 @@ static int gnn_fwd(int kind, const float* x, const float* adj, const float* cons
 static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj,
                    const float* const* cp, const float* const* hp, const uint8_t* const* keeps,
                    const xggm_philox_t* philox, float drop_p, const float* saved_c, float* work, float* gx, float* gadj,
-                   float* const* cg, float* const* hg, int acc, int B, int N, int H, int nc,
+                   float* const* cg, float* const* hg, int acc, const void* x_planes, int B, int N, int H, int nc,
                    cudaStream_t st) {
     XGGM_REQUIRE(kind == XGGM_KIND_GCN || kind == XGGM_KIND_GIN);
     XGGM_REQUIRE(B >= 0 && N > 0 && H > 0 && nc >= 0 && nc <= MAX_CONVS && cp && hp && cg && hg);
@@ -337,8 +344,10 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
         XGGM_TRY(build_blockdiag(adj, coef_hi, npass() == 3 ? coef_lo : nullptr, B, N, 1.f, nullptr, 0.f, 1, st));
 
     auto act = [&](int j) -> Operand {   // h_j as a GEMM operand (planes saved by the forward pass)
-        return j == 0 ? planes_at(x, saved + L.xplanes, MHn)
-                      : planes_at(saved + L.conv(j - 1, 2), saved + L.conv(j - 1, 6), MHn);
+        if (j == 0)
+            return x_planes ? planes_at(x, static_cast<float*>(const_cast<void*>(x_planes)), MHn)
+                            : planes_at(x, saved + L.xplanes, MHn);
+        return planes_at(saved + L.conv(j - 1, 2), saved + L.conv(j - 1, 6), MHn);
     };
     // Three gradient regions of [M,H] floats each: bf16 planes under the tensor-core engine (the fp32
     // tensor never exists), the fp32 tensor itself under the exact engine.
@@ -581,12 +590,12 @@ static inline bool adj_tc_ok(const void* work, int N, int H) {
 // out (=|+=) self_w * v + alpha * (adj | adj^T) @ v through the tensor cores
 static int adj_apply_tc_f32(const float* adj, const float* v, float* out, int B, int N, int H, float alpha0,
                             const float* alpha_dev, float self_w, int trans, int accumulate, float* work,
-                            cudaStream_t st) {
+                            cudaStream_t st, const void* v_planes = nullptr) {
     const long long n = (long long)B * N * H;
-    const Operand vo = planes_at(v, work, n);
+    const Operand vo = planes_at(v, v_planes ? static_cast<float*>(const_cast<void*>(v_planes)) : work, n);
     bf16* chi = reinterpret_cast<bf16*>(work + pad8(n));
     bf16* clo = chi + pad8(adj_tc_coef_elems(B, N));
-    XGGM_TRY(split_one(vo, n, st));
+    if (!v_planes) XGGM_TRY(split_one(vo, n, st));
     XGGM_TRY(build_blockdiag(adj, chi, npass() == 3 ? clo : nullptr, B, N, alpha0, alpha_dev, self_w, trans, st));
     return adj_apply_tc(chi, clo, vo.hi, vo.lo, out, nullptr, nullptr, B, N, H, accumulate, npass(), st);
 }
@@ -643,33 +652,44 @@ long long xggm_adj_regen_work_bytes(int B, int N, int H) {
     if (B < 0 || N <= 0 || H <= 0) return -1;
     return 4 * pad8((long long)B * N * H);
 }
-int xggm_adj_regen_fwd(const float* x, float* adj_out, float* S, int32_t* amax, int B, int N,
-                       int H, int squash, void* work, xggm_stream_t s) {
+long long xggm_planes_bytes(long long n_elems) { return n_elems < 0 ? -1 : 4 * pad8(n_elems); }
+int xggm_adj_regen_fwd_ex(const float* x, float* adj_out, float* S, int32_t* amax, int B, int N,
+                          int H, int squash, void* work, const void* x_planes, xggm_stream_t s) {
     XGGM_REQUIRE(B >= 0 && H > 0);
     if (B == 0) return XGGM_OK;
     XGGM_REQUIRE(x && adj_out);
-    if (work && S && g_precision != XGGM_PREC_FP32_SIMT && gram_tc_supported(N, H)) {
+    if ((work || x_planes) && S && g_precision != XGGM_PREC_FP32_SIMT && gram_tc_supported(N, H)) {
         // pair scores on the tensor cores: planes of x -> Gram kernel -> S, then the per-graph tail
         const long long n = (long long)B * N * H;
-        const Operand xo = planes_at(x, static_cast<float*>(work), n);
-        XGGM_TRY(split_one(xo, n, as_stream(s)));
+        const Operand xo = planes_at(x, static_cast<float*>(x_planes ? const_cast<void*>(x_planes) : work), n);
+        if (!x_planes) XGGM_TRY(split_one(xo, n, as_stream(s)));
         XGGM_TRY(gram_tc(xo.hi, xo.lo, xo.hi, xo.lo, S, B, N, H, npass(), as_stream(s)));
         return adj_regen_from_s(S, adj_out, amax, B, N, squash, as_stream(s));
     }
     return adj_regen_fwd(x, adj_out, S, amax, B, N, H, squash, as_stream(s));
 }
-int xggm_adj_regen_bwd(const float* gadj, const float* x, const float* S, const int32_t* amax,
-                       float* gx, float* work, int B, int N, int H, int squash,
-                       int accumulate_gx, void* tc_work, xggm_stream_t s) {
+int xggm_adj_regen_fwd(const float* x, float* adj_out, float* S, int32_t* amax, int B, int N,
+                       int H, int squash, void* work, xggm_stream_t s) {
+    return xggm_adj_regen_fwd_ex(x, adj_out, S, amax, B, N, H, squash, work, nullptr, s);
+}
+int xggm_adj_regen_bwd_ex(const float* gadj, const float* x, const float* S, const int32_t* amax,
+                          float* gx, float* work, int B, int N, int H, int squash,
+                          int accumulate_gx, void* tc_work, const void* x_planes, xggm_stream_t s) {
     XGGM_REQUIRE(B >= 0 && H > 0);
     if (B == 0) return XGGM_OK;
     XGGM_REQUIRE(gadj && x && S && amax && gx && work);
     if (adj_tc_ok(tc_work, N, H) && (reinterpret_cast<uintptr_t>(gx) & 15) == 0) {
         // D = dS + dS^T per graph (small kernel), then gx (+)= D x on the tensor cores
         XGGM_TRY(adj_regen_bwd_coeffs(gadj, S, amax, work, B, N, squash, as_stream(s)));
-        return adj_apply_tc_f32(work, x, gx, B, N, H, 1.f, nullptr, 0.f, 0, accumulate_gx, static_cast<float*>(tc_work), as_stream(s));
+        return adj_apply_tc_f32(work, x, gx, B, N, H, 1.f, nullptr, 0.f, 0, accumulate_gx, static_cast<float*>(tc_work),
+                                as_stream(s), x_planes);
     }
     return adj_regen_bwd(gadj, x, S, amax, gx, work, B, N, H, squash, accumulate_gx, as_stream(s));
+}
+int xggm_adj_regen_bwd(const float* gadj, const float* x, const float* S, const int32_t* amax,
+                       float* gx, float* work, int B, int N, int H, int squash,
+                       int accumulate_gx, void* tc_work, xggm_stream_t s) {
+    return xggm_adj_regen_bwd_ex(gadj, x, S, amax, gx, work, B, N, H, squash, accumulate_gx, tc_work, nullptr, s);
 }
 
 long long xggm_gnn_saved_floats(int kind, int B, int N, int H, int n_convs) {
@@ -683,11 +703,28 @@ long long xggm_gnn_work_floats(int kind, int B, int N, int H, int n_convs) {
     const long long wb = L.work_bwd((long long)B * N * N, coef), wf = L.work_fwd(coef);
     return wb > wf ? wb : wf;
 }
+int xggm_gnn_fwd_ex(int kind, const float* x, const float* adj, const float* const* conv_params,
+                    const float* const* head_params, const uint8_t* const* keeps, const xggm_philox_t* philox,
+                    float drop_p, float* out, float* saved, float* work, const void* x_planes, void* out_planes,
+                    int B, int N, int H, int n_convs, xggm_stream_t s) {
+    return gnn_fwd(kind, x, adj, conv_params, head_params, keeps, philox, drop_p, out, saved, work, x_planes, out_planes,
+                   B, N, H, n_convs, as_stream(s));
+}
 int xggm_gnn_fwd(int kind, const float* x, const float* adj, const float* const* conv_params,
                  const float* const* head_params, const uint8_t* const* keeps, const xggm_philox_t* philox,
                  float drop_p, float* out, float* saved, float* work, int B, int N, int H, int n_convs,
                  xggm_stream_t s) {
-    return gnn_fwd(kind, x, adj, conv_params, head_params, keeps, philox, drop_p, out, saved, work, B, N, H, n_convs, as_stream(s));
+    return gnn_fwd(kind, x, adj, conv_params, head_params, keeps, philox, drop_p, out, saved, work, nullptr, nullptr,
+                   B, N, H, n_convs, as_stream(s));
+}
+int xggm_gnn_bwd_ex(int kind, const float* gout, const float* x, const float* adj,
+                    const float* const* conv_params, const float* const* head_params,
+                    const uint8_t* const* keeps, const xggm_philox_t* philox, float drop_p, const float* saved,
+                    float* work, float* gx, float* gadj, float* const* conv_grads, float* const* head_grads,
+                    int accumulate_param_grads, const void* x_planes, int B, int N, int H, int n_convs,
+                    xggm_stream_t s) {
+    return gnn_bwd(kind, gout, x, adj, conv_params, head_params, keeps, philox, drop_p, saved, work, gx, gadj,
+                   conv_grads, head_grads, accumulate_param_grads, x_planes, B, N, H, n_convs, as_stream(s));
 }
 int xggm_gnn_bwd(int kind, const float* gout, const float* x, const float* adj,
                  const float* const* conv_params, const float* const* head_params,
@@ -695,7 +732,7 @@ int xggm_gnn_bwd(int kind, const float* gout, const float* x, const float* adj,
                  float* work, float* gx, float* gadj, float* const* conv_grads, float* const* head_grads,
                  int accumulate_param_grads, int B, int N, int H, int n_convs, xggm_stream_t s) {
     return gnn_bwd(kind, gout, x, adj, conv_params, head_params, keeps, philox, drop_p, saved, work, gx, gadj,
-                   conv_grads, head_grads, accumulate_param_grads, B, N, H, n_convs, as_stream(s));
+                   conv_grads, head_grads, accumulate_param_grads, nullptr, B, N, H, n_convs, as_stream(s));
 }
 
 int xggm_gat_attn_fwd(const float* h, const float* a, const float* adj, float* out, float* att,
@@ -755,11 +792,18 @@ int xggm_edge_noise(const float* adj, const float* randn, double sigma, float* n
     XGGM_REQUIRE(adj && randn && noisy && target && B >= 0 && N > 0 && sigma != 0.0);
     return edge_noise(adj, randn, (float)sigma, (float)(sigma * sigma), noisy, target, B, N, as_stream(s));
 }
-int xggm_feat_noise(const float* f, const float* randn, double sigma, float* noisy, float* target,
-                    int B, int N, int H, int f_is_broadcast, xggm_stream_t s) {
+int xggm_feat_noise_ex(const float* f, const float* randn, double sigma, float* noisy, float* target,
+                       void* noisy_planes, int B, int N, int H, int f_is_broadcast, xggm_stream_t s) {
     if (B == 0) return XGGM_OK;
     XGGM_REQUIRE(f && randn && noisy && target && B >= 0 && N > 0 && H > 0 && sigma != 0.0);
-    return feat_noise(f, randn, (float)sigma, (float)(sigma * sigma), noisy, target, B, N, H, f_is_broadcast, as_stream(s));
+    const bool emit = noisy_planes && g_precision != XGGM_PREC_FP32_SIMT;
+    const Operand o = planes_at(noisy, static_cast<float*>(noisy_planes), (long long)B * N * H);
+    return feat_noise(f, randn, (float)sigma, (float)(sigma * sigma), noisy, target, emit ? mut(o.hi) : nullptr,
+                      emit ? lo_or_null(o) : nullptr, B, N, H, f_is_broadcast, as_stream(s));
+}
+int xggm_feat_noise(const float* f, const float* randn, double sigma, float* noisy, float* target,
+                    int B, int N, int H, int f_is_broadcast, xggm_stream_t s) {
+    return xggm_feat_noise_ex(f, randn, sigma, noisy, target, nullptr, B, N, H, f_is_broadcast, s);
 }
 int xggm_sum_nodes(const float* g, float* out, int B, int N, int H, xggm_stream_t s) {
     if (B == 0) return XGGM_OK;

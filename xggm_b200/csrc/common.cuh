@@ -1,5 +1,6 @@
 // Shared device helpers for the X-GGM graph-block kernels (sm_100a only).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
@@ -130,6 +131,25 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 }  // namespace ptx
+
+// ---- fp32 -> bf16 hi/lo operand planes (four consecutive elements, 8-byte stores; lo may be null) ----
+__device__ __forceinline__ void split_store4(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t off, float a, float b, float c, float d) {
+    const float v[4] = {a, b, c, d};
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        h[i] = __float2bfloat16_rn(v[i]);
+        const float hf = __bfloat162float(h[i]);
+        l[i] = __float2bfloat16_rn((hf - hf == 0.f) ? v[i] - hf : 0.f);
+    }
+    __nv_bfloat162 h01 = __halves2bfloat162(h[0], h[1]), h23 = __halves2bfloat162(h[2], h[3]);
+    *reinterpret_cast<uint2*>(hi + off) = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
+    if (lo) {
+        __nv_bfloat162 l01 = __halves2bfloat162(l[0], l[1]), l23 = __halves2bfloat162(l[2], l[3]);
+        *reinterpret_cast<uint2*>(lo + off) = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
+    }
+}
+
 
 // ---- math ------------------------------------------------------------------
 // Exact-erf GeLU (src/lxrt/modeling.py:116-124 of the reference): x*0.5*(1+erf(x/sqrt2)).

@@ -3,6 +3,7 @@
 // fusion read-out, sigmoid, Philox keep-masks.  All are one-pass, coalesced,
 // HBM-bound element/row kernels.
 #include "common.cuh"
+#include "kernels.cuh"
 
 namespace xggm {
 
@@ -113,7 +114,8 @@ __global__ void feat_noise_kernel(const float* __restrict__ f, const float* __re
 // float4 path: grid (chunks of one graph, B); no 64-bit division per element
 __global__ void __launch_bounds__(256)
 feat_noise_vec_kernel(const float* __restrict__ f, const float* __restrict__ randn, float sigma, float sigma2,
-                      float* __restrict__ noisy, float* __restrict__ target, int NH4, int H, int bcast) {
+                      float* __restrict__ noisy, float* __restrict__ target, __nv_bfloat16* __restrict__ hi,
+                      __nv_bfloat16* __restrict__ lo, int NH4, int H, int bcast) {
     pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;   // float4 index inside graph b
     if (i >= NH4) return;
@@ -123,22 +125,30 @@ feat_noise_vec_kernel(const float* __restrict__ f, const float* __restrict__ ran
     const float4 fv = bcast ? *reinterpret_cast<const float4*>(f + (size_t)b * H + (4 * i) % H)
                             : reinterpret_cast<const float4*>(f)[o];
     const float4 n = make_float4(r.x * sigma, r.y * sigma, r.z * sigma, r.w * sigma);
-    reinterpret_cast<float4*>(noisy)[o] = make_float4(fv.x + n.x, fv.y + n.y, fv.z + n.z, fv.w + n.w);
+    const float4 out = make_float4(fv.x + n.x, fv.y + n.y, fv.z + n.z, fv.w + n.w);
+    reinterpret_cast<float4*>(noisy)[o] = out;
     reinterpret_cast<float4*>(target)[o] = make_float4(-n.x / sigma2, -n.y / sigma2, -n.z / sigma2, -n.w / sigma2);
+    if (hi) split_store4(hi, lo, 4 * o, out.x, out.y, out.z, out.w);   // operand planes for the first GNN layer
 }
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 int feat_noise(const float* f, const float* randn, float sigma, float sigma2, float* noisy,
-               float* target, int B, int N, int H, int bcast, cudaStream_t st) {
+               float* target, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int N, int H, int bcast, cudaStream_t st) {
     const long long total = (long long)B * N * H;
     if (total <= 0) return XGGM_OK;
     if (H % 4 == 0 && al16(f) && al16(randn) && al16(noisy) && al16(target) && (long long)N * H / 4 < (1LL << 30)) {
         const int NH4 = N * H / 4;
-        XGGM_LAUNCH((feat_noise_vec_kernel), dim3(ceil_div(NH4, 256), B), 256, 0, st, f, randn, sigma, sigma2, noisy, target, NH4, H, bcast);
+        XGGM_LAUNCH((feat_noise_vec_kernel), dim3(ceil_div(NH4, 256), B), 256, 0, st, f, randn, sigma, sigma2, noisy, target, hi, lo, NH4, H, bcast);
         XGGM_LAUNCH_CHECK();
         return XGGM_OK;
     }
     XGGM_LAUNCH((feat_noise_kernel), grid1d(total), 256, 0, st, f, randn, sigma, sigma2, noisy, target, total, N, H, bcast);
     XGGM_LAUNCH_CHECK();
+    if (hi) {   // (rare shapes: planes through the stand-alone splitter)
+        const float* src[1] = {noisy};
+        __nv_bfloat16* h[1] = {hi};
+        __nv_bfloat16* l[1] = {lo};
+        return split_planes(src, h, lo ? l : nullptr, &total, 1, st);
+    }
     return XGGM_OK;
 }
 

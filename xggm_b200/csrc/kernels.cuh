@@ -69,7 +69,7 @@ int strip_diag(const float*, float*, int, int, cudaStream_t);
 int triu_scatter_fwd(const float*, float*, int, int, cudaStream_t);
 int triu_scatter_bwd(const float*, float*, int, int, cudaStream_t);
 int edge_noise(const float*, const float*, float, float, float*, float*, int, int, cudaStream_t);
-int feat_noise(const float*, const float*, float, float, float*, float*, int, int, int, int, cudaStream_t);
+int feat_noise(const float*, const float*, float, float, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, int, int, cudaStream_t);
 int sum_nodes(const float*, float*, int, int, int, cudaStream_t);
 int score_mse_fwd(const float*, const float*, float, float*, long long, cudaStream_t);
 int score_mse_bwd(const float*, const float*, const float*, float, float*, long long, cudaStream_t);

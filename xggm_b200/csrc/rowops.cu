@@ -20,23 +20,6 @@ typedef __nv_bfloat16 bf16;
 
 constexpr int ROW_WARPS = 8;  // warps per CTA (fast path)
 
-__device__ __forceinline__ void split_store4(bf16* hi, bf16* lo, size_t off, float a, float b, float c, float d) {
-    const float v[4] = {a, b, c, d};
-    bf16 h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        h[i] = __float2bfloat16_rn(v[i]);
-        const float hf = __bfloat162float(h[i]);
-        l[i] = __float2bfloat16_rn((hf - hf == 0.f) ? v[i] - hf : 0.f);
-    }
-    __nv_bfloat162 h01 = __halves2bfloat162(h[0], h[1]), h23 = __halves2bfloat162(h[2], h[3]);
-    *reinterpret_cast<uint2*>(hi + off) = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
-    if (lo) {
-        __nv_bfloat162 l01 = __halves2bfloat162(l[0], l[1]), l23 = __halves2bfloat162(l[2], l[3]);
-        *reinterpret_cast<uint2*>(lo + off) = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
-    }
-}
-
 template <int NV>
 __device__ __forceinline__ void load_row(const float* __restrict__ p, int lane, float (&v)[NV * 4]) {
 #pragma unroll

@@ -42,6 +42,40 @@ def _u8(t):
 
 
 # ---------------------------------------------------------------------------
+# operand-plane hand-over (include/xggm_b200.h, "Operand-plane hand-over")
+# ---------------------------------------------------------------------------
+# A kernel that produces a [B,N,H] tensor under a tensor-core engine also emits its bf16 operand planes;
+# the buffer rides on the tensor object (``_xggm_planes``) and the consumers of that tensor (next GNN layer,
+# adjacency regeneration fwd/bwd) pick it up instead of re-splitting the tensor.  The record is dropped as
+# soon as the tensor is modified in place, re-allocated, or the engine precision changes.
+def _planes_enabled():
+    return _lib.load().xggm_get_precision() != _lib.PRECISIONS["fp32_simt"]
+
+
+def _new_planes(t):
+    # (the producers emit planes exactly when the tensor-core engine can address the tensor: H % 8 == 0)
+    if not _planes_enabled() or t.shape[-1] % 8 != 0:
+        return None
+    n = _lib.load().xggm_planes_bytes(t.numel())
+    return torch.empty(max(int(n), 16), device=t.device, dtype=torch.uint8)
+
+
+def _attach_planes(t, planes):
+    if planes is not None:
+        t._xggm_planes = (planes, t._version, t.data_ptr(), _lib.load().xggm_get_precision())
+
+
+def _planes_of(t):
+    rec = getattr(t, "_xggm_planes", None)
+    if rec is None or not t.is_contiguous() or t.dtype != torch.float32:
+        return None
+    planes, version, data_ptr, prec = rec
+    if t._version != version or t.data_ptr() != data_ptr or prec != _lib.load().xggm_get_precision():
+        return None
+    return planes
+
+
+# ---------------------------------------------------------------------------
 # dense projection (nn.Linear)
 # ---------------------------------------------------------------------------
 def _linear_work(M, N, K, device):
@@ -225,16 +259,19 @@ def gelu_ln_drop(z, gamma, beta, keep=None, drop_p=0.0, eps=LN_EPS):
 # ---------------------------------------------------------------------------
 class _AdjRegen(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, squash):
+    def forward(ctx, x, squash, x_planes):
         x = f32(x, "x")
         B, N, H = x.shape
         adj = torch.empty((B, N, N), device=x.device, dtype=torch.float32)
         S = torch.empty_like(adj)
         amax = torch.empty((B, N), device=x.device, dtype=torch.int32)
-        nwork = _lib.load().xggm_adj_regen_work_bytes(B, N, H)
-        work = torch.empty(max(int(nwork), 16), device=x.device, dtype=torch.uint8)
-        call("xggm_adj_regen_fwd", ptr(x), ptr(adj), ptr(S), ptr(amax), B, N, H, int(squash), ptr(work))
+        work = None
+        if x_planes is None:
+            nwork = _lib.load().xggm_adj_regen_work_bytes(B, N, H)
+            work = torch.empty(max(int(nwork), 16), device=x.device, dtype=torch.uint8)
+        call("xggm_adj_regen_fwd_ex", ptr(x), ptr(adj), ptr(S), ptr(amax), B, N, H, int(squash), ptr(work), ptr(x_planes))
         ctx.save_for_backward(x, S, amax)
+        ctx.x_planes = x_planes
         ctx.squash = int(squash)
         ctx.mark_non_differentiable(amax)
         return adj, amax
@@ -246,14 +283,14 @@ class _AdjRegen(torch.autograd.Function):
         g = f32(g)
         gx = torch.empty_like(x)
         work = torch.empty_like(S)
-        call("xggm_adj_regen_bwd", ptr(g), ptr(x), ptr(S), ptr(amax), ptr(gx), ptr(work), B, N, H, ctx.squash, 0,
-             ptr(_adj_work(B, N, H, x.device)))
-        return gx, None
+        call("xggm_adj_regen_bwd_ex", ptr(g), ptr(x), ptr(S), ptr(amax), ptr(gx), ptr(work), B, N, H, ctx.squash, 0,
+             ptr(_adj_work(B, N, H, x.device)), ptr(ctx.x_planes))
+        return gx, None, None
 
 
 def adj_regen(x, squash=True, return_argmax=False):
     """sigmoid(x x^T / colmax) with zero diagonal (ggm.py:225-228)."""
-    adj, amax = _AdjRegen.apply(x, squash)
+    adj, amax = _AdjRegen.apply(x, squash, _planes_of(x))
     return (adj, amax) if return_argmax else adj
 
 
@@ -262,7 +299,7 @@ def adj_regen(x, squash=True, return_argmax=False):
 # ---------------------------------------------------------------------------
 class _GnnLayer(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, kind, n_convs, drop_p, keeps, philox, x, adj, *params):
+    def forward(ctx, kind, n_convs, drop_p, keeps, philox, x_planes, out_planes, x, adj, *params):
         x, adj = f32(x, "x"), f32(adj, "adj")
         B, N, H = x.shape
         if adj.shape != (B, N, N):
@@ -284,9 +321,10 @@ class _GnnLayer(torch.autograd.Function):
         out = torch.empty_like(x)
         cpt, hpt = ptr_table(cp), ptr_table(hp)
         kt = None if keeps is None else ptr_table(keeps)
-        call("xggm_gnn_fwd", kind, ptr(x), ptr(adj), cpt, hpt, kt, _philox_arg(philox), float(drop_p), ptr(out),
-             ptr(saved), ptr(work), B, N, H, n_convs)
+        call("xggm_gnn_fwd_ex", kind, ptr(x), ptr(adj), cpt, hpt, kt, _philox_arg(philox), float(drop_p), ptr(out),
+             ptr(saved), ptr(work), ptr(x_planes), ptr(out_planes), B, N, H, n_convs)
         ctx.save_for_backward(x, adj, saved, *params)
+        ctx.x_planes = x_planes
         ctx.keeps = keeps
         ctx.philox = philox
         ctx.cfg = (kind, n_convs, float(drop_p), n_cp)
@@ -303,19 +341,20 @@ class _GnnLayer(torch.autograd.Function):
         work = torch.empty(max(lib.xggm_gnn_work_floats(kind, B, N, H, n_convs), 1), device=x.device,
                            dtype=torch.float32)
         gx = torch.empty_like(x)
-        # ctx.needs_input_grad: (kind, n_convs, drop_p, keeps, philox, x, adj, *params); GIN needs gq h^T for d eps
-        need_gadj = ctx.needs_input_grad[6] or kind != 0
+        # ctx.needs_input_grad: (kind, n_convs, drop_p, keeps, philox, x_planes, out_planes, x, adj, *params);
+        # GIN needs gq h^T for d eps
+        need_gadj = ctx.needs_input_grad[8] or kind != 0
         gadj = torch.empty_like(adj) if need_gadj else None
         targets = [_grad_target(p) for p in params]
         fused = all(t is not None for t in targets)
         grads = targets if fused else [torch.empty_like(p) for p in params]
         kt = None if ctx.keeps is None else ptr_table(ctx.keeps)
-        call("xggm_gnn_bwd", kind, ptr(g), ptr(x), ptr(adj), ptr_table(cp), ptr_table(hp), kt,
+        call("xggm_gnn_bwd_ex", kind, ptr(g), ptr(x), ptr(adj), ptr_table(cp), ptr_table(hp), kt,
              _philox_arg(ctx.philox), drop_p, ptr(saved), ptr(work), ptr(gx), ptr(gadj), ptr_table(grads[:n_cp]),
-             ptr_table(grads[n_cp:]), int(fused), B, N, H, n_convs)
+             ptr_table(grads[n_cp:]), int(fused), ptr(ctx.x_planes), B, N, H, n_convs)
         if fused:
             grads = [None] * len(params)
-        return (None, None, None, None, None, gx, (gadj if ctx.needs_input_grad[6] else None), *grads)
+        return (None, None, None, None, None, None, None, gx, (gadj if ctx.needs_input_grad[8] else None), *grads)
 
 
 def _philox_arg(philox):
@@ -341,7 +380,10 @@ def gnn_layer(kind, x, adj, conv_params, head_params, training=False, drop_p=0.5
             keeps = [keep_mask(x.shape, drop_p, x.device) for _ in range(n_convs + 1)]
         else:
             philox = (torch.initial_seed(), _next_sites(n_convs + 1), _drop.epoch)
-    return _GnnLayer.apply(k, n_convs, drop_p, keeps, philox, x, adj, *conv_params, *head_params)
+    out_planes = _new_planes(x)
+    out = _GnnLayer.apply(k, n_convs, drop_p, keeps, philox, _planes_of(x), out_planes, x, adj, *conv_params, *head_params)
+    _attach_planes(out, out_planes)
+    return out
 
 
 # ---------------------------------------------------------------------------
@@ -528,12 +570,13 @@ class _EdgeNoise(torch.autograd.Function):
 
 class _FeatNoise(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, f, randn, sigma):
+    def forward(ctx, f, randn, sigma, planes=None):
         f, randn = f32(f, "feats"), f32(randn, "randn")
         B, N, H = randn.shape
         bcast = f.dim() == 2
         noisy, target = torch.empty_like(randn), torch.empty_like(randn)
-        call("xggm_feat_noise", ptr(f), ptr(randn), float(sigma), ptr(noisy), ptr(target), B, N, H, int(bcast))
+        call("xggm_feat_noise_ex", ptr(f), ptr(randn), float(sigma), ptr(noisy), ptr(target), ptr(planes), B, N, H,
+             int(bcast))
         ctx.bcast = bcast
         ctx.mark_non_differentiable(target)
         return noisy, target
@@ -541,12 +584,12 @@ class _FeatNoise(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g, _gt):
         if not ctx.bcast:
-            return g, None, None
+            return g, None, None, None
         g = f32(g)
         B, N, H = g.shape
         out = torch.empty((B, H), device=g.device, dtype=torch.float32)
         call("xggm_sum_nodes", ptr(g), ptr(out), B, N, H)
-        return out, None, None
+        return out, None, None, None
 
 
 class _ScoreMse(torch.autograd.Function):

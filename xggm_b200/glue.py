@@ -36,7 +36,10 @@ def add_feature_noise_v2(feats, sigma=0.2, randn=None, n_nodes=None):
         shape = feats.shape
     if randn is None:
         randn = torch.randn(shape, device=feats.device, dtype=feats.dtype)
-    return XF._FeatNoise.apply(feats, randn, sigma)
+    planes = XF._new_planes(randn)
+    noisy, target = XF._FeatNoise.apply(feats, randn, sigma, planes)
+    XF._attach_planes(noisy, planes)   # operand planes for the first GNN layer that consumes `noisy`
+    return noisy, target
 
 
 add_edge_noise = add_edge_noise_v2
