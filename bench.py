@@ -12,8 +12,8 @@ the block.  The LXMERT encoder / answer head that surround the block are outside
 (SURVEY.md section 8); their place is taken by resident inputs and a fixed cotangent on x_gen.
 
 Per-GPU batch B=256 (BASELINE configs[1]), N=36, H=768, fp32.  N>1 ranks = data parallel
-(weak scaling): each rank runs its own B=256 shard and the block's gradients are summed with
-one NCCL all-reduce per step.
+(weak scaling): each rank runs its own B=256 shard and the block's gradients are averaged with
+one NCCL all-reduce per step (part of the captured step).
 
 Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port of the
 reference path on the host cores instead (rank 0 only).
@@ -34,12 +34,12 @@ sys.path.insert(0, ROOT)
 B_PER_GPU, N_NODES, HID, N_LAYERS, SIGMA, NUM_ANS, GNN = 256, 36, 768, 2, 1.0, 2274, "GCN"
 CPU_SAMPLE_B = 32
 METRIC = "xggm_graph_block_train_samples_per_sec"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (forward projection,
-# M=9216 N=K=768, CTA-pair kernel) from the committed `ncu --set full` capture
-# profiles/r01d_ncu_gemm_tc_pair_fwd.txt: 30.72 MB read + 0.91 MB written back (the fp32 output stays in
-# the 126 MB L2 at kernel end).  Algorithmic bytes of that launch: 28.3 MB A planes + 2.4 MB W planes +
-# 28.3 MB C = 59.0 MB.
-TRAFFIC_NCU = 30716928 + 909568
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel -- the grouped forward
+# projection {u = h + agg Wc^T ; z = h W0^T + b}, two [9216,768]x[768,768] members, CTA-pair kernel -- from the
+# committed `ncu --set full` capture profiles/r01o_ncu_gemm_group_fwd_and_adj_apply.txt: 89.79 MB read + 20.58 MB
+# written back (most of the fp32 output is still in the 126 MB L2 at kernel end).  Algorithmic bytes of that
+# launch: 2 x (28.3 MB A planes + 2.4 MB W planes + 28.3 MB C) + 28.3 MB residual = 146 MB.
+TRAFFIC_NCU = 89787648 + 20575744
 
 
 def algorithmic_flops_per_sample(N=N_NODES, H=HID, L=N_LAYERS):
@@ -171,7 +171,14 @@ def run_gpu(args):
     X.set_precision(args.precision)
     model = X.XGGMHeads(HID, args.gnn, N_LAYERS, N_NODES).to(dev).train()
     from xggm_b200.ddp import FlatGrads
-    grads = FlatGrads(model.parameters())  # .grad are views of one flat buffer -> one all-reduce, no staging copy
+    # .grad are views of one flat buffer (no staging copy); N > 1: one NCCL all-reduce (AVG) at the end of the
+    # step, inside the captured graph.  XGGM_DDP_OVERLAP=1 instead ships the bucket of the modules whose backward
+    # runs first (fusion_fc, last generator layer) on a side stream during the first layer's backward -- measured
+    # equal at N=2 (2.013 vs 2.015 ms/step): the persistent one-CTA-per-SM GEMMs leave NCCL no SMs to overlap on.
+    early = []
+    if os.environ.get("XGGM_DDP_OVERLAP") == "1":
+        early = list(model.fusion_fc.parameters()) + list(model.generator.gnn_layers[-1].parameters())
+    grads = FlatGrads(model.parameters(), early=early)
     flat_grad = grads.flat
 
     visn_h, xp_h, adj_h = (t.pin_memory() for t in O.make_inputs(9596 + rank, B, N_NODES, HID))
@@ -184,9 +191,11 @@ def run_gpu(args):
         flat_grad.zero_()
         x = xp.requires_grad_(True)
         feat = visn.requires_grad_(True)
-        x_gen, loss_sm, _, _ = model.node_step(x, feat, adj, SIGMA, NUM_ANS)
-        loss = (x_gen * cot_d).sum() + 1.1 * loss_sm
-        loss.backward()
+        with grads.overlap(average=True):
+            x_gen, loss_sm, _, _ = model.node_step(x, feat, adj, SIGMA, NUM_ANS)
+            loss = (x_gen * cot_d).sum() + 1.1 * loss_sm
+            loss.backward()
+        grads.all_reduce(average=True)  # NCCL gradient all-reduce (no-op at world size 1)
         return loss_sm.detach()
 
     # the public entry point for a captured step: one CUDA-graph launch per step (xggm_b200.GraphedStep)
@@ -205,7 +214,6 @@ def run_gpu(args):
             l = graphed.replay()
         else:
             l = compute(visn_d.detach(), xp_d.detach(), adj_d)
-        grads.all_reduce(average=True)  # one NCCL collective per step (no-op at world size 1)
         return l
 
     def e2e_step():
@@ -217,7 +225,6 @@ def run_gpu(args):
         else:
             l = compute(visn_h.to(dev, non_blocking=True), xp_h.to(dev, non_blocking=True),
                         adj_h.to(dev, non_blocking=True))
-        grads.all_reduce(average=True)
         loss_host.copy_(l.reshape(1), non_blocking=True)
 
     def timed(fn, k):
@@ -275,7 +282,6 @@ def run_gpu(args):
 
         def bf16_step():
             graphed_bf16.replay()
-            grads.all_reduce(average=True)
 
         for _ in range(3):
             bf16_step()
@@ -284,9 +290,17 @@ def run_gpu(args):
         alt = {"dtype": "bf16", "ms_per_step": ms_alt / args.steps, "value": B * world / (ms_alt / args.steps * 1e-3),
                "unit": "samples/s", "note": "same step, projection engine set to single-pass bf16 tensor cores"}
 
-    if rank != 0:
+    def shutdown():
+        # the captured steps contain NCCL kernels: tearing the communicator down under them can hang, and
+        # nothing is left to clean up in a benchmark process -> flush and leave
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            os._exit(0)
+
+    if rank != 0:
+        shutdown()
         return
     peaks = load_peaks()
     ms_step = ms_res / args.steps
@@ -329,8 +343,7 @@ def run_gpu(args):
                          "sample": f"B={CPU_SAMPLE_B} graphs/step, 5 timed steps after 2 warm-up, median"},
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 def main():

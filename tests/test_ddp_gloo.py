@@ -31,6 +31,33 @@ def _worker(rank, world, port, out):
         fg.all_reduce(average=True)
         mean_scale = sum(r + 1 for r in range(world)) / world
         ok = all(torch.allclose(p.grad, torch.full_like(p, (i + 1) * mean_scale)) for i, p in enumerate(fg.params))
+        # bucketed variant: the early bucket is reduced from a backward hook at the layer boundary, the rest at
+        # the end; the result must equal the single-collective average of the same per-rank gradients
+        from xggm_b200 import ddp
+        torch.manual_seed(1)
+        l1, l2 = torch.nn.Linear(8, 8), torch.nn.Linear(8, 4)
+        fg2 = FlatGrads(list(l1.parameters()) + list(l2.parameters()), early=list(l2.parameters()))
+        ok = ok and fg2.split > 0 and fg2.params[0] is l2.weight
+        xin = torch.randn(5, 8, generator=torch.Generator().manual_seed(100 + rank))
+        fired = []
+        with fg2.overlap(average=True):
+            h = torch.tanh(l1(xin))
+            ddp.notify_layer_boundary(h)
+            h.register_hook(lambda g: fired.append(fg2._early_in_flight))
+            l2(h).square().sum().backward()
+        ok = ok and fired == [True]            # the early bucket went out before backward finished
+        local = fg2.flat.clone()
+        # (the early part of `local` is already averaged; rebuild the pure local gradient for the reference)
+        l1.zero_grad(set_to_none=False); l2.zero_grad(set_to_none=False)
+        fg2.flat.zero_()
+        l2(torch.tanh(l1(xin))).square().sum().backward()
+        ref = fg2.flat.clone()
+        dist.all_reduce(ref)
+        ref /= world
+        fg2.flat.copy_(local)
+        fg2._early_in_flight = True
+        fg2.all_reduce(average=True)
+        ok = ok and torch.allclose(fg2.flat, ref, rtol=1e-6, atol=1e-7)
         lo, hi = shard_range(37, rank, world)
         sched = BranchSchedule(delta=5, seed=9595)
         picks = [sched.next() for _ in range(32)]

@@ -23,34 +23,117 @@ def shard_range(n_items, rank, world):
 
 
 class FlatGrads:
-    """Point every ``p.grad`` at a slice of one flat buffer (same dtype/device as the parameters)."""
+    """Point every ``p.grad`` at a slice of one flat buffer (same dtype/device as the parameters).
 
-    def __init__(self, params):
-        self.params = [p for p in params if p.requires_grad]
+    ``early``: parameters whose gradients are complete first in the backward pass (the modules applied LAST
+    in the forward pass: fusion_fc and the last generator layer).  They are laid out at the front of the
+    buffer, so ``reduce_early()`` -- fired by ``overlap()`` when backward crosses the boundary between the
+    last two generator layers -- can put that bucket on the wire on a side stream while the rest of the
+    backward pass is still computing; ``all_reduce()`` then only has the remaining bucket left.
+    """
+
+    def __init__(self, params, early=()):
+        params = [p for p in params if p.requires_grad]
+        early_ids = {id(p) for p in early}
+        self.params = [p for p in params if id(p) in early_ids] + [p for p in params if id(p) not in early_ids]
         if not self.params:
             raise ValueError("no trainable parameters")
         p0 = self.params[0]
         # every slice starts on a 128-byte boundary: the kernels' vector (float4) paths need 16-byte alignment
         align = 128 // p0.element_size()
         offs, off = [], 0
+        self.split = 0
         for p in self.params:
             offs.append(off)
             off += (p.numel() + align - 1) // align * align
+            if id(p) in early_ids:
+                self.split = off
         self.flat = torch.zeros(off, device=p0.device, dtype=p0.dtype)
         for p, o in zip(self.params, offs):
             p.grad = self.flat[o:o + p.numel()].view_as(p)
+        self._side = None
+        self._early_in_flight = False
+        self._average = True
 
     def zero_(self):
         self.flat.zero_()
 
-    def all_reduce(self, average=True):
-        """Sum (or average) the gradients over all ranks with one collective."""
-        if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
-            return self.flat
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+    @staticmethod
+    def _distributed():
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    def _reduce(self, buf, average):
+        if average and dist.get_backend() == "nccl":
+            dist.all_reduce(buf, op=dist.ReduceOp.AVG)     # averaged inside the collective: no extra pass
+            return
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
         if average:
-            self.flat.div_(dist.get_world_size())
+            buf.div_(dist.get_world_size())
+
+    def reduce_early(self):
+        """All-reduce the early bucket now, on a side stream that waits for the work enqueued so far."""
+        if not self._distributed() or self.split == 0 or self._early_in_flight:
+            return
+        if self.flat.is_cuda:
+            cur = torch.cuda.current_stream(self.flat.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.flat.device)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                self._reduce(self.flat[:self.split], self._average)
+        else:
+            self._reduce(self.flat[:self.split], self._average)
+        self._early_in_flight = True
+
+    def all_reduce(self, average=True):
+        """Sum (or average) the gradients over all ranks: one collective, or -- when ``reduce_early()`` already
+        shipped the first bucket during the backward pass -- the remaining bucket plus a join."""
+        if not self._distributed():
+            return self.flat
+        if self._early_in_flight:
+            if average != self._average:
+                raise RuntimeError("xggm_b200.FlatGrads: overlap(average=...) and all_reduce(average=...) disagree")
+            self._reduce(self.flat[self.split:], average)
+            if self.flat.is_cuda:
+                torch.cuda.current_stream(self.flat.device).wait_stream(self._side)
+            self._early_in_flight = False
+            return self.flat
+        self._reduce(self.flat, average)
         return self.flat
+
+    def overlap(self, average=True):
+        """Context manager for one forward+backward: generators report the boundary between their last two
+        layers (``notify_layer_boundary``); when backward reaches it the early bucket is reduced."""
+        return _Overlap(self, average)
+
+
+_active = None   # the FlatGrads whose overlap() context is open (one per process: one process per GPU)
+
+
+class _Overlap:
+    def __init__(self, grads, average):
+        self.grads, self.average = grads, average
+
+    def __enter__(self):
+        global _active
+        self.grads._average = self.average
+        _active = self.grads
+        return self.grads
+
+    def __exit__(self, *exc):
+        global _active
+        _active = None
+
+
+def notify_layer_boundary(x):
+    """Called by the generators on the tensor that enters their LAST layer.  Its gradient exists exactly when
+    the backward pass of everything after it (last layer, read-out, losses) has finished."""
+    g = _active
+    if g is not None and g.split > 0 and g._distributed() and isinstance(x, torch.Tensor) and x.requires_grad:
+        def _fire(_grad, g=g):
+            g.reduce_early()
+        x.register_hook(_fire)
+    return x
 
 
 class BranchSchedule:

@@ -13,6 +13,7 @@ import math
 import torch
 import torch.nn as nn
 
+from . import ddp
 from . import functional as XF
 
 
@@ -188,6 +189,8 @@ class _Generator(nn.Module):
 
     def forward(self, x, adj):
         for layer in range(self.n_layers):
+            if layer > 0 and layer == self.n_layers - 1:
+                ddp.notify_layer_boundary(x)   # data-parallel runs: gradients of the last layer can ship early
             x = self.gnn_layers[layer](x, adj)
             adj = XF.adj_regen(x, self.squash)
         return x, adj
