@@ -8,7 +8,8 @@ shipped VQA-CP v2 recipe always takes (--delta 0, script/vqacpv2.sh:22 of the re
 strip_diag(adj_true) -> node_fc(x) (+36-fold broadcast) -> Gaussian feature noise ->
 GCNGenerator(L=2) -> symmetric-KL + score-matching losses -> fusion_fc read-out, forward AND
 backward down to every parameter gradient and the gradients of the LXMERT outputs that feed
-the block.  The LXMERT encoder / answer head that surround the block are outside the hot path
+the block, then the gradient all-reduce (N > 1), clip_grad_norm_(5.) and the BertAdam update of the
+block's parameters.  The LXMERT encoder / answer head that surround the block are outside the hot path
 (SURVEY.md section 8); their place is taken by resident inputs and a fixed cotangent on x_gen.
 
 Per-GPU batch B=256 (BASELINE configs[1]), N=36, H=768, fp32.  N>1 ranks = data parallel
@@ -102,6 +103,7 @@ def cpu_reference_steps(steps, warmup, threads, B=CPU_SAMPLE_B):
     p = O.make_params(9595, GNN, HID, N_LAYERS, N_NODES, heads=True)
     for v in p.values():
         v.requires_grad_(True)
+    mom = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in p.items()}
     visn, xp, adj_true = O.make_inputs(9596, B, N_NODES, HID)
     g = torch.Generator().manual_seed(1)
     c = torch.randn(B, HID, generator=g)
@@ -114,6 +116,14 @@ def cpu_reference_steps(steps, warmup, threads, B=CPU_SAMPLE_B):
         randn = torch.randn(B, N_NODES, HID)
         x_gen, loss_sm, _, _ = O.node_branch(x, feat, adj_true, p, SIGMA, randn, keeps, NUM_ANS, GNN, N_LAYERS)
         ((x_gen * c).sum() + 1.1 * loss_sm).backward()
+        # clip_grad_norm_(., 5.) + BertAdam.step, per tensor as the reference does (src/lxrt/optimization.py:139-193)
+        live = [k for k, v in p.items() if v.grad is not None]
+        _, coef = O.clip_coef([p[k].grad for k in live], 5.0)
+        with torch.no_grad():
+            for k in live:
+                new_p, m, v2 = O.bertadam_step(p[k], p[k].grad * coef, mom[k][0], mom[k][1], 4e-6)
+                p[k].copy_(new_p)
+                mom[k] = (m, v2)
         for v in p.values():
             v.grad = None
         if it >= warmup:
@@ -142,7 +152,7 @@ def run_reference(args):
 def workload_config(n_gpus, B=B_PER_GPU, gnn=GNN, precision="fp32"):
     arith = {"fp32": "fp32 (tensor cores, 3 split-bf16 passes)", "bf16": "bf16 tensor cores, fp32 storage",
              "fp32_simt": "fp32 FMA"}[precision]
-    return {"workload": f"cfg2 graph block: VQA-CP v2 GGM node branch (delta=0), {gnn}Generator L={N_LAYERS}, fwd+bwd, "
+    return {"workload": f"cfg2 graph block: VQA-CP v2 GGM node branch (delta=0), {gnn}Generator L={N_LAYERS}, fwd+bwd + clip_grad_norm_(5) + BertAdam, "
                         f"B={B}/GPU, N={N_NODES}, H={HID}, sigma={SIGMA}, A={NUM_ANS}, {arith}",
             "global_batch": B * n_gpus, "per_gpu_batch": B, "parallelism": f"dp{n_gpus}",
             "l2": "flushed between timed steps (256 MiB write, outside the per-step CUDA-event pairs)",
@@ -180,6 +190,10 @@ def run_gpu(args):
         early = list(model.fusion_fc.parameters()) + list(model.generator.gnn_layers[-1].parameters())
     grads = FlatGrads(model.parameters(), early=early)
     flat_grad = grads.flat
+    # BertAdam over the block's parameters as the trainer configures it for the down-task group (4 * --lr with
+    # --lr 1e-6, script/vqacpv2.sh:24, src/vqa/vqacpv2.py:125-128; constant schedule so the captured step stays
+    # valid), preceded by clip_grad_norm_(., 5.) (src/vqa/vqacpv2.py:252)
+    optim = X.BertAdam(model.parameters(), lr=4e-6, flat_grads=grads)
 
     visn_h, xp_h, adj_h = (t.pin_memory() for t in O.make_inputs(9596 + rank, B, N_NODES, HID))
     cot_h = torch.randn(B, HID, generator=torch.Generator().manual_seed(2 + rank)).pin_memory()
@@ -196,6 +210,7 @@ def run_gpu(args):
             loss = (x_gen * cot_d).sum() + 1.1 * loss_sm
             loss.backward()
         grads.all_reduce(average=True)  # NCCL gradient all-reduce (no-op at world size 1)
+        optim.step(X.clip_grad_norm_(grads, 5.0))   # one norm reduction + one fused update kernel
         return loss_sm.detach()
 
     # the public entry point for a captured step: one CUDA-graph launch per step (xggm_b200.GraphedStep)

@@ -288,6 +288,28 @@ int xggm_node_tail_bwd(const float* nodes, const float* feat, const float* targe
                        const float* gloss, const float* gcat, double sigma, double kl_w, double sm_w,
                        float* gnodes, float* gfeat, float* gxp, float* grow, int B, int N, int H,
                        xggm_stream_t s);
+/* ------------------------------------------------------------------------- *
+ * Training-step tail: answer loss, gradient clipping, BertAdam -- fused passes over
+ * flat fp32 buffers (all parameters / gradients / moments of a parameter group contiguous, same offsets).
+ * ------------------------------------------------------------------------- */
+/* nn.BCEWithLogitsLoss()(logit, target) * scale           src/vqa/vqacpv2.py:110,173 (scale = target.size(1))
+ * loss[0] = scale / n * sum( max(x,0) - x t + log(1 + exp(-|x|)) );  gx = gloss[0] * scale / n * (sigmoid(x) - t) */
+int xggm_bce_logits_fwd(const float* logit, const float* target, double scale, float* loss, long long n,
+                        xggm_stream_t s);
+int xggm_bce_logits_bwd(const float* logit, const float* target, const float* gloss, double scale,
+                        float* glogit, long long n, xggm_stream_t s);
+/* sumsq[0] (+)= sum g^2 : the squared total norm of nn.utils.clip_grad_norm_ (src/vqa/vqacpv2.py:175,223,252).
+ * Call once per flat gradient buffer with accumulate = 1 after the first to clip several buffers (e.g. the
+ * block's and the encoder's) by their joint norm. */
+int xggm_grad_sumsq(const float* g, long long n, float* sumsq, int accumulate, xggm_stream_t s);
+/* BertAdam.step                                           src/lxrt/optimization.py:116-203
+ *   g' = g * min(1, max_norm / (sqrt(sumsq[0]) + 1e-6))      (sumsq NULL or max_norm <= 0: no clipping)
+ *   m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2;  p -= lr * (m / (sqrt(v) + eps) + weight_decay * p)
+ * `lr` is the SCHEDULED learning rate of this step (warmup_linear etc. are host arithmetic on the step
+ * counter, optimization.py:28-55); there is no bias correction, as in the reference.  g is not modified. */
+int xggm_bertadam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double b1,
+                       double b2, double eps, double weight_decay, const float* sumsq, double max_norm,
+                       xggm_stream_t s);
 /* elementwise sigmoid (encoder_adj tail, src/vqa/vqacpv2_model.py:91-94) */
 int xggm_sigmoid_fwd(const float* x, float* y, long long n, xggm_stream_t s);
 int xggm_sigmoid_bwd(const float* gy, const float* y, float* gx, long long n, xggm_stream_t s);

@@ -263,6 +263,47 @@ def visual_feat_case(seed=301, B=3, hidden=768, training=True):
     return res
 
 
+def _npc(t):
+    return t.detach().cpu().numpy().copy()   # a snapshot: the optimiser keeps updating these tensors in place
+
+
+def optimizer_case(seed=401, steps=4):
+    """The reference BertAdam (src/lxrt/optimization.py, imported as is) driven the way the trainers drive it:
+    clip_grad_norm_(params, 5.) then optim.step() (src/vqa/vqacpv2.py:175-177), warmup_linear schedule, plus
+    nn.BCEWithLogitsLoss()(logit, target) * target.size(1) and its gradient (src/vqa/vqacpv2.py:110,173)."""
+    sys.path.insert(0, REF)
+    from lxrt.optimization import BertAdam
+    g = torch.Generator().manual_seed(seed)
+    shapes = [(48, 40), (40,), (7, 33), (1,)]
+    params = [torch.nn.Parameter(torch.randn(s, generator=g) * 0.3) for s in shapes]
+    res = {"seed": np.array([seed, steps]), "lr": np.array([4e-3]), "t_total": np.array([10]),
+           "warmup": np.array([0.25]), "weight_decay": np.array([0.01]), "max_norm": np.array([5.0])}
+    for i, p in enumerate(params):
+        res[f"p0/{i}"] = _npc(p)
+    opt = BertAdam(params, lr=4e-3, warmup=0.25, t_total=10)
+    for s in range(steps):
+        scale = [0.05, 3.0, 0.5, 40.0][s % 4]          # steps with and without active clipping
+        for i, p in enumerate(params):
+            p.grad = torch.randn(p.shape, generator=g) * scale
+            res[f"g{s}/{i}"] = _npc(p.grad)
+        norm = torch.nn.utils.clip_grad_norm_(params, 5.0)
+        res[f"norm{s}"] = np.array([float(norm)])
+        res[f"lr{s}"] = np.array(opt.get_lr()[:1] if s else [0.0])   # get_lr() is [0] before the first step
+        opt.step()
+        for i, p in enumerate(params):
+            res[f"p{s + 1}/{i}"] = _npc(p)
+            res[f"m{s + 1}/{i}"] = _npc(opt.state[p]["next_m"])
+            res[f"v{s + 1}/{i}"] = _npc(opt.state[p]["next_v"])
+    logit = (torch.randn(5, 2274, generator=g) * 3).requires_grad_(True)
+    target = (torch.rand(5, 2274, generator=g) < 0.002).float() * torch.tensor([0.3, 0.6, 0.9, 1.0])[
+        torch.randint(0, 4, (5, 2274), generator=g)]
+    loss = torch.nn.BCEWithLogitsLoss()(logit, target) * target.size(1)
+    loss.backward()
+    res.update({"bce/logit": _npc(logit), "bce/target": _npc(target), "bce/loss": np.array([float(loss)]),
+                "bce/glogit": _npc(logit.grad)})
+    return res
+
+
 def main():
     torch.set_num_threads(1)  # fixed summation order for the fixtures
     ggm, gu, loss_func, compute_kl_loss = _import_reference()
@@ -283,6 +324,7 @@ def main():
         "glue": lambda: glue_case(gu, loss_func, compute_kl_loss),
         "visual_feat_train": lambda: visual_feat_case(301, 3, 768, True),
         "visual_feat_eval": lambda: visual_feat_case(302, 2, 768, False),
+        "optimizer": lambda: optimizer_case(),
     }
     only = [a for a in sys.argv[1:] if not a.startswith("-")]   # regenerate just the named cases
     for name, fn in cases.items():

@@ -414,3 +414,56 @@ def make_keeps(seed, n_layers, n_heads, shape, p=0.5):
     g = torch.Generator().manual_seed(seed)
     return [[(torch.rand(shape, generator=g) >= p).to(torch.uint8) for _ in range(n_heads)]
             for _ in range(n_layers)]
+
+
+# ---------------------------------------------------------------------------
+# training-step tail
+# ---------------------------------------------------------------------------
+def warmup_constant(x, warmup=0.002):
+    """src/lxrt/optimization.py:34-40."""
+    return x / warmup if x < warmup else 1.0
+
+
+def warmup_linear(x, warmup=0.002):
+    """src/lxrt/optimization.py:43-49."""
+    return x / warmup if x < warmup else max((x - 1.0) / (warmup - 1.0), 0)
+
+
+def warmup_cosine(x, warmup=0.002):
+    """src/lxrt/optimization.py:28-31 (the reference calls torch.cos on a Python float there; math.cos is the
+    intended arithmetic)."""
+    return x / warmup if x < warmup else 0.5 * (1.0 + math.cos(math.pi * x))
+
+
+SCHEDULES = {"warmup_cosine": warmup_cosine, "warmup_constant": warmup_constant, "warmup_linear": warmup_linear}
+
+
+def scheduled_lr(lr, step, t_total, warmup, schedule="warmup_linear"):
+    """BertAdam's per-step learning rate, src/lxrt/optimization.py:176-191 (`step` = steps already taken)."""
+    if t_total == -1:
+        return lr
+    return lr * SCHEDULES[schedule](step / t_total, warmup)
+
+
+def clip_coef(grads, max_norm):
+    """torch.nn.utils.clip_grad_norm_(params, max_norm) as the trainers call it (src/vqa/vqacpv2.py:175):
+    total 2-norm over ALL gradients, coefficient max_norm / (norm + 1e-6) clamped to 1.  Returns (norm, coef)."""
+    total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads))
+    return float(total), min(1.0, max_norm / (float(total) + 1e-6))
+
+
+def bertadam_step(p, g, m, v, lr, b1=0.9, b2=0.999, e=1e-6, weight_decay=0.01):
+    """One BertAdam update of one tensor, src/lxrt/optimization.py:156-193 (no bias correction; `lr` already
+    scheduled; `g` already clipped).  Returns (p, m, v) without modifying the inputs."""
+    m = m * b1 + (1 - b1) * g
+    v = v * b2 + (1 - b2) * g * g
+    update = m / (v.sqrt() + e)
+    if weight_decay > 0.0:
+        update = update + weight_decay * p
+    return p - lr * update, m, v
+
+
+def bce_with_logits(x, t, scale=1.0):
+    """nn.BCEWithLogitsLoss()(x, t) * scale (src/vqa/vqacpv2.py:110,173): mean over all elements of
+    max(x,0) - x t + log(1 + exp(-|x|))."""
+    return scale * (x.clamp(min=0) - x * t + torch.log1p(torch.exp(-x.abs()))).mean()

@@ -113,3 +113,39 @@ def test_mask_injection_bookkeeping():
         with inject_keep_masks([torch.ones(2, 2, dtype=torch.uint8)]):
             pass
     assert _mask_feed == []
+
+
+def test_bertadam_host_logic_flat_layout_and_schedule():
+    """xggm_b200.optim.BertAdam on CPU tensors: parameters and gradients share one offset table, argument
+    validation mirrors the reference constructor, the schedule is the reference's (no kernels run here)."""
+    import pytest
+    import torch
+    from oracle import xggm_oracle as O
+    from xggm_b200.ddp import FlatGrads
+    from xggm_b200.optim import BertAdam, SCHEDULES
+    ps = [torch.nn.Parameter(torch.randn(5, 7)), torch.nn.Parameter(torch.randn(3)), torch.nn.Parameter(torch.randn(2, 2))]
+    before = [p.detach().clone() for p in ps]
+    fg = FlatGrads(ps)
+    opt = BertAdam(ps, lr=1e-3, warmup=0.1, t_total=50, flat_grads=fg)
+    grp = opt.groups[0]
+    assert grp.grads is fg and grp.flat_p.shape == fg.flat.shape
+    for p, b in zip(ps, before):
+        assert torch.equal(p.detach(), b)                                   # values survive the move
+        off_p = (p.data_ptr() - grp.flat_p.data_ptr()) // 4
+        off_g = (p.grad.data_ptr() - fg.flat.data_ptr()) // 4
+        assert off_p == off_g and off_p % 32 == 0                           # same 128-byte aligned offsets
+    assert opt.get_lr() == [0]
+    for step in (0, 3, 5, 20, 49, 60):
+        grp.step = step
+        assert grp.lr_scheduled() == O.scheduled_lr(1e-3, step, 50, 0.1)
+    for name, fn in SCHEDULES.items():
+        for x in (0.0, 0.001, 0.3, 1.0, 1.2):
+            assert fn(x, 0.25) == O.SCHEDULES[name](x, 0.25)
+    with pytest.raises(ValueError):
+        BertAdam(ps, lr=-1.0)
+    with pytest.raises(ValueError):
+        BertAdam(ps, lr=1e-3, schedule="nope")
+    with pytest.raises(ValueError):
+        BertAdam(ps, lr=1e-3, b1=1.0)
+    with pytest.raises(ValueError):
+        BertAdam([torch.nn.Parameter(torch.zeros(2))], lr=1e-3, flat_grads=fg)   # bucket of other parameters

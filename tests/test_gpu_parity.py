@@ -687,3 +687,63 @@ def test_visual_feat_encoder_matches_reference_fixture(name, engine):
     for k in ("box_fc.weight", "box_fc.bias", "visn_layer_norm.weight", "box_layer_norm.bias"):
         _close(named[k].grad, gold["g/" + k], 3 * TOL, k)
     _param_grad_check(gold, list(mod.named_parameters()), 3 * TOL)
+
+
+# --------------------------------------------------------------------------- training-step tail
+def test_bertadam_clip_and_bce_match_reference_fixture():
+    """xggm_grad_sumsq + xggm_bertadam_step (clip applied on the fly) and xggm_bce_logits_* against the
+    reference BertAdam / clip_grad_norm_ / BCEWithLogitsLoss fixture (tests/golden/optimizer.npz)."""
+    import xggm_b200 as X
+    g = load_golden("optimizer")
+    steps = int(g["seed"][1])
+    n = sum(1 for k in g if k.startswith("p0/"))
+    params = [torch.nn.Parameter(_t(g[f"p0/{i}"]).to(dev())) for i in range(n)]
+    opt = X.BertAdam(params, lr=float(g["lr"][0]), warmup=float(g["warmup"][0]), t_total=int(g["t_total"][0]),
+                     weight_decay=float(g["weight_decay"][0]))
+    grp = opt.groups[0]
+    for s in range(steps):
+        for i, p in enumerate(params):
+            p.grad.copy_(_t(g[f"g{s}/{i}"]))
+        clip = X.clip_grad_norm_(opt, float(g["max_norm"][0]))
+        assert abs(clip.total_norm() - float(g[f"norm{s}"][0])) <= 1e-5 * float(g[f"norm{s}"][0])
+        opt.step(clip)
+        for i, p in enumerate(params):
+            _close(p, g[f"p{s + 1}/{i}"], 1e-6, f"p step {s}")
+            o = (p.data_ptr() - grp.flat_p.data_ptr()) // 4
+            _close(grp.m[o:o + p.numel()].view_as(p), g[f"m{s + 1}/{i}"], 1e-6, f"m step {s}")
+            _close(grp.v[o:o + p.numel()].view_as(p), g[f"v{s + 1}/{i}"], 2e-6, f"v step {s}")
+    x = _t(g["bce/logit"]).to(dev()).requires_grad_(True)
+    loss = X.bce_with_logits(x, _t(g["bce/target"]).to(dev()), scale=x.shape[1])
+    (1.0 * loss).backward()
+    assert abs(float(loss) - float(g["bce/loss"][0])) <= 1e-5 * abs(float(g["bce/loss"][0]))
+    _close(x.grad, g["bce/glogit"], 1e-5, "glogit")
+
+
+def test_bertadam_full_size_properties():
+    """At the block's real size (8.2 M parameters): zero gradients and zero weight decay leave the parameters
+    bit-identical; the update is elementwise (a permuted problem gives the permuted result); padding between
+    tensors stays zero."""
+    import xggm_b200 as X
+    torch.manual_seed(3)
+    model = X.XGGMHeads(768, "GCN", 2, 36).to(dev())
+    opt = X.BertAdam(model.parameters(), lr=1e-3, weight_decay=0.0)
+    grp = opt.groups[0]
+    before = grp.flat_p.clone()
+    opt.step(X.clip_grad_norm_(opt, 5.0))
+    assert torch.equal(grp.flat_p, before) and float(grp.m.abs().max()) == 0.0
+    grp.grads.flat.normal_()
+    mask = torch.zeros_like(grp.flat_p, dtype=torch.bool)
+    for p in grp.params:
+        o = (p.data_ptr() - grp.flat_p.data_ptr()) // 4
+        mask[o:o + p.numel()] = True
+    grp.grads.flat.mul_(mask)
+    clip = X.clip_grad_norm_(opt, 5.0)
+    ref_norm = float(grp.grads.flat.double().norm())
+    assert abs(clip.total_norm() - ref_norm) <= 1e-5 * ref_norm
+    opt.step(clip)
+    if bool((~mask).any()):
+        assert float(grp.flat_p[~mask].abs().max()) == 0.0
+    coef = min(1.0, 5.0 / (ref_norm + 1e-6))
+    gq = grp.grads.flat.double() * coef
+    want = before.double() - 1e-3 * ((0.1 * gq) / ((0.001 * gq * gq).sqrt() + 1e-6))
+    _close(grp.flat_p, want.float().cpu(), 1e-6, "one step from zero moments")

@@ -146,3 +146,34 @@ def test_visual_feat_encoder_matches_reference(name):
     assert rel_l2(b.grad, g["gboxes"]) < 20 * TOL
     for k in ("box_fc.weight", "box_fc.bias", "visn_layer_norm.weight", "box_layer_norm.bias"):
         assert rel_l2(p[k].grad, g["g/" + k]) < 20 * TOL, k
+
+
+def test_optimizer_tail_oracle_matches_reference_fixture():
+    """BertAdam + clip_grad_norm_(5.) + BCEWithLogits*A restated in oracle/ vs the reference classes executed by
+    oracle/make_golden.py (src/lxrt/optimization.py:116-203, src/vqa/vqacpv2.py:110,173-177)."""
+    g = load_golden("optimizer")
+    steps = int(g["seed"][1])
+    n = sum(1 for k in g if k.startswith("p0/"))
+    lr, t_total, warmup = float(g["lr"][0]), int(g["t_total"][0]), float(g["warmup"][0])
+    wd, max_norm = float(g["weight_decay"][0]), float(g["max_norm"][0])
+    p = [_t(g[f"p0/{i}"]) for i in range(n)]
+    m = [torch.zeros_like(t) for t in p]
+    v = [torch.zeros_like(t) for t in p]
+    clipped = 0
+    for s in range(steps):
+        grads = [_t(g[f"g{s}/{i}"]) for i in range(n)]
+        norm, coef = O.clip_coef(grads, max_norm)
+        clipped += coef < 1.0
+        assert abs(norm - float(g[f"norm{s}"][0])) <= 1e-5 * norm
+        lr_s = O.scheduled_lr(lr, s, t_total, warmup)
+        assert abs(lr_s - float(g[f"lr{s}"][0])) <= 1e-12
+        for i in range(n):
+            p[i], m[i], v[i] = O.bertadam_step(p[i], grads[i] * coef, m[i], v[i], lr_s, weight_decay=wd)
+            assert rel_l2(p[i], g[f"p{s + 1}/{i}"]) < 1e-6 and rel_l2(m[i], g[f"m{s + 1}/{i}"]) < 1e-6
+            assert rel_l2(v[i], g[f"v{s + 1}/{i}"]) < 1e-6
+    assert 0 < clipped < steps   # the fixture exercises both the clipped and the unclipped regime
+    x = _t(g["bce/logit"]).requires_grad_(True)
+    loss = O.bce_with_logits(x, _t(g["bce/target"]), scale=x.shape[1])
+    loss.backward()
+    assert abs(float(loss) - float(g["bce/loss"][0])) <= 1e-5 * abs(float(g["bce/loss"][0]))
+    assert rel_l2(x.grad, g["bce/glogit"]) < 1e-5

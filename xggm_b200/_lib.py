@@ -72,6 +72,10 @@ SIGNATURES = {
     "xggm_fuse_readout_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "xggm_node_tail_fwd": [_vp, _vp, _vp, _vp, _d, _d, _d, _vp, _vp, _i, _i, _i, _vp],
     "xggm_node_tail_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "xggm_bce_logits_fwd": [_vp, _vp, _d, _vp, _ll, _vp],
+    "xggm_bce_logits_bwd": [_vp, _vp, _vp, _d, _vp, _ll, _vp],
+    "xggm_grad_sumsq": [_vp, _ll, _vp, _i, _vp],
+    "xggm_bertadam_step": [_vp, _vp, _vp, _vp, _ll, _d, _d, _d, _d, _d, _vp, _d, _vp],
     "xggm_sigmoid_fwd": [_vp, _vp, _ll, _vp],
     "xggm_sigmoid_bwd": [_vp, _vp, _vp, _ll, _vp],
     "xggm_keep_mask": [_vp, _ll, _f, _u64, _u64, _vp, _vp],

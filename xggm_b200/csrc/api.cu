@@ -863,6 +863,28 @@ int xggm_node_tail_bwd(const float* nodes, const float* feat, const float* targe
     return node_tail_bwd(nodes, feat, target, cat, gloss, gcat, (float)sigma, (float)kl_w, (float)sm_w, gnodes, gfeat,
                          gxp, grow, B, N, H, as_stream(s));
 }
+int xggm_bce_logits_fwd(const float* logit, const float* target, double scale, float* loss, long long n,
+                        xggm_stream_t s) {
+    XGGM_REQUIRE(loss && n >= 0 && (n == 0 || (logit && target)));
+    return bce_logits_fwd(logit, target, (float)scale, loss, n, as_stream(s));
+}
+int xggm_bce_logits_bwd(const float* logit, const float* target, const float* gloss, double scale,
+                        float* glogit, long long n, xggm_stream_t s) {
+    if (n == 0) return XGGM_OK;
+    XGGM_REQUIRE(logit && target && gloss && glogit && n >= 0);
+    return bce_logits_bwd(logit, target, gloss, (float)scale, glogit, n, as_stream(s));
+}
+int xggm_grad_sumsq(const float* g, long long n, float* sumsq, int accumulate, xggm_stream_t s) {
+    XGGM_REQUIRE(sumsq && n >= 0 && (n == 0 || g));
+    return grad_sumsq(g, n, sumsq, accumulate, as_stream(s));
+}
+int xggm_bertadam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double b1,
+                       double b2, double eps, double weight_decay, const float* sumsq, double max_norm,
+                       xggm_stream_t s) {
+    if (n == 0) return XGGM_OK;
+    XGGM_REQUIRE(p && g && m && v && n >= 0 && b1 >= 0.0 && b1 < 1.0 && b2 >= 0.0 && b2 < 1.0 && eps >= 0.0);
+    return bertadam_step(p, g, m, v, n, lr, b1, b2, eps, weight_decay, sumsq, max_norm, as_stream(s));
+}
 int xggm_sigmoid_fwd(const float* x, float* y, long long n, xggm_stream_t s) {
     if (n == 0) return XGGM_OK;
     XGGM_REQUIRE(x && y && n >= 0);

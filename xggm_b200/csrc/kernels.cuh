@@ -5,6 +5,7 @@
 //   rowops.cu     LayerNorm and GeLU+LayerNorm+dropout row kernels
 //   graph_ops.cu  per-graph SIMT kernels (message passing, pair scores, adjacency regeneration, GAT attention)
 //   glue.cu       trainer glue (noise, scatter, losses, read-out, masks)
+//   optim.cu      answer-loss / gradient-norm / BertAdam passes over the flat parameter buffers
 #pragma once
 #include <cuda_bf16.h>
 
@@ -82,6 +83,11 @@ int node_tail_fwd(const float* nodes, const float* feat, const float* target, co
 int node_tail_bwd(const float* nodes, const float* feat, const float* target, const float* cat, const float* gloss,
                   const float* gcat, float sigma, float kl_w, float sm_w, float* gnodes, float* gfeat, float* gxp,
                   float* grow, int B, int N, int H, cudaStream_t st);
+int bce_logits_fwd(const float* x, const float* t, float scale, float* loss, long long n, cudaStream_t st);
+int bce_logits_bwd(const float* x, const float* t, const float* gloss, float scale, float* gx, long long n, cudaStream_t st);
+int grad_sumsq(const float* g, long long n, float* out, int accumulate, cudaStream_t st);
+int bertadam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double b1, double b2, double eps,
+                  double wd, const float* sumsq, double max_norm, cudaStream_t st);
 int sigmoid_fwd(const float*, float*, long long, cudaStream_t);
 int sigmoid_bwd(const float*, const float*, float*, long long, cudaStream_t);
 int keep_mask(uint8_t*, long long, float, uint64_t, uint64_t, const uint64_t*, cudaStream_t);

@@ -1,0 +1,195 @@
+"""Training-step tail of the reference trainers on fused kernels.
+
+    optim = BertAdam(params, lr=..., warmup=0.1, t_total=...)       # src/lxrt/optimization.py:58-98
+    loss = bce_with_logits(logit, target, scale=target.size(1))     # src/vqa/vqacpv2.py:110,173
+    loss.backward()
+    clip = clip_grad_norm_(optim, 5.)                                # src/vqa/vqacpv2.py:175
+    optim.step(clip)                                                  # src/vqa/vqacpv2.py:176
+
+The reference optimiser is a Python loop over parameters (three elementwise kernels per tensor, two more for
+the clip); here every parameter group lives in four flat fp32 buffers (parameters, gradients -- the
+``xggm_b200.ddp.FlatGrads`` bucket the backward kernels write and NCCL reduces --, first and second moments)
+and a step is one gradient-norm reduction plus one update kernel per group (``xggm_grad_sumsq``,
+``xggm_bertadam_step``).  ``clip_grad_norm_`` does not rescale the gradients in a pass of its own: it returns
+the squared norm as a device scalar and the update kernel applies min(1, max_norm / (norm + 1e-6)) on the fly,
+so the step needs no host synchronisation and can be captured in a CUDA graph.
+"""
+import math
+
+import torch
+
+from . import _lib
+from ._lib import call, f32, ptr
+from .ddp import FlatGrads
+
+
+def warmup_cosine(x, warmup=0.002):
+    return x / warmup if x < warmup else 0.5 * (1.0 + math.cos(math.pi * x))
+
+
+def warmup_constant(x, warmup=0.002):
+    return x / warmup if x < warmup else 1.0
+
+
+def warmup_linear(x, warmup=0.002):
+    return x / warmup if x < warmup else max((x - 1.0) / (warmup - 1.0), 0)
+
+
+SCHEDULES = {"warmup_cosine": warmup_cosine, "warmup_constant": warmup_constant, "warmup_linear": warmup_linear}
+
+
+class _Group:
+    def __init__(self, params, opts, flat_grads):
+        self.opts = opts
+        self.grads = flat_grads if flat_grads is not None else FlatGrads(params)
+        self.params = self.grads.params
+        g = self.grads.flat
+        # parameters move into one flat buffer with the offsets of the gradient bucket
+        self.flat_p = torch.zeros_like(g)
+        base = g.data_ptr()
+        for p in self.params:
+            o = (p.grad.data_ptr() - base) // g.element_size()
+            view = self.flat_p[o:o + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view
+        self.m = torch.zeros_like(g)
+        self.v = torch.zeros_like(g)
+        self.step = 0
+
+    def lr_scheduled(self):
+        o = self.opts
+        if o["t_total"] == -1:
+            return o["lr"]
+        return o["lr"] * SCHEDULES[o["schedule"]](self.step / o["t_total"], o["warmup"])
+
+
+class BertAdam:
+    """Constructor signature and update rule of ``lxrt.optimization.BertAdam`` (no bias correction; decoupled
+    weight decay; ``max_grad_norm`` accepted and, as in the reference, unused -- the trainers clip outside).
+
+    ``params``: an iterable of parameters or of ``{"params": [...], "lr": ...}`` groups.  ``flat_grads``: an
+    existing ``FlatGrads`` (or one per group) whose buffer already holds the parameters' gradients; otherwise
+    one is created, which re-points every ``p.grad``.  Every ``p.data`` becomes a view of the group's flat
+    parameter buffer.
+    """
+
+    def __init__(self, params, lr, warmup=-1, t_total=-1, schedule="warmup_linear", b1=0.9, b2=0.999, e=1e-6,
+                 weight_decay=0.01, max_grad_norm=1.0, flat_grads=None):
+        if lr < 0.0:
+            raise ValueError("Invalid learning rate: {} - should be >= 0.0".format(lr))
+        if schedule not in SCHEDULES:
+            raise ValueError("Invalid schedule parameter: {}".format(schedule))
+        if not 0.0 <= warmup < 1.0 and not warmup == -1:
+            raise ValueError("Invalid warmup: {} - should be in [0.0, 1.0[ or -1".format(warmup))
+        if not 0.0 <= b1 < 1.0:
+            raise ValueError("Invalid b1 parameter: {} - should be in [0.0, 1.0[".format(b1))
+        if not 0.0 <= b2 < 1.0:
+            raise ValueError("Invalid b2 parameter: {} - should be in [0.0, 1.0[".format(b2))
+        if not e >= 0.0:
+            raise ValueError("Invalid epsilon value: {} - should be >= 0.0".format(e))
+        defaults = dict(lr=lr, schedule=schedule, warmup=warmup, t_total=t_total, b1=b1, b2=b2, e=e,
+                        weight_decay=weight_decay, max_grad_norm=max_grad_norm)
+        params = list(params)
+        if not params:
+            raise ValueError("optimizer got an empty parameter list")
+        groups = params if isinstance(params[0], dict) else [{"params": params}]
+        if flat_grads is None or isinstance(flat_grads, FlatGrads):
+            flat_grads = [flat_grads] * len(groups)
+        if len(flat_grads) != len(groups):
+            raise ValueError("need one FlatGrads per parameter group")
+        self.groups = []
+        for grp, fg in zip(groups, flat_grads):
+            opts = dict(defaults)
+            opts.update({k: v for k, v in grp.items() if k != "params"})
+            plist = [p for p in grp["params"] if p.requires_grad]
+            if fg is not None and {id(p) for p in fg.params} != {id(p) for p in plist}:
+                raise ValueError("flat_grads does not cover exactly this group's parameters")
+            self.groups.append(_Group(plist, opts, fg))
+
+    @property
+    def param_groups(self):
+        return [dict(g.opts, params=g.params) for g in self.groups]
+
+    def get_lr(self):
+        """Scheduled learning rate of the NEXT step, one entry per parameter ([0] before the first step, as the
+        reference does)."""
+        if all(g.step == 0 for g in self.groups):
+            return [0]
+        return [g.lr_scheduled() for g in self.groups for _ in g.params]
+
+    def zero_grad(self):
+        for g in self.groups:
+            g.grads.zero_()
+
+    def step(self, clip=None):
+        """One update of every group.  ``clip``: the handle returned by ``clip_grad_norm_`` (squared total
+        gradient norm on the device + max_norm), applied inside the update kernel; None = no clipping."""
+        sumsq, max_norm = (None, 0.0) if clip is None else (clip.sumsq, clip.max_norm)
+        for g in self.groups:
+            o = g.opts
+            _lib.check_device(g.flat_p)
+            call("xggm_bertadam_step", ptr(g.flat_p), ptr(g.grads.flat), ptr(g.m), ptr(g.v), g.flat_p.numel(),
+                 float(g.lr_scheduled()), float(o["b1"]), float(o["b2"]), float(o["e"]), float(o["weight_decay"]),
+                 ptr(sumsq), float(max_norm))
+            g.step += 1
+
+
+class GradClip:
+    """Squared total gradient norm (device scalar, no host sync) and the clip threshold."""
+
+    def __init__(self, sumsq, max_norm):
+        self.sumsq, self.max_norm = sumsq, float(max_norm)
+
+    def total_norm(self):
+        """The value torch.nn.utils.clip_grad_norm_ returns (synchronises)."""
+        return float(self.sumsq.sqrt())
+
+
+def clip_grad_norm_(source, max_norm, sumsq=None):
+    """torch.nn.utils.clip_grad_norm_(parameters, max_norm) for gradients held in flat buckets.
+
+    ``source``: a ``BertAdam``, a ``FlatGrads`` or a list of them -- everything that is clipped TOGETHER (the
+    reference clips ``self.model.parameters()``, i.e. the block and the encoder, by their joint norm; pass
+    ``sumsq`` to keep accumulating into an existing scalar).  Returns a ``GradClip`` for ``BertAdam.step``.
+    """
+    if isinstance(source, BertAdam):
+        buckets = [g.grads for g in source.groups]
+    elif isinstance(source, FlatGrads):
+        buckets = [source]
+    else:
+        buckets = [b for s in source for b in ([g.grads for g in s.groups] if isinstance(s, BertAdam) else [s])]
+    if not buckets:
+        raise ValueError("nothing to clip")
+    accumulate = sumsq is not None
+    if sumsq is None:
+        sumsq = torch.empty(1, device=buckets[0].flat.device, dtype=torch.float32)
+    for b in buckets:
+        flat = f32(b.flat, "gradient bucket")
+        call("xggm_grad_sumsq", ptr(flat), flat.numel(), ptr(sumsq), int(accumulate))
+        accumulate = True
+    return GradClip(sumsq, max_norm)
+
+
+class _BceLogits(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logit, target, scale):
+        logit, target = f32(logit, "logit"), f32(target, "target")
+        if logit.shape != target.shape:
+            raise RuntimeError("xggm_b200.bce_with_logits: shape mismatch")
+        loss = torch.empty(1, device=logit.device, dtype=torch.float32)
+        call("xggm_bce_logits_fwd", ptr(logit), ptr(target), float(scale), ptr(loss), logit.numel())
+        ctx.save_for_backward(logit, target)
+        ctx.scale = float(scale)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        logit, target = ctx.saved_tensors
+        gl = torch.empty_like(logit)
+        call("xggm_bce_logits_bwd", ptr(logit), ptr(target), ptr(f32(g).reshape(1)), ctx.scale, ptr(gl), logit.numel())
+        return gl, None, None
+
+
+def bce_with_logits(logit, target, scale=1.0):
+    """nn.BCEWithLogitsLoss()(logit, target) * scale (the trainers use scale = target.size(1))."""
+    return _BceLogits.apply(logit, target, scale)
