@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define XGGM_ABI_VERSION 2
+#define XGGM_ABI_VERSION 3
 
 #define XGGM_OK 0
 #define XGGM_ERR_ARG (-1)         /* bad shape / NULL pointer / unsupported size */

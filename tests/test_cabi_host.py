@@ -28,7 +28,7 @@ def test_library_builds_loads_and_exports_header_symbols():
         assert hasattr(lib, s), f"{s} declared in xggm_b200.h but not exported"
     # every declared entry point has a ctypes signature (argument-count drift is a bug)
     assert set(syms) == set(_lib.SIGNATURES), set(syms) ^ set(_lib.SIGNATURES)
-    assert lib.xggm_abi_version() == 2
+    assert lib.xggm_abi_version() == 3
     assert b"argument" in lib.xggm_strerror(-1)
     # 2 convs x (3 fp32 [M,H] + 2 [M] + 2 plane regions) + 3 heads x (z + mean + rstd) + P(x); M = 72
     assert lib.xggm_gnn_saved_floats(0, 2, 36, 768, 2) == 2 * (5 * 55296 + 144) + 3 * (55296 + 144) + 55296
