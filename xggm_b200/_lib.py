@@ -120,7 +120,7 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
-    if lib.xggm_abi_version() != 2:
+    if lib.xggm_abi_version() != 3:
         raise RuntimeError("libxggm_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib
