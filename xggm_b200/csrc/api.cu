@@ -158,6 +158,18 @@ static int split_weights(int kind, const float* const* cp, const float* const* h
 
 constexpr int MAX_CONVS = 7;
 
+// XGGM_FUSED_ADJ_LN=1: GCN forward message passing inside the LayerNorm kernel (adj_ln_fwd, one CTA per graph) instead
+// of the tensor-core kernel + LayerNorm.  Measured slower at B=256 (140 vs 24 + 18 us: one graph per SM leaves too
+// little memory parallelism), so it is only the path of the exact-fp32 engine and of shapes the tensor cores skip.
+static bool fused_adj_ln() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("XGGM_FUSED_ADJ_LN");
+        on = (e && e[0] == '1') ? 1 : 0;
+    }
+    return on != 0;
+}
+
 // dropout of read-out head j: explicit masks win, then in-kernel Philox, else none
 static inline DropSpec head_drop(const uint8_t* const* keeps, const xggm_philox_t* ph, float drop_p, int j) {
     const float scale = 1.f / (1.f - drop_p);
@@ -219,6 +231,13 @@ static int wgrad_group(bool tc, const Lin* l, int n, int M, int N, int K, cudaSt
     return gemm_tc_group(true, true, q, n, N, K, M, 1, npass(), st);
 }
 
+// ga[M,K] (+)= g0 w0 + g1 w1 as ONE product whose contraction runs over both gradients (same output, one epilogue)
+static int dgrad_kcat(bool tc, const Lin* l, int M, int N, int K, cudaStream_t st) {
+    if (!tc) return dgrad_group(false, l, 2, M, N, K, st);
+    GemmProb q[2] = {as_prob(l[0]), as_prob(l[1])};
+    return gemm_tc_group(false, false, q, 2, M, K, N, 0, npass(), st, true);
+}
+
 static int gnn_fwd(int kind, const float* x, const float* adj, const float* const* cp,
                    const float* const* hp, const uint8_t* const* keeps, const xggm_philox_t* philox, float drop_p, float* out,
                    float* saved, float* work, const void* x_planes, void* out_planes, int B, int N, int H, int nc,
@@ -245,7 +264,7 @@ static int gnn_fwd(int kind, const float* x, const float* adj, const float* cons
     const bool adjtc = tc && adj_tc_supported(N, H);
     bf16* coef_hi = reinterpret_cast<bf16*>(work + L.MH + (2 * nc + 1) * L.HH);
     bf16* coef_lo = coef_hi + pad8(adjtc ? adj_tc_coef_elems(B, N) : 0);
-    if (adjtc && kind == XGGM_KIND_GCN && nc > 0)
+    if (adjtc && kind == XGGM_KIND_GCN && nc > 0 && !fused_adj_ln())
         XGGM_TRY(build_blockdiag(adj, coef_hi, npass() == 3 ? coef_lo : nullptr, B, N, 1.f, nullptr, 0.f, 0, st));
     auto head_lin = [&](int j) -> Lin {   // z_j = h_j W_j^T + b_j
         return Lin{hops[j], whead[j], hp[4 * j + 1], nullptr, saved + L.head(j, 0), nullptr, 0};
@@ -260,30 +279,56 @@ static int gnn_fwd(int kind, const float* x, const float* adj, const float* cons
     };
     for (int k = 0; k < nc; ++k) {
         float* h_next = saved + L.conv(k, 2);
-        float* pre = saved + L.conv(k, 0);   // GCN: agg = adj @ h ; GIN: pre = h + (1+eps) adj @ h
-        Operand pre_op = planes_at(pre, saved + L.conv(k, 5), MHn);
         const Operand next_op = planes_at(h_next, saved + L.conv(k, 6), MHn);
         const bool gcn = kind == XGGM_KIND_GCN;
-        const float* eps = gcn ? nullptr : cp[5 * k];
-        // tensor-core engine: the aggregate is only ever a GEMM operand -> bf16 planes, no fp32 copy
-        if (adjtc) {
-            if (!gcn) XGGM_TRY(build_blockdiag(adj, coef_hi, npass() == 3 ? coef_lo : nullptr, B, N, 1.f, eps, 1.f, 0, st));
-            XGGM_TRY(adj_apply_tc(coef_hi, coef_lo, hops[k].hi, hops[k].lo, nullptr, mut(pre_op.hi), lo_or_null(pre_op),
-                                  B, N, H, 0, npass(), st));
-        } else {
-            XGGM_TRY(adj_apply(adj, h, tc ? nullptr : pre, tc ? mut(pre_op.hi) : nullptr, tc ? lo_or_null(pre_op) : nullptr,
-                               B, N, H, 1.f, eps, gcn ? 0.f : 1.f, false, 0, st));
-        }
-        // conv projection + read-out head k in one launch
         Lin g[2];
-        if (gcn) g[0] = Lin{pre_op, wconv[k], nullptr, h, work /* u */, nullptr, 0};
-        else g[0] = Lin{pre_op, wconv[k], cp[5 * k + 2], nullptr, saved + L.conv(k, 1) /* z */, nullptr, 0};
-        g[1] = head_lin(k);
-        XGGM_TRY(fwd_group(tc, g, 2, M, H, H, st));
-        if (gcn) {
+        if (gcn && adjtc && !fused_adj_ln()) {
+            // GCNConv with W.(adj @ h) re-associated as adj @ (W.h): P = h Wc^T shares its launch AND its A operand
+            // with read-out head k and leaves the GEMM as operand planes; the message passing then runs on the tensor
+            // cores with the residual in its epilogue, u = h + adj @ P, and LayerNorm follows.
+            const Operand P_op = planes_at(saved + L.conv(k, 0), saved + L.conv(k, 5), MHn);
+            g[0] = Lin{hops[k], wconv[k], nullptr, nullptr, nullptr, &P_op, 0};
+            g[1] = head_lin(k);
+            XGGM_TRY(fwd_group(tc, g, 2, M, H, H, st));
+            XGGM_TRY(adj_apply_tc(coef_hi, coef_lo, P_op.hi, P_op.lo, work /* u */, nullptr, nullptr, B, N, H, 0, npass(), st, h));
+            XGGM_TRY(layernorm_fwd(work, cp[3 * k + 1], cp[3 * k + 2], h_next, saved + L.conv(k, 1), saved + L.conv(k, 3),
+                                   mut(next_op.hi), lo_or_null(next_op), M, H, LN_EPS, st));
+        } else if (gcn && adj_ln_supported(N, H)) {
+            // same algebra with the message passing folded into the LayerNorm kernel (one CTA per graph):
+            //     h_next = LN(h + adj @ P)
+            float* P = saved + L.conv(k, 0);
+            g[0] = Lin{hops[k], wconv[k], nullptr, nullptr, P, nullptr, 0};
+            g[1] = head_lin(k);
+            XGGM_TRY(fwd_group(tc, g, 2, M, H, H, st));
+            XGGM_TRY(adj_ln_fwd(adj, P, h, cp[3 * k + 1], cp[3 * k + 2], h_next, saved + L.conv(k, 1), saved + L.conv(k, 3),
+                                tc ? mut(next_op.hi) : nullptr, tc ? lo_or_null(next_op) : nullptr, B, N, H, LN_EPS, st));
+        } else if (gcn) {
+            // shapes the fused kernel does not take: the same re-associated algebra from separate kernels
+            float* P = saved + L.conv(k, 0);
+            g[0] = Lin{hops[k], wconv[k], nullptr, nullptr, P, nullptr, 0};
+            g[1] = head_lin(k);
+            XGGM_TRY(fwd_group(tc, g, 2, M, H, H, st));
+            XGGM_CUDA_TRY(cudaMemcpyAsync(work, h, sizeof(float) * (size_t)MHn, cudaMemcpyDeviceToDevice, st));
+            XGGM_TRY(adj_apply(adj, P, work, nullptr, nullptr, B, N, H, 1.f, nullptr, 0.f, false, 1, st));   // u = h + adj @ P
             XGGM_TRY(layernorm_fwd(work, cp[3 * k + 1], cp[3 * k + 2], h_next, saved + L.conv(k, 1), saved + L.conv(k, 3),
                                    tc ? mut(next_op.hi) : nullptr, tc ? lo_or_null(next_op) : nullptr, M, H, LN_EPS, st));
         } else {
+            float* pre = saved + L.conv(k, 0);   // GIN: pre = h + (1+eps) adj @ h
+            Operand pre_op = planes_at(pre, saved + L.conv(k, 5), MHn);
+            const float* eps = cp[5 * k];
+            // tensor-core engine: the aggregate is only ever a GEMM operand -> bf16 planes, no fp32 copy
+            if (adjtc) {
+                XGGM_TRY(build_blockdiag(adj, coef_hi, npass() == 3 ? coef_lo : nullptr, B, N, 1.f, eps, 1.f, 0, st));
+                XGGM_TRY(adj_apply_tc(coef_hi, coef_lo, hops[k].hi, hops[k].lo, nullptr, mut(pre_op.hi), lo_or_null(pre_op),
+                                      B, N, H, 0, npass(), st));
+            } else {
+                XGGM_TRY(adj_apply(adj, h, tc ? nullptr : pre, tc ? mut(pre_op.hi) : nullptr, tc ? lo_or_null(pre_op) : nullptr,
+                                   B, N, H, 1.f, eps, 1.f, false, 0, st));
+            }
+            // conv projection + read-out head k in one launch
+            g[0] = Lin{pre_op, wconv[k], cp[5 * k + 2], nullptr, saved + L.conv(k, 1) /* z */, nullptr, 0};
+            g[1] = head_lin(k);
+            XGGM_TRY(fwd_group(tc, g, 2, M, H, H, st));
             XGGM_TRY(gelu_ln_drop_fwd(saved + L.conv(k, 1), cp[5 * k + 3], cp[5 * k + 4], drop_none(), h_next,
                                       saved + L.conv(k, 3), saved + L.conv(k, 4), tc ? mut(next_op.hi) : nullptr,
                                       tc ? lo_or_null(next_op) : nullptr, M, H, LN_EPS, 0, st));
@@ -380,7 +425,6 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
     for (int k = nc - 1; k >= 0; --k) {
         const float* hk = (k == 0) ? x : saved + L.conv(k - 1, 2);
         float* gnext = (k == 0) ? gx : buf[cur ^ 1];
-        const Operand pre_op = planes_at(saved + L.conv(k, 0), saved + L.conv(k, 5), MHn);
         // conv-level gradient g0: GCN gu = LN backward (also the residual path: written into gnext);
         // GIN gz of the conv's GeLU+LN
         const float* g0_f32 = gcn ? gnext : gt;
@@ -403,53 +447,79 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
         }
         XGGM_TRY(head_gz(k, R[1]));
         const Operand g1 = planes_at(R[1], R[1], MHn);
+        if (gcn) {
+            // re-associated conv (see gnn_fwd): u = h_k + adj @ P, P = h_k Wc^T, so with gu = LN backward
+            //   gP = adj^T gu ;  gWc = gP^T h_k ;  gadj += gu P^T ;  grad h_k = gu + gP Wc + gz_k W_k
+            // gP lives in the `gq` region: bf16 planes (tensor-core engine) or fp32 (exact engine).
+            const Operand gP = planes_at(gq, gq, MHn);
+            if (adjtc)
+                XGGM_TRY(adj_apply_tc(coef_hi, coef_lo, g0.hi, g0.lo, nullptr, mut(gP.hi), lo_or_null(gP), B, N, H, 0,
+                                      npass(), st));
+            else
+                XGGM_TRY(adj_apply(adj, gnext, tc ? nullptr : gq, tc ? mut(gP.hi) : nullptr, tc ? lo_or_null(gP) : nullptr,
+                                   B, N, H, 1.f, nullptr, 0.f, true, 0, st));
+            if (gadj) {   // (a constant adjacency, e.g. the ground-truth graph of the node branch, needs none)
+                const float* Pf = saved + L.conv(k, 0);
+                if (gram) {
+                    // planes of P: saved by the forward tensor-core path, else built here from the fp32 copy
+                    const bool saved_planes = adjtc && !fused_adj_ln();
+                    const Operand Pop = saved_planes ? planes_at(Pf, saved + L.conv(k, 5), MHn) : planes_at(Pf, work + 5 * MH, MHn);
+                    if (!saved_planes) XGGM_TRY(split_one(Pop, MHn, st));
+                    XGGM_TRY(gram_tc(g0.hi, g0.lo, Pop.hi, Pop.lo, s_scratch, B, N, H, npass(), st));
+                    XGGM_TRY(scale_accum(s_scratch, gadj, BNN, 1.f, nullptr, 1, nullptr, nullptr, st));
+                } else {
+                    XGGM_TRY(bmm_nt(gnext, Pf, gadj, B, N, H, 1.f, nullptr, 1, nullptr, nullptr, st));
+                }
+            }
+            {   // both weight gradients read h_k (+ the pending last head)
+                Lin w[3];
+                int n = 0;
+                w[n++] = Lin{gP, act(k), nullptr, nullptr, cg[3 * k], nullptr, acc};
+                w[n++] = Lin{g1, act(k), nullptr, nullptr, hg[4 * k], nullptr, acc};
+                if (have_pending) { w[n++] = pending_w; have_pending = false; }
+                XGGM_TRY(wgrad_group(tc, w, n, M, H, H, st));
+            }
+            {   // gnext (= gu) += [gP | gz_k] [Wc ; W_k]: ONE product with the two contractions concatenated
+                Lin d[2];
+                d[0] = Lin{gP, wconv[k], nullptr, nullptr, gnext, nullptr, 1};
+                d[1] = Lin{g1, whead[k], nullptr, nullptr, gnext, nullptr, 1};
+                XGGM_TRY(dgrad_kcat(tc, d, M, H, H, st));
+            }
+            gh = gnext;
+            cur ^= 1;
+            continue;
+        }
+        const Operand pre_op = planes_at(saved + L.conv(k, 0), saved + L.conv(k, 5), MHn);
         // weight gradients of the conv projection and of head k (+ the pending last head) in one launch
         {
             Lin w[3];
             int n = 0;
-            w[n++] = Lin{g0, pre_op, nullptr, nullptr, gcn ? cg[3 * k] : cg[5 * k + 1], nullptr, acc};
+            w[n++] = Lin{g0, pre_op, nullptr, nullptr, cg[5 * k + 1], nullptr, acc};
             w[n++] = Lin{g1, act(k), nullptr, nullptr, hg[4 * k], nullptr, acc};
             if (have_pending) { w[n++] = pending_w; have_pending = false; }
             XGGM_TRY(wgrad_group(tc, w, n, M, H, H, st));
         }
-        // input gradients: gq = g0 Wc (with planes for the Gram / message-passing kernels) and
-        // gnext (+)= gz_k W_k.  GCN: gnext already holds gu; GIN: gnext is first written here.
+        // input gradients: gq = gz Wc (with planes for the Gram / message-passing kernels) and gnext = gz_k W_k
         {
             Lin d[2];
             d[0] = Lin{g0, wconv[k], nullptr, nullptr, gq, gram ? &gq_op : nullptr, 0};
-            d[1] = Lin{g1, whead[k], nullptr, nullptr, gnext, nullptr, gcn ? 1 : 0};
+            d[1] = Lin{g1, whead[k], nullptr, nullptr, gnext, nullptr, 0};
             XGGM_TRY(dgrad_group(tc, d, 2, M, H, H, st));
         }
-        if (gcn) {
-            if (!gadj) {
-                // adjacency is a constant input (e.g. the ground-truth graph of the node branch): no gq h^T
-            } else if (gram) {   // gadj += gq h_k^T
-                const Operand hk_op = act(k);
-                XGGM_TRY(gram_tc(gq_op.hi, gq_op.lo, hk_op.hi, hk_op.lo, s_scratch, B, N, H, npass(), st));
-                XGGM_TRY(scale_accum(s_scratch, gadj, BNN, 1.f, nullptr, 1, nullptr, nullptr, st));
-            } else {
-                XGGM_TRY(bmm_nt(gq, hk, gadj, B, N, H, 1.f, nullptr, 1, nullptr, nullptr, st));
-            }
-            if (adjtc)   // gnext += adj^T gq
-                XGGM_TRY(adj_apply_tc(coef_hi, coef_lo, gq_op.hi, gq_op.lo, gnext, nullptr, nullptr, B, N, H, 1, npass(), st));
-            else
-                XGGM_TRY(adj_apply(adj, gq, gnext, nullptr, nullptr, B, N, H, 1.f, nullptr, 0.f, true, 1, st));
+        // gadj += (1+eps) gpre h^T ; geps += <gpre h^T, adj>
+        if (gram) {
+            const Operand hk_op = act(k);
+            XGGM_TRY(gram_tc(gq_op.hi, gq_op.lo, hk_op.hi, hk_op.lo, s_scratch, B, N, H, npass(), st));
+            XGGM_TRY(scale_accum(s_scratch, gadj, BNN, 1.f, eps, 1, adj, cg[5 * k], st));
         } else {
-            // gadj += (1+eps) gpre h^T ; geps += <gpre h^T, adj>
-            if (gram) {
-                const Operand hk_op = act(k);
-                XGGM_TRY(gram_tc(gq_op.hi, gq_op.lo, hk_op.hi, hk_op.lo, s_scratch, B, N, H, npass(), st));
-                XGGM_TRY(scale_accum(s_scratch, gadj, BNN, 1.f, eps, 1, adj, cg[5 * k], st));
-            } else {
-                XGGM_TRY(bmm_nt(gq, hk, gadj, B, N, H, 1.f, eps, 1, adj, cg[5 * k], st));
-            }
-            // grad h_k += gpre + (1+eps) adj^T gpre
-            if (adjtc) {
-                XGGM_TRY(build_blockdiag(adj, coef_hi, npass() == 3 ? coef_lo : nullptr, B, N, 1.f, eps, 1.f, 1, st));
-                XGGM_TRY(adj_apply_tc(coef_hi, coef_lo, gq_op.hi, gq_op.lo, gnext, nullptr, nullptr, B, N, H, 1, npass(), st));
-            } else {
-                XGGM_TRY(adj_apply(adj, gq, gnext, nullptr, nullptr, B, N, H, 1.f, eps, 1.f, true, 1, st));
-            }
+            XGGM_TRY(bmm_nt(gq, hk, gadj, B, N, H, 1.f, eps, 1, adj, cg[5 * k], st));
+        }
+        // grad h_k += gpre + (1+eps) adj^T gpre
+        if (adjtc) {
+            XGGM_TRY(build_blockdiag(adj, coef_hi, npass() == 3 ? coef_lo : nullptr, B, N, 1.f, eps, 1.f, 1, st));
+            XGGM_TRY(adj_apply_tc(coef_hi, coef_lo, gq_op.hi, gq_op.lo, gnext, nullptr, nullptr, B, N, H, 1, npass(), st));
+        } else {
+            XGGM_TRY(adj_apply(adj, gq, gnext, nullptr, nullptr, B, N, H, 1.f, eps, 1.f, true, 1, st));
         }
         gh = gnext;
         cur ^= 1;

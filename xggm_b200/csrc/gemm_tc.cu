@@ -246,6 +246,8 @@ struct Params {
     int tiles_m, tiles_n, splits, kb_per_split;
     int group;           // number of problems in this launch (1..MAX_GROUP)
     int tiles_per_prob;  // tiles_m * tiles_n * splits
+    int kcat;            // > 0: ONE product whose contraction is the concatenation of two operand pairs (map sets 0 and
+                         // 1, kcat k-blocks each): ga = gP Wc + gz Wk as a single K = 2 x 768 GEMM
     ProbOut pr[MAX_GROUP];
     int ldc;
     int atomic;          // split-K partial sums: atomicAdd into a pre-zeroed / pre-initialised C
@@ -345,7 +347,6 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const Params p) {
             uint32_t phase = 0;
             for (int tile = worker; tile < num_tiles; tile += num_workers) {
                 const int prob = tile / p.tiles_per_prob, t = tile - prob * p.tiles_per_prob;
-                const MapSet& ms = maps.m[prob];
                 const int sp = t % p.splits;
                 const int mn = t / p.splits;
                 int m0 = (mn / p.tiles_n) * (BM * CG) + (int)rank * BM, n0 = (mn % p.tiles_n) * BN;
@@ -353,6 +354,9 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const Params p) {
                 const int b_krow0 = p.bd_stride > 0 ? (mn / p.tiles_n) * p.bd_stride : 0;   // block-diagonal mode
                 const int kb0 = sp * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
+                    const int seg = (p.kcat > 0 && kb >= p.kcat) ? 1 : 0;   // K-concatenated product: second operand pair
+                    const MapSet& ms = maps.m[prob + seg];
+                    const int kseg = kb - seg * p.kcat;
                     mbar_wait(&empty[stage], phase ^ 1);
                     if (CG == 2) {
                         // pair: both CTAs' bytes are counted on the leader's barrier
@@ -360,7 +364,7 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const Params p) {
                         if (rank == 0) mbar_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
                         uint8_t* sa = stage_base + stage * C::STAGE_BYTES;
                         uint8_t* sb = sa + C::NPLANE * C::A_TILE;
-                        const int k0 = kb * BK;
+                        const int k0 = kseg * BK;
 #pragma unroll
                         for (int pl = 0; pl < C::NPLANE; ++pl) {
                             tma_load_2d_pair(sa + pl * C::A_TILE, pl == 0 ? &ms.a_hi : &ms.a_lo, lead_full, k0, m0);
@@ -373,7 +377,7 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const Params p) {
                     mbar_expect_tx(&full[stage], C::STAGE_BYTES);
                     uint8_t* sa = stage_base + stage * C::STAGE_BYTES;
                     uint8_t* sb = sa + C::NPLANE * C::A_TILE;
-                    const int k0 = kb * BK;
+                    const int k0 = kseg * BK;
 #pragma unroll
                     for (int pl = 0; pl < C::NPLANE; ++pl) {
                         const CUtensorMap* ma = pl == 0 ? &ms.a_hi : &ms.a_lo;
@@ -845,6 +849,7 @@ bool gemm_tc_supported(int M, int N, int K) {
 static void single_problem(tc::Params& p, const float* bias, const float* resid, float* C, __nv_bfloat16* c_hi,
                            __nv_bfloat16* c_lo, int accumulate) {
     p.group = 1;
+    p.kcat = 0;
     p.tiles_per_prob = p.tiles_m * p.tiles_n * p.splits;
     for (int g = 0; g < tc::MAX_GROUP; ++g) p.pr[g] = tc::ProbOut{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
     p.pr[0] = tc::ProbOut{bias, resid, C, c_hi, c_lo, accumulate, 0};
@@ -852,14 +857,19 @@ static void single_problem(tc::Params& p, const float* bias, const float* resid,
 
 // `count` (1..3) products of the same shape in ONE launch.
 // A planes: a_mn ? [K,M] : [M,K];  B planes: b_mn ? [K,N] : [N,K].  lo planes may be null when npass == 1.
+// kcat: the two entries of `pr` are the two K-segments of ONE product, C = A0 B0^T + A1 B1^T (+ addends of pr[0]).
 int gemm_tc_group(bool a_mn, bool b_mn, const GemmProb* pr, int count, int M, int N, int K, int allow_split_k,
-                  int npass, cudaStream_t st) {
+                  int npass, cudaStream_t st, bool kcat) {
     if (M <= 0 || N <= 0 || K <= 0 || count <= 0) return XGGM_OK;
     XGGM_REQUIRE(pr && count <= tc::MAX_GROUP && (npass == 1 || npass == 3));
-    for (int g = 0; g < count; ++g)
-        XGGM_REQUIRE(pr[g].a_hi && pr[g].b_hi && pr[g].C && (npass == 1 || (pr[g].a_lo && pr[g].b_lo)));
+    XGGM_REQUIRE(!kcat || (count == 2 && !a_mn && !b_mn && !allow_split_k));
+    const int segments = count;          // operand pairs to build tensor maps for
+    if (kcat) count = 1;                 // ... but one output problem
+    for (int g = 0; g < segments; ++g)
+        XGGM_REQUIRE(pr[g].a_hi && pr[g].b_hi && (pr[g].C || pr[g].c_hi || g >= count) && (npass == 1 || (pr[g].a_lo && pr[g].b_lo)));
     const int sms = num_sms();
-    const int num_kb = ceil_div(K, tc::BK);
+    const int seg_kb = ceil_div(K, tc::BK);
+    const int num_kb = kcat ? 2 * seg_kb : seg_kb;
     // Few output tiles (a head on [B,768] rows: M = 256 -> 4 pair tiles) cannot fill the machine: those products
     // take the single-CTA kernel with narrow 128 x 64 tiles (3x the CTAs, whole K per tile -> still deterministic).
     const long long pair_tiles = (long long)ceil_div(M, 2 * tc::BM) * ceil_div(N, 192) * count;
@@ -901,6 +911,7 @@ int gemm_tc_group(bool a_mn, bool b_mn, const GemmProb* pr, int count, int M, in
     p.M = M; p.N = N; p.num_kb = num_kb;
     p.tiles_m = tiles_m; p.tiles_n = tiles_n; p.splits = splits; p.kb_per_split = kb_per_split;
     p.group = count; p.tiles_per_prob = tiles_m * tiles_n * splits;
+    p.kcat = kcat ? seg_kb : 0;
     p.ldc = N;
     p.atomic = splits > 1 ? 1 : 0;
     p.vec4 = (N % 4 == 0);
@@ -908,7 +919,7 @@ int gemm_tc_group(bool a_mn, bool b_mn, const GemmProb* pr, int count, int M, in
     p.bd_stride = 0;
     p.dbg = g_tc_dbg;
     for (int g = 0; g < tc::MAX_GROUP; ++g) {
-        const GemmProb& q = pr[g < count ? g : 0];
+        const GemmProb& q = pr[g < segments ? g : 0];
         XGGM_TRY(make_map(&maps.m[g].a_hi, q.a_hi, a_rows, a_cols, a_box));
         XGGM_TRY(make_map(&maps.m[g].b_hi, q.b_hi, b_rows, b_cols, b_box));
         if (npass == 3) {
@@ -929,11 +940,12 @@ int gemm_tc_group(bool a_mn, bool b_mn, const GemmProb* pr, int count, int M, in
         if (q.c_hi && (!p.vec4 || p.atomic || (reinterpret_cast<uintptr_t>(q.c_hi) & 7) ||
                        (reinterpret_cast<uintptr_t>(q.c_lo) & 7)))
             return XGGM_ERR_ARG;  // plane emission needs the float4 epilogue
-        if (splits > 1 && !q.accumulate)
+        if (splits > 1 && !q.accumulate && q.C)
             XGGM_CUDA_TRY(cudaMemsetAsync(q.C, 0, sizeof(float) * (size_t)M * N, st));
+        if (splits > 1 && !q.C) return XGGM_ERR_ARG;   // planes-only output needs whole-K tiles
     }
     const int total = p.tiles_per_prob * count;
-    void* prof = gemm_prof_begin(2.0 * M * N * K * count, st, count);
+    void* prof = gemm_prof_begin(2.0 * M * N * K * segments, st, segments);
     int rc;
     if (pair) {
         const int grid = 2 * min(sms / 2, total);
@@ -960,7 +972,7 @@ int gemm_tc(bool a_mn, bool b_mn, const __nv_bfloat16* a_hi, const __nv_bfloat16
             const __nv_bfloat16* b_lo, const float* bias, const float* resid, float* C, __nv_bfloat16* c_hi,
             __nv_bfloat16* c_lo, int M, int N, int K, int accumulate, int allow_split_k, int npass, cudaStream_t st) {
     const GemmProb q{a_hi, a_lo, b_hi, b_lo, bias, resid, C, c_hi, c_lo, accumulate};
-    return gemm_tc_group(a_mn, b_mn, &q, 1, M, N, K, allow_split_k, npass, st);
+    return gemm_tc_group(a_mn, b_mn, &q, 1, M, N, K, allow_split_k, npass, st, false);
 }
 
 bool gram_tc_supported(int N, int H) { return N >= 1 && N <= tc::BM && H > 0 && H % 8 == 0; }
@@ -1017,10 +1029,10 @@ int build_blockdiag(const float* adj, __nv_bfloat16* hi, __nv_bfloat16* lo, int 
 }
 
 // out[b] (=|+=) C[b] @ x[b] for every graph: coefficient planes from build_blockdiag, x as [B*N, H] bf16 planes.
-// out (fp32) and / or out planes; accumulate adds to the previous fp32 out.
+// out (fp32) and / or out planes; accumulate adds to the previous fp32 out; resid (optional, [B*N,H] fp32) is added.
 int adj_apply_tc(const __nv_bfloat16* c_hi_in, const __nv_bfloat16* c_lo_in, const __nv_bfloat16* x_hi,
                  const __nv_bfloat16* x_lo, float* out, __nv_bfloat16* o_hi, __nv_bfloat16* o_lo, int B, int N, int H,
-                 int accumulate, int npass, cudaStream_t st) {
+                 int accumulate, int npass, cudaStream_t st, const float* resid) {
     if (B <= 0) return XGGM_OK;
     XGGM_REQUIRE(c_hi_in && x_hi && (out || o_hi) && adj_tc_supported(N, H) && (npass == 1 || (c_lo_in && x_lo)));
     XGGM_REQUIRE(!accumulate || out);
@@ -1044,7 +1056,8 @@ int adj_apply_tc(const __nv_bfloat16* c_hi_in, const __nv_bfloat16* c_lo_in, con
     p.ldc = H;
     p.atomic = 0;
     p.vec4 = (H % 4 == 0) && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-    single_problem(p, nullptr, nullptr, out, o_hi, npass == 3 ? o_lo : nullptr, accumulate);
+    single_problem(p, nullptr, resid, out, o_hi, npass == 3 ? o_lo : nullptr, accumulate);
+    if (resid && (reinterpret_cast<uintptr_t>(resid) & 15)) return XGGM_ERR_ARG;
     for (int g = 1; g < tc::MAX_GROUP; ++g) maps.m[g] = maps.m[0];
     p.gram_n = p.gram_g = p.gram_b = 0;
     p.bd_stride = G * N;

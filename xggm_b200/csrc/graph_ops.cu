@@ -165,6 +165,190 @@ int adj_apply(const float* adj, const float* x, float* out, bf16* hi, bf16* lo, 
     return XGGM_OK;
 }
 
+// ---------------------------------------------------------------- adj_ln_fwd
+// GCNConv tail with the message passing folded in (src/module/gcn.py:22-29, with W.(adj @ h) re-associated
+// as adj @ (W.h), P = h W^T coming from the projection GEMM):
+//     u = resid + adj_b @ P_b ;  h = LayerNorm(u)          (also xhat, rstd and the bf16 planes of h)
+// One CTA per graph.  A thread owns CB feature columns (c = tid + cb * ALN_THREADS) of ALL rows of a chunk of
+// RC nodes: it streams P[j][c] once from global memory (each element is read by exactly one thread, so there
+// is nothing to stage) and accumulates RC x CB outputs in registers against the adjacency column adj[:, j],
+// which sits transposed in shared memory and is read as broadcast float4s.  Row statistics: warp shuffles +
+// one shared-memory hop across the 12 warps, two-pass variance as in layernorm_fwd.
+constexpr int ALN_THREADS = 384;
+constexpr int ALN_RC = 36;   // node rows per register chunk (a multiple of 4)
+constexpr int ALN_JU = 6;    // rows of P a thread keeps in flight
+template <int CB>
+__global__ void __launch_bounds__(ALN_THREADS, 1)
+adj_ln_fwd_kernel(const float* __restrict__ adj, const float* __restrict__ P, const float* __restrict__ resid,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ h,
+                  float* __restrict__ xhat, float* __restrict__ rstd_out, bf16* __restrict__ hi,
+                  bf16* __restrict__ lo, int N, int NP, int H, float eps) {
+    pdl_prologue();
+    extern __shared__ __align__(16) float aln_sm[];
+    const int NJ = (N + ALN_JU - 1) / ALN_JU * ALN_JU;
+    float* adjT = aln_sm;                           // [NJ][NP]: adjT[j*NP + i] = adj[i][j], zero for i >= N or j >= N
+    float* red = adjT + (size_t)NJ * NP;            // [ALN_RC][ALN_THREADS/32] partial row sums
+    float* stat = red + ALN_RC * (ALN_THREADS / 32);  // [ALN_RC] mean, then rstd
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* ab = adj + (size_t)b * N * N;
+    for (int e = tid; e < NJ * NP; e += ALN_THREADS) {
+        const int j = e / NP, i = e - j * NP;
+        adjT[e] = (i < N && j < N) ? ab[i * N + j] : 0.f;
+    }
+    __syncthreads();
+    const size_t row0 = (size_t)b * N;
+    int col[CB];
+    bool live[CB];
+    float g[CB], bt[CB];
+#pragma unroll
+    for (int cb = 0; cb < CB; ++cb) {
+        col[cb] = tid + cb * ALN_THREADS;
+        live[cb] = col[cb] < H;
+        g[cb] = live[cb] ? gamma[col[cb]] : 0.f;
+        bt[cb] = live[cb] ? beta[col[cb]] : 0.f;
+    }
+    const float inv_h = 1.0f / (float)H;
+    for (int r0 = 0; r0 < N; r0 += ALN_RC) {
+        const int rows = min(ALN_RC, N - r0);
+        float acc[ALN_RC][CB];
+#pragma unroll
+        for (int i = 0; i < ALN_RC; ++i)
+#pragma unroll
+            for (int cb = 0; cb < CB; ++cb) acc[i][cb] = 0.f;
+        // ALN_JU rows of P in flight per thread: the loop is bound by memory latency, not by its FMAs
+        for (int j0 = 0; j0 < N; j0 += ALN_JU) {
+            float pv[ALN_JU][CB];
+#pragma unroll
+            for (int u = 0; u < ALN_JU; ++u)
+#pragma unroll
+                for (int cb = 0; cb < CB; ++cb)
+                    pv[u][cb] = (live[cb] && j0 + u < N) ? P[(row0 + j0 + u) * H + col[cb]] : 0.f;
+#pragma unroll
+            for (int u = 0; u < ALN_JU; ++u) {
+                const float4* a4 = reinterpret_cast<const float4*>(adjT + (size_t)(j0 + u) * NP + r0);
+#pragma unroll
+                for (int q = 0; q < ALN_RC / 4; ++q) {
+                    const float4 a = a4[q];
+#pragma unroll
+                    for (int cb = 0; cb < CB; ++cb) {
+                        acc[4 * q][cb] = fmaf(a.x, pv[u][cb], acc[4 * q][cb]);
+                        acc[4 * q + 1][cb] = fmaf(a.y, pv[u][cb], acc[4 * q + 1][cb]);
+                        acc[4 * q + 2][cb] = fmaf(a.z, pv[u][cb], acc[4 * q + 2][cb]);
+                        acc[4 * q + 3][cb] = fmaf(a.w, pv[u][cb], acc[4 * q + 3][cb]);
+                    }
+                }
+            }
+        }
+        // residual, then the row mean
+#pragma unroll
+        for (int i = 0; i < ALN_RC; ++i) {
+            float s = 0.f;
+            if (i < rows) {
+#pragma unroll
+                for (int cb = 0; cb < CB; ++cb) {
+                    if (live[cb]) {
+                        acc[i][cb] += resid[(row0 + r0 + i) * H + col[cb]];
+                        s += acc[i][cb];
+                    }
+                }
+            }
+            s = warp_sum(s);
+            if (lane == 0) red[i * (ALN_THREADS / 32) + warp] = s;
+        }
+        __syncthreads();
+        if (tid < ALN_RC) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < ALN_THREADS / 32; ++w) s += red[tid * (ALN_THREADS / 32) + w];
+            stat[tid] = s * inv_h;
+        }
+        __syncthreads();
+        // centred second moment
+#pragma unroll
+        for (int i = 0; i < ALN_RC; ++i) {
+            const float mean = stat[i];
+            float q = 0.f;
+            if (i < rows) {
+#pragma unroll
+                for (int cb = 0; cb < CB; ++cb) {
+                    if (live[cb]) {
+                        acc[i][cb] -= mean;
+                        q = fmaf(acc[i][cb], acc[i][cb], q);
+                    }
+                }
+            }
+            q = warp_sum(q);
+            if (lane == 0) red[i * (ALN_THREADS / 32) + warp] = q;
+        }
+        __syncthreads();
+        if (tid < ALN_RC) {
+            float q = 0.f;
+#pragma unroll
+            for (int w = 0; w < ALN_THREADS / 32; ++w) q += red[tid * (ALN_THREADS / 32) + w];
+            const float r = 1.0f / sqrtf(q * inv_h + eps);
+            stat[tid] = r;
+            if (tid < rows && rstd_out) rstd_out[row0 + r0 + tid] = r;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < ALN_RC; ++i) {
+            if (i < rows) {
+                const float r = stat[i];
+#pragma unroll
+                for (int cb = 0; cb < CB; ++cb) {
+                    if (live[cb]) {
+                        const size_t o = (row0 + r0 + i) * H + col[cb];
+                        const float xh = acc[i][cb] * r;
+                        const float hv = fmaf(xh, g[cb], bt[cb]);
+                        h[o] = hv;
+                        if (xhat) xhat[o] = xh;
+                        if (hi) {
+                            bf16 a, c;
+                            split_bf16(hv, a, c);
+                            hi[o] = a;
+                            if (lo) lo[o] = c;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();   // stat / red are reused by the next chunk
+    }
+}
+
+// (four column blocks per thread would spill: wider rows take the unfused kernels)
+bool adj_ln_supported(int N, int H) { return N >= 1 && N <= 128 && H >= 1 && H <= 3 * ALN_THREADS; }
+
+// h = LN(resid + adj @ P) per graph; hi/lo (optional): bf16 planes of h
+int adj_ln_fwd(const float* adj, const float* P, const float* resid, const float* gamma, const float* beta, float* h,
+               float* xhat, float* rstd, bf16* hi, bf16* lo, int B, int N, int H, float eps, cudaStream_t st) {
+    if (B <= 0) return XGGM_OK;
+    XGGM_REQUIRE(adj && P && resid && gamma && beta && h && adj_ln_supported(N, H));
+    const int NP = ceil_div(N, ALN_RC) * ALN_RC;
+    const int NJ = ceil_div(N, ALN_JU) * ALN_JU;
+    const size_t smem = sizeof(float) * ((size_t)NJ * NP + ALN_RC * (ALN_THREADS / 32) + ALN_RC);
+    const int cb = ceil_div(H, ALN_THREADS);
+#define XGGM_ALN_LAUNCH(CBV)                                                                                        \
+    do {                                                                                                            \
+        static bool attr = false;                                                                                   \
+        if (!attr) {                                                                                                \
+            XGGM_CUDA_TRY(cudaFuncSetAttribute(adj_ln_fwd_kernel<CBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                               (int)(sizeof(float) * (132 * 144 + ALN_RC * (ALN_THREADS / 32) + ALN_RC)))); \
+            attr = true;                                                                                            \
+        }                                                                                                           \
+        XGGM_LAUNCH((adj_ln_fwd_kernel<CBV>), B, ALN_THREADS, smem, st, adj, P, resid, gamma, beta, h, xhat, rstd, hi, lo, \
+                    N, NP, H, eps);                                                                                 \
+    } while (0)
+    switch (cb) {
+        case 1: XGGM_ALN_LAUNCH(1); break;
+        case 2: XGGM_ALN_LAUNCH(2); break;
+        default: XGGM_ALN_LAUNCH(3); break;
+    }
+#undef XGGM_ALN_LAUNCH
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+
 // -------------------------------------------------------------------- bmm_nt
 // One CTA per graph.  Feature columns are streamed through smem in chunks of CK;
 // each thread owns up to MAXB 3x3 blocks of the N x N result.  The k-order of every

@@ -30,14 +30,14 @@ struct GemmProb {
     int accumulate;
 };
 int gemm_tc_group(bool a_mn, bool b_mn, const GemmProb* pr, int count, int M, int N, int K, int allow_split_k,
-                  int npass, cudaStream_t st);
+                  int npass, cudaStream_t st, bool kcat = false);
 bool adj_tc_supported(int N, int H);
 long long adj_tc_coef_elems(int B, int N);
 int build_blockdiag(const float* adj, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int N, float alpha0,
                     const float* alpha_dev, float self_w, int trans, cudaStream_t st);
 int adj_apply_tc(const __nv_bfloat16* c_hi, const __nv_bfloat16* c_lo, const __nv_bfloat16* x_hi,
                  const __nv_bfloat16* x_lo, float* out, __nv_bfloat16* o_hi, __nv_bfloat16* o_lo, int B, int N, int H,
-                 int accumulate, int npass, cudaStream_t st);
+                 int accumulate, int npass, cudaStream_t st, const float* resid = nullptr);
 bool gram_tc_supported(int N, int H);
 int gram_tc(const __nv_bfloat16* p_hi, const __nv_bfloat16* p_lo, const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo,
             float* S, int B, int N, int H, int npass, cudaStream_t st);
@@ -56,6 +56,9 @@ int layernorm_bwd(const float*, const float*, const float*, const float*, float*
 int gelu_ln_drop_fwd(const float*, const float*, const float*, const DropSpec&, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, float, int, cudaStream_t);
 int gelu_ln_drop_bwd(const float*, const float*, const float*, const float*, const float*, const DropSpec&, float*, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, cudaStream_t);
 int adj_apply(const float*, const float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, int, float, const float*, float, bool, int, cudaStream_t);
+bool adj_ln_supported(int N, int H);
+int adj_ln_fwd(const float* adj, const float* P, const float* resid, const float* gamma, const float* beta, float* h,
+               float* xhat, float* rstd, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int N, int H, float eps, cudaStream_t st);
 int bmm_nt(const float*, const float*, float*, int, int, int, float, const float*, int, const float*, float*, cudaStream_t);
 int adj_regen_fwd(const float*, float*, float*, int32_t*, int, int, int, int, cudaStream_t);
 int adj_regen_bwd(const float*, const float*, const float*, const int32_t*, float*, float*, int, int, int, int, int, cudaStream_t);
