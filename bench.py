@@ -95,7 +95,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------- CPU baseline
-def cpu_reference_steps(steps, warmup, threads, B=CPU_SAMPLE_B):
+def cpu_reference_steps(steps, warmup, threads, B=CPU_SAMPLE_B, branch="node"):
     """The reference's PyTorch CPU path for the same step, restated in oracle/ (the reference tree
     does not exist on the GPU box).  Returns seconds per step (median)."""
     from oracle import xggm_oracle as O
@@ -113,9 +113,14 @@ def cpu_reference_steps(steps, warmup, threads, B=CPU_SAMPLE_B):
         x = xp.clone().requires_grad_(True)
         feat = visn.clone().requires_grad_(True)
         keeps = [[(torch.rand(B, N_NODES, HID) >= 0.5) for _ in range(3)] for _ in range(N_LAYERS)]  # F.dropout's bernoulli
-        randn = torch.randn(B, N_NODES, HID)
-        x_gen, loss_sm, _, _ = O.node_branch(x, feat, adj_true, p, SIGMA, randn, keeps, NUM_ANS, GNN, N_LAYERS)
-        ((x_gen * c).sum() + 1.1 * loss_sm).backward()
+        if branch == "relation":
+            randn = torch.randn(B, N_NODES, N_NODES)
+            x_gen, loss_sm, _, _ = O.relation_branch(x, feat, adj_true, p, SIGMA, randn, keeps, NUM_ANS, GNN, N_LAYERS, 12.0)
+            ((x_gen * c).sum() + 6.0 * loss_sm).backward()
+        else:
+            randn = torch.randn(B, N_NODES, HID)
+            x_gen, loss_sm, _, _ = O.node_branch(x, feat, adj_true, p, SIGMA, randn, keeps, NUM_ANS, GNN, N_LAYERS)
+            ((x_gen * c).sum() + 1.1 * loss_sm).backward()
         # clip_grad_norm_(., 5.) + BertAdam.step, per tensor as the reference does (src/lxrt/optimization.py:139-193)
         live = [k for k, v in p.items() if v.grad is not None]
         _, coef = O.clip_coef([p[k].grad for k in live], 5.0)
@@ -137,22 +142,23 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sec = cpu_reference_steps(args.steps, args.warmup, threads)
+    sec = cpu_reference_steps(args.steps, args.warmup, threads, branch=args.branch)
     val = CPU_SAMPLE_B / sec
     sample = f"B={CPU_SAMPLE_B} graphs per step (bounded sample of the B={B_PER_GPU} workload), {args.steps} steps"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.gpus),
+            "config": workload_config(args.gpus, branch=args.branch),
             "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus, B=B_PER_GPU, gnn=GNN, precision="fp32"):
+def workload_config(n_gpus, B=B_PER_GPU, gnn=GNN, precision="fp32", branch="node"):
     arith = {"fp32": "fp32 (tensor cores, 3 split-bf16 passes)", "bf16": "bf16 tensor cores, fp32 storage",
              "fp32_simt": "fp32 FMA"}[precision]
-    return {"workload": f"cfg2 graph block: VQA-CP v2 GGM node branch (delta=0), {gnn}Generator L={N_LAYERS}, fwd+bwd + clip_grad_norm_(5) + BertAdam, "
+    which = "VQA-CP v2 GGM node branch (delta=0)" if branch == "node" else "GGM relation branch (GQA-OOD weights)"
+    return {"workload": f"cfg2 graph block: {which}, {gnn}Generator L={N_LAYERS}, fwd+bwd + clip_grad_norm_(5) + BertAdam, "
                         f"B={B}/GPU, N={N_NODES}, H={HID}, sigma={SIGMA}, A={NUM_ANS}, {arith}",
             "global_batch": B * n_gpus, "per_gpu_batch": B, "parallelism": f"dp{n_gpus}",
             "l2": "flushed between timed steps (256 MiB write, outside the per-step CUDA-event pairs)",
@@ -206,8 +212,12 @@ def run_gpu(args):
         x = xp.requires_grad_(True)
         feat = visn.requires_grad_(True)
         with grads.overlap(average=True):
-            x_gen, loss_sm, _, _ = model.node_step(x, feat, adj, SIGMA, NUM_ANS)
-            loss = (x_gen * cot_d).sum() + 1.1 * loss_sm
+            if args.branch == "relation":   # GQA-OOD weights, src/gqa/gqa_ood.py:197
+                x_gen, loss_sm, _, _ = model.relation_step(x, feat, adj, SIGMA, NUM_ANS, kl_weight=12.0)
+                loss = (x_gen * cot_d).sum() + 6.0 * loss_sm
+            else:
+                x_gen, loss_sm, _, _ = model.node_step(x, feat, adj, SIGMA, NUM_ANS)
+                loss = (x_gen * cot_d).sum() + 1.1 * loss_sm
             loss.backward()
         grads.all_reduce(average=True)  # NCCL gradient all-reduce (no-op at world size 1)
         optim.step(X.clip_grad_norm_(grads, 5.0))   # one norm reduction + one fused update kernel
@@ -329,12 +339,12 @@ def run_gpu(args):
     peak = peaks["bf16_tflops"]
     h2d = sum(t.numel() * 4 for t in (visn_h, xp_h, adj_h))
     threads = os.cpu_count() or 1
-    cpu_sec = cpu_reference_steps(5, 2, threads)
+    cpu_sec = cpu_reference_steps(5, 2, threads, branch=args.branch)
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": workload_config(world, B, args.gnn, args.precision),
+        "config": workload_config(world, B, args.gnn, args.precision, args.branch),
         "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
@@ -372,6 +382,9 @@ def main():
                     help="projection engine (default fp32 = BASELINE cfg 2; bf16 = cfg 3 arithmetic)")
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="graphs per GPU (default 256, the BASELINE config)")
     ap.add_argument("--gnn", default=GNN, choices=["GCN", "GIN"])
+    ap.add_argument("--branch", default="node", choices=["node", "relation"],
+                    help="GGM branch of the step: node generation (the --delta 0 recipe of script/vqacpv2.sh, default) or "
+                         "relation generation (taken with probability delta/10; GQA-OOD uses delta 5)")
     ap.add_argument("--nodes", type=int, default=N_NODES, help="nodes per graph (36 = obj36; 64/100 = BASELINE cfg 4 sweep)")
     args = ap.parse_args()
     if args.impl == "reference":
