@@ -169,180 +169,183 @@ int adj_apply(const float* adj, const float* x, float* out, bf16* hi, bf16* lo, 
 // GCNConv tail with the message passing folded in (src/module/gcn.py:22-29, with W.(adj @ h) re-associated
 // as adj @ (W.h), P = h W^T coming from the projection GEMM):
 //     u = resid + adj_b @ P_b ;  h = LayerNorm(u)          (also xhat, rstd and the bf16 planes of h)
-// One CTA per graph.  A thread owns CB feature columns (c = tid + cb * ALN_THREADS) of ALL rows of a chunk of
-// RC nodes: it streams P[j][c] once from global memory (each element is read by exactly one thread, so there
-// is nothing to stage) and accumulates RC x CB outputs in registers against the adjacency column adj[:, j],
-// which sits transposed in shared memory and is read as broadcast float4s.  Row statistics: warp shuffles +
-// one shared-memory hop across the 12 warps, two-pass variance as in layernorm_fwd.
+// Each graph is staged whole in shared memory: persistent CTAs (one per SM) take one graph at a time; thread 0
+// streams the graph's [N,H] P tile in with bulk async copies (six row groups, one mbarrier each) into one of
+// TWO tile buffers, so the tile of graph g+1 arrives under the math of graph g; the residual rows are pulled
+// into L2 by a bulk prefetch at the start of the graph and read with 16-byte loads after the accumulation.  Work split: a warp owns ALN_RW complete node rows, a lane
+// owns the columns 128 q + 4 lane + {0..3} (the row kernels' layout), so the accumulation
+//     acc[r][c] += adj[i_r][j] * P[j][c]      (j = 0..N-1: one real loop, 3 broadcast + NV vector LDS, 12 NV FMA)
+// needs no register indexing by row, the LayerNorm statistics are plain warp reductions, and every global
+// store is a 16-byte (fp32) or 8-byte (bf16 plane) vector.
 constexpr int ALN_THREADS = 384;
-constexpr int ALN_RC = 36;   // node rows per register chunk (a multiple of 4)
-constexpr int ALN_JU = 6;    // rows of P a thread keeps in flight
-template <int CB>
+constexpr int ALN_WARPS = ALN_THREADS / 32;
+constexpr int ALN_RW = 3;                          // node rows per warp
+constexpr int ALN_MAXN = ALN_WARPS * ALN_RW;       // 36 = obj36
+constexpr int ALN_JU = 6;                          // P rows per copy group / mbarrier
+constexpr int ALN_GROUPS = ALN_MAXN / ALN_JU;
+template <int NV>
 __global__ void __launch_bounds__(ALN_THREADS, 1)
 adj_ln_fwd_kernel(const float* __restrict__ adj, const float* __restrict__ P, const float* __restrict__ resid,
                   const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ h,
                   float* __restrict__ xhat, float* __restrict__ rstd_out, bf16* __restrict__ hi,
-                  bf16* __restrict__ lo, int N, int NP, int H, float eps) {
+                  bf16* __restrict__ lo, int B, int N, float eps) {
     pdl_prologue();
+    constexpr int H = NV * 128;
     extern __shared__ __align__(16) float aln_sm[];
-    const int NJ = (N + ALN_JU - 1) / ALN_JU * ALN_JU;
-    float* adjT = aln_sm;                           // [NJ][NP]: adjT[j*NP + i] = adj[i][j], zero for i >= N or j >= N
-    float* red = adjT + (size_t)NJ * NP;            // [ALN_RC][ALN_THREADS/32] partial row sums
-    float* stat = red + ALN_RC * (ALN_THREADS / 32);  // [ALN_RC] mean, then rstd
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float* ab = adj + (size_t)b * N * N;
-    for (int e = tid; e < NJ * NP; e += ALN_THREADS) {
-        const int j = e / NP, i = e - j * NP;
-        adjT[e] = (i < N && j < N) ? ab[i * N + j] : 0.f;
+    const int tile = N * H;                                    // floats per staged tile
+    float* Ps = aln_sm;                                        // [2][tile]: double-buffered P tiles
+    float* adjS = Ps + 2 * (size_t)tile;                       // [2][ALN_MAXN * ALN_MAXN]: adjacency, row stride N
+    uint64_t* bar = reinterpret_cast<uint64_t*>(adjS + 2 * ALN_MAXN * ALN_MAXN);   // [2][GROUPS]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int groups = (N + ALN_JU - 1) / ALN_JU;
+    // the N x N adjacency rides with the first P row group when a bulk copy can address it
+    const bool adj_bulk = ((N * N * 4) % 16 == 0) && ((reinterpret_cast<uintptr_t>(adj) & 15) == 0);
+    if (tid == 0) {
+        for (int g = 0; g < 2 * ALN_GROUPS; ++g) ptx::mbar_init(&bar[g], 1);
+        ptx::fence_barrier_init();
     }
     __syncthreads();
-    const size_t row0 = (size_t)b * N;
-    int col[CB];
-    bool live[CB];
-    float g[CB], bt[CB];
-#pragma unroll
-    for (int cb = 0; cb < CB; ++cb) {
-        col[cb] = tid + cb * ALN_THREADS;
-        live[cb] = col[cb] < H;
-        g[cb] = live[cb] ? gamma[col[cb]] : 0.f;
-        bt[cb] = live[cb] ? beta[col[cb]] : 0.f;
-    }
+    auto issue_p = [&](int buf, int b) {      // thread 0 only
+        ptx::fence_proxy_async();             // the buffer was last read through the generic proxy
+        for (int g = 0; g < groups; ++g) {
+            const int r0 = g * ALN_JU, rows = min(ALN_JU, N - r0);
+            const uint32_t bytes = (uint32_t)(rows * H * 4);
+            const uint32_t abytes = (g == 0 && adj_bulk) ? (uint32_t)(N * N * 4) : 0u;
+            ptx::mbar_expect_tx(&bar[buf * ALN_GROUPS + g], bytes + abytes);
+            if (abytes)
+                ptx::bulk_g2s(adjS + buf * ALN_MAXN * ALN_MAXN, adj + (size_t)b * N * N, abytes, &bar[buf * ALN_GROUPS]);
+            ptx::bulk_g2s(Ps + (size_t)buf * tile + (size_t)r0 * H, P + ((size_t)b * N + r0) * H, bytes,
+                          &bar[buf * ALN_GROUPS + g]);
+        }
+    };
+    if (tid == 0 && (int)blockIdx.x < B) issue_p(0, blockIdx.x);
+    const int i0 = warp * ALN_RW;                              // this warp's rows: i0 .. i0 + ALN_RW - 1
     const float inv_h = 1.0f / (float)H;
-    for (int r0 = 0; r0 < N; r0 += ALN_RC) {
-        const int rows = min(ALN_RC, N - r0);
-        float acc[ALN_RC][CB];
+    int it = 0;
+    for (int b = blockIdx.x; b < B; b += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t phase = (it >> 1) & 1;
+        const int next_b = b + gridDim.x;
+        if (tid == 0) {
+            // the other buffer was drained one graph ago: the next graph's P streams in under this graph's math;
+            // this graph's residual tile is pulled into L2 so that the reads after the accumulation hit there
+            if (next_b < B) issue_p(buf ^ 1, next_b);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(resid + (size_t)b * tile), "r"(tile * 4) : "memory");
+        }
+        float* adjB = adjS + buf * ALN_MAXN * ALN_MAXN;
+        if (!adj_bulk) {
+            const float* ab = adj + (size_t)b * N * N;
+            for (int e = tid; e < N * N; e += ALN_THREADS) adjB[e] = ab[e];
+            __syncthreads();
+        }
+        const float* Pb = Ps + (size_t)buf * tile;
+        float acc[ALN_RW][NV * 4];
 #pragma unroll
-        for (int i = 0; i < ALN_RC; ++i)
+        for (int r = 0; r < ALN_RW; ++r)
 #pragma unroll
-            for (int cb = 0; cb < CB; ++cb) acc[i][cb] = 0.f;
-        // ALN_JU rows of P in flight per thread: the loop is bound by memory latency, not by its FMAs
-        for (int j0 = 0; j0 < N; j0 += ALN_JU) {
-            float pv[ALN_JU][CB];
+            for (int c = 0; c < NV * 4; ++c) acc[r][c] = 0.f;
+        for (int g = 0; g < groups; ++g) {
+            ptx::mbar_wait(&bar[buf * ALN_GROUPS + g], phase);
+            const int j1 = min(N, (g + 1) * ALN_JU);
+#pragma unroll 2
+            for (int j = g * ALN_JU; j < j1; ++j) {
+                float a[ALN_RW];
 #pragma unroll
-            for (int u = 0; u < ALN_JU; ++u)
+                for (int r = 0; r < ALN_RW; ++r) a[r] = adjB[min(i0 + r, N - 1) * N + j];   // (rows >= N: idle warps)
+                const float* pj = Pb + (size_t)j * H + 4 * lane;
 #pragma unroll
-                for (int cb = 0; cb < CB; ++cb)
-                    pv[u][cb] = (live[cb] && j0 + u < N) ? P[(row0 + j0 + u) * H + col[cb]] : 0.f;
+                for (int q = 0; q < NV; ++q) {
+                    const float4 p = *reinterpret_cast<const float4*>(pj + 128 * q);
 #pragma unroll
-            for (int u = 0; u < ALN_JU; ++u) {
-                const float4* a4 = reinterpret_cast<const float4*>(adjT + (size_t)(j0 + u) * NP + r0);
-#pragma unroll
-                for (int q = 0; q < ALN_RC / 4; ++q) {
-                    const float4 a = a4[q];
-#pragma unroll
-                    for (int cb = 0; cb < CB; ++cb) {
-                        acc[4 * q][cb] = fmaf(a.x, pv[u][cb], acc[4 * q][cb]);
-                        acc[4 * q + 1][cb] = fmaf(a.y, pv[u][cb], acc[4 * q + 1][cb]);
-                        acc[4 * q + 2][cb] = fmaf(a.z, pv[u][cb], acc[4 * q + 2][cb]);
-                        acc[4 * q + 3][cb] = fmaf(a.w, pv[u][cb], acc[4 * q + 3][cb]);
+                    for (int r = 0; r < ALN_RW; ++r) {
+                        acc[r][4 * q] = fmaf(a[r], p.x, acc[r][4 * q]);
+                        acc[r][4 * q + 1] = fmaf(a[r], p.y, acc[r][4 * q + 1]);
+                        acc[r][4 * q + 2] = fmaf(a[r], p.z, acc[r][4 * q + 2]);
+                        acc[r][4 * q + 3] = fmaf(a[r], p.w, acc[r][4 * q + 3]);
                     }
                 }
             }
         }
-        // residual, then the row mean
 #pragma unroll
-        for (int i = 0; i < ALN_RC; ++i) {
-            float s = 0.f;
-            if (i < rows) {
+        for (int r = 0; r < ALN_RW; ++r) {
+            const int i = i0 + r;
+            if (i < N) {                                   // warp-uniform
+                const size_t ro = ((size_t)b * N + i) * H + 4 * lane;
+                float4 t[NV];
 #pragma unroll
-                for (int cb = 0; cb < CB; ++cb) {
-                    if (live[cb]) {
-                        acc[i][cb] += resid[(row0 + r0 + i) * H + col[cb]];
-                        s += acc[i][cb];
-                    }
+                for (int q = 0; q < NV; ++q) t[q] = *reinterpret_cast<const float4*>(resid + ro + 128 * q);
+                float s = 0.f;
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+                    acc[r][4 * q] += t[q].x; acc[r][4 * q + 1] += t[q].y; acc[r][4 * q + 2] += t[q].z; acc[r][4 * q + 3] += t[q].w;
+                    s += (acc[r][4 * q] + acc[r][4 * q + 1]) + (acc[r][4 * q + 2] + acc[r][4 * q + 3]);
                 }
-            }
-            s = warp_sum(s);
-            if (lane == 0) red[i * (ALN_THREADS / 32) + warp] = s;
-        }
-        __syncthreads();
-        if (tid < ALN_RC) {
-            float s = 0.f;
+                const float mean = warp_sum(s) * inv_h;
+                float qs = 0.f;
 #pragma unroll
-            for (int w = 0; w < ALN_THREADS / 32; ++w) s += red[tid * (ALN_THREADS / 32) + w];
-            stat[tid] = s * inv_h;
-        }
-        __syncthreads();
-        // centred second moment
-#pragma unroll
-        for (int i = 0; i < ALN_RC; ++i) {
-            const float mean = stat[i];
-            float q = 0.f;
-            if (i < rows) {
-#pragma unroll
-                for (int cb = 0; cb < CB; ++cb) {
-                    if (live[cb]) {
-                        acc[i][cb] -= mean;
-                        q = fmaf(acc[i][cb], acc[i][cb], q);
-                    }
+                for (int c = 0; c < NV * 4; ++c) {
+                    acc[r][c] -= mean;
+                    qs = fmaf(acc[r][c], acc[r][c], qs);
                 }
-            }
-            q = warp_sum(q);
-            if (lane == 0) red[i * (ALN_THREADS / 32) + warp] = q;
-        }
-        __syncthreads();
-        if (tid < ALN_RC) {
-            float q = 0.f;
+                const float rstd = 1.0f / sqrtf(warp_sum(qs) * inv_h + eps);
 #pragma unroll
-            for (int w = 0; w < ALN_THREADS / 32; ++w) q += red[tid * (ALN_THREADS / 32) + w];
-            const float r = 1.0f / sqrtf(q * inv_h + eps);
-            stat[tid] = r;
-            if (tid < rows && rstd_out) rstd_out[row0 + r0 + tid] = r;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < ALN_RC; ++i) {
-            if (i < rows) {
-                const float r = stat[i];
-#pragma unroll
-                for (int cb = 0; cb < CB; ++cb) {
-                    if (live[cb]) {
-                        const size_t o = (row0 + r0 + i) * H + col[cb];
-                        const float xh = acc[i][cb] * r;
-                        const float hv = fmaf(xh, g[cb], bt[cb]);
-                        h[o] = hv;
-                        if (xhat) xhat[o] = xh;
-                        if (hi) {
-                            bf16 a, c;
-                            split_bf16(hv, a, c);
-                            hi[o] = a;
-                            if (lo) lo[o] = c;
-                        }
-                    }
+                for (int q = 0; q < NV; ++q) {
+                    const float4 gq = *reinterpret_cast<const float4*>(gamma + 128 * q + 4 * lane);
+                    const float4 bq = *reinterpret_cast<const float4*>(beta + 128 * q + 4 * lane);
+                    const float x0 = acc[r][4 * q] * rstd, x1 = acc[r][4 * q + 1] * rstd;
+                    const float x2 = acc[r][4 * q + 2] * rstd, x3 = acc[r][4 * q + 3] * rstd;
+                    const float4 hv = make_float4(fmaf(x0, gq.x, bq.x), fmaf(x1, gq.y, bq.y), fmaf(x2, gq.z, bq.z),
+                                                  fmaf(x3, gq.w, bq.w));
+                    *reinterpret_cast<float4*>(h + ro + 128 * q) = hv;
+                    if (xhat) *reinterpret_cast<float4*>(xhat + ro + 128 * q) = make_float4(x0, x1, x2, x3);
+                    if (hi) split_store4(hi, lo, ro + 128 * q, hv.x, hv.y, hv.z, hv.w);
                 }
+                if (lane == 0 && rstd_out) rstd_out[(size_t)b * N + i] = rstd;
             }
         }
-        __syncthreads();   // stat / red are reused by the next chunk
+        __syncthreads();   // every warp is done with this P / adjacency buffer before it is re-armed
     }
 }
-
-// (four column blocks per thread would spill: wider rows take the unfused kernels)
-bool adj_ln_supported(int N, int H) { return N >= 1 && N <= 128 && H >= 1 && H <= 3 * ALN_THREADS; }
+static size_t aln_smem(int N, int H) {
+    return sizeof(float) * (2 * (size_t)N * H + 2 * ALN_MAXN * ALN_MAXN) + sizeof(uint64_t) * (2 * ALN_GROUPS);
+}
+// obj36-sized graphs whose two fp32 tiles fit in shared memory (N = 36, H = 768: 221 KB); other shapes take the
+// unfused kernels
+bool adj_ln_supported(int N, int H) {
+    return N >= 1 && N <= ALN_MAXN && H % 128 == 0 && H >= 128 && H <= 768 && aln_smem(N, H) <= 227 * 1024;
+}
 
 // h = LN(resid + adj @ P) per graph; hi/lo (optional): bf16 planes of h
 int adj_ln_fwd(const float* adj, const float* P, const float* resid, const float* gamma, const float* beta, float* h,
                float* xhat, float* rstd, bf16* hi, bf16* lo, int B, int N, int H, float eps, cudaStream_t st) {
     if (B <= 0) return XGGM_OK;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     XGGM_REQUIRE(adj && P && resid && gamma && beta && h && adj_ln_supported(N, H));
-    const int NP = ceil_div(N, ALN_RC) * ALN_RC;
-    const int NJ = ceil_div(N, ALN_JU) * ALN_JU;
-    const size_t smem = sizeof(float) * ((size_t)NJ * NP + ALN_RC * (ALN_THREADS / 32) + ALN_RC);
-    const int cb = ceil_div(H, ALN_THREADS);
-#define XGGM_ALN_LAUNCH(CBV)                                                                                        \
-    do {                                                                                                            \
-        static bool attr = false;                                                                                   \
-        if (!attr) {                                                                                                \
-            XGGM_CUDA_TRY(cudaFuncSetAttribute(adj_ln_fwd_kernel<CBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                               (int)(sizeof(float) * (132 * 144 + ALN_RC * (ALN_THREADS / 32) + ALN_RC)))); \
-            attr = true;                                                                                            \
-        }                                                                                                           \
-        XGGM_LAUNCH((adj_ln_fwd_kernel<CBV>), B, ALN_THREADS, smem, st, adj, P, resid, gamma, beta, h, xhat, rstd, hi, lo, \
-                    N, NP, H, eps);                                                                                 \
-    } while (0)
-    switch (cb) {
-        case 1: XGGM_ALN_LAUNCH(1); break;
-        case 2: XGGM_ALN_LAUNCH(2); break;
-        default: XGGM_ALN_LAUNCH(3); break;
+    XGGM_REQUIRE(al16(P) && al16(resid) && al16(gamma) && al16(beta) && al16(h) && al16(xhat) && al16(hi) && al16(lo));
+    const size_t smem = aln_smem(N, H);
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = min(B, sms);
+#define XGGM_ALN_LAUNCH(NVV)                                                                                         \
+    case NVV: {                                                                                                      \
+        static bool attr = false;                                                                                    \
+        if (!attr) {                                                                                                 \
+            XGGM_CUDA_TRY(cudaFuncSetAttribute(adj_ln_fwd_kernel<NVV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                               227 * 1024));                                                         \
+            attr = true;                                                                                             \
+        }                                                                                                            \
+        XGGM_LAUNCH((adj_ln_fwd_kernel<NVV>), grid, ALN_THREADS, smem, st, adj, P, resid, gamma, beta, h, xhat, rstd, hi, \
+                    lo, B, N, eps);                                                                                  \
+    } break;
+    switch (H / 128) {
+        XGGM_ALN_LAUNCH(1)
+        XGGM_ALN_LAUNCH(2)
+        XGGM_ALN_LAUNCH(3)
+        XGGM_ALN_LAUNCH(4)
+        XGGM_ALN_LAUNCH(5)
+        XGGM_ALN_LAUNCH(6)
+        default: return XGGM_ERR_ARG;
     }
 #undef XGGM_ALN_LAUNCH
     XGGM_LAUNCH_CHECK();
