@@ -218,6 +218,20 @@ struct DropSpec {
     float scale;       // 1 / (1 - p)
     int mode;
 };
+// p = 0.5 (the only rate the reference uses) needs ONE random bit per element: element e keeps iff bit (e % 128)
+// of the 128-bit Philox block with counter e / 128 is set -- 32x fewer Philox blocks than a 32-bit word per
+// element.  Every consumer (the row kernels, xggm_keep_mask) switches to this mapping when the threshold is
+// exactly 1/2; other rates keep the word-per-element mapping.
+constexpr uint32_t XGGM_COIN_THRESH = 0x80000000u;
+__device__ __forceinline__ uint32_t philox_word(const uint4& r, uint32_t w) {
+    return w == 0 ? r.x : (w == 1 ? r.y : (w == 2 ? r.z : r.w));
+}
+// the 4 keep bits of elements off .. off+3 (off % 4 == 0) under the coin mapping, bit j = element off + j
+__device__ __forceinline__ uint32_t coin_nibble(const Philox& rng, uint64_t stream, size_t off) {
+    const uint4 r = rng((uint64_t)(off >> 7), stream);
+    const uint32_t b = (uint32_t)(off & 127);
+    return (philox_word(r, b >> 5) >> (b & 31)) & 0xFu;
+}
 static inline uint32_t drop_threshold(float p) {
     const double t = (double)p * 4294967296.0;
     return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;

@@ -677,6 +677,17 @@ __global__ void keep_mask_kernel(uint8_t* __restrict__ keep, long long n, uint32
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (q * 4 >= n) return;
     const uint64_t stream = stream_id + (epoch ? (*epoch << 32) : 0ull);
+    if (thresh == XGGM_COIN_THRESH) {   // one bit per element (common.cuh): the mapping the row kernels use for p = 1/2
+        const uint32_t nib = coin_nibble(Philox(seed), stream, (size_t)q * 4);
+        if (aligned4 && q * 4 + 3 < n) {
+            reinterpret_cast<uchar4*>(keep)[q] = make_uchar4(nib & 1u, (nib >> 1) & 1u, (nib >> 2) & 1u, (nib >> 3) & 1u);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (q * 4 + i < n) keep[q * 4 + i] = (nib >> i) & 1u;
+        }
+        return;
+    }
     const uint4 r = Philox(seed)((uint64_t)q, stream);
     const uint32_t w[4] = {r.x, r.y, r.z, r.w};
     if (aligned4 && q * 4 + 3 < n) {
