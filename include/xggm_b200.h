@@ -178,8 +178,10 @@ int xggm_adj_regen_bwd_ex(const float* gadj, const float* x, const float* S, con
 #define XGGM_KIND_GCN 0
 #define XGGM_KIND_GIN 1
 /* In-kernel dropout of the read-out heads (used when `keeps` is NULL, `philox` is not, drop_p > 0):
- * Philox4x32-10, key = seed, counter = element index / 4, subsequence = stream0 + head index
- * (+ (*dev_epoch << 32) when dev_epoch, a DEVICE counter, is given -- lets a captured CUDA graph
+ * Philox4x32-10, key = seed, subsequence = stream0 + head index; counter = element index / 4 and one 32-bit
+ * word per element (keep iff word >= p * 2^32), except for drop_p == 0.5 exactly, where counter = element index
+ * / 128 and element e keeps iff bit (e % 128) of the 128-bit block is set (one random bit per element).
+ * The subsequence gains (*dev_epoch << 32) when dev_epoch, a DEVICE counter, is given -- lets a captured CUDA graph
  * draw fresh masks on every replay).  Forward and backward must receive the same triple.
  * xggm_keep_mask(seed, stream0 + j, dev_epoch) materialises exactly the mask head j uses. */
 typedef struct {
