@@ -354,7 +354,10 @@ def run_gpu(args):
                                "fp32 parity via 3 split-bf16 passes => 3x the algorithmic FLOPs are executed)",
                      "achieved": gemm_tflops, "peak": peak, "unit": "TFLOP/s", "frac": gemm_tflops / peak,
                      "executed_tflops": passes * gemm_tflops, "executed_frac": passes * gemm_tflops / peak,
-                     "traffic": TRAFFIC_NCU, "peak_source": f"{peaks['source']} bf16 burst (MEASURED_PEAKS.json)",
+                     "traffic": TRAFFIC_NCU,
+                     "traffic_of": "one grouped forward launch (2 projections: 2 x 10.87 GFLOP algorithmic), ncu --set full, "
+                                   "profiles/r01o_ncu_gemm_group_fwd_and_adj_apply.txt",
+                     "peak_source": f"{peaks['source']} bf16 burst (MEASURED_PEAKS.json)",
                      "launches_timed": g_n, "avg_launch_us": (g_ms / g_n * 1e3) if g_n else None,
                      "gemm_share_of_step": (g_ms / prof_steps) / ms_step if ms_step > 0 else None,
                      "note": "launches of the dominant shape [B*N,768]x[768,768] (fwd, dgrad, wgrad), timed eagerly "
