@@ -274,12 +274,15 @@ class _AdjRegen(torch.autograd.Function):
         ctx.x_planes = x_planes
         ctx.squash = int(squash)
         ctx.mark_non_differentiable(amax)
+        ctx.set_materialize_grads(False)   # no zero-filled stand-in for the (never used) gradient of amax
         return adj, amax
 
     @staticmethod
     def backward(ctx, g, _g_amax):
         x, S, amax = ctx.saved_tensors
         B, N, H = x.shape
+        if g is None:
+            return None, None, None
         g = f32(g)
         gx = torch.empty_like(x)
         work = torch.empty_like(S)
@@ -561,6 +564,7 @@ class _EdgeNoise(torch.autograd.Function):
         noisy, target = torch.empty_like(adj), torch.empty_like(adj)
         call("xggm_edge_noise", ptr(adj), ptr(randn), float(sigma), ptr(noisy), ptr(target), B, N)
         ctx.mark_non_differentiable(target)
+        ctx.set_materialize_grads(False)   # autograd would otherwise fill a [B,N,N] zero gradient for `target`
         return noisy, target
 
     @staticmethod
@@ -579,11 +583,12 @@ class _FeatNoise(torch.autograd.Function):
              int(bcast))
         ctx.bcast = bcast
         ctx.mark_non_differentiable(target)
+        ctx.set_materialize_grads(False)   # autograd would otherwise fill a [B,N,H] zero gradient for `target`
         return noisy, target
 
     @staticmethod
     def backward(ctx, g, _gt):
-        if not ctx.bcast:
+        if g is None or not ctx.bcast:
             return g, None, None, None
         g = f32(g)
         B, N, H = g.shape
