@@ -60,36 +60,58 @@ def load_peaks():
 
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock and throttle reasons sampled while the timed region runs: one streaming `nvidia-smi -lms 20`
+    process (a query per sample would take longer than the region itself), lines stamped as they arrive and
+    kept if they fall between __enter__ and __exit__."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
         self.t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
-        while not self.stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
-            except Exception:
-                pass
-            self.stop.wait(0.2)
+        try:
+            for line in self.proc.stdout:
+                self.rows.append((time.time(), [c.strip() for c in line.strip().split(",")]))
+        except Exception:
+            pass
+
+    def start(self):
+        """Spawn the sampler (call a little before the region so that the first samples are not lost)."""
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
 
     def __enter__(self):
-        self.t.start()
+        if self.proc is None and not self.t.is_alive():
+            self.start()
+        self.t0 = time.time()
         return self
 
     def __exit__(self, *a):
-        self.stop.set()
+        self.t1 = time.time()
+        time.sleep(0.05)   # let the line of the last in-region sample arrive
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
         self.t.join(timeout=6)
 
     def summary(self):
-        sm = sorted(int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
+        inside = [r for t, r in self.rows if self.t0 <= t <= self.t1 + 0.03]
+        rows = inside if inside else [r for _, r in self.rows[-1:]]   # (never empty-handed: fall back to the nearest sample)
+        sm = sorted(int(r[0]) for r in rows if len(r) >= 6 and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) >= 6 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -278,7 +300,11 @@ def run_gpu(args):
         e2e_step()
     torch.cuda.synchronize()
 
-    with ClockSampler(local) as clk:
+    sampler = ClockSampler(local).start()
+    for _ in range(3):       # keep the GPU busy while the sampler process starts
+        resident_step()
+    torch.cuda.synchronize()
+    with sampler as clk:
         l0 = _lib.kernel_launches()
         ms_res = timed(resident_step, args.steps)
         launches = _lib.kernel_launches() - l0
