@@ -127,6 +127,11 @@ ln_fwd_fast(const float* __restrict__ u, const float* __restrict__ gamma, const 
         const float* src[1] = {u + (size_t)wid * H};
         pf.issue(0, src, lane);
     }
+    // gamma / beta stay in registers for all rows of this warp (re-loading them per row cost a third of the
+    // kernel's stall samples: an L1 round trip in front of every row's stores)
+    float gam[NV * 4], bet[NV * 4];
+    load_row<NV>(gamma, lane, gam);
+    load_row<NV>(beta, lane, bet);
     int it = 0;
     for (int r = wid; r < M; r += nw, ++it) {
         const int stage = it & 1;
@@ -144,14 +149,7 @@ ln_fwd_fast(const float* __restrict__ u, const float* __restrict__ gamma, const 
         for (int i = 0; i < NV * 4; ++i) v[i] = (v[i] - mean) * rstd;
         if (xhat) store_row<NV>(xhat + (size_t)r * H, lane, v);
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const float4 g = *reinterpret_cast<const float4*>(gamma + 128 * i + 4 * lane);
-            const float4 b = *reinterpret_cast<const float4*>(beta + 128 * i + 4 * lane);
-            v[4 * i] = fmaf(v[4 * i], g.x, b.x);
-            v[4 * i + 1] = fmaf(v[4 * i + 1], g.y, b.y);
-            v[4 * i + 2] = fmaf(v[4 * i + 2], g.z, b.z);
-            v[4 * i + 3] = fmaf(v[4 * i + 3], g.w, b.w);
-        }
+        for (int i = 0; i < NV * 4; ++i) v[i] = fmaf(v[i], gam[i], bet[i]);
         store_row<NV>(h + (size_t)r * H, lane, v);
         if (hi) store_planes<NV>(hi, lo, (size_t)r * H, lane, v);
         if (lane == 0 && rstd_out) rstd_out[r] = rstd;
@@ -650,7 +648,7 @@ int layernorm_fwd(const float* u, const float* gamma, const float* beta, float* 
             constexpr size_t smem = RowPrefetch<NV, 1>::SMEM;
             static bool attr = false;
             if (!attr) { XGGM_CUDA_TRY(cudaFuncSetAttribute(ln_fwd_fast<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-            XGGM_LAUNCH((ln_fwd_fast<NV>), fast_grid(M, 3), ROW_WARPS * 32, smem, st, u, gamma, beta, h, xhat, rstd, hi, lo, M, eps);
+            XGGM_LAUNCH((ln_fwd_fast<NV>), fast_grid(M, 2), ROW_WARPS * 32, smem, st, u, gamma, beta, h, xhat, rstd, hi, lo, M, eps);
         });
     } else {
         XGGM_LAUNCH((ln_fwd_gen), gen_grid(M), GEN_WARPS * 32, 0, st, u, gamma, beta, h, xhat, rstd, hi, lo, M, H, eps);
