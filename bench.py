@@ -60,7 +60,7 @@ def load_peaks():
 
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """SM clock and throttle reasons sampled while the timed region runs: one streaming `nvidia-smi -lms 20`
+    """SM clock and throttle reasons sampled while the timed region runs: one streaming `nvidia-smi -lms 25`
     process (a query per sample would take longer than the region itself), lines stamped as they arrive and
     kept if they fall between __enter__ and __exit__."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -81,7 +81,7 @@ class ClockSampler:
         """Spawn the sampler (call a little before the region so that the first samples are not lost)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t.start()
         except Exception:
@@ -89,8 +89,6 @@ class ClockSampler:
         return self
 
     def __enter__(self):
-        if self.proc is None and not self.t.is_alive():
-            self.start()
         self.t0 = time.time()
         return self
 
@@ -103,7 +101,7 @@ class ClockSampler:
                 self.proc.wait(timeout=5)
             except Exception:
                 self.proc.kill()
-        self.t.join(timeout=6)
+            self.t.join(timeout=6)
 
     def summary(self):
         inside = [r for t, r in self.rows if self.t0 <= t <= self.t1 + 0.03]
@@ -300,7 +298,10 @@ def run_gpu(args):
         e2e_step()
     torch.cuda.synchronize()
 
-    sampler = ClockSampler(local).start()
+    # only rank 0 polls (its line is the one printed): eight 50 Hz NVML pollers on one host slow every rank down
+    sampler = ClockSampler(local)
+    if rank == 0 and os.environ.get("XGGM_BENCH_NO_CLOCKS") != "1":
+        sampler.start()
     for _ in range(3):       # keep the GPU busy while the sampler process starts
         resident_step()
     torch.cuda.synchronize()
