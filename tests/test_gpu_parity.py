@@ -747,3 +747,70 @@ def test_bertadam_full_size_properties():
     gq = grp.grads.flat.double() * coef
     want = before.double() - 1e-3 * ((0.1 * gq) / ((0.001 * gq * gq).sqrt() + 1e-6))
     _close(grp.flat_p, want.float().cpu(), 1e-6, "one step from zero moments")
+
+
+def test_training_iteration_node_branch_matches_oracle_pipeline():
+    """Three complete GGM training iterations of the node branch the way the trainer runs them
+    (src/vqa/vqacpv2.py:226-254): node_step -> logit_fc -> BCEWithLogits * A + 1.1 * loss_sm -> backward ->
+    clip_grad_norm_(5.) -> BertAdam.step, through the library (flat buffers, fused kernels) and through the fp64
+    oracle pipeline on the same weights, inputs, noise and dropout masks.  Checks the losses, the clip norm and
+    the parameter UPDATES of both iterations."""
+    import xggm_b200 as X
+    from xggm_b200.functional import inject_keep_masks
+    B, N, H, L, A, sigma, lr = 3, 36, 128, 2, 50, 1.0, 1e-3
+    p = O.make_params(11, "GCN", H, L, N, heads=True)
+    g = torch.Generator().manual_seed(12)
+    head = {"logit_fc.0.weight": torch.randn(2 * H, H, generator=g) * 0.02, "logit_fc.0.bias": torch.zeros(2 * H),
+            "logit_fc.2.weight": torch.ones(2 * H), "logit_fc.2.bias": torch.zeros(2 * H),
+            "logit_fc.3.weight": torch.randn(A, 2 * H, generator=g) * 0.02, "logit_fc.3.bias": torch.zeros(A)}
+    mod = X.XGGMHeads(H, "GCN", L, N).to(dev()).train()
+    mod.load_state_dict(p, strict=True)
+    ans = X.AnswerHead(H, A).to(dev()).train()
+    ans.load_state_dict(head, strict=True)
+    # encoder_adj takes no part in the node branch: the trainer's optimiser skips it too (its .grad stays None)
+    params = [q for n_, q in mod.named_parameters() if not n_.startswith("encoder_adj")] + list(ans.parameters())
+    names = [n_ for n_, _ in mod.named_parameters() if not n_.startswith("encoder_adj")] + [n_ for n_, _ in ans.named_parameters()]
+    opt = X.BertAdam(params, lr=lr, warmup=0.1, t_total=20)
+    ref = {k: v.double().clone() for k, v in {**p, **head}.items()}
+    mom = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in ref.items()}
+    for it in range(3):   # (the warm-up schedule makes the first step a zero-length one: lr(0) = 0)
+        visn, xp, adj_true = O.make_inputs(100 + it, B, N, H)
+        keeps = O.make_keeps(200 + it, L, 3, (B, N, H))
+        randn = torch.randn(B, N, H, generator=g)
+        target = (torch.rand(B, A, generator=g) < 0.05).float()
+        # ---- library
+        opt.zero_grad()
+        x = xp.clone().to(dev()).requires_grad_(True)
+        feat = visn.clone().to(dev()).requires_grad_(True)
+        with inject_keep_masks([m for layer in keeps for m in layer]):
+            x_gen, loss_sm, _, _ = mod.node_step(x, feat, adj_true.to(dev()), sigma, A, randn.to(dev()))
+        loss = X.bce_with_logits(ans(x_gen), target.to(dev()), scale=A) + 1.1 * loss_sm
+        loss.backward()
+        clip = X.clip_grad_norm_(opt, 5.0)
+        before = {n_: q.detach().clone() for n_, q in zip(names, params)}
+        opt.step(clip)
+        # ---- oracle (fp64)
+        rp = {k: v.clone().requires_grad_(True) for k, v in ref.items()}
+        xg_r, ls_r, _, _ = O.node_branch(xp.double(), visn.double(), adj_true.double(), rp, sigma, randn.double(), keeps, A)
+        hdn = torch.nn.functional.layer_norm(
+            O.gelu_erf(xg_r @ rp["logit_fc.0.weight"].T + rp["logit_fc.0.bias"]), (2 * H,), rp["logit_fc.2.weight"],
+            rp["logit_fc.2.bias"], 1e-12)
+        logit_r = hdn @ rp["logit_fc.3.weight"].T + rp["logit_fc.3.bias"]
+        loss_r = O.bce_with_logits(logit_r, target.double(), scale=A) + 1.1 * ls_r
+        loss_r.backward()
+        live = [k for k in names if rp[k].grad is not None]
+        assert set(live) == set(names)
+        norm_r, coef = O.clip_coef([rp[k].grad for k in live], 5.0)
+        lr_s = O.scheduled_lr(lr, it, 20, 0.1)
+        assert abs(float(loss) - float(loss_r)) <= 1e-4 * abs(float(loss_r))
+        assert abs(clip.total_norm() - norm_r) <= 2e-4 * norm_r
+        for k, q in zip(names, params):
+            new_p, m1, v1 = O.bertadam_step(ref[k], rp[k].grad * coef, mom[k][0], mom[k][1], lr_s)
+            upd_ref = (new_p - ref[k])
+            upd = (q.detach().cpu().double() - before[k].cpu().double())
+            # the Adam direction m / (sqrt(v) + e) is sign-like where |g| is tiny: compare updates against the
+            # step size lr * 3.2 (|update| <= lr * (0.1 / sqrt(0.001)) in the first steps), not element-relative
+            scale_ = max(lr_s * 3.2, 1e-12)
+            assert float((upd - upd_ref).abs().max()) <= 0.02 * scale_ + 1e-9, (it, k)
+            assert float((upd - upd_ref).norm()) <= 2e-3 * float(upd_ref.norm()) + 1e-12, (it, k)
+            ref[k], mom[k] = new_p.detach(), (m1.detach(), v1.detach())

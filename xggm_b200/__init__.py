@@ -9,7 +9,7 @@ from .glue import (add_edge_noise, add_edge_noise_v2, add_feature_noise,  # noqa
                    add_feature_noise_v2, compute_kl_loss, loss_func)
 from ._lib import get_precision, set_precision  # noqa: F401
 from .graphs import GraphedStep  # noqa: F401
-from .model import XGGMHeads  # noqa: F401
+from .model import AnswerHead, XGGMHeads  # noqa: F401
 from .optim import BertAdam, bce_with_logits, clip_grad_norm_  # noqa: F401
 from .nn import (GAT, GCN, GIN, Discriminator, DiscriminatorV2, EdgeGenerator, GATConv,  # noqa: F401
                  GATGenerator, GCNConv, GCNGenerator, GCNPlainEncoder, GeLU, GINConv, GINGenerator,

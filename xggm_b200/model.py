@@ -18,6 +18,28 @@ from .nn import GATGenerator, GCNGenerator, GeLU, GINGenerator
 GENERATORS = {"GCN": GCNGenerator, "GIN": GINGenerator, "GAT": GATGenerator}
 
 
+class AnswerHead(nn.Module):
+    """``logit_fc`` of VQAModel / GQAModel (src/vqa/vqacpv2_model.py:63-69):
+    Linear(H, 2H) -> GeLU -> BertLayerNorm(2H, eps 1e-12) -> Linear(2H, num_answers), initialised as
+    ``init_bert_weights`` does (N(0, 0.02) weights, zero biases, unit LayerNorm; src/lxrt/modeling.py:734-747).
+    Sub-module indices match the reference's nn.Sequential, so ``logit_fc.*`` checkpoint keys load unchanged."""
+
+    def __init__(self, hid_dim=768, num_answers=2274, initializer_range=0.02):
+        super().__init__()
+        self.logit_fc = nn.Sequential(nn.Linear(hid_dim, hid_dim * 2), GeLU(), nn.LayerNorm(hid_dim * 2, eps=1e-12),
+                                      nn.Linear(hid_dim * 2, num_answers))
+        for m in self.logit_fc:
+            if isinstance(m, nn.Linear):
+                m.weight.data.normal_(mean=0.0, std=initializer_range)
+                m.bias.data.zero_()
+
+    def forward(self, x):
+        m = self.logit_fc
+        z = XF.linear(x, m[0].weight, m[0].bias)
+        h = XF.gelu_ln_drop(z, m[2].weight, m[2].bias, None, 0.0, m[2].eps)
+        return XF.linear(h, m[3].weight, m[3].bias)
+
+
 class XGGMHeads(nn.Module):
     def __init__(self, hid_dim=768, gnn="GCN", n_layers=2, n_nodes=36):
         super().__init__()
