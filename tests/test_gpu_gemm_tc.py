@@ -63,15 +63,20 @@ def test_linear_products(M, N, K, mode, tol):
     assert not bad, f"{mode} M={M} N={N} K={K}: {errs}"
 
 
-def test_unaligned_shapes_take_simt_kernel():
-    # N or K not a multiple of 8: TMA cannot address the planes -> exact kernel, still correct
+def test_unaligned_shapes():
+    # K not a multiple of 8: TMA cannot address the K-contiguous planes -> exact kernel, still correct
     errs = _run(257, 10, 7)
     assert all(v[0] < 3e-6 for v in errs.values()), errs
-    errs = _run(3, 630, 768)
-    assert all(v[0] < 3e-6 for v in errs.values()), errs
+    # ragged OUTPUT width (encoder_adj: 630, the answer head: 2274) stays on the tensor cores: planes whose rows
+    # have length N carry a pitch padded to 8 with zero columns -> the split-bf16 error budget applies
+    for M, N, K in ((3, 630, 768), (256, 630, 768), (256, 2274, 1536), (130, 10, 64), (300, 201, 136)):
+        errs = _run(M, N, K)
+        bad = {k: v for k, v in errs.items() if not (v[0] < 3e-5 and v[1] < 3e-4)}
+        assert not bad, f"M={M} N={N} K={K}: {errs}"
 
 
-@pytest.mark.parametrize("M,N,K", [(300, 200, 136), (130, 64, 96), (9252, 768, 768), (257, 776, 72)])
+@pytest.mark.parametrize("M,N,K", [(300, 200, 136), (130, 64, 96), (9252, 768, 768), (257, 776, 72), (256, 630, 768),
+                                   (77, 203, 72)])
 def test_outputs_stay_inside_their_buffers(M, N, K):
     """compute-sanitizer is closed on this GPU pool, so bounds are checked by hand: every output of the
     three Linear products (ragged M / N / K tails through TMA zero fill and the clipped epilogues) sits in

@@ -19,6 +19,7 @@ ap.add_argument("--nodes", type=int, default=36)
 ap.add_argument("--precision", default="fp32")
 ap.add_argument("--gnn", default="GCN")
 ap.add_argument("--steps", type=int, default=1)
+ap.add_argument("--branch", default="node", choices=["node", "relation"])
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 torch.manual_seed(9595)
@@ -34,8 +35,12 @@ def compute():
     grads.flat.zero_()
     x = xp.detach().requires_grad_(True)
     feat = visn.detach().requires_grad_(True)
-    x_gen, loss_sm, _, _ = model.node_step(x, feat, adj, 1.0, 2274)
-    ((x_gen * cot).sum() + 1.1 * loss_sm).backward()
+    if a.branch == "relation":
+        x_gen, loss_sm, _, _ = model.relation_step(x, feat, adj, 1.0, 2274, kl_weight=12.0)
+        ((x_gen * cot).sum() + 6.0 * loss_sm).backward()
+    else:
+        x_gen, loss_sm, _, _ = model.node_step(x, feat, adj, 1.0, 2274)
+        ((x_gen * cot).sum() + 1.1 * loss_sm).backward()
 
 
 for _ in range(3):

@@ -69,23 +69,6 @@ static int proj_fwd(bool tc, const Operand& a, const Operand& w, const float* bi
     if (tc) return gemm_tc(false, false, a.hi, a.lo, w.hi, w.lo, bias, resid, out, nullptr, nullptr, M, N, K, 0, 0, npass(), st);
     return gemm_simt(0, a.f32, w.f32, bias, resid, out, M, N, K, 0, st);
 }
-// ga[M,K] (+)= g[M,N] w[N,K]
-// Tensor-core engine: `w` carries the planes of W^T ([K,N], contraction N contiguous) so that dgrad is
-// the same K-major x K-major product as the forward pass.  ga_planes (optional): also emit ga as planes.
-static int proj_dgrad(bool tc, const Operand& g, const Operand& w, float* ga, int M, int N, int K,
-                      int accumulate, cudaStream_t st, const Operand* ga_planes = nullptr) {
-    if (tc) return gemm_tc(false, false, g.hi, g.lo, w.hi, w.lo, nullptr, nullptr, ga,
-                           ga_planes ? const_cast<bf16*>(ga_planes->hi) : nullptr,
-                           ga_planes ? const_cast<bf16*>(ga_planes->lo) : nullptr, M, K, N, accumulate, 0, npass(), st);
-    return gemm_simt(1, g.f32, w.f32, nullptr, nullptr, ga, M, K, N, accumulate, st);
-}
-// gw[N,K] = g[M,N]^T a[M,K]
-static int proj_wgrad(bool tc, const Operand& g, const Operand& a, float* gw, int M, int N, int K,
-                      int accumulate, cudaStream_t st) {
-    if (tc) return gemm_tc(true, true, g.hi, g.lo, a.hi, a.lo, nullptr, nullptr, gw, nullptr, nullptr, N, K, M, accumulate, 1, npass(), st);
-    return gemm_simt(2, g.f32, a.f32, nullptr, nullptr, gw, N, K, M, accumulate, st);
-}
-
 // ---- saved-activation layout of one GCN / GIN layer ---------------------------
 struct GnnLayout {
     long long MH, Mr, HH;   // padded sizes of an [M,H], an [M] and an [H,H] chunk
@@ -577,13 +560,17 @@ int xggm_set_precision(int mode) {
 }
 int xggm_get_precision(void) { return g_precision; }
 
-// work layout of the Linear entry points: P(a)[M,K] | P(w)[N,K] | P(g)[M,N]
+// work layout of the Linear entry points: P(a)[M,K] | P(w)[N,K] or P(w^T)[K,Np] | P(g)[M,Np]
+// Np = N rounded up to 8: planes whose rows have length N are stored with that pitch and zero columns, so a
+// ragged output width (encoder_adj: 630, answer head: 2274) stays on the tensor cores.
+static inline int pad8i(int n) { return (n + 7) & ~7; }
 long long xggm_linear_work_bytes(int M, int N, int K) {
     if (M < 0 || N <= 0 || K <= 0) return -1;
-    return 4 * (pad8((long long)M * K) + pad8((long long)N * K) + pad8((long long)M * N));
+    const long long Np = pad8i(N);
+    return 4 * (pad8((long long)M * K) + pad8(Np * K) + pad8((long long)M * Np));
 }
 static inline bool linear_tc(const void* work, int M, int N, int K) {
-    return work != nullptr && M > 0 && use_tc(M, N, K);
+    return work != nullptr && M > 0 && g_precision != XGGM_PREC_FP32_SIMT && gemm_tc_ragged_ok(M, N, K);
 }
 
 int xggm_linear_fwd(const float* a, const float* w, const float* bias, const float* resid,
@@ -595,7 +582,7 @@ int xggm_linear_fwd(const float* a, const float* w, const float* bias, const flo
     Operand ao{a, nullptr, nullptr}, wo{w, nullptr, nullptr};
     if (tc) {
         ao = planes_at(a, wk, (long long)M * K);
-        wo = planes_at(w, wk + pad8((long long)M * K), (long long)N * K);
+        wo = planes_at(w, wk + pad8((long long)M * K), (long long)pad8i(N) * K);
         const float* src[2] = {a, w};
         bf16* hi[2] = {const_cast<bf16*>(ao.hi), const_cast<bf16*>(wo.hi)};
         bf16* lo[2] = {const_cast<bf16*>(ao.lo), const_cast<bf16*>(wo.lo)};
@@ -609,18 +596,19 @@ int xggm_linear_bwd_input(const float* g, const float* w, float* ga, int M, int 
     if (M == 0) return XGGM_OK;
     XGGM_REQUIRE(g && w && ga && M >= 0 && N > 0 && K > 0);
     const bool tc = linear_tc(work, M, N, K);
+    if (!tc) return gemm_simt(1, g, w, nullptr, nullptr, ga, M, K, N, accumulate, as_stream(s));
     float* wk = static_cast<float*>(work);
-    Operand go{g, nullptr, nullptr}, wo{w, nullptr, nullptr};
-    if (tc) {
-        wo = planes_at(w, wk + pad8((long long)M * K), (long long)N * K);
-        go = planes_at(g, wk + pad8((long long)M * K) + pad8((long long)N * K), (long long)M * N);
-        XGGM_TRY(split_one(go, (long long)M * N, as_stream(s)));
-        const float* src[1] = {w};
-        bf16* hi[1] = {const_cast<bf16*>(wo.hi)};
-        bf16* lo[1] = {const_cast<bf16*>(wo.lo)};
-        XGGM_TRY(split_planes_t(src, hi, npass() == 3 ? lo : nullptr, N, K, 1, as_stream(s)));   // planes of w^T [K,N]
-    }
-    return proj_dgrad(tc, go, wo, ga, M, N, K, accumulate, as_stream(s));
+    const int Np = pad8i(N);
+    const Operand wo = planes_at(w, wk + pad8((long long)M * K), (long long)Np * K);                                  // w^T [K,Np]
+    const Operand go = planes_at(g, wk + pad8((long long)M * K) + pad8((long long)Np * K), (long long)M * Np);        // g [M,Np]
+    XGGM_TRY(split_planes_pitched(g, mut(go.hi), lo_or_null(go), M, N, Np, as_stream(s)));
+    const float* src[1] = {w};
+    bf16* hi[1] = {mut(wo.hi)};
+    bf16* lo[1] = {mut(wo.lo)};
+    XGGM_TRY(split_planes_t(src, hi, npass() == 3 ? lo : nullptr, N, K, 1, as_stream(s), Np));
+    // ga[M,K] (+)= g[M,Np] (w^T[K,Np])^T : the zero columns N..Np-1 add nothing
+    return gemm_tc(false, false, go.hi, go.lo, wo.hi, wo.lo, nullptr, nullptr, ga, nullptr, nullptr, M, K, Np, accumulate, 0,
+                   npass(), as_stream(s));
 }
 int xggm_linear_bwd_weight(const float* g, const float* a, float* gw, float* gbias, int M, int N,
                            int K, int accumulate, void* work, xggm_stream_t s) {
@@ -634,17 +622,18 @@ int xggm_linear_bwd_weight(const float* g, const float* a, float* gw, float* gbi
     XGGM_REQUIRE(g && a);
     const bool tc = linear_tc(work, M, N, K);
     float* wk = static_cast<float*>(work);
-    Operand go{g, nullptr, nullptr}, ao{a, nullptr, nullptr};
     if (tc) {
-        ao = planes_at(a, wk, (long long)M * K);
-        go = planes_at(g, wk + pad8((long long)M * K) + pad8((long long)N * K), (long long)M * N);
-        const float* src[2] = {g, a};
-        bf16* hi[2] = {const_cast<bf16*>(go.hi), const_cast<bf16*>(ao.hi)};
-        bf16* lo[2] = {const_cast<bf16*>(go.lo), const_cast<bf16*>(ao.lo)};
-        const long long n[2] = {(long long)M * N, (long long)M * K};
-        XGGM_TRY(split_planes(src, hi, npass() == 3 ? lo : nullptr, n, 2, as_stream(s)));
+        const int Np = pad8i(N);
+        const Operand ao = planes_at(a, wk, (long long)M * K);
+        const Operand go = planes_at(g, wk + pad8((long long)M * K) + pad8((long long)Np * K), (long long)M * Np);
+        XGGM_TRY(split_planes_pitched(g, mut(go.hi), lo_or_null(go), M, N, Np, as_stream(s)));
+        XGGM_TRY(split_one(ao, (long long)M * K, as_stream(s)));
+        // gw[N,K] (+)= g[M,N]^T a[M,K]: A = g planes read MN-major with row pitch Np
+        XGGM_TRY(gemm_tc(true, true, go.hi, go.lo, ao.hi, ao.lo, nullptr, nullptr, gw, nullptr, nullptr, N, K, M, accumulate,
+                         1, npass(), as_stream(s), Np, 0));
+    } else {
+        XGGM_TRY(gemm_simt(2, g, a, nullptr, nullptr, gw, N, K, M, accumulate, as_stream(s)));
     }
-    XGGM_TRY(proj_wgrad(tc, go, ao, gw, M, N, K, accumulate, as_stream(s)));
     if (gbias) XGGM_TRY(colsum(g, gbias, M, N, accumulate, as_stream(s)));
     return XGGM_OK;
 }

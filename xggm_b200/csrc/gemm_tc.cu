@@ -673,6 +673,22 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const SplitJobs jobs)
     }
 }
 
+// pitched split: src [R,C] fp32 -> hi/lo [R,P] bf16 with zero columns C..P-1 (P % 8 == 0)
+__global__ void __launch_bounds__(256)
+split_planes_pitched_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                            long long R, int C, int P) {
+    pdl_prologue();
+    const long long n = R * P, stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const long long r = i / P;
+        const int c = (int)(i - r * P);
+        __nv_bfloat16 h, l;
+        split1(c < C ? src[r * C + c] : 0.f, h, l);
+        hi[i] = h;
+        if (lo) lo[i] = l;
+    }
+}
+
 // transposed split: src [R,C] fp32 -> hi/lo [C,R] bf16 (weights only: dgrad reads W^T K-major)
 struct SplitTJob {
     const float* src;
@@ -682,7 +698,7 @@ struct SplitTJob {
 struct SplitTJobs {
     SplitTJob j[MAX_SPLIT_JOBS];
 };
-__global__ void __launch_bounds__(256) split_planes_t_kernel(const SplitTJobs jobs, int R, int C) {
+__global__ void __launch_bounds__(256) split_planes_t_kernel(const SplitTJobs jobs, int R, int C, int P) {
     pdl_prologue();
     __shared__ float tile[32][33];
     const SplitTJob job = jobs.j[blockIdx.z];
@@ -694,12 +710,12 @@ __global__ void __launch_bounds__(256) split_planes_t_kernel(const SplitTJobs jo
     }
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
-        const int c = c0 + i, r = r0 + tx;   // output row = source column
-        if (c < C && r < R) {
+        const int c = c0 + i, r = r0 + tx;   // output row = source column; output pitch P >= R, zero padded
+        if (c < C && r < P) {
             __nv_bfloat16 h, l;
-            split1(tile[tx][i], h, l);
-            job.hi[(size_t)c * R + r] = h;
-            if (job.lo) job.lo[(size_t)c * R + r] = l;
+            split1(r < R ? tile[tx][i] : 0.f, h, l);
+            job.hi[(size_t)c * P + r] = h;
+            if (job.lo) job.lo[(size_t)c * P + r] = l;
         }
     }
 }
@@ -760,11 +776,12 @@ static EncodeTiledFn encode_fn() {
 }
 
 // 2-D bf16 tensor [rows][cols] (cols contiguous), box = [box_rows][64], SWIZZLE_128B, zero OOB fill.
-static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows) {
+// `pitch` (elements, 0 = cols): row pitch of a padded plane (ragged widths are stored with a multiple-of-8 pitch).
+static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows, long long pitch = 0) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return XGGM_ERR_UNSUPPORTED;
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    const cuuint64_t strides[1] = {(cuuint64_t)(pitch > 0 ? pitch : cols) * 2};
     const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1u, 1u};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
@@ -841,6 +858,10 @@ static int dispatch_major(bool a_mn, bool b_mn, const tc::GroupMaps& maps, const
     return XGGM_ERR_UNSUPPORTED;  // (MN-major A with K-major B is not needed by a Linear layer)
 }
 
+// Linear layers whose OUTPUT width N is ragged (encoder_adj: 630, the answer head: 2274) still run on the tensor
+// cores: the planes that have N as their row length (the gradient g [M,N] and W^T [K,N]) are stored with the pitch
+// padded to a multiple of 8 and zero columns, which the contraction simply runs over.
+bool gemm_tc_ragged_ok(int M, int N, int K) { return M > 0 && N > 0 && K > 0 && (K % 8 == 0); }
 bool gemm_tc_supported(int M, int N, int K) {
     // TMA needs 16-byte row pitches in every plane a Linear's three products touch
     return M > 0 && N > 0 && K > 0 && (N % 8 == 0) && (K % 8 == 0);
@@ -920,11 +941,11 @@ int gemm_tc_group(bool a_mn, bool b_mn, const GemmProb* pr, int count, int M, in
     p.dbg = g_tc_dbg;
     for (int g = 0; g < tc::MAX_GROUP; ++g) {
         const GemmProb& q = pr[g < segments ? g : 0];
-        XGGM_TRY(make_map(&maps.m[g].a_hi, q.a_hi, a_rows, a_cols, a_box));
-        XGGM_TRY(make_map(&maps.m[g].b_hi, q.b_hi, b_rows, b_cols, b_box));
+        XGGM_TRY(make_map(&maps.m[g].a_hi, q.a_hi, a_rows, a_cols, a_box, q.lda));
+        XGGM_TRY(make_map(&maps.m[g].b_hi, q.b_hi, b_rows, b_cols, b_box, q.ldb));
         if (npass == 3) {
-            XGGM_TRY(make_map(&maps.m[g].a_lo, q.a_lo, a_rows, a_cols, a_box));
-            XGGM_TRY(make_map(&maps.m[g].b_lo, q.b_lo, b_rows, b_cols, b_box));
+            XGGM_TRY(make_map(&maps.m[g].a_lo, q.a_lo, a_rows, a_cols, a_box, q.lda));
+            XGGM_TRY(make_map(&maps.m[g].b_lo, q.b_lo, b_rows, b_cols, b_box, q.ldb));
         } else {
             maps.m[g].a_lo = maps.m[g].a_hi;
             maps.m[g].b_lo = maps.m[g].b_hi;
@@ -970,8 +991,9 @@ int gemm_tc_group(bool a_mn, bool b_mn, const GemmProb* pr, int count, int M, in
 
 int gemm_tc(bool a_mn, bool b_mn, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const __nv_bfloat16* b_hi,
             const __nv_bfloat16* b_lo, const float* bias, const float* resid, float* C, __nv_bfloat16* c_hi,
-            __nv_bfloat16* c_lo, int M, int N, int K, int accumulate, int allow_split_k, int npass, cudaStream_t st) {
-    const GemmProb q{a_hi, a_lo, b_hi, b_lo, bias, resid, C, c_hi, c_lo, accumulate};
+            __nv_bfloat16* c_lo, int M, int N, int K, int accumulate, int allow_split_k, int npass, cudaStream_t st,
+            int lda, int ldb) {
+    const GemmProb q{a_hi, a_lo, b_hi, b_lo, bias, resid, C, c_hi, c_lo, accumulate, lda, ldb};
     return gemm_tc_group(a_mn, b_mn, &q, 1, M, N, K, allow_split_k, npass, st, false);
 }
 
@@ -1071,7 +1093,8 @@ int adj_apply_tc(const __nv_bfloat16* c_hi_in, const __nv_bfloat16* c_lo_in, con
 
 // Transposed split of `count` [R,C] fp32 matrices into [C,R] bf16 planes (one launch per 8 matrices).
 int split_planes_t(const float* const* src, __nv_bfloat16* const* hi, __nv_bfloat16* const* lo, int R, int C,
-                   int count, cudaStream_t st) {
+                   int count, cudaStream_t st, int pitch) {
+    const int P = pitch > 0 ? pitch : R;
     int done = 0;
     while (done < count) {
         tc::SplitTJobs jobs;
@@ -1082,11 +1105,21 @@ int split_planes_t(const float* const* src, __nv_bfloat16* const* hi, __nv_bfloa
             jobs.j[i].lo = lo ? lo[done + i] : nullptr;
         }
         if (R > 0 && C > 0) {
-            XGGM_LAUNCH((tc::split_planes_t_kernel), dim3(ceil_div(C, 32), ceil_div(R, 32), n), 256, 0, st, jobs, R, C);
+            XGGM_LAUNCH((tc::split_planes_t_kernel), dim3(ceil_div(C, 32), ceil_div(P, 32), n), 256, 0, st, jobs, R, C, P);
             XGGM_LAUNCH_CHECK();
         }
         done += n;
     }
+    return XGGM_OK;
+}
+
+// src [R,C] -> planes [R,P] (P >= C, P % 8 == 0), zero padded
+int split_planes_pitched(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, long long R, int C, int P, cudaStream_t st) {
+    if (R <= 0 || C <= 0) return XGGM_OK;
+    XGGM_REQUIRE(src && hi && P >= C);
+    const int grid = (int)max(1LL, min((long long)num_sms() * 8, (R * P + 255) / 256));
+    XGGM_LAUNCH((tc::split_planes_pitched_kernel), grid, 256, 0, st, src, hi, lo, R, C, P);
+    XGGM_LAUNCH_CHECK();
     return XGGM_OK;
 }
 

@@ -19,7 +19,10 @@ int colsum(const float* g, float* out, int R, int C, int accumulate, cudaStream_
 bool gemm_tc_supported(int M, int N, int K);
 int gemm_tc(bool a_mn, bool b_mn, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const __nv_bfloat16* b_hi,
             const __nv_bfloat16* b_lo, const float* bias, const float* resid, float* C, __nv_bfloat16* c_hi,
-            __nv_bfloat16* c_lo, int M, int N, int K, int accumulate, int allow_split_k, int npass, cudaStream_t st);
+            __nv_bfloat16* c_lo, int M, int N, int K, int accumulate, int allow_split_k, int npass, cudaStream_t st,
+            int lda = 0, int ldb = 0);
+bool gemm_tc_ragged_ok(int M, int N, int K);
+int split_planes_pitched(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, long long R, int C, int P, cudaStream_t st);
 // one product of a grouped launch (gemm_tc_group): same shape / operand layout for every member
 struct GemmProb {
     const __nv_bfloat16 *a_hi, *a_lo, *b_hi, *b_lo;
@@ -28,6 +31,7 @@ struct GemmProb {
     float* C;
     __nv_bfloat16 *c_hi, *c_lo;
     int accumulate;
+    int lda, ldb;   // row pitch (elements) of padded A / B planes; 0 = dense
 };
 int gemm_tc_group(bool a_mn, bool b_mn, const GemmProb* pr, int count, int M, int N, int K, int allow_split_k,
                   int npass, cudaStream_t st, bool kcat = false);
@@ -47,7 +51,7 @@ int scale_accum(const float* S, float* out, long long n, float alpha0, const flo
 int split_planes(const float* const* src, __nv_bfloat16* const* hi, __nv_bfloat16* const* lo, const long long* n,
                  int count, cudaStream_t st);
 int split_planes_t(const float* const* src, __nv_bfloat16* const* hi, __nv_bfloat16* const* lo, int R, int C,
-                   int count, cudaStream_t st);
+                   int count, cudaStream_t st, int pitch = 0);
 void gemm_tc_set_debug(unsigned long long* dev_buf);
 int gemm_prof_enable(int on);
 int gemm_prof_read(double* total_ms, long long* launches, double* flops);
