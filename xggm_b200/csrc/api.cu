@@ -601,7 +601,8 @@ int xggm_linear_bwd_input(const float* g, const float* w, float* ga, int M, int 
     const int Np = pad8i(N);
     const Operand wo = planes_at(w, wk + pad8((long long)M * K), (long long)Np * K);                                  // w^T [K,Np]
     const Operand go = planes_at(g, wk + pad8((long long)M * K) + pad8((long long)Np * K), (long long)M * Np);        // g [M,Np]
-    XGGM_TRY(split_planes_pitched(g, mut(go.hi), lo_or_null(go), M, N, Np, as_stream(s)));
+    if (Np == N) XGGM_TRY(split_one(go, (long long)M * N, as_stream(s)));   // dense rows: the vectorised splitter
+    else XGGM_TRY(split_planes_pitched(g, mut(go.hi), lo_or_null(go), M, N, Np, as_stream(s)));
     const float* src[1] = {w};
     bf16* hi[1] = {mut(wo.hi)};
     bf16* lo[1] = {mut(wo.lo)};
@@ -626,8 +627,16 @@ int xggm_linear_bwd_weight(const float* g, const float* a, float* gw, float* gbi
         const int Np = pad8i(N);
         const Operand ao = planes_at(a, wk, (long long)M * K);
         const Operand go = planes_at(g, wk + pad8((long long)M * K) + pad8((long long)Np * K), (long long)M * Np);
-        XGGM_TRY(split_planes_pitched(g, mut(go.hi), lo_or_null(go), M, N, Np, as_stream(s)));
-        XGGM_TRY(split_one(ao, (long long)M * K, as_stream(s)));
+        if (Np == N) {
+            const float* src[2] = {g, a};
+            bf16* hi[2] = {mut(go.hi), mut(ao.hi)};
+            bf16* lo[2] = {mut(go.lo), mut(ao.lo)};
+            const long long n[2] = {(long long)M * N, (long long)M * K};
+            XGGM_TRY(split_planes(src, hi, npass() == 3 ? lo : nullptr, n, 2, as_stream(s)));
+        } else {
+            XGGM_TRY(split_planes_pitched(g, mut(go.hi), lo_or_null(go), M, N, Np, as_stream(s)));
+            XGGM_TRY(split_one(ao, (long long)M * K, as_stream(s)));
+        }
         // gw[N,K] (+)= g[M,N]^T a[M,K]: A = g planes read MN-major with row pitch Np
         XGGM_TRY(gemm_tc(true, true, go.hi, go.lo, ao.hi, ao.lo, nullptr, nullptr, gw, nullptr, nullptr, N, K, M, accumulate,
                          1, npass(), as_stream(s), Np, 0));
