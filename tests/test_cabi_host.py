@@ -149,3 +149,26 @@ def test_bertadam_host_logic_flat_layout_and_schedule():
         BertAdam(ps, lr=1e-3, b1=1.0)
     with pytest.raises(ValueError):
         BertAdam([torch.nn.Parameter(torch.zeros(2))], lr=1e-3, flat_grads=fg)   # bucket of other parameters
+
+
+def test_operand_plane_record_is_dropped_when_the_tensor_changes():
+    """functional._attach_planes / _planes_of (host logic of the operand-plane hand-over): the record follows
+    the tensor object and is invalidated by an in-place update, a re-allocation or an engine change."""
+    import torch
+    import xggm_b200 as X
+    import xggm_b200.functional as XF
+    t = torch.zeros(4, 6, 16)
+    planes = torch.empty(64, dtype=torch.uint8)
+    assert XF._planes_of(t) is None
+    XF._attach_planes(t, planes)
+    assert XF._planes_of(t) is planes
+    assert XF._planes_of(t.clone()) is None            # a different tensor object / storage
+    X.set_precision("bf16")                              # planes written under another engine are not reused
+    try:
+        assert XF._planes_of(t) is None
+    finally:
+        X.set_precision("fp32")
+    assert XF._planes_of(t) is planes
+    t.add_(1.0)                                          # in-place update bumps the version counter
+    assert XF._planes_of(t) is None
+    assert XF._new_planes(torch.zeros(2, 3, 10)) is None     # row length not a multiple of 8: producers emit nothing
