@@ -418,6 +418,50 @@ def test_full_size_properties():
             assert torch.isfinite(p_.grad).all()
 
 
+@pytest.mark.parametrize("branch", ["node", "relation"])
+def test_full_size_tensor_core_engine_matches_exact_engine(branch):
+    """BASELINE size (B=256, N=36, H=768, train mode): the tensor-core engine -- CTA-pair kernel, grouped launches,
+    K-concatenated dgrad, tensor-core message passing / Gram tiles, operand-plane hand-over; none of which the
+    small fixtures reach (M <= 128 rows there) -- against the exact-fp32 engine (itself pinned to the oracle by the
+    fixture tests) on the same weights, inputs, noise and Philox dropout sites: outputs, input gradients and every
+    parameter gradient within the fp32 budget."""
+    import xggm_b200 as X
+    import xggm_b200.functional as XF
+    B, N, H, A = 256, 36, 768, 2274
+    torch.manual_seed(31)
+    mod = X.XGGMHeads(H, "GCN", 2).to(dev()).train()
+    visn, xp, adj_true = (t.to(dev()) for t in O.make_inputs(5, B, N, H))
+    g = torch.Generator().manual_seed(6)
+    randn = (torch.randn(B, N, H, generator=g) if branch == "node" else torch.randn(B, N, N, generator=g)).to(dev())
+    cot = torch.randn(B, H, generator=g).to(dev())
+    res = {}
+    for engine in ("fp32", "fp32_simt"):
+        X.set_precision(engine)
+        try:
+            mod.zero_grad(set_to_none=True)
+            XF._drop.site = 500
+            x = xp.clone().requires_grad_(True)
+            feat = visn.clone().requires_grad_(True)
+            if branch == "node":
+                x_gen, loss_sm, nodes, adj_g = mod.node_step(x, feat, adj_true, 1.0, A, randn)
+                ((x_gen * cot).sum() + 1.1 * loss_sm).backward()
+            else:
+                x_gen, loss_sm, nodes, adj_g = mod.relation_step(x, feat, adj_true, 1.0, A, kl_weight=12.0, randn=randn)
+                ((x_gen * cot).sum() + 6.0 * loss_sm).backward()
+            res[engine] = {"x_gen": x_gen.detach().cpu(), "loss_sm": loss_sm.detach().cpu().reshape(1),
+                           "nodes": nodes.detach().cpu(), "adj": adj_g.detach().cpu(), "gx": x.grad.cpu(),
+                           "gfeat": feat.grad.cpu(),
+                           **{"g/" + n_: p_.grad.detach().cpu().clone() for n_, p_ in mod.named_parameters()
+                              if p_.grad is not None}}
+        finally:
+            X.set_precision("fp32")
+    assert res["fp32"].keys() == res["fp32_simt"].keys() and len(res["fp32"]) > 20
+    for k, ref in res["fp32_simt"].items():
+        # parameter gradients are sums over 9216 rows of products of O(1e-5)-accurate factors: 2e-4 as in the
+        # fixture tests; activations and input gradients 1e-4
+        _close(res["fp32"][k], ref, 2e-4 if k.startswith("g/") else TOL, f"{branch}: {k}")
+
+
 def test_keep_mask_statistics_and_determinism():
     import xggm_b200.functional as XF
     torch.manual_seed(123)
