@@ -522,7 +522,10 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const Params p) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int col = c * 32 + j;
-                            if (col >= gl * gn && col < gl * gn + gn) orow[col] = __uint_as_float(v[j]);
+                            if (col >= gl * gn && col < gl * gn + gn) {
+                                if (p.atomic) atomicAdd(&orow[col], __uint_as_float(v[j]));
+                                else orow[col] = __uint_as_float(v[j]);
+                            }
                         }
                     }
                 }
@@ -1021,14 +1024,20 @@ int gram_tc(const __nv_bfloat16* p_hi, const __nv_bfloat16* p_lo, const __nv_bfl
     for (int g = 1; g < tc::MAX_GROUP; ++g) maps.m[g] = maps.m[0];
     tc::Params p;
     p.M = (int)M; p.N = (int)M; p.num_kb = ceil_div(H, tc::BK);
-    p.tiles_m = ceil_div(B, G); p.tiles_n = 1; p.splits = 1; p.kb_per_split = p.num_kb;
+    p.tiles_m = ceil_div(B, G); p.tiles_n = 1;
+    // fewer tiles than half the SMs (B = 256 graphs of 36 nodes: 86 tiles on 148 SMs): the contraction is cut in
+    // two and the halves meet in S with atomic adds (two addends from zero: the sum does not depend on their order)
+    p.splits = (2 * p.tiles_m <= num_sms() && p.num_kb >= 4) ? 2 : 1;
+    p.kb_per_split = ceil_div(p.num_kb, p.splits);
+    p.splits = ceil_div(p.num_kb, p.kb_per_split);
     p.ldc = N;
-    p.atomic = 0; p.vec4 = 0;
+    p.atomic = p.splits > 1 ? 1 : 0; p.vec4 = 0;
+    if (p.atomic) XGGM_CUDA_TRY(cudaMemsetAsync(S, 0, sizeof(float) * (size_t)B * N * N, st));
     single_problem(p, nullptr, nullptr, S, nullptr, nullptr, 0);
     p.gram_n = N; p.gram_g = G; p.gram_b = B;
     p.bd_stride = 0;
     p.dbg = nullptr;
-    const int grid = min(num_sms(), p.tiles_m);
+    const int grid = min(num_sms(), p.tiles_m * p.splits);
     void* prof = gemm_prof_begin(2.0 * B * N * N * H, st);
     const int rc = npass == 3 ? launch_tc<128, 3, false, false>(maps, p, grid, st)
                               : launch_tc<128, 1, false, false>(maps, p, grid, st);
