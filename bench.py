@@ -185,12 +185,26 @@ def workload_config(n_gpus, B=B_PER_GPU, gnn=GNN, precision="fp32", branch="node
             "launch": "one CUDA-graph replay per step (xggm_b200.GraphedStep)"}
 
 
+def synthetic_inputs(seed, B, n_nodes=N_NODES, hidden=HID):
+    """Synthetic block inputs in the shapes of SURVEY.md section 8d (the same recipe as the oracle's input factory,
+    restated here so that the measured arm does not touch oracle/): visn = layer_norm(N(0,1)) -- LXMERT's visual
+    output is a LayerNorm output --, pooled = tanh(N(0,1)), adj_true = obj36_adj look-alike (symmetrised
+    U(-0.2, 1), max-normalised, non-zero diagonal)."""
+    g = torch.Generator().manual_seed(seed)
+    v = torch.randn(B, n_nodes, hidden, generator=g, dtype=torch.float64)
+    v = (v - v.mean(-1, keepdim=True)) / v.std(-1, unbiased=False, keepdim=True)
+    xp = torch.tanh(torch.randn(B, hidden, generator=g, dtype=torch.float64))
+    c = torch.rand(B, n_nodes, n_nodes, generator=g, dtype=torch.float64) * 1.2 - 0.2
+    c = c + c.transpose(1, 2)
+    c = c / c.amax(dim=(1, 2), keepdim=True)
+    return v.float(), xp.float(), c.float()
+
+
 # ---------------------------------------------------------------------------------- GPU arm
 def run_gpu(args):
     import torch.distributed as dist
     import xggm_b200 as X
     from xggm_b200 import _lib
-    from oracle import xggm_oracle as O  # input factory + cpu_baseline leg only
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -221,7 +235,7 @@ def run_gpu(args):
     # valid), preceded by clip_grad_norm_(., 5.) (src/vqa/vqacpv2.py:252)
     optim = X.BertAdam(model.parameters(), lr=4e-6, flat_grads=grads)
 
-    visn_h, xp_h, adj_h = (t.pin_memory() for t in O.make_inputs(9596 + rank, B, N_NODES, HID))
+    visn_h, xp_h, adj_h = (t.pin_memory() for t in synthetic_inputs(9596 + rank, B, N_NODES, HID))
     cot_h = torch.randn(B, HID, generator=torch.Generator().manual_seed(2 + rank)).pin_memory()
     visn_d, xp_d, adj_d, cot_d = (t.to(dev) for t in (visn_h, xp_h, adj_h, cot_h))
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)

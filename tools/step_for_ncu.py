@@ -11,7 +11,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import xggm_b200 as X  # noqa: E402
-from oracle import xggm_oracle as O  # noqa: E402  (input factory only)
+from bench import synthetic_inputs  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=256)
@@ -27,7 +27,7 @@ X.set_precision(a.precision)
 model = X.XGGMHeads(768, a.gnn, 2, a.nodes).to(dev).train()
 from xggm_b200.ddp import FlatGrads  # noqa: E402
 grads = FlatGrads(model.parameters())
-visn, xp, adj = (t.to(dev) for t in O.make_inputs(9596, a.batch, a.nodes, 768))
+visn, xp, adj = (t.to(dev) for t in synthetic_inputs(9596, a.batch, a.nodes, 768))
 cot = torch.randn(a.batch, 768, device=dev)
 
 
