@@ -242,7 +242,7 @@ def run_gpu(args):
     loss_host = torch.zeros(1).pin_memory()
 
     def compute(visn, xp, adj):  # forward + backward of the block; gradients land in the flat bucket
-        flat_grad.zero_()
+        grads.zero_()
         x = xp.requires_grad_(True)
         feat = visn.requires_grad_(True)
         with grads.overlap(average=True):

@@ -13,7 +13,11 @@
  *  - B graphs, N nodes per graph (36 for obj36), H feature width (768), M = B*N rows.
  *  - Every call enqueues on the caller's stream and returns without synchronising.
  *  - Return value: XGGM_OK or a negative XGGM_ERR_* code.  Nothing throws.
- *  - Stateless and re-entrant; one CUDA context per process (one process per GPU).
+ *  - No per-call state is kept, but three PROCESS-WIDE settings exist and are not synchronised: the projection
+ *    engine (xggm_set_precision), the bench instrumentation (xggm_prof_*, xggm_debug_timeline) and the launch
+ *    counter (atomic).  Set them before worker threads start issuing calls; entry points themselves may be
+ *    called from several host threads (autograd does) as long as each call's buffers are its own.
+ *    One CUDA context per process (one process per GPU).
  *  - No CPU fallback: xggm_device_check() fails on anything but compute
  *    capability 10.x and the kernels exist only as sm_100a SASS.
  */
@@ -26,7 +30,7 @@
 extern "C" {
 #endif
 
-#define XGGM_ABI_VERSION 3
+#define XGGM_ABI_VERSION 4
 
 #define XGGM_OK 0
 #define XGGM_ERR_ARG (-1)         /* bad shape / NULL pointer / unsupported size */
@@ -312,6 +316,27 @@ int xggm_grad_sumsq(const float* g, long long n, float* sumsq, int accumulate, x
 int xggm_bertadam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double b1,
                        double b2, double eps, double weight_decay, const float* sumsq, double max_norm,
                        xggm_stream_t s);
+/* CUDA-graph-safe variant: the learning-rate schedule of optimization.py:28-55,176-191 is evaluated ON THE DEVICE
+ * from a device step counter, so a captured step keeps following warmup_linear / warmup_cosine / warmup_constant
+ * across replays.  lr_scheduled = lr * schedule(step_dev[0] / t_total, warmup) (t_total <= 0: lr unscheduled);
+ * with advance != 0 the launch also increments step_dev[0] after every CTA has read it (ticket_dev: a zero-
+ * initialised device word the library uses for that hand-shake; it is left at zero).  A parameter group that
+ * is updated in several calls (disjoint ranges, see xggm_b200.optim) sets advance on the last call only.
+ * n == 0 with advance != 0 only advances the counter.  sched == NULL: identical to xggm_bertadam_step. */
+#define XGGM_SCHED_COSINE 0
+#define XGGM_SCHED_CONSTANT 1
+#define XGGM_SCHED_LINEAR 2
+typedef struct {
+    long long* step_dev;        /* device int64: optimizer steps taken so far */
+    unsigned int* ticket_dev;   /* device uint32, zero between calls */
+    double warmup;              /* optimization.py: `warmup` (fraction of t_total) */
+    long long t_total;          /* optimization.py: `t_total` (-1 / 0: constant lr) */
+    int schedule;               /* XGGM_SCHED_* */
+    int advance;                /* != 0: step_dev[0] += 1 at the end of this launch */
+} xggm_lr_schedule_t;
+int xggm_bertadam_step_ex(float* p, const float* g, float* m, float* v, long long n, double lr, double b1,
+                          double b2, double eps, double weight_decay, const float* sumsq, double max_norm,
+                          const xggm_lr_schedule_t* sched, xggm_stream_t s);
 /* elementwise sigmoid (encoder_adj tail, src/vqa/vqacpv2_model.py:91-94) */
 int xggm_sigmoid_fwd(const float* x, float* y, long long n, xggm_stream_t s);
 int xggm_sigmoid_bwd(const float* gy, const float* y, float* gx, long long n, xggm_stream_t s);

@@ -209,6 +209,54 @@ def _branch(ggm, gu, loss_func, compute_kl_loss, which, gnn, hidden, B, seed, si
     return out
 
 
+def api_surface_case(ggm, seed=501, hidden=64, B=3, n_layers=2):
+    """the classes of ggm.py:15-159,272-323 no trainer builds, plus GCNConv(dropout>0) (gcn.py:28) and
+    GAT(merge != 'cat') (gat.py:76-77).  Each reference module is built under a seed, its own state_dict is
+    stored, and it runs forward + backward on shared inputs with injected dropout masks."""
+    import module.gcn as gcn_mod
+    import module.gat as gat_mod
+    N = 36
+    g = torch.Generator().manual_seed(seed)
+    visn, _, adj_true = O.make_inputs(seed + 1, B, N, hidden)
+    adj = O.strip_diag(adj_true) + 0.3 * torch.randn(B, N, N, generator=g)
+    out = {"x_in": _np(visn), "adj_in": _np(adj), "meta": np.array([seed, hidden, B, n_layers])}
+
+    def run(tag, mod, fn, n_masks, mask_shape, p=0.5):
+        torch.manual_seed(seed + len(tag))
+        for k_, v_ in mod.named_parameters():      # perturb the default init so LN / eps gradients are exercised
+            if v_.dim() == 1:
+                v_.data.add_(0.1 * torch.randn(v_.shape, generator=g))
+        mod.train()
+        masks = [(torch.rand(mask_shape, generator=g) >= p).to(torch.uint8) for _ in range(n_masks)]
+        x = visn.clone().requires_grad_(True)
+        a = adj.clone().requires_grad_(True)
+        y = _run_with_masks(lambda: fn(mod, x, a), masks, p)
+        c = torch.randn(y.shape, generator=g)
+        (y * c).sum().backward()
+        for k_, v_ in mod.state_dict().items():
+            out[f"{tag}/sd/{k_}"] = _np(v_)
+        for i, m in enumerate(masks):
+            out[f"{tag}/keep{i}"] = _np(m)
+        out[f"{tag}/c"] = _np(c)
+        out[f"{tag}/y"] = _np(y)
+        out[f"{tag}/gx"] = _np(x.grad if x.grad is not None else torch.zeros_like(x))
+        out[f"{tag}/gadj"] = _np(a.grad if a.grad is not None else torch.zeros_like(a))
+        for k_, v_ in mod.named_parameters():
+            out[f"{tag}/g/{k_}"] = _np(v_.grad if v_.grad is not None else torch.zeros_like(v_))
+
+    shape = (B, N, hidden)
+    run("edge_generator", ggm.EdgeGenerator(hidden, n_layers), lambda m, x, a: m(x, a), 2 * n_layers, shape)
+    run("node_generator", ggm.NodeGenerator(hidden, n_layers), lambda m, x, a: m(x, a), 2 * n_layers, shape)
+    run("gin_plain_encoder", ggm.GinPlainEncoder(hidden, n_layers), lambda m, x, a: m(x, a), 2 * n_layers, shape)
+    run("gcn_plain_encoder", ggm.GCNPlainEncoder(hidden, n_layers), lambda m, x, a: m(x, a), 2 * n_layers, shape)
+    # (the discriminators flatten their input; two node rows = 2*hidden features keep the fixture small)
+    run("discriminator", ggm.Discriminator(2 * hidden), lambda m, x, a: m(x[:, :2]), 0, shape)
+    run("discriminator_v2", ggm.DiscriminatorV2(2 * hidden), lambda m, x, a: m(x[:, :2]), 0, shape)
+    run("gcn_conv_dropout", gcn_mod.GCNConv(hidden, dropout=0.25), lambda m, x, a: m(x, a), 1, shape, p=0.25)
+    run("gat_mean", gat_mod.GAT(hidden, hidden, n_head=2, merge="mean"), lambda m, x, a: m(x, a).reshape(1), 1, shape)
+    return out
+
+
 def glue_case(gu, loss_func, compute_kl_loss, seed=7):
     g = torch.Generator().manual_seed(seed)
     a = torch.randn(3, 36, 36, generator=g)
@@ -321,6 +369,8 @@ def main():
         "branch_node_gcn_h64": lambda: _branch(ggm, gu, loss_func, compute_kl_loss, "node", "GCN", 64, 3, 202),
         "branch_node_gcn_h768": lambda: _branch(ggm, gu, loss_func, compute_kl_loss, "node", "GCN", 768, 2, 203),
         "branch_relation_gin_h64": lambda: _branch(ggm, gu, loss_func, compute_kl_loss, "relation", "GIN", 64, 3, 204),
+        "branch_relation_gcn_h768": lambda: _branch(ggm, gu, loss_func, compute_kl_loss, "relation", "GCN", 768, 2, 205),
+        "api_surface": lambda: api_surface_case(ggm),
         "glue": lambda: glue_case(gu, loss_func, compute_kl_loss),
         "visual_feat_train": lambda: visual_feat_case(301, 3, 768, True),
         "visual_feat_eval": lambda: visual_feat_case(302, 2, 768, False),

@@ -222,6 +222,58 @@ def gat_generator(x, adj, p, n_layers=1, keeps=None, drop_p=0.5, pre=""):
 
 
 # --------------------------------------------------------------------------
+# API-surface compositions no trainer builds: ggm.py:15-159
+# --------------------------------------------------------------------------
+def gcn_conv_dropout(x, adj, p, pre, keep, drop_p):
+    """GCNConv.forward with dropout > 0 on the projected aggregate, src/module/gcn.py:28."""
+    agg = affine(torch.bmm(adj, x), p[pre + "ctx_layer.weight"])
+    u = x + keep_scale(agg, keep, drop_p)
+    return row_norm(u, p[pre + "layer_norm.weight"], p[pre + "layer_norm.bias"])
+
+
+def gnn_stack(x, adj, p, kind, n_layers, keeps=None, drop_p=0.5, pre=""):
+    """GinPlainEncoder / GCNPlainEncoder / NodeGenerator.forward (ggm.py:27-40, 55-68, 146-159): n_layers x
+    GIN|GCN(n_layers=1) -- one conv + two read-out heads each -- applied in sequence with the SAME adjacency.
+    keeps[l][j]."""
+    layer = gin if kind == "GIN" else gcn
+    for l in range(n_layers):
+        x = layer(x, adj, p, f"{pre}gnn_layers.{l}.", 1, None if keeps is None else keeps[l], drop_p)
+    return x
+
+
+def edge_generator(x, adj, p, n_layers, keeps=None, drop_p=0.5, pre=""):
+    """EdgeGenerator.forward, ggm.py:115-130: GIN(n_layers=1) layers, adjacency regenerated WITHOUT the
+    sigmoid; returns the adjacency only."""
+    for l in range(n_layers):
+        x = gin(x, adj, p, f"{pre}gnn_layers.{l}.", 1, None if keeps is None else keeps[l], drop_p)
+        adj = adj_regen(x, squash=False)
+    return adj
+
+
+def discriminator(x, p, pre="model."):
+    """Discriminator.forward, ggm.py:71-82: Linear -> GeLU -> LayerNorm -> Linear on the flattened input."""
+    h = x.reshape(x.shape[0], -1)
+    h = row_norm(gelu_erf(affine(h, p[pre + "0.weight"], p[pre + "0.bias"])), p[pre + "2.weight"], p[pre + "2.bias"])
+    return affine(h, p[pre + "3.weight"], p[pre + "3.bias"])
+
+
+def discriminator_v2(x, p, pre="model."):
+    """DiscriminatorV2.forward, ggm.py:85-97."""
+    lrelu = torch.nn.functional.leaky_relu
+    h = x.reshape(x.shape[0], -1)
+    h = lrelu(affine(h, p[pre + "0.weight"], p[pre + "0.bias"]), 0.2)
+    h = lrelu(affine(h, p[pre + "2.weight"], p[pre + "2.bias"]), 0.2)
+    return affine(h, p[pre + "4.weight"], p[pre + "4.bias"])
+
+
+def gat_mean(x, adj, p, pre="", n_head=2, keep=None, drop_p=0.5):
+    """GAT.forward with merge != 'cat', src/module/gat.py:76-77: torch.mean over the STACK of head outputs --
+    a global scalar mean (all heads, graphs, nodes and features), as the reference computes it."""
+    x = keep_scale(x, keep, drop_p)
+    return torch.mean(torch.stack([gat_conv(x, adj, p, f"{pre}gat_layers.{h}.") for h in range(n_head)]))
+
+
+# --------------------------------------------------------------------------
 # noise + losses + trainer glue
 # --------------------------------------------------------------------------
 def edge_noise(adj, sigma, randn):

@@ -28,7 +28,7 @@ def test_library_builds_loads_and_exports_header_symbols():
         assert hasattr(lib, s), f"{s} declared in xggm_b200.h but not exported"
     # every declared entry point has a ctypes signature (argument-count drift is a bug)
     assert set(syms) == set(_lib.SIGNATURES), set(syms) ^ set(_lib.SIGNATURES)
-    assert lib.xggm_abi_version() == 3
+    assert lib.xggm_abi_version() == 4
     assert b"argument" in lib.xggm_strerror(-1)
     # 2 convs x (3 fp32 [M,H] + 2 [M] + 2 plane regions) + 3 heads x (z + mean + rstd) + P(x); M = 72
     assert lib.xggm_gnn_saved_floats(0, 2, 36, 768, 2) == 2 * (5 * 55296 + 144) + 3 * (55296 + 144) + 55296
@@ -136,8 +136,10 @@ def test_bertadam_host_logic_flat_layout_and_schedule():
         assert off_p == off_g and off_p % 32 == 0                           # same 128-byte aligned offsets
     assert opt.get_lr() == [0]
     for step in (0, 3, 5, 20, 49, 60):
-        grp.step = step
+        grp.step_dev.fill_(step)
+        assert grp.step == step
         assert grp.lr_scheduled() == O.scheduled_lr(1e-3, step, 50, 0.1)
+    grp.step_dev.fill_(0)
     for name, fn in SCHEDULES.items():
         for x in (0.0, 0.001, 0.3, 1.0, 1.2):
             assert fn(x, 0.25) == O.SCHEDULES[name](x, 0.25)
@@ -172,3 +174,76 @@ def test_operand_plane_record_is_dropped_when_the_tensor_changes():
     t.add_(1.0)                                          # in-place update bumps the version counter
     assert XF._planes_of(t) is None
     assert XF._new_planes(torch.zeros(2, 3, 10)) is None     # row length not a multiple of 8: producers emit nothing
+
+
+def test_flatgrads_survives_model_zero_grad_and_tracks_active_parameters():
+    """model.zero_grad() (set_to_none on torch >= 2) un-links every p.grad from the bucket; the next
+    backward then allocates gradients elsewhere.  relink() -- run by all_reduce() and BertAdam.step() -- copies
+    them into their slices and restores the link; strict mode raises.  active_ranges() lists the bucket ranges of
+    the parameters that received a gradient since zero_() (the reference optimiser skips p.grad is None)."""
+    import torch
+    from xggm_b200.ddp import FlatGrads
+    model = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2), torch.nn.Linear(2, 5))
+    fg = FlatGrads(model.parameters())
+    x = torch.randn(6, 4)
+    model[1](model[0](x)).sum().backward()                # the third layer takes no part
+    assert float(fg.flat.abs().sum()) > 0
+    used = sum(o2 - o1 for (o1, o2) in fg.active_ranges())
+    assert fg.active_ranges()[0][0] == 0 and used == fg.offsets[4]          # four tensors of the first two layers
+    ref = fg.flat.clone()
+    model.zero_grad()                                      # what the reference trainer calls (vqacpv2.py:170)
+    assert all(p.grad is None for p in model.parameters())
+    fg.zero_()
+    model[1](model[0](x)).sum().backward()
+    assert float(fg.flat.abs().sum()) == 0.0               # the gradients live outside the bucket now ...
+    with pytest.raises(RuntimeError, match="no longer points"):
+        fg.relink(strict=True)
+    assert fg.relink() == 6                                # ... until the link is repaired (all six were un-linked)
+    assert torch.equal(fg.flat, ref)
+    base = fg.flat.data_ptr()
+    for p, o in zip(fg.params, fg.offsets):
+        assert p.grad.data_ptr() == base + 4 * o
+    assert sum(o2 - o1 for (o1, o2) in fg.active_ranges()) == used          # the unused layer stays inactive
+    assert fg.relink() == 0
+    fg.zero_()
+    assert fg.active_ranges() == [(0, fg.flat.numel())]    # nothing reported: everything counts as active
+
+
+def test_fused_grad_accumulation_is_opt_in():
+    """only parameters registered with a FlatGrads may be accumulated into in place."""
+    import torch
+    import xggm_b200.functional as XF
+    from xggm_b200.ddp import FlatGrads
+    p = torch.nn.Parameter(torch.randn(3, 3))
+    p.grad = torch.zeros(3, 3)
+    assert XF._grad_target(p) is None                      # a dense .grad alone is not consent
+    fg = FlatGrads([p])
+    assert XF._grad_target(p) is p.grad
+    p.grad = torch.zeros(3, 3)                             # un-linked from the bucket
+    assert XF._grad_target(p) is None
+    fg.relink()
+    XF.FUSE_GRAD_ACCUMULATION = False
+    try:
+        assert XF._grad_target(p) is None
+    finally:
+        XF.FUSE_GRAD_ACCUMULATION = True
+
+
+def test_bertadam_state_dict_round_trip():
+    import torch
+    from xggm_b200.optim import BertAdam
+    ps = [torch.nn.Parameter(torch.randn(5, 7)), torch.nn.Parameter(torch.randn(3))]
+    opt = BertAdam(ps, lr=1e-3, warmup=0.1, t_total=50)
+    g = opt.groups[0]
+    g.m.normal_(); g.v.uniform_(); g.step_dev.fill_(7)
+    sd = opt.state_dict()
+    assert set(sd) == {"state", "param_groups"} and sd["state"][0]["step"] == 7
+    assert sd["state"][0]["next_m"].shape == (5, 7) and sd["param_groups"][0]["params"] == [0, 1]
+    ps2 = [torch.nn.Parameter(torch.randn(5, 7)), torch.nn.Parameter(torch.randn(3))]
+    opt2 = BertAdam(ps2, lr=5e-4)
+    opt2.load_state_dict(sd)
+    g2 = opt2.groups[0]
+    for p, o in zip(g2.params, g2.grads.offsets):
+        n = p.numel()
+        assert torch.equal(g2.m[o:o + n], g.m[o:o + n]) and torch.equal(g2.v[o:o + n], g.v[o:o + n])
+    assert g2.step == 7 and g2.opts["lr"] == 1e-3 and g2.opts["t_total"] == 50

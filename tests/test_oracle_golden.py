@@ -73,7 +73,8 @@ def test_generator_matches_reference(name, gnn):
 BRANCH_CASES = [("branch_relation_gcn_h64", "relation", "GCN"),
                 ("branch_node_gcn_h64", "node", "GCN"),
                 ("branch_node_gcn_h768", "node", "GCN"),
-                ("branch_relation_gin_h64", "relation", "GIN")]
+                ("branch_relation_gin_h64", "relation", "GIN"),
+                ("branch_relation_gcn_h768", "relation", "GCN")]
 
 
 @pytest.mark.parametrize("name,which,gnn", BRANCH_CASES)
@@ -177,3 +178,61 @@ def test_optimizer_tail_oracle_matches_reference_fixture():
     loss.backward()
     assert abs(float(loss) - float(g["bce/loss"][0])) <= 1e-5 * abs(float(g["bce/loss"][0]))
     assert rel_l2(x.grad, g["bce/glogit"]) < 1e-5
+
+
+# ---------------------------------------------------------------------------- SURVEY 8 a-18
+API_CASES = ["edge_generator", "node_generator", "gin_plain_encoder", "gcn_plain_encoder", "discriminator",
+             "discriminator_v2", "gcn_conv_dropout", "gat_mean"]
+
+
+def api_surface_oracle(tag, gold, dtype=torch.float32):
+    """Run the oracle's restatement of one API-surface class on the fixture's inputs, weights and masks.
+    Returns (y, x, adj, params) with gradients populated for cotangent gold[tag/c]."""
+    seed, hidden, B, n_layers = [int(v) for v in gold["meta"]]
+    p = {k[len(tag) + 4:]: _t(v).to(dtype).requires_grad_(True) for k, v in gold.items() if k.startswith(tag + "/sd/")}
+    x = _t(gold["x_in"]).to(dtype).requires_grad_(True)
+    adj = _t(gold["adj_in"]).to(dtype).requires_grad_(True)
+    masks = []
+    while f"{tag}/keep{len(masks)}" in gold:
+        masks.append(_t(gold[f"{tag}/keep{len(masks)}"]))
+    keeps = [masks[2 * l:2 * l + 2] for l in range(n_layers)]
+    if tag == "edge_generator":
+        y = O.edge_generator(x, adj, p, n_layers, keeps)
+    elif tag in ("node_generator", "gin_plain_encoder"):
+        y = O.gnn_stack(x, adj, p, "GIN", n_layers, keeps)
+    elif tag == "gcn_plain_encoder":
+        y = O.gnn_stack(x, adj, p, "GCN", n_layers, keeps)
+    elif tag == "discriminator":
+        y = O.discriminator(x[:, :2], p)
+    elif tag == "discriminator_v2":
+        y = O.discriminator_v2(x[:, :2], p)
+    elif tag == "gcn_conv_dropout":
+        y = O.gcn_conv_dropout(x, adj, p, "", masks[0], 0.25)
+    elif tag == "gat_mean":
+        y = O.gat_mean(x, adj, p, "", 2, masks[0]).reshape(1)
+    else:
+        raise KeyError(tag)
+    (y * _t(gold[tag + "/c"]).to(dtype)).sum().backward()
+    return y, x, adj, p
+
+
+@pytest.mark.parametrize("tag", API_CASES)
+def test_api_surface_matches_reference(tag):
+    gold = load_golden("api_surface")
+    y, x, adj, p = api_surface_oracle(tag, gold)
+    assert rel_l2(y, gold[tag + "/y"]) < TOL
+    assert rel_l2(x.grad, gold[tag + "/gx"]) < 5 * TOL
+    if np.abs(gold[tag + "/gadj"]).max() > 0:
+        assert rel_l2(adj.grad, gold[tag + "/gadj"]) < 5 * TOL
+    else:
+        assert adj.grad is None or float(adj.grad.abs().max()) == 0.0
+    n = 0
+    for k, v in p.items():
+        ref = gold[f"{tag}/g/{k}"]
+        g = v.grad if v.grad is not None else torch.zeros_like(v)
+        if np.abs(ref).max() == 0:
+            assert float(g.abs().max()) == 0.0, k
+        else:
+            assert rel_l2(g, ref) < 10 * TOL, k
+        n += 1
+    assert n == sum(1 for k in gold if k.startswith(tag + "/g/"))

@@ -76,6 +76,7 @@ SIGNATURES = {
     "xggm_bce_logits_bwd": [_vp, _vp, _vp, _d, _vp, _ll, _vp],
     "xggm_grad_sumsq": [_vp, _ll, _vp, _i, _vp],
     "xggm_bertadam_step": [_vp, _vp, _vp, _vp, _ll, _d, _d, _d, _d, _d, _vp, _d, _vp],
+    "xggm_bertadam_step_ex": [_vp, _vp, _vp, _vp, _ll, _d, _d, _d, _d, _d, _vp, _d, _vp, _vp],
     "xggm_sigmoid_fwd": [_vp, _vp, _ll, _vp],
     "xggm_sigmoid_bwd": [_vp, _vp, _vp, _ll, _vp],
     "xggm_keep_mask": [_vp, _ll, _f, _u64, _u64, _vp, _vp],
@@ -83,6 +84,7 @@ SIGNATURES = {
 _RESTYPES = {"xggm_launch_count": C.c_ulonglong, "xggm_strerror": C.c_char_p, "xggm_last_cuda_error": C.c_char_p,
              "xggm_planes_bytes": _ll, "xggm_gnn_saved_floats": _ll, "xggm_gnn_work_floats": _ll, "xggm_linear_work_bytes": _ll, "xggm_adj_regen_work_bytes": _ll, "xggm_adj_apply_work_bytes": _ll}
 
+ABI_VERSION = 4
 _lib = None
 _checked_devices = set()
 
@@ -120,7 +122,7 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
-    if lib.xggm_abi_version() != 3:
+    if lib.xggm_abi_version() != ABI_VERSION:
         raise RuntimeError("libxggm_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib
@@ -129,6 +131,12 @@ def load():
 class PhiloxSpec(C.Structure):
     """xggm_philox_t of include/xggm_b200.h."""
     _fields_ = [("seed", C.c_uint64), ("stream0", C.c_uint64), ("dev_epoch", C.c_void_p)]
+
+
+class LrSchedule(C.Structure):
+    """xggm_lr_schedule_t of include/xggm_b200.h."""
+    _fields_ = [("step_dev", C.c_void_p), ("ticket_dev", C.c_void_p), ("warmup", C.c_double),
+                ("t_total", C.c_longlong), ("schedule", C.c_int), ("advance", C.c_int)]
 
 
 PRECISIONS = {"fp32": 0, "bf16": 1, "fp32_simt": 2}
@@ -160,6 +168,10 @@ def check_device(t):
     if not t.is_cuda:
         raise RuntimeError("xggm_b200: tensors must live on a CUDA (B200) device; there is no CPU path")
     idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if idx != torch.cuda.current_device():
+        # the call would enqueue on the CURRENT device's stream with another device's pointers
+        raise RuntimeError(f"xggm_b200: tensor lives on cuda:{idx} but the current device is "
+                           f"cuda:{torch.cuda.current_device()}; wrap the call in torch.cuda.device({idx})")
     if idx not in _checked_devices:
         rc = load().xggm_device_check(idx)
         if rc != 0:

@@ -13,7 +13,7 @@ namespace xggm {
 
 // ---- error state -------------------------------------------------------------
 static thread_local char g_cuda_err[256] = "";
-unsigned long long g_kernel_launches = 0;
+std::atomic<unsigned long long> g_kernel_launches{0};
 void set_cuda_error(cudaError_t e, const char* where) {
     snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", cudaGetErrorName(e), cudaGetErrorString(e), where);
 }
@@ -540,7 +540,7 @@ int xggm_prof_read(double* total_ms, long long* launches, double* flops) {
     XGGM_REQUIRE(total_ms && launches && flops);
     return gemm_prof_read(total_ms, launches, flops);
 }
-unsigned long long xggm_launch_count(void) { return g_kernel_launches; }
+unsigned long long xggm_launch_count(void) { return g_kernel_launches.load(); }
 
 int xggm_set_device(int device) {
     XGGM_CUDA_TRY(cudaSetDevice(device));
@@ -951,7 +951,14 @@ int xggm_bertadam_step(float* p, const float* g, float* m, float* v, long long n
                        xggm_stream_t s) {
     if (n == 0) return XGGM_OK;
     XGGM_REQUIRE(p && g && m && v && n >= 0 && b1 >= 0.0 && b1 < 1.0 && b2 >= 0.0 && b2 < 1.0 && eps >= 0.0);
-    return bertadam_step(p, g, m, v, n, lr, b1, b2, eps, weight_decay, sumsq, max_norm, as_stream(s));
+    return bertadam_step(p, g, m, v, n, lr, b1, b2, eps, weight_decay, sumsq, max_norm, nullptr, as_stream(s));
+}
+int xggm_bertadam_step_ex(float* p, const float* g, float* m, float* v, long long n, double lr, double b1,
+                          double b2, double eps, double weight_decay, const float* sumsq, double max_norm,
+                          const xggm_lr_schedule_t* sched, xggm_stream_t s) {
+    if (n == 0 && !(sched && sched->advance)) return XGGM_OK;
+    XGGM_REQUIRE(n >= 0 && (n == 0 || (p && g && m && v)) && b1 >= 0.0 && b1 < 1.0 && b2 >= 0.0 && b2 < 1.0 && eps >= 0.0);
+    return bertadam_step(p, g, m, v, n, lr, b1, b2, eps, weight_decay, sumsq, max_norm, sched, as_stream(s));
 }
 int xggm_sigmoid_fwd(const float* x, float* y, long long n, xggm_stream_t s) {
     if (n == 0) return XGGM_OK;

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include <atomic>
 
 #include "../../include/xggm_b200.h"
 
@@ -22,7 +23,7 @@ void set_cuda_error(cudaError_t e, const char* where);
         }                                                     \
     } while (0)
 // one XGGM_LAUNCH_CHECK per kernel launch: also feeds xggm_launch_count()
-extern unsigned long long g_kernel_launches;
+extern std::atomic<unsigned long long> g_kernel_launches;
 #define XGGM_LAUNCH_CHECK()                  \
     do {                                     \
         ++::xggm::g_kernel_launches;         \

@@ -94,7 +94,7 @@ int bce_logits_fwd(const float* x, const float* t, float scale, float* loss, lon
 int bce_logits_bwd(const float* x, const float* t, const float* gloss, float scale, float* gx, long long n, cudaStream_t st);
 int grad_sumsq(const float* g, long long n, float* out, int accumulate, cudaStream_t st);
 int bertadam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double b1, double b2, double eps,
-                  double wd, const float* sumsq, double max_norm, cudaStream_t st);
+                  double wd, const float* sumsq, double max_norm, const xggm_lr_schedule_t* sched, cudaStream_t st);
 int sigmoid_fwd(const float*, float*, long long, cudaStream_t);
 int sigmoid_bwd(const float*, const float*, float*, long long, cudaStream_t);
 int keep_mask(uint8_t*, long long, float, uint64_t, uint64_t, const uint64_t*, cudaStream_t);

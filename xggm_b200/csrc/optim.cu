@@ -104,14 +104,30 @@ int grad_sumsq(const float* g, long long n, float* out, int accumulate, cudaStre
 struct AdamArgs {
     float lr, b1, one_b1, b2, one_b2, eps, wd, max_norm;
     const float* sumsq;   // device scalar: squared norm of ALL gradients being clipped together, or null
+    // device-side schedule (CUDA-graph-safe steps): lr is multiplied by schedule(step / t_total, warmup) with `step`
+    // read from the device counter; with `advance` the LAST CTA of the grid increments the counter (every CTA has read
+    // it before taking its ticket, so the increment cannot race with a read of the same launch)
+    long long* step_dev;
+    unsigned int* ticket;
+    double warmup;
+    long long t_total;
+    int schedule, advance;
 };
-__device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, const AdamArgs& a, float clip) {
+// src/lxrt/optimization.py:28-49 (x = step / t_total)
+__device__ __forceinline__ double schedule_factor(int schedule, double x, double warmup) {
+    if (x < warmup) return x / warmup;
+    if (schedule == XGGM_SCHED_COSINE) return 0.5 * (1.0 + cos(3.14159265358979323846 * x));
+    if (schedule == XGGM_SCHED_CONSTANT) return 1.0;
+    const double l = (x - 1.0) / (warmup - 1.0);
+    return l > 0.0 ? l : 0.0;
+}
+__device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, const AdamArgs& a, float lr, float clip) {
     g *= clip;
     m = m * a.b1 + a.one_b1 * g;
     v = v * a.b2 + a.one_b2 * (g * g);
     float upd = m / (sqrtf(v) + a.eps);
     if (a.wd > 0.f) upd += a.wd * p;
-    p -= a.lr * upd;
+    p -= lr * upd;
 }
 __global__ void __launch_bounds__(256)
 bertadam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
@@ -121,6 +137,11 @@ bertadam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __res
     if (a.sumsq && a.max_norm > 0.f) {
         const float c = a.max_norm / (sqrtf(a.sumsq[0]) + 1e-6f);
         clip = c < 1.f ? c : 1.f;
+    }
+    float lr = a.lr;
+    if (a.step_dev && a.t_total > 0) {
+        const long long step = *reinterpret_cast<volatile long long*>(a.step_dev);
+        lr = (float)((double)a.lr * schedule_factor(a.schedule, (double)step / (double)a.t_total, a.warmup));
     }
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
     long long done = 0;
@@ -133,21 +154,42 @@ bertadam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __res
         for (long long i = tid; i < n4; i += nth) {
             float4 pv = p4[i], mv = m4[i], vv = v4[i];
             const float4 gv = g4[i];
-            adam1(pv.x, gv.x, mv.x, vv.x, a, clip);
-            adam1(pv.y, gv.y, mv.y, vv.y, a, clip);
-            adam1(pv.z, gv.z, mv.z, vv.z, a, clip);
-            adam1(pv.w, gv.w, mv.w, vv.w, a, clip);
+            adam1(pv.x, gv.x, mv.x, vv.x, a, lr, clip);
+            adam1(pv.y, gv.y, mv.y, vv.y, a, lr, clip);
+            adam1(pv.z, gv.z, mv.z, vv.z, a, lr, clip);
+            adam1(pv.w, gv.w, mv.w, vv.w, a, lr, clip);
             p4[i] = pv; m4[i] = mv; v4[i] = vv;
         }
         done = n4 << 2;
     }
-    for (long long i = done + tid; i < n; i += nth) adam1(p[i], g[i], m[i], v[i], a, clip);
+    for (long long i = done + tid; i < n; i += nth) adam1(p[i], g[i], m[i], v[i], a, lr, clip);
+    if (a.step_dev && a.advance) {
+        __syncthreads();                       // every thread of this CTA has read the counter
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(a.ticket, 1u) == gridDim.x - 1) {
+                *a.step_dev += 1;
+                *a.ticket = 0u;
+                __threadfence();
+            }
+        }
+    }
 }
 int bertadam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double b1, double b2,
-                  double eps, double wd, const float* sumsq, double max_norm, cudaStream_t st) {
-    if (n <= 0) return XGGM_OK;
-    const AdamArgs a{(float)lr, (float)b1, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2), (float)eps, (float)wd,
-                     (float)max_norm, sumsq};
+                  double eps, double wd, const float* sumsq, double max_norm, const xggm_lr_schedule_t* sched,
+                  cudaStream_t st) {
+    if (n <= 0 && !(sched && sched->advance)) return XGGM_OK;
+    AdamArgs a{(float)lr, (float)b1, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2), (float)eps, (float)wd,
+               (float)max_norm, sumsq, nullptr, nullptr, 0.0, 0, 0, 0};
+    if (sched) {
+        XGGM_REQUIRE(sched->step_dev && sched->ticket_dev && sched->schedule >= 0 && sched->schedule <= 2);
+        a.step_dev = sched->step_dev;
+        a.ticket = sched->ticket_dev;
+        a.warmup = sched->warmup;
+        a.t_total = sched->t_total;
+        a.schedule = sched->schedule;
+        a.advance = sched->advance;
+    }
     const int vec = aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v);
     XGGM_LAUNCH((bertadam_kernel), stream_grid(n, 2048), 256, 0, st, p, g, m, v, n, a, vec);
     XGGM_LAUNCH_CHECK();

@@ -49,14 +49,70 @@ class FlatGrads:
             if id(p) in early_ids:
                 self.split = off
         self.flat = torch.zeros(off, device=p0.device, dtype=p0.dtype)
+        self.offsets = offs
         for p, o in zip(self.params, offs):
             p.grad = self.flat[o:o + p.numel()].view_as(p)
+            # opt-in marker for functional.FUSE_GRAD_ACCUMULATION: only parameters registered here may have
+            # their gradients accumulated in place by the backward kernels
+            p._xggm_flat = self
+            if hasattr(p, "register_post_accumulate_grad_hook"):   # gradients that arrive through autograd itself
+                p.register_post_accumulate_grad_hook(lambda q, self=self: self.touch(q))
+        self._touched = set()
         self._side = None
         self._early_in_flight = False
         self._average = True
 
     def zero_(self):
+        """Zero the bucket (use this, or ``BertAdam.zero_grad()``, instead of ``model.zero_grad()``: the latter
+        sets every ``p.grad`` to None on torch >= 2 and un-links the parameters from the bucket; ``relink()``
+        -- called by ``all_reduce`` and ``BertAdam.step`` -- repairs that, at the price of a copy)."""
         self.flat.zero_()
+        self._touched.clear()
+
+    # -- which parameters received a gradient since the last zero_() ------------------------------------
+    def touch(self, p):
+        self._touched.add(id(p))
+
+    def active_ranges(self):
+        """Contiguous [lo, hi) element ranges of the bucket that belong to parameters whose gradient was
+        written since the last ``zero_()`` (the reference optimiser skips parameters whose ``.grad`` is None,
+        src/lxrt/optimization.py:139-141: e.g. ``encoder_adj`` in a node-branch step).  If nothing was reported
+        (gradients written by other means) every parameter counts as active."""
+        if not self._touched:
+            return [(0, self.flat.numel())]
+        ranges = []
+        for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+            if id(p) not in self._touched:
+                continue
+            hi = self.offsets[i + 1] if i + 1 < len(self.params) else self.flat.numel()
+            if ranges and ranges[-1][1] == o:
+                ranges[-1] = (ranges[-1][0], hi)
+            else:
+                ranges.append((o, hi))
+        return ranges
+
+    def relink(self, strict=False):
+        """Make sure every ``p.grad`` is still its slice of the bucket.  ``model.zero_grad()`` (set_to_none) or
+        code that assigns ``p.grad`` breaks the link: the next backward then allocates gradients OUTSIDE the
+        bucket and the all-reduce / optimiser would silently read stale zeros.  Stray gradients are copied into
+        their slice and the link is restored (``strict=True`` raises instead).  Returns the number of repairs."""
+        base, esz, fixed = self.flat.data_ptr(), self.flat.element_size(), 0
+        for p, o in zip(self.params, self.offsets):
+            g = p.grad
+            want = base + o * esz
+            if g is not None and g.data_ptr() == want and g.shape == p.shape and g.is_contiguous():
+                continue
+            if strict:
+                raise RuntimeError("xggm_b200.FlatGrads: a parameter's .grad no longer points into the flat bucket "
+                                   "(model.zero_grad() sets it to None on torch >= 2); use FlatGrads.zero_() / "
+                                   "BertAdam.zero_grad(), or call relink()")
+            view = self.flat[o:o + p.numel()].view_as(p)
+            if g is not None:
+                view.copy_(g)
+                self.touch(p)
+            p.grad = view
+            fixed += 1
+        return fixed
 
     @staticmethod
     def _distributed():
@@ -88,6 +144,7 @@ class FlatGrads:
     def all_reduce(self, average=True):
         """Sum (or average) the gradients over all ranks: one collective, or -- when ``reduce_early()`` already
         shipped the first bucket during the backward pass -- the remaining bucket plus a join."""
+        self.relink()
         if not self._distributed():
             return self.flat
         if self._early_in_flight:

@@ -15,20 +15,30 @@ from ._lib import call, f32, ptr, ptr_table
 LN_EPS = 1e-5
 KIND = {"GCN": 0, "GIN": 1}
 
-# When a leaf parameter already owns a dense fp32 ``.grad`` buffer (e.g. a slice of
-# ``xggm_b200.ddp.FlatGrads``), the backward kernels accumulate into it directly and the autograd
-# Function returns None for that parameter: no temporary gradient, no extra add kernel.  Set to
-# False if something must observe parameter gradients through autograd hooks (torch DDP does).
+# OPT-IN in-place gradient accumulation: when a leaf parameter has been registered with an
+# ``xggm_b200.ddp.FlatGrads`` bucket (which tags it ``_xggm_flat``) and its ``.grad`` still is that bucket's
+# slice, the backward kernels accumulate into the slice directly and the autograd Function returns None for
+# the parameter: no temporary gradient, no extra add kernel.  Parameters that were NOT registered always get
+# their gradients through autograd (hooks, torch.autograd.grad, torch DDP's reducer keep working).  For the
+# registered ones ``loss.backward()`` is the supported entry; ``torch.autograd.grad`` w.r.t. them returns None
+# -- set this flag to False around such calls.
 FUSE_GRAD_ACCUMULATION = True
 
 
 def _grad_target(p):
-    """The live .grad buffer of ``p`` if the kernels may accumulate into it, else None."""
+    """The live .grad slice of ``p`` if the kernels may accumulate into it, else None."""
     if not FUSE_GRAD_ACCUMULATION or not getattr(p, "is_leaf", False) or not p.requires_grad:
+        return None
+    flat = getattr(p, "_xggm_flat", None)
+    if flat is None:
         return None
     g = p.grad
     if g is None or g.dtype != torch.float32 or g.device != p.device or g.shape != p.shape or not g.is_contiguous():
         return None
+    lo = flat.flat.data_ptr()
+    if not (lo <= g.data_ptr() < lo + flat.flat.numel() * flat.flat.element_size()):
+        return None     # un-linked (model.zero_grad()): autograd allocates, FlatGrads.relink() repairs later
+    flat.touch(p)
     return g
 
 

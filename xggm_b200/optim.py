@@ -14,6 +14,7 @@ and a step is one gradient-norm reduction plus one update kernel per group (``xg
 the squared norm as a device scalar and the update kernel applies min(1, max_norm / (norm + 1e-6)) on the fly,
 so the step needs no host synchronisation and can be captured in a CUDA graph.
 """
+import ctypes as C
 import math
 
 import torch
@@ -36,6 +37,7 @@ def warmup_linear(x, warmup=0.002):
 
 
 SCHEDULES = {"warmup_cosine": warmup_cosine, "warmup_constant": warmup_constant, "warmup_linear": warmup_linear}
+_SCHED_ID = {"warmup_cosine": 0, "warmup_constant": 1, "warmup_linear": 2}   # XGGM_SCHED_* of include/xggm_b200.h
 
 
 class _Group:
@@ -54,13 +56,22 @@ class _Group:
             p.data = view
         self.m = torch.zeros_like(g)
         self.v = torch.zeros_like(g)
-        self.step = 0
+        # the step counter lives on the device (the update kernel evaluates the schedule from it and advances it,
+        # so a CUDA-graph replay keeps following the schedule); `_ticket` is the kernel's hand-shake word
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=g.device)
+        self._ticket = torch.zeros(1, dtype=torch.int32, device=g.device)
 
-    def lr_scheduled(self):
+    @property
+    def step(self):
+        """Optimizer steps taken so far (reads the device counter: synchronises)."""
+        return int(self.step_dev.item())
+
+    def lr_scheduled(self, step=None):
         o = self.opts
         if o["t_total"] == -1:
             return o["lr"]
-        return o["lr"] * SCHEDULES[o["schedule"]](self.step / o["t_total"], o["warmup"])
+        step = self.step if step is None else step
+        return o["lr"] * SCHEDULES[o["schedule"]](step / o["t_total"], o["warmup"])
 
 
 class BertAdam:
@@ -112,26 +123,75 @@ class BertAdam:
 
     def get_lr(self):
         """Scheduled learning rate of the NEXT step, one entry per parameter ([0] before the first step, as the
-        reference does)."""
-        if all(g.step == 0 for g in self.groups):
+        reference does).  Reads the device step counters (synchronises)."""
+        steps = [g.step for g in self.groups]
+        if all(s == 0 for s in steps):
             return [0]
-        return [g.lr_scheduled() for g in self.groups for _ in g.params]
+        return [g.lr_scheduled(s) for g, s in zip(self.groups, steps) for _ in g.params]
 
     def zero_grad(self):
+        """Zero the gradient buckets (keeps every ``p.grad`` linked; see ``FlatGrads.zero_``)."""
         for g in self.groups:
             g.grads.zero_()
 
     def step(self, clip=None):
         """One update of every group.  ``clip``: the handle returned by ``clip_grad_norm_`` (squared total
-        gradient norm on the device + max_norm), applied inside the update kernel; None = no clipping."""
+        gradient norm on the device + max_norm), applied inside the update kernel; None = no clipping.
+
+        The learning-rate schedule is evaluated inside the kernel from a DEVICE step counter that the kernel
+        advances, so the call is CUDA-graph capturable with any schedule (a host-computed lr would be baked into
+        the capture).  As in the reference (src/lxrt/optimization.py:139-141, ``if p.grad is None: continue``)
+        parameters that received no gradient since the last ``zero_grad()`` are left untouched -- no moment
+        decay, no weight decay: the update runs over the bucket's active ranges only."""
         sumsq, max_norm = (None, 0.0) if clip is None else (clip.sumsq, clip.max_norm)
         for g in self.groups:
             o = g.opts
             _lib.check_device(g.flat_p)
-            call("xggm_bertadam_step", ptr(g.flat_p), ptr(g.grads.flat), ptr(g.m), ptr(g.v), g.flat_p.numel(),
-                 float(g.lr_scheduled()), float(o["b1"]), float(o["b2"]), float(o["e"]), float(o["weight_decay"]),
-                 ptr(sumsq), float(max_norm))
-            g.step += 1
+            g.grads.relink()
+            ranges = g.grads.active_ranges()
+            for i, (lo, hi) in enumerate(ranges):
+                sched = _lib.LrSchedule(g.step_dev.data_ptr(), g._ticket.data_ptr(), float(o["warmup"]),
+                                        int(o["t_total"]), _SCHED_ID[o["schedule"]], int(i == len(ranges) - 1))
+                call("xggm_bertadam_step_ex", ptr(g.flat_p[lo:hi]), ptr(g.grads.flat[lo:hi]), ptr(g.m[lo:hi]),
+                     ptr(g.v[lo:hi]), hi - lo, float(o["lr"]), float(o["b1"]), float(o["b2"]), float(o["e"]),
+                     float(o["weight_decay"]), ptr(sumsq), float(max_norm), C.cast(C.pointer(sched), C.c_void_p))
+
+    # -- checkpointing (the reference trainers do not save optimiser state, SURVEY section 5; torch-style layout) ----
+    def state_dict(self):
+        """``{"state": {index: {"step", "next_m", "next_v"}}, "param_groups": [...]}`` with the reference's state
+        keys (src/lxrt/optimization.py:146-152); parameter indices run over the groups in order."""
+        state, groups, idx = {}, [], 0
+        for g in self.groups:
+            step = g.step
+            ids = []
+            for p, o in zip(g.params, g.grads.offsets):
+                n = p.numel()
+                state[idx] = {"step": step, "next_m": g.m[o:o + n].view_as(p).clone(),
+                              "next_v": g.v[o:o + n].view_as(p).clone()}
+                ids.append(idx)
+                idx += 1
+            groups.append(dict(g.opts, params=ids))
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd):
+        idx = 0
+        if len(sd["param_groups"]) != len(self.groups):
+            raise ValueError("loaded state dict has a different number of parameter groups")
+        for g, saved in zip(self.groups, sd["param_groups"]):
+            if len(saved["params"]) != len(g.params):
+                raise ValueError("loaded state dict contains a parameter group that doesn't match the size of "
+                                 "optimizer's group")
+            g.opts.update({k: v for k, v in saved.items() if k != "params"})
+            step = 0
+            for p, o in zip(g.params, g.grads.offsets):
+                st = sd["state"].get(idx, sd["state"].get(str(idx)))
+                if st is not None:
+                    n = p.numel()
+                    g.m[o:o + n].copy_(st["next_m"].reshape(-1))
+                    g.v[o:o + n].copy_(st["next_v"].reshape(-1))
+                    step = max(step, int(st["step"]))
+                idx += 1
+            g.step_dev.fill_(step)
 
 
 class GradClip:
