@@ -114,47 +114,56 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------- CPU baseline
-def cpu_reference_steps(steps, warmup, threads, B=CPU_SAMPLE_B, branch="node"):
-    """The reference's PyTorch CPU path for the same step, restated in oracle/ (the reference tree
-    does not exist on the GPU box).  Returns seconds per step (median)."""
-    from oracle import xggm_oracle as O
+# ------------------------------------------------------------------------------- CPU / eager baselines
+def _cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_reference_steps(steps, warmup, threads, B=CPU_SAMPLE_B, branch="node", gnn=GNN):
+    """The reference's PyTorch CPU path for the same step: the UNMODIFIED reference modules vendored into
+    oracle/_ref by oracle/vendor_ref.py (kind "reference"), else the oracle port (kind "port").
+    Returns (seconds per step (median), kind)."""
+    from oracle.ref_step import ReferenceStep
     torch.set_num_threads(threads)
-    p = O.make_params(9595, GNN, HID, N_LAYERS, N_NODES, heads=True)
-    for v in p.values():
-        v.requires_grad_(True)
-    mom = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in p.items()}
-    visn, xp, adj_true = O.make_inputs(9596, B, N_NODES, HID)
-    g = torch.Generator().manual_seed(1)
-    c = torch.randn(B, HID, generator=g)
+    ref = ReferenceStep("cpu", B, branch, gnn, HID, N_LAYERS, N_NODES, SIGMA, NUM_ANS, lr=4e-6)
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        x = xp.clone().requires_grad_(True)
-        feat = visn.clone().requires_grad_(True)
-        keeps = [[(torch.rand(B, N_NODES, HID) >= 0.5) for _ in range(3)] for _ in range(N_LAYERS)]  # F.dropout's bernoulli
-        if branch == "relation":
-            randn = torch.randn(B, N_NODES, N_NODES)
-            x_gen, loss_sm, _, _ = O.relation_branch(x, feat, adj_true, p, SIGMA, randn, keeps, NUM_ANS, GNN, N_LAYERS, 12.0)
-            ((x_gen * c).sum() + 6.0 * loss_sm).backward()
-        else:
-            randn = torch.randn(B, N_NODES, HID)
-            x_gen, loss_sm, _, _ = O.node_branch(x, feat, adj_true, p, SIGMA, randn, keeps, NUM_ANS, GNN, N_LAYERS)
-            ((x_gen * c).sum() + 1.1 * loss_sm).backward()
-        # clip_grad_norm_(., 5.) + BertAdam.step, per tensor as the reference does (src/lxrt/optimization.py:139-193)
-        live = [k for k, v in p.items() if v.grad is not None]
-        _, coef = O.clip_coef([p[k].grad for k in live], 5.0)
-        with torch.no_grad():
-            for k in live:
-                new_p, m, v2 = O.bertadam_step(p[k], p[k].grad * coef, mom[k][0], mom[k][1], 4e-6)
-                p[k].copy_(new_p)
-                mom[k] = (m, v2)
-        for v in p.values():
-            v.grad = None
+        ref.step()
         if it >= warmup:
             times.append(time.perf_counter() - t0)
     times.sort()
-    return times[len(times) // 2]
+    return times[len(times) // 2], ref.kind
+
+
+def eager_gpu_steps(dev, steps, warmup, B, branch="node", gnn=GNN):
+    """The reference's eager PyTorch path ON THE B200 (SURVEY 2a / BASELINE.md section 1, bar (i)): same modules, same
+    step, device cuda, true fp32 (allow_tf32 off -- the torch default the reference runs with), CUDA-event timed.
+    Returns (ms per step, kind)."""
+    from oracle.ref_step import ReferenceStep
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = ReferenceStep(dev, B, branch, gnn, HID, N_LAYERS, N_NODES, SIGMA, NUM_ANS, lr=4e-6)
+        for _ in range(warmup):
+            ref.step()
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for s_, e_ in evs:
+            s_.record()
+            ref.step()
+            e_.record()
+        torch.cuda.synchronize()
+        return sum(s_.elapsed_time(e_) for s_, e_ in evs) / steps, ref.kind
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
 
 
 def run_reference(args):
@@ -162,14 +171,26 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sec = cpu_reference_steps(args.steps, args.warmup, threads, branch=args.branch)
+    sec, kind = cpu_reference_steps(args.steps, args.warmup, threads, branch=args.branch, gnn=args.gnn)
     val = CPU_SAMPLE_B / sec
-    sample = f"B={CPU_SAMPLE_B} graphs per step (bounded sample of the B={B_PER_GPU} workload), {args.steps} steps"
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus,
+    other = "relation" if args.branch == "node" else "node"
+    sec_other, _ = cpu_reference_steps(3, 1, threads, branch=other, gnn=args.gnn)
+    sec_1t, _ = cpu_reference_steps(2, 1, 1, branch=args.branch, gnn=args.gnn)
+    sample = (f"B={CPU_SAMPLE_B} graphs per step (BASELINE configs[0]; a bounded sample of the B={B_PER_GPU}/GPU workload), "
+              f"{args.steps} timed steps after {args.warmup} warm-up, median; eager PyTorch on the host, {threads} threads")
+    cfg = workload_config(args.gpus, gnn=args.gnn, branch=args.branch)
+    cfg["workload"] = cfg["workload"].replace("fp32 (tensor cores, 3 split-bf16 passes)", "fp32")
+    cfg.update({"arm": "reference CPU path: eager PyTorch on the host cores, no CUDA graph, fp32",
+                "per_step_batch": CPU_SAMPLE_B, "device": "cpu", "threads": threads, "cpu_model": _cpu_model(),
+                "l2": "n/a (CPU)", "launch": "eager PyTorch ops from Python"})
+    line = {"impl": "reference", "kind": kind, "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.gpus, branch=args.branch),
-            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+            "config": cfg,
+            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": kind, "sample": sample,
+                             "branch": args.branch, "other_branch": {"branch": other, "value": CPU_SAMPLE_B / sec_other,
+                                                                     "ms_per_step": sec_other * 1e3},
+                             "one_thread": {"value": CPU_SAMPLE_B / sec_1t, "ms_per_step": sec_1t * 1e3}},
             "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -380,7 +401,8 @@ def run_gpu(args):
     peak = peaks["bf16_tflops"]
     h2d = sum(t.numel() * 4 for t in (visn_h, xp_h, adj_h))
     threads = os.cpu_count() or 1
-    cpu_sec = cpu_reference_steps(5, 2, threads, branch=args.branch)
+    cpu_sec, cpu_kind = cpu_reference_steps(5, 2, threads, branch=args.branch, gnn=args.gnn)
+    eager_ms, eager_kind = eager_gpu_steps(dev, 10, 3, B, branch=args.branch, gnn=args.gnn)
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -408,8 +430,12 @@ def run_gpu(args):
                            "frac_of_bf16_peak": flops_step / (ms_step * 1e-3) / 1e12 / peak,
                            "t_roof_us": flops_step / (peak * 1e12) * 1e6},
         "bf16_engine": alt,
-        "cpu_baseline": {"value": CPU_SAMPLE_B / cpu_sec, "unit": "samples/s", "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": CPU_SAMPLE_B / cpu_sec, "unit": "samples/s", "cores": threads, "kind": cpu_kind,
                          "sample": f"B={CPU_SAMPLE_B} graphs/step, 5 timed steps after 2 warm-up, median"},
+        # the reference's own eager PyTorch path on this B200 (same step, same B, true fp32, no CUDA graph)
+        "eager_gpu_baseline": {"value": B / (eager_ms * 1e-3), "unit": "samples/s", "ms_per_step": eager_ms,
+                               "kind": eager_kind, "dtype": "f32 (allow_tf32=False)", "n_gpus": 1,
+                               "sample": f"B={B} graphs/step on rank 0's GPU, 10 timed steps after 3 warm-up, CUDA events"},
     }
     print(json.dumps(line), flush=True)
     shutdown()

@@ -236,3 +236,22 @@ def test_api_surface_matches_reference(tag):
             assert rel_l2(g, ref) < 10 * TOL, k
         n += 1
     assert n == sum(1 for k in gold if k.startswith(tag + "/g/"))
+
+
+@pytest.mark.parametrize("branch", ["node", "relation"])
+def test_reference_step_runner(branch):
+    """oracle/ref_step.py (the baselines' step: real reference modules from oracle/_ref when vendored, else the
+    port) runs a full training step on CPU and moves the parameters."""
+    from oracle.ref_step import ReferenceStep, reference_available
+    kinds = [True, False] if reference_available() else [False]
+    for prefer in kinds:
+        s = ReferenceStep("cpu", 2, branch, hidden=64, prefer_reference=prefer, lr=1e-3)
+        assert s.kind == ("reference" if prefer else "port")
+        if s.kind == "reference":
+            before = [p.detach().clone() for p in s.params]
+        l1 = float(s.step())
+        l2 = float(s.step())
+        assert l1 == l1 and l2 == l2 and abs(l1) < 1e6
+        if s.kind == "reference":
+            moved = sum(float((p.detach() - b).abs().sum()) for p, b in zip(s.params, before))
+            assert moved > 0
