@@ -88,6 +88,21 @@ int xggm_linear_fwd(const float* a, const float* w, const float* bias, const flo
 /* ga[M,K] (+)= g[M,N] w[N,K]   (accumulate != 0 adds into ga) */
 int xggm_linear_bwd_input(const float* g, const float* w, float* ga, int M, int N, int K,
                           int accumulate, void* work, xggm_stream_t s);
+/* Prepared weight planes.  A weight changes once per optimiser step but is read by several products per step
+ * (forward as W, input gradient as W^T, in every layer call): xggm_weight_planes_build turns `count` fp32
+ * matrices W_i [N_i,K_i] into both bf16 operand layouts in ONE launch (per 16 matrices) -- buffer i is
+ * xggm_weight_planes_bytes(N_i,K_i) bytes, 16-byte aligned, layout hi[N,K] | lo[N,K] | hi(W^T)[K,P] | lo(W^T)[K,P],
+ * P = N rounded up to 8 -- and the `_ex` entry points take it instead of splitting W themselves (w_planes /
+ * weight_planes NULL = split internally, as the plain entry points do).  The caller rebuilds the planes whenever
+ * the fp32 weights change (xggm_b200.optim.BertAdam does, right after its update kernel) and when the engine
+ * precision changes; the exact-fp32 engine ignores them. */
+long long xggm_weight_planes_bytes(int N, int K);
+int xggm_weight_planes_build(const float* const* weights, void* const* planes, const int* N, const int* K, int count,
+                             xggm_stream_t s);
+int xggm_linear_fwd_ex(const float* a, const float* w, const float* bias, const float* resid,
+                       float* out, int M, int N, int K, void* work, const void* w_planes, xggm_stream_t s);
+int xggm_linear_bwd_input_ex(const float* g, const float* w, float* ga, int M, int N, int K,
+                             int accumulate, void* work, const void* w_planes, xggm_stream_t s);
 /* gw[N,K] (+)= g[M,N]^T a[M,K];  gbias[N]? (+)= column sums of g.  accumulate != 0 adds into the
  * buffers (gradient accumulation straight into a parameter's .grad), otherwise they are overwritten. */
 int xggm_linear_bwd_weight(const float* g, const float* a, float* gw, float* gbias,
@@ -200,11 +215,13 @@ int xggm_gnn_fwd(int kind, const float* x, const float* adj, const float* const*
                  float drop_p, float* out, float* saved, float* work, int B, int N, int H, int n_convs,
                  xggm_stream_t s);
 /* x_planes? : planes of x from its producer; out_planes? : receives the planes of `out` (emitted by the
- * last read-out accumulation).  The backward call must get the same x_planes. */
+ * last read-out accumulation).  The backward call must get the same x_planes.
+ * weight_planes? : HOST table of 2*n_convs + 1 prepared weight-plane buffers (xggm_weight_planes_build; conv k ->
+ * entry k, head j -> entry n_convs + j), or NULL. */
 int xggm_gnn_fwd_ex(int kind, const float* x, const float* adj, const float* const* conv_params,
                     const float* const* head_params, const uint8_t* const* keeps, const xggm_philox_t* philox,
                     float drop_p, float* out, float* saved, float* work, const void* x_planes, void* out_planes,
-                    int B, int N, int H, int n_convs, xggm_stream_t s);
+                    int B, int N, int H, int n_convs, const void* const* weight_planes, xggm_stream_t s);
 /* Gradient tables mirror the parameter tables (same order); every parameter-gradient buffer is
  * overwritten, or accumulated into when accumulate_param_grads != 0 (the buffers then are the
  * parameters' live .grad tensors).  gx[B,N,H] is always overwritten; gadj[B,N,N] is overwritten, or may be
@@ -220,7 +237,7 @@ int xggm_gnn_bwd_ex(int kind, const float* gout, const float* x, const float* ad
                     const uint8_t* const* keeps, const xggm_philox_t* philox, float drop_p, const float* saved,
                     float* work, float* gx, float* gadj, float* const* conv_grads, float* const* head_grads,
                     int accumulate_param_grads, const void* x_planes, int B, int N, int H, int n_convs,
-                    xggm_stream_t s);
+                    const void* const* weight_planes, xggm_stream_t s);
 
 /* ------------------------------------------------------------------------- *
  * GAT attention  src/module/gat.py:25-49 (after h = linear_layer(x), which is

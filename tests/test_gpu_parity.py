@@ -924,6 +924,64 @@ def test_bertadam_schedule_on_device_survives_graph_replay_and_skips_unused_para
     assert sd["state"][0]["step"] == 6 and float(sd["state"][0]["next_v"].abs().max()) > 0
 
 
+def test_prepared_weight_planes_are_exact_and_follow_the_weights():
+    """Prepared weight planes (xggm_weight_planes_build; functional.weight_planes): a layer called with cached
+    planes gives bit-identical outputs and gradients to one that splits its weights per call; the optimiser step
+    rebuilds them; a torch-visible in-place change of a weight invalidates its record."""
+    import xggm_b200 as X
+    import xggm_b200.functional as XF
+    B, N, H = 8, 36, 256
+    torch.manual_seed(21)
+    mod = X.XGGMHeads(H, "GCN", 2).to(dev()).train()
+    visn, xp, adj_true = (t.to(dev()) for t in O.make_inputs(22, B, N, H))
+    randn = torch.randn(B, N, H, device=dev())
+
+    def run():
+        XF._drop.site = 900
+        for p_ in mod.parameters():
+            p_.grad = None
+        x = xp.clone().requires_grad_(True)
+        feat = visn.clone().requires_grad_(True)
+        x_gen, loss_sm, nodes, adj_g = mod.node_step(x, feat, adj_true, 1.0, 100, randn)
+        (x_gen.sum() + loss_sm).backward()
+        return [x_gen.detach().clone(), nodes.detach().clone(), x.grad.clone(), feat.grad.clone()] + \
+               [p_.grad.clone() for p_ in mod.parameters() if p_.grad is not None]
+
+    plain = run()
+    mats = [p_ for p_ in mod.parameters() if p_.dim() == 2]
+    XF.cache_weight_planes(mats)
+    l0 = X._lib.kernel_launches()
+    cached_first = run()
+    l1 = X._lib.kernel_launches()
+    cached_again = run()
+    l2 = X._lib.kernel_launches()
+    assert all(getattr(m_, "_xggm_wp", None) is not None for m_ in mats if m_ is not mod.encoder_adj[0].weight)
+    assert l2 - l1 < l1 - l0                      # the second call found every record valid: no build launches
+    for a, b, c in zip(plain, cached_first, cached_again):
+        assert torch.equal(a, b) and torch.equal(a, c)
+    # a visible in-place update invalidates the record; the next call rebuilds and matches the uncached path
+    w = mod.generator.gnn_layers[0].linear_prediction[0][0].weight
+    with torch.no_grad():
+        w.mul_(1.5)
+    assert XF._wp_valid(w) is None
+    after = run()
+    XF.cache_weight_planes(mats, enable=False)
+    after_plain = run()
+    for a, b in zip(after, after_plain):
+        assert torch.equal(a, b)
+    assert not torch.equal(after[0], plain[0])
+    # BertAdam opts its parameters in and refreshes the planes after its (version-invisible) update kernel
+    opt = X.BertAdam(mod.parameters(), lr=1e-2)
+    run_a = run()                                  # builds planes of the current weights
+    opt.step()                                     # weights move; planes are rebuilt by the step
+    moved = run()
+    XF.cache_weight_planes(mats, enable=False)
+    moved_plain = run()
+    assert not torch.equal(moved[0], run_a[0])
+    for a, b in zip(moved, moved_plain):
+        assert torch.equal(a, b)
+
+
 # --------------------------------------------------------------------------- BASELINE size against the fp64 oracle
 def _oracle_branch_fp64(branch, p, visn, xp, adj_true, randn, keeps, cot, A, w_sm, kl_weight):
     """The fp64 CPU oracle of one GGM branch with every gradient (seconds at B=256 on the box's cores)."""

@@ -27,12 +27,13 @@ X.set_precision(a.precision)
 model = X.XGGMHeads(768, a.gnn, 2, a.nodes).to(dev).train()
 from xggm_b200.ddp import FlatGrads  # noqa: E402
 grads = FlatGrads(model.parameters())
+optim = X.BertAdam(model.parameters(), lr=4e-6, flat_grads=grads)
 visn, xp, adj = (t.to(dev) for t in synthetic_inputs(9596, a.batch, a.nodes, 768))
 cot = torch.randn(a.batch, 768, device=dev)
 
 
 def compute():
-    grads.flat.zero_()
+    grads.zero_()
     x = xp.detach().requires_grad_(True)
     feat = visn.detach().requires_grad_(True)
     if a.branch == "relation":
@@ -41,6 +42,7 @@ def compute():
     else:
         x_gen, loss_sm, _, _ = model.node_step(x, feat, adj, 1.0, 2274)
         ((x_gen * cot).sum() + 1.1 * loss_sm).backward()
+    optim.step(X.clip_grad_norm_(grads, 5.0))
 
 
 for _ in range(3):

@@ -43,9 +43,13 @@ SIGNATURES = {
     "xggm_planes_bytes": [_ll],
     "xggm_adj_regen_fwd_ex": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "xggm_adj_regen_bwd_ex": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp],
-    "xggm_gnn_fwd_ex": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "xggm_gnn_fwd_ex": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "xggm_gnn_bwd_ex": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp,
-                        _i, _vp, _i, _i, _i, _i, _vp],
+                        _i, _vp, _i, _i, _i, _i, _vp, _vp],
+    "xggm_weight_planes_bytes": [_i, _i],
+    "xggm_weight_planes_build": [_vp, _vp, _vp, _vp, _i, _vp],
+    "xggm_linear_fwd_ex": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
+    "xggm_linear_bwd_input_ex": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "xggm_feat_noise_ex": [_vp, _vp, _d, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "xggm_gnn_saved_floats": [_i, _i, _i, _i, _i],
     "xggm_gnn_work_floats": [_i, _i, _i, _i, _i],
@@ -82,7 +86,8 @@ SIGNATURES = {
     "xggm_keep_mask": [_vp, _ll, _f, _u64, _u64, _vp, _vp],
 }
 _RESTYPES = {"xggm_launch_count": C.c_ulonglong, "xggm_strerror": C.c_char_p, "xggm_last_cuda_error": C.c_char_p,
-             "xggm_planes_bytes": _ll, "xggm_gnn_saved_floats": _ll, "xggm_gnn_work_floats": _ll, "xggm_linear_work_bytes": _ll, "xggm_adj_regen_work_bytes": _ll, "xggm_adj_apply_work_bytes": _ll}
+             "xggm_planes_bytes": _ll, "xggm_gnn_saved_floats": _ll, "xggm_gnn_work_floats": _ll, "xggm_linear_work_bytes": _ll, "xggm_adj_regen_work_bytes": _ll, "xggm_adj_apply_work_bytes": _ll,
+             "xggm_weight_planes_bytes": _ll}
 
 ABI_VERSION = 4
 _lib = None

@@ -108,8 +108,20 @@ struct GnnLayout {
 // transposed = true (backward pass): the planes hold W^T, the layout proj_dgrad wants.
 static int split_weights(int kind, const float* const* cp, const float* const* hp, float* wregion,
                          const GnnLayout& L, int H, Operand* wconv, Operand* whead, bool tc, bool transposed,
-                         cudaStream_t st) {
+                         cudaStream_t st, const void* const* wplanes = nullptr) {
     const int nc = L.n_convs;
+    if (tc && wplanes) {
+        // prepared weight planes (xggm_weight_planes_build): conv k -> entry k, head j -> entry nc + j; nothing to split
+        for (int i = 0; i < 2 * nc + 1; ++i) {
+            XGGM_REQUIRE(wplanes[i]);
+            const float* W = i < nc ? ((kind == XGGM_KIND_GCN) ? cp[3 * i] : cp[5 * i + 1]) : hp[4 * (i - nc)];
+            bf16 *hi, *lo, *thi, *tlo;
+            weight_planes_views(const_cast<void*>(wplanes[i]), H, H, &hi, &lo, &thi, &tlo);
+            const Operand o = transposed ? Operand{W, thi, tlo} : Operand{W, hi, lo};
+            if (i < nc) wconv[i] = o; else whead[i - nc] = o;
+        }
+        return XGGM_OK;
+    }
     const float* src[16];
     bf16* hi[16];
     bf16* lo[16];
@@ -224,7 +236,7 @@ static int dgrad_kcat(bool tc, const Lin* l, int M, int N, int K, cudaStream_t s
 static int gnn_fwd(int kind, const float* x, const float* adj, const float* const* cp,
                    const float* const* hp, const uint8_t* const* keeps, const xggm_philox_t* philox, float drop_p, float* out,
                    float* saved, float* work, const void* x_planes, void* out_planes, int B, int N, int H, int nc,
-                   cudaStream_t st) {
+                   cudaStream_t st, const void* const* wplanes = nullptr) {
     XGGM_REQUIRE(kind == XGGM_KIND_GCN || kind == XGGM_KIND_GIN);
     XGGM_REQUIRE(B >= 0 && N > 0 && H > 0 && nc >= 0 && nc <= MAX_CONVS && drop_p >= 0.f && drop_p < 1.f);
     const int M = B * N;
@@ -234,7 +246,7 @@ static int gnn_fwd(int kind, const float* x, const float* adj, const float* cons
     const bool tc = use_tc(M, H, H);
     const long long MHn = (long long)M * H;
     Operand wconv[MAX_CONVS], whead[MAX_CONVS + 1];
-    XGGM_TRY(split_weights(kind, cp, hp, work + L.MH, L, H, wconv, whead, tc, false, st));
+    XGGM_TRY(split_weights(kind, cp, hp, work + L.MH, L, H, wconv, whead, tc, false, st, wplanes));
     // current node features as a GEMM operand: planes handed over by the producer of x, else built here
     Operand hop = x_planes ? planes_at(x, static_cast<float*>(const_cast<void*>(x_planes)), MHn)
                            : planes_at(x, saved + L.xplanes, MHn);
@@ -329,7 +341,7 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
                    const float* const* cp, const float* const* hp, const uint8_t* const* keeps,
                    const xggm_philox_t* philox, float drop_p, const float* saved_c, float* work, float* gx, float* gadj,
                    float* const* cg, float* const* hg, int acc, const void* x_planes, int B, int N, int H, int nc,
-                   cudaStream_t st) {
+                   cudaStream_t st, const void* const* wplanes = nullptr) {
     XGGM_REQUIRE(kind == XGGM_KIND_GCN || kind == XGGM_KIND_GIN);
     XGGM_REQUIRE(B >= 0 && N > 0 && H > 0 && nc >= 0 && nc <= MAX_CONVS && cp && hp && cg && hg);
     const int M = B * N;
@@ -358,7 +370,7 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
     float* gt = work + 2 * MH;  // GIN: gz of the conv (exact engine only; planes otherwise)
     float* gq = work + 3 * MH;
     Operand wconv[MAX_CONVS], whead[MAX_CONVS + 1];
-    XGGM_TRY(split_weights(kind, cp, hp, work + 6 * MH, L, H, wconv, whead, tc, true, st));
+    XGGM_TRY(split_weights(kind, cp, hp, work + 6 * MH, L, H, wconv, whead, tc, true, st, wplanes));
     if (gadj) XGGM_CUDA_TRY(cudaMemsetAsync(gadj, 0, sizeof(float) * (size_t)B * N * N, st));
     // per-graph products gq h^T go through the tensor-core Gram kernel when it can address them
     const bool gram = tc && gram_tc_supported(N, H);
@@ -573,8 +585,8 @@ static inline bool linear_tc(const void* work, int M, int N, int K) {
     return work != nullptr && M > 0 && g_precision != XGGM_PREC_FP32_SIMT && gemm_tc_ragged_ok(M, N, K);
 }
 
-int xggm_linear_fwd(const float* a, const float* w, const float* bias, const float* resid,
-                    float* out, int M, int N, int K, void* work, xggm_stream_t s) {
+int xggm_linear_fwd_ex(const float* a, const float* w, const float* bias, const float* resid,
+                       float* out, int M, int N, int K, void* work, const void* w_planes, xggm_stream_t s) {
     if (M == 0) return XGGM_OK;
     XGGM_REQUIRE(a && w && out && M >= 0 && N > 0 && K > 0);
     const bool tc = linear_tc(work, M, N, K);
@@ -582,31 +594,52 @@ int xggm_linear_fwd(const float* a, const float* w, const float* bias, const flo
     Operand ao{a, nullptr, nullptr}, wo{w, nullptr, nullptr};
     if (tc) {
         ao = planes_at(a, wk, (long long)M * K);
-        wo = planes_at(w, wk + pad8((long long)M * K), (long long)pad8i(N) * K);
-        const float* src[2] = {a, w};
-        bf16* hi[2] = {const_cast<bf16*>(ao.hi), const_cast<bf16*>(wo.hi)};
-        bf16* lo[2] = {const_cast<bf16*>(ao.lo), const_cast<bf16*>(wo.lo)};
-        const long long n[2] = {(long long)M * K, (long long)N * K};
-        XGGM_TRY(split_planes(src, hi, npass() == 3 ? lo : nullptr, n, 2, as_stream(s)));
+        if (w_planes) {   // prepared weight planes: only the activations are split here
+            bf16 *hi, *lo, *thi, *tlo;
+            weight_planes_views(const_cast<void*>(w_planes), N, K, &hi, &lo, &thi, &tlo);
+            wo = Operand{w, hi, lo};
+            XGGM_TRY(split_one(ao, (long long)M * K, as_stream(s)));
+        } else {
+            wo = planes_at(w, wk + pad8((long long)M * K), (long long)pad8i(N) * K);
+            const float* src[2] = {a, w};
+            bf16* hi[2] = {const_cast<bf16*>(ao.hi), const_cast<bf16*>(wo.hi)};
+            bf16* lo[2] = {const_cast<bf16*>(ao.lo), const_cast<bf16*>(wo.lo)};
+            const long long n[2] = {(long long)M * K, (long long)N * K};
+            XGGM_TRY(split_planes(src, hi, npass() == 3 ? lo : nullptr, n, 2, as_stream(s)));
+        }
     }
     return proj_fwd(tc, ao, wo, bias, resid, out, M, N, K, as_stream(s));
 }
+int xggm_linear_fwd(const float* a, const float* w, const float* bias, const float* resid,
+                    float* out, int M, int N, int K, void* work, xggm_stream_t s) {
+    return xggm_linear_fwd_ex(a, w, bias, resid, out, M, N, K, work, nullptr, s);
+}
 int xggm_linear_bwd_input(const float* g, const float* w, float* ga, int M, int N, int K,
                           int accumulate, void* work, xggm_stream_t s) {
+    return xggm_linear_bwd_input_ex(g, w, ga, M, N, K, accumulate, work, nullptr, s);
+}
+int xggm_linear_bwd_input_ex(const float* g, const float* w, float* ga, int M, int N, int K,
+                             int accumulate, void* work, const void* w_planes, xggm_stream_t s) {
     if (M == 0) return XGGM_OK;
     XGGM_REQUIRE(g && w && ga && M >= 0 && N > 0 && K > 0);
     const bool tc = linear_tc(work, M, N, K);
     if (!tc) return gemm_simt(1, g, w, nullptr, nullptr, ga, M, K, N, accumulate, as_stream(s));
     float* wk = static_cast<float*>(work);
     const int Np = pad8i(N);
-    const Operand wo = planes_at(w, wk + pad8((long long)M * K), (long long)Np * K);                                  // w^T [K,Np]
+    Operand wo = planes_at(w, wk + pad8((long long)M * K), (long long)Np * K);                                        // w^T [K,Np]
     const Operand go = planes_at(g, wk + pad8((long long)M * K) + pad8((long long)Np * K), (long long)M * Np);        // g [M,Np]
     if (Np == N) XGGM_TRY(split_one(go, (long long)M * N, as_stream(s)));   // dense rows: the vectorised splitter
     else XGGM_TRY(split_planes_pitched(g, mut(go.hi), lo_or_null(go), M, N, Np, as_stream(s)));
-    const float* src[1] = {w};
-    bf16* hi[1] = {mut(wo.hi)};
-    bf16* lo[1] = {mut(wo.lo)};
-    XGGM_TRY(split_planes_t(src, hi, npass() == 3 ? lo : nullptr, N, K, 1, as_stream(s), Np));
+    if (w_planes) {
+        bf16 *hi, *lo, *thi, *tlo;
+        weight_planes_views(const_cast<void*>(w_planes), N, K, &hi, &lo, &thi, &tlo);
+        wo = Operand{w, thi, tlo};
+    } else {
+        const float* src[1] = {w};
+        bf16* hi[1] = {mut(wo.hi)};
+        bf16* lo[1] = {mut(wo.lo)};
+        XGGM_TRY(split_planes_t(src, hi, npass() == 3 ? lo : nullptr, N, K, 1, as_stream(s), Np));
+    }
     // ga[M,K] (+)= g[M,Np] (w^T[K,Np])^T : the zero columns N..Np-1 add nothing
     return gemm_tc(false, false, go.hi, go.lo, wo.hi, wo.lo, nullptr, nullptr, ga, nullptr, nullptr, M, K, Np, accumulate, 0,
                    npass(), as_stream(s));
@@ -721,6 +754,14 @@ long long xggm_adj_regen_work_bytes(int B, int N, int H) {
     return 4 * pad8((long long)B * N * H);
 }
 long long xggm_planes_bytes(long long n_elems) { return n_elems < 0 ? -1 : 4 * pad8(n_elems); }
+long long xggm_weight_planes_bytes(int N, int K) { return (N <= 0 || K <= 0) ? -1 : 2 * weight_planes_elems(N, K); }
+int xggm_weight_planes_build(const float* const* weights, void* const* planes, const int* N, const int* K, int count,
+                             xggm_stream_t s) {
+    if (count == 0) return XGGM_OK;
+    XGGM_REQUIRE(weights && planes && N && K && count > 0);
+    if (g_precision == XGGM_PREC_FP32_SIMT) return XGGM_OK;   // the exact engine reads the fp32 weights
+    return weight_planes_build(weights, planes, N, K, count, npass() == 3, as_stream(s));
+}
 int xggm_adj_regen_fwd_ex(const float* x, float* adj_out, float* S, int32_t* amax, int B, int N,
                           int H, int squash, void* work, const void* x_planes, xggm_stream_t s) {
     XGGM_REQUIRE(B >= 0 && H > 0);
@@ -774,9 +815,9 @@ long long xggm_gnn_work_floats(int kind, int B, int N, int H, int n_convs) {
 int xggm_gnn_fwd_ex(int kind, const float* x, const float* adj, const float* const* conv_params,
                     const float* const* head_params, const uint8_t* const* keeps, const xggm_philox_t* philox,
                     float drop_p, float* out, float* saved, float* work, const void* x_planes, void* out_planes,
-                    int B, int N, int H, int n_convs, xggm_stream_t s) {
+                    int B, int N, int H, int n_convs, const void* const* weight_planes, xggm_stream_t s) {
     return gnn_fwd(kind, x, adj, conv_params, head_params, keeps, philox, drop_p, out, saved, work, x_planes, out_planes,
-                   B, N, H, n_convs, as_stream(s));
+                   B, N, H, n_convs, as_stream(s), weight_planes);
 }
 int xggm_gnn_fwd(int kind, const float* x, const float* adj, const float* const* conv_params,
                  const float* const* head_params, const uint8_t* const* keeps, const xggm_philox_t* philox,
@@ -790,9 +831,9 @@ int xggm_gnn_bwd_ex(int kind, const float* gout, const float* x, const float* ad
                     const uint8_t* const* keeps, const xggm_philox_t* philox, float drop_p, const float* saved,
                     float* work, float* gx, float* gadj, float* const* conv_grads, float* const* head_grads,
                     int accumulate_param_grads, const void* x_planes, int B, int N, int H, int n_convs,
-                    xggm_stream_t s) {
+                    const void* const* weight_planes, xggm_stream_t s) {
     return gnn_bwd(kind, gout, x, adj, conv_params, head_params, keeps, philox, drop_p, saved, work, gx, gadj,
-                   conv_grads, head_grads, accumulate_param_grads, x_planes, B, N, H, n_convs, as_stream(s));
+                   conv_grads, head_grads, accumulate_param_grads, x_planes, B, N, H, n_convs, as_stream(s), weight_planes);
 }
 int xggm_gnn_bwd(int kind, const float* gout, const float* x, const float* adj,
                  const float* const* conv_params, const float* const* head_params,

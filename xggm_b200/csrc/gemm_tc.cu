@@ -757,6 +757,53 @@ build_blockdiag_kernel(const float* __restrict__ adj, __nv_bfloat16* __restrict_
     }
 }
 
+// Prepared weight planes: ONE launch turns up to MAX_WP_JOBS fp32 matrices W [N,K] into BOTH operand layouts the
+// projections read -- the K-major planes of W (forward) and the planes of W^T [K,P] (P = N rounded up to 8, zero
+// padded; the input-gradient product) -- so that a training step splits its weights once (after the optimiser
+// update) instead of once per layer call and direction.  32 x 32 tiles through shared memory: both outputs are
+// written with coalesced rows.
+constexpr int MAX_WP_JOBS = 16;
+struct WPlaneJob {
+    const float* src;
+    __nv_bfloat16* hi;    // [N,K]
+    __nv_bfloat16* lo;    // may be null (bf16 engine)
+    __nv_bfloat16* thi;   // [K,P]
+    __nv_bfloat16* tlo;
+    int N, K, P;
+};
+struct WPlaneJobs {
+    WPlaneJob j[MAX_WP_JOBS];
+};
+__global__ void __launch_bounds__(256) weight_planes_kernel(const WPlaneJobs jobs) {
+    pdl_prologue();
+    __shared__ float tile[32][33];
+    const WPlaneJob job = jobs.j[blockIdx.z];
+    const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;    // W rows n, columns k
+    if (k0 >= job.K || n0 >= job.P) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int i = ty; i < 32; i += 8) {
+        const int n = n0 + i, k = k0 + tx;
+        const float v = (n < job.N && k < job.K) ? job.src[(size_t)n * job.K + k] : 0.f;
+        tile[i][tx] = v;
+        if (n < job.N && k < job.K) {
+            __nv_bfloat16 h, l;
+            split1(v, h, l);
+            job.hi[(size_t)n * job.K + k] = h;
+            if (job.lo) job.lo[(size_t)n * job.K + k] = l;
+        }
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int k = k0 + i, n = n0 + tx;   // W^T row k, column n (pitch P, zero padded beyond N)
+        if (k < job.K && n < job.P) {
+            __nv_bfloat16 h, l;
+            split1(n < job.N ? tile[tx][i] : 0.f, h, l);
+            job.thi[(size_t)k * job.P + n] = h;
+            if (job.tlo) job.tlo[(size_t)k * job.P + n] = l;
+        }
+    }
+}
+
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------------------
@@ -1157,4 +1204,43 @@ int split_planes(const float* const* src, __nv_bfloat16* const* hi, __nv_bfloat1
     return XGGM_OK;
 }
 
+// Layout of one prepared weight buffer (bf16 elements): hi[pad8(N*K)] | lo[pad8(N*K)] | thi[pad8(K*P)] | tlo[pad8(K*P)]
+static inline long long wp_pad8(long long n) { return (n + 7) & ~7LL; }
+long long weight_planes_elems(int N, int K) {
+    const long long P = (N + 7) & ~7;
+    return 2 * wp_pad8((long long)N * K) + 2 * wp_pad8((long long)K * P);
+}
+void weight_planes_views(void* buf, int N, int K, __nv_bfloat16** hi, __nv_bfloat16** lo, __nv_bfloat16** thi,
+                         __nv_bfloat16** tlo) {
+    const long long P = (N + 7) & ~7;
+    __nv_bfloat16* b = static_cast<__nv_bfloat16*>(buf);
+    *hi = b;
+    *lo = b + wp_pad8((long long)N * K);
+    *thi = b + 2 * wp_pad8((long long)N * K);
+    *tlo = *thi + wp_pad8((long long)K * P);
+}
+int weight_planes_build(const float* const* W, void* const* bufs, const int* N, const int* K, int count, bool with_lo,
+                        cudaStream_t st) {
+    int done = 0;
+    while (done < count) {
+        tc::WPlaneJobs jobs;
+        const int n = min(tc::MAX_WP_JOBS, count - done);
+        int kmax = 0, pmax = 0;
+        for (int i = 0; i < n; ++i) {
+            tc::WPlaneJob& j = jobs.j[i];
+            XGGM_REQUIRE(W[done + i] && bufs[done + i] && N[done + i] > 0 && K[done + i] > 0);
+            j.src = W[done + i];
+            j.N = N[done + i]; j.K = K[done + i]; j.P = (j.N + 7) & ~7;
+            weight_planes_views(bufs[done + i], j.N, j.K, &j.hi, &j.lo, &j.thi, &j.tlo);
+            if (!with_lo) { j.lo = nullptr; j.tlo = nullptr; }
+            kmax = max(kmax, j.K); pmax = max(pmax, j.P);
+        }
+        XGGM_LAUNCH((tc::weight_planes_kernel), dim3(ceil_div(kmax, 32), ceil_div(pmax, 32), n), 256, 0, st, jobs);
+        XGGM_LAUNCH_CHECK();
+        done += n;
+    }
+    return XGGM_OK;
+}
+
 }  // namespace xggm
+

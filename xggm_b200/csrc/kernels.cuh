@@ -95,6 +95,11 @@ int bce_logits_bwd(const float* x, const float* t, const float* gloss, float sca
 int grad_sumsq(const float* g, long long n, float* out, int accumulate, cudaStream_t st);
 int bertadam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double b1, double b2, double eps,
                   double wd, const float* sumsq, double max_norm, const xggm_lr_schedule_t* sched, cudaStream_t st);
+long long weight_planes_elems(int N, int K);
+void weight_planes_views(void* buf, int N, int K, __nv_bfloat16** hi, __nv_bfloat16** lo, __nv_bfloat16** thi,
+                         __nv_bfloat16** tlo);
+int weight_planes_build(const float* const* W, void* const* bufs, const int* N, const int* K, int count, bool with_lo,
+                        cudaStream_t st);
 int sigmoid_fwd(const float*, float*, long long, cudaStream_t);
 int sigmoid_bwd(const float*, const float*, float*, long long, cudaStream_t);
 int keep_mask(uint8_t*, long long, float, uint64_t, uint64_t, const uint64_t*, cudaStream_t);

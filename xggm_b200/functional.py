@@ -86,6 +86,78 @@ def _planes_of(t):
 
 
 # ---------------------------------------------------------------------------
+# prepared weight planes (include/xggm_b200.h, "Prepared weight planes")
+# ---------------------------------------------------------------------------
+# A weight matrix changes once per optimiser step but is read as a tensor-core operand by several products per
+# step (W in the forward pass, W^T in the input-gradient product, in every layer call).  For parameters that
+# OPT IN -- ``cache_weight_planes(params)``; ``xggm_b200.optim.BertAdam`` opts its parameters in and rebuilds the
+# planes right after its update kernel -- both bf16 layouts are built once (one launch for all stale matrices)
+# and handed to the entry points, instead of being re-split inside every call.  Opt-in because a record cannot
+# see writes that bypass torch's version counter (``p.data.add_()``, as the reference's own optimiser does): code
+# that updates weights that way must call ``refresh_weight_planes`` itself or leave the cache off.
+def cache_weight_planes(params, enable=True):
+    for p in params:
+        if enable:
+            p._xggm_wp_ok = True
+        else:
+            p._xggm_wp_ok = False
+            p._xggm_wp = None
+
+
+def _wp_valid(w):
+    rec = getattr(w, "_xggm_wp", None)
+    if rec is None:
+        return None
+    buf, version, data_ptr, prec = rec
+    if w._version != version or w.data_ptr() != data_ptr or prec != _lib.load().xggm_get_precision():
+        return None
+    return buf
+
+
+def _build_weight_planes(ws):
+    lib = _lib.load()
+    prec = lib.xggm_get_precision()
+    n = len(ws)
+    bufs = []
+    for w in ws:
+        N, K = w.shape
+        nbytes = int(lib.xggm_weight_planes_bytes(N, K))
+        rec = getattr(w, "_xggm_wp", None)
+        buf = rec[0] if (rec is not None and rec[0].numel() == nbytes and rec[0].device == w.device) else \
+            torch.empty(nbytes, device=w.device, dtype=torch.uint8)
+        bufs.append(buf)
+    wt, bt = ptr_table(ws), ptr_table(bufs)
+    Ns = (C.c_int * n)(*[int(w.shape[0]) for w in ws])
+    Ks = (C.c_int * n)(*[int(w.shape[1]) for w in ws])
+    call("xggm_weight_planes_build", wt, bt, Ns, Ks, n)
+    for w, buf in zip(ws, bufs):
+        w._xggm_wp = (buf, w._version, w.data_ptr(), prec)
+
+
+def weight_planes(ws):
+    """Prepared plane buffers of the 2-D fp32 weights ``ws`` (None where a weight has not opted in or the engine
+    cannot use them); stale ones are rebuilt first, all in one launch."""
+    if not _planes_enabled():
+        return [None] * len(ws)
+    ok = [bool(getattr(w, "_xggm_wp_ok", False)) and w.dim() == 2 and w.shape[1] % 8 == 0 and w.is_contiguous()
+          and w.dtype == torch.float32 and w.is_cuda for w in ws]
+    stale = [w for w, o in zip(ws, ok) if o and _wp_valid(w) is None]
+    if stale:
+        _build_weight_planes(stale)
+    return [w._xggm_wp[0] if o else None for w, o in zip(ws, ok)]
+
+
+def refresh_weight_planes(params):
+    """Rebuild (in place, one launch) the planes of every parameter in ``params`` that has a plane record: to be
+    called after the weights were updated by something torch's version counter does not see."""
+    if not _planes_enabled():
+        return
+    ws = [p for p in params if getattr(p, "_xggm_wp_ok", False) and getattr(p, "_xggm_wp", None) is not None]
+    if ws:
+        _build_weight_planes(ws)
+
+
+# ---------------------------------------------------------------------------
 # dense projection (nn.Linear)
 # ---------------------------------------------------------------------------
 def _linear_work(M, N, K, device):
@@ -107,7 +179,9 @@ class _Linear(torch.autograd.Function):
         r2 = None if resid is None else f32(resid, "resid").reshape(-1, N)
         out = torch.empty((M, N), device=a.device, dtype=torch.float32)
         work = _linear_work(M, N, K, a.device)
-        call("xggm_linear_fwd", ptr(a2), ptr(w), ptr(bias), ptr(r2), ptr(out), M, N, K, ptr(work))
+        wp = weight_planes([w])[0] if M > 0 else None
+        call("xggm_linear_fwd_ex", ptr(a2), ptr(w), ptr(bias), ptr(r2), ptr(out), M, N, K, ptr(work), ptr(wp))
+        ctx.w_planes = wp
         ctx.save_for_backward(a2, w)
         ctx.bias_ref = bias   # only consulted for its .grad buffer in backward
         ctx.has_bias, ctx.has_resid, ctx.in_shape = bias is not None, resid is not None, a.shape
@@ -123,7 +197,8 @@ class _Linear(torch.autograd.Function):
         work = _linear_work(M, N, K, g.device)
         if ctx.needs_input_grad[0]:
             ga = torch.empty_like(a2)
-            call("xggm_linear_bwd_input", ptr(g2), ptr(w), ptr(ga), M, N, K, 0, ptr(work))
+            wp = ctx.w_planes if (ctx.w_planes is not None and _wp_valid(w) is ctx.w_planes) else None
+            call("xggm_linear_bwd_input_ex", ptr(g2), ptr(w), ptr(ga), M, N, K, 0, ptr(work), ptr(wp))
             ga = ga.reshape(ctx.in_shape)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             bias = ctx.bias_ref
@@ -334,8 +409,13 @@ class _GnnLayer(torch.autograd.Function):
         out = torch.empty_like(x)
         cpt, hpt = ptr_table(cp), ptr_table(hp)
         kt = None if keeps is None else ptr_table(keeps)
+        mats = _layer_matrices(kind, n_convs, cp, hp)
+        wps = weight_planes(mats) if B * N > 0 else [None]
+        wps = wps if all(b is not None for b in wps) else None
         call("xggm_gnn_fwd_ex", kind, ptr(x), ptr(adj), cpt, hpt, kt, _philox_arg(philox), float(drop_p), ptr(out),
-             ptr(saved), ptr(work), ptr(x_planes), ptr(out_planes), B, N, H, n_convs)
+             ptr(saved), ptr(work), ptr(x_planes), ptr(out_planes), B, N, H, n_convs,
+             None if wps is None else ptr_table(wps))
+        ctx.wps = wps
         ctx.save_for_backward(x, adj, saved, *params)
         ctx.x_planes = x_planes
         ctx.keeps = keeps
@@ -362,12 +442,24 @@ class _GnnLayer(torch.autograd.Function):
         fused = all(t is not None for t in targets)
         grads = targets if fused else [torch.empty_like(p) for p in params]
         kt = None if ctx.keeps is None else ptr_table(ctx.keeps)
+        wps = ctx.wps     # the forward pass's prepared weight planes, if the weights have not changed since
+        if wps is not None:
+            mats = _layer_matrices(kind, n_convs, cp, hp)
+            if not all(_wp_valid(w) is b for w, b in zip(mats, wps)):
+                wps = None
         call("xggm_gnn_bwd_ex", kind, ptr(g), ptr(x), ptr(adj), ptr_table(cp), ptr_table(hp), kt,
              _philox_arg(ctx.philox), drop_p, ptr(saved), ptr(work), ptr(gx), ptr(gadj), ptr_table(grads[:n_cp]),
-             ptr_table(grads[n_cp:]), int(fused), ptr(ctx.x_planes), B, N, H, n_convs)
+             ptr_table(grads[n_cp:]), int(fused), ptr(ctx.x_planes), B, N, H, n_convs,
+             None if wps is None else ptr_table(wps))
         if fused:
             grads = [None] * len(params)
         return (None, None, None, None, None, None, None, gx, (gadj if ctx.needs_input_grad[8] else None), *grads)
+
+
+def _layer_matrices(kind, n_convs, cp, hp):
+    """The 2*n_convs + 1 weight matrices of a layer in the order of the C ABI's weight_planes table."""
+    per = 3 if kind == 0 else 5
+    return [cp[per * k + (0 if kind == 0 else 1)] for k in range(n_convs)] + [hp[4 * j] for j in range(n_convs + 1)]
 
 
 def _philox_arg(philox):

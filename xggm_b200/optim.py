@@ -56,6 +56,10 @@ class _Group:
             p.data = view
         self.m = torch.zeros_like(g)
         self.v = torch.zeros_like(g)
+        # the optimiser is the only writer of these weights: their tensor-core operand planes may be cached and are
+        # rebuilt by step() right after the update (functional.weight_planes)
+        from . import functional as XF
+        XF.cache_weight_planes([p for p in self.params if p.dim() == 2])
         # the step counter lives on the device (the update kernel evaluates the schedule from it and advances it,
         # so a CUDA-graph replay keeps following the schedule); `_ticket` is the kernel's hand-shake word
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=g.device)
@@ -155,6 +159,9 @@ class BertAdam:
                 call("xggm_bertadam_step_ex", ptr(g.flat_p[lo:hi]), ptr(g.grads.flat[lo:hi]), ptr(g.m[lo:hi]),
                      ptr(g.v[lo:hi]), hi - lo, float(o["lr"]), float(o["b1"]), float(o["b2"]), float(o["e"]),
                      float(o["weight_decay"]), ptr(sumsq), float(max_norm), C.cast(C.pointer(sched), C.c_void_p))
+            if g.flat_p.is_cuda:
+                from . import functional as XF
+                XF.refresh_weight_planes(g.params)     # one launch: both operand layouts of every cached weight
 
     # -- checkpointing (the reference trainers do not save optimiser state; torch-style layout) ----
     def state_dict(self):
