@@ -957,8 +957,17 @@ def test_prepared_weight_planes_are_exact_and_follow_the_weights():
     l2 = X._lib.kernel_launches()
     assert all(getattr(m_, "_xggm_wp", None) is not None for m_ in mats if m_ is not mod.encoder_adj[0].weight)
     assert l2 - l1 < l1 - l0                      # the second call found every record valid: no build launches
-    for a, b, c in zip(plain, cached_first, cached_again):
-        assert torch.equal(a, b) and torch.equal(a, c)
+    def same(u, v):
+        # outputs and input gradients are deterministic: bit-identical.  Parameter gradients are reduced with
+        # atomics (column sums, split-K weight gradients): equal to rounding
+        for i, (a, b) in enumerate(zip(u, v)):
+            if i < 4:
+                assert torch.equal(a, b), i
+            else:
+                assert rel_l2(a.cpu(), b.cpu()) < 2e-6, i
+
+    same(plain, cached_first)
+    same(plain, cached_again)
     # a visible in-place update invalidates the record; the next call rebuilds and matches the uncached path
     w = mod.generator.gnn_layers[0].linear_prediction[0][0].weight
     with torch.no_grad():
@@ -967,8 +976,7 @@ def test_prepared_weight_planes_are_exact_and_follow_the_weights():
     after = run()
     XF.cache_weight_planes(mats, enable=False)
     after_plain = run()
-    for a, b in zip(after, after_plain):
-        assert torch.equal(a, b)
+    same(after, after_plain)
     assert not torch.equal(after[0], plain[0])
     # BertAdam opts its parameters in and refreshes the planes after its (version-invisible) update kernel
     opt = X.BertAdam(mod.parameters(), lr=1e-2)
@@ -978,8 +986,7 @@ def test_prepared_weight_planes_are_exact_and_follow_the_weights():
     XF.cache_weight_planes(mats, enable=False)
     moved_plain = run()
     assert not torch.equal(moved[0], run_a[0])
-    for a, b in zip(moved, moved_plain):
-        assert torch.equal(a, b)
+    same(moved, moved_plain)
 
 
 # --------------------------------------------------------------------------- BASELINE size against the fp64 oracle

@@ -261,6 +261,10 @@ struct Params {
     // graphs starting at row t*bd_stride, zero elsewhere), B is x itself read MN-major with its k rows
     // starting at t*bd_stride, and only the first bd_stride rows of each output tile exist.
     int bd_stride;
+    // bd_kn > 0: UNALIGNED block-diagonal tiles.  Tile t covers output rows [128 t, 128 t + 128) whatever graphs they
+    // fall in; its k rows start at the first row of the first graph it touches, bd_kn * floor(128 t / bd_kn), and
+    // the coefficient tile is 128 x (64 num_kb) wide.  No dead rows (128 / 128 instead of 108 / 128 live at N = 36).
+    int bd_kn;
     unsigned long long* dbg;   // optional device buffer: CTA 0 records a globaltimer timeline (tools/gemm_timeline.py)
 };
 
@@ -351,7 +355,8 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const Params p) {
                 const int mn = t / p.splits;
                 int m0 = (mn / p.tiles_n) * (BM * CG) + (int)rank * BM, n0 = (mn % p.tiles_n) * BN;
                 if (p.gram_n > 0) m0 = n0 = mn * p.gram_g * p.gram_n;
-                const int b_krow0 = p.bd_stride > 0 ? (mn / p.tiles_n) * p.bd_stride : 0;   // block-diagonal mode
+                int b_krow0 = p.bd_stride > 0 ? (mn / p.tiles_n) * p.bd_stride : 0;   // block-diagonal mode
+                if (p.bd_kn > 0) b_krow0 = ((mn / p.tiles_n) * BM / p.bd_kn) * p.bd_kn;
                 const int kb0 = sp * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     const int seg = (p.kcat > 0 && kb >= p.kcat) ? 1 : 0;   // K-concatenated product: second operand pair
@@ -757,6 +762,41 @@ build_blockdiag_kernel(const float* __restrict__ adj, __nv_bfloat16* __restrict_
     }
 }
 
+// Unaligned variant (Params::bd_kn): tile t = output rows [128 t, 128 t + 128), columns = the KW k rows starting at
+// row N * floor(128 t / N) (the first row of the first graph the tile touches).  Dense [128][KW] K-major tile.
+__global__ void __launch_bounds__(128)
+build_blockdiag_u_kernel(const float* __restrict__ adj, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                         long long M, int N, int KW, float alpha0, const float* __restrict__ alpha_dev, float self_w, int trans) {
+    pdl_prologue();
+    const int t = blockIdx.x;
+    const float alpha = alpha0 + (alpha_dev ? alpha_dev[0] : 0.f);
+    const long long kstart = ((long long)t * BM / N) * N;
+    __nv_bfloat16* th = hi + (size_t)t * BM * KW;
+    __nv_bfloat16* tl = lo ? lo + (size_t)t * BM * KW : nullptr;
+    const int vec_per_row = KW / 8;
+    for (int v = threadIdx.x; v < 32 * vec_per_row; v += blockDim.x) {
+        const int r = blockIdx.y * 32 + v / vec_per_row, c0 = (v % vec_per_row) * 8;
+        const long long m = (long long)t * BM + r;
+        const long long b = m / N;
+        const int i = (int)(m - b * N);
+        const bool row_live = m < M;
+        const float* ab = adj + (size_t)(row_live ? b : 0) * N * N;
+        __align__(16) __nv_bfloat16 hv[8], lv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const long long j = kstart + c0 + u - b * N;
+            float val = 0.f;
+            if (row_live && j >= 0 && j < N) {
+                val = alpha * ab[trans ? j * N + i : (long long)i * N + j];
+                if (i == j) val += self_w;
+            }
+            split1(val, hv[u], lv[u]);
+        }
+        *reinterpret_cast<uint4*>(th + (size_t)r * KW + c0) = *reinterpret_cast<const uint4*>(hv);
+        if (tl) *reinterpret_cast<uint4*>(tl + (size_t)r * KW + c0) = *reinterpret_cast<const uint4*>(lv);
+    }
+}
+
 // Prepared weight planes: ONE launch turns up to MAX_WP_JOBS fp32 matrices W [N,K] into BOTH operand layouts the
 // projections read -- the K-major planes of W (forward) and the planes of W^T [K,P] (P = N rounded up to 8, zero
 // padded; the input-gradient product) -- so that a training step splits its weights once (after the optimiser
@@ -988,6 +1028,7 @@ int gemm_tc_group(bool a_mn, bool b_mn, const GemmProb* pr, int count, int M, in
     p.vec4 = (N % 4 == 0);
     p.gram_n = p.gram_g = p.gram_b = 0;
     p.bd_stride = 0;
+    p.bd_kn = 0;
     p.dbg = g_tc_dbg;
     for (int g = 0; g < tc::MAX_GROUP; ++g) {
         const GemmProb& q = pr[g < segments ? g : 0];
@@ -1083,6 +1124,7 @@ int gram_tc(const __nv_bfloat16* p_hi, const __nv_bfloat16* p_lo, const __nv_bfl
     single_problem(p, nullptr, nullptr, S, nullptr, nullptr, 0);
     p.gram_n = N; p.gram_g = G; p.gram_b = B;
     p.bd_stride = 0;
+    p.bd_kn = 0;
     p.dbg = nullptr;
     const int grid = min(num_sms(), p.tiles_m * p.splits);
     void* prof = gemm_prof_begin(2.0 * B * N * N * H, st);
@@ -1093,13 +1135,38 @@ int gram_tc(const __nv_bfloat16* p_hi, const __nv_bfloat16* p_lo, const __nv_bfl
 }
 
 bool adj_tc_supported(int N, int H) { return N >= 1 && N <= tc::BM && H > 0 && H % 8 == 0; }
-long long adj_tc_coef_elems(int B, int N) { return (long long)ceil_div(B, tc::BM / N) * tc::BM * tc::BM; }
+// Widest k range a 128-row output tile can touch: the rows of every graph it overlaps.
+static inline int bd_span(int N) { return N * ((N - 1 + tc::BM - 1) / N + 1); }
+constexpr int BD_KW = 192;   // coefficient-tile width of the unaligned scheme (3 k-blocks)
+// Unaligned tiles (all 128 rows of every tile live, ceil(M/128) row tiles) whenever the span fits 192 k rows
+// (N <= 48 and N = 64: obj36 graphs touch at most 5 graphs = 180 rows); XGGM_ADJ_ALIGNED=1 keeps the graph-aligned
+// tiles (floor(128/N) whole graphs per tile) for A/B runs, and wider graphs always take them.
+static bool bd_unaligned(int N) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("XGGM_ADJ_ALIGNED");
+        forced = (e && e[0] == '1') ? 1 : 0;
+    }
+    return !forced && bd_span(N) <= BD_KW;
+}
+long long adj_tc_coef_elems(int B, int N) {
+    const long long aligned = (long long)ceil_div(B, tc::BM / N) * tc::BM * tc::BM;
+    const long long unaligned = (long long)ceil_div((long long)B * N, tc::BM) * tc::BM * BD_KW;
+    return aligned > unaligned ? aligned : unaligned;
+}
 
 // coefficient planes (adj_tc_coef_elems bf16 each) for adj_apply_tc
 int build_blockdiag(const float* adj, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int N, float alpha0,
                     const float* alpha_dev, float self_w, int trans, cudaStream_t st) {
     if (B <= 0) return XGGM_OK;
     XGGM_REQUIRE(adj && hi && N >= 1 && N <= tc::BM);
+    if (bd_unaligned(N)) {
+        const long long M = (long long)B * N;
+        XGGM_LAUNCH((tc::build_blockdiag_u_kernel), dim3(ceil_div(M, tc::BM), 4), 128, 0, st, adj, hi, lo, M, N, BD_KW, alpha0,
+                    alpha_dev, self_w, trans);
+        XGGM_LAUNCH_CHECK();
+        return XGGM_OK;
+    }
     const int G = tc::BM / N;
     XGGM_LAUNCH((tc::build_blockdiag_kernel), dim3(ceil_div(B, G), 4), 128, 0, st, adj, hi, lo, B, N, G, alpha0, alpha_dev, self_w, trans);
     XGGM_LAUNCH_CHECK();
@@ -1114,22 +1181,24 @@ int adj_apply_tc(const __nv_bfloat16* c_hi_in, const __nv_bfloat16* c_lo_in, con
     if (B <= 0) return XGGM_OK;
     XGGM_REQUIRE(c_hi_in && x_hi && (out || o_hi) && adj_tc_supported(N, H) && (npass == 1 || (c_lo_in && x_lo)));
     XGGM_REQUIRE(!accumulate || out);
-    const int G = tc::BM / N, T = ceil_div(B, G);
     const long long M = (long long)B * N;
+    const bool unal = bd_unaligned(N);
+    const int G = tc::BM / N, T = unal ? ceil_div(M, tc::BM) : ceil_div(B, G);
+    const int KW = unal ? BD_KW : tc::BM;
     constexpr int ABN = 192;
     tc::GroupMaps maps;
     CUtensorMap &ah = maps.m[0].a_hi, &al = maps.m[0].a_lo, &bh = maps.m[0].b_hi, &bl = maps.m[0].b_lo;
-    XGGM_TRY(make_map(&ah, c_hi_in, (long long)T * tc::BM, tc::BM, tc::BM));
+    XGGM_TRY(make_map(&ah, c_hi_in, (long long)T * tc::BM, KW, tc::BM));
     XGGM_TRY(make_map(&bh, x_hi, M, H, tc::BK));
     if (npass == 3) {
-        XGGM_TRY(make_map(&al, c_lo_in, (long long)T * tc::BM, tc::BM, tc::BM));
+        XGGM_TRY(make_map(&al, c_lo_in, (long long)T * tc::BM, KW, tc::BM));
         XGGM_TRY(make_map(&bl, x_lo, M, H, tc::BK));
     } else {
         al = ah;
         bl = bh;
     }
     tc::Params p;
-    p.M = (int)M; p.N = H; p.num_kb = tc::BM / tc::BK;
+    p.M = (int)M; p.N = H; p.num_kb = KW / tc::BK;
     p.tiles_m = T; p.tiles_n = ceil_div(H, ABN); p.splits = 1; p.kb_per_split = p.num_kb;
     p.ldc = H;
     p.atomic = 0;
@@ -1138,7 +1207,8 @@ int adj_apply_tc(const __nv_bfloat16* c_hi_in, const __nv_bfloat16* c_lo_in, con
     if (resid && (reinterpret_cast<uintptr_t>(resid) & 15)) return XGGM_ERR_ARG;
     for (int g = 1; g < tc::MAX_GROUP; ++g) maps.m[g] = maps.m[0];
     p.gram_n = p.gram_g = p.gram_b = 0;
-    p.bd_stride = G * N;
+    p.bd_stride = unal ? tc::BM : G * N;
+    p.bd_kn = unal ? N : 0;
     p.dbg = g_tc_dbg;
     XGGM_REQUIRE(p.vec4 && (reinterpret_cast<uintptr_t>(o_hi) & 7) == 0 && (reinterpret_cast<uintptr_t>(o_lo) & 7) == 0);
     const int grid = min(num_sms(), p.tiles_m * p.tiles_n);
