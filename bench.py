@@ -262,6 +262,8 @@ def run_gpu(args):
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
     loss_host = torch.zeros(1).pin_memory()
 
+    w_rel, w_node = torch.tensor(6.0, device=dev), torch.tensor(1.1, device=dev)   # vqacpv2.py:221,250
+
     def compute(visn, xp, adj):  # forward + backward of the block; gradients land in the flat bucket
         grads.zero_()
         x = xp.requires_grad_(True)
@@ -269,11 +271,13 @@ def run_gpu(args):
         with grads.overlap(average=True):
             if args.branch == "relation":   # GQA-OOD weights, src/gqa/gqa_ood.py:197
                 x_gen, loss_sm, _, _ = model.relation_step(x, feat, adj, SIGMA, NUM_ANS, kl_weight=12.0)
-                loss = (x_gen * cot_d).sum() + 6.0 * loss_sm
+                w_sm = w_rel
             else:
                 x_gen, loss_sm, _, _ = model.node_step(x, feat, adj, SIGMA, NUM_ANS)
-                loss = (x_gen * cot_d).sum() + 1.1 * loss_sm
-            loss.backward()
+                w_sm = w_node
+            # loss = <x_gen, cot> + w * loss_sm, where cot stands for d BCE(logit_fc(x_gen)) / d x_gen of the answer head
+            # that follows the block (outside the hot path): its backward pass is seeded directly with (cot, w)
+            torch.autograd.backward([x_gen, loss_sm], [cot_d, w_sm])
         grads.all_reduce(average=True)  # NCCL gradient all-reduce (no-op at world size 1)
         optim.step(X.clip_grad_norm_(grads, 5.0))   # one norm reduction + one fused update kernel
         return loss_sm.detach()

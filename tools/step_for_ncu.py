@@ -30,6 +30,7 @@ grads = FlatGrads(model.parameters())
 optim = X.BertAdam(model.parameters(), lr=4e-6, flat_grads=grads)
 visn, xp, adj = (t.to(dev) for t in synthetic_inputs(9596, a.batch, a.nodes, 768))
 cot = torch.randn(a.batch, 768, device=dev)
+w_rel, w_node = torch.tensor(6.0, device=dev), torch.tensor(1.1, device=dev)
 
 
 def compute():
@@ -38,10 +39,10 @@ def compute():
     feat = visn.detach().requires_grad_(True)
     if a.branch == "relation":
         x_gen, loss_sm, _, _ = model.relation_step(x, feat, adj, 1.0, 2274, kl_weight=12.0)
-        ((x_gen * cot).sum() + 6.0 * loss_sm).backward()
+        torch.autograd.backward([x_gen, loss_sm], [cot, w_rel])
     else:
         x_gen, loss_sm, _, _ = model.node_step(x, feat, adj, 1.0, 2274)
-        ((x_gen * cot).sum() + 1.1 * loss_sm).backward()
+        torch.autograd.backward([x_gen, loss_sm], [cot, w_node])
     optim.step(X.clip_grad_norm_(grads, 5.0))
 
 

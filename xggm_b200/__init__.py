@@ -4,7 +4,7 @@ Drop-in for the reference's ``module.graph_generative_modeling`` / ``module.gcn`
 ``module.gin`` / ``module.gat`` / ``module.graph_utils`` hot path; see DESIGN.md.
 Importing the package does not need a GPU; running any operator does (no fallback).
 """
-from . import _lib, ddp, functional, glue, graphs, optim  # noqa: F401
+from . import _lib, data, ddp, functional, glue, graphs, optim  # noqa: F401
 from .glue import (add_edge_noise, add_edge_noise_v2, add_feature_noise,  # noqa: F401
                    add_feature_noise_v2, compute_kl_loss, loss_func)
 from ._lib import get_precision, set_precision  # noqa: F401
