@@ -445,6 +445,175 @@ def run_gpu(args):
     shutdown()
 
 
+# ---------------------------------------------------------------------------- full training iteration
+ITER_METRIC = "xggm_train_iteration_samples_per_sec"
+
+
+def run_iteration(args):
+    """BASELINE configs[1] (fp32) / configs[2] (--precision bf16): one full trainer iteration -- stock-PyTorch LXMERT
+    (tools/lxmert_torch.py, shared by every arm, outside the hot path) + the library's graph block, answer head,
+    BCE, clip and BertAdam; two optimiser steps, two all-reduces of the 220.8 M-parameter buckets (2 x 0.88 GB) per
+    iteration at N > 1.  See tools/iteration.py."""
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import iteration as IT
+    from xggm_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    autocast = args.precision == "bf16"
+    torch.backends.cuda.matmul.allow_tf32 = False      # the reference's (torch default) true-fp32 matmuls
+    torch.backends.cudnn.allow_tf32 = False
+    it = IT.XGGMIteration(dev, B, autocast=autocast, delta=args.delta)
+    batches = [IT.synthetic_batch(9596 + 17 * rank + i, B) for i in range(2)]
+    h2d = it.h2d_bytes(batches[0])
+    loss_host = torch.zeros(1).pin_memory()
+    it.prefetch(batches[0])
+    resident = [t.to(dev) for t in batches[0]]
+    graph = None
+    if args.graph_iteration:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                it.iteration(resident)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            graph_loss = it.iteration(resident)
+
+    def resident_iter():
+        if graph is not None:
+            graph.replay()
+            return graph_loss
+        return it.iteration(resident)
+
+    k = [0]
+
+    def e2e_iter():
+        cur = it.take()                      # this iteration's batch (copied while the previous one computed)
+        k[0] += 1
+        it.prefetch(batches[k[0] % 2])       # next iteration's H2D on the side stream
+        if graph is not None:
+            for d, s in zip(resident, cur):
+                d.copy_(s, non_blocking=True)
+            graph.replay()
+            l = graph_loss
+        else:
+            l = it.iteration(cur)
+        loss_host.copy_(l.reshape(1), non_blocking=True)
+
+    def timed(fn, n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+            dist.barrier()
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        resident_iter()
+        e2e_iter()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0 and os.environ.get("XGGM_BENCH_NO_CLOCKS") != "1":
+        sampler.start()
+    resident_iter()
+    torch.cuda.synchronize()
+    with sampler as clk:
+        l0 = _lib.kernel_launches()
+        ms_res = timed(resident_iter, args.steps)
+        launches = _lib.kernel_launches() - l0
+        ms_e2e = timed(e2e_iter, args.steps)
+    clocks = clk.summary()
+    # the library's share: the GGM part of step B alone on fixed encoder outputs
+    visn, pooled = it.block_only(resident)
+    adj = resident[5]
+
+    def block():
+        it.fg_down.zero_()
+        x = pooled.detach().requires_grad_(True)
+        f = visn.detach().requires_grad_(True)
+        x_gen, loss_sm, _, _ = it.heads.node_step(x, f, adj, 1.0, it.A)
+        torch.autograd.backward([x_gen, loss_sm], [torch.ones_like(x_gen), torch.tensor(1.1, device=dev)])
+
+    for _ in range(3):
+        block()
+    ms_block = timed(block, 10) / 10
+    if rank != 0:
+        sys.stdout.flush()
+        if world > 1:
+            torch.cuda.synchronize()
+            os._exit(0)
+        return
+    eager = None
+    if not args.no_eager:
+        try:
+            from oracle.ref_step import ReferenceIteration, reference_available
+            if reference_available():
+                ref = ReferenceIteration(dev, autocast=autocast)
+                for _ in range(2):
+                    ref.iteration(batches[0])
+                torch.cuda.synchronize()
+                n = max(2, min(args.steps, 5))
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                for i in range(n):
+                    ref.iteration(batches[i % 2])
+                e.record()
+                torch.cuda.synchronize()
+                ms_ref = s.elapsed_time(e) / n
+                eager = {"value": B / (ms_ref * 1e-3), "unit": "samples/s", "ms_per_iteration": ms_ref, "kind": "reference",
+                         "n_gpus": 1, "sample": f"the unmodified reference modules (LXMERT, heads, GCNGenerator, BertAdam) "
+                                                f"from oracle/_ref on rank 0's GPU, eager PyTorch, B={B}, {n} iterations"}
+        except Exception as ex:   # the baseline must never take the measured arm down
+            eager = {"unavailable": repr(ex)[:200]}
+    ms_it = ms_res / args.steps
+    n_par = sum(p.numel() for p in it.fg_base.params) + sum(p.numel() for p in it.fg_down.params)
+    line = {
+        "metric": ITER_METRIC, "value": B * world / (ms_it * 1e-3), "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_it, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if autocast else "f32", "data": "synthetic",
+        "config": {"workload": f"cfg{3 if autocast else 2} full VQA-CP v2 training iteration (step A plain VQA + step B GGM "
+                               f"node branch, delta={args.delta}): stock-PyTorch LXMERT 9/5/5 ({'bf16 autocast' if autocast else 'true fp32'}) "
+                               f"+ xggm_b200 graph block / answer head / BCE / clip / BertAdam, B={B}/GPU, 36 objects x 2048-d, "
+                               f"20 tokens, A={NUM_ANS}",
+                   "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world}",
+                   "parameters": n_par, "allreduce_bytes_per_iteration": 2 * 4 * n_par if world > 1 else 0,
+                   "l2": "inputs and activations far exceed the 126 MB L2 (no flush needed)",
+                   "launch": "CUDA graph of the whole iteration" if graph is not None else "eager launches"},
+        "e2e": {"value": B * world / (ms_e2e / args.steps * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+                "note": "one H2D of the batch per iteration (the reference copies it in both steps), overlapped with "
+                        "the previous iteration"},
+        "gpu_launches": launches, "clocks": clocks,
+        "graph_block": {"ms": ms_block, "share_of_iteration": ms_block / ms_it,
+                        "note": "the library's GGM part of step B alone (node_step fwd+bwd) on fixed encoder outputs"},
+        "eager_gpu_baseline": eager,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.cuda.synchronize()
+        os._exit(0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -460,7 +629,16 @@ def main():
                     help="GGM branch of the step: node generation (the --delta 0 recipe of script/vqacpv2.sh, default) or "
                          "relation generation (taken with probability delta/10; GQA-OOD uses delta 5)")
     ap.add_argument("--nodes", type=int, default=N_NODES, help="nodes per graph (36 = obj36; 64/100 = BASELINE cfg 4 sweep)")
+    ap.add_argument("--workload", default="block", choices=["block", "iteration"],
+                    help="block: the graph block's training step (default, the headline); iteration: the full trainer "
+                         "iteration with a stock-PyTorch LXMERT around the block (BASELINE configs[1]/[2])")
+    ap.add_argument("--delta", type=int, default=0, help="--workload iteration: GGM branch threshold out of 10 (0 = VQA-CP recipe)")
+    ap.add_argument("--graph-iteration", action="store_true", help="--workload iteration: capture the iteration in a CUDA graph")
+    ap.add_argument("--no-eager", action="store_true", help="--workload iteration: skip the eager reference baseline")
     args = ap.parse_args()
+    if args.workload == "iteration" and args.impl != "reference":
+        run_iteration(args)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

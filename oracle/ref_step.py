@@ -166,3 +166,81 @@ class ReferenceStep:
 
     def step(self):
         return self._step_reference() if self.kind == "reference" else self._step_port()
+
+
+class ReferenceIteration:
+    """One full trainer iteration (src/vqa/vqacpv2.py:164-254: step A plain VQA, step B GGM node branch) built from
+    the UNMODIFIED reference modules vendored in oracle/_ref -- LXRTFeatureExtraction (9/5/5 layers, stock PyTorch),
+    logit_fc, GCNGenerator + heads, the reference's BertAdam with its two learning-rate groups -- for the
+    eager-PyTorch-on-B200 baseline of `bench.py --workload iteration`.  Needs oracle/_ref (there is no port of the
+    LXMERT encoder).  `autocast`: torch.autocast(bf16) around the model calls (the reference has no reduced-precision
+    path of its own)."""
+
+    def __init__(self, device, autocast=False, lr=1e-6, t_total=100000, num_answers=2274, hidden=768, n_nodes=36, sigma=1.0):
+        import torch.nn as nn
+        ggm, gu, GeLU, BertAdam, loss_func, compute_kl_loss = _import_reference()
+        import lxrt.modeling as RM
+        self.device, self.autocast, self.A, self.N, self.sigma = torch.device(device), autocast, num_answers, n_nodes, sigma
+        RM.VISUAL_CONFIG.l_layers, RM.VISUAL_CONFIG.x_layers, RM.VISUAL_CONFIG.r_layers = 9, 5, 5   # entry.py:24-34 + param.py
+        torch.manual_seed(9595)
+        cfg = RM.BertConfig(vocab_size_or_config_json_file=30522)
+        self.lxmert = RM.LXRTFeatureExtraction(cfg, mode="lxr")
+        H = hidden
+        self.logit_fc = nn.Sequential(nn.Linear(H, H * 2), GeLU(), RM.BertLayerNorm(H * 2, eps=1e-12),
+                                      nn.Linear(H * 2, num_answers))                               # vqacpv2_model.py:63-69
+        self.logit_fc.apply(self.lxmert.init_bert_weights)
+        self.generator = ggm.GCNGenerator(hidden_dim=H, n_layers=2)
+        self.node_fc = nn.Sequential(nn.Linear(H, H), GeLU(), nn.LayerNorm(H))
+        self.fusion_fc = nn.Sequential(nn.Linear(H * 2, H), GeLU(), nn.LayerNorm(H))
+        self.encoder_adj = nn.Sequential(nn.Linear(H, n_nodes * (n_nodes - 1) // 2), nn.Sigmoid())
+        self.mods = [self.lxmert, self.logit_fc, self.generator, self.node_fc, self.fusion_fc, self.encoder_adj]
+        for m in self.mods:
+            m.to(self.device).train()
+        base = list(self.lxmert.parameters())
+        down = [p for m in self.mods[1:] for p in m.parameters()]
+        self.params = base + down
+        self.optim = BertAdam([{"params": down}, {"params": base, "lr": lr}], lr=4 * lr, warmup=0.1,
+                              t_total=t_total)                                                      # vqacpv2.py:113-128
+        self.bce = nn.BCEWithLogitsLoss()
+        self.gu, self.loss_func, self.compute_kl_loss = gu, loss_func, compute_kl_loss
+
+    def _model(self, feats, boxes, ids, mask):
+        with torch.autocast(self.device.type, dtype=torch.bfloat16, enabled=self.autocast):
+            (lang, visn), pooled = self.lxmert(ids, None, mask, visual_feats=(feats, boxes))
+        return visn.float(), pooled.float()
+
+    def iteration(self, host_batch):
+        """host_batch: (feats, boxes, ids, mask, target, adj) on the HOST; copied to the device in both steps, as
+        the reference does (vqacpv2.py:171,185)."""
+        feats_h, boxes_h, ids_h, mask_h, target_h, adj_h = host_batch
+        dev = self.device
+        ids, mask, target = ids_h.to(dev), mask_h.to(dev), target_h.to(dev)                        # :166-167
+        # ---- step A (:170-177)
+        for p in self.params:
+            p.grad = None
+        _, x = self._model(feats_h.to(dev), boxes_h.to(dev), ids, mask)
+        logit = self.logit_fc(x)
+        loss = self.bce(logit, target) * logit.size(1)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(self.params, 5.)
+        self.optim.step()
+        # ---- step B, node branch (:183-254 with --delta 0)
+        for p in self.params:
+            p.grad = None
+        feat, x = self._model(feats_h.to(dev), boxes_h.to(dev), ids, mask)                         # :185
+        adj_true = adj_h.to(dev)
+        adj_true = adj_true.triu(1) + adj_true.tril(-1)                                             # :187-188
+        node_feats = x.unsqueeze(1).repeat(1, self.N, 1)                                            # :228
+        node_feats = self.node_fc(node_feats)
+        node_feats, feat_grad = self.gu.add_feature_noise_v2(node_feats, sigma=self.sigma)
+        node_feats, _ = self.generator(node_feats, adj_true)
+        d_loss = self.compute_kl_loss(node_feats, feat) * logit.size(1)
+        loss_grad = self.loss_func(node_feats, feat_grad, sigma=self.sigma)
+        loss_sm = 0.15 * d_loss + 6 * loss_grad
+        x_gen = self.fusion_fc(torch.cat([x, torch.tanh(node_feats.mean(1))], dim=-1))
+        logit = self.logit_fc(x_gen)
+        loss = self.bce(logit, target) * logit.size(1) + 1.1 * loss_sm
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(self.params, 5.)
+        self.optim.step()
+        return loss.detach()
