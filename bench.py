@@ -476,23 +476,21 @@ def run_iteration(args):
     loss_host = torch.zeros(1).pin_memory()
     it.prefetch(batches[0])
     resident = [t.to(dev) for t in batches[0]]
-    graph = None
-    if args.graph_iteration:
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                it.iteration(resident)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            graph_loss = it.iteration(resident)
+    import xggm_b200 as X
+    graphs = None
+    if not args.no_graph:
+        # one captured graph per GGM branch the schedule can draw (delta = 0: node only); X.GraphedStep keeps the
+        # library's dropout fresh across replays (device epoch) and torch's own RNG is graph-aware
+        branches = ["node"] if args.delta <= 0 else (["relation"] if args.delta >= 10 else ["node", "relation"])
+        graphs = {b: X.GraphedStep(lambda *t, b=b: it.iteration(list(t), b), resident, warmup=2) for b in branches}
+
+    def run_graph(src):
+        g = graphs[it.branch.next()]
+        return g(*src)
 
     def resident_iter():
-        if graph is not None:
-            graph.replay()
-            return graph_loss
+        if graphs is not None:
+            return run_graph(resident)
         return it.iteration(resident)
 
     k = [0]
@@ -501,13 +499,7 @@ def run_iteration(args):
         cur = it.take()                      # this iteration's batch (copied while the previous one computed)
         k[0] += 1
         it.prefetch(batches[k[0] % 2])       # next iteration's H2D on the side stream
-        if graph is not None:
-            for d, s in zip(resident, cur):
-                d.copy_(s, non_blocking=True)
-            graph.replay()
-            l = graph_loss
-        else:
-            l = it.iteration(cur)
+        l = run_graph(cur) if graphs is not None else it.iteration(cur)
         loss_host.copy_(l.reshape(1), non_blocking=True)
 
     def timed(fn, n):
@@ -568,7 +560,9 @@ def run_iteration(args):
         try:
             from oracle.ref_step import ReferenceIteration, reference_available
             if reference_available():
-                ref = ReferenceIteration(dev, autocast=autocast)
+                import contextlib
+                with contextlib.redirect_stdout(sys.stderr):     # the reference prints its layer counts
+                    ref = ReferenceIteration(dev, autocast=autocast)
                 for _ in range(2):
                     ref.iteration(batches[0])
                 torch.cuda.synchronize()
@@ -598,7 +592,8 @@ def run_iteration(args):
                    "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world}",
                    "parameters": n_par, "allreduce_bytes_per_iteration": 2 * 4 * n_par if world > 1 else 0,
                    "l2": "inputs and activations far exceed the 126 MB L2 (no flush needed)",
-                   "launch": "CUDA graph of the whole iteration" if graph is not None else "eager launches"},
+                   "launch": "one CUDA-graph replay per iteration (xggm_b200.GraphedStep, one graph per GGM branch)"
+                             if graphs is not None else "eager launches"},
         "e2e": {"value": B * world / (ms_e2e / args.steps * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
                 "note": "one H2D of the batch per iteration (the reference copies it in both steps), overlapped with "
@@ -633,7 +628,6 @@ def main():
                     help="block: the graph block's training step (default, the headline); iteration: the full trainer "
                          "iteration with a stock-PyTorch LXMERT around the block (BASELINE configs[1]/[2])")
     ap.add_argument("--delta", type=int, default=0, help="--workload iteration: GGM branch threshold out of 10 (0 = VQA-CP recipe)")
-    ap.add_argument("--graph-iteration", action="store_true", help="--workload iteration: capture the iteration in a CUDA graph")
     ap.add_argument("--no-eager", action="store_true", help="--workload iteration: skip the eager reference baseline")
     args = ap.parse_args()
     if args.workload == "iteration" and args.impl != "reference":

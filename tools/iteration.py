@@ -128,11 +128,11 @@ class XGGMIteration:
         self._reduce_and_step()
         return loss.detach()
 
-    def step_b(self, feats, boxes, ids, mask, target, adj_true):
+    def step_b(self, feats, boxes, ids, mask, target, adj_true, branch=None):
         X = self.X
         self.optim.zero_grad()
         visn, pooled = self._encode(feats, boxes, ids, mask)
-        if self.branch.next() == "relation":
+        if (branch or self.branch.next()) == "relation":
             x_gen, loss_sm, _, _ = self.heads.relation_step(pooled, visn, adj_true, 1.0, self.A, kl_weight=8.0)
             w = 6.0
         else:
@@ -144,10 +144,12 @@ class XGGMIteration:
         self._reduce_and_step()
         return loss.detach()
 
-    def iteration(self, batch):
+    def iteration(self, batch, branch=None):
+        """branch: None = draw it from the rank-synchronous schedule (eager runs); 'node' / 'relation' = fixed (one
+        CUDA graph is captured per branch and the schedule picks the graph to replay)."""
         feats, boxes, ids, mask, target, adj = batch
         self.step_a(feats, boxes, ids, mask, target)
-        return self.step_b(feats, boxes, ids, mask, target, adj)
+        return self.step_b(feats, boxes, ids, mask, target, adj, branch)
 
     def block_only(self, batch):
         """Just the library's part of step B on fixed encoder outputs (for the share-of-iteration figure)."""
