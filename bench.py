@@ -206,6 +206,7 @@ def workload_config(n_gpus, B=B_PER_GPU, gnn=GNN, precision="fp32", branch="node
             "launch": "one CUDA-graph replay per step (xggm_b200.GraphedStep)"}
 
 
+
 def synthetic_inputs(seed, B, n_nodes=N_NODES, hidden=HID):
     """Synthetic block inputs in the shapes of SURVEY.md section 8d (the same recipe as the oracle's input factory,
     restated here so that the measured arm does not touch oracle/): visn = layer_norm(N(0,1)) -- LXMERT's visual
@@ -249,12 +250,17 @@ def run_gpu(args):
     early = []
     if os.environ.get("XGGM_DDP_OVERLAP") == "1":
         early = list(model.fusion_fc.parameters()) + list(model.generator.gnn_layers[-1].parameters())
-    grads = FlatGrads(model.parameters(), early=early)
+    # N > 1: the gradient bucket (and the parameter buffer) live in NVLink-addressable symmetric memory and the
+    # all-reduce + clip + BertAdam run as the fused peer-memory sequence (xggm_dp_bertadam_step); XGGM_DP_FUSED=0 keeps
+    # the NCCL all-reduce + separate clip / update kernels for A/B runs
+    want_fused = world > 1 and os.environ.get("XGGM_DP_FUSED", "1") != "0" and not early
+    grads = FlatGrads(model.parameters(), early=early, symmetric=want_fused)
     flat_grad = grads.flat
     # BertAdam over the block's parameters as the trainer configures it for the down-task group (4 * --lr with
     # --lr 1e-6, script/vqacpv2.sh:24, src/vqa/vqacpv2.py:125-128; constant schedule so the captured step stays
     # valid), preceded by clip_grad_norm_(., 5.) (src/vqa/vqacpv2.py:252)
     optim = X.BertAdam(model.parameters(), lr=4e-6, flat_grads=grads)
+    fused_dp = want_fused and optim.fused_allreduce_available()
 
     visn_h, xp_h, adj_h = (t.pin_memory() for t in synthetic_inputs(9596 + rank, B, N_NODES, HID))
     cot_h = torch.randn(B, HID, generator=torch.Generator().manual_seed(2 + rank)).pin_memory()
@@ -278,8 +284,11 @@ def run_gpu(args):
             # loss = <x_gen, cot> + w * loss_sm, where cot stands for d BCE(logit_fc(x_gen)) / d x_gen of the answer head
             # that follows the block (outside the hot path): its backward pass is seeded directly with (cot, w)
             torch.autograd.backward([x_gen, loss_sm], [cot_d, w_sm])
-        grads.all_reduce(average=True)  # NCCL gradient all-reduce (no-op at world size 1)
-        optim.step(X.clip_grad_norm_(grads, 5.0))   # one norm reduction + one fused update kernel
+        if fused_dp:
+            optim.step_allreduce(5.0)       # reduce-scatter + clip + BertAdam (1/N of it) + parameter all-gather over NVLink
+        else:
+            grads.all_reduce(average=True)  # NCCL gradient all-reduce (no-op at world size 1)
+            optim.step(X.clip_grad_norm_(grads, 5.0))   # one norm reduction + one fused update kernel
         return loss_sm.detach()
 
     # the public entry point for a captured step: one CUDA-graph launch per step (xggm_b200.GraphedStep)
@@ -411,7 +420,10 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": workload_config(world, B, args.gnn, args.precision, args.branch),
+        "config": dict(workload_config(world, B, args.gnn, args.precision, args.branch),
+                       collective=("none (one GPU)" if world == 1 else
+                                   ("fused reduce-scatter + clip + BertAdam + parameter all-gather over NVLink peer memory "
+                                    "(xggm_dp_bertadam_step)" if fused_dp else "NCCL all-reduce (AVG) of the flat gradient bucket"))),
         "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,

@@ -354,6 +354,36 @@ typedef struct {
 int xggm_bertadam_step_ex(float* p, const float* g, float* m, float* v, long long n, double lr, double b1,
                           double b2, double eps, double weight_decay, const float* sumsq, double max_norm,
                           const xggm_lr_schedule_t* sched, xggm_stream_t s);
+/* ------------------------------------------------------------------------- *
+ * Data-parallel optimiser step over NVLink / NVSwitch PEER MEMORY (one process per GPU): the gradient
+ * all-reduce (average), clip_grad_norm_, BertAdam and the parameter all-gather as one fused sequence in which rank r
+ * owns the r-th 1/world slice of the flat buffers: it averages its slice of the `world` peer gradient buckets with
+ * 16-byte loads from peer memory (reduce-scatter), the squared norms of the slices meet through one word per peer
+ * (summed in rank order: bit-identical clip coefficient everywhere), BertAdam runs on the slice only and the new
+ * parameters are pushed into every peer's parameter buffer with remote stores (all-gather).  Five short kernels on the
+ * caller's stream; the cross-GPU hand-shakes are system-scope flag words in the peers' control blocks (bounded waits:
+ * a missing peer is a CUDA error after 2 s).  CUDA-graph capturable (the epoch lives in the control block).
+ *   peers->grad[k] / param[k] : rank k's flat gradient / parameter buffer (n floats each, 16-byte aligned), mapped in
+ *                               this process (torch symmetric memory / CUDA IPC / VMM -- the library only sees pointers)
+ *   peers->ctl[k]             : rank k's control block, XGGM_DP_CTL_BYTES bytes, zeroed once at allocation
+ *   m, v                      : this rank's moment buffers (only its slice is touched)
+ *   range_lo/hi               : the bucket's ACTIVE element ranges (multiples of 4; parameters without a gradient this
+ *                               step are skipped as optimization.py:139-141 does); n_ranges <= XGGM_DP_MAX_RANGES
+ *   sumsq_out?                : receives the squared total norm of the averaged gradient
+ * Every rank must make the same call (same n, ranges, hyper-parameters) once per step.  world == 1 is valid. */
+#define XGGM_DP_MAX_RANKS 16
+#define XGGM_DP_MAX_RANGES 8
+#define XGGM_DP_CTL_BYTES 512
+typedef struct {
+    int rank, world;
+    void* grad[XGGM_DP_MAX_RANKS];
+    void* param[XGGM_DP_MAX_RANKS];
+    void* ctl[XGGM_DP_MAX_RANKS];
+} xggm_dp_peers_t;
+int xggm_dp_bertadam_step(const xggm_dp_peers_t* peers, float* m, float* v, long long n, const long long* range_lo,
+                          const long long* range_hi, int n_ranges, double lr, double b1, double b2, double eps,
+                          double weight_decay, double max_norm, const xggm_lr_schedule_t* sched, float* sumsq_out,
+                          xggm_stream_t s);
 /* elementwise sigmoid (encoder_adj tail, src/vqa/vqacpv2_model.py:91-94) */
 int xggm_sigmoid_fwd(const float* x, float* y, long long n, xggm_stream_t s);
 int xggm_sigmoid_bwd(const float* gy, const float* y, float* gx, long long n, xggm_stream_t s);

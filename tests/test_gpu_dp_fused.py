@@ -1,0 +1,96 @@
+"""Fused data-parallel optimiser step over NVLink peer memory (xggm_dp_bertadam_step) against the NCCL path
+(all_reduce AVG + clip_grad_norm_ + BertAdam.step) on two GPUs of one box.  Skipped with fewer than two GPUs."""
+import os
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, out):
+    os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank), "WORLD_SIZE": str(world),
+                       "LOCAL_RANK": str(rank)})
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import xggm_b200 as X
+    from xggm_b200.ddp import FlatGrads
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", device_id=dev)
+    try:
+        results = {}
+        for mode in ("nccl", "fused", "fused_graph"):
+            torch.manual_seed(7)                                  # same initial weights on both ranks and in both modes
+            mod = X.XGGMHeads(128, "GCN", 2).to(dev).train()
+            fg = FlatGrads(mod.parameters(), symmetric=(mode != "nccl"))
+            opt = X.BertAdam(mod.parameters(), lr=1e-2, warmup=0.1, t_total=20, flat_grads=fg)
+            if mode != "nccl":
+                assert opt.fused_allreduce_available(), "symmetric memory not available"
+            g = torch.Generator(device="cpu").manual_seed(100 + rank)   # different data per rank
+            visn = torch.randn(4, 36, 128, generator=g).to(dev)
+            xp = torch.tanh(torch.randn(4, 128, generator=g)).to(dev)
+            adj = torch.rand(4, 36, 36, generator=g).to(dev)
+            randn = torch.randn(4, 36, 128, generator=g).to(dev)
+            masks = [(torch.rand(4, 36, 128, generator=g) >= 0.5).to(torch.uint8).to(dev) for _ in range(6)]
+
+            def step():
+                fg.zero_()
+                x = xp.clone().requires_grad_(True)
+                f = visn.clone().requires_grad_(True)
+                with X.functional.inject_keep_masks(list(masks)):
+                    x_gen, loss_sm, _, _ = mod.node_step(x, f, adj, 1.0, 50, randn)
+                (x_gen.sum() + loss_sm).backward()
+                if mode == "nccl":
+                    fg.all_reduce(average=True)
+                    opt.step(X.clip_grad_norm_(fg, 0.5))
+                else:
+                    opt.step_allreduce(0.5)
+
+            if mode == "fused_graph":
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    step()
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    step()
+                for _ in range(3):
+                    graph.replay()
+            else:
+                for _ in range(4):
+                    step()
+            torch.cuda.synchronize()
+            results[mode] = torch.cat([p.detach().reshape(-1) for p in mod.parameters()]).cpu()
+            assert opt.groups[0].step == 4
+            dist.barrier()
+        # both ranks hold the same parameters in every mode
+        flat = results["fused"].to(dev)
+        other = flat.clone()
+        dist.broadcast(other, src=0)
+        same_across_ranks = bool(torch.equal(flat, other))
+        if rank == 0:
+            torch.save({"results": results, "same": same_across_ranks}, out)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fused_dp_step_matches_nccl_path(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker, args=(2, 29533, out), nprocs=2, join=True)
+    r = torch.load(out)
+    ref, fused, graph = r["results"]["nccl"], r["results"]["fused"], r["results"]["fused_graph"]
+    assert r["same"], "ranks diverged after the fused step"
+    moved = float((ref - fused).abs().max())
+    scale = float(ref.abs().max())
+    # same arithmetic up to the order of the 2-term average and of the norm partials
+    assert moved <= 2e-6 * scale + 1e-7, moved
+    assert float((ref - graph).abs().max()) <= 2e-6 * scale + 1e-7

@@ -81,6 +81,7 @@ SIGNATURES = {
     "xggm_grad_sumsq": [_vp, _ll, _vp, _i, _vp],
     "xggm_bertadam_step": [_vp, _vp, _vp, _vp, _ll, _d, _d, _d, _d, _d, _vp, _d, _vp],
     "xggm_bertadam_step_ex": [_vp, _vp, _vp, _vp, _ll, _d, _d, _d, _d, _d, _vp, _d, _vp, _vp],
+    "xggm_dp_bertadam_step": [_vp, _vp, _vp, _ll, _vp, _vp, _i, _d, _d, _d, _d, _d, _d, _vp, _vp, _vp],
     "xggm_sigmoid_fwd": [_vp, _vp, _ll, _vp],
     "xggm_sigmoid_bwd": [_vp, _vp, _vp, _ll, _vp],
     "xggm_keep_mask": [_vp, _ll, _f, _u64, _u64, _vp, _vp],
@@ -142,6 +143,15 @@ class LrSchedule(C.Structure):
     """xggm_lr_schedule_t of include/xggm_b200.h."""
     _fields_ = [("step_dev", C.c_void_p), ("ticket_dev", C.c_void_p), ("warmup", C.c_double),
                 ("t_total", C.c_longlong), ("schedule", C.c_int), ("advance", C.c_int)]
+
+
+DP_MAX_RANKS, DP_MAX_RANGES, DP_CTL_BYTES = 16, 8, 512
+
+
+class DpPeers(C.Structure):
+    """xggm_dp_peers_t of include/xggm_b200.h."""
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("grad", C.c_void_p * DP_MAX_RANKS),
+                ("param", C.c_void_p * DP_MAX_RANKS), ("ctl", C.c_void_p * DP_MAX_RANKS)]
 
 
 PRECISIONS = {"fp32": 0, "bf16": 1, "fp32_simt": 2}

@@ -1001,6 +1001,14 @@ int xggm_bertadam_step_ex(float* p, const float* g, float* m, float* v, long lon
     XGGM_REQUIRE(n >= 0 && (n == 0 || (p && g && m && v)) && b1 >= 0.0 && b1 < 1.0 && b2 >= 0.0 && b2 < 1.0 && eps >= 0.0);
     return bertadam_step(p, g, m, v, n, lr, b1, b2, eps, weight_decay, sumsq, max_norm, sched, as_stream(s));
 }
+int xggm_dp_bertadam_step(const xggm_dp_peers_t* peers, float* m, float* v, long long n, const long long* range_lo,
+                          const long long* range_hi, int n_ranges, double lr, double b1, double b2, double eps,
+                          double weight_decay, double max_norm, const xggm_lr_schedule_t* sched, float* sumsq_out,
+                          xggm_stream_t s) {
+    XGGM_REQUIRE(b1 >= 0.0 && b1 < 1.0 && b2 >= 0.0 && b2 < 1.0 && eps >= 0.0);
+    return dp_bertadam_step(peers, m, v, n, range_lo, range_hi, n_ranges, lr, b1, b2, eps, weight_decay, max_norm, sched,
+                            sumsq_out, as_stream(s));
+}
 int xggm_sigmoid_fwd(const float* x, float* y, long long n, xggm_stream_t s) {
     if (n == 0) return XGGM_OK;
     XGGM_REQUIRE(x && y && n >= 0);

@@ -95,6 +95,9 @@ int bce_logits_bwd(const float* x, const float* t, const float* gloss, float sca
 int grad_sumsq(const float* g, long long n, float* out, int accumulate, cudaStream_t st);
 int bertadam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double b1, double b2, double eps,
                   double wd, const float* sumsq, double max_norm, const xggm_lr_schedule_t* sched, cudaStream_t st);
+int dp_bertadam_step(const xggm_dp_peers_t* peers, float* m, float* v, long long n, const long long* range_lo,
+                     const long long* range_hi, int n_ranges, double lr, double b1, double b2, double eps, double wd,
+                     double max_norm, const xggm_lr_schedule_t* sched, float* sumsq_out, cudaStream_t st);
 long long weight_planes_elems(int N, int K);
 void weight_planes_views(void* buf, int N, int K, __nv_bfloat16** hi, __nv_bfloat16** lo, __nv_bfloat16** thi,
                          __nv_bfloat16** tlo);

@@ -196,4 +196,217 @@ int bertadam_step(float* p, const float* g, float* m, float* v, long long n, dou
     return XGGM_OK;
 }
 
+
+
+// ================================================================================================
+// Data-parallel optimiser step over NVLink / NVSwitch peer memory (one process per GPU):
+//     gradient all-reduce (AVG)  +  clip_grad_norm_  +  BertAdam  +  parameter all-gather
+// as ONE fused sequence in which every rank owns 1/W of the flat buffers:
+//   K1 dp_begin   publish "my gradient bucket is complete" (epoch flag) to every peer
+//   K2 dp_reduce  wait for all peers' flags; reduce-SCATTER: average MY slice over the W peer buckets (16-byte loads
+//                 straight from peer memory) and accumulate its squared norm
+//   K3 dp_norm    publish my partial squared norm to every peer
+//   K4 dp_adam    wait; total norm = sum of the W partials in rank order (bit-identical on every rank); BertAdam on MY
+//                 slice only (1/W of the update work) and PUSH the new parameters into every peer's parameter buffer
+//                 (all-gather by remote stores); last CTA publishes "my slice has landed"
+//   K5 dp_end     wait until every peer's slice has landed here
+// Compared with ncclAllReduce + sumsq + update this moves the same gradient bytes once over the fabric (reduce-scatter)
+// plus the parameters once (all-gather) -- the volume of one ring all-reduce -- but drops the separate norm pass,
+// does 1/W of the Adam work per GPU, and has no collective-launch latency: flags are plain system-scope words in peer
+// memory (torch symmetric memory allocates and exchanges the buffers; this file only sees raw pointers).
+// Every wait is bounded: a peer that never arrives becomes a CUDA error after 2 s, never a hung GPU.
+// ================================================================================================
+constexpr int DP_MAX_RANKS = 16;
+constexpr int DP_CTL_EPOCH = 0, DP_CTL_TICKET = 1, DP_CTL_SLICE_SUMSQ = 2, DP_CTL_FLAG_A = 16, DP_CTL_FLAG_B = 32, DP_CTL_FLAG_C = 48,
+              DP_CTL_PARTIAL = 64;   // uint32 word offsets inside a rank's control block (XGGM_DP_CTL_BYTES)
+struct DpPeers {
+    int rank, world;
+    float* grad[DP_MAX_RANKS];
+    float* param[DP_MAX_RANKS];
+    unsigned int* ctl[DP_MAX_RANKS];
+};
+struct DpRanges {
+    int count;
+    long long lo[XGGM_DP_MAX_RANGES], hi[XGGM_DP_MAX_RANGES];
+};
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_peer_f4(const float* p) {   // peer memory: bypass L1, no read-only path
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_peer_f4(float* p, const float4& v) {
+    asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// block-wide: wait until every peer's flag word (base + k) has reached `epoch`
+__device__ __forceinline__ void dp_wait_flags(const unsigned int* ctl, int base, int world, unsigned int epoch) {
+    if ((int)threadIdx.x < world) {
+        unsigned long long t0, t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while ((int)(ld_acquire_sys(ctl + base + threadIdx.x) - epoch) < 0) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > 2000000000ull) __trap();
+        }
+    }
+    __syncthreads();
+}
+__global__ void __launch_bounds__(32) dp_begin_kernel(const DpPeers pe) {
+    unsigned int* ctl = pe.ctl[pe.rank];
+    __shared__ unsigned int epoch_s;
+    if (threadIdx.x == 0) {
+        epoch_s = ctl[DP_CTL_EPOCH] + 1;
+        ctl[DP_CTL_EPOCH] = epoch_s;
+        ctl[DP_CTL_TICKET] = 0;
+        reinterpret_cast<float*>(ctl)[DP_CTL_SLICE_SUMSQ] = 0.f;
+        __threadfence_system();     // the backward kernels' gradient writes (earlier in this stream) before the flag
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < pe.world) st_release_sys(pe.ctl[threadIdx.x] + DP_CTL_FLAG_A + pe.rank, epoch_s);
+}
+__global__ void __launch_bounds__(256) dp_reduce_kernel(const DpPeers pe, long long slice_lo, long long slice_hi) {
+    unsigned int* ctl = pe.ctl[pe.rank];
+    const unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(ctl + DP_CTL_EPOCH);
+    dp_wait_flags(ctl, DP_CTL_FLAG_A, pe.world, epoch);
+    __shared__ float part[8];
+    const float inv = 1.f / (float)pe.world;
+    float acc = 0.f;
+    float* mine = pe.grad[pe.rank];
+    const long long n4 = (slice_hi - slice_lo) >> 2;     // slices are multiples of 4 floats
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const long long e = slice_lo + 4 * i;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < pe.world; ++k) {             // fixed rank order: the same sum on whichever rank owns the slice
+            const float4 v = ld_peer_f4(pe.grad[k] + e);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        s.x *= inv; s.y *= inv; s.z *= inv; s.w *= inv;
+        *reinterpret_cast<float4*>(mine + e) = s;
+        acc += (s.x * s.x + s.y * s.y) + (s.z * s.z + s.w * s.w);
+    }
+    const float r = block_sum_256(acc, part);
+    if (threadIdx.x == 0) atomicAdd(reinterpret_cast<float*>(ctl) + DP_CTL_SLICE_SUMSQ, r);
+}
+__global__ void __launch_bounds__(32) dp_norm_kernel(const DpPeers pe) {
+    unsigned int* ctl = pe.ctl[pe.rank];
+    const unsigned int epoch = ctl[DP_CTL_EPOCH];
+    const float v = reinterpret_cast<float*>(ctl)[DP_CTL_SLICE_SUMSQ];
+    if ((int)threadIdx.x < pe.world) {
+        unsigned int* peer = pe.ctl[threadIdx.x];
+        asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(reinterpret_cast<float*>(peer) + DP_CTL_PARTIAL + pe.rank), "f"(v) : "memory");
+        __threadfence_system();
+        st_release_sys(peer + DP_CTL_FLAG_B + pe.rank, epoch);
+    }
+}
+__global__ void __launch_bounds__(256)
+dp_adam_kernel(const DpPeers pe, long long slice_lo, long long slice_hi, const DpRanges rg, float* __restrict__ m,
+               float* __restrict__ v, const AdamArgs a, float* __restrict__ sumsq_out) {
+    unsigned int* ctl = pe.ctl[pe.rank];
+    const unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(ctl + DP_CTL_EPOCH);
+    dp_wait_flags(ctl, DP_CTL_FLAG_B, pe.world, epoch);
+    float total = 0.f;
+    for (int k = 0; k < pe.world; ++k) total += *reinterpret_cast<volatile float*>(reinterpret_cast<float*>(ctl) + DP_CTL_PARTIAL + k);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && sumsq_out) sumsq_out[0] = total;
+    float clip = 1.f;
+    if (a.max_norm > 0.f) {
+        const float c = a.max_norm / (sqrtf(total) + 1e-6f);
+        clip = c < 1.f ? c : 1.f;
+    }
+    float lr = a.lr;
+    if (a.step_dev && a.t_total > 0) {
+        const long long step = *reinterpret_cast<volatile long long*>(a.step_dev);
+        lr = (float)((double)a.lr * schedule_factor(a.schedule, (double)step / (double)a.t_total, a.warmup));
+    }
+    float* p_mine = pe.param[pe.rank];
+    const float* g_mine = pe.grad[pe.rank];
+    for (int r = 0; r < rg.count; ++r) {                  // the active ranges of the bucket, clipped to my slice
+        const long long lo = rg.lo[r] > slice_lo ? rg.lo[r] : slice_lo, hi = rg.hi[r] < slice_hi ? rg.hi[r] : slice_hi;
+        if (hi <= lo) continue;
+        const long long n4 = (hi - lo) >> 2;              // range bounds are multiples of 32 floats (FlatGrads alignment)
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+            const long long e = lo + 4 * i;
+            float4 pv = *reinterpret_cast<const float4*>(p_mine + e);
+            const float4 gv = *reinterpret_cast<const float4*>(g_mine + e);
+            float4 mv = *reinterpret_cast<float4*>(m + e), vv = *reinterpret_cast<float4*>(v + e);
+            adam1(pv.x, gv.x, mv.x, vv.x, a, lr, clip);
+            adam1(pv.y, gv.y, mv.y, vv.y, a, lr, clip);
+            adam1(pv.z, gv.z, mv.z, vv.z, a, lr, clip);
+            adam1(pv.w, gv.w, mv.w, vv.w, a, lr, clip);
+            *reinterpret_cast<float4*>(m + e) = mv;
+            *reinterpret_cast<float4*>(v + e) = vv;
+            for (int k = 0; k < pe.world; ++k) {          // all-gather by remote stores (own copy included)
+                const int kk = (pe.rank + k) % pe.world;  // start at home: spreads the fabric traffic over the peers
+                st_peer_f4(pe.param[kk] + e, pv);
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(ctl + DP_CTL_TICKET, 1u) == gridDim.x - 1) {   // last CTA of this rank: every slice element is on its way
+            __threadfence_system();
+            if (a.step_dev && a.advance) *a.step_dev += 1;
+            for (int k = 0; k < pe.world; ++k) st_release_sys(pe.ctl[k] + DP_CTL_FLAG_C + pe.rank, epoch);
+        }
+    }
+}
+__global__ void __launch_bounds__(32) dp_end_kernel(const DpPeers pe) {
+    unsigned int* ctl = pe.ctl[pe.rank];
+    const unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(ctl + DP_CTL_EPOCH);
+    dp_wait_flags(ctl, DP_CTL_FLAG_C, pe.world, epoch);
+    __threadfence_system();
+}
+
+int dp_bertadam_step(const xggm_dp_peers_t* peers, float* m, float* v, long long n, const long long* range_lo,
+                     const long long* range_hi, int n_ranges, double lr, double b1, double b2, double eps, double wd,
+                     double max_norm, const xggm_lr_schedule_t* sched, float* sumsq_out, cudaStream_t st) {
+    XGGM_REQUIRE(peers && m && v && n > 0 && peers->world >= 1 && peers->world <= DP_MAX_RANKS && peers->rank >= 0 &&
+                 peers->rank < peers->world && n_ranges >= 0 && n_ranges <= XGGM_DP_MAX_RANGES && (n_ranges == 0 || (range_lo && range_hi)));
+    DpPeers pe;
+    pe.rank = peers->rank; pe.world = peers->world;
+    for (int k = 0; k < DP_MAX_RANKS; ++k) {
+        const bool live = k < pe.world;
+        pe.grad[k] = live ? static_cast<float*>(peers->grad[k]) : nullptr;
+        pe.param[k] = live ? static_cast<float*>(peers->param[k]) : nullptr;
+        pe.ctl[k] = live ? static_cast<unsigned int*>(peers->ctl[k]) : nullptr;
+        if (live) XGGM_REQUIRE(pe.grad[k] && pe.param[k] && pe.ctl[k] && aligned16(pe.grad[k]) && aligned16(pe.param[k]));
+    }
+    XGGM_REQUIRE(aligned16(m) && aligned16(v));
+    DpRanges rg;
+    rg.count = n_ranges;
+    for (int r = 0; r < n_ranges; ++r) {
+        XGGM_REQUIRE(range_lo[r] % 4 == 0 && range_hi[r] % 4 == 0 && range_lo[r] >= 0 && range_hi[r] <= n);
+        rg.lo[r] = range_lo[r]; rg.hi[r] = range_hi[r];
+    }
+    // equal slices, 4-float granularity (the bucket length is a multiple of 32)
+    const long long per = ((n + pe.world - 1) / pe.world + 3) & ~3LL;
+    const long long lo = per * pe.rank < n ? per * pe.rank : n, hi = lo + per < n ? lo + per : n;
+    XGGM_REQUIRE(n % 4 == 0);
+    AdamArgs a{(float)lr, (float)b1, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2), (float)eps, (float)wd,
+               (float)max_norm, nullptr, nullptr, nullptr, 0.0, 0, 0, 0};
+    if (sched) {
+        XGGM_REQUIRE(sched->step_dev && sched->schedule >= 0 && sched->schedule <= 2);
+        a.step_dev = sched->step_dev; a.warmup = sched->warmup; a.t_total = sched->t_total;
+        a.schedule = sched->schedule; a.advance = sched->advance;
+    }
+    const int grid = stream_grid(hi - lo, 2048);
+    XGGM_LAUNCH((dp_begin_kernel), 1, 32, 0, st, pe);
+    XGGM_LAUNCH_CHECK();
+    XGGM_LAUNCH((dp_reduce_kernel), grid, 256, 0, st, pe, lo, hi);
+    XGGM_LAUNCH_CHECK();
+    XGGM_LAUNCH((dp_norm_kernel), 1, 32, 0, st, pe);
+    XGGM_LAUNCH_CHECK();
+    XGGM_LAUNCH((dp_adam_kernel), grid, 256, 0, st, pe, lo, hi, rg, m, v, a, sumsq_out);
+    XGGM_LAUNCH_CHECK();
+    XGGM_LAUNCH((dp_end_kernel), 1, 32, 0, st, pe);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+
 }  // namespace xggm

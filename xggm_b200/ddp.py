@@ -13,6 +13,33 @@ import torch
 import torch.distributed as dist
 
 
+def symmetric_empty(numel, dtype, device, zero=True):
+    """A tensor every rank of the default process group can address through NVLink / NVSwitch peer pointers
+    (torch symmetric memory: CUDA VMM allocations exchanged at rendezvous).  Returns (tensor, peer_pointers) -- the
+    base address of the same allocation on every rank, this process's mapping -- or (None, None) when symmetric
+    memory is not available (no NCCL group, one rank, or an older torch)."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) or dist.get_backend() != "nccl":
+        return None, None
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+        group = dist.group.WORLD
+        try:
+            symm_mem.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass
+        t = symm_mem.empty(numel, dtype=dtype, device=device)
+        hdl = symm_mem.rendezvous(t, group.group_name)
+        if zero:
+            t.zero_()
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        t._xggm_symm_handle = hdl          # keeps the mapping alive
+        return t, ptrs
+    except Exception as e:                 # pragma: no cover - depends on the platform
+        import warnings
+        warnings.warn(f"xggm_b200: symmetric memory unavailable ({e!r}); using NCCL collectives")
+        return None, None
+
+
 def shard_range(n_items, rank, world):
     """Contiguous shard [lo, hi) of ``n_items`` for ``rank``; sizes differ by at most one."""
     if not (0 <= rank < world):
@@ -32,7 +59,9 @@ class FlatGrads:
     backward pass is still computing; ``all_reduce()`` then only has the remaining bucket left.
     """
 
-    def __init__(self, params, early=()):
+    def __init__(self, params, early=(), symmetric=False):
+        """symmetric=True (NCCL group, world > 1): the bucket lives in NVLink-addressable symmetric memory so that
+        ``BertAdam.step_allreduce`` can run the fused reduce-scatter + clip + update + all-gather kernels on it."""
         params = [p for p in params if p.requires_grad]
         early_ids = {id(p) for p in early}
         self.params = [p for p in params if id(p) in early_ids] + [p for p in params if id(p) not in early_ids]
@@ -48,7 +77,15 @@ class FlatGrads:
             off += (p.numel() + align - 1) // align * align
             if id(p) in early_ids:
                 self.split = off
-        self.flat = torch.zeros(off, device=p0.device, dtype=p0.dtype)
+        self.peer_ptrs = self.ctl = self.ctl_ptrs = None
+        flat = None
+        if symmetric and p0.is_cuda and p0.dtype == torch.float32:
+            flat, self.peer_ptrs = symmetric_empty(off, p0.dtype, p0.device)
+            if flat is not None:
+                self.ctl, self.ctl_ptrs = symmetric_empty(128, torch.int32, p0.device)   # XGGM_DP_CTL_BYTES
+                if self.ctl is None:
+                    flat, self.peer_ptrs = None, None
+        self.flat = flat if flat is not None else torch.zeros(off, device=p0.device, dtype=p0.dtype)
         self.offsets = offs
         for p, o in zip(self.params, offs):
             p.grad = self.flat[o:o + p.numel()].view_as(p)

@@ -46,8 +46,14 @@ class _Group:
         self.grads = flat_grads if flat_grads is not None else FlatGrads(params)
         self.params = self.grads.params
         g = self.grads.flat
-        # parameters move into one flat buffer with the offsets of the gradient bucket
-        self.flat_p = torch.zeros_like(g)
+        # parameters move into one flat buffer with the offsets of the gradient bucket (in symmetric memory when the
+        # gradient bucket is: the fused data-parallel step pushes parameter slices into the peers' buffers)
+        self.param_ptrs = None
+        flat_p = None
+        if self.grads.peer_ptrs is not None:
+            from .ddp import symmetric_empty
+            flat_p, self.param_ptrs = symmetric_empty(g.numel(), g.dtype, g.device)
+        self.flat_p = flat_p if flat_p is not None else torch.zeros_like(g)
         base = g.data_ptr()
         for p in self.params:
             o = (p.grad.data_ptr() - base) // g.element_size()
@@ -162,6 +168,44 @@ class BertAdam:
             if g.flat_p.is_cuda:
                 from . import functional as XF
                 XF.refresh_weight_planes(g.params)     # one launch: both operand layouts of every cached weight
+
+    def fused_allreduce_available(self):
+        """True when every group's buckets live in symmetric memory and there is ONE group (the squared norm the
+        fused kernels clip by is the bucket's own)."""
+        return len(self.groups) == 1 and self.groups[0].param_ptrs is not None and self.groups[0].grads.ctl_ptrs is not None
+
+    def step_allreduce(self, max_norm=0.0, sumsq_out=None):
+        """Data-parallel step: gradient all-reduce (average) + clip_grad_norm_(max_norm) + BertAdam update, fused
+        over NVLink peer memory (xggm_dp_bertadam_step: reduce-scatter, 1/world of the update per rank, parameter
+        all-gather by remote stores).  Replaces ``grads.all_reduce(); optim.step(clip_grad_norm_(grads, max_norm))``.
+        Every rank must call it once per step.  Returns the device scalar holding the squared total norm."""
+        if not self.fused_allreduce_available():
+            raise RuntimeError("xggm_b200.BertAdam.step_allreduce needs one parameter group whose FlatGrads was built "
+                               "with symmetric=True under an NCCL process group (world > 1)")
+        import torch.distributed as dist
+        g = self.groups[0]
+        o = g.opts
+        _lib.check_device(g.flat_p)
+        g.grads.relink()
+        ranges = g.grads.active_ranges()
+        if len(ranges) > _lib.DP_MAX_RANGES:
+            ranges = [(ranges[0][0], ranges[-1][1])]
+        peers = _lib.DpPeers()
+        peers.rank, peers.world = dist.get_rank(), dist.get_world_size()
+        for k in range(peers.world):
+            peers.grad[k], peers.param[k], peers.ctl[k] = g.grads.peer_ptrs[k], g.param_ptrs[k], g.grads.ctl_ptrs[k]
+        lo = (C.c_longlong * len(ranges))(*[r[0] for r in ranges])
+        hi = (C.c_longlong * len(ranges))(*[r[1] for r in ranges])
+        sched = _lib.LrSchedule(g.step_dev.data_ptr(), g._ticket.data_ptr(), float(o["warmup"]), int(o["t_total"]),
+                                _SCHED_ID[o["schedule"]], 1)
+        if sumsq_out is None:
+            sumsq_out = torch.empty(1, device=g.flat_p.device, dtype=torch.float32)
+        call("xggm_dp_bertadam_step", C.cast(C.pointer(peers), C.c_void_p), ptr(g.m), ptr(g.v), g.flat_p.numel(), lo, hi,
+             len(ranges), float(o["lr"]), float(o["b1"]), float(o["b2"]), float(o["e"]), float(o["weight_decay"]),
+             float(max_norm), C.cast(C.pointer(sched), C.c_void_p), ptr(sumsq_out))
+        from . import functional as XF
+        XF.refresh_weight_planes(g.params)
+        return GradClip(sumsq_out, max_norm)
 
     # -- checkpointing (the reference trainers do not save optimiser state, SURVEY section 5; torch-style layout) ----
     def state_dict(self):
