@@ -89,8 +89,11 @@ def test_fused_dp_step_matches_nccl_path(tmp_path):
     r = torch.load(out)
     ref, fused, graph = r["results"]["nccl"], r["results"]["fused"], r["results"]["fused_graph"]
     assert r["same"], "ranks diverged after the fused step"
-    moved = float((ref - fused).abs().max())
-    scale = float(ref.abs().max())
-    # same arithmetic up to the order of the 2-term average and of the norm partials
-    assert moved <= 2e-6 * scale + 1e-7, moved
-    assert float((ref - graph).abs().max()) <= 2e-6 * scale + 1e-7
+    # Same arithmetic up to summation order -- but the parameter gradients themselves are reduced with atomics and
+    # differ in the last bits from run to run, and the Adam direction m / (sqrt(v) + e) is sign-like where |g| is
+    # tiny: compare against the step size lr * 3.2 (|update| <= lr * 0.1 / sqrt(0.001) in the first steps), as
+    # test_training_iteration_node_branch_matches_oracle_pipeline does.
+    step_size = 1e-2 * 3.2
+    assert float((ref - fused).abs().max()) <= 2e-3 * step_size, float((ref - fused).abs().max())
+    assert float((ref - graph).abs().max()) <= 2e-3 * step_size, float((ref - graph).abs().max())
+    assert float((ref - fused).norm()) <= 1e-4 * float((ref).norm())
