@@ -202,14 +202,13 @@ int bertadam_step(float* p, const float* g, float* m, float* v, long long n, dou
 // Data-parallel optimiser step over NVLink / NVSwitch peer memory (one process per GPU):
 //     gradient all-reduce (AVG)  +  clip_grad_norm_  +  BertAdam  +  parameter all-gather
 // as ONE fused sequence in which every rank owns 1/W of the flat buffers:
-//   K1 dp_begin   publish "my gradient bucket is complete" (epoch flag) to every peer
-//   K2 dp_reduce  wait for all peers' flags; reduce-SCATTER: average MY slice over the W peer buckets (16-byte loads
-//                 straight from peer memory) and accumulate its squared norm
-//   K3 dp_norm    publish my partial squared norm to every peer
-//   K4 dp_adam    wait; total norm = sum of the W partials in rank order (bit-identical on every rank); BertAdam on MY
+//   dp_reduce  publish "my gradient bucket is complete" (epoch flag) to every peer and wait for theirs; reduce-SCATTER:
+//              average MY slice over the W peer buckets (16-byte loads straight from peer memory), accumulate its
+//              squared norm; the last CTA publishes that partial norm to every peer
+//   dp_adam    wait; total norm = sum of the W partials in rank order (bit-identical on every rank); BertAdam on MY
 //                 slice only (1/W of the update work) and PUSH the new parameters into every peer's parameter buffer
-//                 (all-gather by remote stores); last CTA publishes "my slice has landed"
-//   K5 dp_end     wait until every peer's slice has landed here
+//                 (all-gather by remote stores); the last CTA publishes "my slice has landed"
+//   dp_end     wait until every peer's slice has landed here; advance the epoch
 // Compared with ncclAllReduce + sumsq + update this moves the same gradient bytes once over the fabric (reduce-scatter)
 // plus the parameters once (all-gather) -- the volume of one ring all-reduce -- but drops the separate norm pass,
 // does 1/W of the Adam work per GPU, and has no collective-launch latency: flags are plain system-scope words in peer
@@ -217,7 +216,7 @@ int bertadam_step(float* p, const float* g, float* m, float* v, long long n, dou
 // Every wait is bounded: a peer that never arrives becomes a CUDA error after 2 s, never a hung GPU.
 // ================================================================================================
 constexpr int DP_MAX_RANKS = 16;
-constexpr int DP_CTL_EPOCH = 0, DP_CTL_TICKET = 1, DP_CTL_SLICE_SUMSQ = 2, DP_CTL_FLAG_A = 16, DP_CTL_FLAG_B = 32, DP_CTL_FLAG_C = 48,
+constexpr int DP_CTL_EPOCH = 0, DP_CTL_TICKET = 1, DP_CTL_SLICE_SUMSQ = 2, DP_CTL_TICKET2 = 3, DP_CTL_FLAG_A = 16, DP_CTL_FLAG_B = 32, DP_CTL_FLAG_C = 48,
               DP_CTL_PARTIAL = 64;   // uint32 word offsets inside a rank's control block (XGGM_DP_CTL_BYTES)
 struct DpPeers {
     int rank, world;
@@ -257,22 +256,15 @@ __device__ __forceinline__ void dp_wait_flags(const unsigned int* ctl, int base,
     }
     __syncthreads();
 }
-__global__ void __launch_bounds__(32) dp_begin_kernel(const DpPeers pe) {
-    unsigned int* ctl = pe.ctl[pe.rank];
-    __shared__ unsigned int epoch_s;
-    if (threadIdx.x == 0) {
-        epoch_s = ctl[DP_CTL_EPOCH] + 1;
-        ctl[DP_CTL_EPOCH] = epoch_s;
-        ctl[DP_CTL_TICKET] = 0;
-        reinterpret_cast<float*>(ctl)[DP_CTL_SLICE_SUMSQ] = 0.f;
-        __threadfence_system();     // the backward kernels' gradient writes (earlier in this stream) before the flag
-    }
-    __syncthreads();
-    if ((int)threadIdx.x < pe.world) st_release_sys(pe.ctl[threadIdx.x] + DP_CTL_FLAG_A + pe.rank, epoch_s);
-}
+// K2: publish "my gradient bucket is complete", wait for every peer's, reduce-scatter my slice, and (last CTA) publish
+// the slice's squared norm.  The epoch word only changes in dp_end_kernel, so every CTA of K2 / K4 reads the same value.
 __global__ void __launch_bounds__(256) dp_reduce_kernel(const DpPeers pe, long long slice_lo, long long slice_hi) {
     unsigned int* ctl = pe.ctl[pe.rank];
-    const unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(ctl + DP_CTL_EPOCH);
+    const unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(ctl + DP_CTL_EPOCH) + 1u;
+    if (blockIdx.x == 0) {
+        __threadfence_system();     // the backward kernels' gradient writes (earlier in this stream) before the flag
+        if ((int)threadIdx.x < pe.world) st_release_sys(pe.ctl[threadIdx.x] + DP_CTL_FLAG_A + pe.rank, epoch);
+    }
     dp_wait_flags(ctl, DP_CTL_FLAG_A, pe.world, epoch);
     __shared__ float part[8];
     const float inv = 1.f / (float)pe.world;
@@ -291,24 +283,33 @@ __global__ void __launch_bounds__(256) dp_reduce_kernel(const DpPeers pe, long l
         acc += (s.x * s.x + s.y * s.y) + (s.z * s.z + s.w * s.w);
     }
     const float r = block_sum_256(acc, part);
-    if (threadIdx.x == 0) atomicAdd(reinterpret_cast<float*>(ctl) + DP_CTL_SLICE_SUMSQ, r);
-}
-__global__ void __launch_bounds__(32) dp_norm_kernel(const DpPeers pe) {
-    unsigned int* ctl = pe.ctl[pe.rank];
-    const unsigned int epoch = ctl[DP_CTL_EPOCH];
-    const float v = reinterpret_cast<float*>(ctl)[DP_CTL_SLICE_SUMSQ];
-    if ((int)threadIdx.x < pe.world) {
-        unsigned int* peer = pe.ctl[threadIdx.x];
-        asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(reinterpret_cast<float*>(peer) + DP_CTL_PARTIAL + pe.rank), "f"(v) : "memory");
-        __threadfence_system();
-        st_release_sys(peer + DP_CTL_FLAG_B + pe.rank, epoch);
+    __shared__ unsigned int last_s;
+    if (threadIdx.x == 0) {
+        atomicAdd(reinterpret_cast<float*>(ctl) + DP_CTL_SLICE_SUMSQ, r);
+        __threadfence();
+        last_s = (atomicAdd(ctl + DP_CTL_TICKET, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (last_s) {       // every CTA's partial is in: publish the slice norm to all peers (one lane per peer)
+        const float v = *reinterpret_cast<volatile float*>(reinterpret_cast<float*>(ctl) + DP_CTL_SLICE_SUMSQ);
+        __syncthreads();
+        if ((int)threadIdx.x < pe.world) {
+            unsigned int* peer = pe.ctl[threadIdx.x];
+            asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(reinterpret_cast<float*>(peer) + DP_CTL_PARTIAL + pe.rank), "f"(v) : "memory");
+            __threadfence_system();
+            st_release_sys(peer + DP_CTL_FLAG_B + pe.rank, epoch);
+        }
+        if (threadIdx.x == 0) {   // reset for the next step
+            ctl[DP_CTL_TICKET] = 0u;
+            reinterpret_cast<float*>(ctl)[DP_CTL_SLICE_SUMSQ] = 0.f;
+        }
     }
 }
 __global__ void __launch_bounds__(256)
 dp_adam_kernel(const DpPeers pe, long long slice_lo, long long slice_hi, const DpRanges rg, float* __restrict__ m,
                float* __restrict__ v, const AdamArgs a, float* __restrict__ sumsq_out) {
     unsigned int* ctl = pe.ctl[pe.rank];
-    const unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(ctl + DP_CTL_EPOCH);
+    const unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(ctl + DP_CTL_EPOCH) + 1u;
     dp_wait_flags(ctl, DP_CTL_FLAG_B, pe.world, epoch);
     float total = 0.f;
     for (int k = 0; k < pe.world; ++k) total += *reinterpret_cast<volatile float*>(reinterpret_cast<float*>(ctl) + DP_CTL_PARTIAL + k);
@@ -349,8 +350,9 @@ dp_adam_kernel(const DpPeers pe, long long slice_lo, long long slice_hi, const D
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (atomicAdd(ctl + DP_CTL_TICKET, 1u) == gridDim.x - 1) {   // last CTA of this rank: every slice element is on its way
+        if (atomicAdd(ctl + DP_CTL_TICKET2, 1u) == gridDim.x - 1) {   // last CTA of this rank: every slice element is on its way
             __threadfence_system();
+            ctl[DP_CTL_TICKET2] = 0u;
             if (a.step_dev && a.advance) *a.step_dev += 1;
             for (int k = 0; k < pe.world; ++k) st_release_sys(pe.ctl[k] + DP_CTL_FLAG_C + pe.rank, epoch);
         }
@@ -358,9 +360,10 @@ dp_adam_kernel(const DpPeers pe, long long slice_lo, long long slice_hi, const D
 }
 __global__ void __launch_bounds__(32) dp_end_kernel(const DpPeers pe) {
     unsigned int* ctl = pe.ctl[pe.rank];
-    const unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(ctl + DP_CTL_EPOCH);
+    const unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(ctl + DP_CTL_EPOCH) + 1u;
     dp_wait_flags(ctl, DP_CTL_FLAG_C, pe.world, epoch);
     __threadfence_system();
+    if (threadIdx.x == 0) ctl[DP_CTL_EPOCH] = epoch;    // the step is over on this rank: next call, next epoch
 }
 
 int dp_bertadam_step(const xggm_dp_peers_t* peers, float* m, float* v, long long n, const long long* range_lo,
@@ -396,11 +399,7 @@ int dp_bertadam_step(const xggm_dp_peers_t* peers, float* m, float* v, long long
         a.schedule = sched->schedule; a.advance = sched->advance;
     }
     const int grid = stream_grid(hi - lo, 2048);
-    XGGM_LAUNCH((dp_begin_kernel), 1, 32, 0, st, pe);
-    XGGM_LAUNCH_CHECK();
     XGGM_LAUNCH((dp_reduce_kernel), grid, 256, 0, st, pe, lo, hi);
-    XGGM_LAUNCH_CHECK();
-    XGGM_LAUNCH((dp_norm_kernel), 1, 32, 0, st, pe);
     XGGM_LAUNCH_CHECK();
     XGGM_LAUNCH((dp_adam_kernel), grid, 256, 0, st, pe, lo, hi, rg, m, v, a, sumsq_out);
     XGGM_LAUNCH_CHECK();
