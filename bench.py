@@ -374,7 +374,7 @@ def run_gpu(args):
 
     # secondary leg: the same step on the single-pass bf16 engine (BASELINE cfg 3 arithmetic, 2e-2 budget)
     alt = None
-    if args.precision == "fp32" and graphed is not None:
+    if args.precision == "fp32" and graphed is not None and not args.quick:
         X.set_precision("bf16")
         for _ in range(2):
             compute(visn_d.detach(), xp_d.detach(), adj_d)
@@ -414,8 +414,11 @@ def run_gpu(args):
     peak = peaks["bf16_tflops"]
     h2d = sum(t.numel() * 4 for t in (visn_h, xp_h, adj_h))
     threads = os.cpu_count() or 1
-    cpu_sec, cpu_kind = cpu_reference_steps(5, 2, threads, branch=args.branch, gnn=args.gnn)
-    eager_ms, eager_kind = eager_gpu_steps(dev, 10, 3, B, branch=args.branch, gnn=args.gnn)
+    if args.quick:      # sweep lines (tools/sweep.py): the GPU arm only
+        cpu_sec, cpu_kind, eager_ms, eager_kind = float("inf"), "skipped", float("inf"), "skipped"
+    else:
+        cpu_sec, cpu_kind = cpu_reference_steps(5, 2, threads, branch=args.branch, gnn=args.gnn)
+        eager_ms, eager_kind = eager_gpu_steps(dev, 10, 3, B, branch=args.branch, gnn=args.gnn)
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -636,6 +639,7 @@ def main():
                     help="GGM branch of the step: node generation (the --delta 0 recipe of script/vqacpv2.sh, default) or "
                          "relation generation (taken with probability delta/10; GQA-OOD uses delta 5)")
     ap.add_argument("--nodes", type=int, default=N_NODES, help="nodes per graph (36 = obj36; 64/100 = BASELINE cfg 4 sweep)")
+    ap.add_argument("--quick", action="store_true", help="skip the CPU / eager-GPU baselines and the bf16 leg (sweeps)")
     ap.add_argument("--workload", default="block", choices=["block", "iteration"],
                     help="block: the graph block's training step (default, the headline); iteration: the full trainer "
                          "iteration with a stock-PyTorch LXMERT around the block (BASELINE configs[1]/[2])")
