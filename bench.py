@@ -624,6 +624,96 @@ def run_iteration(args):
         os._exit(0)
 
 
+# ---------------------------------------------------------------------------- VisualFeatEncoder leg
+def run_visn(args):
+    """The 2048-d region-feature projection that produces the block's node features
+    ((LN(W_f feats) + LN(W_b boxes)) / 2 + dropout, src/lxrt/modeling.py:530-556) on the library kernels: forward and
+    forward+backward at B graphs x 36 objects.  Roofline: the K = 2048 projection is tensor-bound in fp32-parity mode
+    (3 passes) and close to the HBM line in bf16 mode; both figures are reported."""
+    import xggm_b200 as X
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    B, H, F = args.batch, HID, 2048
+    X.set_precision(args.precision)
+    torch.manual_seed(9595)
+    enc = X.VisualFeatEncoder(hidden_size=H, hidden_dropout_prob=0.1, feat_dim=F, pos_dim=4).to(dev).train()
+    from xggm_b200.ddp import FlatGrads
+    import xggm_b200.functional as XF
+    fg = FlatGrads(enc.parameters())
+    XF.cache_weight_planes([p for p in enc.parameters() if p.dim() == 2])
+    g = torch.Generator().manual_seed(1)
+    feats_h = torch.relu(torch.randn(B, 36, F, generator=g)).pin_memory()
+    xy = torch.rand(B, 36, 2, 2, generator=g).sort(dim=-1)[0]
+    boxes_h = torch.stack([xy[..., 0, 0], xy[..., 1, 0], xy[..., 0, 1], xy[..., 1, 1]], dim=-1).contiguous().pin_memory()
+    feats, boxes = feats_h.to(dev), boxes_h.to(dev)
+    cot = torch.randn(B, 36, H, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+
+    def fwd():
+        with torch.no_grad():
+            return enc((feats, boxes))
+
+    def fwd_bwd():
+        fg.zero_()
+        out = enc((feats, boxes))
+        torch.autograd.backward([out], [cot])
+        return out
+
+    def e2e():
+        fg.zero_()
+        out = enc((feats_h.to(dev, non_blocking=True), boxes_h.to(dev, non_blocking=True)))
+        torch.autograd.backward([out], [cot])
+        return out
+
+    def timed(fn, k):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+        torch.cuda.synchronize()
+        for s_, e_ in evs:
+            flush.fill_(1.0)
+            s_.record()
+            fn()
+            e_.record()
+        torch.cuda.synchronize()
+        return sum(s_.elapsed_time(e_) for s_, e_ in evs) / k
+
+    from xggm_b200 import _lib
+    for fn in (fwd, fwd_bwd, e2e):
+        for _ in range(max(args.warmup, 3)):
+            fn()
+    l0 = _lib.kernel_launches()
+    ms_f = timed(fwd, args.steps)
+    l1 = _lib.kernel_launches()
+    ms_fb = timed(fwd_bwd, args.steps)
+    l2 = _lib.kernel_launches()
+    ms_e2e = timed(e2e, args.steps)
+    peaks = load_peaks()
+    M = B * 36
+    flops_f = 2.0 * M * F * H + 2.0 * M * 4 * H
+    bytes_f = 4.0 * (M * F + M * 4 + M * H + F * H)                 # read feats, boxes, weights; write out
+    bytes_fb = bytes_f + 4.0 * (M * H + M * F + 2 * F * H)          # + read gout, re-read feats (wgrad), weight-grad RMW
+    passes = 1 if args.precision == "bf16" else 3
+    line = {
+        "metric": "xggm_visual_feat_encoder_samples_per_sec", "value": B / (ms_fb * 1e-3), "unit": "samples/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_fb, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": f"SURVEY 8 f-1 VisualFeatEncoder fwd+bwd (weight gradients; the inputs need none), B={B} x 36 objects x "
+                               f"2048-d features + 4-d boxes -> 768, dropout 0.1, {args.precision} engine",
+                   "l2": "flushed between timed steps", "launch": "eager launches"},
+        "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(feats_h.numel() * 4 + boxes_h.numel() * 4), "d2h_bytes_per_step": 0},
+        "gpu_launches": l2 - l1, "forward": {"ms": ms_f, "launches_per_call": (l1 - l0) // args.steps},
+        "roofline": {"bound": "tensor" if passes == 3 else "hbm", "kernel": "visn_fc projection [B*36,2048]x[2048,768] + fused row tail",
+                     "forward_tflops_algorithmic": flops_f / (ms_f * 1e-3) / 1e12,
+                     "forward_tflops_executed": passes * flops_f / (ms_f * 1e-3) / 1e12,
+                     "forward_frac_of_bf16_peak_executed": passes * flops_f / (ms_f * 1e-3) / 1e12 / peaks["bf16_tflops"],
+                     "forward_gbs_algorithmic": bytes_f / (ms_f * 1e-3) / 1e9,
+                     "forward_frac_of_hbm_peak": bytes_f / (ms_f * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                     "fwd_bwd_gbs_algorithmic": bytes_fb / (ms_fb * 1e-3) / 1e9,
+                     "algorithmic_bytes_per_sample_forward": bytes_f / B, "peak_source": peaks["source"]},
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -640,7 +730,7 @@ def main():
                          "relation generation (taken with probability delta/10; GQA-OOD uses delta 5)")
     ap.add_argument("--nodes", type=int, default=N_NODES, help="nodes per graph (36 = obj36; 64/100 = BASELINE cfg 4 sweep)")
     ap.add_argument("--quick", action="store_true", help="skip the CPU / eager-GPU baselines and the bf16 leg (sweeps)")
-    ap.add_argument("--workload", default="block", choices=["block", "iteration"],
+    ap.add_argument("--workload", default="block", choices=["block", "iteration", "visn"],
                     help="block: the graph block's training step (default, the headline); iteration: the full trainer "
                          "iteration with a stock-PyTorch LXMERT around the block (BASELINE configs[1]/[2])")
     ap.add_argument("--delta", type=int, default=0, help="--workload iteration: GGM branch threshold out of 10 (0 = VQA-CP recipe)")
@@ -648,6 +738,9 @@ def main():
     args = ap.parse_args()
     if args.workload == "iteration" and args.impl != "reference":
         run_iteration(args)
+        return
+    if args.workload == "visn" and args.impl != "reference":
+        run_visn(args)
         return
     if args.impl == "reference":
         run_reference(args)

@@ -399,6 +399,22 @@ int xggm_mask_scale(const float* x, const uint8_t* keep, float scale, float* y, 
  * xggm_mask_scale(gout, keep, scale/2). */
 int xggm_avg2_drop(const float* x, const float* y, const uint8_t* keep, float scale, float* out, long long n,
                    xggm_stream_t s);
+/* The whole tail of VisualFeatEncoder in one pass over z = visn_fc(feats) [M,H] (src/lxrt/modeling.py:546-556):
+ *   out = dropout( (LN_eps(z) * gamma1 + beta1  +  LN_eps(boxes box_w^T + box_b) * gamma2 + beta2) / 2 )
+ * boxes [M,4], box_w [H,4] (box_fc.weight), keep? uint8 [M,H] (NULL = eval), scale = 1/(1-p).  Saves xhat1 [M,H],
+ * rstd1 [M], mean2 [M], rstd2 [M].  Supported for pos_dim == 4, H % 128 == 0, H <= 1024 (xggm_visn_tail_supported);
+ * other shapes compose xggm_linear_* / xggm_layernorm_* / xggm_avg2_drop.
+ * Backward: gz = d loss / d z, gt = d loss / d (box projection output) (feed xggm_linear_bwd_weight with feats / boxes),
+ * and the four LayerNorm parameter gradients, ACCUMULATED into (caller zeroes them). */
+int xggm_visn_tail_supported(int H, int pos_dim);
+int xggm_visn_tail_fwd(const float* z, const float* boxes, const float* box_w, const float* box_b, const float* gamma1,
+                       const float* beta1, const float* gamma2, const float* beta2, const uint8_t* keep, float scale,
+                       float* out, float* xhat1, float* rstd1, float* mean2, float* rstd2, int M, int H, float eps,
+                       xggm_stream_t s);
+int xggm_visn_tail_bwd(const float* gout, const float* xhat1, const float* rstd1, const float* boxes, const float* box_w,
+                       const float* box_b, const float* mean2, const float* rstd2, const float* gamma1, const float* gamma2,
+                       const uint8_t* keep, float scale, float* gz, float* gt, float* ggamma1, float* gbeta1, float* ggamma2,
+                       float* gbeta2, int M, int H, xggm_stream_t s);
 /* Philox keep-mask (1 = keep with probability 1-p): counter = element index / 4,
  * subsequence = stream_id + (*dev_epoch << 32 if dev_epoch, a device counter, is non-NULL). */
 int xggm_keep_mask(uint8_t* keep, long long n, float p, uint64_t seed, uint64_t stream_id,

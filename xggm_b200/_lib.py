@@ -81,6 +81,9 @@ SIGNATURES = {
     "xggm_grad_sumsq": [_vp, _ll, _vp, _i, _vp],
     "xggm_bertadam_step": [_vp, _vp, _vp, _vp, _ll, _d, _d, _d, _d, _d, _vp, _d, _vp],
     "xggm_bertadam_step_ex": [_vp, _vp, _vp, _vp, _ll, _d, _d, _d, _d, _d, _vp, _d, _vp, _vp],
+    "xggm_visn_tail_supported": [_i, _i],
+    "xggm_visn_tail_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp],
+    "xggm_visn_tail_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "xggm_dp_bertadam_step": [_vp, _vp, _vp, _ll, _vp, _vp, _i, _d, _d, _d, _d, _d, _d, _vp, _vp, _vp],
     "xggm_sigmoid_fwd": [_vp, _vp, _ll, _vp],
     "xggm_sigmoid_bwd": [_vp, _vp, _vp, _ll, _vp],

@@ -1001,6 +1001,28 @@ int xggm_bertadam_step_ex(float* p, const float* g, float* m, float* v, long lon
     XGGM_REQUIRE(n >= 0 && (n == 0 || (p && g && m && v)) && b1 >= 0.0 && b1 < 1.0 && b2 >= 0.0 && b2 < 1.0 && eps >= 0.0);
     return bertadam_step(p, g, m, v, n, lr, b1, b2, eps, weight_decay, sumsq, max_norm, sched, as_stream(s));
 }
+int xggm_visn_tail_supported(int H, int pos_dim) { return visn_tail_supported(H, pos_dim) ? 1 : 0; }
+int xggm_visn_tail_fwd(const float* z, const float* boxes, const float* box_w, const float* box_b, const float* gamma1,
+                       const float* beta1, const float* gamma2, const float* beta2, const uint8_t* keep, float scale,
+                       float* out, float* xhat1, float* rstd1, float* mean2, float* rstd2, int M, int H, float eps,
+                       xggm_stream_t s) {
+    if (M == 0) return XGGM_OK;
+    XGGM_REQUIRE(z && boxes && box_w && box_b && gamma1 && beta1 && gamma2 && beta2 && out && xhat1 && rstd1 && mean2 && rstd2 && M >= 0);
+    return visn_tail_fwd(z, boxes, box_w, box_b, gamma1, beta1, gamma2, beta2, drop_mask(keep, scale), out, xhat1, rstd1, mean2, rstd2,
+                         M, H, eps, as_stream(s));
+}
+int xggm_visn_tail_bwd(const float* gout, const float* xhat1, const float* rstd1, const float* boxes, const float* box_w,
+                       const float* box_b, const float* mean2, const float* rstd2, const float* gamma1, const float* gamma2,
+                       const uint8_t* keep, float scale, float* gz, float* gt, float* ggamma1, float* gbeta1, float* ggamma2,
+                       float* gbeta2, int M, int H, xggm_stream_t s) {
+    if (M == 0) return XGGM_OK;
+    XGGM_REQUIRE(gout && xhat1 && rstd1 && boxes && box_w && box_b && mean2 && rstd2 && gamma1 && gamma2 && gz && gt && ggamma1 &&
+                 gbeta1 && ggamma2 && gbeta2 && M >= 0);
+    DropSpec d = drop_mask(keep, scale);
+    if (!keep) d.scale = scale;      // eval mode / no mask: plain scale (1.0)
+    return visn_tail_bwd(gout, xhat1, rstd1, boxes, box_w, box_b, mean2, rstd2, gamma1, gamma2, d, gz, gt, ggamma1, gbeta1, ggamma2,
+                         gbeta2, M, H, as_stream(s));
+}
 int xggm_dp_bertadam_step(const xggm_dp_peers_t* peers, float* m, float* v, long long n, const long long* range_lo,
                           const long long* range_hi, int n_ranges, double lr, double b1, double b2, double eps,
                           double weight_decay, double max_norm, const xggm_lr_schedule_t* sched, float* sumsq_out,

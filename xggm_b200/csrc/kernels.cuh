@@ -98,6 +98,14 @@ int bertadam_step(float* p, const float* g, float* m, float* v, long long n, dou
 int dp_bertadam_step(const xggm_dp_peers_t* peers, float* m, float* v, long long n, const long long* range_lo,
                      const long long* range_hi, int n_ranges, double lr, double b1, double b2, double eps, double wd,
                      double max_norm, const xggm_lr_schedule_t* sched, float* sumsq_out, cudaStream_t st);
+bool visn_tail_supported(int H, int pos_dim);
+int visn_tail_fwd(const float* z, const float* boxes, const float* Wb, const float* bb, const float* g1, const float* b1,
+                  const float* g2, const float* b2, const DropSpec& drop, float* out, float* xhat1, float* rstd1, float* mean2,
+                  float* rstd2, int M, int H, float eps, cudaStream_t st);
+int visn_tail_bwd(const float* gout, const float* xhat1, const float* rstd1, const float* boxes, const float* Wb,
+                  const float* bb, const float* mean2, const float* rstd2, const float* g1, const float* g2,
+                  const DropSpec& drop, float* gz, float* gt, float* gg1, float* gb1, float* gg2, float* gb2, int M, int H,
+                  cudaStream_t st);
 long long weight_planes_elems(int N, int K);
 void weight_planes_views(void* buf, int N, int K, __nv_bfloat16** hi, __nv_bfloat16** lo, __nv_bfloat16** thi,
                          __nv_bfloat16** tlo);

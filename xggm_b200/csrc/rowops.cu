@@ -716,4 +716,214 @@ int gelu_ln_drop_bwd(const float* gout, const float* z, const float* mean, const
     return XGGM_OK;
 }
 
+// ================================================================== VisualFeatEncoder tail
+// out = dropout( (LN(z) + LN(box_fc(boxes))) / 2 ), src/lxrt/modeling.py:546-556, with z = visn_fc(feats) from the
+// projection GEMM: the 4 -> H box projection (4 FMAs per element), both BertLayerNorms (eps 1e-12), the average and the
+// dropout in ONE pass over z (was: SIMT GEMM + 2 LayerNorm + avg/dropout = 4 launches and 5 extra [M,H] round trips).
+// Parameters (box weight [H,4], box bias, two gamma / beta pairs) live in shared memory; a warp owns a row.
+struct VisnTailSmem {
+    // floats: Wb[H*4] | bb[H] | g1[H] | b1[H] | g2[H] | b2[H]
+    static __host__ __device__ constexpr int floats(int H) { return 9 * H; }
+};
+template <int NV>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+visn_tail_fwd_fast(const float* __restrict__ z, const float* __restrict__ boxes, const float* __restrict__ Wb,
+                   const float* __restrict__ bb, const float* __restrict__ g1, const float* __restrict__ b1,
+                   const float* __restrict__ g2, const float* __restrict__ b2, const DropSpec drop,
+                   float* __restrict__ out, float* __restrict__ xhat1, float* __restrict__ rstd1,
+                   float* __restrict__ mean2, float* __restrict__ rstd2, int M, float eps) {
+    pdl_prologue();
+    constexpr int H = NV * 128;
+    extern __shared__ __align__(16) float sm[];
+    float* sW = sm;
+    float* sb = sW + 4 * H;
+    float* sg1 = sb + H; float* sb1 = sg1 + H; float* sg2 = sb1 + H; float* sb2 = sg2 + H;
+    for (int i = threadIdx.x; i < 4 * H; i += blockDim.x) sW[i] = Wb[i];
+    for (int i = threadIdx.x; i < H; i += blockDim.x) { sb[i] = bb[i]; sg1[i] = g1[i]; sb1[i] = b1[i]; sg2[i] = g2[i]; sb2[i] = b2[i]; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t dstream = drop_stream(drop);
+    const float scale = drop.scale;
+    const int wid = blockIdx.x * ROW_WARPS + warp, nw = gridDim.x * ROW_WARPS;
+    for (int r = wid; r < M; r += nw) {
+        const size_t ro = (size_t)r * H;
+        float v[NV * 4], t[NV * 4];
+        load_row<NV>(z + ro, lane, v);
+        const float4 bx = *reinterpret_cast<const float4*>(boxes + (size_t)r * 4);
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = 128 * i + 4 * lane + j;
+                const float4 w = *reinterpret_cast<const float4*>(sW + 4 * c);
+                t[4 * i + j] = fmaf(w.w, bx.w, fmaf(w.z, bx.z, fmaf(w.y, bx.y, fmaf(w.x, bx.x, sb[c]))));
+            }
+        float m1, r1, m2, r2;
+        row_stats<NV>(v, 1.0f / (float)H, eps, m1, r1);
+        row_stats<NV>(t, 1.0f / (float)H, eps, m2, r2);
+#pragma unroll
+        for (int i = 0; i < NV * 4; ++i) v[i] = (v[i] - m1) * r1;
+        if (xhat1) store_row<NV>(xhat1 + ro, lane, v);
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = 128 * i + 4 * lane + j, e = 4 * i + j;
+                const float y1 = fmaf(v[e], sg1[c], sb1[c]);
+                const float y2 = fmaf((t[e] - m2) * r2, sg2[c], sb2[c]);
+                v[e] = 0.5f * (y1 + y2);
+            }
+        if (drop.mode) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                bool m[4];
+                drop_bits4(drop, dstream, ro + 128 * i + 4 * lane, m);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[4 * i + j] = m[j] ? v[4 * i + j] * scale : 0.f;
+            }
+        }
+        store_row<NV>(out + ro, lane, v);
+        if (lane == 0) {
+            if (rstd1) rstd1[r] = r1;
+            if (mean2) mean2[r] = m2;
+            if (rstd2) rstd2[r] = r2;
+        }
+    }
+}
+
+// backward: gz (gradient of z = visn_fc output), gt (gradient of the box projection's output), gamma / beta gradients of
+// both LayerNorms (ACCUMULATED into).  The box projection and its normalised value are recomputed from the 16-byte box row.
+template <int NV>
+__global__ void __launch_bounds__(ROW_WARPS * 32, 1)
+visn_tail_bwd_fast(const float* __restrict__ gout, const float* __restrict__ xhat1, const float* __restrict__ rstd1,
+                   const float* __restrict__ boxes, const float* __restrict__ Wb, const float* __restrict__ bb,
+                   const float* __restrict__ mean2, const float* __restrict__ rstd2, const float* __restrict__ g1,
+                   const float* __restrict__ g2, const DropSpec drop, float* __restrict__ gz, float* __restrict__ gt,
+                   float* __restrict__ gg1, float* __restrict__ gb1, float* __restrict__ gg2, float* __restrict__ gb2, int M) {
+    pdl_prologue();
+    constexpr int H = NV * 128;
+    extern __shared__ __align__(16) float sm[];
+    float* sW = sm;
+    float* sb = sW + 4 * H;
+    float* sg1 = sb + H; float* sg2 = sg1 + H;
+    float* red = sg2 + H;     // ROW_WARPS * H floats for flush_columns
+    for (int i = threadIdx.x; i < 4 * H; i += blockDim.x) sW[i] = Wb[i];
+    for (int i = threadIdx.x; i < H; i += blockDim.x) { sb[i] = bb[i]; sg1[i] = g1[i]; sg2[i] = g2[i]; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t dstream = drop_stream(drop);
+    const float scale = 0.5f * drop.scale;
+    const int wid = blockIdx.x * ROW_WARPS + warp, nw = gridDim.x * ROW_WARPS;
+    float a1[NV * 4], a2[NV * 4], ab[NV * 4];
+#pragma unroll
+    for (int i = 0; i < NV * 4; ++i) { a1[i] = 0.f; a2[i] = 0.f; ab[i] = 0.f; }
+    for (int r = wid; r < M; r += nw) {
+        const size_t ro = (size_t)r * H;
+        float g[NV * 4], xh[NV * 4];
+        load_row<NV>(gout + ro, lane, g);
+        load_row<NV>(xhat1 + ro, lane, xh);
+        const float4 bx = *reinterpret_cast<const float4*>(boxes + (size_t)r * 4);
+        const float r1 = rstd1[r], m2 = mean2[r], r2 = rstd2[r];
+        if (drop.mode) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                bool m[4];
+                drop_bits4(drop, dstream, ro + 128 * i + 4 * lane, m);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) g[4 * i + j] = m[j] ? g[4 * i + j] * scale : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NV * 4; ++i) g[i] *= scale;
+        }
+        // LayerNorm 1 (visual features)
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = 128 * i + 4 * lane + j, e = 4 * i + j;
+                const float d = g[e] * sg1[c];
+                s1 += d;
+                s2 = fmaf(d, xh[e], s2);
+            }
+        float c1 = warp_sum(s1) / (float)H, c2 = warp_sum(s2) / (float)H;
+        float o[NV * 4];
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = 128 * i + 4 * lane + j, e = 4 * i + j;
+                a1[e] = fmaf(g[e], xh[e], a1[e]);
+                ab[e] += g[e];
+                o[e] = r1 * (g[e] * sg1[c] - c1 - xh[e] * c2);
+            }
+        store_row<NV>(gz + ro, lane, o);
+        // LayerNorm 2 (boxes): recompute the projection and its normalised value
+        s1 = 0.f; s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = 128 * i + 4 * lane + j, e = 4 * i + j;
+                const float4 w = *reinterpret_cast<const float4*>(sW + 4 * c);
+                const float tv = fmaf(w.w, bx.w, fmaf(w.z, bx.z, fmaf(w.y, bx.y, fmaf(w.x, bx.x, sb[c]))));
+                xh[e] = (tv - m2) * r2;
+                const float d = g[e] * sg2[c];
+                s1 += d;
+                s2 = fmaf(d, xh[e], s2);
+            }
+        c1 = warp_sum(s1) / (float)H; c2 = warp_sum(s2) / (float)H;
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = 128 * i + 4 * lane + j, e = 4 * i + j;
+                a2[e] = fmaf(g[e], xh[e], a2[e]);
+                o[e] = r2 * (g[e] * sg2[c] - c1 - xh[e] * c2);
+            }
+        store_row<NV>(gt + ro, lane, o);
+    }
+    flush_columns<NV>(a1, gg1, red);
+    flush_columns<NV>(a2, gg2, red);
+    flush_columns<NV>(ab, gb1, red);
+    flush_columns<NV>(ab, gb2, red);
+}
+
+bool visn_tail_supported(int H, int pos_dim) { return pos_dim == 4 && H % 128 == 0 && H >= 128 && H <= 1024; }
+
+int visn_tail_fwd(const float* z, const float* boxes, const float* Wb, const float* bb, const float* g1, const float* b1,
+                  const float* g2, const float* b2, const DropSpec& drop, float* out, float* xhat1, float* rstd1, float* mean2,
+                  float* rstd2, int M, int H, float eps, cudaStream_t st) {
+    if (M <= 0) return XGGM_OK;
+    XGGM_REQUIRE(visn_tail_supported(H, 4) && fast_ok(H, z, out, xhat1) && (reinterpret_cast<uintptr_t>(boxes) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(Wb) & 15) == 0 && (reinterpret_cast<uintptr_t>(drop.keep) & 3) == 0);
+    XGGM_ROW_DISPATCH(H, {
+        const size_t smem = sizeof(float) * VisnTailSmem::floats(H);
+        XGGM_LAUNCH((visn_tail_fwd_fast<NV>), fast_grid(M, 4), ROW_WARPS * 32, smem, st, z, boxes, Wb, bb, g1, b1, g2, b2, drop, out,
+                    xhat1, rstd1, mean2, rstd2, M, eps);
+    });
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+
+int visn_tail_bwd(const float* gout, const float* xhat1, const float* rstd1, const float* boxes, const float* Wb,
+                  const float* bb, const float* mean2, const float* rstd2, const float* g1, const float* g2,
+                  const DropSpec& drop, float* gz, float* gt, float* gg1, float* gb1, float* gg2, float* gb2, int M, int H,
+                  cudaStream_t st) {
+    if (M <= 0) return XGGM_OK;
+    XGGM_REQUIRE(visn_tail_supported(H, 4) && fast_ok(H, gout, xhat1, gz) && fast_ok(H, gt) &&
+                 (reinterpret_cast<uintptr_t>(boxes) & 15) == 0 && (reinterpret_cast<uintptr_t>(Wb) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(drop.keep) & 3) == 0);
+    XGGM_ROW_DISPATCH(H, {
+        const size_t smem = sizeof(float) * (7 * H + ROW_WARPS * H);
+        static bool attr = false;
+        if (!attr) { XGGM_CUDA_TRY(cudaFuncSetAttribute(visn_tail_bwd_fast<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+        XGGM_LAUNCH((visn_tail_bwd_fast<NV>), fast_grid(M, 1), ROW_WARPS * 32, smem, st, gout, xhat1, rstd1, boxes, Wb, bb, mean2, rstd2,
+                    g1, g2, drop, gz, gt, gg1, gb1, gg2, gb2, M);
+    });
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
+
 }  // namespace xggm

@@ -594,6 +594,65 @@ class _Avg2Drop(torch.autograd.Function):
         return gx, gx, None, None
 
 
+class _VisnTail(torch.autograd.Function):
+    """dropout((LN(z) + LN(box_fc(boxes))) / 2) in one pass (xggm_visn_tail_*): the tail of VisualFeatEncoder."""
+
+    @staticmethod
+    def forward(ctx, z, boxes, bw, bb, g1, b1, g2, b2, keep, scale, eps):
+        z2 = f32(z, "z").reshape(-1, z.shape[-1])
+        bx = f32(boxes, "boxes").reshape(-1, boxes.shape[-1])
+        bw, bb, g1, b1, g2, b2 = (f32(t, "parameter") for t in (bw, bb, g1, b1, g2, b2))
+        keep = _u8(keep)
+        M, H = z2.shape
+        out, xhat1 = torch.empty_like(z2), torch.empty_like(z2)
+        rstd1, mean2, rstd2 = (torch.empty(M, device=z.device, dtype=torch.float32) for _ in range(3))
+        call("xggm_visn_tail_fwd", ptr(z2), ptr(bx), ptr(bw), ptr(bb), ptr(g1), ptr(b1), ptr(g2), ptr(b2), ptr(keep), float(scale),
+             ptr(out), ptr(xhat1), ptr(rstd1), ptr(mean2), ptr(rstd2), M, H, float(eps))
+        ctx.save_for_backward(xhat1, rstd1, mean2, rstd2, bx, bw, bb, g1, g2, keep)
+        ctx.refs = (b1, b2)
+        ctx.scale, ctx.shapes = float(scale), (z.shape, boxes.shape)
+        return out.reshape(z.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        xhat1, rstd1, mean2, rstd2, bx, bw, bb, g1, g2, keep = ctx.saved_tensors
+        b1, b2 = ctx.refs
+        M, H = xhat1.shape
+        g2d = f32(g).reshape(M, H)
+        gz, gt = torch.empty_like(xhat1), torch.empty_like(xhat1)
+        tg = [_grad_target(t) for t in (g1, b1, g2, b2)]
+        fused = all(t is not None for t in tg)
+        gg1, gb1, gg2, gb2 = tg if fused else [torch.zeros(H, device=g.device, dtype=torch.float32) for _ in range(4)]
+        call("xggm_visn_tail_bwd", ptr(g2d), ptr(xhat1), ptr(rstd1), ptr(bx), ptr(bw), ptr(bb), ptr(mean2), ptr(rstd2), ptr(g1),
+             ptr(g2), ptr(keep), ctx.scale, ptr(gz), ptr(gt), ptr(gg1), ptr(gb1), ptr(gg2), ptr(gb2), M, H)
+        # box_fc's own gradients: gW = gt^T boxes [H,4], gb = column sums of gt (K = 4: the exact SIMT product)
+        tw, tb = _grad_target(bw), _grad_target(bb)
+        if tw is not None and tb is not None:
+            call("xggm_linear_bwd_weight", ptr(gt), ptr(bx), ptr(tw), ptr(tb), M, H, bx.shape[1], 1, None)
+            gbw = gbb = None
+        else:
+            gbw, gbb = torch.empty_like(bw), torch.empty_like(bb)
+            call("xggm_linear_bwd_weight", ptr(gt), ptr(bx), ptr(gbw), ptr(gbb), M, H, bx.shape[1], 0, None)
+        gboxes = None
+        if ctx.needs_input_grad[1]:
+            gboxes = torch.empty_like(bx)
+            call("xggm_linear_bwd_input", ptr(gt), ptr(bw), ptr(gboxes), M, H, bx.shape[1], 0, None)
+            gboxes = gboxes.reshape(ctx.shapes[1])
+        none4 = (None, None, None, None)
+        return (gz.reshape(ctx.shapes[0]), gboxes, gbw, gbb) + (none4 if fused else (gg1, gb1, gg2, gb2)) + (None, None, None)
+
+
+def visn_tail_supported(H, pos_dim):
+    return bool(_lib.load().xggm_visn_tail_supported(int(H), int(pos_dim)))
+
+
+def visn_tail(z, boxes, box_w, box_b, g1, b1, g2, b2, p, training, eps):
+    """dropout((LN(z) g1 + b1 + LN(boxes box_w^T + box_b) g2 + b2) / 2) -- src/lxrt/modeling.py:546-556."""
+    if training and p > 0.0:
+        return _VisnTail.apply(z, boxes, box_w, box_b, g1, b1, g2, b2, keep_mask(z.shape, p, z.device), 1.0 / (1.0 - p), eps)
+    return _VisnTail.apply(z, boxes, box_w, box_b, g1, b1, g2, b2, None, 1.0, eps)
+
+
 def avg2_dropout(x, y, p, training):
     """dropout((x + y) / 2) -- the tail of VisualFeatEncoder (src/lxrt/modeling.py:553-555)."""
     if training and p > 0.0:

@@ -361,7 +361,8 @@ class VisualFeatEncoder(nn.Module):
     ``config`` is the reference's BertConfig (only ``hidden_size`` and ``hidden_dropout_prob`` are read);
     feat_dim / pos_dim are VISUAL_CONFIG.visual_feat_dim / visual_pos_dim (2048 / 4).  Parameter names match
     the reference, so the ``bert.encoder.visn_fc.*`` slice of an LXMERT checkpoint loads unchanged.  The
-    2048 -> 768 projection runs on the tcgen05 engine, the 4 -> 768 box projection on the exact kernel."""
+    2048 -> 768 projection runs on the tcgen05 engine; everything after it (the 4 -> 768 box projection, both
+    LayerNorms, the average and the dropout) is ONE row kernel per direction (``xggm_visn_tail_*``)."""
 
     def __init__(self, config=None, hidden_size=768, hidden_dropout_prob=0.1, feat_dim=2048, pos_dim=4):
         super().__init__()
@@ -375,6 +376,12 @@ class VisualFeatEncoder(nn.Module):
 
     def forward(self, visn_input):
         feats, boxes = visn_input
+        ln1, ln2 = self.visn_layer_norm, self.box_layer_norm
+        if ln1.eps == ln2.eps and XF.visn_tail_supported(self.visn_fc.out_features, self.box_fc.in_features):
+            # projection GEMM + ONE fused row kernel (box projection, both LayerNorms, average, dropout)
+            z = XF.linear(feats, self.visn_fc.weight, self.visn_fc.bias)
+            return XF.visn_tail(z, boxes, self.box_fc.weight, self.box_fc.bias, ln1.weight, ln1.bias, ln2.weight, ln2.bias,
+                                self.dropout.p, self.training, ln1.eps)
         x = XF.layer_norm(XF.linear(feats, self.visn_fc.weight, self.visn_fc.bias),
                           self.visn_layer_norm.weight, self.visn_layer_norm.bias, self.visn_layer_norm.eps)
         y = XF.layer_norm(XF.linear(boxes, self.box_fc.weight, self.box_fc.bias),
