@@ -50,6 +50,18 @@ static inline bool use_tc(int M, int N, int K) {
     return g_precision != XGGM_PREC_FP32_SIMT && gemm_tc_supported(M, N, K);
 }
 static inline int npass() { return g_precision == XGGM_PREC_BF16 ? 1 : 3; }
+// bf16 STORAGE (BASELINE configs[2]): under the single-pass bf16 engine the saved pre-activations z and normalised
+// values xhat of a GCN / GIN layer are kept as bf16 only (the projection writes z as its hi plane and nothing else; the
+// row kernels read / write bf16 rows) -- half the bytes of the fp32 copies the fp32-parity engine needs.  Fast row
+// kernels only (H % 128 == 0, H <= 1024); XGGM_BF16_STORAGE=0 keeps fp32 storage for A/B runs.
+static inline bool bf16_storage(int H) {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("XGGM_BF16_STORAGE");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on && g_precision == XGGM_PREC_BF16 && H % 128 == 0 && H >= 128 && H <= 1024;
+}
 // planes of an [n]-element fp32 array stored in a region of pad8(n) floats: hi | lo
 static inline Operand planes_at(const float* f32, float* region, long long n) {
     bf16* hi = reinterpret_cast<bf16*>(region);
@@ -261,7 +273,11 @@ static int gnn_fwd(int kind, const float* x, const float* adj, const float* cons
     bf16* coef_lo = coef_hi + pad8(adjtc ? adj_tc_coef_elems(B, N) : 0);
     if (adjtc && kind == XGGM_KIND_GCN && nc > 0 && !fused_adj_ln())
         XGGM_TRY(build_blockdiag(adj, coef_hi, npass() == 3 ? coef_lo : nullptr, B, N, 1.f, nullptr, 0.f, 0, st));
+    const bool bst = tc && bf16_storage(H);
+    Operand zplane[MAX_CONVS + 1];   // bf16 storage: z_j exists only as the hi plane the projection writes
+    for (int j = 0; j <= nc; ++j) zplane[j] = Operand{nullptr, reinterpret_cast<const bf16*>(saved + L.head(j, 0)), nullptr};
     auto head_lin = [&](int j) -> Lin {   // z_j = h_j W_j^T + b_j
+        if (bst) return Lin{hops[j], whead[j], hp[4 * j + 1], nullptr, nullptr, &zplane[j], 0};
         return Lin{hops[j], whead[j], hp[4 * j + 1], nullptr, saved + L.head(j, 0), nullptr, 0};
     };
     // out (+)= dropout(LN(GeLU(z_j))); the last accumulation can also emit `out` as operand planes for its consumers
@@ -270,7 +286,7 @@ static int gnn_fwd(int kind, const float* x, const float* adj, const float* cons
         const bool emit = tc && out_planes && j == nc;
         return gelu_ln_drop_fwd(saved + L.head(j, 0), hp[4 * j + 2], hp[4 * j + 3], head_drop(keeps, philox, drop_p, j), out,
                                 saved + L.head(j, 1), saved + L.head(j, 2), emit ? mut(out_op.hi) : nullptr,
-                                emit ? lo_or_null(out_op) : nullptr, M, H, LN_EPS, j > 0, st);
+                                emit ? lo_or_null(out_op) : nullptr, M, H, LN_EPS, j > 0, st, bst ? 1 : 0);
     };
     for (int k = 0; k < nc; ++k) {
         float* h_next = saved + L.conv(k, 2);
@@ -285,9 +301,13 @@ static int gnn_fwd(int kind, const float* x, const float* adj, const float* cons
             g[0] = Lin{hops[k], wconv[k], nullptr, nullptr, nullptr, &P_op, 0};
             g[1] = head_lin(k);
             XGGM_TRY(fwd_group(tc, g, 2, M, H, H, st));
-            XGGM_TRY(adj_apply_tc(coef_hi, coef_lo, P_op.hi, P_op.lo, work /* u */, nullptr, nullptr, B, N, H, 0, npass(), st, h));
-            XGGM_TRY(layernorm_fwd(work, cp[3 * k + 1], cp[3 * k + 2], h_next, saved + L.conv(k, 1), saved + L.conv(k, 3),
-                                   mut(next_op.hi), lo_or_null(next_op), M, H, LN_EPS, st));
+            // the residual h_k comes from its operand planes (hi + lo = 16 mantissa bits, ~1e-5 like the products), so
+            // h_{k+1} never has to exist as an fp32 tensor: LayerNorm writes xhat and the planes only
+            const bool fast_ln = H % 128 == 0 && H >= 128 && H <= 1024;
+            XGGM_TRY(adj_apply_tc(coef_hi, coef_lo, P_op.hi, P_op.lo, work /* u */, nullptr, nullptr, B, N, H, 0, npass(), st,
+                                  nullptr, hops[k].hi, hops[k].lo));
+            XGGM_TRY(layernorm_fwd(work, cp[3 * k + 1], cp[3 * k + 2], fast_ln ? nullptr : h_next, saved + L.conv(k, 1),
+                                   saved + L.conv(k, 3), mut(next_op.hi), lo_or_null(next_op), M, H, LN_EPS, st, bst ? 1 : 0));
         } else if (gcn && adj_ln_supported(N, H)) {
             // same algebra with the message passing folded into the LayerNorm kernel (one CTA per graph):
             //     h_next = LN(h + adj @ P)
@@ -321,12 +341,14 @@ static int gnn_fwd(int kind, const float* x, const float* adj, const float* cons
                                    B, N, H, 1.f, eps, 1.f, false, 0, st));
             }
             // conv projection + read-out head k in one launch
-            g[0] = Lin{pre_op, wconv[k], cp[5 * k + 2], nullptr, saved + L.conv(k, 1) /* z */, nullptr, 0};
+            const Operand zc = Operand{nullptr, reinterpret_cast<const bf16*>(saved + L.conv(k, 1)), nullptr};
+            g[0] = bst ? Lin{pre_op, wconv[k], cp[5 * k + 2], nullptr, nullptr, &zc, 0}
+                       : Lin{pre_op, wconv[k], cp[5 * k + 2], nullptr, saved + L.conv(k, 1) /* z */, nullptr, 0};
             g[1] = head_lin(k);
             XGGM_TRY(fwd_group(tc, g, 2, M, H, H, st));
             XGGM_TRY(gelu_ln_drop_fwd(saved + L.conv(k, 1), cp[5 * k + 3], cp[5 * k + 4], drop_none(), h_next,
                                       saved + L.conv(k, 3), saved + L.conv(k, 4), tc ? mut(next_op.hi) : nullptr,
-                                      tc ? lo_or_null(next_op) : nullptr, M, H, LN_EPS, 0, st));
+                                      tc ? lo_or_null(next_op) : nullptr, M, H, LN_EPS, 0, st, bst ? 1 : 0));
         }
         XGGM_TRY(head_post(k));
         hops[k + 1] = next_op;
@@ -365,6 +387,7 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
     const GnnLayout L(kind, M, H, nc);
     const bool tc = use_tc(M, H, H);
     const bool gcn = kind == XGGM_KIND_GCN;
+    const bool bst = tc && bf16_storage(H);      // must mirror gnn_fwd: z / xhat were saved as bf16
     const long long MH = L.MH, MHn = (long long)M * H;
     float* buf[2] = {work, work + MH};
     float* gt = work + 2 * MH;  // GIN: gz of the conv (exact engine only; planes otherwise)
@@ -403,7 +426,7 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
         return gelu_ln_drop_bwd(gout, saved + L.head(j, 0), saved + L.head(j, 1), saved + L.head(j, 2),
                                 hp[4 * j + 2], head_drop(keeps, philox, drop_p, j), tc ? nullptr : region,
                                 hg[4 * j + 2], hg[4 * j + 3], hg[4 * j + 1], tc ? mut(g.hi) : nullptr,
-                                tc ? lo_or_null(g) : nullptr, M, H, st);
+                                tc ? lo_or_null(g) : nullptr, M, H, st, bst ? 1 : 0);
     };
 
     int cur = 0;
@@ -428,9 +451,10 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
         if (gcn) {
             if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(cg[3 * k + 1], 0, sizeof(float) * H, st));
             if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(cg[3 * k + 2], 0, sizeof(float) * H, st));
+            const bool xb = bst && adj_tc_supported(N, H) && !fused_adj_ln();   // (the path of gnn_fwd that wrote bf16 xhat)
             XGGM_TRY(layernorm_bwd(gh, saved + L.conv(k, 1), saved + L.conv(k, 3), cp[3 * k + 1], gnext,
                                    cg[3 * k + 1], cg[3 * k + 2], tc ? mut(g0.hi) : nullptr,
-                                   tc ? lo_or_null(g0) : nullptr, M, H, st));
+                                   tc ? lo_or_null(g0) : nullptr, M, H, st, xb ? 1 : 0));
         } else {
             if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k], 0, sizeof(float), st));
             if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k + 3], 0, sizeof(float) * H, st));
@@ -438,7 +462,7 @@ static int gnn_bwd(int kind, const float* gout, const float* x, const float* adj
             if (!acc) XGGM_CUDA_TRY(cudaMemsetAsync(cg[5 * k + 2], 0, sizeof(float) * H, st));
             XGGM_TRY(gelu_ln_drop_bwd(gh, saved + L.conv(k, 1), saved + L.conv(k, 3), saved + L.conv(k, 4),
                                       cp[5 * k + 3], drop_none(), tc ? nullptr : gt, cg[5 * k + 3], cg[5 * k + 4], cg[5 * k + 2],
-                                      tc ? mut(g0.hi) : nullptr, tc ? lo_or_null(g0) : nullptr, M, H, st));
+                                      tc ? mut(g0.hi) : nullptr, tc ? lo_or_null(g0) : nullptr, M, H, st, bst ? 1 : 0));
         }
         XGGM_TRY(head_gz(k, R[1]));
         const Operand g1 = planes_at(R[1], R[1], MHn);

@@ -233,6 +233,8 @@ struct ProbOut {
     __nv_bfloat16* c_lo;
     int accumulate;      // C += (non-atomic)
     int pad_;
+    const __nv_bfloat16* r_hi;   // optional: the residual given as bf16 operand planes (hi + lo = 16 mantissa bits; lo may be
+    const __nv_bfloat16* r_lo;   // null) instead of an fp32 tensor -- lets a producer keep ONLY the planes of a tensor
 };
 struct MapSet {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
@@ -492,6 +494,25 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const Params p) {
                 bv = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (ok && lead && po.bias) bv = __ldg(reinterpret_cast<const float4*>(po.bias + nv));
                 const float* src = (lead && po.resid) ? po.resid : ((po.accumulate && !p.atomic) ? po.C : nullptr);
+                if (lead && po.r_hi) {      // residual from bf16 planes: 8-byte loads, hi (+ lo)
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int row = 4 * it + rsub;
+                        x[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ok && row < rows) {
+                            const size_t off = (size_t)(mrow0 + row) * p.ldc + nv;
+                            const uint2 h = *reinterpret_cast<const uint2*>(po.r_hi + off);
+                            const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&h.x), h1 = *reinterpret_cast<const __nv_bfloat162*>(&h.y);
+                            x[it] = make_float4(__low2float(h0), __high2float(h0), __low2float(h1), __high2float(h1));
+                            if (po.r_lo) {
+                                const uint2 l = *reinterpret_cast<const uint2*>(po.r_lo + off);
+                                const __nv_bfloat162 l0 = *reinterpret_cast<const __nv_bfloat162*>(&l.x), l1 = *reinterpret_cast<const __nv_bfloat162*>(&l.y);
+                                x[it].x += __low2float(l0); x[it].y += __high2float(l0); x[it].z += __low2float(l1); x[it].w += __high2float(l1);
+                            }
+                        }
+                    }
+                    return;
+                }
 #pragma unroll
                 for (int it = 0; it < 8; ++it) {
                     const int row = 4 * it + rsub;
@@ -962,8 +983,8 @@ static void single_problem(tc::Params& p, const float* bias, const float* resid,
     p.group = 1;
     p.kcat = 0;
     p.tiles_per_prob = p.tiles_m * p.tiles_n * p.splits;
-    for (int g = 0; g < tc::MAX_GROUP; ++g) p.pr[g] = tc::ProbOut{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
-    p.pr[0] = tc::ProbOut{bias, resid, C, c_hi, c_lo, accumulate, 0};
+    for (int g = 0; g < tc::MAX_GROUP; ++g) p.pr[g] = tc::ProbOut{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr};
+    p.pr[0] = tc::ProbOut{bias, resid, C, c_hi, c_lo, accumulate, 0, nullptr, nullptr};
 }
 
 // `count` (1..3) products of the same shape in ONE launch.
@@ -1041,7 +1062,7 @@ int gemm_tc_group(bool a_mn, bool b_mn, const GemmProb* pr, int count, int M, in
             maps.m[g].a_lo = maps.m[g].a_hi;
             maps.m[g].b_lo = maps.m[g].b_hi;
         }
-        p.pr[g] = tc::ProbOut{q.bias, q.resid, q.C, q.c_hi, npass == 3 ? q.c_lo : nullptr, q.accumulate, 0};
+        p.pr[g] = tc::ProbOut{q.bias, q.resid, q.C, q.c_hi, npass == 3 ? q.c_lo : nullptr, q.accumulate, 0, nullptr, nullptr};
         if (g >= count) continue;
         if (((reinterpret_cast<uintptr_t>(q.C) | reinterpret_cast<uintptr_t>(q.resid) |
               reinterpret_cast<uintptr_t>(q.bias)) & 15) != 0)
@@ -1177,9 +1198,11 @@ int build_blockdiag(const float* adj, __nv_bfloat16* hi, __nv_bfloat16* lo, int 
 // out (fp32) and / or out planes; accumulate adds to the previous fp32 out; resid (optional, [B*N,H] fp32) is added.
 int adj_apply_tc(const __nv_bfloat16* c_hi_in, const __nv_bfloat16* c_lo_in, const __nv_bfloat16* x_hi,
                  const __nv_bfloat16* x_lo, float* out, __nv_bfloat16* o_hi, __nv_bfloat16* o_lo, int B, int N, int H,
-                 int accumulate, int npass, cudaStream_t st, const float* resid) {
+                 int accumulate, int npass, cudaStream_t st, const float* resid, const __nv_bfloat16* r_hi,
+                 const __nv_bfloat16* r_lo) {
     if (B <= 0) return XGGM_OK;
     XGGM_REQUIRE(c_hi_in && x_hi && (out || o_hi) && adj_tc_supported(N, H) && (npass == 1 || (c_lo_in && x_lo)));
+    XGGM_REQUIRE(!(resid && r_hi) && (reinterpret_cast<uintptr_t>(r_hi) & 7) == 0 && (reinterpret_cast<uintptr_t>(r_lo) & 7) == 0);
     XGGM_REQUIRE(!accumulate || out);
     const long long M = (long long)B * N;
     const bool unal = bd_unaligned(N);
@@ -1204,6 +1227,8 @@ int adj_apply_tc(const __nv_bfloat16* c_hi_in, const __nv_bfloat16* c_lo_in, con
     p.atomic = 0;
     p.vec4 = (H % 4 == 0) && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     single_problem(p, nullptr, resid, out, o_hi, npass == 3 ? o_lo : nullptr, accumulate);
+    p.pr[0].r_hi = r_hi;
+    p.pr[0].r_lo = npass == 3 ? r_lo : nullptr;
     if (resid && (reinterpret_cast<uintptr_t>(resid) & 15)) return XGGM_ERR_ARG;
     for (int g = 1; g < tc::MAX_GROUP; ++g) maps.m[g] = maps.m[0];
     p.gram_n = p.gram_g = p.gram_b = 0;

@@ -41,7 +41,8 @@ int build_blockdiag(const float* adj, __nv_bfloat16* hi, __nv_bfloat16* lo, int 
                     const float* alpha_dev, float self_w, int trans, cudaStream_t st);
 int adj_apply_tc(const __nv_bfloat16* c_hi, const __nv_bfloat16* c_lo, const __nv_bfloat16* x_hi,
                  const __nv_bfloat16* x_lo, float* out, __nv_bfloat16* o_hi, __nv_bfloat16* o_lo, int B, int N, int H,
-                 int accumulate, int npass, cudaStream_t st, const float* resid = nullptr);
+                 int accumulate, int npass, cudaStream_t st, const float* resid = nullptr, const __nv_bfloat16* r_hi = nullptr,
+                 const __nv_bfloat16* r_lo = nullptr);
 bool gram_tc_supported(int N, int H);
 int gram_tc(const __nv_bfloat16* p_hi, const __nv_bfloat16* p_lo, const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo,
             float* S, int B, int N, int H, int npass, cudaStream_t st);
@@ -55,10 +56,10 @@ int split_planes_t(const float* const* src, __nv_bfloat16* const* hi, __nv_bfloa
 void gemm_tc_set_debug(unsigned long long* dev_buf);
 int gemm_prof_enable(int on);
 int gemm_prof_read(double* total_ms, long long* launches, double* flops);
-int layernorm_fwd(const float*, const float*, const float*, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, float, cudaStream_t);
-int layernorm_bwd(const float*, const float*, const float*, const float*, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, cudaStream_t);
-int gelu_ln_drop_fwd(const float*, const float*, const float*, const DropSpec&, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, float, int, cudaStream_t);
-int gelu_ln_drop_bwd(const float*, const float*, const float*, const float*, const float*, const DropSpec&, float*, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, cudaStream_t);
+int layernorm_fwd(const float*, const float*, const float*, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, float, cudaStream_t, int xhat_bf16 = 0);
+int layernorm_bwd(const float*, const float*, const float*, const float*, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, cudaStream_t, int xhat_bf16 = 0);
+int gelu_ln_drop_fwd(const float*, const float*, const float*, const DropSpec&, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, float, int, cudaStream_t, int z_bf16 = 0);
+int gelu_ln_drop_bwd(const float*, const float*, const float*, const float*, const float*, const DropSpec&, float*, float*, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, cudaStream_t, int z_bf16 = 0);
 int adj_apply(const float*, const float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, int, float, const float*, float, bool, int, cudaStream_t);
 bool adj_ln_supported(int N, int H);
 int adj_ln_fwd(const float* adj, const float* P, const float* resid, const float* gamma, const float* beta, float* h,

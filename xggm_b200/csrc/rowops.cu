@@ -34,6 +34,24 @@ __device__ __forceinline__ void store_row(float* __restrict__ p, int lane, const
     for (int i = 0; i < NV; ++i)
         *reinterpret_cast<float4*>(p + 128 * i + 4 * lane) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
+// bf16 STORAGE rows (bf16 engine: saved z / xhat are kept as bf16 only): lane l holds elements 128 i + 4 l .. + 3
+template <int NV>
+__device__ __forceinline__ void load_row_bf16(const bf16* __restrict__ p, int lane, float (&v)[NV * 4]) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const uint2 t = *reinterpret_cast<const uint2*>(p + 128 * i + 4 * lane);
+        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&t.x), b = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+        v[4 * i] = __low2float(a); v[4 * i + 1] = __high2float(a); v[4 * i + 2] = __low2float(b); v[4 * i + 3] = __high2float(b);
+    }
+}
+template <int NV>
+__device__ __forceinline__ void store_row_bf16(bf16* __restrict__ p, int lane, const float (&v)[NV * 4]) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v[4 * i], v[4 * i + 1]), b = __floats2bfloat162_rn(v[4 * i + 2], v[4 * i + 3]);
+        *reinterpret_cast<uint2*>(p + 128 * i + 4 * lane) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    }
+}
 template <int NV>
 __device__ __forceinline__ void store_planes(bf16* hi, bf16* lo, size_t row_off, int lane, const float (&v)[NV * 4]) {
 #pragma unroll
@@ -74,7 +92,8 @@ __device__ __forceinline__ void flush_columns(const float (&acc)[NV * 4], float*
 // Per-warp two-stage row prefetch: lane 0 launches 1-D bulk async copies (cp.async.bulk + mbarrier
 // complete_tx) of the NEXT row of up to NT input tensors into this warp's shared-memory stage while
 // the warp computes on the current one, so a warp never sits on a DRAM round trip between rows.
-template <int NV, int NT>
+// E1: bytes per element of tensor 1 (4, or 2 when that tensor is a bf16 storage row; its stage slot keeps H floats).
+template <int NV, int NT, int E1 = 4>
 struct RowPrefetch {
     static constexpr int H = NV * 128;
     static constexpr int STAGE = NT * H;                          // floats per stage
@@ -97,21 +116,23 @@ struct RowPrefetch {
         if (lane == 0) {
             uint32_t bytes = 0;
 #pragma unroll
-            for (int t = 0; t < NT; ++t) bytes += src[t] ? H * 4 : 0;
+            for (int t = 0; t < NT; ++t) bytes += src[t] ? H * (t == 1 ? E1 : 4) : 0;
             ptx::fence_proxy_async();   // the stage was last read through the generic proxy
             ptx::mbar_expect_tx(&bar[stage], bytes);
 #pragma unroll
             for (int t = 0; t < NT; ++t)
-                if (src[t]) ptx::bulk_g2s(buf + stage * STAGE + t * H, src[t], H * 4, &bar[stage]);
+                if (src[t]) ptx::bulk_g2s(buf + stage * STAGE + t * H, src[t], H * (t == 1 ? E1 : 4), &bar[stage]);
         }
     }
     __device__ __forceinline__ void wait(int stage, uint32_t phase) { ptx::mbar_wait(&bar[stage], phase); }
     __device__ __forceinline__ void read(int stage, int t, int lane, float (&v)[NV * 4]) {
-        load_row<NV>(buf + stage * STAGE + t * H, lane, v);
+        if (t == 1 && E1 == 2) load_row_bf16<NV>(reinterpret_cast<const bf16*>(buf + stage * STAGE + t * H), lane, v);
+        else load_row<NV>(buf + stage * STAGE + t * H, lane, v);
     }
 };
 
-template <int NV>
+// XB: xhat is stored as bf16 (bf16 engine).  h may be null when only its operand planes are wanted.
+template <int NV, bool XB>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 ln_fwd_fast(const float* __restrict__ u, const float* __restrict__ gamma, const float* __restrict__ beta,
             float* __restrict__ h, float* __restrict__ xhat, float* __restrict__ rstd_out,
@@ -147,16 +168,19 @@ ln_fwd_fast(const float* __restrict__ u, const float* __restrict__ gamma, const 
         row_stats<NV>(v, 1.0f / (float)H, eps, mean, rstd);
 #pragma unroll
         for (int i = 0; i < NV * 4; ++i) v[i] = (v[i] - mean) * rstd;
-        if (xhat) store_row<NV>(xhat + (size_t)r * H, lane, v);
+        if (xhat) {
+            if (XB) store_row_bf16<NV>(reinterpret_cast<bf16*>(xhat) + (size_t)r * H, lane, v);
+            else store_row<NV>(xhat + (size_t)r * H, lane, v);
+        }
 #pragma unroll
         for (int i = 0; i < NV * 4; ++i) v[i] = fmaf(v[i], gam[i], bet[i]);
-        store_row<NV>(h + (size_t)r * H, lane, v);
+        if (h) store_row<NV>(h + (size_t)r * H, lane, v);
         if (hi) store_planes<NV>(hi, lo, (size_t)r * H, lane, v);
         if (lane == 0 && rstd_out) rstd_out[r] = rstd;
     }
 }
 
-template <int NV>
+template <int NV, bool XB>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 ln_bwd_fast(const float* __restrict__ gh, const float* __restrict__ xhat, const float* __restrict__ rstd,
             const float* __restrict__ gamma, float* __restrict__ gu, float* __restrict__ ggamma,
@@ -166,10 +190,11 @@ ln_bwd_fast(const float* __restrict__ gh, const float* __restrict__ xhat, const 
     extern __shared__ __align__(16) float sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wid = blockIdx.x * ROW_WARPS + warp, nw = gridDim.x * ROW_WARPS;
-    RowPrefetch<NV, 2> pf;
+    RowPrefetch<NV, 2, XB ? 2 : 4> pf;
+    constexpr int XS = XB ? 2 : 1;   // xhat rows advance by H elements of 2 (bf16) or 4 bytes: index in half-floats
     pf.init(sm, warp, lane);
     if (wid < M) {
-        const float* src[2] = {gh + (size_t)wid * H, xhat + (size_t)wid * H};
+        const float* src[2] = {gh + (size_t)wid * H, xhat + (size_t)wid * H / XS};
         pf.issue(0, src, lane);
     }
     float gam[NV * 4], ag[NV * 4], ab[NV * 4];
@@ -180,7 +205,7 @@ ln_bwd_fast(const float* __restrict__ gh, const float* __restrict__ xhat, const 
     for (int r = wid; r < M; r += nw, ++it) {
         const int stage = it & 1;
         if (r + nw < M) {
-            const float* src[2] = {gh + (size_t)(r + nw) * H, xhat + (size_t)(r + nw) * H};
+            const float* src[2] = {gh + (size_t)(r + nw) * H, xhat + (size_t)(r + nw) * H / XS};
             pf.issue(stage ^ 1, src, lane);
         }
         const float rs = rstd[r];
@@ -255,7 +280,8 @@ __device__ __forceinline__ uint64_t drop_stream(const DropSpec& d) {
     return d.stream + ((d.mode == 2 && d.epoch) ? (*d.epoch << 32) : 0ull);
 }
 
-template <int NV>
+// ZB: z is a bf16 storage row (bf16 engine)
+template <int NV, bool ZB>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 gld_fwd_fast(const float* __restrict__ z, const float* __restrict__ gamma, const float* __restrict__ beta,
              const DropSpec drop, float* __restrict__ out,
@@ -268,10 +294,11 @@ gld_fwd_fast(const float* __restrict__ z, const float* __restrict__ gamma, const
     const uint64_t dstream = drop_stream(drop);
     const float scale = drop.scale;
     const int wid = blockIdx.x * ROW_WARPS + warp, nw = gridDim.x * ROW_WARPS;
-    RowPrefetch<NV, 2> pf;
+    RowPrefetch<NV, 2, ZB ? 2 : 4> pf;   // tensor 0 = previous out (accumulate), tensor 1 = z
+    constexpr int ZS = ZB ? 2 : 1;
     pf.init(sm, warp, lane);
     if (wid < M) {
-        const float* src[2] = {z + (size_t)wid * H, accumulate ? out + (size_t)wid * H : nullptr};
+        const float* src[2] = {accumulate ? out + (size_t)wid * H : nullptr, z + (size_t)wid * H / ZS};
         pf.issue(0, src, lane);
     }
     int it = 0;
@@ -279,13 +306,13 @@ gld_fwd_fast(const float* __restrict__ z, const float* __restrict__ gamma, const
         const int stage = it & 1;
         const size_t ro = (size_t)r * H;
         if (r + nw < M) {
-            const float* src[2] = {z + (size_t)(r + nw) * H, accumulate ? out + (size_t)(r + nw) * H : nullptr};
+            const float* src[2] = {accumulate ? out + (size_t)(r + nw) * H : nullptr, z + (size_t)(r + nw) * H / ZS};
             pf.issue(stage ^ 1, src, lane);
         }
         pf.wait(stage, (it >> 1) & 1);
         float v[NV * 4], o[NV * 4];
-        pf.read(stage, 0, lane, v);
-        if (accumulate) pf.read(stage, 1, lane, o);
+        pf.read(stage, 1, lane, v);
+        if (accumulate) pf.read(stage, 0, lane, o);
         __syncwarp();   // every lane has drained the stage before lane 0 refills it next iteration
 #pragma unroll
         for (int i = 0; i < NV * 4; ++i) v[i] = gelu_fast(v[i]);
@@ -329,7 +356,7 @@ gld_fwd_fast(const float* __restrict__ z, const float* __restrict__ gamma, const
     }
 }
 
-template <int NV>
+template <int NV, bool ZB>
 __global__ void __launch_bounds__(ROW_WARPS * 32, 1)
 gld_bwd_fast(const float* __restrict__ gout, const float* __restrict__ z, const float* __restrict__ mean,
              const float* __restrict__ rstd, const float* __restrict__ gamma, const DropSpec drop,
@@ -342,10 +369,11 @@ gld_bwd_fast(const float* __restrict__ gout, const float* __restrict__ z, const 
     const uint64_t dstream = drop_stream(drop);
     const float scale = drop.scale;
     const int wid = blockIdx.x * ROW_WARPS + warp, nw = gridDim.x * ROW_WARPS;
-    RowPrefetch<NV, 2> pf;
+    RowPrefetch<NV, 2, ZB ? 2 : 4> pf;
+    constexpr int ZS = ZB ? 2 : 1;
     pf.init(sm, warp, lane);
     if (wid < M) {
-        const float* src[2] = {gout + (size_t)wid * H, z + (size_t)wid * H};
+        const float* src[2] = {gout + (size_t)wid * H, z + (size_t)wid * H / ZS};
         pf.issue(0, src, lane);
     }
     float ag[NV * 4], ab[NV * 4], az[NV * 4];
@@ -356,7 +384,7 @@ gld_bwd_fast(const float* __restrict__ gout, const float* __restrict__ z, const 
         const int stage = it & 1;
         const size_t ro = (size_t)r * H;
         if (r + nw < M) {
-            const float* src[2] = {gout + (size_t)(r + nw) * H, z + (size_t)(r + nw) * H};
+            const float* src[2] = {gout + (size_t)(r + nw) * H, z + (size_t)(r + nw) * H / ZS};
             pf.issue(stage ^ 1, src, lane);
         }
         const float mu = mean[r], rs = rstd[r];
@@ -640,17 +668,25 @@ static int gen_smem(K kernel, int H, size_t& bytes) {
 }
 
 // hi/lo: optional bf16 planes of the output h (lo may be null with hi set: bf16 engine)
+// xhat_bf16: xhat is written as bf16 (fast path only; the bf16 engine's storage mode).  h may be null (fast path).
 int layernorm_fwd(const float* u, const float* gamma, const float* beta, float* h, float* xhat, float* rstd,
-                  bf16* hi, bf16* lo, int M, int H, float eps, cudaStream_t st) {
+                  bf16* hi, bf16* lo, int M, int H, float eps, cudaStream_t st, int xhat_bf16) {
     if (M <= 0) return XGGM_OK;
     if (fast_ok(H, u, h, xhat) && fast_ok(H, gamma, beta, hi) && fast_ok(H, lo)) {
         XGGM_ROW_DISPATCH(H, {
             constexpr size_t smem = RowPrefetch<NV, 1>::SMEM;
-            static bool attr = false;
-            if (!attr) { XGGM_CUDA_TRY(cudaFuncSetAttribute(ln_fwd_fast<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-            XGGM_LAUNCH((ln_fwd_fast<NV>), fast_grid(M, 2), ROW_WARPS * 32, smem, st, u, gamma, beta, h, xhat, rstd, hi, lo, M, eps);
+            if (xhat_bf16) {
+                static bool attr = false;
+                if (!attr) { XGGM_CUDA_TRY(cudaFuncSetAttribute(ln_fwd_fast<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+                XGGM_LAUNCH((ln_fwd_fast<NV, true>), fast_grid(M, 2), ROW_WARPS * 32, smem, st, u, gamma, beta, h, xhat, rstd, hi, lo, M, eps);
+            } else {
+                static bool attr = false;
+                if (!attr) { XGGM_CUDA_TRY(cudaFuncSetAttribute(ln_fwd_fast<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+                XGGM_LAUNCH((ln_fwd_fast<NV, false>), fast_grid(M, 2), ROW_WARPS * 32, smem, st, u, gamma, beta, h, xhat, rstd, hi, lo, M, eps);
+            }
         });
     } else {
+        XGGM_REQUIRE(!xhat_bf16 && h);
         XGGM_LAUNCH((ln_fwd_gen), gen_grid(M), GEN_WARPS * 32, 0, st, u, gamma, beta, h, xhat, rstd, hi, lo, M, H, eps);
     }
     XGGM_LAUNCH_CHECK();
@@ -659,16 +695,23 @@ int layernorm_fwd(const float* u, const float* gamma, const float* beta, float* 
 
 // ggamma / gbeta are ACCUMULATED into (caller zeroes them)
 int layernorm_bwd(const float* gh, const float* xhat, const float* rstd, const float* gamma, float* gu,
-                  float* ggamma, float* gbeta, bf16* hi, bf16* lo, int M, int H, cudaStream_t st) {
+                  float* ggamma, float* gbeta, bf16* hi, bf16* lo, int M, int H, cudaStream_t st, int xhat_bf16) {
     if (M <= 0) return XGGM_OK;
     if (fast_ok(H, gh, xhat, gu) && fast_ok(H, gamma, hi, lo)) {
         XGGM_ROW_DISPATCH(H, {
             constexpr size_t smem = RowPrefetch<NV, 2>::SMEM;   // (>= the ROW_WARPS*H floats flush_columns needs)
-            static bool attr = false;
-            if (!attr) { XGGM_CUDA_TRY(cudaFuncSetAttribute(ln_bwd_fast<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-            XGGM_LAUNCH((ln_bwd_fast<NV>), fast_grid(M, 1), ROW_WARPS * 32, smem, st, gh, xhat, rstd, gamma, gu, ggamma, gbeta, hi, lo, M);
+            if (xhat_bf16) {
+                static bool attr = false;
+                if (!attr) { XGGM_CUDA_TRY(cudaFuncSetAttribute(ln_bwd_fast<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+                XGGM_LAUNCH((ln_bwd_fast<NV, true>), fast_grid(M, 1), ROW_WARPS * 32, smem, st, gh, xhat, rstd, gamma, gu, ggamma, gbeta, hi, lo, M);
+            } else {
+                static bool attr = false;
+                if (!attr) { XGGM_CUDA_TRY(cudaFuncSetAttribute(ln_bwd_fast<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+                XGGM_LAUNCH((ln_bwd_fast<NV, false>), fast_grid(M, 1), ROW_WARPS * 32, smem, st, gh, xhat, rstd, gamma, gu, ggamma, gbeta, hi, lo, M);
+            }
         });
     } else {
+        XGGM_REQUIRE(!xhat_bf16);
         size_t smem;
         XGGM_TRY(gen_smem(ln_bwd_gen, H, smem));
         XGGM_LAUNCH((ln_bwd_gen), gen_grid(M), GEN_WARPS * 32, smem, st, gh, xhat, rstd, gamma, gu, ggamma, gbeta, hi, lo, M, H);
@@ -679,16 +722,23 @@ int layernorm_bwd(const float* gh, const float* xhat, const float* rstd, const f
 
 int gelu_ln_drop_fwd(const float* z, const float* gamma, const float* beta, const DropSpec& drop,
                      float* out, float* mean, float* rstd, bf16* hi, bf16* lo, int M, int H, float eps,
-                     int accumulate, cudaStream_t st) {
+                     int accumulate, cudaStream_t st, int z_bf16) {
     if (M <= 0) return XGGM_OK;
     if (fast_ok(H, z, out, hi) && fast_ok(H, gamma, beta, lo) && (reinterpret_cast<uintptr_t>(drop.keep) & 3) == 0) {
         XGGM_ROW_DISPATCH(H, {
             constexpr size_t smem = RowPrefetch<NV, 2>::SMEM;
-            static bool attr = false;
-            if (!attr) { XGGM_CUDA_TRY(cudaFuncSetAttribute(gld_fwd_fast<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-            XGGM_LAUNCH((gld_fwd_fast<NV>), fast_grid(M), ROW_WARPS * 32, smem, st, z, gamma, beta, drop, out, mean, rstd, hi, lo, M, eps, accumulate);
+            if (z_bf16) {
+                static bool attr = false;
+                if (!attr) { XGGM_CUDA_TRY(cudaFuncSetAttribute(gld_fwd_fast<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+                XGGM_LAUNCH((gld_fwd_fast<NV, true>), fast_grid(M), ROW_WARPS * 32, smem, st, z, gamma, beta, drop, out, mean, rstd, hi, lo, M, eps, accumulate);
+            } else {
+                static bool attr = false;
+                if (!attr) { XGGM_CUDA_TRY(cudaFuncSetAttribute(gld_fwd_fast<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+                XGGM_LAUNCH((gld_fwd_fast<NV, false>), fast_grid(M), ROW_WARPS * 32, smem, st, z, gamma, beta, drop, out, mean, rstd, hi, lo, M, eps, accumulate);
+            }
         });
     } else {
+        XGGM_REQUIRE(!z_bf16);
         XGGM_LAUNCH((gld_fwd_gen), gen_grid(M), GEN_WARPS * 32, 0, st, z, gamma, beta, drop, out, mean, rstd, hi, lo, M, H, eps, accumulate);
     }
     XGGM_LAUNCH_CHECK();
@@ -698,16 +748,23 @@ int gelu_ln_drop_fwd(const float* z, const float* gamma, const float* beta, cons
 // gz may be null (only the planes are wanted); ggamma / gbeta / gbias? are ACCUMULATED into
 int gelu_ln_drop_bwd(const float* gout, const float* z, const float* mean, const float* rstd, const float* gamma,
                      const DropSpec& drop, float* gz, float* ggamma, float* gbeta, float* gbias,
-                     bf16* hi, bf16* lo, int M, int H, cudaStream_t st) {
+                     bf16* hi, bf16* lo, int M, int H, cudaStream_t st, int z_bf16) {
     if (M <= 0) return XGGM_OK;
     if (fast_ok(H, gout, z, gz) && fast_ok(H, gamma, hi, lo) && (reinterpret_cast<uintptr_t>(drop.keep) & 3) == 0) {
         XGGM_ROW_DISPATCH(H, {
             constexpr size_t smem = RowPrefetch<NV, 2>::SMEM;   // (>= the ROW_WARPS*H floats flush_columns needs)
-            static bool attr = false;
-            if (!attr) { XGGM_CUDA_TRY(cudaFuncSetAttribute(gld_bwd_fast<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-            XGGM_LAUNCH((gld_bwd_fast<NV>), fast_grid(M, 1), ROW_WARPS * 32, smem, st, gout, z, mean, rstd, gamma, drop, gz, ggamma, gbeta, gbias, hi, lo, M);
+            if (z_bf16) {
+                static bool attr = false;
+                if (!attr) { XGGM_CUDA_TRY(cudaFuncSetAttribute(gld_bwd_fast<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+                XGGM_LAUNCH((gld_bwd_fast<NV, true>), fast_grid(M, 1), ROW_WARPS * 32, smem, st, gout, z, mean, rstd, gamma, drop, gz, ggamma, gbeta, gbias, hi, lo, M);
+            } else {
+                static bool attr = false;
+                if (!attr) { XGGM_CUDA_TRY(cudaFuncSetAttribute(gld_bwd_fast<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+                XGGM_LAUNCH((gld_bwd_fast<NV, false>), fast_grid(M, 1), ROW_WARPS * 32, smem, st, gout, z, mean, rstd, gamma, drop, gz, ggamma, gbeta, gbias, hi, lo, M);
+            }
         });
     } else {
+        XGGM_REQUIRE(!z_bf16);
         size_t smem;
         XGGM_TRY(gen_smem(gld_bwd_gen, H, smem));
         XGGM_LAUNCH((gld_bwd_gen), gen_grid(M), GEN_WARPS * 32, smem, st, gout, z, mean, rstd, gamma, drop, gz, ggamma, gbeta, gbias, hi, lo, M, H);
