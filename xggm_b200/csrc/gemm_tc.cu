@@ -292,6 +292,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const Params p) {
     using C = Cfg<BN, NPASS, CG>;
     static_assert(CG == 1 || (!A_MN && !B_MN), "the CTA-pair kernel takes K-major operands");
+    // K-major A x MN-major B is the message-passing product only: the one kernel whose residual may arrive as operand planes
+    constexpr bool PLANE_RESID = !A_MN && B_MN;
     pdl_launch_dependents();   // the next kernel may be scheduled once every CTA of this one is resident
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for SWIZZLE_128B, computed as an offset so the pointer keeps its shared-space provenance
@@ -494,24 +496,22 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const Params p) {
                 bv = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (ok && lead && po.bias) bv = __ldg(reinterpret_cast<const float4*>(po.bias + nv));
                 const float* src = (lead && po.resid) ? po.resid : ((po.accumulate && !p.atomic) ? po.C : nullptr);
-                if (lead && po.r_hi) {      // residual from bf16 planes: 8-byte loads, hi (+ lo)
+                if constexpr (PLANE_RESID) {
+                    if (lead && po.r_hi) {      // residual from bf16 planes: RAW 8-byte loads (hi -> x.xy, lo -> x.zw), decoded at use
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int row = 4 * it + rsub;
-                        x[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (ok && row < rows) {
-                            const size_t off = (size_t)(mrow0 + row) * p.ldc + nv;
-                            const uint2 h = *reinterpret_cast<const uint2*>(po.r_hi + off);
-                            const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&h.x), h1 = *reinterpret_cast<const __nv_bfloat162*>(&h.y);
-                            x[it] = make_float4(__low2float(h0), __high2float(h0), __low2float(h1), __high2float(h1));
-                            if (po.r_lo) {
-                                const uint2 l = *reinterpret_cast<const uint2*>(po.r_lo + off);
-                                const __nv_bfloat162 l0 = *reinterpret_cast<const __nv_bfloat162*>(&l.x), l1 = *reinterpret_cast<const __nv_bfloat162*>(&l.y);
-                                x[it].x += __low2float(l0); x[it].y += __high2float(l0); x[it].z += __low2float(l1); x[it].w += __high2float(l1);
+                        for (int it = 0; it < 8; ++it) {
+                            const int row = 4 * it + rsub;
+                            x[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (ok && row < rows) {
+                                const size_t off = (size_t)(mrow0 + row) * p.ldc + nv;
+                                const uint2 h = *reinterpret_cast<const uint2*>(po.r_hi + off);
+                                uint2 l = make_uint2(0u, 0u);
+                                if (po.r_lo) l = *reinterpret_cast<const uint2*>(po.r_lo + off);
+                                x[it] = make_float4(__uint_as_float(h.x), __uint_as_float(h.y), __uint_as_float(l.x), __uint_as_float(l.y));
                             }
                         }
+                        return;
                     }
-                    return;
                 }
 #pragma unroll
                 for (int it = 0; it < 8; ++it) {
@@ -597,7 +597,17 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const Params p) {
                         for (int it = 0; it < 8; ++it) {
                             const int row = 4 * it + rsub;
                             const float4 sp = st4[row * 8 + ((lane & 7) ^ (row & 7))];
-                            const float4 bv = bvs[ci], x = xs[ci][it];
+                            const float4 bv = bvs[ci];
+                            float4 x = xs[ci][it];
+                            if constexpr (PLANE_RESID) {
+                                if (lead && po.r_hi) {   // decode the raw plane words: bf16 pairs, value = hi + lo
+                                    const uint32_t h0 = __float_as_uint(x.x), h1 = __float_as_uint(x.y), l0 = __float_as_uint(x.z), l1 = __float_as_uint(x.w);
+                                    x = make_float4(__uint_as_float(h0 << 16) + __uint_as_float(l0 << 16),
+                                                    __uint_as_float(h0 & 0xFFFF0000u) + __uint_as_float(l0 & 0xFFFF0000u),
+                                                    __uint_as_float(h1 << 16) + __uint_as_float(l1 << 16),
+                                                    __uint_as_float(h1 & 0xFFFF0000u) + __uint_as_float(l1 & 0xFFFF0000u));
+                                }
+                            }
                             o[it] = make_float4(sp.x + bv.x + x.x, sp.y + bv.y + x.y, sp.z + bv.z + x.z, sp.w + bv.w + x.w);
                         }
 #pragma unroll
