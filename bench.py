@@ -198,7 +198,8 @@ def run_reference(args):
 def workload_config(n_gpus, B=B_PER_GPU, gnn=GNN, precision="fp32", branch="node"):
     arith = {"fp32": "fp32 (tensor cores, 3 split-bf16 passes)", "bf16": "bf16 tensor cores, fp32 storage",
              "fp32_simt": "fp32 FMA"}[precision]
-    which = "VQA-CP v2 GGM node branch (delta=0)" if branch == "node" else "GGM relation branch (GQA-OOD weights)"
+    which = {"node": "VQA-CP v2 GGM node branch (delta=0)", "relation": "GGM relation branch (GQA-OOD weights)",
+             "mixed": "GQA-OOD recipe: relation / node branch drawn per step by a rank-synchronous BranchSchedule (delta=5)"}[branch]
     return {"workload": f"cfg2 graph block: {which}, {gnn}Generator L={N_LAYERS}, fwd+bwd + clip_grad_norm_(5) + BertAdam, "
                         f"B={B}/GPU, N={N_NODES}, H={HID}, sigma={SIGMA}, A={NUM_ANS}, {arith}",
             "global_batch": B * n_gpus, "per_gpu_batch": B, "parallelism": f"dp{n_gpus}",
@@ -275,7 +276,7 @@ def run_gpu(args):
         x = xp.requires_grad_(True)
         feat = visn.requires_grad_(True)
         with grads.overlap(average=True):
-            if args.branch == "relation":   # GQA-OOD weights, src/gqa/gqa_ood.py:197
+            if args.branch == "relation":   # GQA-OOD weights, src/gqa/gqa_ood.py:197 ("mixed" captures both)
                 x_gen, loss_sm, _, _ = model.relation_step(x, feat, adj, SIGMA, NUM_ANS, kl_weight=12.0)
                 w_sm = w_rel
             else:
@@ -294,6 +295,7 @@ def run_gpu(args):
     # the public entry point for a captured step: one CUDA-graph launch per step (xggm_b200.GraphedStep)
     graphed = None
     launches_per_step = None
+    mixed = None
     if not args.no_graph:
         for _ in range(2):
             compute(visn_d.detach(), xp_d.detach(), adj_d)
@@ -301,16 +303,32 @@ def run_gpu(args):
         compute(visn_d.detach(), xp_d.detach(), adj_d)
         launches_per_step = _lib.kernel_launches() - l0
         graphed = X.GraphedStep(compute, [visn_d, xp_d, adj_d])
+        if args.branch == "mixed":
+            # GQA-OOD recipe (--delta 5, script/gqa_ood.sh:21): a rank-synchronous BranchSchedule draws the branch of every
+            # step; one captured graph per branch, the schedule picks the graph to replay
+            from xggm_b200.ddp import BranchSchedule
+            sched = BranchSchedule(args.delta if args.delta > 0 else 5)
+            args.branch = "relation"
+            for _ in range(2):
+                compute(visn_d.detach(), xp_d.detach(), adj_d)
+            g_rel = X.GraphedStep(compute, [visn_d, xp_d, adj_d])
+            args.branch = "mixed"
+            mixed = (sched, {"node": graphed, "relation": g_rel})
 
     def resident_step():
-        if graphed is not None:
+        if mixed is not None:
+            l = mixed[1][mixed[0].next()].replay()
+        elif graphed is not None:
             l = graphed.replay()
         else:
             l = compute(visn_d.detach(), xp_d.detach(), adj_d)
         return l
 
     def e2e_step():
-        if graphed is not None:
+        if mixed is not None:
+            g_ = mixed[1][mixed[0].next()]
+            l = g_(visn_h.to(dev, non_blocking=True), xp_h.to(dev, non_blocking=True), adj_h.to(dev, non_blocking=True))
+        elif graphed is not None:
             # every step: this step's inputs were put on the wire (pinned host -> device staging, side
             # stream) while the previous step computed; move them in, replay, start the next step's H2D
             l = graphed.run_prefetched()
@@ -725,7 +743,7 @@ def main():
                     help="projection engine (default fp32 = BASELINE cfg 2; bf16 = cfg 3 arithmetic)")
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="graphs per GPU (default 256, the BASELINE config)")
     ap.add_argument("--gnn", default=GNN, choices=["GCN", "GIN"])
-    ap.add_argument("--branch", default="node", choices=["node", "relation"],
+    ap.add_argument("--branch", default="node", choices=["node", "relation", "mixed"],
                     help="GGM branch of the step: node generation (the --delta 0 recipe of script/vqacpv2.sh, default) or "
                          "relation generation (taken with probability delta/10; GQA-OOD uses delta 5)")
     ap.add_argument("--nodes", type=int, default=N_NODES, help="nodes per graph (36 = obj36; 64/100 = BASELINE cfg 4 sweep)")
