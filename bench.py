@@ -444,7 +444,10 @@ def run_gpu(args):
         "config": dict(workload_config(world, B, args.gnn, args.precision, args.branch),
                        collective=("none (one GPU)" if world == 1 else
                                    ("fused reduce-scatter + clip + BertAdam + parameter all-gather over NVLink peer memory "
-                                    "(xggm_dp_bertadam_step)" if fused_dp else "NCCL all-reduce (AVG) of the flat gradient bucket"))),
+                                    "(xggm_dp_bertadam_step; "
+                                    + ("NVSwitch multicast: multimem.ld_reduce / multimem.st" if getattr(flat_grad, "_xggm_multicast_ptr", 0)
+                                       else "unicast peer loads / stores") + ")"
+                                    if fused_dp else "NCCL all-reduce (AVG) of the flat gradient bucket"))),
         "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,

@@ -365,6 +365,7 @@ int xggm_bertadam_step_ex(float* p, const float* g, float* m, float* v, long lon
  * a missing peer is a CUDA error after 2 s).  CUDA-graph capturable (the epoch lives in the control block).
  *   peers->grad[k] / param[k] : rank k's flat gradient / parameter buffer (n floats each, 16-byte aligned), mapped in
  *                               this process (torch symmetric memory / CUDA IPC / VMM -- the library only sees pointers)
+ *   peers->grad_multicast / param_multicast : see the struct
  *   peers->ctl[k]             : rank k's control block, XGGM_DP_CTL_BYTES bytes, zeroed once at allocation
  *   m, v                      : this rank's moment buffers (only its slice is touched)
  *   range_lo/hi               : the bucket's ACTIVE element ranges (multiples of 4; parameters without a gradient this
@@ -379,6 +380,11 @@ typedef struct {
     void* grad[XGGM_DP_MAX_RANKS];
     void* param[XGGM_DP_MAX_RANKS];
     void* ctl[XGGM_DP_MAX_RANKS];
+    /* optional NVSwitch multicast (NVLS) addresses of the same two symmetric allocations: when non-NULL the reduce-scatter
+     * is ONE multimem.ld_reduce per 16 bytes (summed inside the switch) and the all-gather ONE multimem.st, instead of
+     * `world` peer loads / stores.  NULL (no multicast support): unicast loops. */
+    void* grad_multicast;
+    void* param_multicast;
 } xggm_dp_peers_t;
 int xggm_dp_bertadam_step(const xggm_dp_peers_t* peers, float* m, float* v, long long n, const long long* range_lo,
                           const long long* range_hi, int n_ranges, double lr, double b1, double b2, double eps,

@@ -154,7 +154,8 @@ DP_MAX_RANKS, DP_MAX_RANGES, DP_CTL_BYTES = 16, 8, 512
 class DpPeers(C.Structure):
     """xggm_dp_peers_t of include/xggm_b200.h."""
     _fields_ = [("rank", C.c_int), ("world", C.c_int), ("grad", C.c_void_p * DP_MAX_RANKS),
-                ("param", C.c_void_p * DP_MAX_RANKS), ("ctl", C.c_void_p * DP_MAX_RANKS)]
+                ("param", C.c_void_p * DP_MAX_RANKS), ("ctl", C.c_void_p * DP_MAX_RANKS),
+                ("grad_multicast", C.c_void_p), ("param_multicast", C.c_void_p)]
 
 
 PRECISIONS = {"fp32": 0, "bf16": 1, "fp32_simt": 2}

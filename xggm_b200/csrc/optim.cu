@@ -223,6 +223,8 @@ struct DpPeers {
     float* grad[DP_MAX_RANKS];
     float* param[DP_MAX_RANKS];
     unsigned int* ctl[DP_MAX_RANKS];
+    float* grad_mc;     // NVSwitch MULTICAST address of the gradient buckets (all ranks' copies at once), or null
+    float* param_mc;    // ... of the parameter buffers
 };
 struct DpRanges {
     int count;
@@ -240,6 +242,17 @@ __device__ __forceinline__ float4 ld_peer_f4(const float* p) {   // peer memory:
     float4 v;
     asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
     return v;
+}
+// NVLS: one load that returns the SUM of the addressed 16 bytes over every GPU of the multicast group (the reduction
+// happens inside the switch), and one store that lands in every GPU's copy.
+__device__ __forceinline__ float4 multimem_ld_reduce_f4(const float* mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+__device__ __forceinline__ void multimem_st_f4(float* mc, const float4& v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 __device__ __forceinline__ void st_peer_f4(float* p, const float4& v) {
     asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -274,9 +287,13 @@ __global__ void __launch_bounds__(256) dp_reduce_kernel(const DpPeers pe, long l
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const long long e = slice_lo + 4 * i;
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int k = 0; k < pe.world; ++k) {             // fixed rank order: the same sum on whichever rank owns the slice
-            const float4 v = ld_peer_f4(pe.grad[k] + e);
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        if (pe.grad_mc) {
+            s = multimem_ld_reduce_f4(pe.grad_mc + e);   // summed inside the NVSwitch: 1/W of the fabric reads
+        } else {
+            for (int k = 0; k < pe.world; ++k) {         // fixed rank order: the same sum on whichever rank owns the slice
+                const float4 v = ld_peer_f4(pe.grad[k] + e);
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
         }
         s.x *= inv; s.y *= inv; s.z *= inv; s.w *= inv;
         *reinterpret_cast<float4*>(mine + e) = s;
@@ -341,9 +358,13 @@ dp_adam_kernel(const DpPeers pe, long long slice_lo, long long slice_hi, const D
             adam1(pv.w, gv.w, mv.w, vv.w, a, lr, clip);
             *reinterpret_cast<float4*>(m + e) = mv;
             *reinterpret_cast<float4*>(v + e) = vv;
-            for (int k = 0; k < pe.world; ++k) {          // all-gather by remote stores (own copy included)
-                const int kk = (pe.rank + k) % pe.world;  // start at home: spreads the fabric traffic over the peers
-                st_peer_f4(pe.param[kk] + e, pv);
+            if (pe.param_mc) {
+                multimem_st_f4(pe.param_mc + e, pv);      // one store, every rank's copy (own included)
+            } else {
+                for (int k = 0; k < pe.world; ++k) {      // all-gather by remote stores (own copy included)
+                    const int kk = (pe.rank + k) % pe.world;  // start at home: spreads the fabric traffic over the peers
+                    st_peer_f4(pe.param[kk] + e, pv);
+                }
             }
         }
     }
@@ -373,6 +394,9 @@ int dp_bertadam_step(const xggm_dp_peers_t* peers, float* m, float* v, long long
                  peers->rank < peers->world && n_ranges >= 0 && n_ranges <= XGGM_DP_MAX_RANGES && (n_ranges == 0 || (range_lo && range_hi)));
     DpPeers pe;
     pe.rank = peers->rank; pe.world = peers->world;
+    pe.grad_mc = static_cast<float*>(peers->grad_multicast);
+    pe.param_mc = static_cast<float*>(peers->param_multicast);
+    XGGM_REQUIRE(aligned16(pe.grad_mc) && aligned16(pe.param_mc));
     for (int k = 0; k < DP_MAX_RANKS; ++k) {
         const bool live = k < pe.world;
         pe.grad[k] = live ? static_cast<float*>(peers->grad[k]) : nullptr;

@@ -7,6 +7,7 @@ staging copy.  The reference's branch choice (``random.randint(1, 10) <= delta``
 src/vqa/vqacpv2.py:192-194) must be identical on every rank or the ranks would reduce different
 parameter sets: ``BranchSchedule`` derives it from a shared seed.
 """
+import os
 import random
 
 import torch
@@ -33,6 +34,13 @@ def symmetric_empty(numel, dtype, device, zero=True):
             t.zero_()
         ptrs = [int(p) for p in hdl.buffer_ptrs]
         t._xggm_symm_handle = hdl          # keeps the mapping alive
+        mc = 0
+        try:                               # NVSwitch multicast (NVLS) address of the same allocation, if the fabric has one
+            if os.environ.get("XGGM_DP_MULTICAST", "1") != "0" and getattr(hdl, "has_multicast_support", False):
+                mc = int(hdl.multicast_ptr or 0)
+        except Exception:
+            mc = 0
+        t._xggm_multicast_ptr = mc
         return t, ptrs
     except Exception as e:                 # pragma: no cover - depends on the platform
         import warnings

@@ -194,6 +194,9 @@ class BertAdam:
         peers.rank, peers.world = dist.get_rank(), dist.get_world_size()
         for k in range(peers.world):
             peers.grad[k], peers.param[k], peers.ctl[k] = g.grads.peer_ptrs[k], g.param_ptrs[k], g.grads.ctl_ptrs[k]
+        gmc, pmc = getattr(g.grads.flat, "_xggm_multicast_ptr", 0), getattr(g.flat_p, "_xggm_multicast_ptr", 0)
+        peers.grad_multicast = gmc if (gmc and pmc) else None      # in-switch reduce / broadcast when the fabric offers it
+        peers.param_multicast = pmc if (gmc and pmc) else None
         lo = (C.c_longlong * len(ranges))(*[r[0] for r in ranges])
         hi = (C.c_longlong * len(ranges))(*[r[1] for r in ranges])
         sched = _lib.LrSchedule(g.step_dev.data_ptr(), g._ticket.data_ptr(), float(o["warmup"]), int(o["t_total"]),
