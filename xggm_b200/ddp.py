@@ -36,7 +36,11 @@ def symmetric_empty(numel, dtype, device, zero=True):
         t._xggm_symm_handle = hdl          # keeps the mapping alive
         mc = 0
         try:                               # NVSwitch multicast (NVLS) address of the same allocation, if the fabric has one
-            if os.environ.get("XGGM_DP_MULTICAST", "1") != "0" and getattr(hdl, "has_multicast_support", False):
+            # measured (B=256, 33 MB bucket): 8 GPUs 1.962 ms with multicast vs 1.981 unicast; 2 GPUs 1.971 vs 1.927 -- the
+            # in-switch reduction pays off once a rank would otherwise read more than a couple of peers
+            want = os.environ.get("XGGM_DP_MULTICAST", "auto")
+            use = want == "1" or (want == "auto" and dist.get_world_size() > 2)
+            if use and getattr(hdl, "has_multicast_support", False):
                 mc = int(hdl.multicast_ptr or 0)
         except Exception:
             mc = 0
