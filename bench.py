@@ -36,11 +36,13 @@ B_PER_GPU, N_NODES, HID, N_LAYERS, SIGMA, NUM_ANS, GNN = 256, 36, 768, 2, 1.0, 2
 CPU_SAMPLE_B = 32
 METRIC = "xggm_graph_block_train_samples_per_sec"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel -- the grouped forward
-# projection {u = h + agg Wc^T ; z = h W0^T + b}, two [9216,768]x[768,768] members, CTA-pair kernel -- from the
-# committed `ncu --set full` capture profiles/r01o_ncu_gemm_group_fwd_and_adj_apply.txt: 89.79 MB read + 20.58 MB
-# written back (most of the fp32 output is still in the 126 MB L2 at kernel end).  Algorithmic bytes of that
-# launch: 2 x (28.3 MB A planes + 2.4 MB W planes + 28.3 MB C) + 28.3 MB residual = 146 MB.
-TRAFFIC_NCU = 89787648 + 20575744
+# projection {P = h Wc^T (operand planes out) ; z = h W0^T + b (fp32 out)}, two [9216,768]x[768,768] members, CTA-pair
+# kernel, prepared weight planes -- from the committed `ncu --set full` capture
+# profiles/r02m_ncu_gemm_group_fwd_and_adj_apply.txt: 34.88 MB read + 15.29 MB written back.  Algorithmic bytes of that
+# launch: 28.3 MB A planes (shared by both members) + 2 x 2.4 MB W planes + 28.3 MB P planes + 28.3 MB z = 89.6 MB; the
+# DRAM traffic is BELOW it because the A planes arrive in L2 from the producing kernel and most of the output is still in
+# the 126 MB L2 when the kernel ends.
+TRAFFIC_NCU = 34881536 + 15287296
 
 
 def algorithmic_flops_per_sample(N=N_NODES, H=HID, L=N_LAYERS):
@@ -458,8 +460,8 @@ def run_gpu(args):
                      "achieved": gemm_tflops, "peak": peak, "unit": "TFLOP/s", "frac": gemm_tflops / peak,
                      "executed_tflops": passes * gemm_tflops, "executed_frac": passes * gemm_tflops / peak,
                      "traffic": TRAFFIC_NCU,
-                     "traffic_of": "one grouped forward launch (2 projections: 2 x 10.87 GFLOP algorithmic), ncu --set full, "
-                                   "profiles/r01o_ncu_gemm_group_fwd_and_adj_apply.txt",
+                     "traffic_of": "one grouped forward launch (2 projections: 2 x 10.87 GFLOP algorithmic; 89.6 MB algorithmic "
+                                   "bytes), ncu --set full, profiles/r02m_ncu_gemm_group_fwd_and_adj_apply.txt",
                      "peak_source": f"{peaks['source']} bf16 burst (MEASURED_PEAKS.json)",
                      "launches_timed": g_n, "avg_launch_us": (g_ms / g_n * 1e3) if g_n else None,
                      "gemm_share_of_step": (g_ms / prof_steps) / ms_step if ms_step > 0 else None,
