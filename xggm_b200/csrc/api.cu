@@ -304,10 +304,18 @@ static int gnn_fwd(int kind, const float* x, const float* adj, const float* cons
             // the residual h_k comes from its operand planes (hi + lo = 16 mantissa bits, ~1e-5 like the products), so
             // h_{k+1} never has to exist as an fp32 tensor: LayerNorm writes xhat and the planes only
             const bool fast_ln = H % 128 == 0 && H >= 128 && H <= 1024;
-            XGGM_TRY(adj_apply_tc(coef_hi, coef_lo, P_op.hi, P_op.lo, work /* u */, nullptr, nullptr, B, N, H, 0, npass(), st,
-                                  nullptr, hops[k].hi, hops[k].lo));
-            XGGM_TRY(layernorm_fwd(work, cp[3 * k + 1], cp[3 * k + 2], fast_ln ? nullptr : h_next, saved + L.conv(k, 1),
-                                   saved + L.conv(k, 3), mut(next_op.hi), lo_or_null(next_op), M, H, LN_EPS, st, bst ? 1 : 0));
+            if (adj_ln_tc_supported(N, H)) {
+                // H = 768: message passing + LayerNorm in ONE cluster kernel (four CTAs x 192 columns share a row block and
+                // exchange the row statistics through distributed shared memory); u never reaches global memory
+                XGGM_TRY(adj_ln_tc(coef_hi, coef_lo, P_op.hi, P_op.lo, hops[k].hi, hops[k].lo, cp[3 * k + 1], cp[3 * k + 2],
+                                   saved + L.conv(k, 1), bst ? 1 : 0, saved + L.conv(k, 3), nullptr, mut(next_op.hi),
+                                   lo_or_null(next_op), B, N, H, LN_EPS, npass(), st));
+            } else {
+                XGGM_TRY(adj_apply_tc(coef_hi, coef_lo, P_op.hi, P_op.lo, work /* u */, nullptr, nullptr, B, N, H, 0, npass(), st,
+                                      nullptr, hops[k].hi, hops[k].lo));
+                XGGM_TRY(layernorm_fwd(work, cp[3 * k + 1], cp[3 * k + 2], fast_ln ? nullptr : h_next, saved + L.conv(k, 1),
+                                       saved + L.conv(k, 3), mut(next_op.hi), lo_or_null(next_op), M, H, LN_EPS, st, bst ? 1 : 0));
+            }
         } else if (gcn && adj_ln_supported(N, H)) {
             // same algebra with the message passing folded into the LayerNorm kernel (one CTA per graph):
             //     h_next = LN(h + adj @ P)

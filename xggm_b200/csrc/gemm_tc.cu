@@ -875,6 +875,293 @@ __global__ void __launch_bounds__(256) weight_planes_kernel(const WPlaneJobs job
     }
 }
 
+// =================================================================================================
+// Message passing + LayerNorm in ONE kernel (GCNConv, src/module/gcn.py:28-29, re-associated):
+//     h_next = LN( h + adj_b @ P_b ) * gamma + beta            xhat, rstd saved; h_next leaves as operand planes
+// A row-complete epilogue needs all H = 768 columns of a row, i.e. 768 fp32 TMEM columns where an SM has 512: the row
+// block is therefore split over a CLUSTER OF FOUR CTAs, one 192-column tile each.  Every CTA runs the (tiny, K = 192)
+// block-diagonal product of its tile into TMEM, adds the residual (from h's operand planes, staged through shared
+// memory into the thread-per-row domain), keeps per-row sum / sum of squares of its 192 columns, writes u back INTO
+// TMEM (tcgen05.st), and the four CTAs exchange the partial statistics through distributed shared memory
+// (st.shared::cluster + an mbarrier every epilogue warp of the cluster arrives on).  A second pass over TMEM
+// normalises and stores xhat, the planes of h_next (and optionally fp32 h_next) with coalesced 16-byte accesses.
+// u never touches global memory and the separate LayerNorm kernel disappears.
+// One tile per CTA (grid = 4 x row tiles, cluster dimension 4); warp roles as in gemm_tc_kernel.
+// =================================================================================================
+struct AdjLnParams {
+    int M, H, num_kb, bd_stride, bd_kn;
+    const __nv_bfloat16* r_hi;   // residual h as operand planes (lo may be null: bf16 engine)
+    const __nv_bfloat16* r_lo;
+    const float* gamma;
+    const float* beta;
+    float* xhat;                 // [M,H] fp32, or bf16 when xhat_bf16
+    float* rstd;                 // [M]
+    float* h_out;                // optional fp32 h_next
+    __nv_bfloat16* o_hi;         // planes of h_next
+    __nv_bfloat16* o_lo;
+    float eps;
+    int xhat_bf16;
+};
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+          "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+          "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.b32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const uint64_t t0 = global_ns();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (global_ns() - t0 > 2000000000ull) __trap();
+    }
+}
+__device__ __forceinline__ void st_cluster_f2(uint32_t cluster_addr, float a, float b) {
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
+}
+
+constexpr int ALN_BN = 192;
+constexpr int ALN_CL = 4;       // CTAs per cluster = column tiles per row block (H = 768)
+template <int NPASS>
+struct AlnCfg {
+    static constexpr int A_TILE = BM * BK * 2;
+    static constexpr int B_TILE = ALN_BN * BK * 2;
+    static constexpr int NPLANE = NPASS == 3 ? 2 : 1;
+    static constexpr int STAGE_BYTES = NPLANE * (A_TILE + B_TILE);
+    static constexpr int STAGES = 2;
+    static constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;                  // one swizzled [32][8 float4] tile per warp
+    static constexpr int STAT_BYTES = 2 * ALN_CL * BM * 8;                     // [8 sources][128 rows] float2
+    static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + STAT_BYTES + 256 + 1024;
+    static_assert(SMEM <= SMEM_LIMIT, "adj_ln_tc shared memory");
+};
+
+template <int NPASS>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+adj_ln_tc_kernel(const __grid_constant__ GroupMaps maps, const AdjLnParams p) {
+    using C = AlnCfg<NPASS>;
+    pdl_launch_dependents();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* stage_base = smem;
+    float4* epi = reinterpret_cast<float4*>(smem + C::STAGES * C::STAGE_BYTES);
+    float2* stats = reinterpret_cast<float2*>(smem + C::STAGES * C::STAGE_BYTES + C::EPI_BYTES);   // [2*ALN_CL][BM]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::EPI_BYTES + C::STAT_BYTES);
+    uint64_t* full = bars;                  // [STAGES]
+    uint64_t* empty = bars + C::STAGES;     // [STAGES]
+    uint64_t* acc_full = bars + 2 * C::STAGES;
+    uint64_t* stat_bar = bars + 2 * C::STAGES + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();          // column tile of this CTA
+    const int t = blockIdx.x / ALN_CL;                 // row tile of this cluster
+    const MapSet& ms = maps.m[0];
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&ms.a_hi);
+        prefetch_tmap(&ms.b_hi);
+        if (NPASS == 3) { prefetch_tmap(&ms.a_lo); prefetch_tmap(&ms.b_lo); }
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        mbar_init(stat_bar, ALN_CL * EPI_WARPS);       // one elected arrival per epilogue warp of the whole cluster
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    cluster_sync_all();                                // the peers' barriers exist before anything signals them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    const int n0 = (int)crank * ALN_BN;
+    const int m0 = t * BM;                             // rows of the coefficient tile
+    const int out0 = p.bd_kn > 0 ? t * BM : t * p.bd_stride;                       // first output row of the tile
+    const int live = min(p.bd_kn > 0 ? BM : p.bd_stride, p.M - out0);             // output rows that exist
+    const int b_krow0 = p.bd_kn > 0 ? (t * BM / p.bd_kn) * p.bd_kn : t * p.bd_stride;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                const int stage = kb % C::STAGES;
+                if (kb >= C::STAGES) mbar_wait(&empty[stage], ((kb / C::STAGES) - 1) & 1);
+                mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+                uint8_t* sa = stage_base + stage * C::STAGE_BYTES;
+                uint8_t* sb = sa + C::NPLANE * C::A_TILE;
+#pragma unroll
+                for (int pl = 0; pl < C::NPLANE; ++pl) {
+                    tma_load_2d(sa + pl * C::A_TILE, pl == 0 ? &ms.a_hi : &ms.a_lo, &full[stage], kb * BK, m0);
+#pragma unroll
+                    for (int i = 0; i < ALN_BN / 64; ++i)
+                        tma_load_2d(sb + pl * C::B_TILE + i * (BK * 128), pl == 0 ? &ms.b_hi : &ms.b_lo, &full[stage],
+                                    n0 + 64 * i, b_krow0 + kb * BK);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BM, ALN_BN, false, true);
+            uint32_t first = 1;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                const int stage = kb % C::STAGES;
+                mbar_wait(&full[stage], (kb / C::STAGES) & 1);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(stage_base + stage * C::STAGE_BYTES);
+                const uint32_t sb = sa + C::NPLANE * C::A_TILE;
+#pragma unroll
+                for (int pass = 0; pass < NPASS; ++pass) {
+                    const int apl = (NPASS == 3 && pass == 0) ? 1 : 0;
+                    const int bpl = (NPASS == 3 && pass == 1) ? 1 : 0;
+                    const uint64_t adesc0 = make_sdesc(sa + apl * C::A_TILE, 16, 1024);
+                    const uint64_t bdesc0 = make_sdesc(sb + bpl * C::B_TILE, BK * 128, 1024);
+#pragma unroll
+                    for (int k = 0; k < BK / UK; ++k) {
+                        umma_bf16(tmem_base, adesc0 + (uint64_t)((k * UK * 2) >> 4), bdesc0 + (uint64_t)((k * UK * 128) >> 4), idesc,
+                                  first ? 0u : 1u);
+                        first = 0;
+                    }
+                }
+                umma_commit(&empty[stage]);
+            }
+            umma_commit(acc_full);
+        }
+    } else {
+        // ================================ epilogue: two passes over TMEM ====================================
+        const int q = warp & 3, csub = (warp - 2) >> 2;
+        float4* st4 = epi + (warp - 2) * 32 * 8;
+        const int rsub = lane >> 3, c4i = lane & 7;
+        const int rows = max(0, min(32, live - q * 32));           // live rows of this warp's lane quarter
+        const int mrow0 = out0 + q * 32;
+        constexpr int NCH = (ALN_BN / 32) / 2;                      // column chunks per warp (two warps per quarter)
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) {
+            const int c = csub + 2 * ci;
+            const int nv = n0 + c * 32 + 4 * c4i;
+            // (a) residual chunk: coalesced 8-byte plane loads in the store-domain mapping -> swizzled smem tile
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int row = 4 * it + rsub;
+                float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < rows) {
+                    const size_t off = (size_t)(mrow0 + row) * p.H + nv;
+                    const uint2 h = *reinterpret_cast<const uint2*>(p.r_hi + off);
+                    r = make_float4(__uint_as_float(h.x << 16), __uint_as_float(h.x & 0xFFFF0000u),
+                                    __uint_as_float(h.y << 16), __uint_as_float(h.y & 0xFFFF0000u));
+                    if (p.r_lo) {
+                        const uint2 l = *reinterpret_cast<const uint2*>(p.r_lo + off);
+                        r.x += __uint_as_float(l.x << 16); r.y += __uint_as_float(l.x & 0xFFFF0000u);
+                        r.z += __uint_as_float(l.y << 16); r.w += __uint_as_float(l.y & 0xFFFF0000u);
+                    }
+                }
+                st4[row * 8 + (c4i ^ (row & 7))] = r;
+            }
+            __syncwarp();
+            // (b) accumulator chunk -> registers (thread = row), (c) u = acc + residual, row statistics, (d) u back to TMEM
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + c * 32 + ((uint32_t)(q * 32) << 16);
+            tmem_ld32(taddr, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 r = st4[lane * 8 + (j ^ (lane & 7))];
+                const float u0 = __uint_as_float(v[4 * j]) + r.x, u1 = __uint_as_float(v[4 * j + 1]) + r.y;
+                const float u2 = __uint_as_float(v[4 * j + 2]) + r.z, u3 = __uint_as_float(v[4 * j + 3]) + r.w;
+                s1 += (u0 + u1) + (u2 + u3);
+                s2 = fmaf(u0, u0, fmaf(u1, u1, fmaf(u2, u2, fmaf(u3, u3, s2))));
+                v[4 * j] = __float_as_uint(u0); v[4 * j + 1] = __float_as_uint(u1);
+                v[4 * j + 2] = __float_as_uint(u2); v[4 * j + 3] = __float_as_uint(u3);
+            }
+            tmem_st32(taddr, v);
+            __syncwarp();
+        }
+        // exchange the partial statistics: slot (crank, csub) of every CTA of the cluster, row q*32 + lane
+        {
+            float2* mine = stats + (crank * 2 + csub) * BM + q * 32 + lane;
+#pragma unroll
+            for (uint32_t k = 0; k < ALN_CL; ++k) st_cluster_f2(map_to_cta(mine, k), s1, s2);
+            asm volatile("fence.acq_rel.cluster;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (uint32_t k = 0; k < ALN_CL; ++k) mbar_arrive_cluster(map_to_cta(stat_bar, k));
+            }
+        }
+        mbar_wait_cluster(stat_bar, 0);
+        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 2 * ALN_CL; ++k) {
+            const float2 w = stats[k * BM + q * 32 + lane];
+            t1 += w.x; t2 += w.y;
+        }
+        const float inv_h = 1.0f / (float)p.H;
+        const float mean = t1 * inv_h;
+        const float var = fmaxf(t2 * inv_h - mean * mean, 0.f);
+        const float rstd = 1.0f / sqrtf(var + p.eps);
+        if (crank == 0 && csub == 0 && lane < rows && p.rstd) p.rstd[mrow0 + lane] = rstd;
+        // pass 2: normalise, transpose through smem, coalesced stores of xhat / h_next planes (/ fp32 h_next)
+        tc_fence_after();
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) {
+            const int c = csub + 2 * ci;
+            const int nv = n0 + c * 32 + 4 * c4i;
+            uint32_t v[32];
+            tmem_ld32(tmem_base + c * 32 + ((uint32_t)(q * 32) << 16), v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                st4[lane * 8 + (j ^ (lane & 7))] =
+                    make_float4((__uint_as_float(v[4 * j]) - mean) * rstd, (__uint_as_float(v[4 * j + 1]) - mean) * rstd,
+                                (__uint_as_float(v[4 * j + 2]) - mean) * rstd, (__uint_as_float(v[4 * j + 3]) - mean) * rstd);
+            __syncwarp();
+            const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + nv));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.beta + nv));
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int row = 4 * it + rsub;
+                if (row < rows) {
+                    const float4 x = st4[row * 8 + (c4i ^ (row & 7))];
+                    const size_t off = (size_t)(mrow0 + row) * p.H + nv;
+                    if (p.xhat) {
+                        if (p.xhat_bf16) {
+                            __nv_bfloat162 a = __floats2bfloat162_rn(x.x, x.y), bb = __floats2bfloat162_rn(x.z, x.w);
+                            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.xhat) + off) =
+                                make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&bb));
+                        } else {
+                            *reinterpret_cast<float4*>(p.xhat + off) = x;
+                        }
+                    }
+                    const float4 h = make_float4(fmaf(x.x, g.x, b.x), fmaf(x.y, g.y, b.y), fmaf(x.z, g.z, b.z), fmaf(x.w, g.w, b.w));
+                    if (p.h_out) *reinterpret_cast<float4*>(p.h_out + off) = h;
+                    if (p.o_hi) store_planes4(p.o_hi, p.o_lo, off, h);
+                }
+            }
+            __syncwarp();
+        }
+        tc_fence_before();
+    }
+    tc_fence_before();
+    cluster_sync_all();      // no CTA may exit (or free TMEM) while a peer can still write its statistics / barrier
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------------------
@@ -1250,6 +1537,79 @@ int adj_apply_tc(const __nv_bfloat16* c_hi_in, const __nv_bfloat16* c_lo_in, con
     // (not a projection: kept out of the GEMM roofline accounting)
     return npass == 3 ? launch_tc<ABN, 3, false, true>(maps, p, grid, st)
                       : launch_tc<ABN, 1, false, true>(maps, p, grid, st);
+}
+
+// h_next = LN(h + C[b] @ P[b]) fused (adj_ln_tc_kernel): coefficient planes from build_blockdiag, P and the residual h as
+// [B*N, H] operand planes.  H must be 4 x 192 (X-GGM: 768).  xhat [M,H] (fp32, or bf16 when xhat_bf16), rstd [M],
+// planes of h_next (o_hi / o_lo) and optionally fp32 h_next.
+bool adj_ln_tc_supported(int N, int H) {
+    static int off = -1;
+    if (off < 0) {
+        const char* e = getenv("XGGM_ADJ_LN_TC");
+        off = (e && e[0] == '0') ? 1 : 0;
+    }
+    return !off && adj_tc_supported(N, H) && H == tc::ALN_CL * tc::ALN_BN;
+}
+int adj_ln_tc(const __nv_bfloat16* c_hi_in, const __nv_bfloat16* c_lo_in, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo,
+              const __nv_bfloat16* r_hi, const __nv_bfloat16* r_lo, const float* gamma, const float* beta, float* xhat,
+              int xhat_bf16, float* rstd, float* h_out, __nv_bfloat16* o_hi, __nv_bfloat16* o_lo, int B, int N, int H, float eps,
+              int npass, cudaStream_t st) {
+    if (B <= 0) return XGGM_OK;
+    XGGM_REQUIRE(c_hi_in && x_hi && r_hi && gamma && beta && xhat && rstd && adj_ln_tc_supported(N, H) &&
+                 (npass == 1 || (c_lo_in && x_lo && r_lo)));
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    XGGM_REQUIRE(al16(gamma) && al16(beta) && al16(xhat) && al16(h_out) && (reinterpret_cast<uintptr_t>(r_hi) & 7) == 0 &&
+                 (reinterpret_cast<uintptr_t>(r_lo) & 7) == 0 && (reinterpret_cast<uintptr_t>(o_hi) & 7) == 0 &&
+                 (reinterpret_cast<uintptr_t>(o_lo) & 7) == 0);
+    const long long M = (long long)B * N;
+    const bool unal = bd_unaligned(N);
+    const int G = tc::BM / N, T = unal ? ceil_div(M, tc::BM) : ceil_div(B, G);
+    const int KW = unal ? BD_KW : tc::BM;
+    tc::GroupMaps maps;
+    CUtensorMap &ah = maps.m[0].a_hi, &al = maps.m[0].a_lo, &bh = maps.m[0].b_hi, &bl = maps.m[0].b_lo;
+    XGGM_TRY(make_map(&ah, c_hi_in, (long long)T * tc::BM, KW, tc::BM));
+    XGGM_TRY(make_map(&bh, x_hi, M, H, tc::BK));
+    if (npass == 3) {
+        XGGM_TRY(make_map(&al, c_lo_in, (long long)T * tc::BM, KW, tc::BM));
+        XGGM_TRY(make_map(&bl, x_lo, M, H, tc::BK));
+    } else {
+        al = ah;
+        bl = bh;
+    }
+    for (int g = 1; g < tc::MAX_GROUP; ++g) maps.m[g] = maps.m[0];
+    tc::AdjLnParams p;
+    p.M = (int)M; p.H = H; p.num_kb = KW / tc::BK;
+    p.bd_stride = unal ? tc::BM : G * N;
+    p.bd_kn = unal ? N : 0;
+    p.r_hi = r_hi; p.r_lo = npass == 3 ? r_lo : nullptr;
+    p.gamma = gamma; p.beta = beta;
+    p.xhat = xhat; p.xhat_bf16 = xhat_bf16; p.rstd = rstd; p.h_out = h_out;
+    p.o_hi = o_hi; p.o_lo = npass == 3 ? o_lo : nullptr;
+    p.eps = eps;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(T * tc::ALN_CL);
+    cfg.blockDim = dim3(tc::NUM_THREADS);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = tc::ALN_CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (npass == 3) {
+        static bool set3 = false;
+        if (!set3) { XGGM_CUDA_TRY(cudaFuncSetAttribute(tc::adj_ln_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::AlnCfg<3>::SMEM)); set3 = true; }
+        cfg.dynamicSmemBytes = tc::AlnCfg<3>::SMEM;
+        XGGM_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::adj_ln_tc_kernel<3>, maps, p));
+    } else {
+        static bool set1 = false;
+        if (!set1) { XGGM_CUDA_TRY(cudaFuncSetAttribute(tc::adj_ln_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::AlnCfg<1>::SMEM)); set1 = true; }
+        cfg.dynamicSmemBytes = tc::AlnCfg<1>::SMEM;
+        XGGM_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::adj_ln_tc_kernel<1>, maps, p));
+    }
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
 }
 
 // Transposed split of `count` [R,C] fp32 matrices into [C,R] bf16 planes (one launch per 8 matrices).

@@ -43,6 +43,11 @@ int adj_apply_tc(const __nv_bfloat16* c_hi, const __nv_bfloat16* c_lo, const __n
                  const __nv_bfloat16* x_lo, float* out, __nv_bfloat16* o_hi, __nv_bfloat16* o_lo, int B, int N, int H,
                  int accumulate, int npass, cudaStream_t st, const float* resid = nullptr, const __nv_bfloat16* r_hi = nullptr,
                  const __nv_bfloat16* r_lo = nullptr);
+bool adj_ln_tc_supported(int N, int H);
+int adj_ln_tc(const __nv_bfloat16* c_hi, const __nv_bfloat16* c_lo, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo,
+              const __nv_bfloat16* r_hi, const __nv_bfloat16* r_lo, const float* gamma, const float* beta, float* xhat,
+              int xhat_bf16, float* rstd, float* h_out, __nv_bfloat16* o_hi, __nv_bfloat16* o_lo, int B, int N, int H, float eps,
+              int npass, cudaStream_t st);
 bool gram_tc_supported(int N, int H);
 int gram_tc(const __nv_bfloat16* p_hi, const __nv_bfloat16* p_lo, const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo,
             float* S, int B, int N, int H, int npass, cudaStream_t st);
