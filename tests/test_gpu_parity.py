@@ -9,6 +9,7 @@ from conftest import load_golden, rel_l2, rel_max
 from oracle import xggm_oracle as O
 
 pytestmark = pytest.mark.gpu
+ROOT_DIR = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
 
 TOL = 1e-4
 
@@ -1121,3 +1122,41 @@ def test_api_surface_matches_reference_fixture(tag, engine):
             assert err <= SCALAR_TOL_TC * max(scalars), f"{tag} g/{k}: abs err {err:.3e} vs scale {max(scalars):.3e}"
         else:
             _close(gp, ref, 5 * TOL, f"{tag} g/{k}")
+
+
+def test_fused_message_passing_layernorm_cluster_kernel_matches_the_two_kernel_path():
+    """adj_ln_tc (XGGM_ADJ_LN_TC=1: message passing + LayerNorm in one 4-CTA-cluster kernel, u kept in TMEM, row
+    statistics exchanged through distributed shared memory) against the default adj_apply_tc + layernorm pair, in a
+    child process (the switch is read once per process): outputs and gradients of a GCN generator at B=40 (a ragged
+    last row tile) agree to the engines' rounding."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, torch
+sys.path.insert(0, %r)
+import xggm_b200 as X
+from oracle import xggm_oracle as O
+torch.manual_seed(3)
+dev = torch.device('cuda:0')
+mod = X.GCNGenerator(768, 2).to(dev).eval()
+visn, _, adj_true = O.make_inputs(5, 40, 36, 768)
+x = visn.to(dev).requires_grad_(True)
+a = O.strip_diag(adj_true).to(dev).requires_grad_(True)
+xo, ao = mod(x, a)
+g = torch.Generator().manual_seed(1)
+cx, ca = torch.randn(40, 36, 768, generator=g).to(dev), torch.randn(40, 36, 36, generator=g).to(dev)
+((xo * cx).sum() + (ao * ca).sum()).backward()
+torch.save({'xo': xo.detach().cpu(), 'ao': ao.detach().cpu(), 'gx': x.grad.cpu(), 'ga': a.grad.cpu(),
+            'gw': mod.gnn_layers[0].gnn_layers[0].layer_norm.weight.grad.cpu()}, sys.argv[1])
+""" % ROOT_DIR
+    import tempfile
+    outs = {}
+    with tempfile.TemporaryDirectory() as d:
+        for flag in ("0", "1"):
+            path = os.path.join(d, f"o{flag}.pt")
+            env = dict(os.environ, XGGM_ADJ_LN_TC=flag)
+            subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300)
+            outs[flag] = torch.load(path)
+    for k in outs["0"]:
+        _close(outs["1"][k], outs["0"][k], 2e-5 if k in ("xo", "ao") else 1e-4, k)

@@ -1542,13 +1542,18 @@ int adj_apply_tc(const __nv_bfloat16* c_hi_in, const __nv_bfloat16* c_lo_in, con
 // h_next = LN(h + C[b] @ P[b]) fused (adj_ln_tc_kernel): coefficient planes from build_blockdiag, P and the residual h as
 // [B*N, H] operand planes.  H must be 4 x 192 (X-GGM: 768).  xhat [M,H] (fp32, or bf16 when xhat_bf16), rstd [M],
 // planes of h_next (o_hi / o_lo) and optionally fp32 h_next.
+// OPT-IN (XGGM_ADJ_LN_TC=1).  Parity-green on every fixture and on the B=256 oracle tests, but measured SLOWER than the
+// two kernels it replaces at the BASELINE batch: 90 us per launch against 25 + 13 us (step 2.04 vs 1.87 ms, same box;
+// profiles/r02n_launches.txt).  One tile per CTA serialises prologue -> TMA -> MMA -> two-pass epilogue (~25-30 us), the
+// 72 row blocks of B=256 are 72 clusters of four, and a B200 holds 34 such clusters at a time (GPCs of 18-20 SMs): three
+// rounds.  A persistent, double-buffered variant would hide the epilogue behind the next tile at B >= 1024, not at 256.
 bool adj_ln_tc_supported(int N, int H) {
-    static int off = -1;
-    if (off < 0) {
+    static int on = -1;
+    if (on < 0) {
         const char* e = getenv("XGGM_ADJ_LN_TC");
-        off = (e && e[0] == '0') ? 1 : 0;
+        on = (e && e[0] == '1') ? 1 : 0;
     }
-    return !off && adj_tc_supported(N, H) && H == tc::ALN_CL * tc::ALN_BN;
+    return on && adj_tc_supported(N, H) && H == tc::ALN_CL * tc::ALN_BN;
 }
 int adj_ln_tc(const __nv_bfloat16* c_hi_in, const __nv_bfloat16* c_lo_in, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo,
               const __nv_bfloat16* r_hi, const __nv_bfloat16* r_lo, const float* gamma, const float* beta, float* xhat,
