@@ -225,6 +225,31 @@ def synthetic_inputs(seed, B, n_nodes=N_NODES, hidden=HID):
     return v.float(), xp.float(), c.float()
 
 
+def pin_to_gpu_numa(local):
+    """Bind this rank to the cores of the NUMA node its GPU hangs off (pinned host buffers are then allocated there and
+    the per-step H2D copies of eight ranks do not all cross the inter-socket link).  Best effort: silently does nothing
+    where sysfs does not expose the topology.  XGGM_BENCH_NO_NUMA=1 disables it."""
+    if os.environ.get("XGGM_BENCH_NO_NUMA") == "1":
+        return None
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        dom = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{dom}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 # ---------------------------------------------------------------------------------- GPU arm
 def run_gpu(args):
     import torch.distributed as dist
@@ -236,6 +261,7 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = pin_to_gpu_numa(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(9595)  # reference default seed, src/param.py:49 (same on every rank: same branch, same init)
@@ -451,7 +477,7 @@ def run_gpu(args):
                                        else "unicast peer loads / stores") + ")"
                                     if fused_dp else "NCCL all-reduce (AVG) of the flat gradient bucket"))),
         "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps, "numa_node_of_rank0": numa},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "tensor",
