@@ -460,7 +460,7 @@ def run_gpu(args):
     peak = peaks["bf16_tflops"]
     h2d = sum(t.numel() * 4 for t in (visn_h, xp_h, adj_h))
     threads = os.cpu_count() or 1
-    if args.quick:      # sweep lines (tools/sweep.py): the GPU arm only
+    if args.quick or world > 1:      # sweep lines (tools/sweep.py) and multi-GPU runs: the GPU arm only (baselines: N = 1)
         cpu_sec, cpu_kind, eager_ms, eager_kind = float("inf"), "skipped", float("inf"), "skipped"
     else:
         cpu_sec, cpu_kind = cpu_reference_steps(5, 2, threads, branch=args.branch, gnn=args.gnn)
@@ -498,10 +498,12 @@ def run_gpu(args):
                            "frac_of_bf16_peak": flops_step / (ms_step * 1e-3) / 1e12 / peak,
                            "t_roof_us": flops_step / (peak * 1e12) * 1e6},
         "bf16_engine": alt,
-        "cpu_baseline": {"value": CPU_SAMPLE_B / cpu_sec, "unit": "samples/s", "cores": threads, "kind": cpu_kind,
+        "cpu_baseline": None if cpu_kind == "skipped" else
+                        {"value": CPU_SAMPLE_B / cpu_sec, "unit": "samples/s", "cores": threads, "kind": cpu_kind,
                          "sample": f"B={CPU_SAMPLE_B} graphs/step, 5 timed steps after 2 warm-up, median"},
         # the reference's own eager PyTorch path on this B200 (same step, same B, true fp32, no CUDA graph)
-        "eager_gpu_baseline": {"value": B / (eager_ms * 1e-3), "unit": "samples/s", "ms_per_step": eager_ms,
+        "eager_gpu_baseline": None if eager_kind == "skipped" else
+                              {"value": B / (eager_ms * 1e-3), "unit": "samples/s", "ms_per_step": eager_ms,
                                "kind": eager_kind, "dtype": "f32 (allow_tf32=False)", "n_gpus": 1,
                                "sample": f"B={B} graphs/step on rank 0's GPU, 10 timed steps after 3 warm-up, CUDA events"},
     }
