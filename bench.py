@@ -606,7 +606,7 @@ def run_iteration(args):
     adj = resident[5]
 
     def block():
-        it.fg_down.zero_()
+        it.fg.zero_()
         x = pooled.detach().requires_grad_(True)
         f = visn.detach().requires_grad_(True)
         x_gen, loss_sm, _, _ = it.heads.node_step(x, f, adj, 1.0, it.A)
@@ -646,7 +646,7 @@ def run_iteration(args):
         except Exception as ex:   # the baseline must never take the measured arm down
             eager = {"unavailable": repr(ex)[:200]}
     ms_it = ms_res / args.steps
-    n_par = sum(p.numel() for p in it.fg_base.params) + sum(p.numel() for p in it.fg_down.params)
+    n_par = sum(p.numel() for p in it.fg.params)
     line = {
         "metric": ITER_METRIC, "value": B * world / (ms_it * 1e-3), "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_it, "higher_is_better": True,
@@ -657,6 +657,9 @@ def run_iteration(args):
                                f"20 tokens, A={NUM_ANS}",
                    "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world}",
                    "parameters": n_par, "allreduce_bytes_per_iteration": 2 * 4 * n_par if world > 1 else 0,
+                   "collective": ("none (one GPU)" if world == 1 else
+                                  ("fused reduce-scatter + joint clip + BertAdam + parameter all-gather over NVLink peer memory"
+                                   if it.fused_dp else "NCCL all-reduce (AVG)")),
                    "l2": "inputs and activations far exceed the 126 MB L2 (no flush needed)",
                    "launch": "one CUDA-graph replay per iteration (xggm_b200.GraphedStep, one graph per GGM branch)"
                              if graphs is not None else "eager launches"},

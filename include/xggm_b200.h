@@ -370,6 +370,8 @@ int xggm_bertadam_step_ex(float* p, const float* g, float* m, float* v, long lon
  *   m, v                      : this rank's moment buffers (only its slice is touched)
  *   range_lo/hi               : the bucket's ACTIVE element ranges (multiples of 4; parameters without a gradient this
  *                               step are skipped as optimization.py:139-141 does); n_ranges <= XGGM_DP_MAX_RANGES
+ *   range_lr?                 : base learning rate per range (parameter groups with different rates sharing one
+ *                               bucket, e.g. the trainers' encoder / down-task groups); NULL = `lr` everywhere
  *   sumsq_out?                : receives the squared total norm of the averaged gradient
  * Every rank must make the same call (same n, ranges, hyper-parameters) once per step.  world == 1 is valid. */
 #define XGGM_DP_MAX_RANKS 16
@@ -387,7 +389,7 @@ typedef struct {
     void* param_multicast;
 } xggm_dp_peers_t;
 int xggm_dp_bertadam_step(const xggm_dp_peers_t* peers, float* m, float* v, long long n, const long long* range_lo,
-                          const long long* range_hi, int n_ranges, double lr, double b1, double b2, double eps,
+                          const long long* range_hi, const double* range_lr, int n_ranges, double lr, double b1, double b2, double eps,
                           double weight_decay, double max_norm, const xggm_lr_schedule_t* sched, float* sumsq_out,
                           xggm_stream_t s);
 /* elementwise sigmoid (encoder_adj tail, src/vqa/vqacpv2_model.py:91-94) */

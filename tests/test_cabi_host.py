@@ -247,3 +247,32 @@ def test_bertadam_state_dict_round_trip():
         n = p.numel()
         assert torch.equal(g2.m[o:o + n], g.m[o:o + n]) and torch.equal(g2.v[o:o + n], g.v[o:o + n])
     assert g2.step == 7 and g2.opts["lr"] == 1e-3 and g2.opts["t_total"] == 50
+
+
+def test_bertadam_groups_sharing_one_bucket_keep_their_learning_rates():
+    """Two parameter groups (the trainers' encoder / down-task split, src/vqa/vqacpv2.py:113-128) in ONE FlatGrads:
+    one internal group with a per-parameter base lr, update ranges split where the lr changes and restricted to the
+    parameters that received a gradient."""
+    import torch
+    from xggm_b200.ddp import FlatGrads
+    from xggm_b200.optim import BertAdam
+    enc = [torch.nn.Parameter(torch.randn(40, 8)), torch.nn.Parameter(torch.randn(8))]
+    down = [torch.nn.Parameter(torch.randn(16, 8)), torch.nn.Parameter(torch.randn(3)), torch.nn.Parameter(torch.randn(5))]
+    fg = FlatGrads(enc + down)
+    opt = BertAdam([{"params": enc, "lr": 1e-3}, {"params": down, "lr": 4e-3}], lr=1e-3, warmup=0.1, t_total=10, flat_grads=fg)
+    assert len(opt.groups) == 1 and [g["lr"] for g in opt.param_groups] == [1e-3, 4e-3]
+    assert [len(g["params"]) for g in opt.param_groups] == [2, 3]
+    g = opt.groups[0]
+    r = g.active_ranges()                      # nothing reported: everything active, split at the lr boundary
+    assert len(r) == 2 and r[0][0] == 0 and r[0][1] == r[1][0] == fg.offsets[2] and r[1][1] == fg.flat.numel()
+    assert (r[0][2], r[1][2]) == (1e-3, 4e-3)
+    fg.zero_()
+    (enc[0].sum() + down[1].sum() + down[2].sum()).backward()     # enc[1] and down[0] take no part
+    r = g.active_ranges()
+    assert [(a, b) for a, b, _ in r] == [(fg.offsets[0], fg.offsets[1]), (fg.offsets[3], fg.flat.numel())]
+    assert [lr for _, _, lr in r] == [1e-3, 4e-3]
+    g.step_dev.fill_(3)
+    lrs = opt.get_lr()
+    assert len(lrs) == 5 and abs(lrs[2] - 4 * lrs[0]) < 1e-12
+    with pytest.raises(ValueError, match="lr only"):
+        BertAdam([{"params": enc}, {"params": down, "weight_decay": 0.5}], lr=1e-3, flat_grads=FlatGrads(enc + down))

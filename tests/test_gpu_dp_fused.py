@@ -27,7 +27,11 @@ def _worker(rank, world, port, out):
             torch.manual_seed(7)                                  # same initial weights on both ranks and in both modes
             mod = X.XGGMHeads(128, "GCN", 2).to(dev).train()
             fg = FlatGrads(mod.parameters(), symmetric=(mode != "nccl"))
-            opt = X.BertAdam(mod.parameters(), lr=1e-2, warmup=0.1, t_total=20, flat_grads=fg)
+            # two learning-rate groups sharing the bucket (generator at lr, heads at 4 lr): per-range lr in both paths
+            gen = list(mod.generator.parameters())
+            rest = [q for n_, q in mod.named_parameters() if not n_.startswith("generator.")]
+            opt = X.BertAdam([{"params": gen, "lr": 1e-2}, {"params": rest, "lr": 4e-2}], lr=1e-2, warmup=0.1, t_total=20,
+                             flat_grads=fg)
             if mode != "nccl":
                 assert opt.fused_allreduce_available(), "symmetric memory not available"
             g = torch.Generator(device="cpu").manual_seed(100 + rank)   # different data per rank
@@ -93,7 +97,7 @@ def test_fused_dp_step_matches_nccl_path(tmp_path):
     # differ in the last bits from run to run, and the Adam direction m / (sqrt(v) + e) is sign-like where |g| is
     # tiny: compare against the step size lr * 3.2 (|update| <= lr * 0.1 / sqrt(0.001) in the first steps), as
     # test_training_iteration_node_branch_matches_oracle_pipeline does.
-    step_size = 1e-2 * 3.2
+    step_size = 4e-2 * 3.2
     assert float((ref - fused).abs().max()) <= 2e-3 * step_size, float((ref - fused).abs().max())
     assert float((ref - graph).abs().max()) <= 2e-3 * step_size, float((ref - graph).abs().max())
     assert float((ref - fused).norm()) <= 1e-4 * float((ref).norm())

@@ -70,10 +70,15 @@ class XGGMIteration:
         self.answer = X.AnswerHead(HID, num_answers).to(dev).train()
         base = list(self.lxmert.parameters())
         down = list(self.answer.parameters()) + list(self.heads.parameters())
-        self.fg_base, self.fg_down = FlatGrads(base), FlatGrads(down)
-        # two learning-rate groups, t_total counts both optimiser steps of an iteration (vqacpv2.py:113-128)
+        # ONE bucket for both learning-rate groups (encoder lr, down-task 4 lr; vqacpv2.py:113-128; t_total counts both
+        # optimiser steps of an iteration): at N > 1 it lives in symmetric memory and the all-reduce + joint clip +
+        # BertAdam + parameter all-gather run as the fused peer-memory step (XGGM_DP_FUSED=0: NCCL all-reduce instead)
+        want_fused = self.world > 1 and os.environ.get("XGGM_DP_FUSED", "1") != "0"
+        self.fg = FlatGrads(base + down, symmetric=want_fused)
+        self.fg_base = self.fg_down = self.fg          # (names kept for callers that size the buckets)
         self.optim = X.BertAdam([{"params": base, "lr": lr}, {"params": down, "lr": 4 * lr}], lr=lr, warmup=0.1,
-                                t_total=t_total, flat_grads=[self.fg_base, self.fg_down])
+                                t_total=t_total, flat_grads=self.fg)
+        self.fused_dp = want_fused and self.optim.fused_allreduce_available()
         self.branch = BranchSchedule(delta)
         self.overlap = overlap and self.world > 1
         self.side = torch.cuda.Stream(device=dev)
@@ -113,10 +118,12 @@ class XGGMIteration:
 
     def _reduce_and_step(self):
         X = self.X
+        if self.fused_dp:
+            self.optim.step_allreduce(5.0)
+            return
         if self.world > 1:
-            self.fg_down.all_reduce(average=True)
-            self.fg_base.all_reduce(average=True)
-        self.optim.step(X.clip_grad_norm_([self.fg_base, self.fg_down], 5.0))
+            self.fg.all_reduce(average=True)
+        self.optim.step(X.clip_grad_norm_(self.fg, 5.0))
 
     def step_a(self, feats, boxes, ids, mask, target):
         X = self.X

@@ -84,7 +84,7 @@ SIGNATURES = {
     "xggm_visn_tail_supported": [_i, _i],
     "xggm_visn_tail_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp],
     "xggm_visn_tail_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
-    "xggm_dp_bertadam_step": [_vp, _vp, _vp, _ll, _vp, _vp, _i, _d, _d, _d, _d, _d, _d, _vp, _vp, _vp],
+    "xggm_dp_bertadam_step": [_vp, _vp, _vp, _ll, _vp, _vp, _vp, _i, _d, _d, _d, _d, _d, _d, _vp, _vp, _vp],
     "xggm_sigmoid_fwd": [_vp, _vp, _ll, _vp],
     "xggm_sigmoid_bwd": [_vp, _vp, _vp, _ll, _vp],
     "xggm_keep_mask": [_vp, _ll, _f, _u64, _u64, _vp, _vp],

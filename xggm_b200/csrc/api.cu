@@ -1056,11 +1056,11 @@ int xggm_visn_tail_bwd(const float* gout, const float* xhat1, const float* rstd1
                          gbeta2, M, H, as_stream(s));
 }
 int xggm_dp_bertadam_step(const xggm_dp_peers_t* peers, float* m, float* v, long long n, const long long* range_lo,
-                          const long long* range_hi, int n_ranges, double lr, double b1, double b2, double eps,
+                          const long long* range_hi, const double* range_lr, int n_ranges, double lr, double b1, double b2, double eps,
                           double weight_decay, double max_norm, const xggm_lr_schedule_t* sched, float* sumsq_out,
                           xggm_stream_t s) {
     XGGM_REQUIRE(b1 >= 0.0 && b1 < 1.0 && b2 >= 0.0 && b2 < 1.0 && eps >= 0.0);
-    return dp_bertadam_step(peers, m, v, n, range_lo, range_hi, n_ranges, lr, b1, b2, eps, weight_decay, max_norm, sched,
+    return dp_bertadam_step(peers, m, v, n, range_lo, range_hi, range_lr, n_ranges, lr, b1, b2, eps, weight_decay, max_norm, sched,
                             sumsq_out, as_stream(s));
 }
 int xggm_sigmoid_fwd(const float* x, float* y, long long n, xggm_stream_t s) {

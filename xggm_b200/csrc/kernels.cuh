@@ -102,7 +102,7 @@ int grad_sumsq(const float* g, long long n, float* out, int accumulate, cudaStre
 int bertadam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double b1, double b2, double eps,
                   double wd, const float* sumsq, double max_norm, const xggm_lr_schedule_t* sched, cudaStream_t st);
 int dp_bertadam_step(const xggm_dp_peers_t* peers, float* m, float* v, long long n, const long long* range_lo,
-                     const long long* range_hi, int n_ranges, double lr, double b1, double b2, double eps, double wd,
+                     const long long* range_hi, const double* range_lr, int n_ranges, double lr, double b1, double b2, double eps, double wd,
                      double max_norm, const xggm_lr_schedule_t* sched, float* sumsq_out, cudaStream_t st);
 bool visn_tail_supported(int H, int pos_dim);
 int visn_tail_fwd(const float* z, const float* boxes, const float* Wb, const float* bb, const float* g1, const float* b1,

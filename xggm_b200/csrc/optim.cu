@@ -229,6 +229,7 @@ struct DpPeers {
 struct DpRanges {
     int count;
     long long lo[XGGM_DP_MAX_RANGES], hi[XGGM_DP_MAX_RANGES];
+    float lr[XGGM_DP_MAX_RANGES];     // base learning rate of each range (parameter groups sharing one bucket)
 };
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -336,16 +337,17 @@ dp_adam_kernel(const DpPeers pe, long long slice_lo, long long slice_hi, const D
         const float c = a.max_norm / (sqrtf(total) + 1e-6f);
         clip = c < 1.f ? c : 1.f;
     }
-    float lr = a.lr;
+    double sched = 1.0;
     if (a.step_dev && a.t_total > 0) {
         const long long step = *reinterpret_cast<volatile long long*>(a.step_dev);
-        lr = (float)((double)a.lr * schedule_factor(a.schedule, (double)step / (double)a.t_total, a.warmup));
+        sched = schedule_factor(a.schedule, (double)step / (double)a.t_total, a.warmup);
     }
     float* p_mine = pe.param[pe.rank];
     const float* g_mine = pe.grad[pe.rank];
     for (int r = 0; r < rg.count; ++r) {                  // the active ranges of the bucket, clipped to my slice
         const long long lo = rg.lo[r] > slice_lo ? rg.lo[r] : slice_lo, hi = rg.hi[r] < slice_hi ? rg.hi[r] : slice_hi;
         if (hi <= lo) continue;
+        const float lr = (float)((double)rg.lr[r] * sched);
         const long long n4 = (hi - lo) >> 2;              // range bounds are multiples of 32 floats (FlatGrads alignment)
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
             const long long e = lo + 4 * i;
@@ -388,7 +390,7 @@ __global__ void __launch_bounds__(32) dp_end_kernel(const DpPeers pe) {
 }
 
 int dp_bertadam_step(const xggm_dp_peers_t* peers, float* m, float* v, long long n, const long long* range_lo,
-                     const long long* range_hi, int n_ranges, double lr, double b1, double b2, double eps, double wd,
+                     const long long* range_hi, const double* range_lr, int n_ranges, double lr, double b1, double b2, double eps, double wd,
                      double max_norm, const xggm_lr_schedule_t* sched, float* sumsq_out, cudaStream_t st) {
     XGGM_REQUIRE(peers && m && v && n > 0 && peers->world >= 1 && peers->world <= DP_MAX_RANKS && peers->rank >= 0 &&
                  peers->rank < peers->world && n_ranges >= 0 && n_ranges <= XGGM_DP_MAX_RANGES && (n_ranges == 0 || (range_lo && range_hi)));
@@ -410,6 +412,7 @@ int dp_bertadam_step(const xggm_dp_peers_t* peers, float* m, float* v, long long
     for (int r = 0; r < n_ranges; ++r) {
         XGGM_REQUIRE(range_lo[r] % 4 == 0 && range_hi[r] % 4 == 0 && range_lo[r] >= 0 && range_hi[r] <= n);
         rg.lo[r] = range_lo[r]; rg.hi[r] = range_hi[r];
+        rg.lr[r] = (float)(range_lr ? range_lr[r] : lr);
     }
     // equal slices, 4-float granularity (the bucket length is a multiple of 32)
     const long long per = ((n + pe.world - 1) / pe.world + 3) & ~3LL;

@@ -41,8 +41,9 @@ _SCHED_ID = {"warmup_cosine": 0, "warmup_constant": 1, "warmup_linear": 2}   # X
 
 
 class _Group:
-    def __init__(self, params, opts, flat_grads):
+    def __init__(self, params, opts, flat_grads, lr_of=None):
         self.opts = opts
+        self.lr_of = lr_of or {}      # id(parameter) -> base lr (several user groups sharing ONE bucket); else opts["lr"]
         self.grads = flat_grads if flat_grads is not None else FlatGrads(params)
         self.params = self.grads.params
         g = self.grads.flat
@@ -70,6 +71,22 @@ class _Group:
         # so a CUDA-graph replay keeps following the schedule); `_ticket` is the kernel's hand-shake word
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=g.device)
         self._ticket = torch.zeros(1, dtype=torch.int32, device=g.device)
+
+    def active_ranges(self):
+        """(lo, hi, base_lr) element ranges of the bucket to update: parameters that received a gradient since the last
+        zero_grad() (all of them if nothing was reported), contiguous ones merged while their base lr agrees."""
+        fg = self.grads
+        touched, out = fg._touched, []
+        for i, (p, o) in enumerate(zip(fg.params, fg.offsets)):
+            if touched and id(p) not in touched:
+                continue
+            hi = fg.offsets[i + 1] if i + 1 < len(fg.params) else fg.flat.numel()
+            lr = self.lr_of.get(id(p), self.opts["lr"])
+            if out and out[-1][1] == o and out[-1][2] == lr:
+                out[-1] = (out[-1][0], hi, lr)
+            else:
+                out.append((o, hi, lr))
+        return out
 
     @property
     def step(self):
@@ -119,6 +136,27 @@ class BertAdam:
         if len(flat_grads) != len(groups):
             raise ValueError("need one FlatGrads per parameter group")
         self.groups = []
+        self._user_groups = None
+        shared = flat_grads[0] if (len(groups) > 1 and flat_grads[0] is not None and
+                                   all(f is flat_grads[0] for f in flat_grads)) else None
+        if shared is not None:
+            # several parameter groups living in ONE bucket (the trainers' encoder / down-task groups, which differ in
+            # lr only): one internal group with a per-parameter base lr, so that one fused data-parallel step -- one
+            # joint gradient norm -- covers all of them (step_allreduce)
+            lr_of, user = {}, []
+            for grp in groups:
+                extra = {k: v for k, v in grp.items() if k not in ("params", "lr")}
+                if any(defaults.get(k) != v for k, v in extra.items()):
+                    raise ValueError("parameter groups that share one FlatGrads may differ in lr only")
+                plist = [p for p in grp["params"] if p.requires_grad]
+                for p in plist:
+                    lr_of[id(p)] = grp.get("lr", lr)
+                user.append((dict(defaults, lr=grp.get("lr", lr)), plist))
+            if {id(p) for p in shared.params} != set(lr_of):
+                raise ValueError("flat_grads does not cover exactly the groups' parameters")
+            self.groups.append(_Group(shared.params, dict(defaults), shared, lr_of))
+            self._user_groups = user
+            return
         for grp, fg in zip(groups, flat_grads):
             opts = dict(defaults)
             opts.update({k: v for k, v in grp.items() if k != "params"})
@@ -129,6 +167,8 @@ class BertAdam:
 
     @property
     def param_groups(self):
+        if self._user_groups is not None:
+            return [dict(o, params=pl) for o, pl in self._user_groups]
         return [dict(g.opts, params=g.params) for g in self.groups]
 
     def get_lr(self):
@@ -137,7 +177,12 @@ class BertAdam:
         steps = [g.step for g in self.groups]
         if all(s == 0 for s in steps):
             return [0]
-        return [g.lr_scheduled(s) for g, s in zip(self.groups, steps) for _ in g.params]
+        out = []
+        for g, s_ in zip(self.groups, steps):
+            base = g.opts["lr"]
+            for p in g.params:
+                out.append(g.lr_scheduled(s_) * (g.lr_of.get(id(p), base) / base if base else 1.0))
+        return out
 
     def zero_grad(self):
         """Zero the gradient buckets (keeps every ``p.grad`` linked; see ``FlatGrads.zero_``)."""
@@ -158,12 +203,12 @@ class BertAdam:
             o = g.opts
             _lib.check_device(g.flat_p)
             g.grads.relink()
-            ranges = g.grads.active_ranges()
-            for i, (lo, hi) in enumerate(ranges):
+            ranges = g.active_ranges()
+            for i, (lo, hi, lr_r) in enumerate(ranges):
                 sched = _lib.LrSchedule(g.step_dev.data_ptr(), g._ticket.data_ptr(), float(o["warmup"]),
                                         int(o["t_total"]), _SCHED_ID[o["schedule"]], int(i == len(ranges) - 1))
                 call("xggm_bertadam_step_ex", ptr(g.flat_p[lo:hi]), ptr(g.grads.flat[lo:hi]), ptr(g.m[lo:hi]),
-                     ptr(g.v[lo:hi]), hi - lo, float(o["lr"]), float(o["b1"]), float(o["b2"]), float(o["e"]),
+                     ptr(g.v[lo:hi]), hi - lo, float(lr_r), float(o["b1"]), float(o["b2"]), float(o["e"]),
                      float(o["weight_decay"]), ptr(sumsq), float(max_norm), C.cast(C.pointer(sched), C.c_void_p))
             if g.flat_p.is_cuda:
                 from . import functional as XF
@@ -187,9 +232,10 @@ class BertAdam:
         o = g.opts
         _lib.check_device(g.flat_p)
         g.grads.relink()
-        ranges = g.grads.active_ranges()
+        ranges = g.active_ranges()
         if len(ranges) > _lib.DP_MAX_RANGES:
-            ranges = [(ranges[0][0], ranges[-1][1])]
+            raise RuntimeError(f"xggm_b200.BertAdam.step_allreduce: {len(ranges)} active ranges (max {_lib.DP_MAX_RANGES}); "
+                               "lay parameters with a common lr out contiguously")
         peers = _lib.DpPeers()
         peers.rank, peers.world = dist.get_rank(), dist.get_world_size()
         for k in range(peers.world):
@@ -199,11 +245,12 @@ class BertAdam:
         peers.param_multicast = pmc if (gmc and pmc) else None
         lo = (C.c_longlong * len(ranges))(*[r[0] for r in ranges])
         hi = (C.c_longlong * len(ranges))(*[r[1] for r in ranges])
+        lrs = (C.c_double * len(ranges))(*[float(r[2]) for r in ranges])
         sched = _lib.LrSchedule(g.step_dev.data_ptr(), g._ticket.data_ptr(), float(o["warmup"]), int(o["t_total"]),
                                 _SCHED_ID[o["schedule"]], 1)
         if sumsq_out is None:
             sumsq_out = torch.empty(1, device=g.flat_p.device, dtype=torch.float32)
-        call("xggm_dp_bertadam_step", C.cast(C.pointer(peers), C.c_void_p), ptr(g.m), ptr(g.v), g.flat_p.numel(), lo, hi,
+        call("xggm_dp_bertadam_step", C.cast(C.pointer(peers), C.c_void_p), ptr(g.m), ptr(g.v), g.flat_p.numel(), lo, hi, lrs,
              len(ranges), float(o["lr"]), float(o["b1"]), float(o["b2"]), float(o["e"]), float(o["weight_decay"]),
              float(max_norm), C.cast(C.pointer(sched), C.c_void_p), ptr(sumsq_out))
         from . import functional as XF
