@@ -62,17 +62,33 @@ def load_peaks():
 
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """SM clock and throttle reasons sampled while the timed region runs: one streaming `nvidia-smi -lms 25`
-    process (a query per sample would take longer than the region itself), lines stamped as they arrive and
-    kept if they fall between __enter__ and __exit__."""
+    """SM clock and throttle reasons sampled WHILE the timed region runs.  Primary: an in-process NVML thread
+    (nvidia_ml_py) polling every 2 ms -- the timed region of the default run is ~80 ms, a `nvidia-smi -lms` stream
+    only gets a handful of lines out in that time (`clocks.samples: 1`).  Fallback: one streaming
+    `nvidia-smi -lms 25` process.  Only rank 0 samples (eight pollers on one host cost 1.3 ms/step in round 1)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
+        self.nvml, self.stop, self.src = None, False, None
         self.t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
+        if self.nvml is not None:
+            nv, h = self.nvml
+            names = [("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap)]
+            try:
+                mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+                while not self.stop:
+                    sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    self.rows.append((time.time(), [str(sm), str(mx)] + ["Active" if mask & bit else "Not Active" for _, bit in names]))
+                    time.sleep(0.002)
+            except Exception:
+                pass
+            return
         try:
             for line in self.proc.stdout:
                 self.rows.append((time.time(), [c.strip() for c in line.strip().split(",")]))
@@ -80,11 +96,23 @@ class ClockSampler:
             pass
 
     def start(self):
-        """Spawn the sampler (call a little before the region so that the first samples are not lost)."""
+        """Start sampling (call a little before the region so that the first samples are not lost)."""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.index
+            self.nvml = (nv, nv.nvmlDeviceGetHandleByIndex(phys))
+            self.src = "nvml thread, 2 ms period"
+            self.t.start()
+            return self
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.src = "nvidia-smi -lms 25"
             self.t.start()
         except Exception:
             self.proc = None
@@ -97,12 +125,14 @@ class ClockSampler:
     def __exit__(self, *a):
         self.t1 = time.time()
         time.sleep(0.05)   # let the line of the last in-region sample arrive
+        self.stop = True
         if self.proc is not None:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=5)
             except Exception:
                 self.proc.kill()
+        if self.t.is_alive():
             self.t.join(timeout=6)
 
     def summary(self):
@@ -113,7 +143,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": self.src}
 
 
 # ------------------------------------------------------------------------------- CPU / eager baselines
