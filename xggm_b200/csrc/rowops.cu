@@ -93,17 +93,17 @@ __device__ __forceinline__ void flush_columns(const float (&acc)[NV * 4], float*
 // complete_tx) of the NEXT row of up to NT input tensors into this warp's shared-memory stage while
 // the warp computes on the current one, so a warp never sits on a DRAM round trip between rows.
 // E1: bytes per element of tensor 1 (4, or 2 when that tensor is a bf16 storage row; its stage slot keeps H floats).
-template <int NV, int NT, int E1 = 4, int W = ROW_WARPS>
+template <int NV, int NT, int E1 = 4>
 struct RowPrefetch {
     static constexpr int H = NV * 128;
     static constexpr int STAGE = NT * H;                          // floats per stage
     static constexpr int WARP_FLOATS = 2 * STAGE;
-    static constexpr size_t SMEM = sizeof(float) * W * WARP_FLOATS + sizeof(uint64_t) * W * 2;
+    static constexpr size_t SMEM = sizeof(float) * ROW_WARPS * WARP_FLOATS + sizeof(uint64_t) * ROW_WARPS * 2;
     float* buf;
     uint64_t* bar;
     __device__ __forceinline__ void init(float* sm, int warp, int lane) {
         buf = sm + (size_t)warp * WARP_FLOATS;
-        bar = reinterpret_cast<uint64_t*>(sm + (size_t)W * WARP_FLOATS) + warp * 2;
+        bar = reinterpret_cast<uint64_t*>(sm + (size_t)ROW_WARPS * WARP_FLOATS) + warp * 2;
         if (lane == 0) {
             ptx::mbar_init(&bar[0], 1);
             ptx::mbar_init(&bar[1], 1);
@@ -444,104 +444,6 @@ gld_bwd_fast(const float* __restrict__ gout, const float* __restrict__ z, const 
     if (gbias) flush_columns<NV>(az, gbias, sm);
 }
 
-// gld_bwd with the three column accumulators (gamma / beta / bias gradients) in SHARED memory instead of 72 registers
-// per lane: 242 -> ~170 registers, 12 warps per SM instead of 8 (the kernel is latency-bound: more rows in flight).
-// Accumulator layout [j][32 i + lane] (column = 128 i + 4 lane + j) makes every warp-wide red.shared conflict-free.
-constexpr int GLD2_WARPS = 12;
-template <int NV, bool ZB>
-__global__ void __launch_bounds__(GLD2_WARPS * 32, 1)
-gld_bwd_fast2(const float* __restrict__ gout, const float* __restrict__ z, const float* __restrict__ mean,
-              const float* __restrict__ rstd, const float* __restrict__ gamma, const DropSpec drop,
-              float* __restrict__ gz, float* __restrict__ ggamma, float* __restrict__ gbeta,
-              float* __restrict__ gbias, bf16* __restrict__ hi, bf16* __restrict__ lo, int M) {
-    pdl_prologue();
-    constexpr int H = NV * 128;
-    using PF = RowPrefetch<NV, 2, ZB ? 2 : 4, GLD2_WARPS>;
-    extern __shared__ __align__(16) float sm[];
-    float* accs = sm + (PF::SMEM + 3) / 4;          // [3][H]: gamma, beta, bias sums
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) accs[i] = 0.f;
-    const uint64_t dstream = drop_stream(drop);
-    const float scale = drop.scale;
-    const int wid = blockIdx.x * GLD2_WARPS + warp, nw = gridDim.x * GLD2_WARPS;
-    PF pf;
-    constexpr int ZS = ZB ? 2 : 1;
-    pf.init(sm, warp, lane);
-    __syncthreads();
-    if (wid < M) {
-        const float* src[2] = {gout + (size_t)wid * H, z + (size_t)wid * H / ZS};
-        pf.issue(0, src, lane);
-    }
-    float gam[NV * 4];
-    load_row<NV>(gamma, lane, gam);
-    int it = 0;
-    for (int r = wid; r < M; r += nw, ++it) {
-        const int stage = it & 1;
-        const size_t ro = (size_t)r * H;
-        if (r + nw < M) {
-            const float* src[2] = {gout + (size_t)(r + nw) * H, z + (size_t)(r + nw) * H / ZS};
-            pf.issue(stage ^ 1, src, lane);
-        }
-        const float mu = mean[r], rs = rstd[r];
-        pf.wait(stage, (it >> 1) & 1);
-        float gy[NV * 4], zv[NV * 4], yh[NV * 4];
-        pf.read(stage, 0, lane, gy);
-        pf.read(stage, 1, lane, zv);
-        __syncwarp();
-        if (drop.mode == 2 && drop.thresh == XGGM_COIN_THRESH) {
-            uint32_t nib[NV];
-            coin_row<NV>(drop, dstream, ro, lane, nib);
-#pragma unroll
-            for (int i = 0; i < NV; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) gy[4 * i + j] = ((nib[i] >> j) & 1u) ? gy[4 * i + j] * scale : 0.f;
-        } else if (drop.mode) {
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                bool m[4];
-                drop_bits4(drop, dstream, ro + 128 * i + 4 * lane, m);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) gy[4 * i + j] = m[j] ? gy[4 * i + j] * scale : 0.f;
-            }
-        }
-        float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-        for (int i = 0; i < NV; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int e = 4 * i + j, slot = j * (H / 4) + 32 * i + lane;
-                float cdf, pdf;
-                normal_cdf_pdf(zv[e], cdf, pdf);
-                yh[e] = (zv[e] * cdf - mu) * rs;
-                zv[e] = cdf + zv[e] * pdf;  // gelu'(z)
-                atomicAdd(accs + slot, gy[e] * yh[e]);
-                atomicAdd(accs + H + slot, gy[e]);
-                gy[e] *= gam[e];            // d = gy * gamma
-                s1 += gy[e];
-                s2 = fmaf(gy[e], yh[e], s2);
-            }
-        const float c1 = warp_sum(s1) / (float)H, c2 = warp_sum(s2) / (float)H;
-#pragma unroll
-        for (int i = 0; i < NV; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int e = 4 * i + j;
-                gy[e] = rs * (gy[e] - c1 - yh[e] * c2) * zv[e];
-                if (gbias) atomicAdd(accs + 2 * H + j * (H / 4) + 32 * i + lane, gy[e]);
-            }
-        if (gz) store_row<NV>(gz + ro, lane, gy);
-        if (hi) store_planes<NV>(hi, lo, ro, lane, gy);
-    }
-    __syncthreads();
-    for (int s_ = threadIdx.x; s_ < H; s_ += blockDim.x) {
-        const int j = s_ / (H / 4), rem = s_ - j * (H / 4), i = rem >> 5, l = rem & 31;
-        const int c = 128 * i + 4 * l + j;
-        atomicAdd(&ggamma[c], accs[s_]);
-        atomicAdd(&gbeta[c], accs[H + s_]);
-        if (gbias) atomicAdd(&gbias[c], accs[2 * H + s_]);
-    }
-}
-
 // ================================================================== generic kernels (any H)
 constexpr int GEN_WARPS = 4;
 constexpr int GEN_ROWS = 8;
@@ -848,29 +750,6 @@ int gelu_ln_drop_bwd(const float* gout, const float* z, const float* mean, const
                      const DropSpec& drop, float* gz, float* ggamma, float* gbeta, float* gbias,
                      bf16* hi, bf16* lo, int M, int H, cudaStream_t st, int z_bf16) {
     if (M <= 0) return XGGM_OK;
-    static int v2 = -1;
-    if (v2 < 0) {
-        const char* e = getenv("XGGM_GLD_BWD_V2");
-        v2 = (e && e[0] == '0') ? 0 : 1;
-    }
-    if (v2 && H <= 768 && fast_ok(H, gout, z, gz) && fast_ok(H, gamma, hi, lo) && (reinterpret_cast<uintptr_t>(drop.keep) & 3) == 0) {
-        XGGM_ROW_DISPATCH(H, {
-            using PF = RowPrefetch<NV, 2, 4, GLD2_WARPS>;
-            constexpr size_t smem = ((PF::SMEM + 3) / 4) * 4 + sizeof(float) * 3 * NV * 128;
-            const int grid = max(1, min(ceil_div(M, GLD2_WARPS), row_sms()));
-            if (z_bf16) {
-                static bool attr = false;
-                if (!attr) { XGGM_CUDA_TRY(cudaFuncSetAttribute(gld_bwd_fast2<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-                XGGM_LAUNCH((gld_bwd_fast2<NV, true>), grid, GLD2_WARPS * 32, smem, st, gout, z, mean, rstd, gamma, drop, gz, ggamma, gbeta, gbias, hi, lo, M);
-            } else {
-                static bool attr = false;
-                if (!attr) { XGGM_CUDA_TRY(cudaFuncSetAttribute(gld_bwd_fast2<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-                XGGM_LAUNCH((gld_bwd_fast2<NV, false>), grid, GLD2_WARPS * 32, smem, st, gout, z, mean, rstd, gamma, drop, gz, ggamma, gbeta, gbias, hi, lo, M);
-            }
-        });
-        XGGM_LAUNCH_CHECK();
-        return XGGM_OK;
-    }
     if (fast_ok(H, gout, z, gz) && fast_ok(H, gamma, hi, lo) && (reinterpret_cast<uintptr_t>(drop.keep) & 3) == 0) {
         XGGM_ROW_DISPATCH(H, {
             constexpr size_t smem = RowPrefetch<NV, 2>::SMEM;   // (>= the ROW_WARPS*H floats flush_columns needs)
