@@ -203,7 +203,7 @@ int xggm_adj_regen_bwd_ex(const float* gadj, const float* x, const float* S, con
  * The subsequence gains (*dev_epoch << 32) when dev_epoch, a DEVICE counter, is given -- lets a captured CUDA graph
  * draw fresh masks on every replay).  Forward and backward must receive the same triple.
  * xggm_keep_mask(seed, stream0 + j, dev_epoch) materialises exactly the mask head j uses. */
-typedef struct {
+typedef struct xggm_philox_s {
     uint64_t seed;
     uint64_t stream0;
     const uint64_t* dev_epoch;
@@ -274,6 +274,12 @@ int xggm_feat_noise(const float* f, const float* randn, double sigma, float* noi
 /* same, also emitting the planes of `noisy` (noisy_planes?) for the first GNN layer */
 int xggm_feat_noise_ex(const float* f, const float* randn, double sigma, float* noisy, float* target,
                        void* noisy_planes, int B, int N, int H, int f_is_broadcast, xggm_stream_t s);
+/* same with the Gaussian draw INSIDE the kernel (no randn tensor): Philox4x32-10, key = rng->seed, counter = float4 index,
+ * subsequence = rng->stream0 + (*rng->dev_epoch << 32 if non-NULL), two Box-Muller pairs per counter.  H % 4 == 0.
+ * (xggm_philox_t is declared with the GCN / GIN layers below.) */
+struct xggm_philox_s;
+int xggm_feat_noise_philox(const float* f, const struct xggm_philox_s* rng, double sigma, float* noisy, float* target,
+                           void* noisy_planes, int B, int N, int H, int f_is_broadcast, xggm_stream_t s);
 /* out[B,H] = sum_n g[B,n,H]  (backward of the broadcast above) */
 int xggm_sum_nodes(const float* g, float* out, int B, int N, int H, xggm_stream_t s);
 /* loss_func                                               src/vqa/vqacpv2.py:48-51

@@ -1160,3 +1160,41 @@ torch.save({'xo': xo.detach().cpu(), 'ao': ao.detach().cpu(), 'gx': x.grad.cpu()
             outs[flag] = torch.load(path)
     for k in outs["0"]:
         _close(outs["1"][k], outs["0"][k], 2e-5 if k in ("xo", "ao") else 1e-4, k)
+
+
+def test_in_kernel_gaussian_feature_noise():
+    """add_feature_noise without a randn tensor (xggm_feat_noise_philox: Philox4x32-10 + Box-Muller inside the kernel):
+    standard-normal statistics, target = -noise / sigma^2 exactly, determinism under torch.manual_seed, fresh draws per
+    call, the broadcast ([B,H] -> [B,N,H]) form, and operand planes equal to a split of the noisy tensor."""
+    import xggm_b200 as X
+    import xggm_b200.functional as XF
+    B, N, H, sigma = 64, 36, 768, 0.7
+    f = torch.randn(B, H, device=dev())
+    torch.manual_seed(11)
+    XF._drop.site = 0
+    noisy, target = X.add_feature_noise(f, sigma=sigma, n_nodes=N)
+    n = (noisy - f[:, None, :]).double() / sigma
+    assert abs(float(n.mean())) < 3e-3 and abs(float(n.std()) - 1.0) < 3e-3
+    assert abs(float((n ** 3).mean())) < 2e-2 and abs(float((n ** 4).mean()) - 3.0) < 5e-2       # skewness, kurtosis
+    flat = n.reshape(-1)
+    assert abs(float((flat[:-1] * flat[1:]).mean())) < 3e-3                                        # neighbours uncorrelated
+    assert float((flat.abs() > 4.0).double().mean()) < 3e-4 and float(flat.abs().max()) < 7.0      # tails
+    # target = -noise / sigma^2 with the noise that was actually added (float rounding of the subtraction only)
+    assert float((target.double() * sigma * sigma + (noisy - f[:, None, :]).double()).abs().max()) < 1e-5
+    # deterministic under the seed + site; a second call draws new numbers
+    noisy_b, _ = X.add_feature_noise(f, sigma=sigma, n_nodes=N)
+    torch.manual_seed(11)
+    XF._drop.site = 0
+    noisy_c, _ = X.add_feature_noise(f, sigma=sigma, n_nodes=N)
+    assert torch.equal(noisy, noisy_c) and not torch.equal(noisy, noisy_b)
+    # gradient of the broadcast form: sum over the N copies
+    fr = f.clone().requires_grad_(True)
+    out, _ = X.add_feature_noise(fr, sigma=sigma, n_nodes=N)
+    c = torch.randn_like(out)
+    (out * c).sum().backward()
+    _close(fr.grad, c.sum(1).cpu(), 1e-6, "broadcast grad")
+    # full [B,N,H] form + planes hand-over
+    full = torch.randn(4, N, H, device=dev())
+    nz, _ = X.add_feature_noise(full, sigma=sigma)
+    assert nz.shape == full.shape and XF._planes_of(nz) is not None
+    assert abs(float(((nz - full) / sigma).std()) - 1.0) < 2e-2

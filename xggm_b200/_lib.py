@@ -51,6 +51,7 @@ SIGNATURES = {
     "xggm_linear_fwd_ex": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "xggm_linear_bwd_input_ex": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "xggm_feat_noise_ex": [_vp, _vp, _d, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "xggm_feat_noise_philox": [_vp, _vp, _d, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "xggm_gnn_saved_floats": [_i, _i, _i, _i, _i],
     "xggm_gnn_work_floats": [_i, _i, _i, _i, _i],
     "xggm_gnn_fwd": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _vp],

@@ -942,6 +942,15 @@ int xggm_feat_noise_ex(const float* f, const float* randn, double sigma, float* 
     return feat_noise(f, randn, (float)sigma, (float)(sigma * sigma), noisy, target, emit ? mut(o.hi) : nullptr,
                       emit ? lo_or_null(o) : nullptr, B, N, H, f_is_broadcast, as_stream(s));
 }
+int xggm_feat_noise_philox(const float* f, const xggm_philox_t* rng, double sigma, float* noisy, float* target,
+                           void* noisy_planes, int B, int N, int H, int f_is_broadcast, xggm_stream_t s) {
+    if (B == 0) return XGGM_OK;
+    XGGM_REQUIRE(f && rng && noisy && target && B >= 0 && N > 0 && H > 0 && H % 4 == 0 && sigma != 0.0);
+    const bool emit = noisy_planes && g_precision != XGGM_PREC_FP32_SIMT;
+    const Operand o = planes_at(noisy, static_cast<float*>(noisy_planes), (long long)B * N * H);
+    return feat_noise_philox(f, rng->seed, rng->stream0, rng->dev_epoch, (float)sigma, (float)(sigma * sigma), noisy, target,
+                             emit ? mut(o.hi) : nullptr, emit ? lo_or_null(o) : nullptr, B, N, H, f_is_broadcast, as_stream(s));
+}
 int xggm_feat_noise(const float* f, const float* randn, double sigma, float* noisy, float* target,
                     int B, int N, int H, int f_is_broadcast, xggm_stream_t s) {
     return xggm_feat_noise_ex(f, randn, sigma, noisy, target, nullptr, B, N, H, f_is_broadcast, s);

@@ -130,7 +130,49 @@ feat_noise_vec_kernel(const float* __restrict__ f, const float* __restrict__ ran
     reinterpret_cast<float4*>(target)[o] = make_float4(-n.x / sigma2, -n.y / sigma2, -n.z / sigma2, -n.w / sigma2);
     if (hi) split_store4(hi, lo, 4 * o, out.x, out.y, out.z, out.w);   // operand planes for the first GNN layer
 }
+// The Gaussian draw INSIDE the kernel (no randn tensor: one launch and 8 B/element less): Philox4x32-10, key = seed,
+// counter = float4 index, subsequence = stream + (*epoch << 32); the four 32-bit words give two Box-Muller pairs.
+__device__ __forceinline__ float4 philox_normal4(const Philox& rng, uint64_t counter, uint64_t stream) {
+    const uint4 r = rng(counter, stream);
+    const float u1 = ((float)r.x + 0.5f) * 2.3283064365386963e-10f, u2 = ((float)r.y + 0.5f) * 2.3283064365386963e-10f;
+    const float u3 = ((float)r.z + 0.5f) * 2.3283064365386963e-10f, u4 = ((float)r.w + 0.5f) * 2.3283064365386963e-10f;
+    const float ra = sqrtf(-2.0f * logf(fmaxf(u1, 1e-37f))), rb = sqrtf(-2.0f * logf(fmaxf(u3, 1e-37f)));
+    float sa, ca, sb, cb;
+    sincospif(2.0f * u2, &sa, &ca);
+    sincospif(2.0f * u4, &sb, &cb);
+    return make_float4(ra * ca, ra * sa, rb * cb, rb * sb);
+}
+__global__ void __launch_bounds__(256)
+feat_noise_philox_kernel(const float* __restrict__ f, uint64_t seed, uint64_t stream, const uint64_t* __restrict__ epoch,
+                         float sigma, float sigma2, float* __restrict__ noisy, float* __restrict__ target,
+                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int NH4, int H, int bcast) {
+    pdl_prologue();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NH4) return;
+    const int b = blockIdx.y;
+    const size_t o = (size_t)b * NH4 + i;
+    const float4 r = philox_normal4(Philox(seed), (uint64_t)o, stream + (epoch ? (*epoch << 32) : 0ull));
+    const float4 fv = bcast ? *reinterpret_cast<const float4*>(f + (size_t)b * H + (4 * i) % H)
+                            : reinterpret_cast<const float4*>(f)[o];
+    const float4 n = make_float4(r.x * sigma, r.y * sigma, r.z * sigma, r.w * sigma);
+    const float4 out = make_float4(fv.x + n.x, fv.y + n.y, fv.z + n.z, fv.w + n.w);
+    reinterpret_cast<float4*>(noisy)[o] = out;
+    reinterpret_cast<float4*>(target)[o] = make_float4(-n.x / sigma2, -n.y / sigma2, -n.z / sigma2, -n.w / sigma2);
+    if (hi) split_store4(hi, lo, 4 * o, out.x, out.y, out.z, out.w);
+}
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+int feat_noise_philox(const float* f, uint64_t seed, uint64_t stream, const uint64_t* epoch, float sigma, float sigma2,
+                      float* noisy, float* target, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int N, int H, int bcast,
+                      cudaStream_t st) {
+    const long long total = (long long)B * N * H;
+    if (total <= 0) return XGGM_OK;
+    XGGM_REQUIRE(H % 4 == 0 && al16(f) && al16(noisy) && al16(target) && (long long)N * H / 4 < (1LL << 30));
+    const int NH4 = N * H / 4;
+    XGGM_LAUNCH((feat_noise_philox_kernel), dim3(ceil_div(NH4, 256), B), 256, 0, st, f, seed, stream, epoch, sigma, sigma2, noisy,
+                target, hi, lo, NH4, H, bcast);
+    XGGM_LAUNCH_CHECK();
+    return XGGM_OK;
+}
 int feat_noise(const float* f, const float* randn, float sigma, float sigma2, float* noisy,
                float* target, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int N, int H, int bcast, cudaStream_t st) {
     const long long total = (long long)B * N * H;

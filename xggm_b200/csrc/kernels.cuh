@@ -84,6 +84,9 @@ int triu_scatter_fwd(const float*, float*, int, int, cudaStream_t);
 int triu_scatter_bwd(const float*, float*, int, int, cudaStream_t);
 int edge_noise(const float*, const float*, float, float, float*, float*, int, int, cudaStream_t);
 int feat_noise(const float*, const float*, float, float, float*, float*, __nv_bfloat16*, __nv_bfloat16*, int, int, int, int, cudaStream_t);
+int feat_noise_philox(const float* f, uint64_t seed, uint64_t stream, const uint64_t* epoch, float sigma, float sigma2,
+                      float* noisy, float* target, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int N, int H, int bcast,
+                      cudaStream_t st);
 int sum_nodes(const float*, float*, int, int, int, cudaStream_t);
 int score_mse_fwd(const float*, const float*, float, float*, long long, cudaStream_t);
 int score_mse_bwd(const float*, const float*, const float*, float, float*, long long, cudaStream_t);

@@ -388,8 +388,24 @@ def adj_regen(x, squash=True, return_argmax=False):
 class _GnnLayer(torch.autograd.Function):
     @staticmethod
     def forward(ctx, kind, n_convs, drop_p, keeps, philox, x_planes, out_planes, x, adj, *params):
-        x, adj = f32(x, "x"), f32(adj, "adj")
+        # adj: the [B,N,N] adjacency, or ("regen", squash): the adjacency is REGENERATED from x inside this node
+        # (ggm.py:225-228 followed by the next layer, ggm.py:221-222) -- x then has one consumer instead of two, so
+        # autograd needs no add kernel for its gradient: the regeneration's backward accumulates into the layer's gx
+        x = f32(x, "x")
         B, N, H = x.shape
+        regen = None
+        if isinstance(adj, tuple):
+            regen = int(bool(adj[1]))
+            adj = torch.empty((B, N, N), device=x.device, dtype=torch.float32)
+            S = torch.empty_like(adj)
+            amax = torch.empty((B, N), device=x.device, dtype=torch.int32)
+            rwork = None
+            if x_planes is None:
+                rwork = torch.empty(max(int(_lib.load().xggm_adj_regen_work_bytes(B, N, H)), 16), device=x.device, dtype=torch.uint8)
+            call("xggm_adj_regen_fwd_ex", ptr(x), ptr(adj), ptr(S), ptr(amax), B, N, H, regen, ptr(rwork), ptr(x_planes))
+            ctx.regen_saved = (S, amax)
+        ctx.regen = regen
+        adj = f32(adj, "adj")
         if adj.shape != (B, N, N):
             raise RuntimeError(f"xggm_b200: adj {tuple(adj.shape)} does not match x {tuple(x.shape)}")
         per_conv = 3 if kind == 0 else 5
@@ -436,7 +452,7 @@ class _GnnLayer(torch.autograd.Function):
         gx = torch.empty_like(x)
         # ctx.needs_input_grad: (kind, n_convs, drop_p, keeps, philox, x_planes, out_planes, x, adj, *params);
         # GIN needs gq h^T for d eps
-        need_gadj = ctx.needs_input_grad[8] or kind != 0
+        need_gadj = ctx.needs_input_grad[8] or kind != 0 or ctx.regen is not None
         gadj = torch.empty_like(adj) if need_gadj else None
         targets = [_grad_target(p) for p in params]
         fused = all(t is not None for t in targets)
@@ -453,6 +469,11 @@ class _GnnLayer(torch.autograd.Function):
              None if wps is None else ptr_table(wps))
         if fused:
             grads = [None] * len(params)
+        if ctx.regen is not None:   # gx += (dS + dS^T) x : the regenerated adjacency's path back to x
+            S, amax = ctx.regen_saved
+            call("xggm_adj_regen_bwd_ex", ptr(gadj), ptr(x), ptr(S), ptr(amax), ptr(gx), ptr(torch.empty_like(S)), B, N, H,
+                 ctx.regen, 1, ptr(_adj_work(B, N, H, x.device)), ptr(ctx.x_planes))
+            return (None, None, None, None, None, None, None, gx, None, *grads)
         return (None, None, None, None, None, None, None, gx, (gadj if ctx.needs_input_grad[8] else None), *grads)
 
 
@@ -471,7 +492,7 @@ def _philox_arg(philox):
     return C.cast(C.pointer(spec), C.c_void_p)
 
 
-def gnn_layer(kind, x, adj, conv_params, head_params, training=False, drop_p=0.5):
+def gnn_layer(kind, x, adj, conv_params, head_params, training=False, drop_p=0.5, regen=None):
     """One GCN (kind='GCN') or GIN (kind='GIN') layer: conv chain + jump-knowledge heads.
     conv_params / head_params are flat lists in the order documented in xggm_b200.h.
     Training-mode dropout of the heads: injected keep-masks if any are queued (parity runs),
@@ -486,6 +507,8 @@ def gnn_layer(kind, x, adj, conv_params, head_params, training=False, drop_p=0.5
         else:
             philox = (torch.initial_seed(), _next_sites(n_convs + 1), _drop.epoch)
     out_planes = _new_planes(x)
+    if regen is not None:      # adjacency regenerated from x inside the node (see _GnnLayer.forward)
+        adj = ("regen", bool(regen))
     out = _GnnLayer.apply(k, n_convs, drop_p, keeps, philox, _planes_of(x), out_planes, x, adj, *conv_params, *head_params)
     _attach_planes(out, out_planes)
     return out
@@ -756,6 +779,42 @@ class _FeatNoise(torch.autograd.Function):
         out = torch.empty((B, H), device=g.device, dtype=torch.float32)
         call("xggm_sum_nodes", ptr(g), ptr(out), B, N, H)
         return out, None, None, None
+
+
+class _FeatNoisePhilox(torch.autograd.Function):
+    """add_feature_noise_v2 with the Gaussian draw inside the kernel (xggm_feat_noise_philox): no randn tensor."""
+
+    @staticmethod
+    def forward(ctx, f, shape, sigma, planes, philox):
+        f = f32(f, "feats")
+        B, N, H = shape
+        bcast = f.dim() == 2
+        noisy = torch.empty(shape, device=f.device, dtype=torch.float32)
+        target = torch.empty_like(noisy)
+        call("xggm_feat_noise_philox", ptr(f), _philox_arg(philox), float(sigma), ptr(noisy), ptr(target), ptr(planes),
+             B, N, H, int(bcast))
+        ctx.bcast = bcast
+        ctx.mark_non_differentiable(target)
+        ctx.set_materialize_grads(False)
+        return noisy, target
+
+    @staticmethod
+    def backward(ctx, g, _gt):
+        if g is None or not ctx.bcast:
+            return g, None, None, None, None
+        g = f32(g)
+        B, N, H = g.shape
+        out = torch.empty((B, H), device=g.device, dtype=torch.float32)
+        call("xggm_sum_nodes", ptr(g), ptr(out), B, N, H)
+        return out, None, None, None, None
+
+
+NOISE_SITE_BASE = 1 << 40     # Philox subsequences of the in-kernel Gaussian draws (kept apart from the dropout sites)
+
+
+def feat_noise_philox(feats, shape, sigma, planes):
+    philox = (torch.initial_seed(), NOISE_SITE_BASE + _next_sites(1), _drop.epoch)
+    return _FeatNoisePhilox.apply(feats, tuple(shape), sigma, planes, philox)
 
 
 class _ScoreMse(torch.autograd.Function):

@@ -5,9 +5,13 @@
   loss_func / compute_kl_loss         = src/vqa/vqacpv2.py:48-61 (= src/gqa/gqa_ood.py:48-61)
   strip_diag / triu_scatter           = src/vqa/vqacpv2.py:188 / :195-199
 
-The Gaussian draw itself stays ``torch.randn_like`` (same generator stream as the
-reference on the same device); everything after it is one fused kernel.
+Feature noise draws its Gaussians INSIDE the kernel (Philox4x32-10 + Box-Muller keyed by ``torch.initial_seed()``, a
+per-call site number and -- under CUDA-graph replay -- the device epoch, like the library's dropout): no ``randn``
+tensor, one launch less.  ``XGGM_TORCH_RANDN=1`` (or passing ``randn=``) draws with ``torch.randn`` instead, which
+reproduces the reference's own generator stream on the same device.  Edge noise ([B,36,36]) keeps ``torch.randn_like``.
 """
+import os
+
 import torch
 
 from . import functional as XF
@@ -34,12 +38,22 @@ def add_feature_noise_v2(feats, sigma=0.2, randn=None, n_nodes=None):
         shape = (feats.shape[0], n_nodes if randn is None else randn.shape[1], feats.shape[1])
     else:
         shape = feats.shape
+    if randn is None and shape[-1] % 4 == 0 and os.environ.get("XGGM_TORCH_RANDN") != "1":
+        planes = XF._new_planes(_shape_probe(shape, feats.device))
+        noisy, target = XF.feat_noise_philox(feats, shape, sigma, planes)
+        XF._attach_planes(noisy, planes)
+        return noisy, target
     if randn is None:
         randn = torch.randn(shape, device=feats.device, dtype=feats.dtype)
     planes = XF._new_planes(randn)
     noisy, target = XF._FeatNoise.apply(feats, randn, sigma, planes)
     XF._attach_planes(noisy, planes)   # operand planes for the first GNN layer that consumes `noisy`
     return noisy, target
+
+
+def _shape_probe(shape, device):
+    """A zero-storage tensor of the given shape / device (``_new_planes`` only looks at shape, numel and device)."""
+    return torch.empty(1, device=device).expand(shape)
 
 
 add_edge_noise = add_edge_noise_v2

@@ -89,6 +89,11 @@ class GCN(nn.Module):
         cp, hp = self._flat_params()
         return XF.gnn_layer("GCN", x, adj, cp, hp, self.training, self.dropout_p)
 
+    def forward_regen(self, x, squash=True):
+        """forward(x, adj_regen(x)) as ONE autograd node (the generators' layer-to-layer step, ggm.py:221-228)."""
+        cp, hp = self._flat_params()
+        return XF.gnn_layer("GCN", x, None, cp, hp, self.training, self.dropout_p, regen=squash)
+
 
 # ---------------------------------------------------------------------------
 # GIN  (reference: src/module/gin.py)
@@ -127,6 +132,10 @@ class GIN(nn.Module):
     def forward(self, X, A):
         cp, hp = self._flat_params()
         return XF.gnn_layer("GIN", X, A, cp, hp, self.training, self.dropout_p)
+
+    def forward_regen(self, X, squash=True):
+        cp, hp = self._flat_params()
+        return XF.gnn_layer("GIN", X, None, cp, hp, self.training, self.dropout_p, regen=squash)
 
 
 # ---------------------------------------------------------------------------
@@ -191,8 +200,16 @@ class _Generator(nn.Module):
         for layer in range(self.n_layers):
             if layer > 0 and layer == self.n_layers - 1:
                 ddp.notify_layer_boundary(x)   # data-parallel runs: gradients of the last layer can ship early
-            x = self.gnn_layers[layer](x, adj)
-            adj = XF.adj_regen(x, self.squash)
+            gnn = self.gnn_layers[layer]
+            if layer > 0 and hasattr(gnn, "forward_regen"):
+                # the adjacency between two layers is only ever read by the next layer: regenerate it inside that
+                # layer's autograd node (x keeps a single consumer; no gradient-accumulation kernel)
+                x = gnn.forward_regen(x, self.squash)
+            else:
+                if layer > 0:
+                    adj = XF.adj_regen(x, self.squash)
+                x = gnn(x, adj)
+        adj = XF.adj_regen(x, self.squash)
         return x, adj
 
 
