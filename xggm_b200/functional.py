@@ -237,8 +237,9 @@ class _AdjApply(torch.autograd.Function):
             raise RuntimeError(f"xggm_b200.adj_apply: adj {tuple(adj.shape)} vs x {tuple(x.shape)}")
         al = None if alpha_dev is None else f32(alpha_dev, "alpha")
         out = torch.empty_like(x)
+        tc_work = _adj_work(B, N, H, x.device)    # (scratch buffers are named locals: they must outlive the call)
         call("xggm_adj_apply_fwd", ptr(adj), ptr(x), ptr(out), B, N, H, float(alpha0), ptr(al), float(self_w),
-             ptr(_adj_work(B, N, H, x.device)))
+             ptr(tc_work))
         ctx.save_for_backward(adj, x, al)
         ctx.cfg = (float(alpha0), float(self_w))
         return out
@@ -251,8 +252,9 @@ class _AdjApply(torch.autograd.Function):
         g = f32(g)
         gx = torch.empty_like(x)
         graw = torch.empty_like(adj)
+        tc_work = _adj_work(B, N, H, x.device)
         call("xggm_adj_apply_bwd", ptr(adj), ptr(x), ptr(g), ptr(gx), ptr(graw), B, N, H, alpha0, ptr(al),
-             self_w, 0, ptr(_adj_work(B, N, H, x.device)))
+             self_w, 0, ptr(tc_work))
         alpha = alpha0 if al is None else alpha0 + al
         gadj = graw * alpha
         gal = None
@@ -370,9 +372,9 @@ class _AdjRegen(torch.autograd.Function):
             return None, None, None
         g = f32(g)
         gx = torch.empty_like(x)
-        work = torch.empty_like(S)
+        work, tc_work = torch.empty_like(S), _adj_work(B, N, H, x.device)
         call("xggm_adj_regen_bwd_ex", ptr(g), ptr(x), ptr(S), ptr(amax), ptr(gx), ptr(work), B, N, H, ctx.squash, 0,
-             ptr(_adj_work(B, N, H, x.device)), ptr(ctx.x_planes))
+             ptr(tc_work), ptr(ctx.x_planes))
         return gx, None, None
 
 
@@ -471,8 +473,9 @@ class _GnnLayer(torch.autograd.Function):
             grads = [None] * len(params)
         if ctx.regen is not None:   # gx += (dS + dS^T) x : the regenerated adjacency's path back to x
             S, amax = ctx.regen_saved
-            call("xggm_adj_regen_bwd_ex", ptr(gadj), ptr(x), ptr(S), ptr(amax), ptr(gx), ptr(torch.empty_like(S)), B, N, H,
-                 ctx.regen, 1, ptr(_adj_work(B, N, H, x.device)), ptr(ctx.x_planes))
+            d_scratch, tc_work = torch.empty_like(S), _adj_work(B, N, H, x.device)   # (named: they must outlive the call)
+            call("xggm_adj_regen_bwd_ex", ptr(gadj), ptr(x), ptr(S), ptr(amax), ptr(gx), ptr(d_scratch), B, N, H,
+                 ctx.regen, 1, ptr(tc_work), ptr(ctx.x_planes))
             return (None, None, None, None, None, None, None, gx, None, *grads)
         return (None, None, None, None, None, None, None, gx, (gadj if ctx.needs_input_grad[8] else None), *grads)
 
