@@ -798,6 +798,77 @@ def run_visn(args):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------- BASELINE configs[4]: evaluation
+def run_eval(args):
+    """predict() / evaluate() of the reference (src/vqa/vqacpv2.py:315-344): LXMERT forward + logit_fc + argmax.  The
+    generator is NOT on this path: the graph block contributes zero work, the line exists so that every
+    BASELINE config has a measurement.  Stock-PyTorch LXMERT (tools/lxmert_torch.py) + the library's VisualFeatEncoder and
+    answer head, no gradients; B questions per GPU (default 1024), data parallel without any collective."""
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import iteration as IT
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch if args.batch != B_PER_GPU else 1024
+    autocast = args.precision == "bf16"
+    torch.backends.cuda.matmul.allow_tf32 = False
+    it = IT.XGGMIteration(dev, B, autocast=autocast)
+    it.lxmert.eval(); it.answer.eval(); it.heads.eval()
+    host = IT.synthetic_batch(9596 + rank, B)
+    res = [t.to(dev) for t in host]
+    pred_host = torch.zeros(B, dtype=torch.long).pin_memory()
+
+    def step(batch):
+        with torch.no_grad():
+            _, pooled = it._encode(batch[0], batch[1], batch[2], batch[3])
+            return it.answer(pooled).max(1)[1]                      # vqacpv2.py:331-332
+
+    def e2e():
+        b = [t.to(dev, non_blocking=True) for t in host[:4]]
+        pred_host.copy_(step(b), non_blocking=True)
+
+    for _ in range(max(args.warmup, 3)):
+        step(res); e2e()
+
+    def timed(fn, n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_.record()
+        for _ in range(n):
+            fn()
+        e_.record()
+        torch.cuda.synchronize()
+        ms = s_.elapsed_time(e_)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms / n
+
+    ms = timed(lambda: step(res), args.steps)
+    ms_e2e = timed(e2e, args.steps)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "xggm_eval_samples_per_sec", "value": B * world / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if autocast else "f32", "data": "synthetic",
+            "config": {"workload": f"cfg5 evaluation: stock-PyTorch LXMERT forward + logit_fc + argmax, B={B}/GPU; the graph "
+                                   "generator is not on the evaluation path (src/vqa/vqacpv2.py:315-344)",
+                       "global_batch": B * world, "parallelism": f"dp{world} (no collective)"},
+            "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host[:4]), "d2h_bytes_per_step": B * 8}}), flush=True)
+    if world > 1:
+        torch.cuda.synchronize()
+        os._exit(0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -814,7 +885,7 @@ def main():
                          "relation generation (taken with probability delta/10; GQA-OOD uses delta 5)")
     ap.add_argument("--nodes", type=int, default=N_NODES, help="nodes per graph (36 = obj36; 64/100 = BASELINE cfg 4 sweep)")
     ap.add_argument("--quick", action="store_true", help="skip the CPU / eager-GPU baselines and the bf16 leg (sweeps)")
-    ap.add_argument("--workload", default="block", choices=["block", "iteration", "visn"],
+    ap.add_argument("--workload", default="block", choices=["block", "iteration", "visn", "eval"],
                     help="block: the graph block's training step (default, the headline); iteration: the full trainer "
                          "iteration with a stock-PyTorch LXMERT around the block (BASELINE configs[1]/[2])")
     ap.add_argument("--delta", type=int, default=0, help="--workload iteration: GGM branch threshold out of 10 (0 = VQA-CP recipe)")
@@ -825,6 +896,9 @@ def main():
         return
     if args.workload == "visn" and args.impl != "reference":
         run_visn(args)
+        return
+    if args.workload == "eval" and args.impl != "reference":
+        run_eval(args)
         return
     if args.impl == "reference":
         run_reference(args)

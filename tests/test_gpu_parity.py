@@ -1198,3 +1198,44 @@ def test_in_kernel_gaussian_feature_noise():
     nz, _ = X.add_feature_noise(full, sigma=sigma)
     assert nz.shape == full.shape and XF._planes_of(nz) is not None
     assert abs(float(((nz - full) / sigma).std()) - 1.0) < 2e-2
+
+
+@pytest.mark.parametrize("gnn,B,N", [("GCN", 64, 64), ("GCN", 40, 100), ("GIN", 48, 64), ("GIN", 24, 100)])
+def test_wider_graphs_multi_tile_vs_fp64_oracle(gnn, B, N):
+    """BASELINE configs[3] node counts at sizes that span many row tiles (N=64: unaligned message-passing tiles, two
+    graphs per Gram tile; N=100: graph-aligned tiles, one graph per tile; M = 4096 / 4000 / 3072 / 2400 rows -> the
+    CTA-pair projections, grouped launches and split-K weight gradients are all active), H=768, train mode with
+    injected masks: generator outputs, input gradients and parameter gradients against the fp64 oracle."""
+    import xggm_b200 as X
+    from xggm_b200.functional import inject_keep_masks
+    H = 768
+    p = O.make_params(61 + N, gnn, H, 2, N, heads=False)
+    cls = {"GCN": X.GCNGenerator, "GIN": X.GINGenerator}[gnn]
+    mod = _load_params(cls(H, 2), p, "generator.").to(dev()).train()
+    visn, _, adj_true = O.make_inputs(62 + N, B, N, H)
+    adj = O.strip_diag(adj_true)
+    nh = {"GCN": 3, "GIN": 2}[gnn]
+    keeps = O.make_keeps(63, 2, nh, (B, N, H))
+    x = visn.clone().to(dev()).requires_grad_(True)
+    a = adj.clone().to(dev()).requires_grad_(True)
+    with inject_keep_masks([m for layer in keeps for m in layer]):
+        xo, ao = mod(x, a)
+    g = torch.Generator().manual_seed(64)
+    cx, ca = torch.randn(B, N, H, generator=g), torch.randn(B, N, N, generator=g)
+    ((xo * cx.to(dev())).sum() + (ao * ca.to(dev())).sum()).backward()
+    p64 = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    x64, a64 = visn.double().requires_grad_(True), adj.double().requires_grad_(True)
+    fn = O.gcn_generator if gnn == "GCN" else O.gin_generator
+    xr, ar = fn(x64, a64, p64, 2, keeps, pre="generator.")
+    ((xr * cx.double()).sum() + (ar * ca.double()).sum()).backward()
+    _close(xo, xr.detach(), TOL, "x_out")
+    _close(ao, ar.detach(), TOL, "adj_out")
+    assert float(torch.diagonal(ao, dim1=1, dim2=2).abs().max()) == 0.0
+    _close(x.grad, x64.grad, 2 * TOL, "gx")
+    _close(a.grad, a64.grad, 2 * TOL, "gadj")
+    for k, v in mod.named_parameters():
+        ref = p64["generator." + k].grad
+        if v.numel() == 1:       # GIN eps: cancellation-heavy scalar (see SCALAR_TOL_TC)
+            assert abs(float(v.grad) - float(ref)) <= SCALAR_TOL_TC * max(abs(float(ref)), 1.0), k
+        else:
+            _close(v.grad, ref, 3 * TOL, "g/" + k)
