@@ -29,9 +29,13 @@ def symmetric_empty(numel, dtype, device, zero=True):
         except Exception:
             pass
         t = symm_mem.empty(numel, dtype=dtype, device=device)
-        hdl = symm_mem.rendezvous(t, group.group_name)
         if zero:
+            # zero BEFORE the rendezvous: the rendezvous is a collective, so once any rank leaves it every rank's buffer is
+            # already clean -- zeroing afterwards could wipe a flag a faster peer has just written into it
             t.zero_()
+            torch.cuda.synchronize(device)
+        hdl = symm_mem.rendezvous(t, group.group_name)
+        dist.barrier()
         ptrs = [int(p) for p in hdl.buffer_ptrs]
         t._xggm_symm_handle = hdl          # keeps the mapping alive
         mc = 0
