@@ -795,7 +795,7 @@ build_blockdiag_kernel(const float* __restrict__ adj, __nv_bfloat16* __restrict_
 
 // Unaligned variant (Params::bd_kn): tile t = output rows [128 t, 128 t + 128), columns = the KW k rows starting at
 // row N * floor(128 t / N) (the first row of the first graph the tile touches).  Dense [128][KW] K-major tile.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 build_blockdiag_u_kernel(const float* __restrict__ adj, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                          long long M, int N, int KW, float alpha0, const float* __restrict__ alpha_dev, float self_w, int trans) {
     pdl_prologue();
@@ -805,8 +805,8 @@ build_blockdiag_u_kernel(const float* __restrict__ adj, __nv_bfloat16* __restric
     __nv_bfloat16* th = hi + (size_t)t * BM * KW;
     __nv_bfloat16* tl = lo ? lo + (size_t)t * BM * KW : nullptr;
     const int vec_per_row = KW / 8;
-    for (int v = threadIdx.x; v < 32 * vec_per_row; v += blockDim.x) {
-        const int r = blockIdx.y * 32 + v / vec_per_row, c0 = (v % vec_per_row) * 8;
+    for (int v = threadIdx.x; v < 16 * vec_per_row; v += blockDim.x) {     // grid.y = 8: 16 rows of the tile per CTA
+        const int r = blockIdx.y * 16 + v / vec_per_row, c0 = (v % vec_per_row) * 8;
         const long long m = (long long)t * BM + r;
         const long long b = m / N;
         const int i = (int)(m - b * N);
@@ -847,30 +847,35 @@ struct WPlaneJobs {
 };
 __global__ void __launch_bounds__(256) weight_planes_kernel(const WPlaneJobs jobs) {
     pdl_prologue();
-    __shared__ float tile[32][33];
+    __shared__ float tile[64][65];
     const WPlaneJob job = jobs.j[blockIdx.z];
-    const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;    // W rows n, columns k
+    const int k0 = blockIdx.x * 64, n0 = blockIdx.y * 64;    // W rows n, columns k; K and P are multiples of 8
     if (k0 >= job.K || n0 >= job.P) return;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-    for (int i = ty; i < 32; i += 8) {
-        const int n = n0 + i, k = k0 + tx;
-        const float v = (n < job.N && k < job.K) ? job.src[(size_t)n * job.K + k] : 0.f;
-        tile[i][tx] = v;
+    // phase 1: a thread takes two consecutive k of one row -> one 4-byte store per plane (128 B per warp and row)
+    for (int v = threadIdx.x; v < 64 * 32; v += blockDim.x) {
+        const int i = v >> 5, n = n0 + i, k = k0 + 2 * (v & 31);
+        float2 w = make_float2(0.f, 0.f);
+        if (n < job.N && k < job.K) w = *reinterpret_cast<const float2*>(job.src + (size_t)n * job.K + k);
+        tile[i][2 * (v & 31)] = w.x;
+        tile[i][2 * (v & 31) + 1] = w.y;
         if (n < job.N && k < job.K) {
-            __nv_bfloat16 h, l;
-            split1(v, h, l);
-            job.hi[(size_t)n * job.K + k] = h;
-            if (job.lo) job.lo[(size_t)n * job.K + k] = l;
+            __nv_bfloat16 h0, l0, h1, l1;
+            split1(w.x, h0, l0);
+            split1(w.y, h1, l1);
+            *reinterpret_cast<__nv_bfloat162*>(job.hi + (size_t)n * job.K + k) = __halves2bfloat162(h0, h1);
+            if (job.lo) *reinterpret_cast<__nv_bfloat162*>(job.lo + (size_t)n * job.K + k) = __halves2bfloat162(l0, l1);
         }
     }
     __syncthreads();
-    for (int i = ty; i < 32; i += 8) {
-        const int k = k0 + i, n = n0 + tx;   // W^T row k, column n (pitch P, zero padded beyond N)
+    // phase 2: W^T row k, two consecutive n (pitch P, zero padded beyond N)
+    for (int v = threadIdx.x; v < 64 * 32; v += blockDim.x) {
+        const int i = v >> 5, k = k0 + i, nl = 2 * (v & 31), n = n0 + nl;
         if (k < job.K && n < job.P) {
-            __nv_bfloat16 h, l;
-            split1(n < job.N ? tile[tx][i] : 0.f, h, l);
-            job.thi[(size_t)k * job.P + n] = h;
-            if (job.tlo) job.tlo[(size_t)k * job.P + n] = l;
+            __nv_bfloat16 h0, l0, h1, l1;
+            split1(n < job.N ? tile[nl][i] : 0.f, h0, l0);
+            split1(n + 1 < job.N ? tile[nl + 1][i] : 0.f, h1, l1);
+            *reinterpret_cast<__nv_bfloat162*>(job.thi + (size_t)k * job.P + n) = __halves2bfloat162(h0, h1);
+            if (job.tlo) *reinterpret_cast<__nv_bfloat162*>(job.tlo + (size_t)k * job.P + n) = __halves2bfloat162(l0, l1);
         }
     }
 }
@@ -1480,7 +1485,7 @@ int build_blockdiag(const float* adj, __nv_bfloat16* hi, __nv_bfloat16* lo, int 
     XGGM_REQUIRE(adj && hi && N >= 1 && N <= tc::BM);
     if (bd_unaligned(N)) {
         const long long M = (long long)B * N;
-        XGGM_LAUNCH((tc::build_blockdiag_u_kernel), dim3(ceil_div(M, tc::BM), 4), 128, 0, st, adj, hi, lo, M, N, BD_KW, alpha0,
+        XGGM_LAUNCH((tc::build_blockdiag_u_kernel), dim3(ceil_div(M, tc::BM), 8), 256, 0, st, adj, hi, lo, M, N, BD_KW, alpha0,
                     alpha_dev, self_w, trans);
         XGGM_LAUNCH_CHECK();
         return XGGM_OK;
@@ -1705,7 +1710,7 @@ int weight_planes_build(const float* const* W, void* const* bufs, const int* N, 
             if (!with_lo) { j.lo = nullptr; j.tlo = nullptr; }
             kmax = max(kmax, j.K); pmax = max(pmax, j.P);
         }
-        XGGM_LAUNCH((tc::weight_planes_kernel), dim3(ceil_div(kmax, 32), ceil_div(pmax, 32), n), 256, 0, st, jobs);
+        XGGM_LAUNCH((tc::weight_planes_kernel), dim3(ceil_div(kmax, 64), ceil_div(pmax, 64), n), 256, 0, st, jobs);
         XGGM_LAUNCH_CHECK();
         done += n;
     }
