@@ -948,7 +948,20 @@ def test_prepared_weight_planes_are_exact_and_follow_the_weights():
         return [x_gen.detach().clone(), nodes.detach().clone(), x.grad.clone(), feat.grad.clone()] + \
                [p_.grad.clone() for p_ in mod.parameters() if p_.grad is not None]
 
+    def run_rel():      # the relation branch exercises the ragged 630-wide encoder_adj weight (pitched W^T planes)
+        XF._drop.site = 950
+        for p_ in mod.parameters():
+            p_.grad = None
+        x = xp.clone().requires_grad_(True)
+        feat = visn.clone().requires_grad_(True)
+        x_gen, loss_sm, nodes, adj_g = mod.relation_step(x, feat, adj_true, 1.0, 100, kl_weight=8.0, randn=randn_rel)
+        (x_gen.sum() + loss_sm).backward()
+        return [x_gen.detach().clone(), adj_g.detach().clone(), x.grad.clone(), feat.grad.clone()] + \
+               [p_.grad.clone() for p_ in mod.parameters() if p_.grad is not None]
+
+    randn_rel = torch.randn(B, N, N, device=dev())
     plain = run()
+    plain_rel = run_rel()
     mats = [p_ for p_ in mod.parameters() if p_.dim() == 2]
     XF.cache_weight_planes(mats)
     l0 = X._lib.kernel_launches()
@@ -957,6 +970,7 @@ def test_prepared_weight_planes_are_exact_and_follow_the_weights():
     cached_again = run()
     l2 = X._lib.kernel_launches()
     assert all(getattr(m_, "_xggm_wp", None) is not None for m_ in mats if m_ is not mod.encoder_adj[0].weight)
+    assert getattr(mod.encoder_adj[0].weight, "_xggm_wp", None) is None      # (not used by the node branch)
     assert l2 - l1 < l1 - l0                      # the second call found every record valid: no build launches
     def same(u, v):
         # outputs and input gradients are deterministic: bit-identical.  Parameter gradients are reduced with
@@ -969,6 +983,8 @@ def test_prepared_weight_planes_are_exact_and_follow_the_weights():
 
     same(plain, cached_first)
     same(plain, cached_again)
+    same(plain_rel, run_rel())
+    assert getattr(mod.encoder_adj[0].weight, "_xggm_wp", None) is not None
     # a visible in-place update invalidates the record; the next call rebuilds and matches the uncached path
     w = mod.generator.gnn_layers[0].linear_prediction[0][0].weight
     with torch.no_grad():
