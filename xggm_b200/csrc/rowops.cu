@@ -93,17 +93,17 @@ __device__ __forceinline__ void flush_columns(const float (&acc)[NV * 4], float*
 // complete_tx) of the NEXT row of up to NT input tensors into this warp's shared-memory stage while
 // the warp computes on the current one, so a warp never sits on a DRAM round trip between rows.
 // E1: bytes per element of tensor 1 (4, or 2 when that tensor is a bf16 storage row; its stage slot keeps H floats).
-template <int NV, int NT, int E1 = 4, int W = ROW_WARPS>
+template <int NV, int NT, int E1 = 4>
 struct RowPrefetch {
     static constexpr int H = NV * 128;
     static constexpr int STAGE = NT * H;                          // floats per stage
     static constexpr int WARP_FLOATS = 2 * STAGE;
-    static constexpr size_t SMEM = sizeof(float) * W * WARP_FLOATS + sizeof(uint64_t) * W * 2;
+    static constexpr size_t SMEM = sizeof(float) * ROW_WARPS * WARP_FLOATS + sizeof(uint64_t) * ROW_WARPS * 2;
     float* buf;
     uint64_t* bar;
     __device__ __forceinline__ void init(float* sm, int warp, int lane) {
         buf = sm + (size_t)warp * WARP_FLOATS;
-        bar = reinterpret_cast<uint64_t*>(sm + (size_t)W * WARP_FLOATS) + warp * 2;
+        bar = reinterpret_cast<uint64_t*>(sm + (size_t)ROW_WARPS * WARP_FLOATS) + warp * 2;
         if (lane == 0) {
             ptx::mbar_init(&bar[0], 1);
             ptx::mbar_init(&bar[1], 1);
@@ -444,122 +444,6 @@ gld_bwd_fast(const float* __restrict__ gout, const float* __restrict__ z, const 
     if (gbias) flush_columns<NV>(az, gbias, sm);
 }
 
-// gld_bwd with TWO warps per row (each owns half of the columns): the register arrays halve (242 -> ~128 registers), so
-// 16 warps per SM are resident instead of 8.  ncu on the one-warp-per-row kernel: issue slots 53 % busy, 0.8 eligible warps
-// per scheduler, DRAM 27 % -- bound by warps to issue from, not by memory.  The two half-row sums of the LayerNorm backward
-// meet through shared memory and one named barrier per row pair (double-buffered by row parity).
-constexpr int GLDH_PAIRS = 8;                      // row pairs (= rows in flight) per CTA; 16 warps
-template <int NVH, bool ZB>
-__global__ void __launch_bounds__(GLDH_PAIRS * 64, 1)
-gld_bwd_half(const float* __restrict__ gout, const float* __restrict__ z, const float* __restrict__ mean,
-             const float* __restrict__ rstd, const float* __restrict__ gamma, const DropSpec drop,
-             float* __restrict__ gz, float* __restrict__ ggamma, float* __restrict__ gbeta,
-             float* __restrict__ gbias, bf16* __restrict__ hi, bf16* __restrict__ lo, int M) {
-    pdl_prologue();
-    constexpr int HH = NVH * 128, H = 2 * HH, W = 2 * GLDH_PAIRS;
-    using PF = RowPrefetch<NVH, 2, ZB ? 2 : 4, W>;
-    extern __shared__ __align__(16) float sm[];
-    float2* xch = reinterpret_cast<float2*>(sm + (PF::SMEM + 15) / 16 * 4);    // [2 parities][PAIRS][2 halves]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int pair = warp >> 1, half = warp & 1;
-    const uint64_t dstream = drop_stream(drop);
-    const float scale = drop.scale;
-    const int rid = blockIdx.x * GLDH_PAIRS + pair, nr = gridDim.x * GLDH_PAIRS;
-    constexpr int ZS = ZB ? 2 : 1;
-    PF pf;
-    pf.init(sm, warp, lane);
-    const size_t coff = (size_t)half * HH;            // first column of this warp's half
-    if (rid < M) {
-        const float* src[2] = {gout + (size_t)rid * H + coff, z + ((size_t)rid * H + coff) / ZS};
-        pf.issue(0, src, lane);
-    }
-    float gam[NVH * 4];
-    load_row<NVH>(gamma + coff, lane, gam);
-    float ag[NVH * 4], ab[NVH * 4], az[NVH * 4];
-#pragma unroll
-    for (int i = 0; i < NVH * 4; ++i) { ag[i] = 0.f; ab[i] = 0.f; az[i] = 0.f; }
-    int it = 0;
-    for (int r = rid; r < M; r += nr, ++it) {
-        const int stage = it & 1;
-        const size_t ro = (size_t)r * H;
-        if (r + nr < M) {
-            const float* src[2] = {gout + (size_t)(r + nr) * H + coff, z + ((size_t)(r + nr) * H + coff) / ZS};
-            pf.issue(stage ^ 1, src, lane);
-        }
-        const float mu = mean[r], rs = rstd[r];
-        pf.wait(stage, (it >> 1) & 1);
-        float gy[NVH * 4], zv[NVH * 4], yh[NVH * 4];
-        pf.read(stage, 0, lane, gy);
-        pf.read(stage, 1, lane, zv);
-        __syncwarp();
-        if (drop.mode == 2 && drop.thresh == XGGM_COIN_THRESH) {
-            uint32_t nib[2 * NVH];
-            coin_row<2 * NVH>(drop, dstream, ro, lane, nib);     // the row's 2*NVH Philox blocks; this warp uses its half
-#pragma unroll
-            for (int i = 0; i < NVH; ++i) {
-                const uint32_t nb = half ? nib[NVH + i] : nib[i];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) gy[4 * i + j] = ((nb >> j) & 1u) ? gy[4 * i + j] * scale : 0.f;
-            }
-        } else if (drop.mode) {
-#pragma unroll
-            for (int i = 0; i < NVH; ++i) {
-                bool m[4];
-                drop_bits4(drop, dstream, ro + coff + 128 * i + 4 * lane, m);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) gy[4 * i + j] = m[j] ? gy[4 * i + j] * scale : 0.f;
-            }
-        }
-        float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-        for (int e = 0; e < NVH * 4; ++e) {
-            float cdf, pdf;
-            normal_cdf_pdf(zv[e], cdf, pdf);
-            yh[e] = (zv[e] * cdf - mu) * rs;
-            zv[e] = cdf + zv[e] * pdf;  // gelu'(z)
-            ag[e] = fmaf(gy[e], yh[e], ag[e]);
-            ab[e] += gy[e];
-            gy[e] *= gam[e];            // d = gy * gamma
-            s1 += gy[e];
-            s2 = fmaf(gy[e], yh[e], s2);
-        }
-        s1 = warp_sum(s1);
-        s2 = warp_sum(s2);
-        float2* slot = xch + ((it & 1) * GLDH_PAIRS + pair) * 2;
-        if (lane == 0) slot[half] = make_float2(s1, s2);
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");       // the pair's two warps
-        const float2 other = slot[half ^ 1];
-        const float c1 = (s1 + other.x) / (float)H, c2 = (s2 + other.y) / (float)H;
-#pragma unroll
-        for (int i = 0; i < NVH * 4; ++i) {
-            gy[i] = rs * (gy[i] - c1 - yh[i] * c2) * zv[i];
-            az[i] += gy[i];
-        }
-        if (gz) store_row<NVH>(gz + ro + coff, lane, gy);
-        if (hi) store_planes<NVH>(hi, lo, ro + coff, lane, gy);
-    }
-    // column sums: every warp holds its half's partial sums over the rows it walked; combine the 8 pairs in smem
-    __syncthreads();
-    float* red = sm;                                   // [PAIRS][H] floats (the prefetch stages are idle now)
-    auto flush = [&](const float (&acc)[NVH * 4], float* __restrict__ dst) {
-#pragma unroll
-        for (int i = 0; i < NVH; ++i)
-            *reinterpret_cast<float4*>(red + pair * H + coff + 128 * i + 4 * lane) =
-                make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
-        __syncthreads();
-        for (int c = threadIdx.x; c < H; c += blockDim.x) {
-            float a = 0.f;
-#pragma unroll
-            for (int w = 0; w < GLDH_PAIRS; ++w) a += red[w * H + c];
-            atomicAdd(&dst[c], a);
-        }
-        __syncthreads();
-    };
-    flush(ag, ggamma);
-    flush(ab, gbeta);
-    if (gbias) flush(az, gbias);
-}
-
 // ================================================================== generic kernels (any H)
 constexpr int GEN_WARPS = 4;
 constexpr int GEN_ROWS = 8;
@@ -866,39 +750,6 @@ int gelu_ln_drop_bwd(const float* gout, const float* z, const float* mean, const
                      const DropSpec& drop, float* gz, float* ggamma, float* gbeta, float* gbias,
                      bf16* hi, bf16* lo, int M, int H, cudaStream_t st, int z_bf16) {
     if (M <= 0) return XGGM_OK;
-    static int half_ok = -1;
-    if (half_ok < 0) {
-        const char* e = getenv("XGGM_GLD_BWD_HALF");
-        half_ok = (e && e[0] == '0') ? 0 : 1;
-    }
-    if (half_ok && H % 256 == 0 && M >= 64 && fast_ok(H, gout, z, gz) && fast_ok(H, gamma, hi, lo) &&
-        (reinterpret_cast<uintptr_t>(drop.keep) & 3) == 0) {
-        // two warps per row, 16 warps per SM (see gld_bwd_half)
-        switch (H / 256) {
-#define XGGM_GLDH_CASE(NVH_)                                                                                                   \
-            case NVH_: {                                                                                                       \
-                using PF = RowPrefetch<NVH_, 2, 4, 2 * GLDH_PAIRS>;                                                            \
-                constexpr size_t pf_bytes = (PF::SMEM + 15) / 16 * 16;                                                         \
-                constexpr size_t red_bytes = sizeof(float) * GLDH_PAIRS * 2 * NVH_ * 128;                                      \
-                constexpr size_t smem = (pf_bytes + 256 > red_bytes ? pf_bytes + 256 : red_bytes);                             \
-                const int grid = max(1, min(ceil_div(M, GLDH_PAIRS), row_sms()));                                              \
-                if (z_bf16) {                                                                                                  \
-                    static bool attr = false;                                                                                  \
-                    if (!attr) { XGGM_CUDA_TRY(cudaFuncSetAttribute(gld_bwd_half<NVH_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; } \
-                    XGGM_LAUNCH((gld_bwd_half<NVH_, true>), grid, GLDH_PAIRS * 64, smem, st, gout, z, mean, rstd, gamma, drop, gz, ggamma, gbeta, gbias, hi, lo, M); \
-                } else {                                                                                                       \
-                    static bool attr = false;                                                                                  \
-                    if (!attr) { XGGM_CUDA_TRY(cudaFuncSetAttribute(gld_bwd_half<NVH_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; } \
-                    XGGM_LAUNCH((gld_bwd_half<NVH_, false>), grid, GLDH_PAIRS * 64, smem, st, gout, z, mean, rstd, gamma, drop, gz, ggamma, gbeta, gbias, hi, lo, M); \
-                }                                                                                                              \
-            } break;
-            XGGM_GLDH_CASE(1) XGGM_GLDH_CASE(2) XGGM_GLDH_CASE(3) XGGM_GLDH_CASE(4)
-#undef XGGM_GLDH_CASE
-            default: return XGGM_ERR_ARG;
-        }
-        XGGM_LAUNCH_CHECK();
-        return XGGM_OK;
-    }
     if (fast_ok(H, gout, z, gz) && fast_ok(H, gamma, hi, lo) && (reinterpret_cast<uintptr_t>(drop.keep) & 3) == 0) {
         XGGM_ROW_DISPATCH(H, {
             constexpr size_t smem = RowPrefetch<NV, 2>::SMEM;   // (>= the ROW_WARPS*H floats flush_columns needs)
