@@ -2,22 +2,25 @@
 """Benchmark of the X-GGM graph-generative block (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--workload block|iteration|visn|eval] [--branch node|relation|mixed] [--precision fp32|bf16]
 
-One "step" = one pass of the hot path over one batch: the GGM node-generation branch the
-shipped VQA-CP v2 recipe always takes (--delta 0, script/vqacpv2.sh:22 of the reference):
-strip_diag(adj_true) -> node_fc(x) (+36-fold broadcast) -> Gaussian feature noise ->
-GCNGenerator(L=2) -> symmetric-KL + score-matching losses -> fusion_fc read-out, forward AND
-backward down to every parameter gradient and the gradients of the LXMERT outputs that feed
-the block, then the gradient all-reduce (N > 1), clip_grad_norm_(5.) and the BertAdam update of the
-block's parameters.  The LXMERT encoder / answer head that surround the block are outside the hot path
-(SURVEY.md section 8); their place is taken by resident inputs and a fixed cotangent on x_gen.
+Default workload (`block`, the headline).  One "step" = one pass of the hot path over one batch: the GGM
+node-generation branch the shipped VQA-CP v2 recipe always takes (--delta 0, script/vqacpv2.sh:22 of the reference):
+strip_diag(adj_true) -> node_fc(x) (+36-fold broadcast) -> Gaussian feature noise -> GCNGenerator(L=2) ->
+symmetric-KL + score-matching losses -> fusion_fc read-out, forward AND backward down to every parameter gradient
+and the gradients of the LXMERT outputs that feed the block, then the gradient exchange (N > 1), clip_grad_norm_(5.)
+and the BertAdam update of the block's parameters.  The LXMERT encoder / answer head that surround the block are
+outside the hot path; their place is taken by resident inputs and a fixed cotangent on x_gen.
 
-Per-GPU batch B=256 (BASELINE configs[1]), N=36, H=768, fp32.  N>1 ranks = data parallel
-(weak scaling): each rank runs its own B=256 shard and the block's gradients are averaged with
-one NCCL all-reduce per step (part of the captured step).
+Per-GPU batch B=256 (BASELINE configs[1]), N=36, H=768, fp32.  N>1 ranks = data parallel (weak scaling): each rank
+runs its own B=256 shard; the gradient averaging, the clip and the update run as one fused sequence over NVLink peer
+memory (xggm_dp_bertadam_step; XGGM_DP_FUSED=0: one NCCL all-reduce + separate clip / update), inside the captured step.
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port of the
-reference path on the host cores instead (rank 0 only).
+Prints ONE JSON line (rank 0) with `roofline`, `cpu_baseline`, `eager_gpu_baseline` (the reference's own eager PyTorch
+path on the same GPU), `e2e`, `clocks`, `gpu_launches`.  `--impl reference` times the reference's CPU path on the host
+cores instead (the unmodified reference modules vendored in oracle/_ref, else the oracle port; rank 0 only).
+Other workloads: `iteration` = the full VQA-CP v2 trainer iteration around a stock-PyTorch LXMERT (BASELINE
+configs[1] / [2]); `visn` = the VisualFeatEncoder leg; `eval` = BASELINE configs[4].
 """
 import argparse
 import json
