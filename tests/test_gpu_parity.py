@@ -420,6 +420,60 @@ def test_full_size_properties():
             assert torch.isfinite(p_.grad).all()
 
 
+@pytest.mark.parametrize("B,N", [(4096, 36), (2048, 64), (1024, 100)])
+def test_max_size_properties(B, N):
+    """BASELINE configs[3] corner sizes (B = 4096 at obj36, 2048 x 64, 1024 x 100 nodes; H = 768: up to 147,456 node rows,
+    1,152 row tiles): what is pinned to the fp64 oracle at B <= 256 must hold unchanged at the largest batch.
+
+      * per-graph independence, forward AND backward: graphs taken from the first, a middle and the LAST tile of the big batch
+        give the same outputs and input gradients as the same graphs evaluated alone (small batches are oracle-pinned),
+        and graphs that receive no cotangent receive exactly zero input gradient;
+      * bit-exact structure of the regenerated adjacency (zero diagonal, sigmoid range);
+      * a full training step (dropout, losses, every parameter gradient) stays finite."""
+    import xggm_b200 as X
+    torch.manual_seed(4242)
+    H = 768
+    mod = X.XGGMHeads(H, "GCN", 2, N).to(dev())
+    g = torch.Generator().manual_seed(77)
+    visn = torch.randn(B, N, H, generator=g).to(dev())
+    xp = torch.randn(B, H, generator=g).to(dev())
+    c = torch.rand(B, N, N, generator=g) * 1.2 - 0.2
+    c = c + c.transpose(1, 2)
+    adj_true = (c / c.amax(dim=(1, 2), keepdim=True)).to(dev())
+    adj_in = X.glue.strip_diag(adj_true)
+    mod.eval()
+    picks = [0, 1, B // 2 + 1, B - 2, B - 1]          # first tile, a middle tile, the ragged last tile
+    xa = visn.clone().requires_grad_(True)
+    full, adj_full = mod.generator(xa, adj_in)
+    cot = torch.zeros_like(full)
+    cs = torch.randn(len(picks), N, H, generator=g).to(dev())
+    cot[picks] = cs
+    gfull, = torch.autograd.grad(full, xa, cot)
+    assert float(torch.diagonal(adj_full.detach(), dim1=1, dim2=2).abs().max()) == 0.0
+    off = adj_full.detach()[:, ~torch.eye(N, dtype=torch.bool, device=dev())]
+    assert float(off.min()) > 0.0 and float(off.max()) <= 0.7311
+    xs = visn[picks].clone().requires_grad_(True)
+    part, adj_part = mod.generator(xs, adj_in[picks])
+    gpart, = torch.autograd.grad(part, xs, cs)
+    assert rel_l2(full[picks].detach().cpu(), part.detach().cpu()) < 2e-5 and rel_max(full[picks].detach().cpu(), part.detach().cpu()) < 2e-4
+    assert rel_l2(adj_full[picks].detach().cpu(), adj_part.detach().cpu()) < 2e-5
+    assert rel_l2(gfull[picks].cpu(), gpart.cpu()) < 5e-5 and rel_max(gfull[picks].cpu(), gpart.cpu()) < 5e-4
+    rest = torch.ones(B, dtype=torch.bool)
+    rest[picks] = False
+    assert float(gfull[rest.to(dev())].abs().max()) == 0.0          # no cotangent -> exactly no gradient
+    del full, adj_full, gfull, cot, xa
+    # one full training step of the node branch at this size
+    mod.train()
+    x = xp.clone().requires_grad_(True)
+    feat = visn.clone().requires_grad_(True)
+    x_gen, loss_sm, nodes, adj_g = mod.node_step(x, feat, adj_true, 1.0, 2274)
+    (x_gen.sum() + loss_sm).backward()
+    assert torch.isfinite(loss_sm) and torch.isfinite(x_gen).all() and torch.isfinite(feat.grad).all() and torch.isfinite(x.grad).all()
+    for p_ in mod.parameters():
+        if p_.grad is not None:
+            assert torch.isfinite(p_.grad).all()
+
+
 @pytest.mark.parametrize("branch", ["node", "relation"])
 def test_full_size_tensor_core_engine_matches_exact_engine(branch):
     """BASELINE size (B=256, N=36, H=768, train mode): the tensor-core engine -- CTA-pair kernel, grouped launches,
