@@ -420,8 +420,9 @@ def test_full_size_properties():
             assert torch.isfinite(p_.grad).all()
 
 
-@pytest.mark.parametrize("B,N", [(4096, 36), (2048, 64), (1024, 100)])
-def test_max_size_properties(B, N):
+@pytest.mark.parametrize("B,N,gnn,precision", [(4096, 36, "GCN", "fp32"), (2048, 64, "GCN", "fp32"), (1024, 100, "GCN", "fp32"),
+                                               (4096, 36, "GCN", "bf16"), (4096, 36, "GIN", "fp32"), (1024, 100, "GIN", "bf16")])
+def test_max_size_properties(B, N, gnn, precision):
     """BASELINE configs[3] corner sizes (B = 4096 at obj36, 2048 x 64, 1024 x 100 nodes; H = 768: up to 147,456 node rows,
     1,152 row tiles): what is pinned to the fp64 oracle at B <= 256 must hold unchanged at the largest batch.
 
@@ -431,9 +432,17 @@ def test_max_size_properties(B, N):
       * bit-exact structure of the regenerated adjacency (zero diagonal, sigmoid range);
       * a full training step (dropout, losses, every parameter gradient) stays finite."""
     import xggm_b200 as X
+    X.set_precision(precision)
+    try:
+        _max_size_body(X, B, N, gnn, 1.0 if precision == "fp32" else 100.0)   # bf16 engine: 2e-2 budget (a rounding flip of one
+    finally:                                                                # stored bf16 value is 4e-3 of that element)
+        X.set_precision("fp32")
+
+
+def _max_size_body(X, B, N, gnn, slack):
     torch.manual_seed(4242)
     H = 768
-    mod = X.XGGMHeads(H, "GCN", 2, N).to(dev())
+    mod = X.XGGMHeads(H, gnn, 2, N).to(dev())
     g = torch.Generator().manual_seed(77)
     visn = torch.randn(B, N, H, generator=g).to(dev())
     xp = torch.randn(B, H, generator=g).to(dev())
@@ -455,9 +464,9 @@ def test_max_size_properties(B, N):
     xs = visn[picks].clone().requires_grad_(True)
     part, adj_part = mod.generator(xs, adj_in[picks])
     gpart, = torch.autograd.grad(part, xs, cs)
-    assert rel_l2(full[picks].detach().cpu(), part.detach().cpu()) < 2e-5 and rel_max(full[picks].detach().cpu(), part.detach().cpu()) < 2e-4
-    assert rel_l2(adj_full[picks].detach().cpu(), adj_part.detach().cpu()) < 2e-5
-    assert rel_l2(gfull[picks].cpu(), gpart.cpu()) < 5e-5 and rel_max(gfull[picks].cpu(), gpart.cpu()) < 5e-4
+    assert rel_l2(full[picks].detach().cpu(), part.detach().cpu()) < 2e-5 * slack and rel_max(full[picks].detach().cpu(), part.detach().cpu()) < 2e-4 * slack
+    assert rel_l2(adj_full[picks].detach().cpu(), adj_part.detach().cpu()) < 2e-5 * slack
+    assert rel_l2(gfull[picks].cpu(), gpart.cpu()) < 5e-5 * slack and rel_max(gfull[picks].cpu(), gpart.cpu()) < 5e-4 * slack
     rest = torch.ones(B, dtype=torch.bool)
     rest[picks] = False
     assert float(gfull[rest.to(dev())].abs().max()) == 0.0          # no cotangent -> exactly no gradient
